@@ -1,0 +1,360 @@
+// pgb_solve.cu -- the m x m penalised solve of one PIRLS iteration, fp64, on the device.
+//
+// Replaces pygam.py:783-805 (dense QR of W.B, SVD of [R; E], back-projection B, coef = B.Wz)
+// and the edof / cov part of _estimate_model_statistics (pygam.py:1033-1045) by the
+// algebraically equal normal-equation form
+//     beta = (G + E^T E)^-1 r,  edof = tr(G (G + E^T E)^-1),  cov = A^-1 G A^-1,
+// solved in an orthogonal basis Q = [Nhat | Z] whose first p columns span the analytic null
+// space of the design (one vector per partition-of-unity term block).  In
+// that basis the Nhat rows/columns of Q^T G Q and Nhat^T r are zero in exact arithmetic; the
+// kernel sets them to exact zero, which removes the rounding noise that a plain Cholesky of
+// G + E^T E amplifies by 1/sqrt(EPS) and that otherwise changes iteration counts.
+//
+// One CTA per system.  Small systems (two m x m matrices fit in shared memory) run entirely
+// out of shared memory -- this is the grid-search path, one candidate per CTA; larger ones
+// work in the caller's workspace (L2-resident).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "pgb_internal.h"
+
+static const int kSolveThreads = 512;
+static const size_t kSolveSmemMax = 227 * 1024;
+
+namespace {
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();  // red may still be read from a previous call
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < nw; ++w) s += red[w];
+  return s;
+}
+
+// A <- H A H, H = I - tau v v^T (A symmetric, full storage)
+__device__ void sym_reflect(double* A, int m, const double* v, double tau, double* w, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = warp; i < m; i += nw) {
+    double s = 0.0;
+    const double* row = A + (size_t)i * m;
+    for (int j = lane; j < m; j += 32) s = fma(row[j], v[j], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) w[i] = s;
+  }
+  __syncthreads();
+  double part = 0.0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) part = fma(v[i], w[i], part);
+  const double alpha = block_sum(part, red);
+  const double c = 0.5 * tau * tau * alpha;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) w[i] = tau * w[i] - c * v[i];
+  __syncthreads();
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e / m, j = e - i * m;
+    A[e] -= v[i] * w[j] + w[i] * v[j];
+  }
+  __syncthreads();
+}
+
+// x <- H x
+__device__ void vec_reflect(double* x, int m, const double* v, double tau, double* red) {
+  double part = 0.0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) part = fma(v[i], x[i], part);
+  const double s = tau * block_sum(part, red);
+  for (int i = threadIdx.x; i < m; i += blockDim.x) x[i] -= s * v[i];
+  __syncthreads();
+}
+
+// in-place lower Cholesky A = L L^T (upper part left untouched); returns 0 or 1 (not PD) in *flag
+__device__ void cholesky_lower(double* A, int m, double* col, int* flag) {
+  for (int k = 0; k < m; ++k) {
+    const double akk = A[(size_t)k * m + k];
+    if (!(akk > 0.0) || !isfinite(akk)) {
+      if (threadIdx.x == 0) *flag = 1;
+      __syncthreads();
+      return;
+    }
+    const double d = sqrt(akk);
+    const double inv = 1.0 / d;
+    __syncthreads();
+    for (int i = k + threadIdx.x; i < m; i += blockDim.x) {
+      const double v = (i == k) ? d : A[(size_t)i * m + k] * inv;
+      A[(size_t)i * m + k] = v;
+      col[i] = v;
+    }
+    __syncthreads();
+    const int rem = m - k - 1;
+    // trailing update of the lower triangle: (i, j), k < j <= i
+    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
+      const int ii = e / rem, jj = e - ii * rem;
+      if (jj <= ii) {
+        const int i = k + 1 + ii, j = k + 1 + jj;
+        A[(size_t)i * m + j] = fma(-col[i], col[j], A[(size_t)i * m + j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// x <- L^-1 x (forward) or L^-T x (backward), single right-hand side
+__device__ void tri_solve_vec(const double* L, int m, double* x, bool transpose) {
+  if (!transpose) {
+    for (int k = 0; k < m; ++k) {
+      if (threadIdx.x == 0) x[k] /= L[(size_t)k * m + k];
+      __syncthreads();
+      const double xk = x[k];
+      for (int i = k + 1 + threadIdx.x; i < m; i += blockDim.x) x[i] = fma(-L[(size_t)i * m + k], xk, x[i]);
+      __syncthreads();
+    }
+  } else {
+    for (int k = m - 1; k >= 0; --k) {
+      if (threadIdx.x == 0) x[k] /= L[(size_t)k * m + k];
+      __syncthreads();
+      const double xk = x[k];
+      for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] = fma(-L[(size_t)k * m + i], xk, x[i]);
+      __syncthreads();
+    }
+  }
+}
+
+// B <- L^-1 B (transpose = false) or L^-T B (true); one thread per column of B
+__device__ void tri_solve_cols(const double* L, int m, double* B, bool transpose) {
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    if (!transpose) {
+      for (int i = 0; i < m; ++i) {
+        double s = B[(size_t)i * m + j];
+        const double* Li = L + (size_t)i * m;
+        for (int k = 0; k < i; ++k) s = fma(-Li[k], B[(size_t)k * m + j], s);
+        B[(size_t)i * m + j] = s / Li[i];
+      }
+    } else {
+      for (int i = m - 1; i >= 0; --i) {
+        double s = B[(size_t)i * m + j];
+        for (int k = i + 1; k < m; ++k) s = fma(-L[(size_t)k * m + i], B[(size_t)k * m + j], s);
+        B[(size_t)i * m + j] = s / L[(size_t)i * m + i];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ void transpose_inplace(double* B, int m) {
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e / m, j = e - i * m;
+    if (j > i) {
+      const double a = B[e], b = B[(size_t)j * m + i];
+      B[e] = b;
+      B[(size_t)j * m + i] = a;
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace
+
+#define PGB_SOLVE_WANT_EDOF PGB_SOLVE_EDOF
+#define PGB_SOLVE_WANT_COV PGB_SOLVE_COV
+
+__global__ void __launch_bounds__(kSolveThreads)
+solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__ r_all, int share_gram,
+             const double* __restrict__ EtE_all, const double* __restrict__ hv,
+             const double* __restrict__ tau, int p, const double* __restrict__ beta_prev_all,
+             int share_prev, double* __restrict__ out_all, double* __restrict__ cov_all,
+             double* __restrict__ ws_all, int flags, int use_smem) {
+  extern __shared__ __align__(16) double sm[];
+  const int sys = blockIdx.x;
+  const size_t mm = (size_t)m * m;
+  const double* G = G_all + (share_gram ? 0 : (size_t)sys * mm);
+  const double* r = r_all + (share_gram ? 0 : (size_t)sys * m);
+  const double* EtE = EtE_all + (size_t)sys * mm;
+  const double* beta_prev = beta_prev_all ? beta_prev_all + (share_prev ? 0 : (size_t)sys * m) : nullptr;
+  double* out = out_all + (size_t)sys * (m + PGB_SOLVE_OUT_EXTRA);
+  // small vectors always live in shared memory
+  double* v = sm;          // current reflector
+  double* w = v + m;       // scratch
+  double* x = w + m;       // right-hand side / solution
+  double* col = x + m;     // Cholesky column
+  double* red = col + m;   // 32 doubles
+  int* flag = reinterpret_cast<int*>(red + 32);
+  double* A = use_smem ? (red + 34) : (ws_all + (size_t)sys * 2 * mm);
+  double* B = A + mm;
+  if (threadIdx.x == 0) *flag = 0;
+  __syncthreads();
+
+  // ---- B = Q^T G Q with the null block zeroed; A = Q^T EtE Q + B ----
+  int bad = 0;
+  for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) {
+    const double g = G[e], pe = EtE[e];
+    if (!isfinite(g) || !isfinite(pe)) bad = 1;
+    B[e] = g;
+    A[e] = pe;
+  }
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    x[i] = r[i];
+    if (!isfinite(x[i])) bad = 1;
+  }
+  if (bad) *flag = 2;
+  __syncthreads();
+  if (*flag == 0) {
+    for (int q = 0; q < p; ++q) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = hv[(size_t)q * m + i];
+      __syncthreads();
+      const double t = tau[q];
+      sym_reflect(B, m, v, t, w, red);
+      sym_reflect(A, m, v, t, w, red);
+      vec_reflect(x, m, v, t, red);
+    }
+    for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) {
+      const int i = e / m, j = e - i * m;
+      double g = B[e];
+      if (i < p || j < p) { g = 0.0; B[e] = 0.0; }
+      A[e] += g;
+    }
+    for (int i = threadIdx.x; i < p; i += blockDim.x) x[i] = 0.0;
+    __syncthreads();
+    cholesky_lower(A, m, col, flag);
+  }
+  __syncthreads();
+  const int info = *flag;
+  if (info != 0) {
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = threadIdx.x; i < m + PGB_SOLVE_OUT_EXTRA; i += blockDim.x) out[i] = nanv;
+    __syncthreads();
+    if (threadIdx.x == 0) out[m + 2] = (double)info;
+    return;
+  }
+  // ---- beta = Q L^-T L^-1 x ----
+  double ld_part = 0.0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) ld_part += log(A[(size_t)i * m + i]);
+  const double logdet = 2.0 * block_sum(ld_part, red);
+  tri_solve_vec(A, m, x, false);
+  tri_solve_vec(A, m, x, true);
+  for (int q = p - 1; q >= 0; --q) {
+    for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = hv[(size_t)q * m + i];
+    __syncthreads();
+    vec_reflect(x, m, v, tau[q], red);
+  }
+  double n2 = 0.0, d2 = 0.0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const double b = x[i];
+    out[i] = b;
+    n2 = fma(b, b, n2);
+    if (beta_prev) { const double d = beta_prev[i] - b; d2 = fma(d, d, d2); }
+  }
+  n2 = block_sum(n2, red);
+  d2 = block_sum(d2, red);
+  double edof = __longlong_as_double(0x7ff8000000000000LL);
+  if (flags & (PGB_SOLVE_WANT_EDOF | PGB_SOLVE_WANT_COV)) {
+    // Z = L^-1 Gt L^-T (symmetric); edof = tr(Z)
+    tri_solve_cols(A, m, B, false);
+    transpose_inplace(B, m);
+    tri_solve_cols(A, m, B, false);
+    double tr = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) tr += B[(size_t)i * m + i];
+    edof = block_sum(tr, red);
+    if ((flags & PGB_SOLVE_WANT_COV) && cov_all) {
+      // cov = Q L^-T Z L^-1 Q^T
+      tri_solve_cols(A, m, B, true);
+      transpose_inplace(B, m);
+      tri_solve_cols(A, m, B, true);
+      for (int q = p - 1; q >= 0; --q) {
+        for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = hv[(size_t)q * m + i];
+        __syncthreads();
+        sym_reflect(B, m, v, tau[q], w, red);
+      }
+      double* cov = cov_all + (size_t)sys * mm;
+      for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) cov[e] = B[e];
+    }
+  }
+  if (threadIdx.x == 0) {
+    out[m + 0] = edof;
+    out[m + 1] = beta_prev ? sqrt(d2) / sqrt(n2) : __longlong_as_double(0x7ff8000000000000LL);
+    out[m + 2] = 0.0;
+    out[m + 3] = logdet;
+    out[m + 4] = sqrt(n2);
+    out[m + 5] = 0.0;
+    out[m + 6] = 0.0;
+    out[m + 7] = 0.0;
+  }
+}
+
+static size_t solve_vec_smem(int m) { return ((size_t)4 * m + 34) * 8; }
+static bool solve_fits_smem(int m) { return solve_vec_smem(m) + (size_t)2 * m * m * 8 <= kSolveSmemMax; }
+
+extern "C" int64_t pgb_solve_ws_bytes(int32_t m, int32_t nb) {
+  if (solve_fits_smem(m)) return 256;
+  return (int64_t)nb * 2 * m * m * 8 + 256;
+}
+
+extern "C" int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r, int32_t share_gram,
+                         const double* EtE, const double* hv, const double* tau, int32_t p,
+                         const double* beta_prev, int32_t share_prev, int32_t flags, double* out,
+                         double* cov_out, void* ws, int64_t ws_bytes, void* stream) {
+  if (m < 1 || nb < 1 || !G || !r || !EtE || !out || p < 0 || p > m || (p > 0 && (!hv || !tau))) {
+    pgb_set_error("pgb_solve: bad arguments");
+    return PGB_EINVAL;
+  }
+  const bool in_smem = solve_fits_smem(m);
+  if (!in_smem && (!ws || ws_bytes < pgb_solve_ws_bytes(m, nb))) {
+    pgb_set_error("pgb_solve: workspace too small");
+    return PGB_EINVAL;
+  }
+  size_t smem = solve_vec_smem(m) + (in_smem ? (size_t)2 * m * m * 8 : 0);
+  if (smem > kSolveSmemMax) { pgb_set_error("pgb_solve: m=%d too large", m); return PGB_EUNSUPPORTED; }
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    PGB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax));
+    attr_set = true;
+  }
+  solve_kernel<<<nb, kSolveThreads, smem, (cudaStream_t)stream>>>(m, G, r, share_gram, EtE, hv, tau, p, beta_prev,
+                                                                  share_prev, out, cov_out, (double*)ws, flags,
+                                                                  in_smem ? 1 : 0);
+  pgb_count_launch(1);
+  PGB_CUDA(cudaGetLastError());
+  return PGB_OK;
+}
+
+// Cholesky test of S + P (+ C): GAM._cholesky (pygam.py:499-537) raises NotPositiveDefiniteError
+__global__ void __launch_bounds__(kSolveThreads)
+chol_check_kernel(int m, const double* __restrict__ Ain, int* __restrict__ info, double* __restrict__ ws,
+                  int use_smem) {
+  extern __shared__ __align__(16) double sm[];
+  double* col = sm;
+  int* flag = reinterpret_cast<int*>(col + m);
+  double* A = use_smem ? (col + m + 2) : ws;
+  if (threadIdx.x == 0) *flag = 0;
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) A[e] = Ain[e];
+  __syncthreads();
+  cholesky_lower(A, m, col, flag);
+  __syncthreads();
+  if (threadIdx.x == 0) *info = *flag;
+}
+
+extern "C" int64_t pgb_chol_ws_bytes(int32_t m) { return (int64_t)m * m * 8 + 256; }
+
+extern "C" int pgb_chol_check(int32_t m, const double* A, int32_t* info_out, void* ws, int64_t ws_bytes,
+                              void* stream) {
+  if (m < 1 || !A || !info_out) { pgb_set_error("pgb_chol_check: bad arguments"); return PGB_EINVAL; }
+  const size_t vec = ((size_t)m + 2) * 8;
+  const bool in_smem = vec + (size_t)m * m * 8 <= kSolveSmemMax;
+  if (!in_smem && (!ws || ws_bytes < pgb_chol_ws_bytes(m))) {
+    pgb_set_error("pgb_chol_check: workspace too small");
+    return PGB_EINVAL;
+  }
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    PGB_CUDA(cudaFuncSetAttribute(chol_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax));
+    attr_set = true;
+  }
+  chol_check_kernel<<<1, kSolveThreads, vec + (in_smem ? (size_t)m * m * 8 : 0), (cudaStream_t)stream>>>(
+      m, A, info_out, (double*)ws, in_smem ? 1 : 0);
+  pgb_count_launch(1);
+  PGB_CUDA(cudaGetLastError());
+  return PGB_OK;
+}

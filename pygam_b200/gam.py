@@ -1,0 +1,866 @@
+"""GAM model API on the B200 PIRLS engine.
+
+Public surface mirrors ``/root/reference/pygam/pygam.py``: ``GAM`` (91-2368) and the family
+front-ends ``LinearGAM`` (2371-2506), ``LogisticGAM`` (2509-2682), ``PoissonGAM`` (2685-3046),
+``GammaGAM`` (3049-3165), ``InvGaussGAM`` (3168-3284), ``ExpectileGAM`` (3287-3551) with
+``fit / predict / predict_mu / gridsearch``, fitted attributes ``coef_``, ``statistics_``,
+``logs_`` and the reference's exceptions.  The solver behind them (``_pirls``, pygam.py:715-822)
+is re-designed: a fused on-the-fly-basis Gram pass on the GPU, an all-reduce over row shards and
+a null-space-aware m x m solve; nothing n-sized is computed on the host.
+"""
+
+import copy
+import warnings
+from collections import OrderedDict
+
+import numpy as np
+import scipy.linalg
+import scipy.stats
+import torch
+
+from . import _lib
+from .engine import DeviceData, all_reduce_, column_stats, count_levels, descriptor_key, get_backend
+from .terms import FactorTerm, Intercept, SplineTerm, Term, TermList
+
+EPS = np.finfo(np.float64).eps  # pygam/utils.py:16
+
+
+class NotPositiveDefiniteError(ValueError):
+    """pygam/utils.py:22-23"""
+
+
+class OptimizationError(ValueError):
+    """pygam/utils.py:26-27"""
+
+
+# host-side stand-ins for the reference's Distribution / Link objects (only built-ins have
+# CUDA implementations; custom Python objects raise NotImplementedError)
+class Distribution:
+    def __init__(self, name, scale=None, levels=1):
+        self.name = name
+        self._known_scale = name in ("binomial", "poisson") or scale is not None
+        self.scale = 1.0 if name in ("binomial", "poisson") else scale
+        self.levels = 1 if levels is None else levels
+
+    def __repr__(self):
+        return f"{self.name}(scale={self.scale})"
+
+
+class Link:
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return self.name
+
+
+DISTRIBUTIONS = ("normal", "poisson", "binomial", "gamma", "inv_gauss")
+LINKS = ("identity", "log", "logit", "inverse", "inv_squared")
+CALLBACKS = ("deviance", "diffs", "accuracy", "coef")
+_DEVICE_KEYS = ("_engine", "_engine_key", "_gram_cache", "_dev_memo")
+PLURAL = ["feature", "dtype", "lam", "n_splines", "spline_order", "constraints", "penalties", "basis",
+          "edge_knots_"]
+
+
+def _flatten(v):
+    out = []
+    for x in v:
+        if isinstance(x, (list, tuple, np.ndarray)):
+            out.extend(_flatten(x))
+        else:
+            out.append(x)
+    return out
+
+
+def _combine(*grids):
+    """cartesian product in the order of utils.combine (utils.py:792-816)"""
+    out = [[]]
+    for g in grids:
+        out = [prev + [v] for prev in out for v in g]
+    return out
+
+
+class GAM:
+    def __init__(self, terms="auto", max_iter=100, tol=1e-4, distribution="normal", link="identity",
+                 callbacks=("deviance", "diffs"), fit_intercept=True, verbose=False, **kwargs):
+        self.max_iter = max_iter
+        self.tol = tol
+        self.distribution = distribution
+        self.link = link
+        self.callbacks = list(callbacks)
+        self.verbose = verbose
+        self.terms = TermList(terms) if isinstance(terms, Term) else terms
+        self.fit_intercept = fit_intercept
+        for k, v in kwargs.items():
+            if k not in PLURAL:
+                raise TypeError(f"__init__() got an unexpected keyword argument {k}")
+            setattr(self, k, v)
+        self._pending_plural = {k: v for k, v in kwargs.items()}
+        # pygam.py:187-189
+        self._constraint_lam = 1e9
+        self._constraint_l2 = 1e-3
+        self._constraint_l2_max = 1e-1
+        self._expectile = None
+        self._engine = None
+        self._engine_key = None
+        self._gram_cache = None
+        self._dev_memo = None
+        self._validate_params()
+
+    # ---- parameters ----
+    _param_names = ("max_iter", "tol", "callbacks", "fit_intercept", "verbose", "terms")
+
+    def get_params(self, deep=False):
+        names = list(self._param_names)
+        if type(self) is GAM:
+            names += ["distribution", "link"]
+        out = {k: getattr(self, k) for k in names}
+        for extra in ("scale", "expectile"):
+            if hasattr(self, extra):
+                out[extra] = getattr(self, extra)
+        if deep:
+            for k in ("coef_", "statistics_", "logs_"):
+                if hasattr(self, k):
+                    out[k] = getattr(self, k)
+        return out
+
+    def set_params(self, deep=False, force=False, **parameters):
+        for k, v in parameters.items():
+            if k == "lam" or (k in PLURAL and isinstance(self.terms, TermList) and k != "lam"):
+                self._set_plural(k, v)
+            elif k in self.get_params(deep=deep) or force or k in PLURAL:
+                setattr(self, k, v)
+            elif self.verbose:
+                warnings.warn(f"parameter {k} not found")
+        return self
+
+    def _set_plural(self, name, value):
+        if isinstance(self.terms, TermList):
+            self.terms._set_plural(name, value)
+        else:
+            self._pending_plural[name] = value
+            setattr(self, name, value)
+
+    @property
+    def lam(self):
+        if isinstance(self.terms, TermList):
+            return self.terms.lam
+        return self._pending_plural.get("lam", 0.6)
+
+    @lam.setter
+    def lam(self, value):
+        if isinstance(self.__dict__.get("terms"), TermList):
+            self.terms.lam = value
+        else:
+            self.__dict__.setdefault("_pending_plural", {})["lam"] = value
+
+    @property
+    def _is_fitted(self):
+        return hasattr(self, "coef_")
+
+    def _validate_params(self):
+        """pygam.py:225-284"""
+        if not (isinstance(self.fit_intercept, bool)):
+            raise ValueError(f"fit_intercept must be type bool, but found {self.fit_intercept.__class__}")
+        if not (isinstance(self.terms, (TermList, Term, type(None))) or self.terms == "auto"):
+            raise ValueError(f"terms must be a TermList, but found terms = {self.terms}")
+        if not (isinstance(self.max_iter, (int, np.integer)) and self.max_iter >= 1):
+            raise ValueError(f"max_iter must be int >= 1, but found max_iter = {self.max_iter}")
+        if not (np.isfinite(self.tol) and self.tol > 0):
+            raise ValueError(f"tol must be float > 0, but found tol = {self.tol}")
+        if isinstance(self.distribution, str):
+            if self.distribution not in DISTRIBUTIONS:
+                raise ValueError(f"unsupported distribution {self.distribution}")
+            self.distribution = Distribution(self.distribution, scale=getattr(self, "scale", None),
+                                             levels=getattr(self, "levels", 1))
+        elif not isinstance(self.distribution, Distribution):
+            raise NotImplementedError("custom Distribution objects have no CUDA implementation")
+        if isinstance(self.link, str):
+            if self.link not in LINKS:
+                raise ValueError(f"unsupported link {self.link}")
+            self.link = Link(self.link)
+        elif not isinstance(self.link, Link):
+            raise NotImplementedError("custom Link objects have no CUDA implementation")
+        for c in self.callbacks:
+            if not (isinstance(c, str) and c in CALLBACKS):
+                raise NotImplementedError(
+                    "only the built-in callbacks 'deviance', 'diffs', 'accuracy', 'coef' are supported: "
+                    "arbitrary CallBack objects receive n-sized y/mu arrays (pygam.py:780), which this "
+                    "engine never materialises on the host")
+
+    def _validate_data_dep_params(self, data, col_minmax):
+        """pygam.py:286-331: default terms, the intercept, plural kwargs, term compilation"""
+        F = data.n_features
+        if isinstance(self.terms, str) and self.terms == "auto":
+            self.terms = TermList(*[SplineTerm(feat, verbose=self.verbose) for feat in range(F)])
+        elif self.terms is None:
+            self.terms = TermList()
+        else:
+            self.terms = TermList(self.terms, verbose=self.verbose)
+        if self.fit_intercept:
+            self.terms = self.terms + Intercept()
+        if len(self.terms) == 0:
+            raise ValueError("At least 1 term must be specified")
+        for k, v in list(self._pending_plural.items()):
+            self.terms._set_plural(k, v)
+            if k in self.__dict__:
+                del self.__dict__[k]
+        self._pending_plural = {}
+        n_levels = {}
+        for t in self.terms:
+            if isinstance(t, FactorTerm):
+                lo, hi = col_minmax[t.feature]
+                n_levels[t.feature] = count_levels(data, t.feature, lo, hi)
+        self.terms.compile(_ShapeOnly(data.n, F), col_minmax=col_minmax, n_levels=n_levels)
+        feats = self.terms.features_used()
+        if feats and max(feats) >= F:
+            raise ValueError(f"terms require feature {max(feats)}, but X has only {F} dimensions")
+
+    # ---- data ingestion ----
+    def _prepare_data(self, X, y=None, weights=None, fitting=True):
+        """host arrays -> DeviceData, with the reference's input checks (utils.py:118-355)"""
+        if isinstance(X, DeviceData):
+            data = X
+            if y is not None or weights is not None:
+                data = DeviceData(X.Xt, y if y is not None else X.y, weights if weights is not None else X.w)
+        else:
+            Xh = np.asarray(X)
+            if Xh.dtype.kind not in "fiub":
+                try:
+                    Xh = Xh.astype("float")
+                except ValueError as e:
+                    raise ValueError("X data must be type int or float, but found type: " + str(Xh.dtype)) from e
+            if Xh.ndim == 1:
+                Xh = Xh[:, None]
+            if Xh.ndim != 2:
+                raise ValueError(f"X data must have 2 dimensions, but found {Xh.ndim}")
+            yh = None
+            if y is not None:
+                yh = np.asarray(y)
+                if yh.dtype.kind not in "fiub":
+                    raise ValueError("y data must be type int or float, but found type: " + str(yh.dtype))
+                yh = yh.astype(np.float64).ravel()
+                if len(yh) != Xh.shape[0]:
+                    raise ValueError(f"Inconsistent input and output data shapes. found X: {Xh.shape} "
+                                     f"and y: {yh.shape}")
+            wh = None
+            if weights is not None:
+                wh = np.array(weights).astype("f").ravel()  # float32 cast, pygam.py:889
+                if not np.isfinite(wh).all():
+                    raise ValueError("sample weights data must not contain Inf nor NaN")
+                if len(wh) != Xh.shape[0]:
+                    raise ValueError(f"Inconsistent input data shapes. found {Xh.shape[0]} and {len(wh)}")
+            data = DeviceData.from_host(Xh, yh, wh)
+        if data.n < 1:
+            raise ValueError("X data should have at least 1 samples")
+        if fitting and data.y is not None:
+            self._check_y(data.y)
+        return data
+
+    def _check_y(self, y):
+        """utils.check_y (utils.py:204-248): finite and inside the link's domain"""
+        if not bool(torch.isfinite(y).all()):
+            raise ValueError("y data must not contain Inf nor NaN")
+        lk, levels = self.link.name, float(self.distribution.levels)
+        bad = False
+        if lk == "logit":
+            bad = bool(((y < 0) | (y > levels)).any())
+        elif lk == "log":
+            bad = bool((y < 0).any())
+        if bad:
+            raise ValueError(f"y data is not in domain of {lk} link function. "
+                             f"Expected domain: {self._link_domain()}, but found "
+                             f"{[float(y.min()), float(y.max())]}")
+
+    def _link_domain(self):
+        return {"logit": [0.0, float(self.distribution.levels)], "log": [0.0, np.inf]}.get(
+            self.link.name, [-np.inf, np.inf])
+
+    # ---- engine ----
+    def _get_engine(self, data):
+        desc_key = (descriptor_key(self.terms, data.n_features), self.distribution.name, self.link.name,
+                    float(self.distribution.levels), self._expectile, data.n_features, str(data.device))
+        if self._engine is None or self._engine_key != desc_key:
+            self._engine = get_backend().make_engine(self.terms, self.distribution.name, self.link.name,
+                                                     self.distribution.levels, self._expectile,
+                                                     data.n_features, data.device)
+            self._engine_key = desc_key
+            self._gram_cache = None
+            self._dev_memo = None
+        return self._engine
+
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in _DEVICE_KEYS:
+                new.__dict__[k] = v  # device state is shared, never copied
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        for k in _DEVICE_KEYS:
+            d[k] = None
+        return d
+
+    # ---- the solver ----
+    def _cholesky_check(self, eng, A):
+        """GAM._cholesky (pygam.py:499-537): retry with 10x the diagonal loading, literally"""
+        A = np.array(A, dtype=np.float64)
+        eye = np.eye(A.shape[0])
+        l2 = self._constraint_l2
+        while l2 <= self._constraint_l2_max:
+            if eng.chol_ok(A):
+                self._constraint_l2 = l2
+                return A
+            if self.verbose:
+                warnings.warn("Matrix is not positive definite. \nIncreasing l2 reg by factor of 10.", stacklevel=2)
+            A -= l2 * eye
+            l2 *= 10
+            A += l2 * eye
+        raise NotPositiveDefiniteError("Matrix is not positive \ndefinite.")
+
+    def _initial_estimate(self, eng, data):
+        """pygam.py:665-710: sqrt(EPS) for LinearGAM, else solve(X^T X + sqrt(EPS) I, X^T link(y'))"""
+        m = self.terms.n_coefs
+        if isinstance(self, LinearGAM):
+            return np.ones(m) * np.sqrt(EPS)
+        eng.gram_pass(data, None, mode=_lib.MODE_INIT)
+        sc = eng.gram_scalars()
+        assert sc[_lib.GS_NONFINITE] == 0, "transformed response values should be well-behaved."
+        eng.set_penalty(np.eye(m) * np.sqrt(EPS))
+        sol = eng.solve()
+        if sol["info"] != 0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        return sol["coef"]
+
+    def _coef_independent_gram(self):
+        """Normal/identity without asymmetric weights: W and z do not depend on the coefficients,
+        so G and r are computed once per data set"""
+        return (self.distribution.name == "normal" and self.link.name == "identity" and self._expectile is None)
+
+    def _pirls(self, data):
+        """One penalised IRLS fit (pygam.py:715-822) on device-resident data"""
+        eng = self._get_engine(data)
+        m = self.terms.n_coefs
+        n = self._n_global
+        if (not self._is_fitted or len(self.coef_) != m or not np.isfinite(self.coef_).all()):
+            self.coef_ = self._initial_estimate(eng, data)
+        assert np.isfinite(self.coef_).all(), f"coefficients should be well-behaved, but found: {self.coef_}"
+        self.coef_ = np.asarray(self.coef_, dtype=np.float64)
+
+        P = self.terms.build_penalties()
+        S = np.eye(m) * np.sqrt(EPS)
+        constrained = self.terms.hasconstraint
+        if not constrained:
+            EtE = self._cholesky_check(eng, S + P)
+            eng.set_penalty(EtE)
+
+        cache_ok = self._coef_independent_gram() and not constrained
+        cache = getattr(self, "_gram_cache", None) if cache_ok else None
+        if cache is not None and cache.get("data") is not data:
+            cache = None
+        diff = np.inf
+        for _ in range(self.max_iter):
+            if constrained:
+                P = self.terms.build_penalties()
+                C = self.terms.build_constraints(self.coef_, self._constraint_lam, self._constraint_l2)
+                EtE = self._cholesky_check(eng, S + P + C)
+                eng.set_penalty(EtE)
+
+            if cache is not None:
+                # G, r cached on the device; only the log scalars need the data (O(k) pass)
+                eng.out.copy_(cache["out"])
+                dev, ncorrect = self._dev_at(eng, data, self.coef_)
+                nused = n
+            else:
+                eng.gram_pass(data, self.coef_)
+                sc = eng.gram_scalars()
+                nused, dev, ncorrect = sc[_lib.GS_NUSED], sc[_lib.GS_DEV], sc[_lib.GS_NCORRECT]
+                if nused == 0:
+                    raise OptimizationError(
+                        "PIRLS optimization has diverged.\n"
+                        "Try increasing regularization, or specifying an initial value for self.coef_")
+                if cache_ok and nused == n:
+                    cache = dict(data=data, out=eng.out.clone())
+                    self._gram_cache = cache
+            self._log_start(dev, ncorrect, nused)
+
+            sol = eng.solve(coef_prev=self.coef_)
+            if sol["info"] == 2:
+                raise ValueError("QR decomposition produced NaN or Inf. Check X data.")
+            if sol["info"] != 0:
+                raise NotPositiveDefiniteError("penalised normal equations are not positive definite")
+            coef_new = sol["coef"]
+            diff = sol["diff"]
+            self.coef_ = coef_new
+            self._log_end(diff)
+            if diff < self.tol:
+                break
+
+        self._estimate_model_statistics(eng, data)
+        if diff >= self.tol:
+            print("did not converge")  # pygam.py:818-822
+        return
+
+    def _dev_at(self, eng, data, coef):
+        """unweighted deviance / accuracy count at `coef` through the O(k) statistics pass"""
+        memo = getattr(self, "_dev_memo", None)
+        key = np.asarray(coef, dtype=np.float64).tobytes()
+        if memo is not None and memo[0] is data and memo[1] == key:
+            return memo[2], memo[3]
+        sc, _, _ = eng.stats_pass(data, coef)
+        self._dev_memo = (data, key, sc[_lib.SS_DEV], sc[_lib.SS_NCORRECT])
+        return sc[_lib.SS_DEV], sc[_lib.SS_NCORRECT]
+
+    # ---- logs (callbacks.py:110-233, pygam.py:824-858) ----
+    def _log_start(self, dev, ncorrect, nused):
+        if "deviance" in self.callbacks:
+            self.logs_["deviance"].append(float(dev))
+        if "accuracy" in self.callbacks:
+            self.logs_["accuracy"].append(float(ncorrect) / float(nused))
+        if "coef" in self.callbacks:
+            self.logs_["coef"].append(np.array(self.coef_))
+
+    def _log_end(self, diff):
+        if "diffs" in self.callbacks:
+            self.logs_["diffs"].append(float(diff))
+
+    # ---- statistics (pygam.py:993-1228) ----
+    def _estimate_model_statistics(self, eng, data):
+        n = self._n_global
+        dist = self.distribution
+        st = self.statistics_
+        # edof and cov from the LAST iteration's Gram matrix (weights at the previous
+        # coefficients), as the reference's B and U1 are (pygam.py:815-817)
+        sol = eng.solve(coef_prev=None, want_edof=True, want_cov=True)
+        st["edof_per_coef"] = None
+        st["edof"] = sol["edof"]
+        sc, _, _ = eng.stats_pass(data, self.coef_)
+        self._dev_memo = (data, np.asarray(self.coef_, dtype=np.float64).tobytes(), sc[_lib.SS_DEV],
+                          sc[_lib.SS_NCORRECT])
+        if not dist._known_scale:
+            dist.scale = float(np.sqrt(sc[_lib.SS_PEARSON] / (n - st["edof"])))  # distributions.py:78
+        st["scale"] = dist.scale
+        st["cov"] = sol["cov"] * dist.scale ** 2
+        st["se"] = st["cov"].diagonal() ** 0.5
+        # second O(k) pass: log-likelihood and the null model need scale and mean(y)
+        ybar = sc[_lib.SS_SUMY] / n
+        sc2, _, _ = eng.stats_pass(data, self.coef_, scale=dist.scale, ybar=ybar,
+                                   poisson_round=isinstance(self, PoissonGAM))
+        ll = sc2[_lib.SS_LOGLIK]
+        st["AIC"] = -2 * ll + 2 * st["edof"] + 2 * (not dist._known_scale)
+        st["AICc"] = st["AIC"] + 2 * (st["edof"] + 1) * (st["edof"] + 2) / (n - st["edof"] - 2)
+        dev = sc[_lib.SS_WDEV]
+        null_dev = sc2[_lib.SS_NULL_WDEV]
+        null_ll = sc2[_lib.SS_NULL_LOGLIK]
+        st["pseudo_r2"] = OrderedDict([("explained_deviance", 1.0 - dev / null_dev),
+                                       ("McFadden", ll / null_ll),
+                                       ("McFadden_adj", 1.0 - (ll - st["edof"]) / null_ll)])
+        st["GCV"], st["UBRE"] = self._estimate_GCV_UBRE(dev, n, st["edof"])
+        st["loglikelihood"] = ll
+        div = dist.scale ** 2 if dist.name == "normal" else dist.scale  # scaled deviance, pygam.py:1054-1056
+        st["deviance"] = dev / div
+        st["p_values"] = self._estimate_p_values()
+
+    def _estimate_GCV_UBRE(self, dev, n, edof, gamma=1.4, add_scale=True):
+        """pygam.py:1156-1228; `~add_scale` of the reference is -2 for add_scale=True"""
+        if gamma < 1:
+            raise ValueError(f"gamma scaling should be greater than 1, but found gamma = {gamma}")
+        GCV = UBRE = None
+        if self.distribution._known_scale:
+            scale = self.distribution.scale
+            UBRE = 1.0 / n * dev - (-2 if add_scale else -1) * scale + 2.0 * gamma / n * edof * scale
+        else:
+            GCV = (n * dev) / (n - gamma * edof) ** 2
+        return GCV, UBRE
+
+    def _estimate_p_values(self):
+        return [self._compute_p_value(i) for i in range(len(self.terms))]
+
+    def _compute_p_value(self, term_i):
+        """pygam.py:1241-1295 (Wood 2006, 4.8.5): m-sized host arithmetic on cov and coef"""
+        idxs = self.terms.get_coef_indices(term_i)
+        cov = self.statistics_["cov"][idxs][:, idxs]
+        coef = np.array(self.coef_[idxs])
+        if isinstance(self.terms[term_i], SplineTerm):
+            coef -= coef.mean()
+        inv_cov, rank = scipy.linalg.pinv(cov, return_rank=True)
+        score = coef.T.dot(inv_cov).dot(coef)
+        if self.distribution._known_scale:
+            return 1 - scipy.stats.chi2.cdf(x=score, df=rank)
+        score = score / rank
+        return 1 - scipy.stats.f.cdf(score, rank, self.statistics_["n_samples"] - self.statistics_["edof"])
+
+    # ---- public API ----
+    def fit(self, X, y=None, weights=None):
+        """Fit the model (pygam.py:860-915).  X: (n, F) array-like on the host, or a
+        ``DeviceData`` row shard already resident in HBM (then y / weights may live inside it)."""
+        self._validate_params()
+        data = self._prepare_data(X, y, weights, fitting=True)
+        if data.y is None:
+            raise ValueError("y is required")
+        self._fit_data(data)
+        return self
+
+    def _fit_data(self, data):
+        col_minmax, bad = column_stats(data)
+        if bad.sum() > 0:
+            raise ValueError("X data must not contain Inf nor NaN")
+        nt = torch.tensor([float(data.n)], dtype=torch.float64, device=data.device)
+        self._n_global = int(all_reduce_(nt, "sum").item())
+        self._validate_data_dep_params(data, col_minmax)
+        self.statistics_ = {}
+        self.statistics_["n_samples"] = self._n_global
+        self.statistics_["m_features"] = data.n_features
+        self.logs_ = {c: [] for c in self.callbacks}
+        self._pirls(data)
+        return self
+
+    def _linear_predictor(self, X):
+        """pygam.py:385-421"""
+        data = self._prepare_data(X, fitting=False)
+        self._check_predict_X(data)
+        eng = self._get_engine(data)
+        _, lp, _ = eng.stats_pass(DeviceData(data.Xt), self.coef_, want_lp=True, reduce=False)
+        return lp.cpu().numpy()
+
+    def predict_mu(self, X):
+        """pygam.py:423-450"""
+        if not self._is_fitted:
+            raise AttributeError("GAM has not been fitted. Call fit first.")
+        data = self._prepare_data(X, fitting=False)
+        self._check_predict_X(data)
+        eng = self._get_engine(data)
+        _, _, mu = eng.stats_pass(DeviceData(data.Xt), self.coef_, want_mu=True, reduce=False)
+        return mu.cpu().numpy()
+
+    def predict(self, X):
+        """pygam.py:452-467"""
+        return self.predict_mu(X)
+
+    def _check_predict_X(self, data):
+        F = self.statistics_["m_features"]
+        if data.n_features != F:
+            raise ValueError(f"X data must have {F} features, but found {data.n_features}")
+        if not bool(torch.isfinite(data.Xt).all()):
+            raise ValueError("X data must not contain Inf nor NaN")
+        for t in self.terms:  # categorical range check, utils.py:308-334
+            if isinstance(t, FactorTerm):
+                col = data.Xt[t.feature]
+                lo, hi = float(t.edge_knots_[0]), float(t.edge_knots_[-1])
+                if bool(((col < lo) | (col > hi)).any()):
+                    raise ValueError(f"X data is out of domain for categorical feature {t.feature}. "
+                                     f"Expected data on [{lo}, {hi}], but found data on "
+                                     f"[{float(col.min())}, {float(col.max())}]")
+
+    def _modelmat(self, X, term=-1):
+        """dense model matrix of a (small) X, for inspection (pygam.py:469-497)"""
+        data = self._prepare_data(X, fitting=False)
+        eng = self._get_engine(data)
+        mm = eng.model_matrix(data).cpu().numpy()
+        if term == -1:
+            return mm
+        return mm[:, self.terms.get_coef_indices(term)]
+
+    def _P(self):
+        return self.terms.build_penalties()
+
+    def _C(self):
+        return self.terms.build_constraints(self.coef_, self._constraint_lam, self._constraint_l2)
+
+    def deviance_residuals(self, X, y, weights=None, scaled=False):
+        raise NotImplementedError("n-sized residual vectors are out of scope of the hot path (DESIGN.md)")
+
+    def loglikelihood(self, X, y, weights=None):
+        data = self._prepare_data(X, y, weights, fitting=True)
+        eng = self._get_engine(data)
+        sc, _, _ = eng.stats_pass(data, self.coef_)
+        ybar = sc[_lib.SS_SUMY] / data.n
+        sc2, _, _ = eng.stats_pass(data, self.coef_, scale=self.distribution.scale, ybar=ybar,
+                                   poisson_round=isinstance(self, PoissonGAM))
+        return sc2[_lib.SS_LOGLIK]
+
+    def gridsearch(self, X, y=None, weights=None, return_scores=False, keep_best=True, objective="auto",
+                   progress=False, **param_grids):
+        """Grid search over model parameters, best by GCV / UBRE / AIC / AICc
+        (pygam.py:1808-2085): sequential refits, each warm-started from the previous
+        candidate.  The data is uploaded once; for coefficient-independent weights
+        (LinearGAM) the Gram matrix is accumulated once and every candidate costs one m x m
+        solve plus O(k) passes."""
+        if not self._is_fitted:
+            self._validate_params()
+        data = self._prepare_data(X, y, weights, fitting=True)
+        if data.y is None:
+            raise ValueError("y is required")
+        if objective not in ["auto", "GCV", "UBRE", "AIC", "AICc"]:
+            raise ValueError("objective mut be in ['auto', 'GCV', 'UBRE', 'AIC', 'AICc'], "
+                             f"but found objective = {objective}")
+        if self.distribution._known_scale:
+            if objective == "GCV":
+                raise ValueError("GCV should be used for models withunknown scale")
+            if objective == "auto":
+                objective = "UBRE"
+        else:
+            if objective == "UBRE":
+                raise ValueError("UBRE should be used for models with known scale")
+            if objective == "auto":
+                objective = "GCV"
+        if not self._is_fitted:
+            col_minmax, bad = column_stats(data)
+            if bad.sum() > 0:
+                raise ValueError("X data must not contain Inf nor NaN")
+            self._validate_data_dep_params(data, col_minmax)
+        if not bool(param_grids):
+            param_grids["lam"] = np.logspace(-3, 3, 11)
+        admissible = list(self.get_params()) + PLURAL
+        params, grids = [], []
+        for param, grid in list(param_grids.items()):
+            if param not in admissible:
+                raise ValueError(f"unknown parameter: {param}")
+            if not (np.iterable(grid) and len(grid) > 1):
+                raise ValueError(f"{param} grid must either be iterable of iterables, or an iterable of "
+                                 f"lengnth > 1, but found {grid}")
+            if any(np.iterable(g) and not isinstance(g, str) for g in grid):
+                target_len = len(_flatten(getattr(self.terms, param) if param in PLURAL else getattr(self, param)))
+                cartesian = not isinstance(grid, np.ndarray) or grid.ndim != 2
+                grid = [np.atleast_1d(g) for g in grid]
+                msg = f"{param} grid should have {target_len} columns, but found grid with {len(grid)} columns"
+                if cartesian:
+                    if len(grid) != target_len:
+                        raise ValueError(msg)
+                    grid = _combine(*grid)
+                if not all(len(sub) == target_len for sub in grid):
+                    raise ValueError(msg)
+            params.append(param)
+            grids.append(list(grid))
+        param_grid_list = [dict(zip(params, cand)) for cand in _combine(*grids)]
+
+        best_model, best_score = None, np.inf
+        scores, models = [], []
+        if self._is_fitted:
+            models.append(self)
+            scores.append(self.statistics_[objective])
+            best_model, best_score = models[-1], scores[-1]
+        for param_grid in param_grid_list:
+            try:
+                gam = copy.deepcopy(self)
+                gam.set_params(**param_grid)
+                if models:
+                    gam.coef_ = np.array(models[-1].coef_)
+                gam._validate_params()
+                gam._fit_data(data)
+            except ValueError as error:
+                if self.verbose:
+                    warnings.warn(str(error) + "\non model with params:\n" + str(param_grid) + "\nskipping...\n")
+                continue
+            # candidates share the device engine and the cached Gram matrix
+            for k in _DEVICE_KEYS:
+                self.__dict__[k] = gam.__dict__.get(k)
+            models.append(gam)
+            scores.append(gam.statistics_[objective])
+            if scores[-1] < best_score:
+                best_model, best_score = models[-1], scores[-1]
+        if len(models) == 0:
+            if self.verbose:
+                warnings.warn("No models were fitted.")
+            return self
+        if keep_best:
+            for k, v in best_model.__dict__.items():
+                if k not in _DEVICE_KEYS:
+                    self.__dict__[k] = copy.deepcopy(v)
+        if return_scores:
+            return OrderedDict(zip(models, scores))
+        return self
+
+
+class _ShapeOnly:
+    """stand-in for X in Term.compile(): only the shape is needed once the column extrema and
+    level counts come from the device"""
+
+    def __init__(self, n, F):
+        self.shape = (n, F)
+
+
+def _flatten_knots(terms):
+    out = []
+    for t in terms:
+        if t.istensor:
+            out.extend(q.edge_knots_ for q in t._terms)
+        elif not t.isintercept:
+            out.append(getattr(t, "edge_knots_", None))
+    return out
+
+
+class LinearGAM(GAM):
+    """Normal distribution, identity link (pygam.py:2371-2506)"""
+
+    def __init__(self, terms="auto", max_iter=100, tol=1e-4, scale=None, callbacks=("deviance", "diffs"),
+                 fit_intercept=True, verbose=False, **kwargs):
+        self.scale = scale
+        super().__init__(terms=terms, distribution="normal", link="identity", max_iter=max_iter, tol=tol,
+                         callbacks=callbacks, fit_intercept=fit_intercept, verbose=verbose, **kwargs)
+
+    def _validate_params(self):
+        if isinstance(self.distribution, str):
+            self.distribution = Distribution("normal", scale=self.scale)
+        super()._validate_params()
+
+
+class LogisticGAM(GAM):
+    """Binomial distribution, logit link (pygam.py:2509-2682)"""
+
+    def __init__(self, terms="auto", max_iter=100, tol=1e-4, callbacks=("deviance", "diffs", "accuracy"),
+                 fit_intercept=True, verbose=False, **kwargs):
+        super().__init__(terms=terms, distribution="binomial", link="logit", max_iter=max_iter, tol=tol,
+                         callbacks=callbacks, fit_intercept=fit_intercept, verbose=verbose, **kwargs)
+
+    def accuracy(self, X=None, y=None, mu=None):
+        """pygam.py:2609-2650"""
+        if mu is None:
+            mu = self.predict_mu(X)
+        y = np.asarray(y).ravel()
+        return ((mu > 0.5).astype(int) == y).sum() / len(y)
+
+    def score(self, X, y):
+        return self.accuracy(X=X, y=y)
+
+    def predict(self, X):
+        """pygam.py:2652-2666"""
+        return self.predict_mu(X) > 0.5
+
+    def predict_proba(self, X):
+        return self.predict_mu(X)
+
+
+class PoissonGAM(GAM):
+    """Poisson distribution, log link, exposure support (pygam.py:2685-3046)"""
+
+    def __init__(self, terms="auto", max_iter=100, tol=1e-4, callbacks=("deviance", "diffs"),
+                 fit_intercept=True, verbose=False, **kwargs):
+        super().__init__(terms=terms, distribution="poisson", link="log", max_iter=max_iter, tol=tol,
+                         callbacks=callbacks, fit_intercept=fit_intercept, verbose=verbose, **kwargs)
+
+    @staticmethod
+    def _exposure_to_weights(y, exposure=None, weights=None):
+        """pygam.py:2838-2890 incl. the float32 casts"""
+        y = np.asarray(y, dtype=np.float64).ravel()
+        if exposure is not None:
+            exposure = np.array(exposure).astype("f").ravel()
+            if not np.isfinite(exposure).all():
+                raise ValueError("sample exposure data must not contain Inf nor NaN")
+        else:
+            exposure = np.ones_like(y).astype("float64")
+        if len(exposure) != len(y):
+            raise ValueError(f"Inconsistent input data shapes. found {len(y)} and {len(exposure)}")
+        y = y / exposure
+        if weights is not None:
+            weights = np.array(weights).astype("f").ravel()
+            if not np.isfinite(weights).all():
+                raise ValueError("sample weights data must not contain Inf nor NaN")
+        else:
+            weights = np.ones_like(y).astype("float64")
+        if len(exposure) != len(weights):
+            raise ValueError(f"Inconsistent input data shapes. found {len(weights)} and {len(exposure)}")
+        return y, weights * exposure
+
+    def fit(self, X, y=None, exposure=None, weights=None):
+        if isinstance(X, DeviceData) and exposure is None:
+            return super().fit(X, y, weights)
+        y, weights = self._exposure_to_weights(y, exposure, weights)
+        return super().fit(X, y, weights)
+
+    def predict(self, X, exposure=None):
+        """pygam.py:2922-2959"""
+        mu = self.predict_mu(X)
+        if exposure is not None:
+            exposure = np.array(exposure).astype("f")
+        else:
+            exposure = np.ones(len(mu)).astype("f")
+        if len(exposure) != len(mu):
+            raise ValueError(f"Inconsistent input data shapes. found {len(mu)} and {len(exposure)}")
+        return mu * exposure
+
+    def gridsearch(self, X, y=None, exposure=None, weights=None, return_scores=False, keep_best=True,
+                   objective="auto", **param_grids):
+        """pygam.py:2961-3046"""
+        if not (isinstance(X, DeviceData) and exposure is None):
+            y, weights = self._exposure_to_weights(y, exposure, weights)
+        return super().gridsearch(X, y, weights=weights, return_scores=return_scores, keep_best=keep_best,
+                                  objective=objective, **param_grids)
+
+
+class GammaGAM(GAM):
+    """Gamma distribution, log link (pygam.py:3049-3165)"""
+
+    def __init__(self, terms="auto", max_iter=100, tol=1e-4, scale=None, callbacks=("deviance", "diffs"),
+                 fit_intercept=True, verbose=False, **kwargs):
+        self.scale = scale
+        super().__init__(terms=terms, distribution="gamma", link="log", max_iter=max_iter, tol=tol,
+                         callbacks=callbacks, fit_intercept=fit_intercept, verbose=verbose, **kwargs)
+
+
+class InvGaussGAM(GAM):
+    """Inverse Gaussian distribution, log link (pygam.py:3168-3284)"""
+
+    def __init__(self, terms="auto", max_iter=100, tol=1e-4, scale=None, callbacks=("deviance", "diffs"),
+                 fit_intercept=True, verbose=False, **kwargs):
+        self.scale = scale
+        super().__init__(terms=terms, distribution="inv_gauss", link="log", max_iter=max_iter, tol=tol,
+                         callbacks=callbacks, fit_intercept=fit_intercept, verbose=verbose, **kwargs)
+
+
+class ExpectileGAM(GAM):
+    """Normal distribution, identity link, asymmetric least squares (pygam.py:3287-3551)"""
+
+    def __init__(self, terms="auto", max_iter=100, tol=1e-4, scale=None, callbacks=("deviance", "diffs"),
+                 fit_intercept=True, expectile=0.5, verbose=False, **kwargs):
+        self.scale = scale
+        self.expectile = expectile
+        super().__init__(terms=terms, distribution="normal", link="identity", max_iter=max_iter, tol=tol,
+                         callbacks=callbacks, fit_intercept=fit_intercept, verbose=verbose, **kwargs)
+        self._expectile = float(expectile)
+
+    def _validate_params(self):
+        if not (0 < self.expectile < 1):
+            raise ValueError(f"expectile must be in (0,1), but found {self.expectile}")
+        self._expectile = float(self.expectile)
+        if isinstance(self.distribution, str):
+            self.distribution = Distribution("normal", scale=self.scale)
+        super()._validate_params()
+
+    def _get_quantile_ratio(self, X, y):
+        """fraction of the targets below the fitted curve (pygam.py:3462-3480)"""
+        y_pred = self.predict(X)
+        return (y_pred > np.asarray(y).ravel()).mean()
+
+    def fit_quantile(self, X, y, quantile, max_iter=20, tol=0.01, weights=None):
+        """bisection on `expectile` until the model quantile matches (pygam.py:3482-3551)"""
+        if quantile <= 0 or quantile >= 1:
+            raise ValueError(f"quantile must be on (0, 1), but found {quantile}")
+        if tol <= 0:
+            raise ValueError(f"tol must be float > 0 {tol}")
+        if max_iter <= 0:
+            raise ValueError(f"max_iter must be int > 0 {max_iter}")
+        if not self._is_fitted:
+            self.fit(X, y, weights=weights)
+        max_ = 1.0
+        min_ = 0.0
+        n_iter = 0
+        while n_iter < max_iter:
+            ratio = self._get_quantile_ratio(X, y)
+            if np.abs(ratio - quantile) < tol:
+                break
+            if ratio < quantile:
+                min_ = self.expectile
+            else:
+                max_ = self.expectile
+            expectile = (max_ + min_) / 2.0
+            self.set_params(expectile=expectile)
+            self.fit(X, y, weights=weights)
+            n_iter += 1
+        if n_iter == max_iter and self.verbose:
+            warnings.warn("maximum iterations reached")
+        return self

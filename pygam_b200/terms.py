@@ -1,0 +1,650 @@
+"""Term grammar of the GAM API: ``s()``, ``l()``, ``f()``, ``te()``, ``intercept`` and ``TermList``.
+
+Mirrors the public surface of ``/root/reference/pygam/terms.py`` (constructors 497-599, 602-708,
+711-956, 959-1101, 1104-1641, 1644-1979 and the shortcuts 1983-2046): same names, keyword
+arguments, defaults and validation errors.  What differs is what a term *produces*: instead of
+sparse model-matrix columns (``build_columns``) a compiled term flattens into one
+``pgb_term`` record of the device model descriptor (``include/pgb.h``); the basis is then
+evaluated on the fly inside the CUDA kernels.  Penalty and constraint matrices stay host-side
+numpy, as in the reference.
+"""
+
+import copy
+import warnings
+
+import numpy as np
+import scipy.linalg
+
+from . import penalties as _pen
+
+DEFAULT_LAM = 0.6
+MAX_ORDER = 7  # PGB_MAX_ORDER
+MAX_MARGINALS = 4  # PGB_MAX_MARG
+
+
+def _aslist(v):
+    if isinstance(v, (list, tuple, np.ndarray)):
+        return list(v)
+    return [v]
+
+
+class Term:
+    """Common state of a term: feature, per-penalty ``lam``, ``penalties``, ``constraints``."""
+
+    kind = "term"
+    isintercept = False
+    istensor = False
+
+    def __init__(self, feature, lam=DEFAULT_LAM, penalties="auto", constraints=None, dtype="numerical",
+                 by=None, verbose=False):
+        self.feature = feature
+        self.lam = lam
+        self.penalties = penalties
+        self.constraints = constraints
+        self.dtype = dtype
+        self.by = by
+        self.verbose = verbose
+        self.edge_knots_ = None
+        self._validate()
+
+    # -- argument normalisation (terms.py:148-210) --
+    def _validate(self):
+        if self.feature is not None:
+            if not (isinstance(self.feature, (int, np.integer)) and self.feature >= 0):
+                raise ValueError(f"feature must be an integer >= 0, but found {self.feature}")
+            self.feature = int(self.feature)
+        if self.by is not None:
+            if not (isinstance(self.by, (int, np.integer)) and self.by >= 0):
+                raise ValueError(f"by must be an integer >= 0, but found {self.by}")
+            self.by = int(self.by)
+        if self.dtype not in ("numerical", "categorical"):
+            raise ValueError(f"dtype must be in ['numerical', 'categorical'], but found dtype = {self.dtype}")
+        self.constraints = _aslist(self.constraints)
+        for i, c in enumerate(self.constraints):
+            if c is None:
+                continue
+            if not (callable(c) or c in _pen.CONSTRAINTS):
+                raise ValueError(f"unknown constraint {c}")
+        self.penalties = _aslist(self.penalties)
+        for p in self.penalties:
+            if not (callable(p) or p is None or p in _pen.PENALTIES):
+                raise ValueError(f"penalties must be callable or in {list(_pen.PENALTIES)}, but found {p}")
+        lam = _aslist(self.lam)
+        if len(lam) == 1:
+            lam = lam * len(self.penalties)
+        if len(lam) != len(self.penalties):
+            raise ValueError(f"expected 1 lam per penalty, but found lam = {self.lam}, "
+                             f"penalties = {self.penalties}")
+        for v in lam:
+            if not (np.isfinite(v) and v >= 0):
+                raise ValueError(f"lam must be >= 0 and finite, but found {v}")
+        self.lam = [float(v) for v in lam]
+        return self
+
+    # -- grammar --
+    def __add__(self, other):
+        return TermList(self, other)
+
+    def __mul__(self, other):
+        return TermList(self) * other
+
+    def __len__(self):
+        return 1
+
+    def __repr__(self):
+        if self.isintercept:
+            return "intercept"
+        return f"{self.minimal_name}({self.feature})"
+
+    minimal_name = "term"
+
+    @property
+    def info(self):
+        d = {k: (list(v) if isinstance(v, (list, np.ndarray)) else v) for k, v in self.__dict__.items()
+             if not k.endswith("_") and k != "verbose" and not k.startswith("_")}
+        d["term_type"] = self.kind
+        return d
+
+    @property
+    def n_coefs(self):
+        raise NotImplementedError
+
+    @property
+    def hasconstraint(self):
+        """terms.py:260-263 -- any entry that is not None counts, even the string "none" """
+        return any(c is not None for c in self.constraints)
+
+    def compile(self, X, verbose=False):
+        return self
+
+    # -- m x m pieces --
+    def build_penalties(self):
+        """sum_k lam_k * penalty_k(n_coefs) (terms.py:307-349)"""
+        if self.isintercept:
+            return np.array([[0.0]])
+        n = self.n_coefs
+        total = np.zeros((n, n))
+        for pen, lam in zip(self.penalties, self.lam):
+            if pen == "auto":
+                if self.dtype == "numerical":
+                    if self.kind == "spline_term":
+                        pen = "periodic" if self.basis in ["cp"] else "derivative"
+                    else:
+                        pen = "l2"
+                if self.dtype == "categorical":
+                    pen = "l2"
+            if pen is None:
+                pen = "none"
+            fn = _pen.PENALTIES[pen] if isinstance(pen, str) else pen
+            total = total + np.multiply(np.asarray(_dense(fn(n, None)), dtype=np.float64), lam)
+        return total
+
+    def build_constraints(self, coef, constraint_lam, constraint_l2):
+        """sum_k constraint_k(n, coef) * constraint_lam, plus constraint_l2 * I on a block
+        with violations (terms.py:351-396)"""
+        if self.isintercept:
+            return np.array([[0.0]])
+        n = self.n_coefs
+        total = np.zeros((n, n))
+        for c in self.constraints:
+            if c is None:
+                c = "none"
+            fn = _pen.CONSTRAINTS[c] if isinstance(c, str) else c
+            total = total + np.asarray(_dense(fn(n, coef)), dtype=np.float64) * constraint_lam
+        if np.count_nonzero(total) > 0:
+            total = total + constraint_l2 * np.eye(n)
+        return total
+
+
+def _dense(a):
+    return a.toarray() if hasattr(a, "toarray") else a
+
+
+class Intercept(Term):
+    kind = "intercept_term"
+    isintercept = True
+    minimal_name = "intercept"
+
+    def __init__(self, verbose=False):
+        super().__init__(feature=None, lam=[0.0], penalties=[None], constraints=None, verbose=verbose)
+
+    @property
+    def n_coefs(self):
+        return 1
+
+
+class LinearTerm(Term):
+    kind = "linear_term"
+    minimal_name = "l"
+
+    def __init__(self, feature, lam=DEFAULT_LAM, penalties="auto", verbose=False):
+        super().__init__(feature=feature, lam=lam, penalties=penalties, constraints=None,
+                         dtype="numerical", verbose=verbose)
+
+    @property
+    def n_coefs(self):
+        return 1
+
+    def compile(self, X, verbose=False):
+        if self.feature >= X.shape[1]:
+            raise ValueError(f"term requires feature {self.feature}, but X has only {X.shape[1]} dimensions")
+        return self
+
+
+class SplineTerm(Term):
+    kind = "spline_term"
+    minimal_name = "s"
+    _bases = ["ps", "cp"]
+
+    def __init__(self, feature, n_splines=20, spline_order=3, lam=DEFAULT_LAM, penalties="auto",
+                 constraints=None, dtype="numerical", basis="ps", by=None, edge_knots=None,
+                 verbose=False):
+        self.basis = basis
+        self.n_splines = n_splines
+        self.spline_order = spline_order
+        self.edge_knots = edge_knots
+        super().__init__(feature=feature, lam=lam, penalties=penalties, constraints=constraints,
+                         dtype=dtype, by=by, verbose=verbose)
+
+    def _validate(self):
+        super()._validate()
+        if self.basis not in self._bases:
+            raise ValueError(f"basis must be one of {self._bases}, but found: {self.basis}")
+        self.n_splines = int(_check_int(self.n_splines, "n_splines", 0))
+        self.spline_order = int(_check_int(self.spline_order, "spline_order", 0))
+        if not self.n_splines > self.spline_order:
+            raise ValueError(f"n_splines must be > spline_order. found: n_splines = {self.n_splines} "
+                             f"and spline_order = {self.spline_order}")
+        if self.spline_order > MAX_ORDER:
+            raise NotImplementedError(f"spline_order > {MAX_ORDER} is not supported by the CUDA basis evaluation")
+        if self.edge_knots is not None:
+            self.edge_knots = np.asarray(self.edge_knots, dtype=np.float64).ravel()
+        return self
+
+    @property
+    def n_coefs(self):
+        return self.n_splines
+
+    def compile(self, X, col_minmax=None, verbose=False):
+        """terms.py:895-924: user edge knots are kept, otherwise [min, max] of the column"""
+        if self.feature >= X.shape[1]:
+            raise ValueError(f"term requires feature {self.feature}, but X has only {X.shape[1]} dimensions")
+        if self.by is not None and self.by >= X.shape[1]:
+            raise ValueError(f"by variable requires feature {self.by}, but X has only {X.shape[1]} dimensions")
+        if self.edge_knots is not None:
+            self.edge_knots_ = np.asarray(self.edge_knots, dtype=np.float64)
+        if getattr(self, "edge_knots_", None) is None:
+            self.edge_knots_ = _edge_knots(X, self.feature, self.dtype, col_minmax)
+        return self
+
+
+class FactorTerm(SplineTerm):
+    kind = "factor_term"
+    minimal_name = "f"
+    _encodings = ["one-hot", "dummy"]
+
+    def __init__(self, feature, lam=DEFAULT_LAM, penalties="auto", coding="one-hot", verbose=False):
+        self.coding = coding
+        # n_splines is data dependent (terms.py:1071); 1 is a placeholder until compile()
+        super().__init__(feature=feature, n_splines=1, spline_order=0, lam=lam, penalties=penalties,
+                         constraints=None, dtype="categorical", basis="ps", by=None, verbose=verbose)
+
+    def _validate(self):
+        super()._validate()
+        if self.coding not in self._encodings:
+            raise ValueError(f"coding must be one of {self._encodings}, but found: {self.coding}")
+        return self
+
+    @property
+    def n_coefs(self):
+        return self.n_splines - (1 if self.coding == "dummy" else 0)
+
+    def compile(self, X, col_minmax=None, n_levels=None, verbose=False):
+        """terms.py:1054-1075: recomputed on every fit"""
+        if self.feature >= X.shape[1]:
+            raise ValueError(f"term requires feature {self.feature}, but X has only {X.shape[1]} dimensions")
+        if n_levels is None:
+            n_levels = len(np.unique(np.asarray(X[:, self.feature])))
+        self.n_splines = int(n_levels)
+        self.edge_knots_ = _edge_knots(X, self.feature, "categorical", col_minmax)
+        return self
+
+
+class TensorTerm(Term):
+    kind = "tensor_term"
+    minimal_name = "te"
+    istensor = True
+    _N_SPLINES = 10
+
+    def __init__(self, *args, **kwargs):
+        verbose = kwargs.pop("verbose", False)
+        by = kwargs.pop("by", None)
+        if "feature" in kwargs and args != tuple():
+            raise ValueError("Marginal features in a TensorTerm must be specified either as `args` "
+                             "or via keyword as `feature=...` but not both.")
+        args = kwargs.pop("feature", args)
+        m = len(args)
+        if m < 2:
+            raise ValueError("TensorTerm requires at least 2 marginal terms")
+        if m > MAX_MARGINALS:
+            raise NotImplementedError(f"tensor terms with more than {MAX_MARGINALS} marginals are not supported")
+        for k, v in list(kwargs.items()):
+            if isinstance(v, (list, tuple, np.ndarray)):
+                if len(v) != m:
+                    raise ValueError(f"Expected {k} to have length {m}, but found {k} = {v}")
+            else:
+                kwargs[k] = [v] * m
+        margs = []
+        for i, arg in enumerate(args):
+            if isinstance(arg, TensorTerm):
+                raise ValueError("TensorTerm does not accept other TensorTerms. "
+                                 "Please build a flat TensorTerm instead of a nested one.")
+            if isinstance(arg, Term):
+                if not isinstance(arg, SplineTerm) or isinstance(arg, FactorTerm):
+                    raise NotImplementedError("tensor marginals must be spline terms")
+                margs.append(arg)
+                continue
+            kw = {"n_splines": self._N_SPLINES}
+            kw.update({k: v[i] for k, v in kwargs.items()})
+            margs.append(SplineTerm(arg, **kw))
+        self._terms = margs
+        self.feature = [t.feature for t in margs]
+        self.by = by
+        self.verbose = verbose
+        self.dtype = "numerical"
+        if by is not None and not (isinstance(by, (int, np.integer)) and by >= 0):
+            raise ValueError(f"by must be an integer >= 0, but found {by}")
+
+    def __len__(self):
+        return len(self._terms)
+
+    def __getitem__(self, i):
+        return self._terms[i]
+
+    def __repr__(self):
+        return "te(" + ", ".join(str(t.feature) for t in self._terms) + ")"
+
+    @property
+    def info(self):
+        return {"term_type": self.kind, "by": self.by, "terms": [t.info for t in self._terms]}
+
+    @property
+    def n_coefs(self):
+        return int(np.prod([t.n_coefs for t in self._terms]))
+
+    @property
+    def hasconstraint(self):
+        return any(t.hasconstraint for t in self._terms)
+
+    # the plural attributes of a tensor term are the lists over its marginals
+    @property
+    def lam(self):
+        return [t.lam for t in self._terms]
+
+    @property
+    def edge_knots_(self):
+        return [t.edge_knots_ for t in self._terms]
+
+    def compile(self, X, col_minmax=None, verbose=False):
+        for t in self._terms:
+            t.compile(X, col_minmax=col_minmax, verbose=verbose)
+        if self.by is not None and self.by >= X.shape[1]:
+            raise ValueError(f"by variable requires feature {self.by}, but X has only {X.shape[1]} dimensions")
+        return self
+
+    def build_penalties(self):
+        """sum_i I x ... x P_i x ... x I (terms.py:1479-1517)"""
+        total = 0
+        for i in range(len(self._terms)):
+            acc = None
+            for j, t in enumerate(self._terms):
+                Pj = t.build_penalties() if j == i else np.eye(t.n_coefs)
+                acc = Pj if acc is None else np.kron(acc, Pj)
+            total = total + acc
+        return total
+
+    def build_constraints(self, coef, constraint_lam, constraint_l2):
+        """every 1-d slice of the coefficient tensor along each marginal gets that marginal's
+        constraint matrix (terms.py:1519-1609)"""
+        dims = [t.n_coefs for t in self._terms]
+        size = int(np.prod(dims))
+        C = np.zeros((size, size))
+        idx = np.arange(size).reshape(dims)
+        coef = np.asarray(coef)
+        for i, t in enumerate(self._terms):
+            slices = np.moveaxis(idx, i, 0).reshape(dims[i], size // dims[i])
+            for sl in slices.T:
+                C[np.ix_(sl, sl)] += t.build_constraints(coef[sl], constraint_lam, constraint_l2)
+        return C
+
+
+def _check_int(v, name, min_val):
+    if isinstance(v, (bool,)) or not isinstance(v, (int, np.integer)) or v < min_val:
+        if isinstance(v, (float, np.floating)) and float(v).is_integer() and v >= min_val:
+            return int(v)
+        raise ValueError(f"{name} must be int >= {min_val}, but found {name} = {v}")
+    return v
+
+
+def _edge_knots(X, feature, dtype, col_minmax=None):
+    """gen_edge_knots (utils.py:592-621); col_minmax holds device-computed column extrema"""
+    if col_minmax is not None:
+        lo, hi = col_minmax[feature]
+    else:
+        col = np.asarray(X[:, feature])
+        lo, hi = col.min(), col.max()
+    if dtype == "categorical":
+        return np.r_[lo - 0.5, hi + 0.5]
+    knots = np.r_[lo, hi]
+    if lo == hi:
+        warnings.warn("Data contains constant feature. Consider removing and setting fit_intercept=True",
+                      stacklevel=2)
+    return knots
+
+
+class TermList:
+    """Ordered collection of unique terms (terms.py:1644-1979)."""
+
+    def __init__(self, *terms, **kwargs):
+        self.verbose = kwargs.pop("verbose", False)
+        if kwargs:
+            raise ValueError(f"Unexpected keyword argument {kwargs.keys()}")
+        seen, out = set(), []
+        for t in terms:
+            if isinstance(t, Term):
+                items = [t]
+            elif isinstance(t, TermList):
+                items = t._terms
+            else:
+                raise ValueError(f"terms must be instances of Term or TermList, but found term: {t}")
+            for it in items:
+                key = repr(sorted(it.info.items(), key=lambda kv: kv[0]))
+                if key in seen:
+                    if self.verbose:
+                        warnings.warn(f"skipping duplicate term: {it!r}")
+                    continue
+                seen.add(key)
+                out.append(it)
+        self._terms = out
+
+    def __len__(self):
+        return len(self._terms)
+
+    def __getitem__(self, i):
+        return self._terms[i]
+
+    def __iter__(self):
+        return iter(self._terms)
+
+    def __add__(self, other):
+        return TermList(self, other)
+
+    def __radd__(self, other):
+        return TermList(other, self)
+
+    def __repr__(self):
+        return " + ".join(repr(t) for t in self._terms)
+
+    @property
+    def info(self):
+        return {"term_type": "term_list", "terms": [t.info for t in self._terms]}
+
+    @property
+    def n_coefs(self):
+        return sum(t.n_coefs for t in self._terms)
+
+    @property
+    def hasconstraint(self):
+        return any(t.hasconstraint for t in self._terms)
+
+    def get_coef_indices(self, i=-1):
+        """terms.py:1874-1899"""
+        if i == -1:
+            return list(range(self.n_coefs))
+        if i >= len(self._terms):
+            raise ValueError(f"requested {i}th term, but found only {len(self._terms)} terms")
+        start = sum(t.n_coefs for t in self._terms[:i])
+        return list(range(start, start + self._terms[i].n_coefs))
+
+    def pop(self, i=None):
+        if i is None:
+            i = len(self) - 1
+        if i >= len(self._terms) or i < 0:
+            raise ValueError(f"requested pop {i}th term, but found only {len(self._terms)} terms")
+        term = self._terms[i]
+        self._terms = self._terms[:i] + self._terms[i + 1:]
+        return term
+
+    # ---- plural attributes (terms.py:399-494): values are consumed in term order ----
+    def _slots(self):
+        """the objects that own a ``lam`` list: non-intercept terms, tensor marginals flattened"""
+        out = []
+        for t in self._terms:
+            if t.isintercept:
+                continue
+            if t.istensor:
+                out.extend(t._terms)
+            else:
+                out.append(t)
+        return out
+
+    @property
+    def lam(self):
+        out = []
+        for t in self._terms:
+            if t.isintercept:
+                continue
+            out.append(t.lam)
+        return out
+
+    @lam.setter
+    def lam(self, values):
+        slots = self._slots()
+        size = sum(len(s.lam) for s in slots)
+        if np.ndim(values) == 0:
+            flat = [values] * size
+        else:
+            flat = list(_flatten(values))
+        if len(flat) != size:
+            raise ValueError(f"Expected lam to have length {size}, but found lam = {values}")
+        pos = 0
+        for s in slots:
+            k = len(s.lam)
+            s.lam = flat[pos:pos + k]
+            s._validate()
+            pos += k
+
+    def _set_plural(self, name, values):
+        if name == "lam":
+            self.lam = values
+            return
+        slots = [s for s in self._slots() if hasattr(s, name)]
+        if np.ndim(values) == 0 or isinstance(values, str):
+            flat = [values] * len(slots)
+        else:
+            flat = list(values)
+        if len(flat) != len(slots):
+            raise ValueError(f"Expected {name} to have length {len(slots)}, but found {name} = {values}")
+        for s, v in zip(slots, flat):
+            setattr(s, name, v)
+            s._validate()
+
+    @property
+    def edge_knots_(self):
+        return [t.edge_knots_ for t in self._terms if not t.isintercept and t.kind != "linear_term"]
+
+    # ---- data-dependent state ----
+    def compile(self, X, col_minmax=None, n_levels=None, verbose=False):
+        for t in self._terms:
+            if isinstance(t, FactorTerm):
+                t.compile(X, col_minmax=col_minmax,
+                          n_levels=None if n_levels is None else n_levels.get(t.feature), verbose=verbose)
+            elif isinstance(t, (SplineTerm, TensorTerm)):
+                t.compile(X, col_minmax=col_minmax, verbose=verbose)
+            else:
+                t.compile(X, verbose=verbose)
+        n_intercepts = sum(1 for t in self._terms if t.isintercept)
+        if n_intercepts > 1:
+            raise ValueError("cannot have more than one intercept")
+        return self
+
+    def features_used(self):
+        feats = set()
+        for t in self._terms:
+            if t.isintercept:
+                continue
+            if t.istensor:
+                feats.update(t.feature)
+            else:
+                feats.add(t.feature)
+            if t.by is not None:
+                feats.add(t.by)
+        return feats
+
+    # ---- m x m pieces ----
+    def build_penalties(self):
+        """block-diagonal penalty matrix P (terms.py:1925-1947), dense (m, m)"""
+        return scipy.linalg.block_diag(*[t.build_penalties() for t in self._terms])
+
+    def build_constraints(self, coef, constraint_lam, constraint_l2):
+        """block-diagonal constraint matrix C (terms.py:1949-1979), dense (m, m)"""
+        coef = np.asarray(coef, dtype=np.float64).ravel()
+        blocks, start = [], 0
+        for t in self._terms:
+            n = t.n_coefs
+            blocks.append(t.build_constraints(coef[start:start + n], constraint_lam, constraint_l2))
+            start += n
+        return scipy.linalg.block_diag(*blocks)
+
+    def null_vectors(self):
+        """Analytic null space of the design: every ps/cp spline, one-hot factor
+        or tensor block without a ``by`` variable is a partition of unity, so
+        (1 on the block, -1 on the intercept) -- or, without an intercept, (1 on the block, -1 on
+        the first such block) -- is an exact null vector of X.  Returns (m, p)."""
+        m = self.n_coefs
+        blocks, icpt, start = [], None, 0
+        for t in self._terms:
+            n = t.n_coefs
+            if t.isintercept:
+                icpt = start
+            elif t.by is None and (
+                (isinstance(t, FactorTerm) and t.coding == "one-hot")
+                or (isinstance(t, SplineTerm) and not isinstance(t, FactorTerm)
+                    and not (t.spline_order == 0 and t.edge_knots is not None))
+                or (t.istensor and not any(q.spline_order == 0 and q.edge_knots is not None
+                                           for q in t._terms))
+            ):
+                blocks.append((start, n))
+            start += n
+        vecs = []
+        if icpt is not None:
+            for s0, n in blocks:
+                v = np.zeros(m)
+                v[s0:s0 + n] = 1.0
+                v[icpt] = -1.0
+                vecs.append(v)
+        elif len(blocks) > 1:
+            b0, n0 = blocks[0]
+            for s0, n in blocks[1:]:
+                v = np.zeros(m)
+                v[s0:s0 + n] = 1.0
+                v[b0:b0 + n0] = -1.0
+                vecs.append(v)
+        if not vecs:
+            return np.zeros((m, 0))
+        return np.stack(vecs, axis=1)
+
+
+def _flatten(v):
+    for x in v:
+        if isinstance(x, (list, tuple, np.ndarray)):
+            yield from _flatten(x)
+        else:
+            yield x
+
+
+# shortcuts (terms.py:1983-2046)
+def l(feature, lam=DEFAULT_LAM, penalties="auto", verbose=False):  # noqa: E743
+    return LinearTerm(feature=feature, lam=lam, penalties=penalties, verbose=verbose)
+
+
+def s(feature, n_splines=20, spline_order=3, lam=DEFAULT_LAM, penalties="auto", constraints=None,
+      dtype="numerical", basis="ps", by=None, edge_knots=None, verbose=False):
+    return SplineTerm(feature=feature, n_splines=n_splines, spline_order=spline_order, lam=lam,
+                      penalties=penalties, constraints=constraints, dtype=dtype, basis=basis, by=by,
+                      edge_knots=edge_knots, verbose=verbose)
+
+
+def f(feature, lam=DEFAULT_LAM, penalties="auto", coding="one-hot", verbose=False):
+    return FactorTerm(feature=feature, lam=lam, penalties=penalties, coding=coding, verbose=verbose)
+
+
+def te(*args, **kwargs):
+    return TensorTerm(*args, **kwargs)
+
+
+intercept = Intercept()
+
+
+def deepcopy_terms(terms):
+    return copy.deepcopy(terms)

@@ -1,0 +1,127 @@
+"""CPU tests of the product's host logic (no GPU): the PIRLS driver, penalties / constraints,
+statistics assembly and grid search of pygam_b200 are run with the oracle-backed test engine
+(tests/oracle_backend.py) and compared with the golden fixtures of the unmodified reference.
+The solve used here is a numpy mirror of the CUDA solver's algorithm, so these tests also show
+that the Gram-form, null-space-aware method reproduces the reference's iteration counts."""
+import numpy as np
+import pytest
+
+import cases
+import helpers
+from helpers import check_against_golden, fit_case, load
+from oracle_backend import OracleBackend
+from pygam_b200 import engine as pg_engine
+from pygam_b200 import penalties as pg_pen
+import pygam_b200 as pg
+
+
+@pytest.fixture(autouse=True)
+def oracle_backend():
+    old = pg_engine.set_backend(OracleBackend())
+    yield
+    pg_engine.set_backend(old)
+
+
+def test_penalties_known_answers():
+    g = load("penalties")
+    for n in (1, 2, 3, 5, 8, 20):
+        coef = g[f"coef_{n}"]
+        np.testing.assert_array_equal(pg_pen.derivative(n), g[f"derivative_{n}"])
+        np.testing.assert_array_equal(pg_pen.l2(n), g[f"l2_{n}"])
+        if n >= 5:
+            np.testing.assert_array_equal(pg_pen.periodic(n), g[f"periodic_{n}"])
+        for cname in ("monotonic_inc", "monotonic_dec", "convex", "concave"):
+            np.testing.assert_array_equal(pg_pen.CONSTRAINTS[cname](n, coef), g[f"{cname}_{n}"])
+
+
+@pytest.mark.parametrize("name", sorted(cases.FIT_CASES))
+def test_fit_matches_reference(name):
+    case = cases.FIT_CASES[name]
+    g = load("fit_" + name)
+    gam = fit_case(case, g)
+    np.testing.assert_array_equal(gam._P(), g["penalty"])
+    check_against_golden(gam, g, constrained=name in helpers.CONSTRAINED)
+    if "constraint_final" in g:
+        C = gam.terms.build_constraints(g["coef"], gam._constraint_lam, gam._constraint_l2)
+        np.testing.assert_allclose(C, g["constraint_final"], rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("name", sorted(cases.GRID_CASES))
+def test_gridsearch_matches_reference(name):
+    gcase = cases.GRID_CASES[name]
+    case = cases.FIT_CASES[gcase["fit"]]
+    g = load("grid_" + name)
+    f = load("fit_" + gcase["fit"])
+    gam = helpers.build_model(case)
+    kw = {} if gcase["grid"] is None else dict(gcase["grid"])
+    if case["model"] == "PoissonGAM":
+        scores = gam.gridsearch(f["X"], f["y"], exposure=f.get("exposure"), weights=f.get("weights"),
+                                return_scores=True, **kw)
+    else:
+        scores = gam.gridsearch(f["X"], f["y"], weights=f.get("weights"), return_scores=True, **kw)
+    models = list(scores.keys())
+    vals = np.array(list(scores.values()))
+    assert len(vals) == len(g["scores"])
+    np.testing.assert_allclose(vals, g["scores"], rtol=1e-9)
+    np.testing.assert_array_equal([len(mm.logs_["diffs"]) for mm in models], g["n_iters"])
+    np.testing.assert_allclose([mm.statistics_["edof"] for mm in models], g["edofs"], rtol=1e-8)
+    obj = "UBRE" if gam.distribution._known_scale else "GCV"
+    assert abs(gam.statistics_[obj] - float(g["best_score"])) <= 1e-10 * abs(float(g["best_score"]))
+
+
+def test_config1_published_known_answers():
+    """docs/notebooks/quick_start.ipynb:113-118 and tour_of_pygam.ipynb:375-380"""
+    w = load("wage_xy")
+    gam = pg.LinearGAM(pg.s(0) + pg.s(1) + pg.f(2)).fit(w["X"], w["y"])
+    st = gam.statistics_
+    assert round(st["edof"], 4) == 25.1911
+    assert round(st["GCV"], 4) == 1255.6902
+    assert round(st["pseudo_r2"]["explained_deviance"], 4) == 0.2955
+    assert len(gam.logs_["diffs"]) == 2
+    gam2 = pg.LinearGAM(pg.s(0) + pg.s(1) + pg.f(2)).gridsearch(w["X"], w["y"])
+    assert round(gam2.lam[0][0], 4) == 15.8489
+    assert round(gam2.statistics_["edof"], 4) == 19.2602
+    assert round(gam2.statistics_["GCV"], 4) == 1250.3656
+
+
+def test_term_grammar_and_validation():
+    tl = pg.s(0) + pg.s(1, n_splines=7) + pg.f(2) + pg.te(3, 4) + pg.l(5)
+    assert len(tl) == 5
+    assert repr(tl) == "s(0) + s(1) + f(2) + te(3, 4) + l(5)"
+    assert len(pg.s(0) + pg.s(0)) == 1  # duplicates are dropped (terms.py:1646)
+    with pytest.raises(ValueError):
+        pg.s(0, n_splines=3, spline_order=3)
+    with pytest.raises(ValueError):
+        pg.s(0, basis="xx")
+    with pytest.raises(ValueError):
+        pg.te(0)
+    with pytest.raises(ValueError):
+        pg.s(0, lam=-1)
+    with pytest.raises(ValueError):
+        pg.f(0, coding="weird")
+    assert pg.te(0, 1).n_coefs == 100
+    assert pg.s(0, constraints="none").hasconstraint  # the string counts (terms.py:260-263)
+
+
+def test_input_validation():
+    rng = np.random.default_rng(0)
+    X = rng.random((50, 2))
+    y = rng.random(50)
+    Xn = X.copy()
+    Xn[3, 1] = np.nan
+    with pytest.raises(ValueError):
+        pg.LinearGAM().fit(Xn, y)
+    yn = y.copy()
+    yn[0] = np.inf
+    with pytest.raises(ValueError):
+        pg.LinearGAM().fit(X, yn)
+    with pytest.raises(ValueError):
+        pg.LogisticGAM().fit(X, y + 2.0)  # outside the logit domain
+    with pytest.raises(ValueError):
+        pg.LinearGAM().fit(X, y[:-1])
+    with pytest.raises(ValueError):
+        pg.LinearGAM(pg.s(5)).fit(X, y)
+    with pytest.raises(NotImplementedError):
+        pg.LinearGAM(callbacks=[object()])
+    with pytest.raises(AttributeError):
+        pg.LinearGAM().predict_mu(X)
