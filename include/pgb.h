@@ -165,8 +165,12 @@ int pgb_stats_pass(const pgb_model* model, const double* X, int64_t n, int64_t l
  * equal beta = (G + E^T E)^-1 r, solved in a basis T = [Nhat | Z] that separates the analytic
  * null space of the design: T is given as `p` Householder reflectors
  * H_q = I - tau[q] v_q v_q^T (hv: p vectors of length m, one after the other; T = H_0 ... H_{p-1}).  EtE = S + P (+ C) in the ORIGINAL basis.  For a batch of
- * `nb` systems (grid-search candidates) EtE, out are strided by their own sizes while G, r are
- * shared when share_gram != 0.
+ * `nb` systems (grid-search candidates) EtE, EtE_null, out are strided by their own sizes while
+ * G, r are shared when share_gram != 0.  The penalty is passed in two parts, EtE + EtE_null:
+ * EtE_null (may be NULL) holds the components that annihilate the null vectors structurally
+ * (difference penalties, constraint penalties D M D^T, which can be as large as 1e9); like G its
+ * null block is set to exact zero after the change of basis, so that the sqrt(EPS)-sized
+ * entries of the remaining part EtE are not swamped by its rounding noise.
  * out (per system, doubles): [beta (m) | edof | diff | info | logdet | ||beta|| | reserved(3)]
  * = m + 8.  beta_prev (m per system, or one shared vector when share_prev != 0; may be NULL)
  * feeds diff = ||beta_prev - beta|| / ||beta|| (pygam.py:804).  flags: PGB_SOLVE_EDOF computes
@@ -177,7 +181,7 @@ int pgb_stats_pass(const pgb_model* model, const double* X, int64_t n, int64_t l
 enum { PGB_SOLVE_EDOF = 1, PGB_SOLVE_COV = 2 };
 int64_t pgb_solve_ws_bytes(int32_t m, int32_t nb);
 int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r, int32_t share_gram,
-              const double* EtE, const double* hv, const double* tau, int32_t p,
+              const double* EtE, const double* EtE_null, const double* hv, const double* tau, int32_t p,
               const double* beta_prev, int32_t share_prev, int32_t flags, double* out,
               double* cov_out, void* ws, int64_t ws_bytes, void* stream);
 

@@ -163,7 +163,8 @@ __device__ void transpose_inplace(double* B, int m) {
 
 __global__ void __launch_bounds__(kSolveThreads)
 solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__ r_all, int share_gram,
-             const double* __restrict__ EtE_all, const double* __restrict__ hv,
+             const double* __restrict__ EtE_all, const double* __restrict__ Enull_all,
+             const double* __restrict__ hv,
              const double* __restrict__ tau, int p, const double* __restrict__ beta_prev_all,
              int share_prev, double* __restrict__ out_all, double* __restrict__ cov_all,
              double* __restrict__ ws_all, int flags, int use_smem) {
@@ -173,6 +174,7 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   const double* G = G_all + (share_gram ? 0 : (size_t)sys * mm);
   const double* r = r_all + (share_gram ? 0 : (size_t)sys * m);
   const double* EtE = EtE_all + (size_t)sys * mm;
+  const double* Enull = Enull_all ? Enull_all + (size_t)sys * mm : nullptr;
   const double* beta_prev = beta_prev_all ? beta_prev_all + (share_prev ? 0 : (size_t)sys * m) : nullptr;
   double* out = out_all + (size_t)sys * (m + PGB_SOLVE_OUT_EXTRA);
   // small vectors always live in shared memory
@@ -187,12 +189,13 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   if (threadIdx.x == 0) *flag = 0;
   __syncthreads();
 
-  // ---- B = Q^T G Q with the null block zeroed; A = Q^T EtE Q + B ----
+  // ---- A = Q^T E_rest Q + [Q^T E_null Q]_0 + [Q^T G Q]_0, where [.]_0 zeroes the first p rows and
+  //      columns: both E_null and G annihilate the null vectors in exact arithmetic.  B ends up
+  //      holding [Q^T G Q]_0 for the edof / cov step. ----
   int bad = 0;
   for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) {
-    const double g = G[e], pe = EtE[e];
-    if (!isfinite(g) || !isfinite(pe)) bad = 1;
-    B[e] = g;
+    const double pe = EtE[e];
+    if (!isfinite(pe)) bad = 1;
     A[e] = pe;
   }
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
@@ -201,14 +204,27 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   }
   if (bad) *flag = 2;
   __syncthreads();
-  if (*flag == 0) {
+  for (int q = 0; q < p && *flag == 0; ++q) {
+    for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = hv[(size_t)q * m + i];
+    __syncthreads();
+    sym_reflect(A, m, v, tau[q], w, red);
+    vec_reflect(x, m, v, tau[q], red);
+  }
+  for (int pass = (Enull ? 0 : 1); pass < 2; ++pass) {
+    const double* src = (pass == 0) ? Enull : G;
+    bad = 0;
+    for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) {
+      const double g = src[e];
+      if (!isfinite(g)) bad = 1;
+      B[e] = g;
+    }
+    if (bad) *flag = 2;
+    __syncthreads();
+    if (*flag != 0) break;
     for (int q = 0; q < p; ++q) {
       for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = hv[(size_t)q * m + i];
       __syncthreads();
-      const double t = tau[q];
-      sym_reflect(B, m, v, t, w, red);
-      sym_reflect(A, m, v, t, w, red);
-      vec_reflect(x, m, v, t, red);
+      sym_reflect(B, m, v, tau[q], w, red);
     }
     for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) {
       const int i = e / m, j = e - i * m;
@@ -216,6 +232,9 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
       if (i < p || j < p) { g = 0.0; B[e] = 0.0; }
       A[e] += g;
     }
+    __syncthreads();
+  }
+  if (*flag == 0) {
     for (int i = threadIdx.x; i < p; i += blockDim.x) x[i] = 0.0;
     __syncthreads();
     cholesky_lower(A, m, col, flag);
@@ -293,8 +312,8 @@ extern "C" int64_t pgb_solve_ws_bytes(int32_t m, int32_t nb) {
 }
 
 extern "C" int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r, int32_t share_gram,
-                         const double* EtE, const double* hv, const double* tau, int32_t p,
-                         const double* beta_prev, int32_t share_prev, int32_t flags, double* out,
+                         const double* EtE, const double* EtE_null, const double* hv, const double* tau,
+                         int32_t p, const double* beta_prev, int32_t share_prev, int32_t flags, double* out,
                          double* cov_out, void* ws, int64_t ws_bytes, void* stream) {
   if (m < 1 || nb < 1 || !G || !r || !EtE || !out || p < 0 || p > m || (p > 0 && (!hv || !tau))) {
     pgb_set_error("pgb_solve: bad arguments");
@@ -312,7 +331,7 @@ extern "C" int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r
     PGB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax));
     attr_set = true;
   }
-  solve_kernel<<<nb, kSolveThreads, smem, (cudaStream_t)stream>>>(m, G, r, share_gram, EtE, hv, tau, p, beta_prev,
+  solve_kernel<<<nb, kSolveThreads, smem, (cudaStream_t)stream>>>(m, G, r, share_gram, EtE, EtE_null, hv, tau, p, beta_prev,
                                                                   share_prev, out, cov_out, (double*)ws, flags,
                                                                   in_smem ? 1 : 0);
   pgb_count_launch(1);

@@ -201,6 +201,8 @@ class Engine:
         self.beta = torch.zeros(m, **f64)
         self.beta_prev = torch.zeros(m, **f64)
         self.EtE = torch.zeros(m * m, **f64)
+        self.EtE_null = torch.zeros(m * m, **f64)
+        self._has_null_part = False
         self.sol = torch.zeros(m + _lib.SOLVE_OUT_EXTRA, **f64)
         self.cov = None
         self.stat_scalars = torch.zeros(_lib.SS_COUNT, **f64)
@@ -274,8 +276,13 @@ class Engine:
     def gram_scalars(self):
         return self.out[self.m * self.m + self.m:].cpu().numpy()
 
-    def set_penalty(self, EtE):
+    def set_penalty(self, EtE, EtE_null=None):
+        """penalty of the m x m system as EtE + EtE_null; EtE_null holds the components that
+        annihilate the analytic null vectors structurally (see pgb_solve in include/pgb.h)"""
         self.EtE.copy_(torch.from_numpy(np.ascontiguousarray(EtE, dtype=np.float64).ravel()))
+        self._has_null_part = EtE_null is not None
+        if EtE_null is not None:
+            self.EtE_null.copy_(torch.from_numpy(np.ascontiguousarray(EtE_null, dtype=np.float64).ravel()))
 
     def chol_ok(self, A):
         """True when A (host, m x m) has a Cholesky factor: utils.cholesky (utils.py:77-91)"""
@@ -301,7 +308,9 @@ class Engine:
             prev = self.beta_prev
         G = self.out
         r = self.out[m * m:]
-        _lib.check(self.lib.pgb_solve(m, 1, _ptr(G), _ptr(r), 1, _ptr(self.EtE), _ptr(self.hv), _ptr(self.tau),
+        _lib.check(self.lib.pgb_solve(m, 1, _ptr(G), _ptr(r), 1, _ptr(self.EtE),
+                                      _ptr(self.EtE_null) if self._has_null_part else C.c_void_p(0),
+                                      _ptr(self.hv), _ptr(self.tau),
                                       self.p, _ptr(prev), 1, flags, _ptr(self.sol),
                                       _ptr(self.cov) if want_cov else C.c_void_p(0), _ptr(self._solve_ws),
                                       self._solve_ws.numel() * 8, _stream()), "pgb_solve")

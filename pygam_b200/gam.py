@@ -351,12 +351,12 @@ class GAM:
         assert np.isfinite(self.coef_).all(), f"coefficients should be well-behaved, but found: {self.coef_}"
         self.coef_ = np.asarray(self.coef_, dtype=np.float64)
 
-        P = self.terms.build_penalties()
+        Pn, Pr = self.terms.build_penalties(split=True)
         S = np.eye(m) * np.sqrt(EPS)
         constrained = self.terms.hasconstraint
         if not constrained:
-            EtE = self._cholesky_check(eng, S + P)
-            eng.set_penalty(EtE)
+            EtE = self._cholesky_check(eng, S + (Pn + Pr))
+            eng.set_penalty(EtE - Pn, Pn)
 
         cache_ok = self._coef_independent_gram() and not constrained
         cache = getattr(self, "_gram_cache", None) if cache_ok else None
@@ -365,10 +365,13 @@ class GAM:
         diff = np.inf
         for _ in range(self.max_iter):
             if constrained:
-                P = self.terms.build_penalties()
-                C = self.terms.build_constraints(self.coef_, self._constraint_lam, self._constraint_l2)
-                EtE = self._cholesky_check(eng, S + P + C)
-                eng.set_penalty(EtE)
+                Pn, Pr = self.terms.build_penalties(split=True)
+                Cn, Cr = self.terms.build_constraints(self.coef_, self._constraint_lam, self._constraint_l2,
+                                                      split=True)
+                # the reference factors S + P + C (pygam.py:758-761); any diagonal loading its
+                # retry loop adds lands in the part that is not null-annihilating
+                EtE = self._cholesky_check(eng, S + (Pn + Pr) + (Cn + Cr))
+                eng.set_penalty(EtE - (Pn + Cn), Pn + Cn)
 
             if cache is not None:
                 # G, r cached on the device; only the log scalars need the data (O(k) pass)

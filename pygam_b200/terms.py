@@ -118,12 +118,15 @@ class Term:
         return self
 
     # -- m x m pieces --
-    def build_penalties(self):
-        """sum_k lam_k * penalty_k(n_coefs) (terms.py:307-349)"""
+    def build_penalties(self, split=False):
+        """sum_k lam_k * penalty_k(n_coefs) (terms.py:307-349).  With split=True returns the sum
+        as (null_part, rest): null_part collects the components that annihilate the constant
+        vector of the block (difference penalties), see ``split_by_constant``."""
         if self.isintercept:
-            return np.array([[0.0]])
+            return (np.array([[0.0]]), np.array([[0.0]])) if split else np.array([[0.0]])
         n = self.n_coefs
         total = np.zeros((n, n))
+        parts = []
         for pen, lam in zip(self.penalties, self.lam):
             if pen == "auto":
                 if self.dtype == "numerical":
@@ -136,24 +139,48 @@ class Term:
             if pen is None:
                 pen = "none"
             fn = _pen.PENALTIES[pen] if isinstance(pen, str) else pen
-            total = total + np.multiply(np.asarray(_dense(fn(n, None)), dtype=np.float64), lam)
-        return total
+            comp = np.multiply(np.asarray(_dense(fn(n, None)), dtype=np.float64), lam)
+            total = total + comp
+            parts.append(comp)
+        return split_by_constant(parts, n) if split else total
 
-    def build_constraints(self, coef, constraint_lam, constraint_l2):
+    def build_constraints(self, coef, constraint_lam, constraint_l2, split=False):
         """sum_k constraint_k(n, coef) * constraint_lam, plus constraint_l2 * I on a block
         with violations (terms.py:351-396)"""
         if self.isintercept:
-            return np.array([[0.0]])
+            return (np.array([[0.0]]), np.array([[0.0]])) if split else np.array([[0.0]])
         n = self.n_coefs
         total = np.zeros((n, n))
+        parts = []
         for c in self.constraints:
             if c is None:
                 c = "none"
             fn = _pen.CONSTRAINTS[c] if isinstance(c, str) else c
-            total = total + np.asarray(_dense(fn(n, coef)), dtype=np.float64) * constraint_lam
+            comp = np.asarray(_dense(fn(n, coef)), dtype=np.float64) * constraint_lam
+            total = total + comp
+            parts.append(comp)
         if np.count_nonzero(total) > 0:
             total = total + constraint_l2 * np.eye(n)
-        return total
+            parts.append(constraint_l2 * np.eye(n))
+        return split_by_constant(parts, n) if split else total
+
+
+def split_by_constant(parts, n):
+    """(sum of the components P with P @ 1 == 0, sum of the others).  Difference penalties and
+    the D M D^T constraint penalties are integer matrices times a scalar, so P @ 1 is zero to
+    rounding; an l2 component is not.  The solver zeroes the null block of the first sum after
+    its change of basis (include/pgb.h, pgb_solve)."""
+    null, rest = np.zeros((n, n)), np.zeros((n, n))
+    ones = np.ones(n)
+    for comp in parts:
+        scale = np.abs(comp).max()
+        if scale == 0.0:
+            continue
+        if np.abs(comp @ ones).max() <= 1e-13 * scale and np.abs(ones @ comp).max() <= 1e-13 * scale:
+            null += comp
+        else:
+            rest += comp
+    return null, rest
 
 
 def _dense(a):
@@ -352,30 +379,38 @@ class TensorTerm(Term):
             raise ValueError(f"by variable requires feature {self.by}, but X has only {X.shape[1]} dimensions")
         return self
 
-    def build_penalties(self):
+    def build_penalties(self, split=False):
         """sum_i I x ... x P_i x ... x I (terms.py:1479-1517)"""
         total = 0
+        parts = []
         for i in range(len(self._terms)):
             acc = None
             for j, t in enumerate(self._terms):
                 Pj = t.build_penalties() if j == i else np.eye(t.n_coefs)
                 acc = Pj if acc is None else np.kron(acc, Pj)
             total = total + acc
-        return total
+            parts.append(acc)
+        return split_by_constant(parts, self.n_coefs) if split else total
 
-    def build_constraints(self, coef, constraint_lam, constraint_l2):
+    def build_constraints(self, coef, constraint_lam, constraint_l2, split=False):
         """every 1-d slice of the coefficient tensor along each marginal gets that marginal's
         constraint matrix (terms.py:1519-1609)"""
         dims = [t.n_coefs for t in self._terms]
         size = int(np.prod(dims))
         C = np.zeros((size, size))
+        Cn = np.zeros((size, size))
         idx = np.arange(size).reshape(dims)
         coef = np.asarray(coef)
         for i, t in enumerate(self._terms):
             slices = np.moveaxis(idx, i, 0).reshape(dims[i], size // dims[i])
             for sl in slices.T:
-                C[np.ix_(sl, sl)] += t.build_constraints(coef[sl], constraint_lam, constraint_l2)
-        return C
+                if split:
+                    a, b = t.build_constraints(coef[sl], constraint_lam, constraint_l2, split=True)
+                    Cn[np.ix_(sl, sl)] += a
+                    C[np.ix_(sl, sl)] += b
+                else:
+                    C[np.ix_(sl, sl)] += t.build_constraints(coef[sl], constraint_lam, constraint_l2)
+        return (Cn, C) if split else C
 
 
 def _check_int(v, name, min_val):
@@ -562,18 +597,26 @@ class TermList:
         return feats
 
     # ---- m x m pieces ----
-    def build_penalties(self):
-        """block-diagonal penalty matrix P (terms.py:1925-1947), dense (m, m)"""
+    def build_penalties(self, split=False):
+        """block-diagonal penalty matrix P (terms.py:1925-1947), dense (m, m); split=True returns
+        (P_null, P_rest) with P = P_null + P_rest (see ``split_by_constant``)"""
+        if split:
+            parts = [t.build_penalties(split=True) for t in self._terms]
+            return (scipy.linalg.block_diag(*[a for a, _ in parts]),
+                    scipy.linalg.block_diag(*[b for _, b in parts]))
         return scipy.linalg.block_diag(*[t.build_penalties() for t in self._terms])
 
-    def build_constraints(self, coef, constraint_lam, constraint_l2):
+    def build_constraints(self, coef, constraint_lam, constraint_l2, split=False):
         """block-diagonal constraint matrix C (terms.py:1949-1979), dense (m, m)"""
         coef = np.asarray(coef, dtype=np.float64).ravel()
         blocks, start = [], 0
         for t in self._terms:
             n = t.n_coefs
-            blocks.append(t.build_constraints(coef[start:start + n], constraint_lam, constraint_l2))
+            blocks.append(t.build_constraints(coef[start:start + n], constraint_lam, constraint_l2, split=split))
             start += n
+        if split:
+            return (scipy.linalg.block_diag(*[a for a, _ in blocks]),
+                    scipy.linalg.block_diag(*[b for _, b in blocks]))
         return scipy.linalg.block_diag(*blocks)
 
     def null_vectors(self):

@@ -60,7 +60,7 @@ def householder(N):
     return V, tau
 
 
-def solve_mirror(G, r, EtE, V, tau, want_cov=False):
+def solve_mirror(G, r, EtE, V, tau, want_cov=False, EtE_null=None):
     """numpy mirror of solve_kernel (pgb_solve.cu)"""
     m = len(r)
     p = len(tau)
@@ -71,6 +71,11 @@ def solve_mirror(G, r, EtE, V, tau, want_cov=False):
     Gt[:p, :] = 0.0
     Gt[:, :p] = 0.0
     A = Q.T @ EtE @ Q + Gt
+    if EtE_null is not None:
+        En = Q.T @ EtE_null @ Q
+        En[:p, :] = 0.0
+        En[:, :p] = 0.0
+        A = A + En
     x = Q.T @ r
     x[:p] = 0.0
     if not (np.isfinite(G).all() and np.isfinite(EtE).all() and np.isfinite(r).all()):
@@ -100,6 +105,7 @@ class OracleEngine:
         m = self.m
         self.out = torch.zeros(m * m + m + _lib.GS_COUNT, dtype=torch.float64)
         self.EtE = np.zeros((m, m))
+        self.EtE_null = None
         self._mm_cache = None
 
     def _modelmat(self, data):
@@ -152,8 +158,9 @@ class OracleEngine:
     def gram_scalars(self):
         return self.out[self.m * self.m + self.m:].numpy().copy()
 
-    def set_penalty(self, EtE):
+    def set_penalty(self, EtE, EtE_null=None):
         self.EtE = np.array(EtE, dtype=np.float64)
+        self.EtE_null = None if EtE_null is None else np.array(EtE_null, dtype=np.float64)
 
     def chol_ok(self, A):
         try:
@@ -167,7 +174,7 @@ class OracleEngine:
         o = self.out.numpy()
         G = o[: m * m].reshape(m, m)
         r = o[m * m: m * m + m]
-        res = solve_mirror(G, r, self.EtE, self.V, self.tau, want_cov=want_cov)
+        res = solve_mirror(G, r, self.EtE, self.V, self.tau, want_cov=want_cov, EtE_null=self.EtE_null)
         if res["info"] != 0:
             return dict(info=res["info"], coef=np.full(m, np.nan), edof=np.nan, diff=np.nan)
         res["diff"] = np.nan

@@ -53,7 +53,7 @@ def test_basis_known_answers(name):
     B = eng.model_matrix(data).cpu().numpy()
     ref = g[name + "_B"]
     assert B.shape == ref.shape
-    np.testing.assert_allclose(B, ref, rtol=0, atol=2e-14)
+    np.testing.assert_allclose(B, ref, rtol=2e-13, atol=2e-14)
 
 
 @pytest.mark.parametrize("name", sorted(cases.FIT_CASES))
@@ -121,7 +121,8 @@ def test_stats_pass_matches_oracle(name):
         assert abs(sc[k] - scr[k]) <= 1e-11 * max(1.0, abs(scr[k])), (k, sc[k], scr[k])
 
 
-@pytest.mark.parametrize("name", ["c1_wage", "c2_logistic", "c3_poisson", "mixed_terms", "no_intercept"])
+@pytest.mark.parametrize("name", ["c1_wage", "c2_logistic", "c3_poisson", "mixed_terms", "no_intercept",
+                                  "c5_expectile"])
 def test_solve_matches_numpy_mirror(name):
     case = cases.FIT_CASES[name]
     g = load("fit_" + name)
@@ -129,12 +130,18 @@ def test_solve_matches_numpy_mirror(name):
     m = eng.m
     cpu = _cpu_data(g, case)
     out = ora.gram_pass(cpu, g["coef"]).numpy().copy()
-    EtE = np.eye(m) * np.sqrt(orc.EPS) + gam._P()
+    Pn, Pr = gam.terms.build_penalties(split=True)
+    np.testing.assert_array_equal(Pn + Pr, gam._P())
+    if gam.terms.hasconstraint:  # 1e9-stiff constraint penalty, all of it null-annihilating
+        Cn, Cr = gam.terms.build_constraints(g["coef"], gam._constraint_lam, gam._constraint_l2, split=True)
+        Pn, Pr = Pn + Cn, Pr + Cr
+        assert np.abs(Cn).max() >= 1e9
+    EtE = np.eye(m) * np.sqrt(orc.EPS) + Pr
     eng.out.copy_(torch.from_numpy(out))
-    eng.set_penalty(EtE)
+    eng.set_penalty(EtE, Pn)
     sol = eng.solve(coef_prev=g["coef"], want_edof=True, want_cov=True)
     V, tau = householder(gam.terms.null_vectors())
-    ref = solve_mirror(out[:m * m].reshape(m, m), out[m * m:m * m + m], EtE, V, tau, want_cov=True)
+    ref = solve_mirror(out[:m * m].reshape(m, m), out[m * m:m * m + m], EtE, V, tau, want_cov=True, EtE_null=Pn)
     assert sol["info"] == 0
     Pz = helpers.identifiable_projector(gam)
     assert np.linalg.norm(Pz @ (sol["coef"] - ref["coef"])) <= 1e-10 * np.linalg.norm(ref["coef"])
