@@ -92,6 +92,10 @@ int pgb_model_create(const pgb_term* terms, int32_t n_terms, int32_t n_features,
                      int32_t link, double levels, double expectile, int32_t device,
                      pgb_model** out);
 void pgb_model_destroy(pgb_model* model);
+/* Host-only planning of the Gram pass (no CUDA call): fills info; *coverage_errors = entries of
+ * the upper triangle of [G | r] not produced by exactly one accumulator element (0 = valid). */
+int pgb_model_plan_host(const pgb_term* terms, int32_t n_terms, int32_t n_features,
+                        pgb_model_info* info, int32_t* coverage_errors);
 int pgb_model_get_info(const pgb_model* model, pgb_model_info* info);
 
 /* gen_edge_knots (pygam/utils.py:592-621): per-feature min and max.  minmax: 2*F doubles

@@ -68,6 +68,8 @@ SYMBOLS = {
     "pgb_model_create": (C.c_int, [C.POINTER(PgbTerm), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_double, C.c_double, C.c_int32, C.POINTER(_P)]),
     "pgb_model_destroy": (None, [_P]),
+    "pgb_model_plan_host": (C.c_int, [C.POINTER(PgbTerm), C.c_int32, C.c_int32, C.POINTER(PgbModelInfo),
+                                      C.POINTER(C.c_int32)]),
     "pgb_model_get_info": (C.c_int, [_P, C.POINTER(PgbModelInfo)]),
     "pgb_col_stats_ws_bytes": (C.c_int64, [C.c_int32]),
     "pgb_col_stats": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P, C.c_int64, _P]),

@@ -26,8 +26,15 @@ struct DMarg {
 
 struct DTerm {
   int32_t kind, n_marg, by, drop_first, coef_offset, n_coefs, nnz, slot0;
+  // placement of the term's coefficients inside its column chunk of the Gram accumulators
+  // (pgb_internal.h): natural pos = pos_base + i, interleaved pos = 16 (i / 4) + pos_base + i % 4
+  int32_t chunk, pos_base, pos_mode, pad;
   DMarg marg[PGB_MAX_MARG];
 };
+
+__host__ __device__ __forceinline__ int term_pos(int pos_base, int pos_mode, int i) {
+  return pos_mode ? (((i >> 2) << 4) + pos_base + (i & 3)) : (pos_base + i);
+}
 
 struct Family {
   int32_t dist, link;

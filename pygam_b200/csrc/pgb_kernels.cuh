@@ -1,0 +1,50 @@
+// pgb_kernels.cuh -- small device helpers shared by the translation units of libpgb.
+#pragma once
+#include "pgb_device.cuh"
+
+static const int kSMs = 148;                 // B200
+static const size_t kSmemMax = 227 * 1024;   // opt-in shared memory per CTA on sm_100
+static const int kPassThreads = 256;
+
+// deterministic block reduction of S per-thread sums -> dst[0..S)
+template <int S>
+__device__ __forceinline__ void block_reduce_store(double (&acc)[S], double* red /* S*32 smem */,
+                                                   double* dst) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    double v = acc[s];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[s * 32 + warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < S) {
+    double v = 0.0;
+    for (int w = 0; w < nw; ++w) v += red[threadIdx.x * 32 + w];
+    dst[threadIdx.x] = v;
+  }
+}
+
+// sum `count` partial vectors of length S in a fixed order: out[s] (+)= sum_c part[c*S+s]
+static __global__ void scalar_reduce_kernel(const double* __restrict__ part, int count, int S,
+                                            double* __restrict__ out, int accumulate) {
+  const int s = threadIdx.x;
+  if (s >= S) return;
+  double v = accumulate ? out[s] : 0.0;
+  for (int c = 0; c < count; ++c) v += part[(int64_t)c * S + s];
+  out[s] = v;
+}
+
+struct EmitLp {
+  const double* beta;
+  double lp;
+  __device__ __forceinline__ void operator()(int c, double v) { lp = fma(v, beta[c], lp); }
+};
+
+__device__ __forceinline__ void load_terms_smem(DTerm* s_terms, const DTerm* g_terms, int n_terms) {
+  const int words = n_terms * (int)(sizeof(DTerm) / 4);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(g_terms);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(s_terms);
+  for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+}
