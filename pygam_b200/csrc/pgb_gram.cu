@@ -169,6 +169,7 @@ int pgb_plan_gram(pgb_model* M) {
     r.n_slots = slot;
     r.needs_all_terms = all_terms ? 1 : 0;
     r.rhs_pos = M->chunks.back().pad0;
+    r.rhs_slot = rhs_slot;
     for (int q = 0; q < r.n_units; ++q) {
       DUnit& u = M->units[r.unit0 + q];
       u.rslot = slot_of[u.row_term];
@@ -184,7 +185,9 @@ int pgb_plan_gram(pgb_model* M) {
   for (;;) {
     smem = 0;
     for (const DRole& r : M->roles) {
-      smem = std::max(smem, (size_t)r.acc_size * 8 + (size_t)tile * rec_row_bytes(r.n_slots) + fixed);
+      size_t need = (size_t)r.acc_size * 8 + (size_t)tile * rec_row_bytes(r.n_slots) + fixed;
+      if (M->roles.size() == 1) need += (size_t)tile * r.n_rterms * 8;  // lp_part of the inline IRLS step
+      smem = std::max(smem, need);
       max_units = std::max(max_units, r.n_units);
     }
     if (smem <= kSmemMax || tile <= 32) break;
@@ -402,7 +405,8 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
   double* acc = reinterpret_cast<double*>(smem_raw);
   double* rec_val = acc + role.acc_size;
   double* rec_w = rec_val + (size_t)T * S;
-  double* s_beta = rec_w + T;
+  double* lp_part = rec_w + T;  // [n_rterms][T], only when the role computes the IRLS step inline
+  double* s_beta = lp_part + (inline_irls ? (size_t)T * role.n_rterms : 0);
   double* s_red = s_beta + ((m + 1) & ~1);
   DTerm* s_terms = reinterpret_cast<DTerm*>(s_red + PGB_GS_COUNT * 32);
   uint16_t* rec_pos = reinterpret_cast<uint16_t*>(s_terms + n_terms);
@@ -433,29 +437,33 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
   for (int64_t tile = tiles_lo; tile < tiles_hi; ++tile) {
     const int64_t row0 = tile * T;
     const int tile_n = (int)min((int64_t)T, n - row0);
-    // ---------------- phase A: one thread per row ----------------
+    // ---------------- phase A: one thread per (row, term) ----------------
+    // consecutive threads take consecutive rows of the same term: coalesced feature loads and
+    // every warp of the CTA busy even when the tile is smaller than the block
+    const int n_items = tile_n * role.n_rterms;
+    for (int item = tid; item < n_items; item += blockDim.x) {
+      const int q = item / tile_n;
+      const int rI = item - q * tile_n;
+      const DRoleTerm rt = g_rterms[role.term0 + q];
+      if (rt.term < 0) continue;  // the rhs slot is filled with the row's weight below
+      const int64_t i = row0 + rI;
+      const DTerm& d = s_terms[rt.term];
+      EmitRec e{rec_val + (size_t)rI * S, rec_pos + (size_t)rI * S, rec_ri + (size_t)rI * S,
+                inline_irls ? s_beta : nullptr, 0.0, rt.slot0, d.coef_offset, d.pos_base, d.pos_mode};
+      eval_term(d, X, ld, i, e);
+      if (inline_irls) lp_part[(size_t)q * T + rI] = e.lp;
+    }
+    if (inline_irls) __syncthreads();
     for (int rI = tid; rI < tile_n; rI += blockDim.x) {
       const int64_t i = row0 + rI;
-      double* rv = rec_val + (size_t)rI * S;
-      uint16_t* rp = rec_pos + (size_t)rI * S;
-      uint16_t* rr = rec_ri + (size_t)rI * S;
-      EmitRec e{rv, rp, rr, inline_irls ? s_beta : nullptr, 0.0, 0, 0, 0, 0};
-      int rhs_slot = -1;
-      for (int q = 0; q < role.n_rterms; ++q) {
-        const DRoleTerm rt = g_rterms[role.term0 + q];
-        if (rt.term < 0) { rhs_slot = rt.slot0; continue; }
-        const DTerm& d = s_terms[rt.term];
-        e.q = rt.slot0;
-        e.coef_offset = d.coef_offset;
-        e.pos_base = d.pos_base;
-        e.pos_mode = d.pos_mode;
-        eval_term(d, X, ld, i, e);
-      }
       double om, z;
       if (inline_irls) {
+        double lp = 0.0;
+        for (int q = 0; q < role.n_rterms; ++q)
+          if (g_rterms[role.term0 + q].term >= 0) lp += lp_part[(size_t)q * T + rI];
         const double yi = __ldg(y + i);
         if (mode == PGB_MODE_IRLS) {
-          const IrlsRow r = irls_row(fam, e.lp, yi, weight_inv(w, i));
+          const IrlsRow r = irls_row(fam, lp, yi, weight_inv(w, i));
           om = r.omega;
           z = r.z;
           if (r.keep) {
@@ -475,10 +483,10 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
         om = t2.x;
         z = t2.y;
       }
-      if (rhs_slot >= 0) {
-        rv[rhs_slot] = z;
-        rp[rhs_slot] = (uint16_t)role.rhs_pos;
-        rr[rhs_slot] = 0;
+      if (role.rhs_slot >= 0) {
+        rec_val[(size_t)rI * S + role.rhs_slot] = z;
+        rec_pos[(size_t)rI * S + role.rhs_slot] = (uint16_t)role.rhs_pos;
+        rec_ri[(size_t)rI * S + role.rhs_slot] = 0;
       }
       rec_w[rI] = om;
     }

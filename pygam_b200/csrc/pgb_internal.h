@@ -51,7 +51,7 @@ struct DRole {
   int32_t n_slots;             // record slots per data row
   int32_t needs_all_terms;     // role evaluates every term (inline IRLS possible)
   int32_t cta0, n_ctas;        // CTAs of the 1-d grid that work for this role
-  int32_t rhs_pos, pad_;       // physical column of the virtual rhs slot inside its chunk
+  int32_t rhs_pos, rhs_slot;   // physical column / record slot of the virtual rhs entry (-1: none)
   int64_t acc_size;            // doubles of the role's accumulator
   int64_t part_off;            // offset of the role's first partial inside the workspace (doubles)
   int64_t map_off;             // offset of the role's element map

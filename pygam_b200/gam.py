@@ -448,7 +448,8 @@ class GAM:
             dist.scale = float(np.sqrt(sc[_lib.SS_PEARSON] / (n - st["edof"])))  # distributions.py:78
         st["scale"] = dist.scale
         st["cov"] = sol["cov"] * dist.scale ** 2
-        st["se"] = st["cov"].diagonal() ** 0.5
+        # cov = A^-1 G A^-1 is positive semi-definite; clamp the -1e-20 rounding of a zero variance
+        st["se"] = np.maximum(st["cov"].diagonal(), 0.0) ** 0.5
         # second O(k) pass: log-likelihood and the null model need scale and mean(y)
         ybar = sc[_lib.SS_SUMY] / n
         sc2, _, _ = eng.stats_pass(data, self.coef_, scale=dist.scale, ybar=ybar,
