@@ -302,6 +302,7 @@ __device__ __forceinline__ double dist_logpdf(const Family& f, double y, double 
 // the elementwise IRLS step of one row (pygam.py:764-777, 580-663, 3419-3460)
 // ----------------------------------------------------------------------------------------
 struct IrlsRow {
+  double sw;     // W (the square root of the IRLS weight) of a kept row, 0 for a masked row
   double omega;  // W^2 of the kept row, 0 for a masked row
   double z;      // working response lp + (y - mu) g'(mu), 0 for a masked row
   double mu;
@@ -322,6 +323,7 @@ __device__ __forceinline__ IrlsRow irls_row(const Family& f, double lp, double y
   }
   r.keep = (fabs(Wd) >= PGB_SQRT_EPS) && isfinite(Wd);  // GAM._mask, pygam.py:657
   r.mu = mu;
+  r.sw = r.keep ? Wd : 0.0;
   r.omega = r.keep ? Wd * Wd : 0.0;
   r.z = r.keep ? lp + (y - mu) * g : 0.0;  // GAM._pseudo_data, pygam.py:597
   return r;

@@ -39,6 +39,7 @@ static size_t role_fixed_smem(const pgb_model* M) {
   return (size_t)M->n_terms * sizeof(DTerm) + (size_t)M->m * 8 + PGB_GS_COUNT * 32 * 8 + 512;
 }
 static size_t rec_row_bytes(int n_slots) { return (size_t)n_slots * 12 + 8; }
+static int padded_nnz(const DTerm& t) { return (t.nnz + 1) & ~1; }  // record slots of a term (even)
 
 int pgb_plan_gram(pgb_model* M) {
   const int m = M->m, nt = M->n_terms;
@@ -50,12 +51,12 @@ int pgb_plan_gram(pgb_model* M) {
     DChunk c{};
     c.first_term = t;
     const bool inter = term_interleavable(T[t]);
-    int slots = T[t].nnz, nterms = 1;
+    int slots = padded_nnz(T[t]), nterms = 1;
     ++t;
-    while (t < nt && slots + T[t].nnz <= 16) {
+    while (t < nt && slots + padded_nnz(T[t]) <= 16) {
       if (inter && (!term_interleavable(T[t]) || nterms >= 4)) break;
       if (!inter && nterms >= 16) break;
-      slots += T[t].nnz;
+      slots += padded_nnz(T[t]);
       ++nterms;
       ++t;
     }
@@ -100,7 +101,8 @@ int pgb_plan_gram(pgb_model* M) {
       u.nnz_r = T[j].nnz;
       u.clen = c.n_slots;
       u.cmin = 0;
-      if (g == T[j].chunk) u.cmin = T[j].slot0 - T[c.first_term].slot0;
+      if (g == T[j].chunk)
+        for (int q = c.first_term; q < j; ++q) u.cmin += padded_nnz(T[q]);
       u.width = c.width;
       u.k_rows = T[j].n_coefs;
       all.push_back(u);
@@ -108,7 +110,9 @@ int pgb_plan_gram(pgb_model* M) {
   }
   // ---- pack units into roles
   const size_t fixed = role_fixed_smem(M);
-  const size_t rec_max = rec_row_bytes(M->k + 1);
+  int k_pad = 2;
+  for (const DTerm& d : T) k_pad += padded_nnz(d);
+  const size_t rec_max = rec_row_bytes(k_pad);
   if (fixed + (size_t)32 * rec_max + 8192 > kSmemMax) {
     pgb_set_error("model too wide for the Gram pass: k=%d non-zeros per row", M->k);
     return PGB_EUNSUPPORTED;
@@ -157,13 +161,13 @@ int pgb_plan_gram(pgb_model* M) {
       if (!need[q]) { all_terms = false; continue; }
       M->rterms.push_back(DRoleTerm{q, slot});
       slot_of[q] = slot;
-      slot += T[q].nnz;
+      slot += padded_nnz(T[q]);
     }
     int rhs_slot = -1;
     if (need_rhs) {
       M->rterms.push_back(DRoleTerm{-1, slot});
       rhs_slot = slot;
-      ++slot;
+      slot += 2;
     }
     r.n_rterms = (int)M->rterms.size() - r.term0;
     r.n_slots = slot;
@@ -185,7 +189,7 @@ int pgb_plan_gram(pgb_model* M) {
   for (;;) {
     smem = 0;
     for (const DRole& r : M->roles) {
-      size_t need = (size_t)r.acc_size * 8 + (size_t)tile * rec_row_bytes(r.n_slots) + fixed;
+      size_t need = (size_t)(r.acc_size + 1) * 8 + (size_t)tile * rec_row_bytes(r.n_slots) + fixed;
       if (M->roles.size() == 1) need += (size_t)tile * r.n_rterms * 8;  // lp_part of the inline IRLS step
       smem = std::max(smem, need);
       max_units = std::max(max_units, r.n_units);
@@ -351,7 +355,7 @@ irls_rows_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Family f
       EmitLp e{s_beta, 0.0};
       for (int t = 0; t < n_terms; ++t) eval_term(s_terms[t], X, ld, i, e);
       const IrlsRow r = irls_row(fam, e.lp, yi, weight_inv(w, i));
-      om = r.omega;
+      om = r.sw;
       z = r.z;
       if (r.keep) {
         acc[PGB_GS_NUSED] += 1.0;
@@ -365,28 +369,30 @@ irls_rows_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Family f
       if (!isfinite(z)) acc[PGB_GS_NONFINITE] += 1.0;
     }
     acc[PGB_GS_NROWS] += 1.0;
-    reinterpret_cast<double2*>(wz)[i] = make_double2(om, z);
+    reinterpret_cast<double2*>(wz)[i] = make_double2(om, om * z);  // (sqrt(omega), sqrt(omega) z)
   }
   block_reduce_store<PGB_GS_COUNT>(acc, s_red, part + (int64_t)blockIdx.x * PGB_GS_COUNT);
 }
 
 struct EmitRec {
   double* val;
-  uint16_t* pos;
-  uint16_t* ri;
+  uint32_t* pr;
   const double* beta;
-  double lp;
+  double lp, scale;
   int q, coef_offset, pos_base, pos_mode;
   __device__ __forceinline__ void operator()(int c, double v) {
     const int i = c - coef_offset;
-    val[q] = v;
-    ri[q] = (uint16_t)i;
-    pos[q] = (uint16_t)term_pos(pos_base, pos_mode, i);
+    val[q] = v * scale;
+    pr[q] = (uint32_t)term_pos(pos_base, pos_mode, i) | ((uint32_t)i << 16);
     ++q;
     if (beta) lp = fma(v, beta[c], lp);
   }
 };
 
+// Shared-memory row record of a tile: for every slot of the role, value[slot] = sqrt(omega) * b
+// (the rhs slot holds sqrt(omega) * z) and pr[slot] = physical column | coefficient index << 16.
+// G = sum (sqrt(omega) b)(sqrt(omega) b)^T is then a plain outer product of the record with
+// itself -- the same arithmetic as the reference's W.B (pygam.py:782) before its QR.
 __global__ void __launch_bounds__(512)
 gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const DChunk* __restrict__ g_chunks,
                   const DUnit* __restrict__ g_units, const DRoleTerm* __restrict__ g_rterms,
@@ -395,25 +401,24 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
                   const float* __restrict__ w, const double* __restrict__ beta, const double* __restrict__ wz,
                   int T, double* __restrict__ partials, double* __restrict__ scal_part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // which role does this CTA work for?
   int ridx = 0;
   while (ridx + 1 < n_roles && (int)blockIdx.x >= g_roles[ridx + 1].cta0) ++ridx;
   const DRole role = g_roles[ridx];
   const int cta_in_role = blockIdx.x - role.cta0;
-  const int S = role.n_slots;
+  const int S = role.n_slots;  // even
 
   double* acc = reinterpret_cast<double*>(smem_raw);
-  double* rec_val = acc + role.acc_size;
+  double* rec_val = acc + ((role.acc_size + 1) & ~(int64_t)1);  // 16-byte aligned
   double* rec_w = rec_val + (size_t)T * S;
   double* lp_part = rec_w + T;  // [n_rterms][T], only when the role computes the IRLS step inline
   double* s_beta = lp_part + (inline_irls ? (size_t)T * role.n_rterms : 0);
   double* s_red = s_beta + ((m + 1) & ~1);
   DTerm* s_terms = reinterpret_cast<DTerm*>(s_red + PGB_GS_COUNT * 32);
-  uint16_t* rec_pos = reinterpret_cast<uint16_t*>(s_terms + n_terms);
-  uint16_t* rec_ri = rec_pos + (size_t)T * S;
+  uint32_t* rec_pr = reinterpret_cast<uint32_t*>(s_terms + n_terms);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int64_t i = tid; i < role.acc_size; i += blockDim.x) acc[i] = 0.0;
+  for (int i = tid; i < T * S; i += blockDim.x) { rec_val[i] = 0.0; rec_pr[i] = 0u; }  // pad slots stay zero
   if (inline_irls) for (int i = tid; i < m; i += blockDim.x) s_beta[i] = (mode == PGB_MODE_IRLS) ? beta[i] : 0.0;
   load_terms_smem(s_terms, g_terms, n_terms);
   __syncthreads();
@@ -422,7 +427,7 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
 #pragma unroll
   for (int s = 0; s < PGB_GS_COUNT; ++s) sc[s] = 0.0;
 
-  // rows of this CTA: contiguous slice of [0, n) in units of T rows
+  // rows of this CTA: a contiguous slice of [0, n) in units of T rows
   const int64_t n_tiles = (n + T - 1) / T;
   const int64_t tiles_lo = n_tiles * cta_in_role / role.n_ctas;
   const int64_t tiles_hi = n_tiles * (cta_in_role + 1) / role.n_ctas;
@@ -431,8 +436,12 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
   DUnit u{};
   if (has_unit) u = g_units[role.unit0 + warp];
   const int s16 = lane & 15, h = lane >> 4;
-  const int ncp = (u.clen + 15) >> 4;
   double* uacc = acc + u.off;
+  const int width = u.width;
+  const bool fast = has_unit && u.clen <= 16 && u.nnz_r <= 4;
+  const bool cvalid = has_unit && (s16 < u.clen) && (s16 >= u.cmin);
+  const bool v0 = cvalid && (2 * h < u.nnz_r), v1 = cvalid && (2 * h + 1 < u.nnz_r);
+  const int coff = u.cslot + s16, roff = u.rslot + 2 * h;
 
   for (int64_t tile = tiles_lo; tile < tiles_hi; ++tile) {
     const int64_t row0 = tile * T;
@@ -445,26 +454,32 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
       const int q = item / tile_n;
       const int rI = item - q * tile_n;
       const DRoleTerm rt = g_rterms[role.term0 + q];
-      if (rt.term < 0) continue;  // the rhs slot is filled with the row's weight below
       const int64_t i = row0 + rI;
+      if (rt.term < 0) {  // rhs slot: sqrt(omega) * z (split mode; inline mode fills it below)
+        if (!inline_irls) {
+          rec_val[(size_t)rI * S + rt.slot0] = __ldg(wz + 2 * i + 1);
+          rec_pr[(size_t)rI * S + rt.slot0] = (uint32_t)role.rhs_pos;
+        }
+        continue;
+      }
       const DTerm& d = s_terms[rt.term];
-      EmitRec e{rec_val + (size_t)rI * S, rec_pos + (size_t)rI * S, rec_ri + (size_t)rI * S,
-                inline_irls ? s_beta : nullptr, 0.0, rt.slot0, d.coef_offset, d.pos_base, d.pos_mode};
+      EmitRec e{rec_val + (size_t)rI * S, rec_pr + (size_t)rI * S, inline_irls ? s_beta : nullptr, 0.0,
+                inline_irls ? 1.0 : __ldg(wz + 2 * i), rt.slot0, d.coef_offset, d.pos_base, d.pos_mode};
       eval_term(d, X, ld, i, e);
       if (inline_irls) lp_part[(size_t)q * T + rI] = e.lp;
     }
-    if (inline_irls) __syncthreads();
-    for (int rI = tid; rI < tile_n; rI += blockDim.x) {
-      const int64_t i = row0 + rI;
-      double om, z;
-      if (inline_irls) {
+    if (inline_irls) {
+      __syncthreads();
+      for (int rI = tid; rI < tile_n; rI += blockDim.x) {
+        const int64_t i = row0 + rI;
         double lp = 0.0;
         for (int q = 0; q < role.n_rterms; ++q)
           if (g_rterms[role.term0 + q].term >= 0) lp += lp_part[(size_t)q * T + rI];
         const double yi = __ldg(y + i);
+        double sw, z;
         if (mode == PGB_MODE_IRLS) {
           const IrlsRow r = irls_row(fam, lp, yi, weight_inv(w, i));
-          om = r.omega;
+          sw = r.sw;
           z = r.z;
           if (r.keep) {
             sc[PGB_GS_NUSED] += 1.0;
@@ -472,43 +487,71 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
             sc[PGB_GS_NCORRECT] += (yi == ((r.mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
           }
         } else {
-          om = 1.0;
+          sw = 1.0;
           z = init_response(fam, yi);
           sc[PGB_GS_NUSED] += 1.0;
           if (!isfinite(z)) sc[PGB_GS_NONFINITE] += 1.0;
         }
         sc[PGB_GS_NROWS] += 1.0;
-      } else {
-        const double2 t2 = __ldg(reinterpret_cast<const double2*>(wz) + i);
-        om = t2.x;
-        z = t2.y;
+        rec_w[rI] = sw;
+        if (role.rhs_slot >= 0) {
+          rec_val[(size_t)rI * S + role.rhs_slot] = z;
+          rec_pr[(size_t)rI * S + role.rhs_slot] = (uint32_t)role.rhs_pos;
+        }
       }
-      if (role.rhs_slot >= 0) {
-        rec_val[(size_t)rI * S + role.rhs_slot] = z;
-        rec_pos[(size_t)rI * S + role.rhs_slot] = (uint16_t)role.rhs_pos;
-        rec_ri[(size_t)rI * S + role.rhs_slot] = 0;
-      }
-      rec_w[rI] = om;
+      __syncthreads();
+      // scale the row's record by sqrt(omega)
+      for (int e = tid; e < tile_n * S; e += blockDim.x) rec_val[e] *= rec_w[e / S];
     }
     __syncthreads();
     // ---------------- phase B: one warp per unit ----------------
-    if (has_unit) {
+    if (fast) {
+      // lanes = 16 column slots x 2 row-side pairs (a = 2h, 2h + 1); operands of the next row are
+      // fetched while the read-modify-write of the current row is in flight
+      const double* pv = rec_val;
+      const uint32_t* pp = rec_pr;
+      double cv = pv[coff];
+      uint32_t cpr = pp[coff];
+      double2 rv = *reinterpret_cast<const double2*>(pv + roff);
+      uint2 rpr = *reinterpret_cast<const uint2*>(pp + roff);
       for (int rI = 0; rI < tile_n; ++rI) {
-        const double om = rec_w[rI];
-        if (om == 0.0) continue;
+        const double cv_c = cv;
+        const uint32_t cpr_c = cpr;
+        const double2 rv_c = rv;
+        const uint2 rpr_c = rpr;
+        if (rI + 1 < tile_n) {
+          pv += S;
+          pp += S;
+          cv = pv[coff];
+          cpr = pp[coff];
+          rv = *reinterpret_cast<const double2*>(pv + roff);
+          rpr = *reinterpret_cast<const uint2*>(pp + roff);
+        }
+        const int pos = (int)(cpr_c & 0xffffu);
+        if (v0) {
+          double* g = uacc + (int)(rpr_c.x >> 16) * width + pos;
+          *g = fma(rv_c.x, cv_c, *g);
+        }
+        if (v1) {
+          double* g = uacc + (int)(rpr_c.y >> 16) * width + pos;
+          *g = fma(rv_c.y, cv_c, *g);
+        }
+      }
+    } else if (has_unit) {
+      const int ncp = (u.clen + 15) >> 4;
+      for (int rI = 0; rI < tile_n; ++rI) {
         const double* rv = rec_val + (size_t)rI * S;
-        const uint16_t* rp = rec_pos + (size_t)rI * S;
-        const uint16_t* rr = rec_ri + (size_t)rI * S;
+        const uint32_t* rp = rec_pr + (size_t)rI * S;
         for (int cp = 0; cp < ncp; ++cp) {
           const int cs = (cp << 4) + s16;
           const bool valid = (cs < u.clen) && (cs >= u.cmin);
-          const int pv = valid ? (int)rp[u.cslot + cs] : 0;
+          const int pos = valid ? (int)(rp[u.cslot + cs] & 0xffffu) : 0;
           const double vv = valid ? rv[u.cslot + cs] : 0.0;
           for (int a = h; a < u.nnz_r; a += 2) {
-            const int ri = rr[u.rslot + a];
-            const double wq = om * rv[u.rslot + a];
+            const int ri = (int)(rp[u.rslot + a] >> 16);
+            const double wq = rv[u.rslot + a];
             if (valid) {
-              double* g = uacc + ri * u.width + pv;
+              double* g = uacc + ri * width + pos;
               *g = fma(wq, vv, *g);
             }
           }
