@@ -119,7 +119,8 @@ int pgb_plan_gram(pgb_model* M) {
   }
   int plan_tile = kPlanTile;
   while (plan_tile > 32 && fixed + (size_t)plan_tile * rec_max > kSmemMax / 2) plan_tile >>= 1;
-  const size_t acc_budget = (kSmemMax - fixed - (size_t)plan_tile * rec_max) / 8;  // doubles
+  const size_t acc_budget =
+      (kSmemMax - fixed - (size_t)(plan_tile + 1) * rec_max - (size_t)16 * 32 * kMaxUnitsPerRole) / 8;  // doubles
   M->units.clear();
   M->roles.clear();
   M->rterms.clear();
@@ -189,7 +190,8 @@ int pgb_plan_gram(pgb_model* M) {
   for (;;) {
     smem = 0;
     for (const DRole& r : M->roles) {
-      size_t need = (size_t)(r.acc_size + 1) * 8 + (size_t)tile * rec_row_bytes(r.n_slots) + fixed;
+      size_t need = (size_t)(r.acc_size + 1) * 8 + (size_t)(tile + 1) * rec_row_bytes(r.n_slots) + fixed +
+                    (size_t)16 * 32 * kMaxUnitsPerRole;
       if (M->roles.size() == 1) need += (size_t)tile * r.n_rterms * 8;  // lp_part of the inline IRLS step
       smem = std::max(smem, need);
       max_units = std::max(max_units, r.n_units);
@@ -238,7 +240,7 @@ int pgb_plan_gram(pgb_model* M) {
     moff += r.acc_size;
   }
   M->gram_ctas = cta;
-  M->partial_doubles = poff;
+  M->partial_doubles = (poff + 1) & ~(int64_t)1;  // keeps the (sqrt(omega), z) pairs after it 16-byte aligned
   M->map_size = moff;
   M->pass_ctas = kSMs * 8;
   // ---- element map: accumulator element -> row * (m + 1) + col of [G | r], upper triangle only
@@ -374,6 +376,23 @@ irls_rows_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Family f
   block_reduce_store<PGB_GS_COUNT>(acc, s_red, part + (int64_t)blockIdx.x * PGB_GS_COUNT);
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lds_f64(double& v, uint32_t a) {
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+}
+__device__ __forceinline__ void lds_u32(uint32_t& v, uint32_t a) {
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+}
+__device__ __forceinline__ void lds_v2f64(double& x, double& y, uint32_t a) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ void lds_v2u32(uint32_t& x, uint32_t& y, uint32_t a) {
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a));
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
 struct EmitRec {
   double* val;
   uint32_t* pr;
@@ -383,7 +402,7 @@ struct EmitRec {
   __device__ __forceinline__ void operator()(int c, double v) {
     const int i = c - coef_offset;
     val[q] = v * scale;
-    pr[q] = (uint32_t)term_pos(pos_base, pos_mode, i) | ((uint32_t)i << 16);
+    pr[q] = ((uint32_t)term_pos(pos_base, pos_mode, i) << 3) | ((uint32_t)i << 16);  // 8 * column | row
     ++q;
     if (beta) lp = fma(v, beta[c], lp);
   }
@@ -409,16 +428,17 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
 
   double* acc = reinterpret_cast<double*>(smem_raw);
   double* rec_val = acc + ((role.acc_size + 1) & ~(int64_t)1);  // 16-byte aligned
-  double* rec_w = rec_val + (size_t)T * S;
-  double* lp_part = rec_w + T;  // [n_rterms][T], only when the role computes the IRLS step inline
+  double* rec_w = rec_val + (size_t)(T + 1) * S;  // one spare row: the prefetch of phase B runs one ahead
+  double* dummy = rec_w + T;                        // 2 cells per thread for lanes without work
+  double* lp_part = dummy + 2 * blockDim.x;  // [n_rterms][T], only when the role computes the IRLS step inline
   double* s_beta = lp_part + (inline_irls ? (size_t)T * role.n_rterms : 0);
   double* s_red = s_beta + ((m + 1) & ~1);
   DTerm* s_terms = reinterpret_cast<DTerm*>(s_red + PGB_GS_COUNT * 32);
-  uint32_t* rec_pr = reinterpret_cast<uint32_t*>(s_terms + n_terms);
+  uint32_t* rec_pr = reinterpret_cast<uint32_t*>(s_terms + n_terms);  // (T + 1) rows
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int64_t i = tid; i < role.acc_size; i += blockDim.x) acc[i] = 0.0;
-  for (int i = tid; i < T * S; i += blockDim.x) { rec_val[i] = 0.0; rec_pr[i] = 0u; }  // pad slots stay zero
+  for (int i = tid; i < (T + 1) * S; i += blockDim.x) { rec_val[i] = 0.0; rec_pr[i] = 0u; }  // pad slots stay zero
   if (inline_irls) for (int i = tid; i < m; i += blockDim.x) s_beta[i] = (mode == PGB_MODE_IRLS) ? beta[i] : 0.0;
   load_terms_smem(s_terms, g_terms, n_terms);
   __syncthreads();
@@ -442,6 +462,10 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
   const bool cvalid = has_unit && (s16 < u.clen) && (s16 >= u.cmin);
   const bool v0 = cvalid && (2 * h < u.nnz_r), v1 = cvalid && (2 * h + 1 < u.nnz_r);
   const int coff = u.cslot + s16, roff = u.rslot + 2 * h;
+  const uint32_t smem_cv = smem_u32(rec_val + coff), smem_cp = smem_u32(rec_pr + coff);
+  const uint32_t smem_rv = smem_u32(rec_val + roff), smem_rp = smem_u32(rec_pr + roff);
+  const uint32_t acc_u32 = smem_u32(uacc), w8 = (uint32_t)width * 8u, sb8 = (uint32_t)S * 8u, sb4 = (uint32_t)S * 4u;
+  const uint32_t dummy_u32 = smem_u32(dummy + 2 * tid);
 
   for (int64_t tile = tiles_lo; tile < tiles_hi; ++tile) {
     const int64_t row0 = tile * T;
@@ -458,7 +482,7 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
       if (rt.term < 0) {  // rhs slot: sqrt(omega) * z (split mode; inline mode fills it below)
         if (!inline_irls) {
           rec_val[(size_t)rI * S + rt.slot0] = __ldg(wz + 2 * i + 1);
-          rec_pr[(size_t)rI * S + rt.slot0] = (uint32_t)role.rhs_pos;
+          rec_pr[(size_t)rI * S + rt.slot0] = (uint32_t)role.rhs_pos << 3;
         }
         continue;
       }
@@ -496,7 +520,7 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
         rec_w[rI] = sw;
         if (role.rhs_slot >= 0) {
           rec_val[(size_t)rI * S + role.rhs_slot] = z;
-          rec_pr[(size_t)rI * S + role.rhs_slot] = (uint32_t)role.rhs_pos;
+          rec_pr[(size_t)rI * S + role.rhs_slot] = (uint32_t)role.rhs_pos << 3;
         }
       }
       __syncthreads();
@@ -506,36 +530,36 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
     __syncthreads();
     // ---------------- phase B: one warp per unit ----------------
     if (fast) {
-      // lanes = 16 column slots x 2 row-side pairs (a = 2h, 2h + 1); operands of the next row are
-      // fetched while the read-modify-write of the current row is in flight
-      const double* pv = rec_val;
-      const uint32_t* pp = rec_pr;
-      double cv = pv[coff];
-      uint32_t cpr = pp[coff];
-      double2 rv = *reinterpret_cast<const double2*>(pv + roff);
-      uint2 rpr = *reinterpret_cast<const uint2*>(pp + roff);
+      // lanes = 16 column slots x 2 row-side pairs (a = 2h, 2h + 1).  Explicit shared-space
+      // loads / stores on 32-bit addresses; lanes without work update a private dummy cell so the
+      // loop body is branch-free; the operands of the next row are fetched while the
+      // read-modify-write of the current row is in flight.
+      asm volatile("" ::: "memory");
+      uint32_t a_cv = smem_cv, a_cp = smem_cp, a_rv = smem_rv, a_rp = smem_rp;
+      double cv, rv0, rv1;
+      uint32_t cpr, rp0, rp1;
+      lds_f64(cv, a_cv);
+      lds_u32(cpr, a_cp);
+      lds_v2f64(rv0, rv1, a_rv);
+      lds_v2u32(rp0, rp1, a_rp);
       for (int rI = 0; rI < tile_n; ++rI) {
-        const double cv_c = cv;
-        const uint32_t cpr_c = cpr;
-        const double2 rv_c = rv;
-        const uint2 rpr_c = rpr;
-        if (rI + 1 < tile_n) {
-          pv += S;
-          pp += S;
-          cv = pv[coff];
-          cpr = pp[coff];
-          rv = *reinterpret_cast<const double2*>(pv + roff);
-          rpr = *reinterpret_cast<const uint2*>(pp + roff);
-        }
-        const int pos = (int)(cpr_c & 0xffffu);
-        if (v0) {
-          double* g = uacc + (int)(rpr_c.x >> 16) * width + pos;
-          *g = fma(rv_c.x, cv_c, *g);
-        }
-        if (v1) {
-          double* g = uacc + (int)(rpr_c.y >> 16) * width + pos;
-          *g = fma(rv_c.y, cv_c, *g);
-        }
+        const uint32_t bp = acc_u32 + (cpr & 0xffffu);  // accumulator base + 8 * column
+        uint32_t g0 = (rp0 >> 16) * w8 + bp, g1 = (rp1 >> 16) * w8 + bp;
+        g0 = v0 ? g0 : dummy_u32;
+        g1 = v1 ? g1 : dummy_u32 + 8;
+        const double c_cv = cv, c_rv0 = rv0, c_rv1 = rv1;
+        a_cv += sb8; a_cp += sb4; a_rv += sb8; a_rp += sb4;  // the record buffer has one spare row
+        lds_f64(cv, a_cv);
+        lds_u32(cpr, a_cp);
+        lds_v2f64(rv0, rv1, a_rv);
+        lds_v2u32(rp0, rp1, a_rp);
+        double x0, x1;
+        lds_f64(x0, g0);
+        lds_f64(x1, g1);
+        x0 = fma(c_rv0, c_cv, x0);
+        x1 = fma(c_rv1, c_cv, x1);
+        sts_f64(g0, x0);
+        sts_f64(g1, x1);
       }
     } else if (has_unit) {
       const int ncp = (u.clen + 15) >> 4;
@@ -545,7 +569,7 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
         for (int cp = 0; cp < ncp; ++cp) {
           const int cs = (cp << 4) + s16;
           const bool valid = (cs < u.clen) && (cs >= u.cmin);
-          const int pos = valid ? (int)(rp[u.cslot + cs] & 0xffffu) : 0;
+          const int pos = valid ? (int)((rp[u.cslot + cs] & 0xffffu) >> 3) : 0;
           const double vv = valid ? rv[u.cslot + cs] : 0.0;
           for (int a = h; a < u.nnz_r; a += 2) {
             const int ri = (int)(rp[u.rslot + a] >> 16);
