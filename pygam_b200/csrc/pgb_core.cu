@@ -111,6 +111,7 @@ static int model_build_host(const pgb_term* terms, int32_t n_terms, int32_t n_fe
       return PGB_EINVAL;
     }
     d.nnz = term_nnz(t);
+    d.fast = (t.kind == PGB_TERM_SPLINE && t.order[0] == 3 && !t.periodic[0] && t.by < 0) ? 1 : 0;
     d.slot0 = slot;
     slot += d.nnz;
     coef += t.n_coefs;

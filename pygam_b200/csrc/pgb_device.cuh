@@ -28,7 +28,8 @@ struct DTerm {
   int32_t kind, n_marg, by, drop_first, coef_offset, n_coefs, nnz, slot0;
   // placement of the term's coefficients inside its column chunk of the Gram accumulators
   // (pgb_internal.h): natural pos = pos_base + i, interleaved pos = 16 (i / 4) + pos_base + i % 4
-  int32_t chunk, pos_base, pos_mode, pad;
+  int32_t chunk, pos_base, pos_mode;
+  int32_t fast;  // plain cubic spline term (order 3, basis "ps", no by): straight-line evaluation
   DMarg marg[PGB_MAX_MARG];
 };
 
@@ -139,6 +140,24 @@ __device__ __forceinline__ int eval_marg(const DMarg& mg, double x, double* v) {
 template <class Emit>
 __device__ __forceinline__ void eval_term(const DTerm& T, const double* __restrict__ X,
                                           int64_t ld, int64_t row, Emit& emit) {
+  if (T.fast) {
+    // the common case, s(feature) with the default cubic P-spline basis, inside the edge knots:
+    // same arithmetic as the general path below, without its dispatch
+    const DMarg& mg = T.marg[0];
+    const double u = (__ldg(X + (int64_t)mg.feature * ld + row) - mg.lo) * mg.inv_span;
+    if (u >= 0.0 && u <= 1.0) {
+      const double s = u * (double)mg.nint;
+      const int i = min((int)s, mg.nint - 1);
+      double v[4];
+      deboor_uniform<3>(s - (double)i, v);
+      const int c = T.coef_offset + i;
+      emit(c, v[0]);
+      emit(c + 1, v[1]);
+      emit(c + 2, v[2]);
+      emit(c + 3, v[3]);
+      return;
+    }
+  }
   if (T.kind == PGB_TERM_INTERCEPT) {
     emit(T.coef_offset, 1.0);
     return;
