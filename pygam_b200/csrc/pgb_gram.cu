@@ -110,7 +110,7 @@ int pgb_plan_gram(pgb_model* M) {
   }
   // ---- pack units into roles
   const size_t fixed = role_fixed_smem(M);
-  int k_pad = 2;
+  int k_pad = 6;
   for (const DTerm& d : T) k_pad += padded_nnz(d);
   const size_t rec_max = rec_row_bytes(k_pad);
   if (fixed + (size_t)32 * rec_max + 8192 > kSmemMax) {
@@ -119,8 +119,7 @@ int pgb_plan_gram(pgb_model* M) {
   }
   int plan_tile = kPlanTile;
   while (plan_tile > 32 && fixed + (size_t)plan_tile * rec_max > kSmemMax / 2) plan_tile >>= 1;
-  const size_t acc_budget =
-      (kSmemMax - fixed - (size_t)(plan_tile + 1) * rec_max - (size_t)16 * 32 * kMaxUnitsPerRole) / 8;  // doubles
+  const size_t acc_budget = (kSmemMax - fixed - (size_t)(plan_tile + 1) * rec_max) / 8;  // doubles
   M->units.clear();
   M->roles.clear();
   M->rterms.clear();
@@ -171,6 +170,7 @@ int pgb_plan_gram(pgb_model* M) {
       slot += 2;
     }
     r.n_rterms = (int)M->rterms.size() - r.term0;
+    while ((slot & 3) != 2) slot += 2;  // even (16-byte aligned rows) and 2 mod 4 (row-strided stores spread over banks)
     r.n_slots = slot;
     r.needs_all_terms = all_terms ? 1 : 0;
     r.rhs_pos = M->chunks.back().pad0;
@@ -183,22 +183,25 @@ int pgb_plan_gram(pgb_model* M) {
     }
     M->roles.push_back(r);
   }
-  // ---- tile rows, shared memory, threads
-  int tile = 256;
-  size_t smem = 0;
+  // ---- tile rows, shared memory, threads: the largest tile that fits; if a tile of >= 96 rows
+  //      also fits twice per SM, take that one (two resident CTAs hide each other's phase A)
   int max_units = 1;
-  for (;;) {
-    smem = 0;
+  for (const DRole& r : M->roles) max_units = std::max(max_units, r.n_units);
+  auto smem_for = [&](int tile) {
+    size_t smem = 0;
     for (const DRole& r : M->roles) {
-      size_t need = (size_t)(r.acc_size + 1) * 8 + (size_t)(tile + 1) * rec_row_bytes(r.n_slots) + fixed +
-                    (size_t)16 * 32 * kMaxUnitsPerRole;
+      size_t need = (size_t)(r.acc_size + 1) * 8 + (size_t)(tile + 1) * rec_row_bytes(r.n_slots) + fixed;
       if (M->roles.size() == 1) need += (size_t)tile * r.n_rterms * 8;  // lp_part of the inline IRLS step
       smem = std::max(smem, need);
-      max_units = std::max(max_units, r.n_units);
     }
-    if (smem <= kSmemMax || tile <= 32) break;
-    tile -= 32;
+    return smem;
+  };
+  int tile = 256;
+  while (tile > 32 && smem_for(tile) > kSmemMax) tile -= 32;
+  for (int t2 = tile; t2 >= 96; t2 -= 32) {
+    if (smem_for(t2) + 1024 <= kSmemMax / 2) { tile = t2; break; }
   }
+  size_t smem = smem_for(tile);
   if (smem > kSmemMax) {
     pgb_set_error("Gram pass does not fit in shared memory (%zu bytes)", smem);
     return PGB_EUNSUPPORTED;
@@ -392,6 +395,14 @@ __device__ __forceinline__ void lds_v2u32(uint32_t& x, uint32_t& y, uint32_t a) 
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
+// predicated forms: a lane whose predicate is off issues no shared-memory access at all
+__device__ __forceinline__ void lds_f64_if(double& v, uint32_t a, uint32_t on) {
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.f64 %0, [%1]; }" : "+d"(v) : "r"(a), "r"(on));
+}
+__device__ __forceinline__ void sts_f64_if(uint32_t a, double v, uint32_t on) {
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.f64 [%0], %1; }" ::"r"(a), "d"(v), "r"(on)
+               : "memory");
+}
 
 struct EmitRec {
   double* val;
@@ -429,8 +440,7 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
   double* acc = reinterpret_cast<double*>(smem_raw);
   double* rec_val = acc + ((role.acc_size + 1) & ~(int64_t)1);  // 16-byte aligned
   double* rec_w = rec_val + (size_t)(T + 1) * S;  // one spare row: the prefetch of phase B runs one ahead
-  double* dummy = rec_w + T;                        // 2 cells per thread for lanes without work
-  double* lp_part = dummy + 2 * blockDim.x;  // [n_rterms][T], only when the role computes the IRLS step inline
+  double* lp_part = rec_w + T;  // [n_rterms][T], only when the role computes the IRLS step inline
   double* s_beta = lp_part + (inline_irls ? (size_t)T * role.n_rterms : 0);
   double* s_red = s_beta + ((m + 1) & ~1);
   DTerm* s_terms = reinterpret_cast<DTerm*>(s_red + PGB_GS_COUNT * 32);
@@ -465,7 +475,7 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
   const uint32_t smem_cv = smem_u32(rec_val + coff), smem_cp = smem_u32(rec_pr + coff);
   const uint32_t smem_rv = smem_u32(rec_val + roff), smem_rp = smem_u32(rec_pr + roff);
   const uint32_t acc_u32 = smem_u32(uacc), w8 = (uint32_t)width * 8u, sb8 = (uint32_t)S * 8u, sb4 = (uint32_t)S * 4u;
-  const uint32_t dummy_u32 = smem_u32(dummy + 2 * tid);
+  const uint32_t p0 = v0 ? 1u : 0u, p1 = v1 ? 1u : 0u;
 
   for (int64_t tile = tiles_lo; tile < tiles_hi; ++tile) {
     const int64_t row0 = tile * T;
@@ -531,8 +541,8 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
     // ---------------- phase B: one warp per unit ----------------
     if (fast) {
       // lanes = 16 column slots x 2 row-side pairs (a = 2h, 2h + 1).  Explicit shared-space
-      // loads / stores on 32-bit addresses; lanes without work update a private dummy cell so the
-      // loop body is branch-free; the operands of the next row are fetched while the
+      // loads / stores on 32-bit addresses; lanes without work are predicated off (no branch, no
+      // shared-memory traffic); the operands of the next row are fetched while the
       // read-modify-write of the current row is in flight.
       asm volatile("" ::: "memory");
       uint32_t a_cv = smem_cv, a_cp = smem_cp, a_rv = smem_rv, a_rp = smem_rp;
@@ -544,22 +554,20 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
       lds_v2u32(rp0, rp1, a_rp);
       for (int rI = 0; rI < tile_n; ++rI) {
         const uint32_t bp = acc_u32 + (cpr & 0xffffu);  // accumulator base + 8 * column
-        uint32_t g0 = (rp0 >> 16) * w8 + bp, g1 = (rp1 >> 16) * w8 + bp;
-        g0 = v0 ? g0 : dummy_u32;
-        g1 = v1 ? g1 : dummy_u32 + 8;
+        const uint32_t g0 = (rp0 >> 16) * w8 + bp, g1 = (rp1 >> 16) * w8 + bp;
         const double c_cv = cv, c_rv0 = rv0, c_rv1 = rv1;
         a_cv += sb8; a_cp += sb4; a_rv += sb8; a_rp += sb4;  // the record buffer has one spare row
         lds_f64(cv, a_cv);
         lds_u32(cpr, a_cp);
         lds_v2f64(rv0, rv1, a_rv);
         lds_v2u32(rp0, rp1, a_rp);
-        double x0, x1;
-        lds_f64(x0, g0);
-        lds_f64(x1, g1);
+        double x0 = 0.0, x1 = 0.0;
+        lds_f64_if(x0, g0, p0);
+        lds_f64_if(x1, g1, p1);
         x0 = fma(c_rv0, c_cv, x0);
         x1 = fma(c_rv1, c_cv, x1);
-        sts_f64(g0, x0);
-        sts_f64(g1, x1);
+        sts_f64_if(g0, x0, p0);
+        sts_f64_if(g1, x1, p1);
       }
     } else if (has_unit) {
       const int ncp = (u.clen + 15) >> 4;
