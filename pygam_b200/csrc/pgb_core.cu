@@ -9,6 +9,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdint.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -307,53 +308,111 @@ extern "C" int pgb_model_matrix(const pgb_model* M, const double* X, int64_t n, 
 // ----------------------------------------------------------------------------------------
 // statistics / predict pass: lp, mu and the sums of _estimate_model_statistics on ALL rows
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPassThreads)
-stats_pass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Family fam,
+// One CTA walks tiles of R rows (round robin over the grid).  Thread 0 issues one TMA bulk copy
+// per input column of the NEXT tile (feature columns, y, w -> shared memory, completion on an
+// mbarrier) before the CTA evaluates the current one: a two-stage producer/consumer ring.
+// Unaligned inputs and the ragged last tile are staged with plain loads instead.
+template <bool HAS_Y, bool FULL>
+__global__ void __launch_bounds__(kPassThreads, 2)
+stats_pass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, int F, Family fam,
                   const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
                   const float* __restrict__ w, const double* __restrict__ beta, double scale,
-                  double ybar, int poisson_round, double* __restrict__ part,
+                  double ybar, int poisson_round, int R, int bulk_ok, double* __restrict__ part,
                   double* __restrict__ lp_out, double* __restrict__ mu_out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_beta = reinterpret_cast<double*>(smem_raw);
-  DTerm* s_terms = reinterpret_cast<DTerm*>(s_beta + ((m + 1) & ~1));
-  double* s_red = reinterpret_cast<double*>(s_terms + n_terms);
-  for (int i = threadIdx.x; i < m; i += blockDim.x) s_beta[i] = beta[i];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int ncol = F + (HAS_Y ? 1 : 0);
+  double* tiles = reinterpret_cast<double*>(smem_raw);                     // [2][ncol][R]
+  float* wtiles = reinterpret_cast<float*>(tiles + (size_t)2 * ncol * R);  // [2][R]
+  double* s_beta = reinterpret_cast<double*>(wtiles + 2 * R);
+  double* s_red = s_beta + ((m + 1) & ~1);
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(s_red + PGB_SS_COUNT * 32);
+  DTerm* s_terms = reinterpret_cast<DTerm*>(mbar + 2);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < m; i += blockDim.x) s_beta[i] = beta[i];
   load_terms_smem(s_terms, g_terms, n_terms);
+  if (tid == 0) {
+    mbar_init(smem_addr(&mbar[0]), 1);
+    mbar_init(smem_addr(&mbar[1]), 1);
+    fence_mbar_init();
+  }
   __syncthreads();
+
+  const int64_t n_tiles = (n + R - 1) / R;
+  const bool use_w = HAS_Y && (w != nullptr);
+  auto tile_rows = [&](int64_t t) { return (int)min((int64_t)R, n - t * R); };
+  // stage tile t into buffer b: TMA bulk copies for a full aligned tile, plain loads otherwise
+  auto issue = [&](int64_t t, int b) {
+    const int rows = tile_rows(t);
+    const int64_t row0 = t * R;
+    double* dst = tiles + (size_t)b * ncol * R;
+    if (bulk_ok && rows == R) {
+      if (tid == 0) {
+        const uint32_t bar = smem_addr(&mbar[b]);
+        mbar_expect_tx(bar, (uint32_t)(ncol * R * 8 + (use_w ? R * 4 : 0)));
+        for (int f = 0; f < F; ++f) bulk_g2s(smem_addr(dst + (size_t)f * R), X + (int64_t)f * ld + row0, R * 8, bar);
+        if (HAS_Y) bulk_g2s(smem_addr(dst + (size_t)F * R), y + row0, R * 8, bar);
+        if (use_w) bulk_g2s(smem_addr(wtiles + (size_t)b * R), w + row0, R * 4, bar);
+      }
+    } else {
+      for (int e = tid; e < ncol * rows; e += blockDim.x) {
+        const int f = e / rows, r = e - f * rows;
+        dst[(size_t)f * R + r] = (f < F) ? __ldg(X + (int64_t)f * ld + row0 + r) : __ldg(y + row0 + r);
+      }
+      if (use_w)
+        for (int r = tid; r < rows; r += blockDim.x) wtiles[(size_t)b * R + r] = __ldg(w + row0 + r);
+    }
+  };
 
   double acc[PGB_SS_COUNT];
 #pragma unroll
   for (int s = 0; s < PGB_SS_COUNT; ++s) acc[s] = 0.0;
-  const double null_mu = ybar;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    EmitLp e{s_beta, 0.0};
-    for (int t = 0; t < n_terms; ++t) eval_term(s_terms[t], X, ld, i, e);
-    const double lp = e.lp;
-    const double mu = link_inv(fam, lp);
-    if (lp_out) lp_out[i] = lp;
-    if (mu_out) mu_out[i] = mu;
-    if (y) {
-      const double yi = __ldg(y + i);
-      const double wi = w ? (double)__ldg(w + i) : 1.0;
-      const double d = dist_dev(fam, yi, mu);
-      const double r = yi - mu;
-      acc[PGB_SS_N] += 1.0;
-      acc[PGB_SS_WDEV] += wi * d;
-      acc[PGB_SS_PEARSON] += wi * (r * r) / dist_var(fam, mu);  // distributions.py:78
-      acc[PGB_SS_DEV] += d;
-      acc[PGB_SS_NCORRECT] += (yi == ((mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
-      acc[PGB_SS_SUMY] += yi;
-      acc[PGB_SS_SUMW] += wi;
-      if (!isfinite(lp) || !isfinite(mu)) acc[PGB_SS_NONFINITE] += 1.0;
-      if (scale > 0.0) {
-        const double yl = poisson_round ? rint(yi * wi) : yi;  // pygam.py:2797-2798
-        acc[PGB_SS_LOGLIK] += dist_logpdf(fam, yl, mu, wi, scale);
-        acc[PGB_SS_NULL_WDEV] += wi * dist_dev(fam, yi, null_mu);
-        acc[PGB_SS_NULL_LOGLIK] += dist_logpdf(fam, yl, null_mu, wi, scale);
-      }
-    } else if (!isfinite(lp) || !isfinite(mu)) {
-      acc[PGB_SS_NONFINITE] += 1.0;
+  uint32_t phase0 = 0u, phase1 = 0u;
+  int64_t t = blockIdx.x;
+  if (t < n_tiles) issue(t, 0);
+  int b = 0;
+  for (; t < n_tiles; t += gridDim.x, b ^= 1) {
+    const int64_t tn = t + gridDim.x;
+    if (tn < n_tiles) issue(tn, b ^ 1);  // buffer b^1 was released by the barrier that ended the previous iteration
+    const int rows = tile_rows(t);
+    if (bulk_ok && rows == R) {
+      if (b == 0) { mbar_wait(smem_addr(&mbar[0]), phase0); phase0 ^= 1u; }
+      else { mbar_wait(smem_addr(&mbar[1]), phase1); phase1 ^= 1u; }
+    } else {
+      __syncthreads();
     }
+    const double* tile = tiles + (size_t)b * ncol * R;
+    const float* wt = wtiles + (size_t)b * R;
+    const int64_t row0 = t * R;
+    for (int r = tid; r < rows; r += blockDim.x) {
+      EmitLp e{s_beta, 0.0};
+      const LoadTile load{tile, R, r};
+      for (int q = 0; q < n_terms; ++q) eval_term(s_terms[q], load, e);
+      const double lp = e.lp;
+      const double mu = link_inv(fam, lp);
+      if (lp_out) lp_out[row0 + r] = lp;
+      if (mu_out) mu_out[row0 + r] = mu;
+      if (!isfinite(lp) || !isfinite(mu)) acc[PGB_SS_NONFINITE] += 1.0;
+      if (HAS_Y) {
+        const double yi = tile[(size_t)F * R + r];
+        const double wi = use_w ? (double)wt[r] : 1.0;
+        const double d = dist_dev(fam, yi, mu);
+        const double res = yi - mu;
+        acc[PGB_SS_N] += 1.0;
+        acc[PGB_SS_WDEV] += wi * d;
+        acc[PGB_SS_PEARSON] += wi * (res * res) / dist_var(fam, mu);  // distributions.py:78
+        acc[PGB_SS_DEV] += d;
+        acc[PGB_SS_NCORRECT] += (yi == ((mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
+        acc[PGB_SS_SUMY] += yi;
+        acc[PGB_SS_SUMW] += wi;
+        if (FULL) {
+          const double yl = poisson_round ? rint(yi * wi) : yi;  // pygam.py:2797-2798
+          acc[PGB_SS_LOGLIK] += dist_logpdf(fam, yl, mu, wi, scale);
+          acc[PGB_SS_NULL_WDEV] += wi * dist_dev(fam, yi, ybar);
+          acc[PGB_SS_NULL_LOGLIK] += dist_logpdf(fam, yl, ybar, wi, scale);
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with buffer b before it is refilled two tiles from now
   }
   block_reduce_store<PGB_SS_COUNT>(acc, s_red, part + (int64_t)blockIdx.x * PGB_SS_COUNT);
 }
@@ -365,16 +424,36 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
   if (!M || !X || !beta || n < 1 || ld < n) { pgb_set_error("pgb_stats_pass: bad arguments"); return PGB_EINVAL; }
   if (ws_bytes < pgb_stats_ws_bytes(M) || !ws) { pgb_set_error("pgb_stats_pass: workspace too small"); return PGB_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = (int)std::min<int64_t>((n + kPassThreads - 1) / kPassThreads, M->pass_ctas);
-  const size_t smem = (size_t)((M->m + 1) & ~1) * 8 + (size_t)M->n_terms * sizeof(DTerm) + PGB_SS_COUNT * 32 * 8;
+  const int F = M->n_features, ncol = F + (y ? 1 : 0);
+  const size_t fixed = (size_t)((M->m + 1) & ~1) * 8 + PGB_SS_COUNT * 32 * 8 + 16 + (size_t)M->n_terms * sizeof(DTerm);
+  // rows per tile: two stages per CTA, two CTAs per SM
+  int R = 1024;
+  while (R > 256 && fixed + (size_t)2 * R * (ncol * 8 + 4) > kSmemMax / 2 - 2048) R -= 256;
+  const size_t smem = fixed + (size_t)2 * R * (ncol * 8 + 4);
+  if (smem > kSmemMax) {
+    pgb_set_error("pgb_stats_pass: %d features do not fit the staging tiles", F);
+    return PGB_EUNSUPPORTED;
+  }
+  // TMA bulk copies need 16-byte aligned sources: every column start and every tile start
+  const bool bulk_ok = ((uintptr_t)X % 16 == 0) && (ld % 2 == 0) && (!y || (uintptr_t)y % 16 == 0) &&
+                       (!w || (uintptr_t)w % 16 == 0);
+  const int64_t n_tiles = (n + R - 1) / R;
+  const int grid = (int)std::min<int64_t>(n_tiles, std::min(M->pass_ctas, kSMs * 2));
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
-  stats_pass_kernel<<<grid, kPassThreads, smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, X, n, ld, y, w,
-                                                      beta, scale, ybar, poisson_round, (double*)ws,
-                                                      lp_out, mu_out);
+#define PGB_STATS_LAUNCH(HY, FL)                                                                              \
+  stats_pass_kernel<HY, FL><<<grid, kPassThreads, smem, st>>>(M->d_terms, M->n_terms, M->m, F, M->fam, X, n, ld, \
+                                                              y, w, beta, scale, ybar, poisson_round, R,      \
+                                                              bulk_ok ? 1 : 0, (double*)ws, lp_out, mu_out)
+  if (!y) PGB_STATS_LAUNCH(false, false);
+  else if (scale > 0.0) PGB_STATS_LAUNCH(true, true);
+  else PGB_STATS_LAUNCH(true, false);
+#undef PGB_STATS_LAUNCH
   PGB_LAUNCHED(1);
   PGB_CUDA(cudaGetLastError());
   if (scalars) {

@@ -137,14 +137,26 @@ __device__ __forceinline__ int eval_marg(const DMarg& mg, double x, double* v) {
 // ----------------------------------------------------------------------------------------
 // one model-matrix row of one term as (column, value) pairs; exactly T.nnz calls of emit
 // ----------------------------------------------------------------------------------------
-template <class Emit>
-__device__ __forceinline__ void eval_term(const DTerm& T, const double* __restrict__ X,
-                                          int64_t ld, int64_t row, Emit& emit) {
+// `load(f)` returns feature f of the row being evaluated: straight from HBM (LoadGlobal) or from a
+// tile staged in shared memory by bulk async copies (LoadTile)
+struct LoadGlobal {
+  const double* __restrict__ X;
+  int64_t ld, row;
+  __device__ __forceinline__ double operator()(int f) const { return __ldg(X + (int64_t)f * ld + row); }
+};
+struct LoadTile {
+  const double* tile;  // [n_features][tile_ld], element (f, r) at tile[f * tile_ld + r]
+  int tile_ld, r;
+  __device__ __forceinline__ double operator()(int f) const { return tile[f * tile_ld + r]; }
+};
+
+template <class Emit, class Load>
+__device__ __forceinline__ void eval_term(const DTerm& T, const Load& load, Emit& emit) {
   if (T.fast) {
     // the common case, s(feature) with the default cubic P-spline basis, inside the edge knots:
     // same arithmetic as the general path below, without its dispatch
     const DMarg& mg = T.marg[0];
-    const double u = (__ldg(X + (int64_t)mg.feature * ld + row) - mg.lo) * mg.inv_span;
+    const double u = (load(mg.feature) - mg.lo) * mg.inv_span;
     if (u >= 0.0 && u <= 1.0) {
       const double s = u * (double)mg.nint;
       const int i = min((int)s, mg.nint - 1);
@@ -163,14 +175,14 @@ __device__ __forceinline__ void eval_term(const DTerm& T, const double* __restri
     return;
   }
   if (T.kind == PGB_TERM_LINEAR) {
-    emit(T.coef_offset, __ldg(X + (int64_t)T.marg[0].feature * ld + row));
+    emit(T.coef_offset, load(T.marg[0].feature));
     return;
   }
-  const double byv = (T.by >= 0) ? __ldg(X + (int64_t)T.by * ld + row) : 1.0;
+  const double byv = (T.by >= 0) ? load(T.by) : 1.0;
   if (T.n_marg == 1) {
     const DMarg& mg = T.marg[0];
     double v[PGB_MAXV];
-    const int i0 = eval_marg(mg, __ldg(X + (int64_t)mg.feature * ld + row), v);
+    const int i0 = eval_marg(mg, load(mg.feature), v);
     const int K = mg.nspl;
 #pragma unroll
     for (int a = 0; a < PGB_MAXV; ++a) {
@@ -194,7 +206,7 @@ __device__ __forceinline__ void eval_term(const DTerm& T, const double* __restri
   for (int q = 0; q < PGB_MAX_MARG; ++q) {
     if (q < T.n_marg) {
       const DMarg& mg = T.marg[q];
-      i0[q] = eval_marg(mg, __ldg(X + (int64_t)mg.feature * ld + row), v[q]);
+      i0[q] = eval_marg(mg, load(mg.feature), v[q]);
       cnt[q] = mg.order + 1;
       K[q] = mg.nspl;
     } else {
@@ -219,6 +231,13 @@ __device__ __forceinline__ void eval_term(const DTerm& T, const double* __restri
       }
     }
   }
+}
+
+template <class Emit>
+__device__ __forceinline__ void eval_term(const DTerm& T, const double* __restrict__ X, int64_t ld,
+                                          int64_t row, Emit& emit) {
+  const LoadGlobal load{X, ld, row};
+  eval_term(T, load, emit);
 }
 
 // ----------------------------------------------------------------------------------------
