@@ -65,6 +65,17 @@ __device__ __forceinline__ void deboor_uniform(double t, double* v) {
   }
 }
 
+// the four non-zero cubic B-splines of a uniform knot vector at local coordinate t, closed form:
+// [(1-t)^3, 3t^3 - 6t^2 + 4, -3t^3 + 3t^2 + 3t + 1, t^3] / 6; agrees with
+// the recursion above to rounding and is what the straight-line cubic path uses everywhere
+__device__ __forceinline__ void cubic_bspline(double t, double& b0, double& b1, double& b2, double& b3) {
+  const double omt = 1.0 - t, t2 = t * t, t3 = t2 * t;
+  b0 = (omt * omt) * (omt * (1.0 / 6.0));
+  b3 = t3 * (1.0 / 6.0);
+  b1 = fma(t3, 0.5, fma(t2, -1.0, 2.0 / 3.0));
+  b2 = fma(t3, -0.5, fma(t2, 0.5, fma(t, 0.5, 1.0 / 6.0)));
+}
+
 __device__ __forceinline__ void deboor_dispatch(int d, double t, double* v) {
   switch (d) {
     case 0: v[0] = 1.0; break;
@@ -160,13 +171,13 @@ __device__ __forceinline__ void eval_term(const DTerm& T, const Load& load, Emit
     if (u >= 0.0 && u <= 1.0) {
       const double s = u * (double)mg.nint;
       const int i = min((int)s, mg.nint - 1);
-      double v[4];
-      deboor_uniform<3>(s - (double)i, v);
+      double b0, b1, b2, b3;
+      cubic_bspline(s - (double)i, b0, b1, b2, b3);
       const int c = T.coef_offset + i;
-      emit(c, v[0]);
-      emit(c + 1, v[1]);
-      emit(c + 2, v[2]);
-      emit(c + 3, v[3]);
+      emit(c, b0);
+      emit(c + 1, b1);
+      emit(c + 2, b2);
+      emit(c + 3, b3);
       return;
     }
   }
@@ -290,7 +301,10 @@ __device__ __forceinline__ double ylogydu(double y, double u) {  // utils.py:773
 __device__ __forceinline__ double dist_dev(const Family& f, double y, double mu) {
   switch (f.dist) {
     case PGB_DIST_NORMAL: { const double r = y - mu; return r * r; }
-    case PGB_DIST_BINOMIAL: return 2.0 * (ylogydu(y, mu) + ylogydu(f.levels - y, f.levels - mu));
+    case PGB_DIST_BINOMIAL:
+      // 0/1 responses: 2 log(1/mu) or 2 log(1/(1-mu)) is all that is left of the general formula
+      if (f.levels == 1.0 && (y == 0.0 || y == 1.0)) return -2.0 * log((y == 1.0) ? mu : 1.0 - mu);
+      return 2.0 * (ylogydu(y, mu) + ylogydu(f.levels - y, f.levels - mu));
     case PGB_DIST_POISSON: return 2.0 * (ylogydu(y, mu) - (y - mu));
     case PGB_DIST_GAMMA: return 2.0 * ((y - mu) / mu - log(y / mu));
     default: { const double r = y - mu; return (r * r) / (mu * mu * y); }
