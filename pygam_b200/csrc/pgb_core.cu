@@ -161,12 +161,12 @@ extern "C" int pgb_model_plan_host(const pgb_term* terms, int32_t n_terms, int32
   if (info) pgb_model_get_info(M, info);
   if (coverage_errors) *coverage_errors = pgb_plan_coverage_errors(M);
   if (getenv("PGB_DEBUG_PLAN")) {
-    fprintf(stderr, "plan: m=%d k=%d chunks=%zu units=%zu roles=%zu tile=%d threads=%d smem=%zu ctas=%d\n", M->m,
-            M->k, M->chunks.size(), M->units.size(), M->roles.size(), M->tile_rows, M->gram_threads,
-            M->gram_smem, M->gram_ctas);
+    fprintf(stderr, "plan: m=%d k=%d groups=%zu blocks=%zu steps=%zu roles=%zu tile=%d threads=%d smem=%zu ctas=%d\n",
+            M->m, M->k, M->groups.size(), M->blocks.size(), M->steps.size(), M->roles.size(), M->tile_rows,
+            M->gram_threads, M->gram_smem, M->gram_ctas);
     for (const DRole& r : M->roles)
-      fprintf(stderr, "  role units=%d slots=%d acc=%lld ctas=%d all_terms=%d\n", r.n_units, r.n_slots,
-              (long long)r.acc_size, r.n_ctas, r.needs_all_terms);
+      fprintf(stderr, "  role warps=%d max_steps=%d slots=%d acc=%lld ctas=%d all_terms=%d\n", r.n_warps, r.max_steps,
+              r.n_slots, (long long)r.acc_size, r.n_ctas, r.needs_all_terms);
   }
   delete M;
   return PGB_OK;

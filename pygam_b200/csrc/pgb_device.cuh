@@ -26,16 +26,12 @@ struct DMarg {
 
 struct DTerm {
   int32_t kind, n_marg, by, drop_first, coef_offset, n_coefs, nnz, slot0;
-  // placement of the term's coefficients inside its column chunk of the Gram accumulators
-  // (pgb_internal.h): natural pos = pos_base + i, interleaved pos = 16 (i / 4) + pos_base + i % 4
-  int32_t chunk, pos_base, pos_mode;
+  // placement of the term inside the Gram plan (pgb_internal.h): coefficient group, index of the
+  // term's first coefficient inside the group, first global record slot (4 per quad)
+  int32_t group, idx_base, gslot0;
   int32_t fast;  // plain cubic spline term (order 3, basis "ps", no by): straight-line evaluation
   DMarg marg[PGB_MAX_MARG];
 };
-
-__host__ __device__ __forceinline__ int term_pos(int pos_base, int pos_mode, int i) {
-  return pos_mode ? (((i >> 2) << 4) + pos_base + (i & 3)) : (pos_base + i);
-}
 
 struct Family {
   int32_t dist, link;

@@ -10,48 +10,76 @@
 #include "pgb_device.cuh"
 
 // ---- plan of the Gram pass (DESIGN.md "Gram pass") ---------------------------------------
-// The non-zeros of one model-matrix row occupy k "slots" (fixed per model: every term emits
-// nnz slots per row) plus one virtual slot for the right-hand side.  Consecutive terms are
-// grouped into column CHUNKS of at most 16 slots.  A UNIT is (row term j, column chunk g >=
-// chunk(j)): the block G[coefficients of term j, columns of chunk g], K_j x width_g doubles, kept
-// in shared memory by ONE warp for the whole kernel -- no two warps ever update the same
-// accumulator, so the fp64 read-modify-write needs no atomics.  Units are packed into ROLES
-// (what one CTA keeps in shared memory); every role walks the rows assigned to its CTAs.
-struct DChunk {
-  int32_t first_term, n_terms;
-  int32_t n_slots;  // slots of the chunk incl. the virtual rhs slot if it lives here
-  int32_t width;    // physical columns of the chunk (layout dependent, >= sum of n_coefs)
-  int32_t has_rhs;  // the virtual rhs column is the last physical column of this chunk
-  int32_t layout;   // 0 natural, 1 four-way interleave (bank-conflict free for cubic splines)
-  int32_t pad0, pad1;
+// The non-zeros of one model-matrix row occupy "slots" (fixed per model: every term emits nnz
+// slots per row) plus one virtual slot for the right-hand side.  Slots are grouped four by four
+// into QUADS; the coefficients are partitioned into GROUPS (one per multi-slot term; single-slot
+// terms -- intercept, l(), f() -- and the rhs share "misc" groups of one quad).  A BLOCK is the
+// accumulator G[group gi, group gj], gi <= gj, rows x pitch doubles with pitch = 4 (mod 8), so
+// that the 4 x 4 outer product of two quads (4 consecutive rows x 4 consecutive columns) lands
+// in 16 distinct 8-byte banks.  An ITEM is (row quad, column quad) of a block: 16 products per
+// data row, computed by the 16 lanes (a, b) of a half-warp.  A STEP is two items, one per
+// half-warp; a warp owns a list of steps for the whole kernel, and every accumulator element
+// is updated by exactly one warp -- the fp64 read-modify-write needs no atomics.  Blocks are
+// packed into ROLES (what one CTA keeps in shared memory); every role walks the rows assigned
+// to its CTAs.
+struct DGroup {
+  int32_t width;    // coefficients of the group (+1 for the rhs column when it lives here)
+  int32_t pitch;    // row pitch (doubles) of a block whose columns are this group
+  int32_t n_quads;
+  int32_t quad0;    // first global quad
 };
 
-struct DUnit {
-  int32_t row_term;  // term whose coefficients are the rows of this block
-  int32_t chunk;
-  int32_t rslot;     // record slot of the row term's first non-zero (role-local)
-  int32_t nnz_r;     // non-zeros of the row term per data row
-  int32_t cslot;     // record slot of the chunk's first slot (role-local)
-  int32_t clen;      // slots of the chunk
-  int32_t cmin;      // first chunk slot that belongs to a term >= row_term (earlier: lower triangle)
-  int32_t width;     // physical width of the block
-  int32_t k_rows;    // n_coefs of the row term
-  int32_t pad;
-  int64_t off;       // offset of the block inside the role's accumulator (doubles)
+struct DBlock {
+  int32_t gi, gj;   // row group <= column group
+  int32_t role;
+  int32_t n_items;
+  int32_t tr, pad;  // tr = 1: stored transposed, [coefficients of gj][pitch of gi]
+  int64_t off;      // offset inside the role's accumulator (doubles)
+};
+
+// one (shared quad, varying quad) pair of a half-step: 16 products per data row
+struct DVar {
+  uint32_t slot;    // role-local record slot of the varying quad's first entry
+  uint32_t off8;    // block offset inside the role's accumulator, bytes
+  uint32_t pitch8;  // block row pitch, bytes
+  uint32_t mask;    // bit 4 * (varying slot) + (shared slot): the lane accumulates; bit 16: same group
+                    // on both sides, element = (min index, max index)
+};
+
+// What one half-warp does per data row in one step: the operand of the SHARED quad is loaded once
+// (lane & 3 selects its slot) and multiplied with up to PGB_MAX_K VARYING quads ((lane >> 2) & 3
+// selects the slot), each product going to its own block at
+// [index of the varying slot][index of the shared slot] (blocks whose shared quad is the row side
+// are stored transposed).
+#define PGB_MAX_K 4
+struct DHalf {
+  uint32_t shared_slot, pad;
+  DVar v[PGB_MAX_K];
+};
+
+struct DStep {
+  DHalf h[2];
+};
+
+struct DWarp {
+  int32_t step0, n_steps;
 };
 
 struct DRoleTerm {
-  int32_t term;   // term index, or -1 for the virtual rhs slot
-  int32_t slot0;  // role-local record slot of its first non-zero
+  int32_t term;      // term index, or -1 for the virtual rhs slot
+  int32_t slot0;     // role-local record slot of its first non-zero
+  int32_t idx_base;  // index of the term's first coefficient inside its group
+  int32_t pad;
 };
 
 struct DRole {
-  int32_t unit0, n_units;      // range in the unit table
+  int32_t warp0, n_warps;      // range in the warp table
   int32_t term0, n_rterms;     // range in the role-term table (terms whose basis the role needs)
-  int32_t n_slots;             // record slots per data row
+  int32_t n_slots;             // record slots per data row (4 per quad)
   int32_t needs_all_terms;     // role evaluates every term (inline IRLS possible)
   int32_t cta0, n_ctas;        // CTAs of the 1-d grid that work for this role
-  int32_t rhs_pos, rhs_slot;   // physical column / record slot of the virtual rhs entry (-1: none)
+  int32_t rhs_slot, max_steps; // record slot of the virtual rhs entry (-1: none); longest warp
+  int32_t step0, n_steps;      // range in the step table (copied to shared memory by every CTA)
   int64_t acc_size;            // doubles of the role's accumulator
   int64_t part_off;            // offset of the role's first partial inside the workspace (doubles)
   int64_t map_off;             // offset of the role's element map
@@ -60,14 +88,16 @@ struct DRole {
 struct pgb_model {
   std::vector<pgb_term> terms;
   std::vector<DTerm> dterms;
-  std::vector<DChunk> chunks;
-  std::vector<DUnit> units;
+  std::vector<DGroup> groups;
+  std::vector<DBlock> blocks;
+  std::vector<DStep> steps;
+  std::vector<DWarp> warps;
   std::vector<DRoleTerm> rterms;
   std::vector<DRole> roles;
   std::vector<int32_t> elem_map;  // per accumulator element: row * (m + 1) + col of G|r, or -1
   DTerm* d_terms = nullptr;
-  DChunk* d_chunks = nullptr;
-  DUnit* d_units = nullptr;
+  DStep* d_steps = nullptr;
+  DWarp* d_warps = nullptr;
   DRoleTerm* d_rterms = nullptr;
   DRole* d_roles = nullptr;
   int32_t* d_elem_map = nullptr;
