@@ -24,21 +24,20 @@
 #include "pgb_internal.h"
 #include "pgb_kernels.cuh"
 
-static const int kMaxWarps = 12;      // consumer (accumulating) warps per CTA of the Gram pass
-#ifndef PGB_STAGE_U
-#define PGB_STAGE_U 2
-#endif
-static const int kMaxProducers = 4;
-static const int kStages = 4;        // raw-column stage buffers of the producers (fetch distance kStages - 1 tiles)  // producer (record staging) warps per CTA
+static const int kMaxWarps = 15;      // consumer (accumulating) warps per CTA of the accumulation kernel; + 1 TMA warp
+static const int kNBuf = 3;           // record buffers of the accumulation kernel (TMA ring)
 static const int kSlotBytes = 12;     // record slot: double value + uint32 index (two arrays)
+static const int kRecThreads = 256;   // CTA of the records kernel
+static const int64_t kChunkRows = 1 << 22;  // rows whose records are materialised at a time
 
 // ----------------------------------------------------------------------------------------
 // plan
 // ----------------------------------------------------------------------------------------
 static const int kMinTile = 16;
-// row pitch of the slot-major tile records: odd (the 4 slots of a quad start in different banks) and
-// two spare rows (phase B prefetches one row pair ahead)
-static int tile_pitch(int tile) { return (tile + 2) | 1; }
+// row pitch of the slot-major tile records ([slot][pitch]): two spare rows (the accumulation
+// prefetches one row pair ahead) and pitch = 2 (mod 4), so that the four slots of a quad start in
+// different banks while every slot row stays 16-byte aligned for the TMA bulk copies
+static int tile_pitch(int tile) { return tile + 2; }
 
 static int pitch_for(int width) {
   int p = std::max(width, 4);
@@ -121,12 +120,11 @@ int pgb_plan_gram(pgb_model* M) {
   // ---- blocks, packed into roles in (gi, gj) order
   const size_t fixed = role_fixed_smem(M);
   const size_t rec_row_all = (size_t)(quads * 4) * kSlotBytes;  // bytes per tile row when a role needs every quad
-  if (fixed + 2 * kMinTile * rec_row_all + 8192 > kSmemMax) {
+  if (fixed + (kMinTile + 2) * rec_row_all * 2 + 16384 > kSmemMax) {
     pgb_set_error("model too wide for the Gram pass: k=%d non-zeros per row", M->k);
     return PGB_EUNSUPPORTED;
   }
-  const size_t stage_min = (size_t)kStages * (M->n_features + 2) * kMinTile * 8 + (size_t)4 * kStages * kMinTile;  // raw-column stage buffers
-  const int64_t acc_budget = (int64_t)((kSmemMax - fixed - 2 * (kMinTile + 3) * rec_row_all - stage_min - 6144) / 8);  // doubles
+  const int64_t acc_budget = (int64_t)((kSmemMax - kNBuf * (kMinTile + 2) * rec_row_all - 8192) / 8);  // doubles
   M->blocks.clear();
   int64_t total_acc = 0;
   for (int gi = 0; gi < ng; ++gi)
@@ -181,6 +179,8 @@ int pgb_plan_gram(pgb_model* M) {
   M->rterms.clear();
   M->steps.clear();
   M->warps.clear();
+  M->runs.clear();
+  M->n_slots_all = 4 * quads;
   int max_warps = 1;
   for (int r = 0; r < n_roles; ++r) {
     DRole R{};
@@ -197,18 +197,17 @@ int pgb_plan_gram(pgb_model* M) {
     }
     R.n_slots = 4 * nlq;
     R.needs_all_terms = all ? 1 : 0;
-    R.term0 = (int)M->rterms.size();
-    for (int j = 0; j < nt; ++j) {
-      if (!gneed[T[j].group]) continue;
-      const int gq = T[j].gslot0 >> 2;
-      M->rterms.push_back(DRoleTerm{j, 4 * lquad[gq] + (T[j].gslot0 & 3), T[j].idx_base, 0});
+    // contiguous runs of global quads -> one TMA bulk copy each (values, indices) per tile
+    R.run0 = (int)M->runs.size();
+    for (int q = 0; q < quads; ++q) {
+      if (lquad[q] < 0) continue;
+      if (!M->runs.empty() && (int)M->runs.size() > R.run0 && M->runs.back().gslot0 + M->runs.back().n_slots == 4 * q)
+        M->runs.back().n_slots += 4;
+      else
+        M->runs.push_back(DRun{4 * q, 4 * lquad[q], 4, 0});
     }
-    R.rhs_slot = -1;
-    if (gneed[rhs_group]) {
-      R.rhs_slot = 4 * lquad[rhs_quad] + rhs_s;
-      M->rterms.push_back(DRoleTerm{-1, R.rhs_slot, rhs_idx, 0});
-    }
-    R.n_rterms = (int)M->rterms.size() - R.term0;
+    R.n_runs = (int)M->runs.size() - R.run0;
+    R.rhs_slot = gneed[rhs_group] ? 4 * lquad[rhs_quad] + rhs_s : -1;
     // Items -> half-steps -> chains.  A block with several items (tensor terms, splines of order
     // > 3) can reach the same accumulator element through different quad pairs on different data
     // rows, so all its half-steps form one chain that stays in one half-warp column of one warp
@@ -305,18 +304,17 @@ int pgb_plan_gram(pgb_model* M) {
     M->roles.push_back(R);
   }
 
-  // ---- tile rows, shared memory, threads: the largest tile that fits; if a tile of >= 64 rows
-  //      also fits twice per SM, take that one (two resident CTAs hide each other's phase A)
-  // records are slot-major ([slot][tile_pitch]); split roles double-buffer them so that staging the
-  // next tile overlaps the accumulation of the current one
+  // ---- every term (and the rhs) with its global record slot: what the records kernel evaluates
+  for (int j = 0; j < nt; ++j) M->rterms.push_back(DRoleTerm{j, T[j].gslot0, T[j].idx_base, 0});
+  M->rterms.push_back(DRoleTerm{-1, 4 * rhs_quad + rhs_s, rhs_idx, 0});
+
+  // ---- tile rows (shared by both kernels) from the accumulation kernel's shared memory: its
+  //      accumulator, kNBuf record buffers of the role's slots, the role's steps
   auto smem_for = [&](int tile) {
     size_t smem = 0;
-    const int nbuf = 2;
     for (const DRole& r : M->roles) {
-      size_t need = (size_t)(r.acc_size + 2) * 8 + (size_t)nbuf * tile_pitch(tile) * r.n_slots * kSlotBytes + (size_t)tile * 8 + fixed +
-                    (size_t)r.n_steps * sizeof(DStep) + (size_t)r.n_rterms * 64 +
-                    (size_t)kStages * (M->n_features + 2) * tile * 8 + (size_t)kStages * tile * 4 + 8 * kStages + 64;
-      if (n_roles == 1) need += (size_t)tile * r.n_rterms * 8;  // lp_part of the inline IRLS step
+      const size_t need = (size_t)(r.acc_size + 2) * 8 + (size_t)kNBuf * tile_pitch(tile) * r.n_slots * kSlotBytes +
+                          (size_t)r.n_steps * sizeof(DStep) + (size_t)r.n_runs * sizeof(DRun) + 8 * kNBuf + 256;
       smem = std::max(smem, need);
     }
     return smem;
@@ -334,9 +332,16 @@ int pgb_plan_gram(pgb_model* M) {
   }
   M->tile_rows = tile;
   M->gram_smem = (smem + 127) & ~(size_t)127;
-  int prod = kMaxProducers;
-  if (const char* ep = getenv("PGB_GRAM_PW")) prod = std::max(1, std::min(kMaxProducers, atoi(ep)));
-  M->gram_threads = 32 * (max_warps + prod);
+  M->gram_threads = 32 * (max_warps + 1);
+  // records kernel: all slots of a tile, the raw columns, lp parts, beta, the terms
+  M->rec_smem = (size_t)tile_pitch(tile) * M->n_slots_all * kSlotBytes + (size_t)(M->n_features + 2) * tile * 8 + (size_t)tile * 4 +
+                (size_t)tile * 8 + (size_t)tile * (nt + 1) * 8 + (size_t)(nt + 1) * 64 + fixed + 256;
+  M->rec_smem = (M->rec_smem + 127) & ~(size_t)127;
+  if (M->rec_smem > kSmemMax) {
+    pgb_set_error("records kernel does not fit in shared memory (%zu bytes)", M->rec_smem);
+    return PGB_EUNSUPPORTED;
+  }
+  M->rec_ctas = kSMs * (int)std::max<size_t>(1, std::min<size_t>(3, kSmemMax / (M->rec_smem + 1024)));
   // ---- CTAs per role proportional to the role's cost per row
   int occ = (int)std::min<size_t>(8, kSmemMax / (M->gram_smem + 1024));
   occ = std::max(1, std::min(occ, 1536 / M->gram_threads));
@@ -380,7 +385,7 @@ int pgb_plan_gram(pgb_model* M) {
     moff += r.acc_size;
   }
   M->gram_ctas = cta;
-  M->partial_doubles = (poff + 1) & ~(int64_t)1;  // keeps the (sqrt(omega), z) pairs after it 16-byte aligned
+  M->partial_doubles = (poff + 1) & ~(int64_t)1;
   M->map_size = moff;
   M->pass_ctas = kSMs * 8;
   // ---- element map: accumulator element -> row * (m + 1) + col of [G | r], row <= col
@@ -412,6 +417,7 @@ int pgb_plan_upload(pgb_model* M) {
   up((void**)&M->d_steps, M->steps.data(), M->steps.size() * sizeof(DStep));
   up((void**)&M->d_warps, M->warps.data(), M->warps.size() * sizeof(DWarp));
   up((void**)&M->d_rterms, M->rterms.data(), M->rterms.size() * sizeof(DRoleTerm));
+  up((void**)&M->d_runs, M->runs.data(), M->runs.size() * sizeof(DRun));
   up((void**)&M->d_roles, M->roles.data(), M->roles.size() * sizeof(DRole));
   up((void**)&M->d_elem_map, M->elem_map.data(), M->elem_map.size() * sizeof(int32_t));
   // the device copy of the terms carries the plan fields (group, idx_base, gslot0)
@@ -461,67 +467,24 @@ void pgb_gram_release(pgb_model* M) {
   cudaFree(M->d_steps);
   cudaFree(M->d_warps);
   cudaFree(M->d_rterms);
+  cudaFree(M->d_runs);
   cudaFree(M->d_roles);
   cudaFree(M->d_elem_map);
-  M->d_steps = nullptr; M->d_warps = nullptr; M->d_rterms = nullptr; M->d_roles = nullptr; M->d_elem_map = nullptr;
+  M->d_steps = nullptr; M->d_warps = nullptr; M->d_rterms = nullptr; M->d_runs = nullptr; M->d_roles = nullptr; M->d_elem_map = nullptr;
 }
 
-static bool gram_inline(const pgb_model* M) { return M->roles.size() == 1 && M->roles[0].needs_all_terms; }
-
-// workspace: [partials][scalar partials][(omega, z) per row when split]
+// tiles / record bytes of a chunk of rows; workspace: [partials][scalar partials][records of one chunk]
+static int64_t rec_tile_bytes(const pgb_model* M) {
+  return (int64_t)M->n_slots_all * tile_pitch(M->tile_rows) * kSlotBytes;
+}
 static int64_t gram_fixed_ws_doubles(const pgb_model* M) {
-  return M->partial_doubles + (int64_t)(M->gram_ctas + M->pass_ctas) * PGB_GS_COUNT;
+  return M->partial_doubles + (int64_t)M->rec_ctas * PGB_GS_COUNT;
 }
 extern "C" int64_t pgb_gram_ws_bytes(const pgb_model* M, int64_t n) {
   if (!M) return 0;
-  int64_t d = gram_fixed_ws_doubles(M);
-  if (!gram_inline(M)) d += 2 * n;
-  return d * 8 + 256;
-}
-
-// ----------------------------------------------------------------------------------------
-// per-row IRLS quantities when the Gram matrix is split over several roles: every role's
-// CTAs read (omega, z) instead of re-evaluating the full linear predictor
-// ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPassThreads)
-irls_rows_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Family fam, int mode,
-                 const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
-                 const float* __restrict__ w, const double* __restrict__ beta,
-                 double* __restrict__ wz, double* __restrict__ part) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_beta = reinterpret_cast<double*>(smem_raw);
-  DTerm* s_terms = reinterpret_cast<DTerm*>(s_beta + ((m + 1) & ~1));
-  double* s_red = reinterpret_cast<double*>(s_terms + n_terms);
-  for (int i = threadIdx.x; i < m; i += blockDim.x) s_beta[i] = (mode == PGB_MODE_IRLS) ? beta[i] : 0.0;
-  load_terms_smem(s_terms, g_terms, n_terms);
-  __syncthreads();
-  double acc[PGB_GS_COUNT];
-#pragma unroll
-  for (int s = 0; s < PGB_GS_COUNT; ++s) acc[s] = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double yi = __ldg(y + i);
-    double om, z;
-    if (mode == PGB_MODE_IRLS) {
-      EmitLp e{s_beta, 0.0};
-      for (int t = 0; t < n_terms; ++t) eval_term(s_terms[t], X, ld, i, e);
-      const IrlsRow r = irls_row(fam, e.lp, yi, weight_inv(w, i));
-      om = r.sw;
-      z = r.z;
-      if (r.keep) {
-        acc[PGB_GS_NUSED] += 1.0;
-        acc[PGB_GS_DEV] += dist_dev(fam, yi, r.mu);
-        acc[PGB_GS_NCORRECT] += (yi == ((r.mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
-      }
-    } else {
-      om = 1.0;
-      z = init_response(fam, yi);
-      acc[PGB_GS_NUSED] += 1.0;
-      if (!isfinite(z)) acc[PGB_GS_NONFINITE] += 1.0;
-    }
-    acc[PGB_GS_NROWS] += 1.0;
-    reinterpret_cast<double2*>(wz)[i] = make_double2(om, om * z);  // (sqrt(omega), sqrt(omega) z)
-  }
-  block_reduce_store<PGB_GS_COUNT>(acc, s_red, part + (int64_t)blockIdx.x * PGB_GS_COUNT);
+  const int64_t rows = std::max<int64_t>(1, std::min(n, kChunkRows));
+  const int64_t tiles = (rows + M->tile_rows - 1) / M->tile_rows;
+  return gram_fixed_ws_doubles(M) * 8 + tiles * rec_tile_bytes(M) + 512;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -563,6 +526,7 @@ __device__ __forceinline__ void st_s32(uint32_t a, uint32_t v) { asm volatile("s
 __device__ __forceinline__ void ld_stterm(uint32_t a, double& lo, double& inv, double& dn, int& kind, int& nint1, int& feature,
                                           int& slot0, int& idx_base, int& coef_offset) {
   int term;
+  (void)term;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(lo), "=d"(inv) : "r"(a));
   asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(dn) : "r"(a));
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+32];" : "=r"(kind), "=r"(nint1), "=r"(feature), "=r"(slot0) : "r"(a));
@@ -662,25 +626,6 @@ __device__ __noinline__ void phase_b_half(const DHalf* hp, int tile_n, uint32_t 
   }
 }
 
-struct StTerm;
-struct GramSmem {
-  DStep* steps;    // the role's steps
-  StTerm* rt;      // the role's terms, compact
-  double* xs[kStages];   // raw columns of the tile being staged and of the next ones
-  float* ws[kStages];
-  unsigned long long* mbar;
-  double* acc;
-  double* rec_val[2];
-  uint32_t* rec_idx[2];
-  double* rec_w;
-  double* lp_part;
-  double* s_beta;
-  double* s_red;
-  DTerm* s_terms;
-};
-
-// named barriers (0 is __syncthreads): the producer and the consumer warps of a CTA hand the two
-// record buffers back and forth; arrive does not wait
 template <int ID>
 __device__ __forceinline__ void bar_sync_id(int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(nthreads) : "memory");
@@ -689,31 +634,31 @@ template <int ID>
 __device__ __forceinline__ void bar_arrive_id(int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(nthreads) : "memory");
 }
-enum { kBarFull = 1, kBarEmpty = 3, kBarProd = 5 };
+// named barriers 1 .. kNBuf ("record buffer b is free again"); 0 is __syncthreads
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
   switch (id) {
     case 1: bar_sync_id<1>(nthreads); break;
     case 2: bar_sync_id<2>(nthreads); break;
-    case 3: bar_sync_id<3>(nthreads); break;
-    case 4: bar_sync_id<4>(nthreads); break;
-    default: bar_sync_id<5>(nthreads); break;
+    default: bar_sync_id<3>(nthreads); break;
   }
 }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
   switch (id) {
     case 1: bar_arrive_id<1>(nthreads); break;
     case 2: bar_arrive_id<2>(nthreads); break;
-    case 3: bar_arrive_id<3>(nthreads); break;
-    default: bar_arrive_id<4>(nthreads); break;
+    default: bar_arrive_id<3>(nthreads); break;
   }
 }
 
-__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
-}
-
-// compact per-role-term descriptor the producers work from (built in shared memory at kernel
-// start): everything the common record kinds need without touching the full DTerm
+// ----------------------------------------------------------------------------------------
+// kernel 1: records.  Per data row: basis values of every term, lp, the IRLS step (mu, W, mask,
+// working response; pygam.py:764-777) or the response of _initial_estimate, and the row's record
+// = (sqrt(omega) * value, index inside the coefficient group) per slot, written to HBM tile by
+// tile in the slot-major layout the accumulation kernel bulk-copies: values [tile][slot][pitch],
+// indices [tile][slot][pitch].  Also the log scalars of the iteration.
+// ----------------------------------------------------------------------------------------
+// compact per-term descriptor (built in shared memory at kernel start): everything the common
+// record kinds need without touching the full DTerm
 enum { kStCubic = 0, kStIntercept = 1, kStLinear = 2, kStRhs = 3, kStGeneric = 4 };
 struct __align__(16) StTerm {
   double lo, inv, dn, pad0;  // cubic spline: edge knot, 1 / span, number of intervals
@@ -721,78 +666,30 @@ struct __align__(16) StTerm {
   int32_t idx_base, term, coef_offset, pad1;
 };
 
-struct StageArgs {
-  const StTerm* rt;
-  const DRoleTerm* g_rterms;
+struct RecArgs {
+  const StTerm* rt;      // [n_rt] every term, the rhs last
   const DTerm* s_terms;
-  const double* X;
-  const double* y;
-  const float* w;
-  const double* wz;
   const double* s_beta;
-  double* lp_part;
-  double* rec_w;
-  double* xs[kStages];   // raw columns of a tile: [F][T] features, then [T] y (inline) or [2T] (sqrt(omega), sqrt(omega) z) (split)
-  float* ws[kStages];    // [T] prior weights
-  unsigned long long* mbar;  // [kStages] completion barriers of the stage buffers
-  int64_t ld, n;
+  double* lp_part;       // [n_rt][T]
+  double* rec_w;         // [T]
+  const double* xs;      // raw columns of the tile: [F][T] features, then [T] y
+  const float* ws;       // [T] prior weights
   Family fam;
-  int mode, inline_irls, T, TP, F, bulk_ok;
+  int mode, T, TP, F, n_rt, n_slots, has_w;
 };
 
-// Fetch one tile's raw columns into stage buffer b: TMA bulk copies (one per column, issued by
-// producer thread 0, completing on the buffer's mbarrier) when everything is 16-byte aligned,
-// plain loads by all producer threads for unaligned inputs and the ragged last tile.
-__device__ __forceinline__ void stage_fetch(const StageArgs& A, int64_t row0, int rows, int b, int ptid, int pn) {
-  double* xs = A.xs[b];
-  const int T = A.T;
-  double* tail = xs + (size_t)A.F * T;
-  const uint32_t bar = smem_u32(A.mbar + b);
-  if (A.bulk_ok && (rows & 3) == 0) {
-    if (ptid == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this buffer vs the async writes
-      const uint32_t bytes = (uint32_t)(A.F * rows * 8 + (A.inline_irls ? rows * 8 + (A.w ? rows * 4 : 0) : rows * 16));
-      mbar_expect_tx(bar, bytes);
-      for (int f = 0; f < A.F; ++f) bulk_g2s(smem_u32(xs + (size_t)f * T), A.X + (int64_t)f * A.ld + row0, rows * 8, bar);
-      if (A.inline_irls) {
-        bulk_g2s(smem_u32(tail), A.y + row0, rows * 8, bar);
-        if (A.w) bulk_g2s(smem_u32(A.ws[b]), A.w + row0, rows * 4, bar);
-      } else {
-        bulk_g2s(smem_u32(tail), A.wz + 2 * row0, rows * 16, bar);
-      }
-    }
-    return;
-  }
-  for (int e = ptid; e < A.F * rows; e += pn) {
-    const int f = e / rows, r = e - f * rows;
-    xs[(size_t)f * T + r] = __ldg(A.X + (int64_t)f * A.ld + row0 + r);
-  }
-  if (A.inline_irls) {
-    for (int r = ptid; r < rows; r += pn) tail[r] = __ldg(A.y + row0 + r);
-    if (A.w)
-      for (int r = ptid; r < rows; r += pn) A.ws[b][r] = __ldg(A.w + row0 + r);
-  } else {
-    for (int r = ptid; r < 2 * rows; r += pn) tail[r] = __ldg(A.wz + 2 * row0 + r);
-  }
-  if (ptid == 0) mbar_arrive(bar);  // visibility of the plain stores: the producers' barrier of the consuming trip
-}
-
-// Phase A of one tile, run by the producer warps (ptid = thread index among them, pn = their
-// count) on the raw columns staged in shared memory: one thread per (row, term), four items per
-// trip -- all loads and the arithmetic of the four items first (independent chains the scheduler can
-// interleave), then their record stores.  Split roles read (sqrt(omega), sqrt(omega) z) written by
-// irls_rows_kernel; a single role evaluates the IRLS step itself: term contributions to lp, then
-// one thread per row, then the records are scaled by sqrt(omega).
+// one tile: one thread per (row, term), U items per trip -- all loads and the arithmetic of the
+// items first (independent chains the scheduler can interleave), then their record stores; then one
+// thread per row for the IRLS step; then the records are scaled by sqrt(omega)
 template <int U>
-__device__ __forceinline__ void stage_tile(const DRole& role, const StageArgs& A, int b, int tile_n, double* rec_val,
-                                           uint32_t* rec_idx, int ptid, int pn, double* sc) {
-  const int TP = A.TP, T = A.T, inl = A.inline_irls;
-  const double* xs = A.xs[b];
+__device__ __forceinline__ void records_tile(const RecArgs& A, int tile_n, double* rec_val, uint32_t* rec_idx, double* sc) {
+  const int TP = A.TP, T = A.T, ptid = threadIdx.x, pn = blockDim.x;
+  const double* xs = A.xs;
   const double* tail = xs + (size_t)A.F * T;
   // explicit shared-space addresses: everything the common kinds touch goes through ld/st.shared
   const uint32_t xs_a = smem_u32(xs), tail_a = smem_u32(tail), rt_a = smem_u32(A.rt), beta_a = smem_u32(A.s_beta);
   const uint32_t lpp_a = smem_u32(A.lp_part), val_a = smem_u32(rec_val), idx_a = smem_u32(rec_idx), recw_a = smem_u32(A.rec_w);
-  const int n_items = tile_n * role.n_rterms;
+  const int n_items = tile_n * A.n_rt;
   const float inv_tn = 1.0f / (float)tile_n;
   for (int it0 = ptid; it0 < n_items; it0 += U * pn) {
     double v[U][4];
@@ -811,7 +708,6 @@ __device__ __forceinline__ void stage_tile(const DRole& role, const StageArgs& A
       at[j] = slot0 * TP + rI;
       i0[j] = idx_base;
       double lp = 0.0;
-      const double scale = inl ? 1.0 : ld_s64(tail_a + 16 * rI);
       if (kind == kStCubic) {
         const double u = (ld_s64(xs_a + 8 * (feature * T + rI)) - lo) * inv;
         if (u >= 0.0 && u <= 1.0) {
@@ -819,11 +715,9 @@ __device__ __forceinline__ void stage_tile(const DRole& role, const StageArgs& A
           const int i = min((int)s, nint1);
           double b0, b1, b2, b3;
           cubic_bspline(s - (double)i, b0, b1, b2, b3);
-          if (inl) {
-            const uint32_t bc = beta_a + 8 * (coef_offset + i);
-            lp = fma(b3, ld_s64(bc + 24), fma(b2, ld_s64(bc + 16), fma(b1, ld_s64(bc + 8), b0 * ld_s64(bc))));
-          }
-          v[j][0] = b0 * scale; v[j][1] = b1 * scale; v[j][2] = b2 * scale; v[j][3] = b3 * scale;
+          const uint32_t bc = beta_a + 8 * (coef_offset + i);
+          lp = fma(b3, ld_s64(bc + 24), fma(b2, ld_s64(bc + 16), fma(b1, ld_s64(bc + 8), b0 * ld_s64(bc))));
+          v[j][0] = b0; v[j][1] = b1; v[j][2] = b2; v[j][3] = b3;
           i0[j] += i;
           nv[j] = 4;
         } else {
@@ -831,21 +725,19 @@ __device__ __forceinline__ void stage_tile(const DRole& role, const StageArgs& A
           gr[j] = rI;
         }
       } else if (kind == kStIntercept) {
-        if (inl) lp = ld_s64(beta_a + 8 * coef_offset);
-        v[j][0] = scale;
+        lp = ld_s64(beta_a + 8 * coef_offset);
+        v[j][0] = 1.0;
         nv[j] = 1;
       } else if (kind == kStLinear) {
         const double x = ld_s64(xs_a + 8 * (feature * T + rI));
-        if (inl) lp = x * ld_s64(beta_a + 8 * coef_offset);
-        v[j][0] = x * scale;
+        lp = x * ld_s64(beta_a + 8 * coef_offset);
+        v[j][0] = x;
         nv[j] = 1;
-      } else if (kind == kStRhs) {
-        if (!inl) { v[j][0] = ld_s64(tail_a + 16 * rI + 8); nv[j] = 1; }
-      } else {
+      } else if (kind == kStGeneric) {
         gq[j] = q;
         gr[j] = rI;
       }
-      if (inl && kind != kStRhs && gq[j] < 0) st_s64(lpp_a + 8 * (q * T + rI), lp);
+      if (kind != kStRhs && gq[j] < 0) st_s64(lpp_a + 8 * (q * T + rI), lp);
     }
 #pragma unroll
     for (int j = 0; j < U; ++j) {
@@ -862,122 +754,82 @@ __device__ __forceinline__ void stage_tile(const DRole& role, const StageArgs& A
       const StTerm& t = A.rt[gq[j]];
       const DTerm& d = A.s_terms[t.term];
       const int at2 = t.slot0 * TP + gr[j];
-      EmitRec e{rec_val + at2, rec_idx + at2, inl ? A.s_beta : nullptr, 0.0, inl ? 1.0 : tail[2 * gr[j]], TP, d.coef_offset, t.idx_base};
+      EmitRec e{rec_val + at2, rec_idx + at2, A.s_beta, 0.0, 1.0, TP, d.coef_offset, t.idx_base};
       const LoadTile load{xs, T, gr[j]};
       eval_term(d, load, e);
-      if (inl) A.lp_part[gq[j] * T + gr[j]] = e.lp;
+      A.lp_part[gq[j] * T + gr[j]] = e.lp;
     }
   }
-  if (inl) {
-    bar_sync(kBarProd, pn);
-    const int rhs_q = role.n_rterms - 1;  // the rhs is the last role term when present
-    for (int rI = ptid; rI < tile_n; rI += pn) {
-      double lp = 0.0;
-      for (int q = 0; q < role.n_rterms; ++q)
-        if (q != rhs_q || role.rhs_slot < 0) lp += ld_s64(lpp_a + 8 * (q * T + rI));
-      const double yi = ld_s64(tail_a + 8 * rI);
-      double sw, z;
-      if (A.mode == PGB_MODE_IRLS) {
-        const double winv = A.w ? (double)__fdiv_rn(1.0f, ld_s32f(smem_u32(A.ws[b]) + 4 * rI)) : 1.0;
-        const IrlsRow r = irls_row(A.fam, lp, yi, winv);
-        sw = r.sw;
-        z = r.z;
-        if (r.keep) {
-          sc[PGB_GS_NUSED] += 1.0;
-          sc[PGB_GS_DEV] += dist_dev(A.fam, yi, r.mu);
-          sc[PGB_GS_NCORRECT] += (yi == ((r.mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
-        }
-      } else {
-        sw = 1.0;
-        z = init_response(A.fam, yi);
+  __syncthreads();
+  const StTerm& rhs = A.rt[A.n_rt - 1];
+  for (int rI = ptid; rI < tile_n; rI += pn) {
+    double lp = 0.0;
+    for (int q = 0; q < A.n_rt - 1; ++q) lp += ld_s64(lpp_a + 8 * (q * T + rI));
+    const double yi = ld_s64(tail_a + 8 * rI);
+    double sw, z;
+    if (A.mode == PGB_MODE_IRLS) {
+      const double winv = A.has_w ? (double)__fdiv_rn(1.0f, ld_s32f(smem_u32(A.ws) + 4 * rI)) : 1.0;
+      const IrlsRow r = irls_row(A.fam, lp, yi, winv);
+      sw = r.sw;
+      z = r.z;
+      if (r.keep) {
         sc[PGB_GS_NUSED] += 1.0;
-        if (!isfinite(z)) sc[PGB_GS_NONFINITE] += 1.0;
+        sc[PGB_GS_DEV] += dist_dev(A.fam, yi, r.mu);
+        sc[PGB_GS_NCORRECT] += (yi == ((r.mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
       }
-      sc[PGB_GS_NROWS] += 1.0;
-      st_s64(recw_a + 8 * rI, sw);
-      if (role.rhs_slot >= 0) {
-        st_s64(val_a + 8 * (role.rhs_slot * TP + rI), z);
-        st_s32(idx_a + 4 * (role.rhs_slot * TP + rI), (uint32_t)A.rt[rhs_q].idx_base);
-      }
+    } else {
+      sw = 1.0;
+      z = init_response(A.fam, yi);
+      sc[PGB_GS_NUSED] += 1.0;
+      if (!isfinite(z)) sc[PGB_GS_NONFINITE] += 1.0;
     }
-    bar_sync(kBarProd, pn);
-    // scale the records by sqrt(omega); phase B works on row pairs: the odd row out contributes zeros
-    const int tn2 = (tile_n + 1) & ~1;
-    const float inv_t2 = 1.0f / (float)tn2;
-    for (int e = ptid; e < role.n_slots * tn2; e += pn) {
-      const int s = (int)(((float)e + 0.5f) * inv_t2), rI = e - s * tn2;
-      const uint32_t a = val_a + 8 * (s * TP + rI);
-      st_s64(a, (rI < tile_n) ? ld_s64(a) * ld_s64(recw_a + 8 * rI) : 0.0);
-    }
-  } else if (tile_n & 1) {
-    for (int s = ptid; s < role.n_slots; s += pn) st_s64(val_a + 8 * (s * TP + tile_n), 0.0);
+    sc[PGB_GS_NROWS] += 1.0;
+    st_s64(recw_a + 8 * rI, sw);
+    st_s64(val_a + 8 * (rhs.slot0 * TP + rI), z);
+    st_s32(idx_a + 4 * (rhs.slot0 * TP + rI), (uint32_t)rhs.idx_base);
+  }
+  __syncthreads();
+  // scale the records by sqrt(omega); the accumulation works on row pairs: the odd row out contributes zeros
+  const int tn2 = (tile_n + 1) & ~1;
+  const float inv_t2 = 1.0f / (float)tn2;
+  for (int e = ptid; e < A.n_slots * tn2; e += pn) {
+    const int s = (int)(((float)e + 0.5f) * inv_t2), rI = e - s * tn2;
+    const uint32_t a = val_a + 8 * (s * TP + rI);
+    st_s64(a, (rI < tile_n) ? ld_s64(a) * ld_s64(recw_a + 8 * rI) : 0.0);
   }
 }
 
-// Shared-memory record of a tile: for every slot of the role, value = sqrt(omega) * b (the rhs
-// slot holds sqrt(omega) * z) and index = position of the coefficient inside its group.
-// G = sum (sqrt(omega) b)(sqrt(omega) b)^T is then a plain outer product of the record with
-// itself -- the same arithmetic as the reference's W.B (pygam.py:782) before its QR.
-// Warps 0 .. role.n_warps-1 are consumers (phase B: accumulation, bound by the shared-memory
-// pipe); the remaining warps are producers (phase A: basis, link, weight -> records of the next
-// tile, bound by HBM latency and the fp64 pipe).  Two record buffers, named barriers full/empty.
-__global__ void __launch_bounds__(32 * (kMaxWarps + kMaxProducers))
-gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const DStep* __restrict__ g_steps,
-                  const DWarp* __restrict__ g_warps, const DRoleTerm* __restrict__ g_rterms,
-                  const DRole* __restrict__ g_roles, int n_roles, Family fam, int mode, int inline_irls,
-                  const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
-                  const float* __restrict__ w, const double* __restrict__ beta, const double* __restrict__ wz,
-                  int T, int F, int dbg, int bulk_ok, double* __restrict__ partials, double* __restrict__ scal_part) {
+__global__ void __launch_bounds__(kRecThreads, 3)
+gram_records_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const DRoleTerm* __restrict__ g_rterms, int n_slots,
+                    Family fam, int mode, const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
+                    const float* __restrict__ w, const double* __restrict__ beta, int T, int F, double* __restrict__ rec_val_g,
+                    uint32_t* __restrict__ rec_idx_g, double* __restrict__ scal_part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int ridx = 0;
-  while (ridx + 1 < n_roles && (int)blockIdx.x >= g_roles[ridx + 1].cta0) ++ridx;
-  const DRole role = g_roles[ridx];
-  const int cta_in_role = blockIdx.x - role.cta0;
-  const int S = role.n_slots, TP = (T + 2) | 1;
+  const int TP = T + 2, n_rt = n_terms + 1, tid = threadIdx.x;
+  double* rec_val = reinterpret_cast<double*>(smem_raw);            // [n_slots][TP]
+  double* xs = rec_val + (size_t)n_slots * TP;                       // [F + 1][T]
+  double* rec_w = xs + (size_t)(F + 1) * T;                          // [T]
+  double* lp_part = rec_w + T;                                       // [n_rt][T]
+  double* s_beta = lp_part + (size_t)n_rt * T;
+  double* s_red = s_beta + ((m + 1) & ~1);
+  StTerm* rt = reinterpret_cast<StTerm*>(s_red + PGB_GS_COUNT * 32);  // 16-byte aligned: everything before is a multiple of 16
+  DTerm* s_terms = reinterpret_cast<DTerm*>(rt + n_rt);
+  uint32_t* rec_idx = reinterpret_cast<uint32_t*>(s_terms + n_terms);  // [n_slots][TP]
+  float* ws = reinterpret_cast<float*>(rec_idx + (size_t)n_slots * TP);  // [T]
 
-  GramSmem sm;
-  sm.acc = reinterpret_cast<double*>(smem_raw);
-  sm.rec_val[0] = sm.acc + role.acc_size;
-  sm.rec_val[1] = sm.rec_val[0] + (size_t)S * TP;
-  sm.rec_w = sm.rec_val[1] + (size_t)S * TP;
-  sm.lp_part = sm.rec_w + T;  // [n_rterms][T], only when the role computes the IRLS step inline
-  sm.s_beta = sm.lp_part + (inline_irls ? (size_t)T * role.n_rterms : 0);
-  sm.s_red = sm.s_beta + ((m + 1) & ~1);
-  sm.s_terms = reinterpret_cast<DTerm*>(sm.s_red + PGB_GS_COUNT * 32);
-  sm.rec_idx[0] = reinterpret_cast<uint32_t*>(sm.s_terms + n_terms);
-  sm.rec_idx[1] = sm.rec_idx[0] + (size_t)S * TP;
-  sm.steps = reinterpret_cast<DStep*>(sm.rec_idx[0] + (((size_t)2 * S * TP + 1) & ~(size_t)1));
-  sm.rt = reinterpret_cast<StTerm*>(sm.steps + role.n_steps);
-  sm.xs[0] = reinterpret_cast<double*>(sm.rt + role.n_rterms);
-  for (int q = 1; q < kStages; ++q) sm.xs[q] = sm.xs[q - 1] + (size_t)(F + 2) * T;
-  sm.ws[0] = reinterpret_cast<float*>(sm.xs[kStages - 1] + (size_t)(F + 2) * T);
-  for (int q = 1; q < kStages; ++q) sm.ws[q] = sm.ws[q - 1] + T;
-  sm.mbar = reinterpret_cast<unsigned long long*>(sm.ws[kStages - 1] + T);  // T is a multiple of 8: 8-byte aligned
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int64_t i = tid; i < role.acc_size; i += blockDim.x) sm.acc[i] = 0.0;
-  for (int i = tid; i < 2 * S * TP; i += blockDim.x) { sm.rec_val[0][i] = 0.0; sm.rec_idx[0][i] = 0u; }  // padding slots stay zero
-  if (inline_irls) for (int i = tid; i < m; i += blockDim.x) sm.s_beta[i] = (mode == PGB_MODE_IRLS) ? beta[i] : 0.0;
-  load_terms_smem(sm.s_terms, g_terms, n_terms);
-  if (tid == 0) {
-    for (int q = 0; q < kStages; ++q) mbar_init(smem_u32(sm.mbar + q), 1);
-    fence_mbar_init();
-  }
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(g_steps + role.step0);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sm.steps);
-    for (int i = tid; i < role.n_steps * (int)(sizeof(DStep) / 4); i += blockDim.x) dst[i] = src[i];
-  }
+  for (int i = tid; i < n_slots * TP; i += blockDim.x) { rec_val[i] = 0.0; rec_idx[i] = 0u; }  // padding slots stay zero
+  for (int i = tid; i < m; i += blockDim.x) s_beta[i] = (mode == PGB_MODE_IRLS) ? beta[i] : 0.0;
+  load_terms_smem(s_terms, g_terms, n_terms);
   __syncthreads();
-  for (int i = tid; i < role.n_rterms; i += blockDim.x) {
-    const DRoleTerm rt = g_rterms[role.term0 + i];
+  for (int i = tid; i < n_rt; i += blockDim.x) {
+    const DRoleTerm r = g_rterms[i];
     StTerm t{};
-    t.slot0 = rt.slot0;
-    t.idx_base = rt.idx_base;
-    t.term = rt.term;
+    t.slot0 = r.slot0;
+    t.idx_base = r.idx_base;
+    t.term = r.term;
     t.kind = kStRhs;
-    if (rt.term >= 0) {
-      const DTerm& d = sm.s_terms[rt.term];
+    if (r.term >= 0) {
+      const DTerm& d = s_terms[r.term];
       const DMarg& mg = d.marg[0];
       t.kind = d.fast ? kStCubic : d.kind == PGB_TERM_INTERCEPT ? kStIntercept : d.kind == PGB_TERM_LINEAR ? kStLinear : kStGeneric;
       t.lo = mg.lo;
@@ -987,58 +839,126 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
       t.feature = mg.feature;
       t.coef_offset = d.coef_offset;
     }
-    sm.rt[i] = t;
+    rt[i] = t;
   }
   __syncthreads();
 
   double sc[PGB_GS_COUNT];
 #pragma unroll
   for (int s = 0; s < PGB_GS_COUNT; ++s) sc[s] = 0.0;
+  const RecArgs A{rt, s_terms, s_beta, lp_part, rec_w, xs, ws, fam, mode, T, TP, F, n_rt, n_slots, w != nullptr};
+  const int64_t n_tiles = (n + T - 1) / T;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * T;
+    const int tile_n = (int)min((int64_t)T, n - row0);
+    // raw columns of the tile: coalesced loads, every thread busy
+    for (int e = tid; e < (F + 1) * tile_n; e += blockDim.x) {
+      const int f = e / tile_n, r = e - f * tile_n;
+      xs[(size_t)f * T + r] = (f < F) ? __ldg(X + (int64_t)f * ld + row0 + r) : __ldg(y + row0 + r);
+    }
+    if (w)
+      for (int r = tid; r < tile_n; r += blockDim.x) ws[r] = __ldg(w + row0 + r);
+    __syncthreads();
+    records_tile<2>(A, tile_n, rec_val, rec_idx, sc);
+    __syncthreads();
+    // copy the tile's records out: 16 bytes per thread, fully coalesced
+    {
+      const int nv2 = n_slots * TP / 2, ni4 = n_slots * TP / 4;  // TP is even, n_slots a multiple of 4
+      double2* dv = reinterpret_cast<double2*>(rec_val_g + (size_t)tile * n_slots * TP);
+      const double2* sv = reinterpret_cast<const double2*>(rec_val);
+      for (int e = tid; e < nv2; e += blockDim.x) dv[e] = sv[e];
+      uint4* di = reinterpret_cast<uint4*>(rec_idx_g + (size_t)tile * n_slots * TP);
+      const uint4* si = reinterpret_cast<const uint4*>(rec_idx);
+      for (int e = tid; e < ni4; e += blockDim.x) di[e] = si[e];
+    }
+    __syncthreads();
+  }
+  block_reduce_store<PGB_GS_COUNT>(sc, s_red, scal_part + (int64_t)blockIdx.x * PGB_GS_COUNT);
+}
 
-  // rows of this CTA: a contiguous slice of [0, n) in units of T rows
+// ----------------------------------------------------------------------------------------
+// kernel 2: accumulation.  G = sum over rows of record (x) record: the same arithmetic as the
+// reference's W.B (pygam.py:782) before its QR.  A CTA works for one role: it keeps the role's
+// blocks of G in shared memory and walks its slice of the tiles.  Warps 0 .. n_warps-1 are
+// consumers (phase_b_half); lane 0 of the next warp is the producer: TMA bulk copies of the role's
+// record slots of a tile (one per run of slots, values and indices) into a ring of kNBuf buffers,
+// completion on mbarriers; the consumers hand a buffer back through a named barrier.
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * (kMaxWarps + 1))
+gram_accum_kernel(const DStep* __restrict__ g_steps, const DWarp* __restrict__ g_warps, const DRun* __restrict__ g_runs,
+                  const DRole* __restrict__ g_roles, int n_roles, const double* __restrict__ rec_val_g,
+                  const uint32_t* __restrict__ rec_idx_g, int64_t n, int T, int n_slots_all, int dbg,
+                  double* __restrict__ partials) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int ridx = 0;
+  while (ridx + 1 < n_roles && (int)blockIdx.x >= g_roles[ridx + 1].cta0) ++ridx;
+  const DRole role = g_roles[ridx];
+  const int cta_in_role = blockIdx.x - role.cta0;
+  const int S = role.n_slots, TP = T + 2;
+
+  double* acc = reinterpret_cast<double*>(smem_raw);
+  double* rec_val = acc + role.acc_size;                                          // [kNBuf][S][TP]
+  uint32_t* rec_idx = reinterpret_cast<uint32_t*>(rec_val + (size_t)kNBuf * S * TP);  // [kNBuf][S][TP]
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(rec_idx + (size_t)kNBuf * S * TP);
+  DStep* steps = reinterpret_cast<DStep*>(mbar + kNBuf);
+  DRun* runs = reinterpret_cast<DRun*>(steps + role.n_steps);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t i = tid; i < role.acc_size; i += blockDim.x) acc[i] = 0.0;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(g_steps + role.step0);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(steps);
+    for (int i = tid; i < role.n_steps * (int)(sizeof(DStep) / 4); i += blockDim.x) dst[i] = src[i];
+    for (int i = tid; i < role.n_runs; i += blockDim.x) runs[i] = g_runs[role.run0 + i];
+  }
+  if (tid == 0) {
+    for (int q = 0; q < kNBuf; ++q) mbar_init(smem_u32(mbar + q), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // tiles of this CTA: a contiguous slice
   const int64_t n_tiles = (n + T - 1) / T;
   const int64_t tiles_lo = n_tiles * cta_in_role / role.n_ctas;
   const int64_t tiles_hi = n_tiles * (cta_in_role + 1) / role.n_ctas;
-  auto rows_of = [&](int64_t tile) { return (int)min((int64_t)T, n - tile * T); };
-  const int nthreads = blockDim.x;
+  const int nbar = 32 * (role.n_warps + 1);  // consumers + the producer warp
 
-  if (warp >= role.n_warps) {
-    // ---------------- producers ----------------
-    const int ptid = tid - 32 * role.n_warps, pn = nthreads - 32 * role.n_warps;
-    DRole prole = role;
-    prole.term0 = 0;  // the role's terms are read from their shared-memory copy
-    StageArgs A{sm.rt, g_rterms, sm.s_terms, X, y, w, wz, sm.s_beta, sm.lp_part, sm.rec_w, {}, {}, sm.mbar, ld, n, fam, mode,
-                inline_irls, T, TP, F, bulk_ok};
-    for (int q = 0; q < kStages; ++q) { A.xs[q] = sm.xs[q]; A.ws[q] = sm.ws[q]; }
-    // raw columns are fetched kStages - 1 tiles ahead
-    auto fetch = [&](int64_t tile, int b) {
-      if (tile < tiles_hi && !(dbg & 4)) stage_fetch(A, tile * T, rows_of(tile), b, ptid, pn);  // dbg 4: no fetch
-    };
-    for (int q = 0; q < kStages - 1; ++q) fetch(tiles_lo + q, q);
-    int buf = 0, sb = 0;
-    uint32_t phases = 0u;  // bit b: parity the next wait on stage buffer b expects
-    for (int64_t tile = tiles_lo; tile < tiles_hi; ++tile, buf ^= 1, sb = (sb + 1) % kStages) {
-      if (!(dbg & 4)) mbar_wait(smem_u32(sm.mbar + sb), (phases >> sb) & 1u);
-      phases ^= 1u << sb;
-      bar_sync(kBarProd, pn);  // this tile's raw columns have landed; everyone is done with the previous tile's
-      fetch(tile + kStages - 1, (sb + kStages - 1) % kStages);
-      if (tile >= tiles_lo + 2) bar_sync(kBarEmpty + buf, nthreads);  // the consumers are done with this record buffer
-      if (!(dbg & 1) || tile < tiles_lo + 2)  // dbg 1: stage only the first two tiles (consumer-only timing)
-        stage_tile<PGB_STAGE_U>(prole, A, sb, rows_of(tile), sm.rec_val[buf], sm.rec_idx[buf], ptid, pn, sc);
-      bar_arrive(kBarFull + buf, nthreads);
+  if (warp == role.n_warps) {
+    // ---------------- producer ----------------
+    const uint32_t bytes = (uint32_t)((size_t)S * TP * kSlotBytes);
+    int b = 0;
+    for (int64_t tile = tiles_lo; tile < tiles_hi; ++tile, b = (b + 1 == kNBuf) ? 0 : b + 1) {
+      if (tile >= tiles_lo + kNBuf) bar_sync(1 + b, nbar);  // the consumers are done with this buffer
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the consumers' generic reads vs the async writes
+        const uint32_t bar = smem_u32(mbar + b);
+        mbar_expect_tx(bar, bytes);
+        const double* gv = rec_val_g + (size_t)tile * n_slots_all * TP;
+        const uint32_t* gi = rec_idx_g + (size_t)tile * n_slots_all * TP;
+        double* sv = rec_val + (size_t)b * S * TP;
+        uint32_t* si = rec_idx + (size_t)b * S * TP;
+        for (int q = 0; q < role.n_runs; ++q) {
+          const DRun r = runs[q];
+          bulk_g2s(smem_u32(sv + (size_t)r.lslot0 * TP), gv + (size_t)r.gslot0 * TP, (uint32_t)(r.n_slots * TP * 8), bar);
+          bulk_g2s(smem_u32(si + (size_t)r.lslot0 * TP), gi + (size_t)r.gslot0 * TP, (uint32_t)(r.n_slots * TP * 4), bar);
+        }
+      }
+      __syncwarp();
     }
-  } else {
+  } else if (warp < role.n_warps) {
     // ---------------- consumers: every warp walks the tile once per step ----------------
     const DWarp wp = g_warps[role.warp0 + warp];
     const int half = lane >> 4, lu = (lane >> 2) & 3, lt = lane & 3;
-    const uint32_t acc_u32 = smem_u32(sm.acc);
-    int buf = 0;
-    for (int64_t tile = tiles_lo; tile < tiles_hi; ++tile, buf ^= 1) {
-      bar_sync(kBarFull + buf, nthreads);
-      const int tile_n = rows_of(tile);
-      const uint32_t val_u32 = smem_u32(sm.rec_val[buf]), idx_u32 = smem_u32(sm.rec_idx[buf]);
-      for (int s = 0; s < ((dbg & 2) ? 0 : wp.n_steps); ++s) {  // dbg 2: no accumulation (producer-only timing)
-        const DHalf* hp = &sm.steps[wp.step0 - role.step0 + s].h[half];
+    const uint32_t acc_u32 = smem_u32(acc);
+    uint32_t phases = 0u;  // bit b: parity the next wait on buffer b expects
+    int b = 0;
+    for (int64_t tile = tiles_lo; tile < tiles_hi; ++tile, b = (b + 1 == kNBuf) ? 0 : b + 1) {
+      mbar_wait(smem_u32(mbar + b), (phases >> b) & 1u);
+      phases ^= 1u << b;
+      const int tile_n = (int)min((int64_t)T, n - tile * T);
+      const uint32_t val_u32 = smem_u32(rec_val + (size_t)b * S * TP), idx_u32 = smem_u32(rec_idx + (size_t)b * S * TP);
+      for (int s = 0; s < ((dbg & 2) ? 0 : wp.n_steps); ++s) {  // dbg 2: no accumulation (timing experiments)
+        const DHalf* hp = &steps[wp.step0 - role.step0 + s].h[half];
         // items in flight: the larger of the two half-steps (warp-uniform trip count)
         int kk = 0, dg = 0;
 #pragma unroll
@@ -1067,14 +987,13 @@ gram_accum_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const D
           }
         }
       }
-      if (tile + 2 < tiles_hi) bar_arrive(kBarEmpty + buf, nthreads);
+      if (tile + kNBuf < tiles_hi) bar_arrive(1 + b, nbar);
     }
   }
   __syncthreads();
   // ---------------- write the partial ----------------
   double* dst = partials + role.part_off + (int64_t)cta_in_role * role.acc_size;
-  for (int64_t i = tid; i < role.acc_size; i += blockDim.x) dst[i] = sm.acc[i];
-  if (inline_irls) block_reduce_store<PGB_GS_COUNT>(sc, sm.s_red, scal_part + (int64_t)blockIdx.x * PGB_GS_COUNT);
+  for (int64_t i = tid; i < role.acc_size; i += blockDim.x) dst[i] = acc[i];
 }
 
 // out = [G (m*m, symmetric) | r (m)]: sum the CTA partials of each role in order, mirror
@@ -1117,48 +1036,51 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
     return PGB_EINVAL;
   }
   const int n_roles = (int)M->roles.size();
+  const int T = M->tile_rows, TP = tile_pitch(T);
   double* partials = (double*)ws;
   double* scal_part = partials + M->partial_doubles;
-  double* wz = scal_part + (int64_t)(M->gram_ctas + M->pass_ctas) * PGB_GS_COUNT;
+  // records of one chunk: values then indices, 256-byte aligned
+  const int64_t chunk_tiles = (std::min(n, kChunkRows) + T - 1) / T;
+  uintptr_t rp = (uintptr_t)(scal_part + (int64_t)M->rec_ctas * PGB_GS_COUNT);
+  rp = (rp + 255) & ~(uintptr_t)255;
+  double* rec_val = (double*)rp;
+  uint32_t* rec_idx = (uint32_t*)(rec_val + chunk_tiles * M->n_slots_all * TP);
   static thread_local bool attr_set = false;
   if (!attr_set) {
     PGB_CUDA(cudaFuncSetAttribute(gram_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    PGB_CUDA(cudaFuncSetAttribute(irls_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    PGB_CUDA(cudaFuncSetAttribute(gram_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
-  const int inline_irls = gram_inline(M) ? 1 : 0;
-  int scal_count = M->gram_ctas;
-  if (!inline_irls) {
-    const int grid = (int)std::min<int64_t>((n + kPassThreads - 1) / kPassThreads, M->pass_ctas);
-    const size_t smem = (size_t)((M->m + 1) & ~1) * 8 + (size_t)M->n_terms * sizeof(DTerm) + PGB_GS_COUNT * 32 * 8;
-    irls_rows_kernel<<<grid, kPassThreads, smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, X, n, ld, y,
-                                                       w, beta, wz, scal_part);
-    pgb_count_launch(1);
-    PGB_CUDA(cudaGetLastError());
-    scal_count = grid;
-  }
-  const int bulk_ok = ((((uintptr_t)X | (uintptr_t)y | (uintptr_t)w | (uintptr_t)wz) & 15) == 0 && (ld & 1) == 0) ? 1 : 0;  // TMA bulk copies need 16-byte alignment
   const char* edbg = getenv("PGB_GRAM_DEBUG");  // timing experiments only
   const int dbg = edbg ? atoi(edbg) : 0;
   pgb_model::Timing& tm = const_cast<pgb_model*>(M)->timing;
-  if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.ev[0], st));
-  gram_accum_kernel<<<M->gram_ctas, M->gram_threads, M->gram_smem, st>>>(
-      M->d_terms, M->n_terms, M->m, M->d_steps, M->d_warps, M->d_rterms, M->d_roles, n_roles, M->fam, mode,
-      inline_irls, X, n, ld, y, w, beta, wz, M->tile_rows, M->n_features, dbg, bulk_ok, partials, scal_part);
+  int chunk = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += kChunkRows, ++chunk) {
+    const int64_t nr = std::min(kChunkRows, n - r0);
+    const int64_t tiles = (nr + T - 1) / T;
+    const int grid1 = (int)std::min<int64_t>(tiles, M->rec_ctas);
+    if (tm.enabled && chunk == 0) PGB_CUDA(cudaEventRecord(tm.ev[0], st));
+    gram_records_kernel<<<grid1, kRecThreads, M->rec_smem, st>>>(M->d_terms, M->n_terms, M->m, M->d_rterms, M->n_slots_all,
+                                                                   M->fam, mode, X + r0, nr, ld, y + r0, w ? w + r0 : nullptr,
+                                                                   beta, T, M->n_features, rec_val, rec_idx, scal_part);
+    PGB_CUDA(cudaGetLastError());
+    gram_accum_kernel<<<M->gram_ctas, M->gram_threads, M->gram_smem, st>>>(M->d_steps, M->d_warps, M->d_runs, M->d_roles, n_roles,
+                                                                              rec_val, rec_idx, nr, T, M->n_slots_all, dbg, partials);
+    PGB_CUDA(cudaGetLastError());
+    const int acc_flag = (accumulate || chunk > 0) ? 1 : 0;
+    const int rb = 256;
+    gram_reduce_kernel<<<(unsigned)((M->map_size + rb - 1) / rb), rb, 0, st>>>(partials, M->d_roles, n_roles, M->d_elem_map,
+                                                                                M->map_size, M->m, out, acc_flag);
+    scalar_reduce_kernel<<<1, 32, 0, st>>>(scal_part, grid1, PGB_GS_COUNT, out + (int64_t)M->m * M->m + M->m, acc_flag);
+    pgb_count_launch(4);
+    PGB_CUDA(cudaGetLastError());
+  }
   if (tm.enabled) { PGB_CUDA(cudaEventRecord(tm.ev[1], st)); tm.pending = true; }
-  PGB_CUDA(cudaGetLastError());
-  const int rb = 256;
-  gram_reduce_kernel<<<(unsigned)((M->map_size + rb - 1) / rb), rb, 0, st>>>(
-      partials, M->d_roles, n_roles, M->d_elem_map, M->map_size, M->m, out, accumulate);
-  scalar_reduce_kernel<<<1, 32, 0, st>>>(scal_part, scal_count, PGB_GS_COUNT,
-                                         out + (int64_t)M->m * M->m + M->m, accumulate);
-  pgb_count_launch(3);
-  PGB_CUDA(cudaGetLastError());
   return PGB_OK;
 }
 
-// optional timing of the dominant kernel (gram_accum_kernel) with CUDA events recorded on the
-// launching stream; used by bench.py for the roofline figure
+// optional timing of the Gram pass kernels (records + accumulation + reductions of all chunks) with
+// CUDA events recorded on the launching stream; used by bench.py for the roofline figure
 extern "C" int pgb_gram_timing(pgb_model* M, int32_t enable) {
   if (!M) { pgb_set_error("pgb_gram_timing: null model"); return PGB_EINVAL; }
   pgb_model::Timing& tm = M->timing;

@@ -72,14 +72,19 @@ struct DRoleTerm {
   int32_t pad;
 };
 
+// a contiguous range of global record slots a role needs: one TMA bulk copy per tile
+struct DRun {
+  int32_t gslot0, lslot0, n_slots, pad;
+};
+
 struct DRole {
   int32_t warp0, n_warps;      // range in the warp table
-  int32_t term0, n_rterms;     // range in the role-term table (terms whose basis the role needs)
   int32_t n_slots;             // record slots per data row (4 per quad)
   int32_t needs_all_terms;     // role evaluates every term (inline IRLS possible)
   int32_t cta0, n_ctas;        // CTAs of the 1-d grid that work for this role
   int32_t rhs_slot, max_steps; // record slot of the virtual rhs entry (-1: none); longest warp
   int32_t step0, n_steps;      // range in the step table (copied to shared memory by every CTA)
+  int32_t run0, n_runs;        // range in the run table
   int64_t acc_size;            // doubles of the role's accumulator
   int64_t part_off;            // offset of the role's first partial inside the workspace (doubles)
   int64_t map_off;             // offset of the role's element map
@@ -92,19 +97,22 @@ struct pgb_model {
   std::vector<DBlock> blocks;
   std::vector<DStep> steps;
   std::vector<DWarp> warps;
-  std::vector<DRoleTerm> rterms;
+  std::vector<DRoleTerm> rterms;  // every term and the rhs with its global record slot
+  std::vector<DRun> runs;
   std::vector<DRole> roles;
   std::vector<int32_t> elem_map;  // per accumulator element: row * (m + 1) + col of G|r, or -1
   DTerm* d_terms = nullptr;
   DStep* d_steps = nullptr;
   DWarp* d_warps = nullptr;
   DRoleTerm* d_rterms = nullptr;
+  DRun* d_runs = nullptr;
   DRole* d_roles = nullptr;
   int32_t* d_elem_map = nullptr;
   Family fam{};
   int32_t n_terms = 0, n_features = 0, m = 0, k = 0, device = 0;
   int32_t tile_rows = 0, gram_threads = 256, gram_ctas = 0;
-  size_t gram_smem = 0;
+  size_t gram_smem = 0, rec_smem = 0;
+  int32_t n_slots_all = 0, rec_ctas = 0;
   int64_t partial_doubles = 0;  // doubles of all partials of all roles
   int64_t map_size = 0;
   int32_t pass_ctas = 0;        // CTAs of the O(k) passes
