@@ -203,25 +203,26 @@ def run_b200(args, rank, world, local_rank):
     launches0 = lib.pgb_launch_count()
     _lib.check(lib.pgb_gram_timing(eng.handle, 1), "pgb_gram_timing")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    accum_ms = []
+    accum_ms, rec_ms = [], []
     e0.record()
     for _ in range(args.steps):
         coef = step(coef)
-        f = C.c_float()
-        _lib.check(lib.pgb_gram_last_ms(eng.handle, C.byref(f)), "pgb_gram_last_ms")
+        f, r = C.c_float(), C.c_float()
+        _lib.check(lib.pgb_gram_last_ms(eng.handle, C.byref(r), C.byref(f)), "pgb_gram_last_ms")
         accum_ms.append(f.value)
+        rec_ms.append(r.value)
     e1.record()
     barrier()
     launches = lib.pgb_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     _lib.check(lib.pgb_gram_timing(eng.handle, 0), "pgb_gram_timing")
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    acc = torch.tensor([float(np.mean(accum_ms))], dtype=torch.float64, device=dev)
+    acc = torch.tensor([float(np.mean(accum_ms)), float(np.mean(rec_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(acc, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
-    accum = float(acc.item())
+    accum, records = float(acc[0].item()), float(acc[1].item())
     value = n * world / (ms_per_step * 1e-3)
 
     # ---- end to end: host buffers in, coefficients out, every step ----
@@ -273,17 +274,20 @@ def run_b200(args, rank, world, local_rank):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = n * BYTES_PER_ROW / (accum * 1e-3) / 1e9
-    fp64_tflops = n * FMA_PER_ROW * 2 / (accum * 1e-3) / 1e12
-    roofline = {"kernel": "gram_accum_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak,
+    gram_ms = accum + records
+    achieved = n * BYTES_PER_ROW / (gram_ms * 1e-3) / 1e9
+    fma_per_clk_sm = n * FMA_PER_ROW / (accum * 1e-3) / (148 * 1.965e9)
+    roofline = {"kernel": "gram_records_kernel + gram_accum_kernel (the Gram pass of one PIRLS iteration)", "bound": "hbm",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
-                "traffic": None, "kernel_ms": accum, "kernel_share_of_step": accum / ms_per_step,
-                "algorithmic_bytes_per_row": BYTES_PER_ROW,
-                "fp64": {"algorithmic_fma_per_row": FMA_PER_ROW, "achieved_tflops": fp64_tflops,
-                         "nominal_peak_tflops": 37.0, "frac_of_nominal": fp64_tflops / 37.0,
-                         "note": "902 fp64 FMA per row at 88 B per row = 20.5 flop/B: the Gram pass is bound by "
-                                 "the fp64 pipe and shared-memory accumulation, not HBM (SURVEY.md 8d)"}}
+                "traffic": None, "kernel_ms": gram_ms, "records_kernel_ms": records, "accum_kernel_ms": accum,
+                "kernel_share_of_step": gram_ms / ms_per_step, "algorithmic_bytes_per_row": BYTES_PER_ROW,
+                "shared_memory_rmw": {"algorithmic_fma_per_row": FMA_PER_ROW, "achieved_fma_per_clk_per_sm": fma_per_clk_sm,
+                                      "measured_peak_fma_per_clk_per_sm": 7.7, "frac": fma_per_clk_sm / 7.7,
+                                      "note": "the accumulation kernel scatters 902 fp64 FMA per row into data-dependent "
+                                              "elements of G held in shared memory: 16 B of shared-memory read-modify-write "
+                                              "per FMA at 128 B/clk/SM (tools/ubench.cu measures 7.7 FMA/clk/SM), 8x below "
+                                              "the fp64 pipe and far below HBM (DESIGN.md section 4)"}}
     line = {"metric": "rows/sec per PIRLS iteration", "value": value, "unit": "rows/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(world, n),

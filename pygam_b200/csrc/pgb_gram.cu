@@ -463,7 +463,8 @@ static void stage_free(pgb_model* M);
 
 void pgb_gram_release(pgb_model* M) {
   stage_free(M);
-  if (M->timing.ev[0]) { cudaEventDestroy(M->timing.ev[0]); cudaEventDestroy(M->timing.ev[1]); }
+  for (cudaEvent_t e : M->timing.chunk_ev) cudaEventDestroy(e);
+  M->timing.chunk_ev.clear();
   cudaFree(M->d_steps);
   cudaFree(M->d_warps);
   cudaFree(M->d_rterms);
@@ -1059,14 +1060,25 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
     const int64_t nr = std::min(kChunkRows, n - r0);
     const int64_t tiles = (nr + T - 1) / T;
     const int grid1 = (int)std::min<int64_t>(tiles, M->rec_ctas);
-    if (tm.enabled && chunk == 0) PGB_CUDA(cudaEventRecord(tm.ev[0], st));
+    cudaEvent_t* ev = nullptr;
+    if (tm.enabled) {
+      while ((int)tm.chunk_ev.size() < 3 * (chunk + 1)) {
+        cudaEvent_t e;
+        PGB_CUDA(cudaEventCreate(&e));
+        tm.chunk_ev.push_back(e);
+      }
+      ev = &tm.chunk_ev[3 * chunk];
+      PGB_CUDA(cudaEventRecord(ev[0], st));
+    }
     gram_records_kernel<<<grid1, kRecThreads, M->rec_smem, st>>>(M->d_terms, M->n_terms, M->m, M->d_rterms, M->n_slots_all,
                                                                    M->fam, mode, X + r0, nr, ld, y + r0, w ? w + r0 : nullptr,
                                                                    beta, T, M->n_features, rec_val, rec_idx, scal_part);
     PGB_CUDA(cudaGetLastError());
+    if (ev) PGB_CUDA(cudaEventRecord(ev[1], st));
     gram_accum_kernel<<<M->gram_ctas, M->gram_threads, M->gram_smem, st>>>(M->d_steps, M->d_warps, M->d_runs, M->d_roles, n_roles,
                                                                               rec_val, rec_idx, nr, T, M->n_slots_all, dbg, partials);
     PGB_CUDA(cudaGetLastError());
+    if (ev) PGB_CUDA(cudaEventRecord(ev[2], st));
     const int acc_flag = (accumulate || chunk > 0) ? 1 : 0;
     const int rb = 256;
     gram_reduce_kernel<<<(unsigned)((M->map_size + rb - 1) / rb), rb, 0, st>>>(partials, M->d_roles, n_roles, M->d_elem_map,
@@ -1075,27 +1087,31 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
     pgb_count_launch(4);
     PGB_CUDA(cudaGetLastError());
   }
-  if (tm.enabled) { PGB_CUDA(cudaEventRecord(tm.ev[1], st)); tm.pending = true; }
+  if (tm.enabled) { tm.pending = true; tm.n_chunks = chunk; }
   return PGB_OK;
 }
 
-// optional timing of the Gram pass kernels (records + accumulation + reductions of all chunks) with
-// CUDA events recorded on the launching stream; used by bench.py for the roofline figure
+// optional timing of the two kernels of the Gram pass with CUDA events recorded on the launching
+// stream (summed over the row chunks); used by bench.py for the roofline figure
 extern "C" int pgb_gram_timing(pgb_model* M, int32_t enable) {
   if (!M) { pgb_set_error("pgb_gram_timing: null model"); return PGB_EINVAL; }
-  pgb_model::Timing& tm = M->timing;
-  if (enable && !tm.ev[0]) {
-    PGB_CUDA(cudaEventCreate(&tm.ev[0]));
-    PGB_CUDA(cudaEventCreate(&tm.ev[1]));
-  }
-  tm.enabled = enable != 0;
-  tm.pending = false;
+  M->timing.enabled = enable != 0;
+  M->timing.pending = false;
   return PGB_OK;
 }
-extern "C" int pgb_gram_last_ms(pgb_model* M, float* accum_ms) {
-  if (!M || !accum_ms || !M->timing.pending) { pgb_set_error("pgb_gram_last_ms: no timed pass"); return PGB_EINVAL; }
-  PGB_CUDA(cudaEventSynchronize(M->timing.ev[1]));
-  PGB_CUDA(cudaEventElapsedTime(accum_ms, M->timing.ev[0], M->timing.ev[1]));
+extern "C" int pgb_gram_last_ms(pgb_model* M, float* records_ms, float* accum_ms) {
+  if (!M || !records_ms || !accum_ms || !M->timing.pending) { pgb_set_error("pgb_gram_last_ms: no timed pass"); return PGB_EINVAL; }
+  pgb_model::Timing& tm = M->timing;
+  *records_ms = 0.f;
+  *accum_ms = 0.f;
+  for (int c = 0; c < tm.n_chunks; ++c) {
+    float a = 0.f, b = 0.f;
+    PGB_CUDA(cudaEventSynchronize(tm.chunk_ev[3 * c + 2]));
+    PGB_CUDA(cudaEventElapsedTime(&a, tm.chunk_ev[3 * c], tm.chunk_ev[3 * c + 1]));
+    PGB_CUDA(cudaEventElapsedTime(&b, tm.chunk_ev[3 * c + 1], tm.chunk_ev[3 * c + 2]));
+    *records_ms += a;
+    *accum_ms += b;
+  }
   return PGB_OK;
 }
 

@@ -131,7 +131,8 @@ struct pgb_model {
   } stage;
   struct Timing {
     bool enabled = false, pending = false;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int n_chunks = 0;
+    std::vector<cudaEvent_t> chunk_ev;  // per row chunk: before records, between, after accumulation
   } timing;
 };
 
