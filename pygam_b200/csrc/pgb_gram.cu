@@ -26,7 +26,7 @@
 
 static const int kMaxWarps = 15;      // consumer (accumulating) warps per CTA of the accumulation kernel; + 1 TMA warp
 static const int kNBuf = 3;           // record buffers of the accumulation kernel (TMA ring)
-static const int kSlotBytes = 12;     // record slot: double value + uint32 index (two arrays)
+static const int kSlotBytes = 10;     // record slot: double value + uint16 index (two arrays)
 static const int kRecThreads = 256;   // CTA of the records kernel
 static const int64_t kChunkRows = 1 << 22;  // rows whose records are materialised at a time
 
@@ -34,10 +34,11 @@ static const int64_t kChunkRows = 1 << 22;  // rows whose records are materialis
 // plan
 // ----------------------------------------------------------------------------------------
 static const int kMinTile = 16;
-// row pitch of the slot-major tile records ([slot][pitch]): two spare rows (the accumulation
-// prefetches one row pair ahead) and pitch = 2 (mod 4), so that the four slots of a quad start in
-// different banks while every slot row stays 16-byte aligned for the TMA bulk copies
-static int tile_pitch(int tile) { return tile + 2; }
+// row pitch of the slot-major tile records ([slot][pitch]): four spare rows (the accumulation works
+// on groups of four rows and prefetches one group ahead) and, with tiles that are multiples of 8 rows,
+// pitch = 4 (mod 8): the four slots of a quad start in different banks, every slot row is 16-byte
+// aligned (TMA bulk copies, 128-bit value loads) and four 16-bit indices are one aligned 64-bit word
+static int tile_pitch(int tile) { return tile + 4; }
 
 static int pitch_for(int width) {
   int p = std::max(width, 4);
@@ -120,11 +121,11 @@ int pgb_plan_gram(pgb_model* M) {
   // ---- blocks, packed into roles in (gi, gj) order
   const size_t fixed = role_fixed_smem(M);
   const size_t rec_row_all = (size_t)(quads * 4) * kSlotBytes;  // bytes per tile row when a role needs every quad
-  if (fixed + (kMinTile + 2) * rec_row_all * 2 + 16384 > kSmemMax) {
+  if (fixed + (kMinTile + 4) * rec_row_all * 2 + 16384 > kSmemMax) {
     pgb_set_error("model too wide for the Gram pass: k=%d non-zeros per row", M->k);
     return PGB_EUNSUPPORTED;
   }
-  const int64_t acc_budget = (int64_t)((kSmemMax - kNBuf * (kMinTile + 2) * rec_row_all - 8192) / 8);  // doubles
+  const int64_t acc_budget = (int64_t)((kSmemMax - kNBuf * (kMinTile + 4) * rec_row_all - 8192) / 8);  // doubles
   M->blocks.clear();
   int64_t total_acc = 0;
   for (int gi = 0; gi < ng; ++gi)
@@ -333,15 +334,18 @@ int pgb_plan_gram(pgb_model* M) {
   M->tile_rows = tile;
   M->gram_smem = (smem + 127) & ~(size_t)127;
   M->gram_threads = 32 * (max_warps + 1);
-  // records kernel: all slots of a tile, the raw columns, lp parts, beta, the terms
-  M->rec_smem = (size_t)tile_pitch(tile) * M->n_slots_all * kSlotBytes + (size_t)(M->n_features + 2) * tile * 8 + (size_t)tile * 4 +
-                (size_t)tile * 8 + (size_t)tile * (nt + 1) * 8 + (size_t)(nt + 1) * 64 + fixed + 256;
-  M->rec_smem = (M->rec_smem + 127) & ~(size_t)127;
-  if (M->rec_smem > kSmemMax) {
-    pgb_set_error("records kernel does not fit in shared memory (%zu bytes)", M->rec_smem);
-    return PGB_EUNSUPPORTED;
+  // records kernel: beta, the terms; record slots no term fills (quads of fewer than four slots)
+  M->pad_slots.clear();
+  {
+    std::vector<char> filled(M->n_slots_all, 0);
+    for (int j = 0; j < nt; ++j)
+      for (int q = 0; q < T[j].nnz; ++q) filled[T[j].gslot0 + q] = 1;
+    filled[4 * rhs_quad + rhs_s] = 1;
+    for (int q = 0; q < M->n_slots_all; ++q)
+      if (!filled[q]) M->pad_slots.push_back(q);
   }
-  M->rec_ctas = kSMs * (int)std::max<size_t>(1, std::min<size_t>(3, kSmemMax / (M->rec_smem + 1024)));
+  M->rec_smem = (fixed + (size_t)(nt + 1) * sizeof(DRoleTerm) + M->pad_slots.size() * 4 + 256 + 127) & ~(size_t)127;
+  M->rec_ctas = kSMs * 8;
   // ---- CTAs per role proportional to the role's cost per row
   int occ = (int)std::min<size_t>(8, kSmemMax / (M->gram_smem + 1024));
   occ = std::max(1, std::min(occ, 1536 / M->gram_threads));
@@ -418,6 +422,7 @@ int pgb_plan_upload(pgb_model* M) {
   up((void**)&M->d_warps, M->warps.data(), M->warps.size() * sizeof(DWarp));
   up((void**)&M->d_rterms, M->rterms.data(), M->rterms.size() * sizeof(DRoleTerm));
   up((void**)&M->d_runs, M->runs.data(), M->runs.size() * sizeof(DRun));
+  up((void**)&M->d_pad_slots, M->pad_slots.data(), M->pad_slots.size() * sizeof(int32_t));
   up((void**)&M->d_roles, M->roles.data(), M->roles.size() * sizeof(DRole));
   up((void**)&M->d_elem_map, M->elem_map.data(), M->elem_map.size() * sizeof(int32_t));
   // the device copy of the terms carries the plan fields (group, idx_base, gslot0)
@@ -469,9 +474,10 @@ void pgb_gram_release(pgb_model* M) {
   cudaFree(M->d_warps);
   cudaFree(M->d_rterms);
   cudaFree(M->d_runs);
+  cudaFree(M->d_pad_slots);
   cudaFree(M->d_roles);
   cudaFree(M->d_elem_map);
-  M->d_steps = nullptr; M->d_warps = nullptr; M->d_rterms = nullptr; M->d_runs = nullptr; M->d_roles = nullptr; M->d_elem_map = nullptr;
+  M->d_steps = nullptr; M->d_warps = nullptr; M->d_rterms = nullptr; M->d_runs = nullptr; M->d_pad_slots = nullptr; M->d_roles = nullptr; M->d_elem_map = nullptr;
 }
 
 // tiles / record bytes of a chunk of rows; workspace: [partials][scalar partials][records of one chunk]
@@ -511,6 +517,14 @@ template <int OFF>
 __device__ __forceinline__ void lds_u32_o(uint32_t& v, uint32_t a) {
   asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
 }
+template <int OFF>
+__device__ __forceinline__ void lds_v2f64_o(double& x, double& y, uint32_t a) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(x), "=d"(y) : "r"(a), "n"(OFF));
+}
+__device__ __forceinline__ void lds_v2u32(uint32_t& x, uint32_t& y, uint32_t a) {
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a));
+}
+__device__ __forceinline__ void st_s16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
 
 __device__ __forceinline__ double ld_s64(uint32_t a) {
   double v;
@@ -537,90 +551,88 @@ __device__ __forceinline__ void ld_stterm(uint32_t a, double& lo, double& inv, d
 
 // tile records are slot-major: slot s of tile row r lives at val[s * TP + r] / idx[s * TP + r]
 struct EmitRec {
-  double* val;    // &val[slot0 * TP + r]
-  uint32_t* idx;  // position of the coefficient inside its group
+  double* val;     // &val[slot0 * TP + r]
+  uint16_t* idx;   // position of the coefficient inside its group
   const double* beta;
   double lp, scale;
   int tp, coef_offset, idx_base;
   __device__ __forceinline__ void operator()(int c, double v) {
     *val = v * scale;
-    *idx = (uint32_t)(idx_base + c - coef_offset);
+    *idx = (uint16_t)(idx_base + c - coef_offset);
     val += tp;
     idx += tp;
     if (beta) lp = fma(v, beta[c], lp);
   }
 };
 
-// One half-step of phase B over the rows of a tile, K items in flight, two data rows per trip:
-// per data row one load of the shared operand (value, index) and K loads of the varying operands,
-// then K independent read-modify-writes at [varying index][shared index] of the items' blocks.
-// The two rows of a trip are updated one after the other (they may hit the same element); the
-// operands of the next trip are fetched while the updates of the current one are in flight.
+// One half-step over the rows of a tile, K items in flight, four data rows per trip: per trip two
+// 128-bit loads of the shared operand's values, one 64-bit load of its four 16-bit indices, the same
+// for each of the K varying operands; then per row K independent read-modify-writes at [varying
+// index][shared index] of the items' blocks.  The rows of a trip are updated one after the other
+// (they may hit the same element); the operands of the next trip are fetched while the updates of
+// the current one are in flight.
 template <int K, bool DG>
-__device__ __noinline__ void phase_b_half(const DHalf* hp, int tile_n, uint32_t val_u32,
-                                             uint32_t idx_u32, uint32_t acc_u32, uint32_t tp, int lt, int lu) {
+__device__ __noinline__ void phase_b_half(const DHalf* hp, int tile_n, uint32_t val_u32, uint32_t idx_u32,
+                                          uint32_t acc_u32, uint32_t tp, int lt, int lu) {
   const uint32_t ss = (hp->shared_slot + lt) * tp;
-  uint32_t a_sv = val_u32 + ss * 8u, a_si = idx_u32 + ss * 4u;
+  uint32_t a_sv = val_u32 + ss * 8u, a_si = idx_u32 + ss * 2u;
   uint32_t a_vv[K], a_vi[K], base[K], pitch8[K], on[K], dg[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const uint32_t vs = (hp->v[k].slot + lu) * tp, mk = hp->v[k].mask;
     a_vv[k] = val_u32 + vs * 8u;
-    a_vi[k] = idx_u32 + vs * 4u;
+    a_vi[k] = idx_u32 + vs * 2u;
     base[k] = acc_u32 + hp->v[k].off8;
     pitch8[k] = hp->v[k].pitch8;
     on[k] = (mk >> (4 * lu + lt)) & 1u;
     dg[k] = (mk >> 16) & 1u;
   }
-  double sv[2], vv[2][K];
-  uint32_t si[2], vi[2][K];
-  lds_f64_o<0>(sv[0], a_sv);
-  lds_f64_o<8>(sv[1], a_sv);
-  lds_u32_o<0>(si[0], a_si);
-  lds_u32_o<4>(si[1], a_si);
+  double sv[4], vv[K][4];
+  uint32_t si[2], vi[K][2];  // four 16-bit indices each
+  lds_v2f64_o<0>(sv[0], sv[1], a_sv);
+  lds_v2f64_o<16>(sv[2], sv[3], a_sv);
+  lds_v2u32(si[0], si[1], a_si);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    lds_f64_o<0>(vv[0][k], a_vv[k]);
-    lds_f64_o<8>(vv[1][k], a_vv[k]);
-    lds_u32_o<0>(vi[0][k], a_vi[k]);
-    lds_u32_o<4>(vi[1][k], a_vi[k]);
+    lds_v2f64_o<0>(vv[k][0], vv[k][1], a_vv[k]);
+    lds_v2f64_o<16>(vv[k][2], vv[k][3], a_vv[k]);
+    lds_v2u32(vi[k][0], vi[k][1], a_vi[k]);
   }
-  for (int rI = 0; rI < tile_n; rI += 2) {
-    uint32_t g[2][K];
-    double c_sv[2], c_vv[2][K];
+  for (int rI = 0; rI < tile_n; rI += 4) {
+    uint32_t g[4][K];
+    double c_sv[4], c_vv[K][4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 4; ++h) {
       c_sv[h] = sv[h];
+      const uint32_t ics = (h & 1) ? (si[h >> 1] >> 16) : (si[h >> 1] & 0xffffu);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        uint32_t ir = vi[h][k], ic = si[h];
+        uint32_t ir = (h & 1) ? (vi[k][h >> 1] >> 16) : (vi[k][h >> 1] & 0xffffu), ic = ics;
         if (DG && dg[k] && ir > ic) { const uint32_t t = ir; ir = ic; ic = t; }  // same group: element (min, max)
         g[h][k] = base[k] + ir * pitch8[k] + (ic << 3);
-        c_vv[h][k] = vv[h][k];
+        c_vv[k][h] = vv[k][h];
       }
     }
-    a_sv += 16u;
+    a_sv += 32u;
     a_si += 8u;
-    lds_f64_o<0>(sv[0], a_sv);  // the record buffers have two spare rows
-    lds_f64_o<8>(sv[1], a_sv);
-    lds_u32_o<0>(si[0], a_si);
-    lds_u32_o<4>(si[1], a_si);
+    lds_v2f64_o<0>(sv[0], sv[1], a_sv);  // the record buffers have four spare rows
+    lds_v2f64_o<16>(sv[2], sv[3], a_sv);
+    lds_v2u32(si[0], si[1], a_si);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      a_vv[k] += 16u;
+      a_vv[k] += 32u;
       a_vi[k] += 8u;
-      lds_f64_o<0>(vv[0][k], a_vv[k]);
-      lds_f64_o<8>(vv[1][k], a_vv[k]);
-      lds_u32_o<0>(vi[0][k], a_vi[k]);
-      lds_u32_o<4>(vi[1][k], a_vi[k]);
+      lds_v2f64_o<0>(vv[k][0], vv[k][1], a_vv[k]);
+      lds_v2f64_o<16>(vv[k][2], vv[k][3], a_vv[k]);
+      lds_v2u32(vi[k][0], vi[k][1], a_vi[k]);
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 4; ++h) {
       double x[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) lds_f64(x[k], g[h][k]);  // masked lanes read a valid element and do not store
 #pragma unroll
-      for (int k = 0; k < K; ++k) x[k] = fma(c_sv[h], c_vv[h][k], x[k]);
+      for (int k = 0; k < K; ++k) x[k] = fma(c_sv[h], c_vv[k][h], x[k]);
 #pragma unroll
       for (int k = 0; k < K; ++k) sts_f64_if(g[h][k], x[k], on[k]);
     }
@@ -652,227 +664,96 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
 }
 
 // ----------------------------------------------------------------------------------------
-// kernel 1: records.  Per data row: basis values of every term, lp, the IRLS step (mu, W, mask,
-// working response; pygam.py:764-777) or the response of _initial_estimate, and the row's record
-// = (sqrt(omega) * value, index inside the coefficient group) per slot, written to HBM tile by
-// tile in the slot-major layout the accumulation kernel bulk-copies: values [tile][slot][pitch],
-// indices [tile][slot][pitch].  Also the log scalars of the iteration.
+// kernel 1: records.  One thread per data row, no shared-memory staging and no barriers: pass 1
+// evaluates the basis of every term for lp; then the IRLS step (mu, W, mask, working response;
+// pygam.py:764-777) or the response of _initial_estimate; pass 2 evaluates the basis again and
+// writes the row's record = (sqrt(omega) * value, index inside the coefficient group) per slot
+// straight to HBM in the slot-major tile layout the accumulation kernel bulk-copies: values
+// [tile][slot][pitch], 16-bit indices [tile][slot][pitch].  Consecutive threads own consecutive
+// rows, so every feature load and every record store is a contiguous run per warp.  Also the log
+// scalars of the iteration.
 // ----------------------------------------------------------------------------------------
-// compact per-term descriptor (built in shared memory at kernel start): everything the common
-// record kinds need without touching the full DTerm
-enum { kStCubic = 0, kStIntercept = 1, kStLinear = 2, kStRhs = 3, kStGeneric = 4 };
-struct __align__(16) StTerm {
-  double lo, inv, dn, pad0;  // cubic spline: edge knot, 1 / span, number of intervals
-  int32_t kind, nint1, feature, slot0;
-  int32_t idx_base, term, coef_offset, pad1;
+struct EmitGlobal {
+  double* val;    // &val[slot0 * TP + r] of the row's tile
+  uint16_t* idx;
+  double scale;
+  int tp, coef_offset, idx_base;
+  __device__ __forceinline__ void operator()(int c, double v) {
+    *val = v * scale;
+    *idx = (uint16_t)(idx_base + c - coef_offset);
+    val += tp;
+    idx += tp;
+  }
 };
 
-struct RecArgs {
-  const StTerm* rt;      // [n_rt] every term, the rhs last
-  const DTerm* s_terms;
-  const double* s_beta;
-  double* lp_part;       // [n_rt][T]
-  double* rec_w;         // [T]
-  const double* xs;      // raw columns of the tile: [F][T] features, then [T] y
-  const float* ws;       // [T] prior weights
-  Family fam;
-  int mode, T, TP, F, n_rt, n_slots, has_w;
-};
-
-// one tile: one thread per (row, term), U items per trip -- all loads and the arithmetic of the
-// items first (independent chains the scheduler can interleave), then their record stores; then one
-// thread per row for the IRLS step; then the records are scaled by sqrt(omega)
-template <int U>
-__device__ __forceinline__ void records_tile(const RecArgs& A, int tile_n, double* rec_val, uint32_t* rec_idx, double* sc) {
-  const int TP = A.TP, T = A.T, ptid = threadIdx.x, pn = blockDim.x;
-  const double* xs = A.xs;
-  const double* tail = xs + (size_t)A.F * T;
-  // explicit shared-space addresses: everything the common kinds touch goes through ld/st.shared
-  const uint32_t xs_a = smem_u32(xs), tail_a = smem_u32(tail), rt_a = smem_u32(A.rt), beta_a = smem_u32(A.s_beta);
-  const uint32_t lpp_a = smem_u32(A.lp_part), val_a = smem_u32(rec_val), idx_a = smem_u32(rec_idx), recw_a = smem_u32(A.rec_w);
-  const int n_items = tile_n * A.n_rt;
-  const float inv_tn = 1.0f / (float)tile_n;
-  for (int it0 = ptid; it0 < n_items; it0 += U * pn) {
-    double v[U][4];
-    int at[U], i0[U], nv[U], gq[U], gr[U];
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const int item = it0 + j * pn;
-      nv[j] = 0;
-      gq[j] = -1;
-      if (item >= n_items) continue;
-      const int q = (int)(((float)item + 0.5f) * inv_tn);  // item / tile_n, exact for these sizes
-      const int rI = item - q * tile_n;
-      double lo, inv, dn;
-      int kind, nint1, feature, slot0, idx_base, coef_offset;
-      ld_stterm(rt_a + q * 64, lo, inv, dn, kind, nint1, feature, slot0, idx_base, coef_offset);
-      at[j] = slot0 * TP + rI;
-      i0[j] = idx_base;
-      double lp = 0.0;
-      if (kind == kStCubic) {
-        const double u = (ld_s64(xs_a + 8 * (feature * T + rI)) - lo) * inv;
-        if (u >= 0.0 && u <= 1.0) {
-          const double s = u * dn;
-          const int i = min((int)s, nint1);
-          double b0, b1, b2, b3;
-          cubic_bspline(s - (double)i, b0, b1, b2, b3);
-          const uint32_t bc = beta_a + 8 * (coef_offset + i);
-          lp = fma(b3, ld_s64(bc + 24), fma(b2, ld_s64(bc + 16), fma(b1, ld_s64(bc + 8), b0 * ld_s64(bc))));
-          v[j][0] = b0; v[j][1] = b1; v[j][2] = b2; v[j][3] = b3;
-          i0[j] += i;
-          nv[j] = 4;
-        } else {
-          gq[j] = q;  // linear extrapolation outside the edge knots: general path
-          gr[j] = rI;
-        }
-      } else if (kind == kStIntercept) {
-        lp = ld_s64(beta_a + 8 * coef_offset);
-        v[j][0] = 1.0;
-        nv[j] = 1;
-      } else if (kind == kStLinear) {
-        const double x = ld_s64(xs_a + 8 * (feature * T + rI));
-        lp = x * ld_s64(beta_a + 8 * coef_offset);
-        v[j][0] = x;
-        nv[j] = 1;
-      } else if (kind == kStGeneric) {
-        gq[j] = q;
-        gr[j] = rI;
-      }
-      if (kind != kStRhs && gq[j] < 0) st_s64(lpp_a + 8 * (q * T + rI), lp);
-    }
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-        if (a < nv[j]) {
-          st_s64(val_a + 8 * (at[j] + a * TP), v[j][a]);
-          st_s32(idx_a + 4 * (at[j] + a * TP), (uint32_t)(i0[j] + a));
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      if (gq[j] < 0) continue;
-      const StTerm& t = A.rt[gq[j]];
-      const DTerm& d = A.s_terms[t.term];
-      const int at2 = t.slot0 * TP + gr[j];
-      EmitRec e{rec_val + at2, rec_idx + at2, A.s_beta, 0.0, 1.0, TP, d.coef_offset, t.idx_base};
-      const LoadTile load{xs, T, gr[j]};
-      eval_term(d, load, e);
-      A.lp_part[gq[j] * T + gr[j]] = e.lp;
-    }
-  }
-  __syncthreads();
-  const StTerm& rhs = A.rt[A.n_rt - 1];
-  for (int rI = ptid; rI < tile_n; rI += pn) {
-    double lp = 0.0;
-    for (int q = 0; q < A.n_rt - 1; ++q) lp += ld_s64(lpp_a + 8 * (q * T + rI));
-    const double yi = ld_s64(tail_a + 8 * rI);
-    double sw, z;
-    if (A.mode == PGB_MODE_IRLS) {
-      const double winv = A.has_w ? (double)__fdiv_rn(1.0f, ld_s32f(smem_u32(A.ws) + 4 * rI)) : 1.0;
-      const IrlsRow r = irls_row(A.fam, lp, yi, winv);
-      sw = r.sw;
-      z = r.z;
-      if (r.keep) {
-        sc[PGB_GS_NUSED] += 1.0;
-        sc[PGB_GS_DEV] += dist_dev(A.fam, yi, r.mu);
-        sc[PGB_GS_NCORRECT] += (yi == ((r.mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
-      }
-    } else {
-      sw = 1.0;
-      z = init_response(A.fam, yi);
-      sc[PGB_GS_NUSED] += 1.0;
-      if (!isfinite(z)) sc[PGB_GS_NONFINITE] += 1.0;
-    }
-    sc[PGB_GS_NROWS] += 1.0;
-    st_s64(recw_a + 8 * rI, sw);
-    st_s64(val_a + 8 * (rhs.slot0 * TP + rI), z);
-    st_s32(idx_a + 4 * (rhs.slot0 * TP + rI), (uint32_t)rhs.idx_base);
-  }
-  __syncthreads();
-  // scale the records by sqrt(omega); the accumulation works on row pairs: the odd row out contributes zeros
-  const int tn2 = (tile_n + 1) & ~1;
-  const float inv_t2 = 1.0f / (float)tn2;
-  for (int e = ptid; e < A.n_slots * tn2; e += pn) {
-    const int s = (int)(((float)e + 0.5f) * inv_t2), rI = e - s * tn2;
-    const uint32_t a = val_a + 8 * (s * TP + rI);
-    st_s64(a, (rI < tile_n) ? ld_s64(a) * ld_s64(recw_a + 8 * rI) : 0.0);
-  }
-}
-
-__global__ void __launch_bounds__(kRecThreads, 3)
-gram_records_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const DRoleTerm* __restrict__ g_rterms, int n_slots,
-                    Family fam, int mode, const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
-                    const float* __restrict__ w, const double* __restrict__ beta, int T, int F, double* __restrict__ rec_val_g,
-                    uint32_t* __restrict__ rec_idx_g, double* __restrict__ scal_part) {
+__global__ void __launch_bounds__(kRecThreads, 4)
+gram_records_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const DRoleTerm* __restrict__ g_rterms,
+                    const int32_t* __restrict__ g_pad_slots, int n_pad, int n_slots, Family fam, int mode,
+                    const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
+                    const float* __restrict__ w, const double* __restrict__ beta, int T, double* __restrict__ rec_val_g,
+                    uint16_t* __restrict__ rec_idx_g, double* __restrict__ scal_part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int TP = T + 2, n_rt = n_terms + 1, tid = threadIdx.x;
-  double* rec_val = reinterpret_cast<double*>(smem_raw);            // [n_slots][TP]
-  double* xs = rec_val + (size_t)n_slots * TP;                       // [F + 1][T]
-  double* rec_w = xs + (size_t)(F + 1) * T;                          // [T]
-  double* lp_part = rec_w + T;                                       // [n_rt][T]
-  double* s_beta = lp_part + (size_t)n_rt * T;
+  const int TP = T + 4, tid = threadIdx.x;
+  double* s_beta = reinterpret_cast<double*>(smem_raw);
   double* s_red = s_beta + ((m + 1) & ~1);
-  StTerm* rt = reinterpret_cast<StTerm*>(s_red + PGB_GS_COUNT * 32);  // 16-byte aligned: everything before is a multiple of 16
-  DTerm* s_terms = reinterpret_cast<DTerm*>(rt + n_rt);
-  uint32_t* rec_idx = reinterpret_cast<uint32_t*>(s_terms + n_terms);  // [n_slots][TP]
-  float* ws = reinterpret_cast<float*>(rec_idx + (size_t)n_slots * TP);  // [T]
-
-  for (int i = tid; i < n_slots * TP; i += blockDim.x) { rec_val[i] = 0.0; rec_idx[i] = 0u; }  // padding slots stay zero
+  DTerm* s_terms = reinterpret_cast<DTerm*>(s_red + PGB_GS_COUNT * 32);
+  DRoleTerm* s_rt = reinterpret_cast<DRoleTerm*>(s_terms + n_terms);  // [n_terms + 1], the rhs last
+  int32_t* s_pad = reinterpret_cast<int32_t*>(s_rt + n_terms + 1);
   for (int i = tid; i < m; i += blockDim.x) s_beta[i] = (mode == PGB_MODE_IRLS) ? beta[i] : 0.0;
   load_terms_smem(s_terms, g_terms, n_terms);
-  __syncthreads();
-  for (int i = tid; i < n_rt; i += blockDim.x) {
-    const DRoleTerm r = g_rterms[i];
-    StTerm t{};
-    t.slot0 = r.slot0;
-    t.idx_base = r.idx_base;
-    t.term = r.term;
-    t.kind = kStRhs;
-    if (r.term >= 0) {
-      const DTerm& d = s_terms[r.term];
-      const DMarg& mg = d.marg[0];
-      t.kind = d.fast ? kStCubic : d.kind == PGB_TERM_INTERCEPT ? kStIntercept : d.kind == PGB_TERM_LINEAR ? kStLinear : kStGeneric;
-      t.lo = mg.lo;
-      t.inv = mg.inv_span;
-      t.dn = (double)mg.nint;
-      t.nint1 = mg.nint - 1;
-      t.feature = mg.feature;
-      t.coef_offset = d.coef_offset;
-    }
-    rt[i] = t;
-  }
+  for (int i = tid; i <= n_terms; i += blockDim.x) s_rt[i] = g_rterms[i];
+  for (int i = tid; i < n_pad; i += blockDim.x) s_pad[i] = g_pad_slots[i];
   __syncthreads();
 
   double sc[PGB_GS_COUNT];
 #pragma unroll
   for (int s = 0; s < PGB_GS_COUNT; ++s) sc[s] = 0.0;
-  const RecArgs A{rt, s_terms, s_beta, lp_part, rec_w, xs, ws, fam, mode, T, TP, F, n_rt, n_slots, w != nullptr};
   const int64_t n_tiles = (n + T - 1) / T;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * T;
-    const int tile_n = (int)min((int64_t)T, n - row0);
-    // raw columns of the tile: coalesced loads, every thread busy
-    for (int e = tid; e < (F + 1) * tile_n; e += blockDim.x) {
-      const int f = e / tile_n, r = e - f * tile_n;
-      xs[(size_t)f * T + r] = (f < F) ? __ldg(X + (int64_t)f * ld + row0 + r) : __ldg(y + row0 + r);
+  const int64_t n_pad_rows = n_tiles * T;  // the rows that fill up the last tile get all-zero records
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < n_pad_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tile = i / T;
+    const int r = (int)(i - tile * T);
+    double* rv = rec_val_g + (size_t)tile * n_slots * TP + r;
+    uint16_t* ri = rec_idx_g + (size_t)tile * n_slots * TP + r;
+    if (i >= n) {
+      for (int s = 0; s < n_slots; ++s) { rv[(size_t)s * TP] = 0.0; ri[(size_t)s * TP] = 0; }
+      continue;
     }
-    if (w)
-      for (int r = tid; r < tile_n; r += blockDim.x) ws[r] = __ldg(w + row0 + r);
-    __syncthreads();
-    records_tile<2>(A, tile_n, rec_val, rec_idx, sc);
-    __syncthreads();
-    // copy the tile's records out: 16 bytes per thread, fully coalesced
+    const double yi = __ldg(y + i);
+    double sw, z;
+    if (mode == PGB_MODE_IRLS) {
+      EmitLp e{s_beta, 0.0};
+      for (int q = 0; q < n_terms; ++q) eval_term(s_terms[q], X, ld, i, e);
+      const IrlsRow ir = irls_row(fam, e.lp, yi, weight_inv(w, i));
+      sw = ir.sw;
+      z = ir.z;
+      if (ir.keep) {
+        sc[PGB_GS_NUSED] += 1.0;
+        sc[PGB_GS_DEV] += dist_dev(fam, yi, ir.mu);
+        sc[PGB_GS_NCORRECT] += (yi == ((ir.mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
+      }
+    } else {
+      sw = 1.0;
+      z = init_response(fam, yi);
+      sc[PGB_GS_NUSED] += 1.0;
+      if (!isfinite(z)) sc[PGB_GS_NONFINITE] += 1.0;
+    }
+    sc[PGB_GS_NROWS] += 1.0;
+    for (int q = 0; q < n_terms; ++q) {
+      const DRoleTerm rt = s_rt[q];
+      const DTerm& d = s_terms[q];
+      EmitGlobal e{rv + (size_t)rt.slot0 * TP, ri + (size_t)rt.slot0 * TP, sw, TP, d.coef_offset, rt.idx_base};
+      eval_term(d, X, ld, i, e);
+    }
     {
-      const int nv2 = n_slots * TP / 2, ni4 = n_slots * TP / 4;  // TP is even, n_slots a multiple of 4
-      double2* dv = reinterpret_cast<double2*>(rec_val_g + (size_t)tile * n_slots * TP);
-      const double2* sv = reinterpret_cast<const double2*>(rec_val);
-      for (int e = tid; e < nv2; e += blockDim.x) dv[e] = sv[e];
-      uint4* di = reinterpret_cast<uint4*>(rec_idx_g + (size_t)tile * n_slots * TP);
-      const uint4* si = reinterpret_cast<const uint4*>(rec_idx);
-      for (int e = tid; e < ni4; e += blockDim.x) di[e] = si[e];
+      const DRoleTerm rt = s_rt[n_terms];  // the rhs column: sqrt(omega) * z
+      rv[(size_t)rt.slot0 * TP] = sw * z;
+      ri[(size_t)rt.slot0 * TP] = (uint16_t)rt.idx_base;
     }
-    __syncthreads();
+    for (int q = 0; q < n_pad; ++q) {  // slots no term fills: masked in the accumulation, but read
+      rv[(size_t)s_pad[q] * TP] = 0.0;
+      ri[(size_t)s_pad[q] * TP] = 0;
+    }
   }
   block_reduce_store<PGB_GS_COUNT>(sc, s_red, scal_part + (int64_t)blockIdx.x * PGB_GS_COUNT);
 }
@@ -888,18 +769,18 @@ gram_records_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const
 __global__ void __launch_bounds__(32 * (kMaxWarps + 1))
 gram_accum_kernel(const DStep* __restrict__ g_steps, const DWarp* __restrict__ g_warps, const DRun* __restrict__ g_runs,
                   const DRole* __restrict__ g_roles, int n_roles, const double* __restrict__ rec_val_g,
-                  const uint32_t* __restrict__ rec_idx_g, int64_t n, int T, int n_slots_all, int dbg,
+                  const uint16_t* __restrict__ rec_idx_g, int64_t n, int T, int n_slots_all, int dbg,
                   double* __restrict__ partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int ridx = 0;
   while (ridx + 1 < n_roles && (int)blockIdx.x >= g_roles[ridx + 1].cta0) ++ridx;
   const DRole role = g_roles[ridx];
   const int cta_in_role = blockIdx.x - role.cta0;
-  const int S = role.n_slots, TP = T + 2;
+  const int S = role.n_slots, TP = T + 4;
 
   double* acc = reinterpret_cast<double*>(smem_raw);
   double* rec_val = acc + role.acc_size;                                          // [kNBuf][S][TP]
-  uint32_t* rec_idx = reinterpret_cast<uint32_t*>(rec_val + (size_t)kNBuf * S * TP);  // [kNBuf][S][TP]
+  uint16_t* rec_idx = reinterpret_cast<uint16_t*>(rec_val + (size_t)kNBuf * S * TP);  // [kNBuf][S][TP]
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(rec_idx + (size_t)kNBuf * S * TP);
   DStep* steps = reinterpret_cast<DStep*>(mbar + kNBuf);
   DRun* runs = reinterpret_cast<DRun*>(steps + role.n_steps);
@@ -935,13 +816,13 @@ gram_accum_kernel(const DStep* __restrict__ g_steps, const DWarp* __restrict__ g
         const uint32_t bar = smem_u32(mbar + b);
         mbar_expect_tx(bar, bytes);
         const double* gv = rec_val_g + (size_t)tile * n_slots_all * TP;
-        const uint32_t* gi = rec_idx_g + (size_t)tile * n_slots_all * TP;
+        const uint16_t* gi = rec_idx_g + (size_t)tile * n_slots_all * TP;
         double* sv = rec_val + (size_t)b * S * TP;
-        uint32_t* si = rec_idx + (size_t)b * S * TP;
+        uint16_t* si = rec_idx + (size_t)b * S * TP;
         for (int q = 0; q < role.n_runs; ++q) {
           const DRun r = runs[q];
           bulk_g2s(smem_u32(sv + (size_t)r.lslot0 * TP), gv + (size_t)r.gslot0 * TP, (uint32_t)(r.n_slots * TP * 8), bar);
-          bulk_g2s(smem_u32(si + (size_t)r.lslot0 * TP), gi + (size_t)r.gslot0 * TP, (uint32_t)(r.n_slots * TP * 4), bar);
+          bulk_g2s(smem_u32(si + (size_t)r.lslot0 * TP), gi + (size_t)r.gslot0 * TP, (uint32_t)(r.n_slots * TP * 2), bar);
         }
       }
       __syncwarp();
@@ -1045,7 +926,7 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
   uintptr_t rp = (uintptr_t)(scal_part + (int64_t)M->rec_ctas * PGB_GS_COUNT);
   rp = (rp + 255) & ~(uintptr_t)255;
   double* rec_val = (double*)rp;
-  uint32_t* rec_idx = (uint32_t*)(rec_val + chunk_tiles * M->n_slots_all * TP);
+  uint16_t* rec_idx = (uint16_t*)(rec_val + chunk_tiles * M->n_slots_all * TP);
   static thread_local bool attr_set = false;
   if (!attr_set) {
     PGB_CUDA(cudaFuncSetAttribute(gram_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
@@ -1059,7 +940,7 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
   for (int64_t r0 = 0; r0 < n; r0 += kChunkRows, ++chunk) {
     const int64_t nr = std::min(kChunkRows, n - r0);
     const int64_t tiles = (nr + T - 1) / T;
-    const int grid1 = (int)std::min<int64_t>(tiles, M->rec_ctas);
+    const int grid1 = (int)std::min<int64_t>((tiles * T + kRecThreads - 1) / kRecThreads, M->rec_ctas);
     cudaEvent_t* ev = nullptr;
     if (tm.enabled) {
       while ((int)tm.chunk_ev.size() < 3 * (chunk + 1)) {
@@ -1070,9 +951,10 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
       ev = &tm.chunk_ev[3 * chunk];
       PGB_CUDA(cudaEventRecord(ev[0], st));
     }
-    gram_records_kernel<<<grid1, kRecThreads, M->rec_smem, st>>>(M->d_terms, M->n_terms, M->m, M->d_rterms, M->n_slots_all,
-                                                                   M->fam, mode, X + r0, nr, ld, y + r0, w ? w + r0 : nullptr,
-                                                                   beta, T, M->n_features, rec_val, rec_idx, scal_part);
+    gram_records_kernel<<<grid1, kRecThreads, M->rec_smem, st>>>(M->d_terms, M->n_terms, M->m, M->d_rterms, M->d_pad_slots,
+                                                                   (int)M->pad_slots.size(), M->n_slots_all, M->fam, mode, X + r0,
+                                                                   nr, ld, y + r0, w ? w + r0 : nullptr, beta, T, rec_val, rec_idx,
+                                                                   scal_part);
     PGB_CUDA(cudaGetLastError());
     if (ev) PGB_CUDA(cudaEventRecord(ev[1], st));
     gram_accum_kernel<<<M->gram_ctas, M->gram_threads, M->gram_smem, st>>>(M->d_steps, M->d_warps, M->d_runs, M->d_roles, n_roles,

@@ -99,6 +99,7 @@ struct pgb_model {
   std::vector<DWarp> warps;
   std::vector<DRoleTerm> rterms;  // every term and the rhs with its global record slot
   std::vector<DRun> runs;
+  std::vector<int32_t> pad_slots;  // global record slots no term fills
   std::vector<DRole> roles;
   std::vector<int32_t> elem_map;  // per accumulator element: row * (m + 1) + col of G|r, or -1
   DTerm* d_terms = nullptr;
@@ -106,6 +107,7 @@ struct pgb_model {
   DWarp* d_warps = nullptr;
   DRoleTerm* d_rterms = nullptr;
   DRun* d_runs = nullptr;
+  int32_t* d_pad_slots = nullptr;
   DRole* d_roles = nullptr;
   int32_t* d_elem_map = nullptr;
   Family fam{};
