@@ -118,16 +118,48 @@ int pgb_plan_gram(pgb_model* M) {
   const int ng = (int)M->groups.size();
   for (DGroup& g : M->groups) g.pitch = pitch_for(g.width);
 
-  // ---- blocks, packed into roles in (gi, gj) order
+  // ---- blocks.  The groups are cut into PANELS of consecutive groups about sqrt(budget)
+  //      coefficients wide and the blocks are ordered by (panel of gi, panel of gj): a role, a run of
+  //      consecutive blocks, then covers about one panel pair and needs the record slots of two
+  //      panels only -- less shared memory for records, larger tiles (a 2-d decomposition of G).
   const size_t fixed = role_fixed_smem(M);
   const size_t rec_row_all = (size_t)(quads * 4) * kSlotBytes;  // bytes per tile row when a role needs every quad
-  if (fixed + (kMinTile + 4) * rec_row_all * 2 + 16384 > kSmemMax) {
+  if ((kMinTile + 4) * rec_row_all * 2 + 32768 > kSmemMax) {
     pgb_set_error("model too wide for the Gram pass: k=%d non-zeros per row", M->k);
     return PGB_EUNSUPPORTED;
   }
-  const int64_t acc_budget = (int64_t)((kSmemMax - kNBuf * (kMinTile + 4) * rec_row_all - 8192) / 8);  // doubles
+  int best_tile = 0, n_roles = 0;
+  double best_budget = 0.0;
+  int tile = 0;
+  size_t smem = 0;
+  int max_warps = 1;
+  const int est_slots = std::min(4 * quads, std::max(32, 2 * quads));
+  double budget_d = (double)(kSmemMax - (size_t)kNBuf * 36 * est_slots * kSlotBytes - 8192) / 8.0;
+  for (int attempt = 0; attempt < 14; ++attempt) {
+  const bool final_pass = (attempt == 13);
+  if (final_pass) {
+    if (best_tile == 0) {
+      pgb_set_error("Gram pass does not fit in shared memory");
+      return PGB_EUNSUPPORTED;
+    }
+    budget_d = best_budget;
+  }
+  const int64_t acc_budget = (int64_t)budget_d;
+  std::vector<int> panel(ng, 0);
+  {
+    const double B = std::sqrt((double)acc_budget);
+    int p = 0;
+    double wsum = 0.0;
+    for (int g = 0; g < ng; ++g) {
+      const double wg = (double)M->groups[g].pitch;
+      if (wsum > 0.0 && wsum + wg > B) { ++p; wsum = 0.0; }
+      panel[g] = p;
+      wsum += wg;
+    }
+  }
   M->blocks.clear();
   int64_t total_acc = 0;
+  bool block_too_big = false;
   for (int gi = 0; gi < ng; ++gi)
     for (int gj = gi; gj < ng; ++gj) {
       DBlock b{};
@@ -139,14 +171,22 @@ int pgb_plan_gram(pgb_model* M) {
       // stored block: the side with fewer quads (the row group => the block is stored transposed)
       b.tr = (gi != gj && b.n_items > 1 && qi <= qj) ? 1 : 0;
       const int64_t sz = block_doubles(M, b);
-      if (sz > acc_budget) {
-        pgb_set_error("a Gram block of %d x %d coefficients does not fit in shared memory", M->groups[gi].width,
-                      M->groups[gj].width);
-        return PGB_EUNSUPPORTED;
-      }
+      if (sz > acc_budget) block_too_big = true;
       total_acc += sz;
       M->blocks.push_back(b);
     }
+  if (block_too_big) {
+    if (attempt == 0) {
+      pgb_set_error("a Gram block does not fit in shared memory (m=%d)", m);
+      return PGB_EUNSUPPORTED;
+    }
+    attempt = 12;  // smaller budgets cannot work either: take the best so far
+    continue;
+  }
+  std::stable_sort(M->blocks.begin(), M->blocks.end(), [&](const DBlock& x, const DBlock& y) {
+    if (panel[x.gi] != panel[y.gi]) return panel[x.gi] < panel[y.gi];
+    return panel[x.gj] < panel[y.gj];
+  });
   // roles of equal accumulator size: walk the blocks in order and close a role when it reaches
   // its share; more roles if one of them overflows the shared-memory budget
   std::vector<int64_t> role_acc;
@@ -173,7 +213,7 @@ int pgb_plan_gram(pgb_model* M) {
     role_acc.push_back(acc);
     if (ok) break;
   }
-  const int n_roles = (int)role_acc.size();
+  n_roles = (int)role_acc.size();
 
   // ---- per role: record layout, terms to evaluate, items -> steps -> warps
   M->roles.clear();
@@ -182,7 +222,7 @@ int pgb_plan_gram(pgb_model* M) {
   M->warps.clear();
   M->runs.clear();
   M->n_slots_all = 4 * quads;
-  int max_warps = 1;
+  max_warps = 1;
   for (int r = 0; r < n_roles; ++r) {
     DRole R{};
     R.acc_size = role_acc[r];
@@ -240,7 +280,7 @@ int pgb_plan_gram(pgb_model* M) {
     int n_single = 0;
     for (const DBlock& b : M->blocks)
       if (b.role == r && b.n_items == 1) ++n_single;
-    int K = n_single > 60 ? 4 : n_single > 40 ? 3 : n_single > 12 ? 2 : 1;
+    int K = n_single > 40 ? 4 : n_single > 24 ? 3 : n_single > 12 ? 2 : 1;
     if (const char* ek = getenv("PGB_GRAM_K")) K = std::max(1, std::min(PGB_MAX_K, atoi(ek)));
     std::vector<std::vector<DHalf>> chains;
     {
@@ -320,17 +360,19 @@ int pgb_plan_gram(pgb_model* M) {
     }
     return smem;
   };
-  int tile = 128;
+  tile = 128;
   if (const char* et = getenv("PGB_GRAM_TILE")) tile = std::max(kMinTile, atoi(et) & ~7);
   while (tile > kMinTile && smem_for(tile) > kSmemMax) tile -= 8;
   for (int t2 = tile; t2 >= 64; t2 -= 8) {
     if (smem_for(t2) + 1024 <= kSmemMax / 2) { tile = t2; break; }
   }
-  size_t smem = smem_for(tile);
-  if (smem > kSmemMax) {
-    pgb_set_error("Gram pass does not fit in shared memory (%zu bytes)", smem);
-    return PGB_EUNSUPPORTED;
-  }
+  smem = smem_for(tile);
+  const bool fits = smem <= kSmemMax;
+  if (final_pass) break;
+  if (fits && tile > best_tile) { best_tile = tile; best_budget = budget_d; }
+  if (fits && (tile >= 40 || n_roles == 1)) { attempt = 12; continue; }  // good enough: rebuild it as the final plan
+  budget_d *= 0.88;
+  }  // attempts
   M->tile_rows = tile;
   M->gram_smem = (smem + 127) & ~(size_t)127;
   M->gram_threads = 32 * (max_warps + 1);
