@@ -183,7 +183,14 @@ int pgb_stats_pass(const pgb_model* model, const double* X, int64_t n, int64_t l
  * (G+EtE)^-1 G (G+EtE)^-1, m x m per system (pygam.py:1043-1045 without scale^2).
  * info: 0 ok, 1 = not positive definite, 2 = non-finite input (pygam.py:785-786). */
 #define PGB_SOLVE_OUT_EXTRA 8
-enum { PGB_SOLVE_EDOF = 1, PGB_SOLVE_COV = 2 };
+enum { PGB_SOLVE_EDOF = 1, PGB_SOLVE_COV = 2,
+       PGB_SOLVE_PREPARED = 4 /* EtE holds the output of pgb_solve_prepare; EtE_null is ignored */ };
+/* The penalty does not change during a PIRLS loop (pygam.py:746-805 builds S + P + C once per
+ * iteration from the same matrices): its change of basis, A0 = Q^T EtE Q + [Q^T EtE_null Q]_0
+ * (m x m per system), can be computed once and passed to pgb_solve as EtE with
+ * PGB_SOLVE_PREPARED.  ws: nb * m * m doubles when EtE_null is given. */
+int pgb_solve_prepare(int32_t m, int32_t nb, const double* EtE, const double* EtE_null, const double* hv,
+                      const double* tau, int32_t p, double* A0, void* ws, int64_t ws_bytes, void* stream);
 int64_t pgb_solve_ws_bytes(int32_t m, int32_t nb);
 int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r, int32_t share_gram,
               const double* EtE, const double* EtE_null, const double* hv, const double* tau, int32_t p,

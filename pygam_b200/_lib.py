@@ -24,7 +24,7 @@ GS_NUSED, GS_DEV, GS_NCORRECT, GS_ZWZ, GS_NROWS, GS_NONFINITE, GS_COUNT = 0, 1, 
 SS_COUNT = 16
 MODE_IRLS, MODE_INIT = 0, 1
 SOLVE_OUT_EXTRA = 8
-SOLVE_EDOF, SOLVE_COV = 1, 2
+SOLVE_EDOF, SOLVE_COV, SOLVE_PREPARED = 1, 2, 4
 
 
 class PgbTerm(C.Structure):
@@ -81,6 +81,7 @@ SYMBOLS = {
     "pgb_stats_pass": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_double, C.c_double,
                                  C.c_int32, _P, _P, _P, _P, C.c_int64, _P]),
     "pgb_solve_ws_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "pgb_solve_prepare": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, _P, C.c_int64, _P]),
     "pgb_solve": (C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, C.c_int32,
                             C.c_int32, _P, _P, _P, C.c_int64, _P]),
     "pgb_chol_ws_bytes": (C.c_int64, [C.c_int32]),

@@ -71,55 +71,123 @@ __device__ void vec_reflect(double* x, int m, const double* v, double tau, doubl
   __syncthreads();
 }
 
-// in-place lower Cholesky A = L L^T (upper part left untouched); returns 0 or 1 (not PD) in *flag
-__device__ void cholesky_lower(double* A, int m, double* col, int* flag) {
-  for (int k = 0; k < m; ++k) {
-    const double akk = A[(size_t)k * m + k];
-    if (!(akk > 0.0) || !isfinite(akk)) {
-      if (threadIdx.x == 0) *flag = 1;
-      __syncthreads();
-      return;
+// Blocked algorithms on an m x m matrix that lives in shared memory (small systems) or in the
+// L2-resident workspace (larger ones): the diagonal block D (kNB x kNB) and the current panel P
+// (rows x kNB) are staged in shared memory, so the O(m^3) work reads its operands from shared memory
+// and touches every trailing element once per block column instead of once per column.
+static const int kNB = 32;
+static const int kLD = kNB + 1;  // padded leading dimension of D and P: conflict-free column access
+
+// in-place lower Cholesky A = L L^T (upper part left untouched); sets *flag = 1 when A is not
+// positive definite
+__device__ void cholesky_lower(double* A, int m, double* D, double* P, int* flag) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  for (int k0 = 0; k0 < m; k0 += kNB) {
+    const int kb = min(kNB, m - k0);
+    for (int e = tid; e < kb * kb; e += nt) {
+      const int i = e / kb, j = e - i * kb;
+      D[i * kLD + j] = A[(size_t)(k0 + i) * m + k0 + j];
     }
-    const double d = sqrt(akk);
-    const double inv = 1.0 / d;
     __syncthreads();
-    for (int i = k + threadIdx.x; i < m; i += blockDim.x) {
-      const double v = (i == k) ? d : A[(size_t)i * m + k] * inv;
-      A[(size_t)i * m + k] = v;
-      col[i] = v;
+    if (warp == 0) {  // unblocked factorisation of the diagonal block: lane = row
+      for (int k = 0; k < kb; ++k) {
+        const double akk = D[k * kLD + k];
+        if (!(akk > 0.0) || !isfinite(akk)) {
+          if (lane == 0) *flag = 1;
+          break;
+        }
+        const double d = sqrt(akk), inv = 1.0 / d;
+        __syncwarp();
+        if (lane >= k && lane < kb) D[lane * kLD + k] = (lane == k) ? d : D[lane * kLD + k] * inv;
+        __syncwarp();
+        if (lane > k && lane < kb) {
+          const double lik = D[lane * kLD + k];
+          for (int j = k + 1; j <= lane; ++j) D[lane * kLD + j] = fma(-lik, D[j * kLD + k], D[lane * kLD + j]);
+        }
+        __syncwarp();
+      }
     }
     __syncthreads();
-    const int rem = m - k - 1;
-    // trailing update of the lower triangle: (i, j), k < j <= i
-    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
-      const int ii = e / rem, jj = e - ii * rem;
+    if (*flag != 0) return;
+    for (int e = tid; e < kb * kb; e += nt) {
+      const int i = e / kb, j = e - i * kb;
+      if (j <= i) A[(size_t)(k0 + i) * m + k0 + j] = D[i * kLD + j];
+    }
+    // panel: L21 = A21 L11^-T, one thread per row
+    const int rows = m - k0 - kb;
+    for (int ii = tid; ii < rows; ii += nt) {
+      double* arow = A + (size_t)(k0 + kb + ii) * m + k0;
+      double* prow = P + (size_t)ii * kLD;
+      for (int c = 0; c < kb; ++c) {
+        double sacc = arow[c];
+        for (int d = 0; d < c; ++d) sacc = fma(-prow[d], D[c * kLD + d], sacc);
+        sacc /= D[c * kLD + c];
+        prow[c] = sacc;
+        arow[c] = sacc;
+      }
+    }
+    __syncthreads();
+    // trailing update of the lower triangle: A22 -= L21 L21^T
+    for (int e = tid; e < rows * rows; e += nt) {
+      const int ii = e / rows, jj = e - ii * rows;
       if (jj <= ii) {
-        const int i = k + 1 + ii, j = k + 1 + jj;
-        A[(size_t)i * m + j] = fma(-col[i], col[j], A[(size_t)i * m + j]);
+        const double* pi = P + (size_t)ii * kLD;
+        const double* pj = P + (size_t)jj * kLD;
+        double sacc = 0.0;
+        for (int c = 0; c < kb; ++c) sacc = fma(pi[c], pj[c], sacc);
+        A[(size_t)(k0 + kb + ii) * m + k0 + kb + jj] -= sacc;
       }
     }
     __syncthreads();
   }
 }
 
-// x <- L^-1 x (forward) or L^-T x (backward), single right-hand side
-__device__ void tri_solve_vec(const double* L, int m, double* x, bool transpose) {
-  if (!transpose) {
-    for (int k = 0; k < m; ++k) {
-      if (threadIdx.x == 0) x[k] /= L[(size_t)k * m + k];
-      __syncthreads();
-      const double xk = x[k];
-      for (int i = k + 1 + threadIdx.x; i < m; i += blockDim.x) x[i] = fma(-L[(size_t)i * m + k], xk, x[i]);
-      __syncthreads();
+// x <- L^-1 x (forward) or L^-T x (backward), single right-hand side, blocked: the diagonal block
+// is solved by one warp out of shared memory, the rest of x is updated by all threads
+__device__ void tri_solve_vec(const double* L, int m, double* x, bool transpose, double* D) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int nblk = (m + kNB - 1) / kNB;
+  for (int bi = 0; bi < nblk; ++bi) {
+    const int k0 = (transpose ? (nblk - 1 - bi) : bi) * kNB;
+    const int kb = min(kNB, m - k0);
+    for (int e = tid; e < kb * kb; e += nt) {
+      const int i = e / kb, j = e - i * kb;
+      D[i * kLD + j] = L[(size_t)(k0 + i) * m + k0 + j];
     }
-  } else {
-    for (int k = m - 1; k >= 0; --k) {
-      if (threadIdx.x == 0) x[k] /= L[(size_t)k * m + k];
-      __syncthreads();
-      const double xk = x[k];
-      for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] = fma(-L[(size_t)k * m + i], xk, x[i]);
-      __syncthreads();
+    __syncthreads();
+    if (warp == 0) {
+      double xi = (lane < kb) ? x[k0 + lane] : 0.0;
+      if (!transpose) {
+        for (int k = 0; k < kb; ++k) {
+          const double xk = __shfl_sync(0xffffffffu, xi, k) / D[k * kLD + k];
+          if (lane == k) xi = xk;
+          else if (lane > k && lane < kb) xi = fma(-D[lane * kLD + k], xk, xi);
+        }
+      } else {
+        for (int k = kb - 1; k >= 0; --k) {
+          const double xk = __shfl_sync(0xffffffffu, xi, k) / D[k * kLD + k];
+          if (lane == k) xi = xk;
+          else if (lane < k) xi = fma(-D[k * kLD + lane], xk, xi);
+        }
+      }
+      if (lane < kb) x[k0 + lane] = xi;
     }
+    __syncthreads();
+    if (!transpose) {
+      for (int i = k0 + kb + tid; i < m; i += nt) {
+        const double* Li = L + (size_t)i * m + k0;
+        double sacc = x[i];
+        for (int c = 0; c < kb; ++c) sacc = fma(-Li[c], x[k0 + c], sacc);
+        x[i] = sacc;
+      }
+    } else {
+      for (int i = tid; i < k0; i += nt) {
+        double sacc = x[i];
+        for (int c = 0; c < kb; ++c) sacc = fma(-L[(size_t)(k0 + c) * m + i], x[k0 + c], sacc);
+        x[i] = sacc;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -184,7 +252,9 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   double* col = x + m;     // Cholesky column
   double* red = col + m;   // 32 doubles
   int* flag = reinterpret_cast<int*>(red + 32);
-  double* A = use_smem ? (red + 34) : (ws_all + (size_t)sys * 2 * mm);
+  double* D = red + 34;                       // diagonal block of the blocked algorithms
+  double* P = D + kNB * kLD;                  // panel, m x kLD
+  double* A = use_smem ? (P + (size_t)m * kLD) : (ws_all + (size_t)sys * 2 * mm);
   double* B = A + mm;
   if (threadIdx.x == 0) *flag = 0;
   __syncthreads();
@@ -204,13 +274,14 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   }
   if (bad) *flag = 2;
   __syncthreads();
+  const bool prepared = (flags & PGB_SOLVE_PREPARED) != 0;  // EtE already holds Q^T E_rest Q + [Q^T E_null Q]_0
   for (int q = 0; q < p && *flag == 0; ++q) {
     for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = hv[(size_t)q * m + i];
     __syncthreads();
-    sym_reflect(A, m, v, tau[q], w, red);
+    if (!prepared) sym_reflect(A, m, v, tau[q], w, red);
     vec_reflect(x, m, v, tau[q], red);
   }
-  for (int pass = (Enull ? 0 : 1); pass < 2; ++pass) {
+  for (int pass = ((Enull && !prepared) ? 0 : 1); pass < 2; ++pass) {
     const double* src = (pass == 0) ? Enull : G;
     bad = 0;
     for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) {
@@ -237,7 +308,7 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   if (*flag == 0) {
     for (int i = threadIdx.x; i < p; i += blockDim.x) x[i] = 0.0;
     __syncthreads();
-    cholesky_lower(A, m, col, flag);
+    cholesky_lower(A, m, D, P, flag);
   }
   __syncthreads();
   const int info = *flag;
@@ -252,8 +323,8 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   double ld_part = 0.0;
   for (int i = threadIdx.x; i < m; i += blockDim.x) ld_part += log(A[(size_t)i * m + i]);
   const double logdet = 2.0 * block_sum(ld_part, red);
-  tri_solve_vec(A, m, x, false);
-  tri_solve_vec(A, m, x, true);
+  tri_solve_vec(A, m, x, false, D);
+  tri_solve_vec(A, m, x, true, D);
   for (int q = p - 1; q >= 0; --q) {
     for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = hv[(size_t)q * m + i];
     __syncthreads();
@@ -303,7 +374,55 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   }
 }
 
-static size_t solve_vec_smem(int m) { return ((size_t)4 * m + 34) * 8; }
+// A0 = Q^T E_rest Q + [Q^T E_null Q]_0: the penalty side of the system in the null-space basis.
+// It does not change during a PIRLS loop, so it is computed once per penalty (pgb_solve_prepare)
+// and handed to pgb_solve with PGB_SOLVE_PREPARED.
+__global__ void __launch_bounds__(kSolveThreads)
+solve_prepare_kernel(int m, const double* __restrict__ EtE_all, const double* __restrict__ Enull_all,
+                     const double* __restrict__ hv, const double* __restrict__ tau, int p, double* __restrict__ A0_all,
+                     double* __restrict__ ws_all) {
+  extern __shared__ __align__(16) double sm[];
+  const int sys = blockIdx.x;
+  const size_t mm = (size_t)m * m;
+  double* v = sm;
+  double* w = v + m;
+  double* red = w + m;
+  double* A = A0_all + (size_t)sys * mm;
+  double* B = ws_all + (size_t)sys * mm;
+  const double* EtE = EtE_all + (size_t)sys * mm;
+  for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) A[e] = EtE[e];
+  if (Enull_all)
+    for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) B[e] = Enull_all[(size_t)sys * mm + e];
+  __syncthreads();
+  for (int q = 0; q < p; ++q) {
+    for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = hv[(size_t)q * m + i];
+    __syncthreads();
+    sym_reflect(A, m, v, tau[q], w, red);
+    if (Enull_all) sym_reflect(B, m, v, tau[q], w, red);
+  }
+  if (Enull_all) {
+    for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) {
+      const int i = e / m, j = e - i * m;
+      if (i >= p && j >= p) A[e] += B[e];
+    }
+  }
+}
+
+extern "C" int pgb_solve_prepare(int32_t m, int32_t nb, const double* EtE, const double* EtE_null, const double* hv,
+                                 const double* tau, int32_t p, double* A0, void* ws, int64_t ws_bytes, void* stream) {
+  if (m < 1 || nb < 1 || !EtE || !A0 || p < 0 || p > m || (p > 0 && (!hv || !tau)) ||
+      (EtE_null && (!ws || ws_bytes < (int64_t)nb * m * m * 8))) {
+    pgb_set_error("pgb_solve_prepare: bad arguments");
+    return PGB_EINVAL;
+  }
+  solve_prepare_kernel<<<nb, kSolveThreads, ((size_t)2 * m + 34) * 8, (cudaStream_t)stream>>>(m, EtE, EtE_null, hv, tau, p, A0,
+                                                                                              (double*)ws);
+  pgb_count_launch(1);
+  PGB_CUDA(cudaGetLastError());
+  return PGB_OK;
+}
+
+static size_t solve_vec_smem(int m) { return ((size_t)4 * m + 34 + kNB * kLD + (size_t)m * kLD) * 8; }
 static bool solve_fits_smem(int m) { return solve_vec_smem(m) + (size_t)2 * m * m * 8 <= kSolveSmemMax; }
 
 extern "C" int64_t pgb_solve_ws_bytes(int32_t m, int32_t nb) {
@@ -344,13 +463,14 @@ __global__ void __launch_bounds__(kSolveThreads)
 chol_check_kernel(int m, const double* __restrict__ Ain, int* __restrict__ info, double* __restrict__ ws,
                   int use_smem) {
   extern __shared__ __align__(16) double sm[];
-  double* col = sm;
-  int* flag = reinterpret_cast<int*>(col + m);
-  double* A = use_smem ? (col + m + 2) : ws;
+  double* D = sm;
+  double* P = D + kNB * kLD;
+  int* flag = reinterpret_cast<int*>(P + (size_t)m * kLD);
+  double* A = use_smem ? (P + (size_t)m * kLD + 2) : ws;
   if (threadIdx.x == 0) *flag = 0;
   for (int e = threadIdx.x; e < m * m; e += blockDim.x) A[e] = Ain[e];
   __syncthreads();
-  cholesky_lower(A, m, col, flag);
+  cholesky_lower(A, m, D, P, flag);
   __syncthreads();
   if (threadIdx.x == 0) *info = *flag;
 }
@@ -360,7 +480,7 @@ extern "C" int64_t pgb_chol_ws_bytes(int32_t m) { return (int64_t)m * m * 8 + 25
 extern "C" int pgb_chol_check(int32_t m, const double* A, int32_t* info_out, void* ws, int64_t ws_bytes,
                               void* stream) {
   if (m < 1 || !A || !info_out) { pgb_set_error("pgb_chol_check: bad arguments"); return PGB_EINVAL; }
-  const size_t vec = ((size_t)m + 2) * 8;
+  const size_t vec = ((size_t)kNB * kLD + (size_t)m * kLD + 2) * 8;
   const bool in_smem = vec + (size_t)m * m * 8 <= kSolveSmemMax;
   if (!in_smem && (!ws || ws_bytes < pgb_chol_ws_bytes(m))) {
     pgb_set_error("pgb_chol_check: workspace too small");

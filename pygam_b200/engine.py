@@ -202,6 +202,8 @@ class Engine:
         self.beta_prev = torch.zeros(m, **f64)
         self.EtE = torch.zeros(m * m, **f64)
         self.EtE_null = torch.zeros(m * m, **f64)
+        self.A0 = torch.zeros(m * m, **f64)  # penalty in the null-space basis (pgb_solve_prepare)
+        self._prep_ws = torch.zeros(m * m, **f64)
         self._has_null_part = False
         self.sol = torch.zeros(m + _lib.SOLVE_OUT_EXTRA, **f64)
         self.cov = None
@@ -283,6 +285,12 @@ class Engine:
         self._has_null_part = EtE_null is not None
         if EtE_null is not None:
             self.EtE_null.copy_(torch.from_numpy(np.ascontiguousarray(EtE_null, dtype=np.float64).ravel()))
+        # the change of basis of the penalty is done once here, not in every PIRLS iteration
+        m = self.m
+        _lib.check(self.lib.pgb_solve_prepare(m, 1, _ptr(self.EtE),
+                                              _ptr(self.EtE_null) if self._has_null_part else C.c_void_p(0),
+                                              _ptr(self.hv), _ptr(self.tau), self.p, _ptr(self.A0), _ptr(self._prep_ws),
+                                              self._prep_ws.numel() * 8, _stream()), "pgb_solve_prepare")
 
     def chol_ok(self, A):
         """True when A (host, m x m) has a Cholesky factor: utils.cholesky (utils.py:77-91)"""
@@ -299,7 +307,7 @@ class Engine:
     def solve(self, coef_prev=None, want_edof=False, want_cov=False, out=None):
         """beta = (G + EtE)^-1 r with the Gram data currently in self.out; returns host dict"""
         m = self.m
-        flags = (_lib.SOLVE_EDOF if want_edof else 0) | (_lib.SOLVE_COV if want_cov else 0)
+        flags = (_lib.SOLVE_EDOF if want_edof else 0) | (_lib.SOLVE_COV if want_cov else 0) | _lib.SOLVE_PREPARED
         if want_cov and self.cov is None:
             self.cov = torch.empty(m * m, dtype=torch.float64, device=self.device)
         prev = None
@@ -308,8 +316,7 @@ class Engine:
             prev = self.beta_prev
         G = self.out
         r = self.out[m * m:]
-        _lib.check(self.lib.pgb_solve(m, 1, _ptr(G), _ptr(r), 1, _ptr(self.EtE),
-                                      _ptr(self.EtE_null) if self._has_null_part else C.c_void_p(0),
+        _lib.check(self.lib.pgb_solve(m, 1, _ptr(G), _ptr(r), 1, _ptr(self.A0), C.c_void_p(0),
                                       _ptr(self.hv), _ptr(self.tau),
                                       self.p, _ptr(prev), 1, flags, _ptr(self.sol),
                                       _ptr(self.cov) if want_cov else C.c_void_p(0), _ptr(self._solve_ws),

@@ -16,7 +16,7 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
-    for name in ("pgb_model_create", "pgb_gram_pass", "pgb_stats_pass", "pgb_solve", "pgb_gram_pass_host",
+    for name in ("pgb_model_create", "pgb_gram_pass", "pgb_stats_pass", "pgb_solve", "pgb_solve_prepare", "pgb_gram_pass_host",
                  "pgb_col_stats", "pgb_model_matrix", "pgb_chol_check"):
         assert name in syms
 
