@@ -93,7 +93,7 @@ def run_reference(args, rank, world):
                              "sample": sample},
             "e2e": {"value": r["rows_per_s"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -300,9 +300,20 @@ def run_b200(args, rank, world, local_rank):
                                 "sample": f"oracle port of the reference PIRLS (sparse model matrix + dense QR + SVD) "
                                           f"on {args.cpu_rows} rows of the same synthetic workload, 3 timed iterations "
                                           f"after 1 warm-up, {r['ms_per_step']:.0f} ms per iteration"}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _emit(line):
+    """the ONE JSON line goes to the process's original stdout"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# libraries loaded later (NCCL prints its version banner to stdout) must not pollute the one-line
+# contract: fd 1 is pointed at stderr for the whole run, the result line is written to the saved fd
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
