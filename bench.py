@@ -203,26 +203,27 @@ def run_b200(args, rank, world, local_rank):
     launches0 = lib.pgb_launch_count()
     _lib.check(lib.pgb_gram_timing(eng.handle, 1), "pgb_gram_timing")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    accum_ms, rec_ms = [], []
+    accum_ms, rec_ms, pass_ms = [], [], []
     e0.record()
     for _ in range(args.steps):
         coef = step(coef)
-        f, r = C.c_float(), C.c_float()
-        _lib.check(lib.pgb_gram_last_ms(eng.handle, C.byref(r), C.byref(f)), "pgb_gram_last_ms")
+        f, r, t = C.c_float(), C.c_float(), C.c_float()
+        _lib.check(lib.pgb_gram_last_ms(eng.handle, C.byref(r), C.byref(f), C.byref(t)), "pgb_gram_last_ms")
         accum_ms.append(f.value)
         rec_ms.append(r.value)
+        pass_ms.append(t.value)
     e1.record()
     barrier()
     launches = lib.pgb_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     _lib.check(lib.pgb_gram_timing(eng.handle, 0), "pgb_gram_timing")
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    acc = torch.tensor([float(np.mean(accum_ms)), float(np.mean(rec_ms))], dtype=torch.float64, device=dev)
+    acc = torch.tensor([float(np.mean(accum_ms)), float(np.mean(rec_ms)), float(np.mean(pass_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(acc, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
-    accum, records = float(acc[0].item()), float(acc[1].item())
+    accum, records, gram_pass_ms = float(acc[0].item()), float(acc[1].item()), float(acc[2].item())
     value = n * world / (ms_per_step * 1e-3)
 
     # ---- end to end: host buffers in, coefficients out, every step ----
@@ -274,7 +275,7 @@ def run_b200(args, rank, world, local_rank):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    gram_ms = accum + records
+    gram_ms = gram_pass_ms  # records + accumulation + reductions of all row chunks
     achieved = n * BYTES_PER_ROW / (gram_ms * 1e-3) / 1e9
     fma_per_clk_sm = n * FMA_PER_ROW / (accum * 1e-3) / (148 * 1.965e9)
     roofline = {"kernel": "gram_records_kernel + gram_accum_kernel (the Gram pass of one PIRLS iteration)", "bound": "hbm",

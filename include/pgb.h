@@ -139,11 +139,11 @@ int pgb_gram_pass(const pgb_model* model, int32_t mode, const double* X, int64_t
                   const double* y, const float* w, const double* beta, double* out, void* ws,
                   int64_t ws_bytes, void* stream);
 
-/* Time the two kernels of the Gram pass with CUDA events on the launching stream: enable, run
- * pgb_gram_pass, then read the device time (ms, summed over the row chunks) of the records kernel
- * (basis + IRLS step -> row records) and of the accumulation kernel (records -> G, r). */
+/* Time the Gram pass with CUDA events: enable, run pgb_gram_pass, then read the device time (ms) of
+ * the records kernel (basis + IRLS step -> row records) and of the accumulation kernel (records ->
+ * G, r), each summed over the row chunks, and of the whole pass (with the reductions). */
 int pgb_gram_timing(pgb_model* model, int32_t enable);
-int pgb_gram_last_ms(pgb_model* model, float* records_ms, float* accum_ms);
+int pgb_gram_last_ms(pgb_model* model, float* records_ms, float* accum_ms, float* total_ms);
 
 /* scalars written by pgb_stats_pass (doubles) */
 enum { PGB_SS_N = 0, PGB_SS_WDEV = 1,  /* sum w * deviance(y, mu), unscaled (pygam.py:1215-1217) */

@@ -64,7 +64,7 @@ SYMBOLS = {
     "pgb_version": (C.c_int, []),
     "pgb_launch_count": (C.c_longlong, []),
     "pgb_gram_timing": (C.c_int, [_P, C.c_int32]),
-    "pgb_gram_last_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "pgb_gram_last_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pgb_model_create": (C.c_int, [C.POINTER(PgbTerm), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_double, C.c_double, C.c_int32, C.POINTER(_P)]),
     "pgb_model_destroy": (None, [_P]),

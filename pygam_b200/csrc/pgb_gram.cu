@@ -28,7 +28,7 @@ static const int kMaxWarps = 15;      // consumer (accumulating) warps per CTA o
 static const int kNBuf = 3;           // record buffers of the accumulation kernel (TMA ring)
 static const int kSlotBytes = 10;     // record slot: double value + uint16 index (two arrays)
 static const int kRecThreads = 256;   // CTA of the records kernel
-static const int64_t kChunkRows = 1 << 22;  // rows whose records are materialised at a time
+static const int64_t kChunkRows = 1 << 22;  // about this many rows' records are materialised at a time
 
 // ----------------------------------------------------------------------------------------
 // plan
@@ -526,14 +526,21 @@ void pgb_gram_release(pgb_model* M) {
 static int64_t rec_tile_bytes(const pgb_model* M) {
   return (int64_t)M->n_slots_all * tile_pitch(M->tile_rows) * kSlotBytes;
 }
-static int64_t gram_fixed_ws_doubles(const pgb_model* M) {
-  return M->partial_doubles + (int64_t)M->rec_ctas * PGB_GS_COUNT;
+// Rows are processed in chunks of whole tiles (bounded record workspace): records kernel, then the
+// accumulation kernel continuing from its partials of the previous chunk.  (Running the records
+// kernel of the next chunk concurrently on a second stream was measured: it contends for the LSU
+// pipe and lengthens the pass by 5 %.)
+static int64_t chunk_rows_for(const pgb_model* M, int64_t n) {
+  const int64_t T = M->tile_rows;
+  if (n <= kChunkRows / 2) return ((n + T - 1) / T) * T;
+  const int64_t nch = std::max<int64_t>(2, (n + kChunkRows - 1) / kChunkRows);
+  const int64_t rows = (n + nch - 1) / nch;
+  return ((rows + T - 1) / T) * T;
 }
 extern "C" int64_t pgb_gram_ws_bytes(const pgb_model* M, int64_t n) {
   if (!M) return 0;
-  const int64_t rows = std::max<int64_t>(1, std::min(n, kChunkRows));
-  const int64_t tiles = (rows + M->tile_rows - 1) / M->tile_rows;
-  return gram_fixed_ws_doubles(M) * 8 + tiles * rec_tile_bytes(M) + 512;
+  const int64_t tiles = chunk_rows_for(M, std::max<int64_t>(n, 1)) / M->tile_rows;
+  return (M->partial_doubles + (int64_t)M->rec_ctas * PGB_GS_COUNT) * 8 + tiles * rec_tile_bytes(M) + 1024;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -811,7 +818,7 @@ gram_records_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, const
 __global__ void __launch_bounds__(32 * (kMaxWarps + 1))
 gram_accum_kernel(const DStep* __restrict__ g_steps, const DWarp* __restrict__ g_warps, const DRun* __restrict__ g_runs,
                   const DRole* __restrict__ g_roles, int n_roles, const double* __restrict__ rec_val_g,
-                  const uint16_t* __restrict__ rec_idx_g, int64_t n, int T, int n_slots_all, int dbg,
+                  const uint16_t* __restrict__ rec_idx_g, int64_t n, int T, int n_slots_all, int dbg, int resume,
                   double* __restrict__ partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int ridx = 0;
@@ -828,7 +835,11 @@ gram_accum_kernel(const DStep* __restrict__ g_steps, const DWarp* __restrict__ g
   DRun* runs = reinterpret_cast<DRun*>(steps + role.n_steps);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int64_t i = tid; i < role.acc_size; i += blockDim.x) acc[i] = 0.0;
+  {
+    // later row chunks of one pass continue from this CTA's partial of the previous chunk
+    const double* prev = partials + role.part_off + (int64_t)cta_in_role * role.acc_size;
+    for (int64_t i = tid; i < role.acc_size; i += blockDim.x) acc[i] = resume ? prev[i] : 0.0;
+  }
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(g_steps + role.step0);
     uint32_t* dst = reinterpret_cast<uint32_t*>(steps);
@@ -961,10 +972,12 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
   }
   const int n_roles = (int)M->roles.size();
   const int T = M->tile_rows, TP = tile_pitch(T);
+  pgb_model* Mm = const_cast<pgb_model*>(M);
   double* partials = (double*)ws;
   double* scal_part = partials + M->partial_doubles;
   // records of one chunk: values then indices, 256-byte aligned
-  const int64_t chunk_tiles = (std::min(n, kChunkRows) + T - 1) / T;
+  const int64_t chunk_rows = chunk_rows_for(M, n);
+  const int64_t chunk_tiles = chunk_rows / T;
   uintptr_t rp = (uintptr_t)(scal_part + (int64_t)M->rec_ctas * PGB_GS_COUNT);
   rp = (rp + 255) & ~(uintptr_t)255;
   double* rec_val = (double*)rp;
@@ -977,62 +990,68 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
   }
   const char* edbg = getenv("PGB_GRAM_DEBUG");  // timing experiments only
   const int dbg = edbg ? atoi(edbg) : 0;
-  pgb_model::Timing& tm = const_cast<pgb_model*>(M)->timing;
-  int chunk = 0;
-  for (int64_t r0 = 0; r0 < n; r0 += kChunkRows, ++chunk) {
-    const int64_t nr = std::min(kChunkRows, n - r0);
+  pgb_model::Timing& tm = Mm->timing;
+  const int n_chunks = (int)((n + chunk_rows - 1) / chunk_rows);
+  if (tm.enabled) {
+    while ((int)tm.chunk_ev.size() < 3 * n_chunks + 2) {
+      cudaEvent_t e;
+      PGB_CUDA(cudaEventCreate(&e));
+      tm.chunk_ev.push_back(e);
+    }
+    PGB_CUDA(cudaEventRecord(tm.chunk_ev[0], st));
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const int64_t r0 = (int64_t)c * chunk_rows, nr = std::min(chunk_rows, n - r0);
     const int64_t tiles = (nr + T - 1) / T;
     const int grid1 = (int)std::min<int64_t>((tiles * T + kRecThreads - 1) / kRecThreads, M->rec_ctas);
-    cudaEvent_t* ev = nullptr;
-    if (tm.enabled) {
-      while ((int)tm.chunk_ev.size() < 3 * (chunk + 1)) {
-        cudaEvent_t e;
-        PGB_CUDA(cudaEventCreate(&e));
-        tm.chunk_ev.push_back(e);
-      }
-      ev = &tm.chunk_ev[3 * chunk];
-      PGB_CUDA(cudaEventRecord(ev[0], st));
-    }
+    if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[2 + 3 * c], st));
     gram_records_kernel<<<grid1, kRecThreads, M->rec_smem, st>>>(M->d_terms, M->n_terms, M->m, M->d_rterms, M->d_pad_slots,
                                                                    (int)M->pad_slots.size(), M->n_slots_all, M->fam, mode, X + r0,
                                                                    nr, ld, y + r0, w ? w + r0 : nullptr, beta, T, rec_val, rec_idx,
                                                                    scal_part);
     PGB_CUDA(cudaGetLastError());
-    if (ev) PGB_CUDA(cudaEventRecord(ev[1], st));
+    if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[3 + 3 * c], st));
     gram_accum_kernel<<<M->gram_ctas, M->gram_threads, M->gram_smem, st>>>(M->d_steps, M->d_warps, M->d_runs, M->d_roles, n_roles,
-                                                                              rec_val, rec_idx, nr, T, M->n_slots_all, dbg, partials);
+                                                                              rec_val, rec_idx, nr, T, M->n_slots_all, dbg,
+                                                                              c > 0 ? 1 : 0, partials);
     PGB_CUDA(cudaGetLastError());
-    if (ev) PGB_CUDA(cudaEventRecord(ev[2], st));
-    const int acc_flag = (accumulate || chunk > 0) ? 1 : 0;
-    const int rb = 256;
-    gram_reduce_kernel<<<(unsigned)((M->map_size + rb - 1) / rb), rb, 0, st>>>(partials, M->d_roles, n_roles, M->d_elem_map,
-                                                                                M->map_size, M->m, out, acc_flag);
-    scalar_reduce_kernel<<<1, 32, 0, st>>>(scal_part, grid1, PGB_GS_COUNT, out + (int64_t)M->m * M->m + M->m, acc_flag);
-    pgb_count_launch(4);
-    PGB_CUDA(cudaGetLastError());
+    if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[4 + 3 * c], st));
+    scalar_reduce_kernel<<<1, 32, 0, st>>>(scal_part, grid1, PGB_GS_COUNT, out + (int64_t)M->m * M->m + M->m,
+                                           (accumulate || c > 0) ? 1 : 0);
+    pgb_count_launch(3);
   }
-  if (tm.enabled) { tm.pending = true; tm.n_chunks = chunk; }
+  const int rb = 256;
+  gram_reduce_kernel<<<(unsigned)((M->map_size + rb - 1) / rb), rb, 0, st>>>(partials, M->d_roles, n_roles, M->d_elem_map,
+                                                                              M->map_size, M->m, out, accumulate);
+  pgb_count_launch(1);
+  PGB_CUDA(cudaGetLastError());
+  if (tm.enabled) {
+    PGB_CUDA(cudaEventRecord(tm.chunk_ev[1], st));
+    tm.pending = true;
+    tm.n_chunks = n_chunks;
+  }
   return PGB_OK;
 }
 
-// optional timing of the two kernels of the Gram pass with CUDA events recorded on the launching
-// stream (summed over the row chunks); used by bench.py for the roofline figure
+// optional timing of the Gram pass with CUDA events on the launching stream: the two kernels (summed
+// over the row chunks) and the whole pass; used by bench.py for the roofline figure
 extern "C" int pgb_gram_timing(pgb_model* M, int32_t enable) {
   if (!M) { pgb_set_error("pgb_gram_timing: null model"); return PGB_EINVAL; }
   M->timing.enabled = enable != 0;
   M->timing.pending = false;
   return PGB_OK;
 }
-extern "C" int pgb_gram_last_ms(pgb_model* M, float* records_ms, float* accum_ms) {
-  if (!M || !records_ms || !accum_ms || !M->timing.pending) { pgb_set_error("pgb_gram_last_ms: no timed pass"); return PGB_EINVAL; }
+extern "C" int pgb_gram_last_ms(pgb_model* M, float* records_ms, float* accum_ms, float* total_ms) {
+  if (!M || !records_ms || !accum_ms || !total_ms || !M->timing.pending) { pgb_set_error("pgb_gram_last_ms: no timed pass"); return PGB_EINVAL; }
   pgb_model::Timing& tm = M->timing;
   *records_ms = 0.f;
   *accum_ms = 0.f;
+  PGB_CUDA(cudaEventSynchronize(tm.chunk_ev[1]));
+  PGB_CUDA(cudaEventElapsedTime(total_ms, tm.chunk_ev[0], tm.chunk_ev[1]));
   for (int c = 0; c < tm.n_chunks; ++c) {
     float a = 0.f, b = 0.f;
-    PGB_CUDA(cudaEventSynchronize(tm.chunk_ev[3 * c + 2]));
-    PGB_CUDA(cudaEventElapsedTime(&a, tm.chunk_ev[3 * c], tm.chunk_ev[3 * c + 1]));
-    PGB_CUDA(cudaEventElapsedTime(&b, tm.chunk_ev[3 * c + 1], tm.chunk_ev[3 * c + 2]));
+    PGB_CUDA(cudaEventElapsedTime(&a, tm.chunk_ev[2 + 3 * c], tm.chunk_ev[3 + 3 * c]));
+    PGB_CUDA(cudaEventElapsedTime(&b, tm.chunk_ev[3 + 3 * c], tm.chunk_ev[4 + 3 * c]));
     *records_ms += a;
     *accum_ms += b;
   }

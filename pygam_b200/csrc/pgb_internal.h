@@ -134,7 +134,7 @@ struct pgb_model {
   struct Timing {
     bool enabled = false, pending = false;
     int n_chunks = 0;
-    std::vector<cudaEvent_t> chunk_ev;  // per row chunk: before records, between, after accumulation
+    std::vector<cudaEvent_t> chunk_ev;  // [0, 1]: whole pass; then per row chunk: before records, between, after accumulation
   } timing;
 };
 

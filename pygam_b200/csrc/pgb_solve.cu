@@ -191,25 +191,66 @@ __device__ void tri_solve_vec(const double* L, int m, double* x, bool transpose,
   }
 }
 
-// B <- L^-1 B (transpose = false) or L^-T B (true); one thread per column of B
-__device__ void tri_solve_cols(const double* L, int m, double* B, bool transpose) {
-  for (int j = threadIdx.x; j < m; j += blockDim.x) {
-    if (!transpose) {
-      for (int i = 0; i < m; ++i) {
-        double s = B[(size_t)i * m + j];
-        const double* Li = L + (size_t)i * m;
-        for (int k = 0; k < i; ++k) s = fma(-Li[k], B[(size_t)k * m + j], s);
-        B[(size_t)i * m + j] = s / Li[i];
+// B <- L^-1 B (transpose = false) or L^-T B (true), blocked: per block row the diagonal block D,
+// the solved block Y (kNB x wc columns) and the panel of L that updates the remaining rows are in
+// shared memory; the columns of B are processed in chunks of wc (what fits next to the panel)
+__device__ void tri_solve_cols(const double* L, int m, double* B, bool transpose, double* D, double* P, double* Y, int wc) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int nblk = (m + kNB - 1) / kNB;
+  for (int j0 = 0; j0 < m; j0 += wc) {
+    const int nc = min(wc, m - j0);
+    for (int bi = 0; bi < nblk; ++bi) {
+      const int k0 = (transpose ? (nblk - 1 - bi) : bi) * kNB;
+      const int kb = min(kNB, m - k0);
+      for (int e = tid; e < kb * kb; e += nt) {
+        const int i = e / kb, j = e - i * kb;
+        D[i * kLD + j] = L[(size_t)(k0 + i) * m + k0 + j];
       }
-    } else {
-      for (int i = m - 1; i >= 0; --i) {
-        double s = B[(size_t)i * m + j];
-        for (int k = i + 1; k < m; ++k) s = fma(-L[(size_t)k * m + i], B[(size_t)k * m + j], s);
-        B[(size_t)i * m + j] = s / L[(size_t)i * m + i];
+      // panel: the rows of B still to be updated, as P[row][c]
+      const int prow0 = transpose ? 0 : k0 + kb, prows = transpose ? k0 : m - k0 - kb;
+      for (int e = tid; e < prows * kb; e += nt) {
+        if (!transpose) {
+          const int ii = e / kb, c = e - ii * kb;
+          P[(size_t)ii * kLD + c] = L[(size_t)(prow0 + ii) * m + k0 + c];
+        } else {
+          const int c = e / prows, ii = e - c * prows;  // consecutive threads read consecutive columns of L
+          P[(size_t)ii * kLD + c] = L[(size_t)(k0 + c) * m + ii];
+        }
       }
+      __syncthreads();
+      // block solve, one thread per column
+      for (int j = tid; j < nc; j += nt) {
+        double* bcol = B + (size_t)k0 * m + j0 + j;
+        if (!transpose) {
+          for (int c = 0; c < kb; ++c) {
+            double sacc = bcol[(size_t)c * m];
+            for (int d = 0; d < c; ++d) sacc = fma(-D[c * kLD + d], Y[(size_t)d * wc + j], sacc);
+            sacc /= D[c * kLD + c];
+            Y[(size_t)c * wc + j] = sacc;
+            bcol[(size_t)c * m] = sacc;
+          }
+        } else {
+          for (int c = kb - 1; c >= 0; --c) {
+            double sacc = bcol[(size_t)c * m];
+            for (int d = c + 1; d < kb; ++d) sacc = fma(-D[d * kLD + c], Y[(size_t)d * wc + j], sacc);
+            sacc /= D[c * kLD + c];
+            Y[(size_t)c * wc + j] = sacc;
+            bcol[(size_t)c * m] = sacc;
+          }
+        }
+      }
+      __syncthreads();
+      // update of the remaining rows: B[row][j] -= sum_c P[row][c] Y[c][j]
+      for (int e = tid; e < prows * nc; e += nt) {
+        const int ii = e / nc, j = e - ii * nc;
+        const double* pr = P + (size_t)ii * kLD;
+        double sacc = 0.0;
+        for (int c = 0; c < kb; ++c) sacc = fma(pr[c], Y[(size_t)c * wc + j], sacc);
+        B[(size_t)(prow0 + ii) * m + j0 + j] -= sacc;
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
 }
 
 __device__ void transpose_inplace(double* B, int m) {
@@ -235,7 +276,7 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
              const double* __restrict__ hv,
              const double* __restrict__ tau, int p, const double* __restrict__ beta_prev_all,
              int share_prev, double* __restrict__ out_all, double* __restrict__ cov_all,
-             double* __restrict__ ws_all, int flags, int use_smem) {
+             double* __restrict__ ws_all, int flags, int use_smem, int wc) {
   extern __shared__ __align__(16) double sm[];
   const int sys = blockIdx.x;
   const size_t mm = (size_t)m * m;
@@ -254,7 +295,8 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   int* flag = reinterpret_cast<int*>(red + 32);
   double* D = red + 34;                       // diagonal block of the blocked algorithms
   double* P = D + kNB * kLD;                  // panel, m x kLD
-  double* A = use_smem ? (P + (size_t)m * kLD) : (ws_all + (size_t)sys * 2 * mm);
+  double* Y = P + (size_t)m * kLD;            // solved block of the column solves, kNB x wc
+  double* A = use_smem ? (Y + (size_t)kNB * wc) : (ws_all + (size_t)sys * 2 * mm);
   double* B = A + mm;
   if (threadIdx.x == 0) *flag = 0;
   __syncthreads();
@@ -342,17 +384,17 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   double edof = __longlong_as_double(0x7ff8000000000000LL);
   if (flags & (PGB_SOLVE_WANT_EDOF | PGB_SOLVE_WANT_COV)) {
     // Z = L^-1 Gt L^-T (symmetric); edof = tr(Z)
-    tri_solve_cols(A, m, B, false);
+    tri_solve_cols(A, m, B, false, D, P, Y, wc);
     transpose_inplace(B, m);
-    tri_solve_cols(A, m, B, false);
+    tri_solve_cols(A, m, B, false, D, P, Y, wc);
     double tr = 0.0;
     for (int i = threadIdx.x; i < m; i += blockDim.x) tr += B[(size_t)i * m + i];
     edof = block_sum(tr, red);
     if ((flags & PGB_SOLVE_WANT_COV) && cov_all) {
       // cov = Q L^-T Z L^-1 Q^T
-      tri_solve_cols(A, m, B, true);
+      tri_solve_cols(A, m, B, true, D, P, Y, wc);
       transpose_inplace(B, m);
-      tri_solve_cols(A, m, B, true);
+      tri_solve_cols(A, m, B, true, D, P, Y, wc);
       for (int q = p - 1; q >= 0; --q) {
         for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = hv[(size_t)q * m + i];
         __syncthreads();
@@ -423,7 +465,13 @@ extern "C" int pgb_solve_prepare(int32_t m, int32_t nb, const double* EtE, const
 }
 
 static size_t solve_vec_smem(int m) { return ((size_t)4 * m + 34 + kNB * kLD + (size_t)m * kLD) * 8; }
-static bool solve_fits_smem(int m) { return solve_vec_smem(m) + (size_t)2 * m * m * 8 <= kSolveSmemMax; }
+// columns of B solved at a time: as many as fit next to the vectors and the panel (at least 32)
+static int solve_col_chunk(int m, bool with_matrices) {
+  const size_t used = solve_vec_smem(m) + (with_matrices ? (size_t)2 * m * m * 8 : 0);
+  if (used + (size_t)kNB * 32 * 8 > kSolveSmemMax) return 0;
+  return (int)std::min<size_t>((size_t)m, (kSolveSmemMax - used) / ((size_t)kNB * 8));
+}
+static bool solve_fits_smem(int m) { return solve_col_chunk(m, true) >= std::min(m, 32); }
 
 extern "C" int64_t pgb_solve_ws_bytes(int32_t m, int32_t nb) {
   if (solve_fits_smem(m)) return 256;
@@ -443,8 +491,9 @@ extern "C" int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r
     pgb_set_error("pgb_solve: workspace too small");
     return PGB_EINVAL;
   }
-  size_t smem = solve_vec_smem(m) + (in_smem ? (size_t)2 * m * m * 8 : 0);
-  if (smem > kSolveSmemMax) { pgb_set_error("pgb_solve: m=%d too large", m); return PGB_EUNSUPPORTED; }
+  const int wc = solve_col_chunk(m, in_smem);
+  if (wc < 1) { pgb_set_error("pgb_solve: m=%d too large", m); return PGB_EUNSUPPORTED; }
+  const size_t smem = solve_vec_smem(m) + (size_t)kNB * wc * 8 + (in_smem ? (size_t)2 * m * m * 8 : 0);
   static thread_local bool attr_set = false;
   if (!attr_set) {
     PGB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax));
@@ -452,7 +501,7 @@ extern "C" int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r
   }
   solve_kernel<<<nb, kSolveThreads, smem, (cudaStream_t)stream>>>(m, G, r, share_gram, EtE, EtE_null, hv, tau, p, beta_prev,
                                                                   share_prev, out, cov_out, (double*)ws, flags,
-                                                                  in_smem ? 1 : 0);
+                                                                  in_smem ? 1 : 0, wc);
   pgb_count_launch(1);
   PGB_CUDA(cudaGetLastError());
   return PGB_OK;
