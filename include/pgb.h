@@ -165,6 +165,15 @@ int pgb_stats_pass(const pgb_model* model, const double* X, int64_t n, int64_t l
                    double ybar, int32_t poisson_round, double* scalars, double* lp_out,
                    double* mu_out, void* ws, int64_t ws_bytes, void* stream);
 
+/* Linear predictor of one term (term >= 0) or of the whole model (term = -1) and its variance
+ * var_i = x_i^T cov x_i per row, basis rows evaluated on the fly: GAM._get_quantiles
+ * (pygam.py:1399-1404) over _modelmat / _linear_predictor restricted to a term (pygam.py:385-421,
+ * 469-497) -- the n-sized part of confidence_intervals / prediction_intervals / partial_dependence
+ * (pygam.py:1297-1334, 1520-1643, 2477-2506).  cov: m x m (device, symmetric); lp_out, var_out: n
+ * doubles each, either may be NULL. */
+int pgb_interval_pass(const pgb_model* model, const double* X, int64_t n, int64_t ld, const double* beta,
+                      const double* cov, int32_t term, double* lp_out, double* var_out, void* stream);
+
 /* ---- m x m penalised solve --------------------------------------------------------------
  * Replaces pygam.py:783-805 (QR of W.B, SVD of [R; E], back-projection) by the algebraically
  * equal beta = (G + E^T E)^-1 r, solved in a basis T = [Nhat | Z] that separates the analytic

@@ -81,6 +81,7 @@ SYMBOLS = {
     "pgb_stats_pass": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_double, C.c_double,
                                  C.c_int32, _P, _P, _P, _P, C.c_int64, _P]),
     "pgb_solve_ws_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "pgb_interval_pass": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, C.c_int32, _P, _P, _P]),
     "pgb_solve_prepare": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, _P, C.c_int64, _P]),
     "pgb_solve": (C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, C.c_int32,
                             C.c_int32, _P, _P, _P, C.c_int64, _P]),

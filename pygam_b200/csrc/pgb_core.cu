@@ -306,6 +306,70 @@ extern "C" int pgb_model_matrix(const pgb_model* M, const double* X, int64_t n, 
 }
 
 // ----------------------------------------------------------------------------------------
+// interval pass: per row the linear predictor of one term (or the whole model) and its variance
+// x_i^T cov x_i with the basis row evaluated on the fly -- GAM._get_quantiles (pygam.py:1399-1404)
+// over _modelmat / _linear_predictor restricted to a term (pygam.py:385-421, 469-497)
+// ----------------------------------------------------------------------------------------
+static const int kIntervalMaxNnz = 320;
+struct EmitCollect {
+  int32_t* col;
+  double* val;
+  int n;
+  __device__ __forceinline__ void operator()(int c, double v) {
+    if (n < kIntervalMaxNnz) { col[n] = c; val[n] = v; }
+    ++n;
+  }
+};
+__global__ void __launch_bounds__(128)
+interval_pass_kernel(const DTerm* __restrict__ terms, int n_terms, int m, int term, const double* __restrict__ X,
+                     int64_t n, int64_t ld, const double* __restrict__ beta, const double* __restrict__ cov,
+                     double* __restrict__ lp_out, double* __restrict__ var_out) {
+  int32_t col[kIntervalMaxNnz];
+  double val[kIntervalMaxNnz];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    EmitCollect e{col, val, 0};
+    if (term < 0) {
+      for (int t = 0; t < n_terms; ++t) eval_term(terms[t], X, ld, i, e);
+    } else {
+      eval_term(terms[term], X, ld, i, e);
+    }
+    const int k = min(e.n, kIntervalMaxNnz);
+    double lp = 0.0, var = 0.0;
+    for (int a = 0; a < k; ++a) lp = fma(val[a], __ldg(beta + col[a]), lp);
+    if (var_out) {
+      for (int a = 0; a < k; ++a) {
+        const double* crow = cov + (size_t)col[a] * m;
+        double s = 0.5 * val[a] * __ldg(crow + col[a]);
+        for (int b = a + 1; b < k; ++b) s = fma(val[b], __ldg(crow + col[b]), s);
+        var = fma(2.0 * val[a], s, var);  // cov is symmetric: diagonal once, every off-diagonal pair twice
+      }
+    }
+    if (lp_out) lp_out[i] = lp;
+    if (var_out) var_out[i] = var;
+  }
+}
+extern "C" int pgb_interval_pass(const pgb_model* M, const double* X, int64_t n, int64_t ld, const double* beta,
+                                 const double* cov, int32_t term, double* lp_out, double* var_out, void* stream) {
+  if (!M || !X || !beta || n < 1 || ld < n || term < -1 || term >= M->n_terms || (var_out && !cov)) {
+    pgb_set_error("pgb_interval_pass: bad arguments");
+    return PGB_EINVAL;
+  }
+  int k = 0;
+  for (int t = 0; t < M->n_terms; ++t)
+    if (term < 0 || t == term) k += M->dterms[t].nnz;
+  if (k > kIntervalMaxNnz) {
+    pgb_set_error("pgb_interval_pass: %d non-zeros per row (limit %d)", k, kIntervalMaxNnz);
+    return PGB_EUNSUPPORTED;
+  }
+  const int grid = (int)std::min<int64_t>((n + 127) / 128, kSMs * 8);
+  interval_pass_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(M->d_terms, M->n_terms, M->m, term, X, n, ld, beta, cov,
+                                                                lp_out, var_out);
+  PGB_LAUNCHED(1);
+  PGB_CUDA(cudaGetLastError());
+  return PGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------
 // statistics / predict pass: lp, mu and the sums of _estimate_model_statistics on ALL rows
 // ----------------------------------------------------------------------------------------
 // One CTA walks tiles of R rows (round robin over the grid).  Thread 0 issues one TMA bulk copy

@@ -342,6 +342,19 @@ class Engine:
             all_reduce_(self.stat_scalars, "sum")
         return self.stat_scalars.cpu().numpy().copy(), lp, mu
 
+    def interval_pass(self, data, coef, cov=None, term=-1):
+        """lp of one term (or all, term = -1) and var_i = x_i^T cov x_i per row (pygam.py:1399-1404);
+        returns device tensors (lp, var); var is None without cov"""
+        self.beta.copy_(torch.as_tensor(coef, dtype=torch.float64))
+        lp = torch.empty(data.n, dtype=torch.float64, device=self.device)
+        var = covd = None
+        if cov is not None:
+            covd = torch.from_numpy(np.ascontiguousarray(cov, dtype=np.float64)).to(self.device)
+            var = torch.empty(data.n, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.pgb_interval_pass(self.handle, _ptr(data.Xt), data.n, data.n, _ptr(self.beta), _ptr(covd),
+                                              int(term), _ptr(lp), _ptr(var), _stream()), "pgb_interval_pass")
+        return lp, var
+
     def model_matrix(self, data):
         out = torch.empty(data.n * self.m, dtype=torch.float64, device=self.device)
         _lib.check(self.lib.pgb_model_matrix(self.handle, _ptr(data.Xt), data.n, data.n, _ptr(out), _stream()),

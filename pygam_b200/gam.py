@@ -569,6 +569,141 @@ class GAM:
             return mm
         return mm[:, self.terms.get_coef_indices(term)]
 
+    # ---- intervals and partial dependence ----
+    def _link_mu(self, lp):
+        """Link.mu on host arrays (links.py:32-314), for the small interval outputs"""
+        name, lv = self.link.name, float(self.distribution.levels)
+        with np.errstate(all="ignore"):
+            if name == "identity":
+                return lp
+            if name == "logit":
+                e = np.exp(lp)
+                return lv * e / (e + 1.0)
+            if name == "log":
+                return np.exp(lp)
+            if name == "inverse":
+                return lp ** -1.0
+            return lp ** -0.5
+
+    def _term_index(self, term):
+        return term if term >= 0 else len(self.terms) + term
+
+    def _get_quantiles(self, X, width, quantiles, prediction=False, xform=True, term=-1, lp_var=None):
+        """pygam.py:1336-1421: lp + q * sqrt(x^T cov x) per quantile; the n-sized part (lp and the
+        quadratic form, basis rows on the fly) is pgb_interval_pass"""
+        if quantiles is not None:
+            quantiles = np.atleast_1d(quantiles)
+        else:
+            alpha = (1 - width) / 2.0
+            quantiles = [alpha, 1 - alpha]
+        for quantile in quantiles:
+            if (quantile >= 1) or (quantile <= 0):
+                raise ValueError(f"quantiles must be in (0, 1), but found {quantiles}")
+        if lp_var is None:
+            lp_var = self._lp_and_var(X, term)
+        lp, var = lp_var
+        var = var.copy()
+        if prediction:
+            var += self.distribution.scale ** 2
+        import scipy.stats
+
+        lines = []
+        for quantile in quantiles:
+            if self.distribution._known_scale:
+                q = scipy.stats.norm.ppf(quantile)
+            else:
+                q = scipy.stats.t.ppf(quantile, df=self.statistics_["n_samples"] - self.statistics_["edof"])
+            lines.append(lp + q * var ** 0.5)
+        lines = np.vstack(lines).T
+        if xform:
+            lines = self._link_mu(lines)
+        return lines
+
+    def _lp_and_var(self, X, term=-1):
+        data = self._prepare_data(X, fitting=False)
+        self._check_predict_X(data)
+        eng = self._get_engine(data)
+        lp, var = eng.interval_pass(DeviceData(data.Xt), self.coef_, self.statistics_["cov"],
+                                    -1 if term == -1 else self._term_index(term))
+        return lp.cpu().numpy(), var.cpu().numpy()
+
+    def confidence_intervals(self, X, width=0.95, quantiles=None):
+        """pygam.py:1297-1334"""
+        if not self._is_fitted:
+            raise AttributeError("GAM has not been fitted. Call fit first.")
+        return self._get_quantiles(X, width, quantiles, prediction=False)
+
+    def _flatten_mesh(self, Xs, term):
+        """pygam.py:1423-1436"""
+        n = Xs[0].size
+        t = self.terms[term]
+        sub = list(t) if t.istensor else [t]
+        X = np.zeros((n, self.statistics_["m_features"]))
+        for term_, x in zip(sub, Xs):
+            X[:, term_.feature] = x.ravel()
+        return X
+
+    def generate_X_grid(self, term, n=100, meshgrid=False):
+        """pygam.py:1438-1518"""
+        if not self._is_fitted:
+            raise AttributeError("GAM has not been fitted. Call fit first.")
+        t = self.terms[term]
+        if t.isintercept:
+            raise ValueError("cannot create grid for intercept term")
+        if t.istensor:
+            Xs = [np.linspace(term_.edge_knots_[0], term_.edge_knots_[1], num=n) for term_ in t]
+            Xs = np.meshgrid(*Xs, indexing="ij")
+            if meshgrid:
+                return tuple(Xs)
+            return self._flatten_mesh(Xs, term=term)
+        if getattr(t, "edge_knots_", None) is not None:
+            x = np.linspace(t.edge_knots_[0], t.edge_knots_[1], num=n)
+            if meshgrid:
+                return (x,)
+            X = np.zeros((n, self.statistics_["m_features"]))
+            X[:, t.feature] = x
+            if getattr(t, "by", None) is not None:
+                X[:, t.by] = 1.0
+            return X
+        raise TypeError(f"Unexpected term type: {t}")
+
+    def partial_dependence(self, term, X=None, width=None, quantiles=None, meshgrid=False):
+        """pygam.py:1520-1643"""
+        if not self._is_fitted:
+            raise AttributeError("GAM has not been fitted. Call fit first.")
+        if not isinstance(term, (int, np.integer)) or isinstance(term, bool):
+            raise ValueError(f"term must be an integer, but found term: {term}")
+        if (term >= len(self.terms)) or (term < -1):
+            raise ValueError(f"Term {term} out of range for model with {len(self.terms)} terms")
+        if self.terms[term].isintercept:
+            raise ValueError("cannot create grid for intercept term")
+        if X is None:
+            X = self.generate_X_grid(term=term, meshgrid=meshgrid)
+        shape = None
+        if meshgrid:
+            if not isinstance(X, tuple):
+                raise ValueError(f"X must be a tuple of grids if `meshgrid=True`, but found X: {X}")
+            shape = X[0].shape
+            X = self._flatten_mesh(X, term=term)
+        compute_quantiles = (width is not None) or (quantiles is not None)
+        data = self._prepare_data(X, fitting=False)
+        self._check_predict_X(data)
+        eng = self._get_engine(data)
+        lp, var = eng.interval_pass(DeviceData(data.Xt), self.coef_, self.statistics_["cov"] if compute_quantiles else None,
+                                    self._term_index(term))
+        pdep = lp.cpu().numpy()
+        out = [pdep]
+        if compute_quantiles:
+            out.append(self._get_quantiles(X, width=width, quantiles=quantiles, term=term, xform=False,
+                                           lp_var=(pdep, var.cpu().numpy())))
+        if meshgrid:
+            for i, array in enumerate(out):
+                shp = shape + (array.shape[-1],) if array.ndim > 1 else shape
+                out[i] = np.reshape(array, shp)
+        if compute_quantiles:
+            return out
+        return out[0]
+
     def _P(self):
         return self.terms.build_penalties()
 
@@ -711,6 +846,12 @@ class LinearGAM(GAM):
         if isinstance(self.distribution, str):
             self.distribution = Distribution("normal", scale=self.scale)
         super()._validate_params()
+
+    def prediction_intervals(self, X, width=0.95, quantiles=None):
+        """pygam.py:2477-2506"""
+        if not self._is_fitted:
+            raise AttributeError("GAM has not been fitted. Call fit first.")
+        return self._get_quantiles(X, width, quantiles, prediction=True)
 
 
 class LogisticGAM(GAM):

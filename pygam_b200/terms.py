@@ -212,9 +212,12 @@ class LinearTerm(Term):
     def n_coefs(self):
         return 1
 
-    def compile(self, X, verbose=False):
+    def compile(self, X, col_minmax=None, verbose=False):
+        """terms.py:668-691: the column range is kept for generate_X_grid (pygam.py:1497-1500)"""
         if self.feature >= X.shape[1]:
             raise ValueError(f"term requires feature {self.feature}, but X has only {X.shape[1]} dimensions")
+        if col_minmax is not None or hasattr(X, "__getitem__"):
+            self.edge_knots_ = _edge_knots(X, self.feature, self.dtype, col_minmax)
         return self
 
 
@@ -574,7 +577,7 @@ class TermList:
             if isinstance(t, FactorTerm):
                 t.compile(X, col_minmax=col_minmax,
                           n_levels=None if n_levels is None else n_levels.get(t.feature), verbose=verbose)
-            elif isinstance(t, (SplineTerm, TensorTerm)):
+            elif isinstance(t, (SplineTerm, TensorTerm, LinearTerm)):
                 t.compile(X, col_minmax=col_minmax, verbose=verbose)
             else:
                 t.compile(X, verbose=verbose)

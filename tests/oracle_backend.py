@@ -100,6 +100,7 @@ class OracleEngine:
     def __init__(self, terms, dist_name, link_name, levels, expectile, n_features, device):
         self.m = terms.n_coefs
         self.oterms = oracle_terms(terms)
+        self.term_coefs = [t.n_coefs for t in terms]
         self.fam = dict(dist=dist_name, link=link_name, levels=levels, expectile=expectile, scale=None)
         self.V, self.tau = householder(terms.null_vectors())
         m = self.m
@@ -215,6 +216,22 @@ class OracleEngine:
 
     def model_matrix(self, data):
         return torch.from_numpy(self._modelmat(data).toarray())
+
+    def interval_pass(self, data, coef, cov=None, term=-1):
+        """numpy restatement of GAM._get_quantiles' n-sized part (pygam.py:1399-1404)"""
+        B = self._modelmat(data).toarray()
+        if term >= 0:
+            start = sum(self.term_coefs[:term])
+            idx = np.arange(start, start + self.term_coefs[term])
+        else:
+            idx = np.arange(self.m)
+        Bt = B[:, idx]
+        lp = Bt.dot(np.asarray(coef)[idx])
+        var = None
+        if cov is not None:
+            c = np.asarray(cov)[idx][:, idx]
+            var = torch.from_numpy((Bt.dot(c) * Bt).sum(axis=1))
+        return torch.from_numpy(lp), var
 
 
 class OracleBackend:
