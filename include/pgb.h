@@ -78,6 +78,8 @@ typedef struct pgb_model_info {
   int32_t gram_ctas;    /* CTAs launched by the Gram pass                       */
   int64_t gram_ws_bytes;/* workspace pgb_gram_pass needs                        */
   int64_t pass_ws_bytes;/* workspace pgb_stats_pass needs                       */
+  int32_t cell_roles;   /* > 0: the Gram pass runs cell-owned (all-spline model), this many roles */
+  int32_t cell_tile_rows;/* rows per shared-memory tile of the cell-owned Gram pass */
 } pgb_model_info;
 
 const char* pgb_last_error(void);

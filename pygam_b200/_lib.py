@@ -54,6 +54,8 @@ class PgbModelInfo(C.Structure):
         ("gram_ctas", C.c_int32),
         ("gram_ws_bytes", C.c_int64),
         ("pass_ws_bytes", C.c_int64),
+        ("cell_roles", C.c_int32),
+        ("cell_tile_rows", C.c_int32),
     ]
 
 

@@ -1,0 +1,649 @@
+// pgb_cells.cu -- the Gram pass of models made of plain cubic s() terms (+ intercept): cell-owned
+// register accumulation.
+//
+// Same result as the general path of pgb_gram.cu (G = X^T W^2 X, r = X^T W^2 z; the reference's
+// W.B and pseudo data, pygam.py:764-783, before its QR), different decomposition.  For a pair of
+// spline terms (i, j) a data row lands in exactly one CELL = (knot interval of x_i, knot interval
+// of x_j) and adds the 4 x 4 outer product of its non-zero basis values to the 16 entries of G
+// that belong to the cell.  The general path scatters those products into shared memory (16 B of
+// read-modify-write per fp64 FMA: 7.7 FMA/clk/SM).  Here a THREAD OWNS A CELL for the whole
+// kernel: the rows of a tile are counting-sorted by cell in shared memory, every thread walks the
+// rows of its own cell, re-evaluates the two bases from x in registers and accumulates its 16
+// sums in registers -- no accumulator traffic at all; the bound is the fp64 pipe.
+//
+//   kernel 1  gram_prepass_kernel   per row: lp -> mu -> W -> mask -> z (pygam.py:764-777), writes
+//                                    omega = W^2 and omega * z (16 B per row) + the log scalars
+//   kernel 2  gram_cells_kernel     one ROLE per CTA at a time: a pair (i, j), i < j (16 sums per
+//                                    cell), or a term's diagonal block (cells = interval x a hash
+//                                    split of the rows; 10 sums + the intercept column + the rhs)
+//   kernel 3  cells_slot_reduce     sums the CTA partials of every role in a fixed order
+//   kernel 4  cells_assemble        gathers [G | r] from the cell sums (every entry of G collects
+//                                    the <= 16 (cell, product) combinations that touch it)
+//
+// Scheduling: rows are cut into BANDS that fit the L2; inside a band the (role, tile) units are
+// dealt role-major to the CTAs in equal shares, so all CTAs work on the same band at the same time
+// (the columns come from HBM once per band, the other roles hit the L2) and a CTA serves the same
+// one or two roles in every band (its register accumulators are parked in its partial slot when
+// it switches).
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <algorithm>
+
+#include "pgb_internal.h"
+#include "pgb_kernels.cuh"
+
+static const int kCellThreads = 512;      // threads of a cells CTA = cells a role owns
+static const int kCellAcc = 18;           // sums per cell (16 for a pair; 10 + 4 + 4 for a diagonal role)
+static const int kPreThreads = 256;
+static const int64_t kBandBytes = 32ll << 20;  // column bytes of a band of rows (stays in the L2)
+
+static const int kCellWarps = kCellThreads / 32;
+// tile: x_i, x_j (or omega z), omega; 16-bit cell key and sorted row index per row; 16-bit counters per (warp, cell)
+static size_t cells_smem(int tile) { return (size_t)tile * (24 + 4) + (size_t)kCellWarps * kCellThreads * 2 + 64; }
+
+// ----------------------------------------------------------------------------------------
+// plan
+// ----------------------------------------------------------------------------------------
+int pgb_plan_cells(pgb_model* M) {
+  pgb_model::Cells& C = M->cells;
+  C = pgb_model::Cells();
+  if (const char* e = getenv("PGB_GRAM_CELLS"))
+    if (atoi(e) == 0) return PGB_OK;
+  const int nt = M->n_terms;
+  int n_spl = 0, icpt = -1;
+  for (int j = 0; j < nt; ++j) {
+    const DTerm& t = M->dterms[j];
+    if (t.kind == PGB_TERM_INTERCEPT) {
+      if (icpt >= 0) return PGB_OK;
+      icpt = j;
+    } else if (t.fast && t.marg[0].nint >= 1 && t.marg[0].nint <= 4096) {
+      ++n_spl;
+    } else {
+      return PGB_OK;  // some other term: the general path
+    }
+  }
+  if (n_spl < 1) return PGB_OK;
+  C.icpt_coef = icpt >= 0 ? M->dterms[icpt].coef_offset : -1;
+  int64_t sum_off = 0;
+  int64_t n_sub = 0;
+  for (int i = 0; i < nt; ++i) {
+    const DTerm& ti = M->dterms[i];
+    if (!ti.fast) continue;
+    for (int j = i; j < nt; ++j) {
+      const DTerm& tj = M->dterms[j];
+      if (!tj.fast) continue;
+      DCellPair P{};
+      P.ti = i;
+      P.tj = (j == i) ? -1 : j;
+      P.off_i = ti.coef_offset;
+      P.off_j = tj.coef_offset;
+      P.nint_i = ti.marg[0].nint;
+      // diagonal role: the rows of an interval are spread over `ncb` cells by row index, for balance
+      P.ncb = (j == i) ? std::max(1, std::min(32, kCellThreads / P.nint_i)) : tj.marg[0].nint;
+      P.ncells = P.nint_i * P.ncb;
+      P.sum_off = sum_off;
+      sum_off += (int64_t)kCellAcc * P.ncells;
+      const int pair = (int)C.pairs.size();
+      C.pairs.push_back(P);
+      for (int k0 = 0; k0 < P.ncells; k0 += kCellThreads) {
+        DCellRole R{};
+        R.a = ti.marg[0];
+        R.b = tj.marg[0];
+        R.diag = (j == i) ? 1 : 0;
+        R.ncb = P.ncb;
+        R.key0 = k0;
+        R.ncell = std::min(kCellThreads, P.ncells - k0);
+        R.pair = pair;
+        C.roles.push_back(R);
+        ++n_sub;
+      }
+    }
+  }
+  // a pair split over many roles re-reads its rows once per role: leave very fine bases to the general path
+  if (n_sub > 4 * (int64_t)C.pairs.size() || C.roles.size() > 4096) {
+    C = pgb_model::Cells();
+    return PGB_OK;
+  }
+  C.sum_doubles = sum_off;
+  C.grid = kSMs;
+  C.tile_rows = 7680;
+  if (const char* e = getenv("PGB_CELLS_TILE")) C.tile_rows = std::max(64, atoi(e) & ~1);
+  while (cells_smem(C.tile_rows) + 1024 > kSmemMax) C.tile_rows -= 64;  // 1 KB for the kernel's static shared memory
+  C.smem = cells_smem(C.tile_rows);
+  C.slots_per_cta = ((int)C.roles.size() + C.grid - 1) / C.grid + 1;
+  C.slot_doubles = (int64_t)kCellAcc * kCellThreads;
+  {
+    // CTA c serves roles inside [floor(R c / grid), ceil(R (c + 1) / grid) - 1] in every band
+    const int64_t nr = (int64_t)C.roles.size();
+    for (int r = 0; r < (int)nr; ++r) {
+      int lo = C.grid, hi = -1;
+      for (int c = 0; c < C.grid; ++c) {
+        const int64_t a = nr * c / C.grid, b = (nr * (c + 1) + C.grid - 1) / C.grid - 1;
+        if (r >= a && r <= b) { lo = std::min(lo, c); hi = std::max(hi, c); }
+      }
+      C.roles[r].c_lo = lo;
+      C.roles[r].c_hi = hi;
+    }
+  }
+  // coefficient -> (term, local index) for the assembly
+  C.coef_term.assign(M->m, -1);
+  for (int j = 0; j < nt; ++j)
+    for (int q = 0; q < M->dterms[j].n_coefs; ++q) C.coef_term[M->dterms[j].coef_offset + q] = j;
+  // (term i, term j) -> pair
+  C.pair_of.assign((size_t)nt * nt, -1);
+  for (size_t p = 0; p < C.pairs.size(); ++p) {
+    const DCellPair& P = C.pairs[p];
+    C.pair_of[(size_t)P.ti * nt + (P.tj < 0 ? P.ti : P.tj)] = (int)p;
+  }
+  C.enabled = true;
+  return PGB_OK;
+}
+
+int pgb_cells_upload(pgb_model* M) {
+  pgb_model::Cells& C = M->cells;
+  if (!C.enabled) return PGB_OK;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void** dptr, const void* src, size_t bytes) {
+    if (e != cudaSuccess) return;
+    e = cudaMalloc(dptr, std::max<size_t>(bytes, 16));
+    if (e == cudaSuccess && bytes) e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+  };
+  up((void**)&C.d_roles, C.roles.data(), C.roles.size() * sizeof(DCellRole));
+  up((void**)&C.d_pairs, C.pairs.data(), C.pairs.size() * sizeof(DCellPair));
+  up((void**)&C.d_coef_term, C.coef_term.data(), C.coef_term.size() * sizeof(int32_t));
+  up((void**)&C.d_pair_of, C.pair_of.data(), C.pair_of.size() * sizeof(int32_t));
+  if (e != cudaSuccess) return pgb_cuda_fail(e, "pgb_cells_upload");
+  return PGB_OK;
+}
+
+void pgb_cells_release(pgb_model* M) {
+  pgb_model::Cells& C = M->cells;
+  cudaFree(C.d_roles);
+  cudaFree(C.d_pairs);
+  cudaFree(C.d_coef_term);
+  cudaFree(C.d_pair_of);
+  C.d_roles = nullptr; C.d_pairs = nullptr; C.d_coef_term = nullptr; C.d_pair_of = nullptr;
+}
+
+// host-only self check: every entry of the upper triangle of [G | r] must be assembled from at
+// least one (pair, product, cell) combination, and every combination of every pair must be used by
+// exactly one entry; returns the number of violations
+int pgb_cells_coverage_errors(const pgb_model* M) {
+  const pgb_model::Cells& C = M->cells;
+  if (!C.enabled) return 0;
+  const int m = M->m, nt = M->n_terms;
+  int errors = 0;
+  std::vector<int> used((size_t)C.sum_doubles, 0);
+  for (int r = 0; r < m; ++r)
+    for (int c = r; c <= m; ++c) {
+      const int tr = C.coef_term[r], tc = (c < m) ? C.coef_term[c] : -2;
+      int hits = 0;
+      if (r == C.icpt_coef && (c == m || c == C.icpt_coef)) { ++hits; }  // from the prepass sums
+      else if (c == m || c == C.icpt_coef || r == C.icpt_coef) {
+        const int ts = (r == C.icpt_coef) ? tc : tr;
+        const int p = ((r == C.icpt_coef) ? c : r) - M->dterms[ts].coef_offset;
+        const DCellPair& P = C.pairs[C.pair_of[(size_t)ts * nt + ts]];
+        for (int a = 0; a < 4; ++a) {
+          const int ci = p - a;
+          if (ci < 0 || ci >= P.nint_i) continue;
+          for (int h = 0; h < P.ncb; ++h) { ++used[P.sum_off + (int64_t)((c == m ? 14 : 10) + a) * P.ncells + ci * P.ncb + h]; ++hits; }
+        }
+      } else if (tr == tc) {
+        const DCellPair& P = C.pairs[C.pair_of[(size_t)tr * nt + tr]];
+        const int p = r - P.off_i, d = c - r;
+        if (d > 3) { continue; }
+        for (int a = 0; a + d < 4; ++a) {
+          const int ci = p - a;
+          if (ci < 0 || ci >= P.nint_i) continue;
+          const int e = a * 4 - a * (a - 1) / 2 + d;  // (a, a + d) of the packed upper triangle
+          for (int h = 0; h < P.ncb; ++h) { ++used[P.sum_off + (int64_t)e * P.ncells + ci * P.ncb + h]; ++hits; }
+        }
+      } else {
+        const int ta = std::min(tr, tc), tb = std::max(tr, tc);
+        const DCellPair& P = C.pairs[C.pair_of[(size_t)ta * nt + tb]];
+        const int p = ((tr == ta) ? r : c) - P.off_i, q = ((tr == ta) ? c : r) - P.off_j;
+        for (int a = 0; a < 4; ++a)
+          for (int b = 0; b < 4; ++b) {
+            const int ci = p - a, cj = q - b;
+            if (ci < 0 || ci >= P.nint_i || cj < 0 || cj >= P.ncb) continue;
+            ++used[P.sum_off + (int64_t)(4 * a + b) * P.ncells + ci * P.ncb + cj];
+            ++hits;
+          }
+      }
+      if (hits < 1) ++errors;
+    }
+  for (const DCellPair& P : C.pairs) {
+    const int n_acc = (P.tj < 0) ? 18 : 16;
+    for (int e = 0; e < n_acc; ++e)
+      for (int k = 0; k < P.ncells; ++k) {
+        // without an intercept the diagonal role's intercept-column sums stay unused
+        const int want = (P.tj < 0 && e >= 10 && e < 14 && C.icpt_coef < 0) ? 0 : 1;
+        if (used[P.sum_off + (int64_t)e * P.ncells + k] != want) ++errors;
+      }
+  }
+  // every cell of every pair belongs to exactly one role
+  for (size_t p = 0; p < C.pairs.size(); ++p) {
+    int covered = 0;
+    for (const DCellRole& R : C.roles)
+      if (R.pair == (int)p) covered += R.ncell;
+    if (covered != C.pairs[p].ncells) ++errors;
+  }
+  return errors;
+}
+
+extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n) {
+  const pgb_model::Cells& C = M->cells;
+  const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
+  return (slots * C.slot_doubles + C.sum_doubles + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2) + 8 + 2 * (n + 2)) * 8 + 1024;
+}
+
+// ----------------------------------------------------------------------------------------
+// kernel 1: the elementwise IRLS step of every row (or the response of _initial_estimate)
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPreThreads, 4)
+gram_prepass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Family fam, int mode,
+                    const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
+                    const float* __restrict__ w, const double* __restrict__ beta, double* __restrict__ om,
+                    double* __restrict__ omz, double* __restrict__ scal_part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  double* s_beta = reinterpret_cast<double*>(smem_raw);
+  double* s_red = s_beta + ((m + 1) & ~1);
+  DTerm* s_terms = reinterpret_cast<DTerm*>(s_red + (PGB_GS_COUNT + 2) * 32);
+  for (int i = tid; i < m; i += blockDim.x) s_beta[i] = (mode == PGB_MODE_IRLS) ? beta[i] : 0.0;
+  load_terms_smem(s_terms, g_terms, n_terms);
+  __syncthreads();
+  double sc[PGB_GS_COUNT + 2];
+#pragma unroll
+  for (int s = 0; s < PGB_GS_COUNT + 2; ++s) sc[s] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double yi = __ldg(y + i);
+    double o, oz;
+    if (mode == PGB_MODE_IRLS) {
+      EmitLp e{s_beta, 0.0};
+      for (int q = 0; q < n_terms; ++q) eval_term(s_terms[q], X, ld, i, e);
+      const IrlsRow ir = irls_row(fam, e.lp, yi, weight_inv(w, i));
+      o = ir.omega;
+      oz = ir.omega * ir.z;
+      if (ir.keep) {
+        sc[PGB_GS_NUSED] += 1.0;
+        sc[PGB_GS_DEV] += dist_dev(fam, yi, ir.mu);
+        sc[PGB_GS_NCORRECT] += (yi == ((ir.mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
+      }
+    } else {
+      o = 1.0;
+      oz = init_response(fam, yi);
+      sc[PGB_GS_NUSED] += 1.0;
+      if (!isfinite(oz)) sc[PGB_GS_NONFINITE] += 1.0;
+    }
+    sc[PGB_GS_NROWS] += 1.0;
+    sc[PGB_GS_COUNT] += o;       // G[intercept, intercept]
+    sc[PGB_GS_COUNT + 1] += oz;  // r[intercept]
+    om[i] = o;
+    omz[i] = oz;
+  }
+  block_reduce_store<PGB_GS_COUNT + 2>(sc, s_red, scal_part + (int64_t)blockIdx.x * (PGB_GS_COUNT + 2));
+}
+
+// ----------------------------------------------------------------------------------------
+// kernel 2: cells
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ int cell_of(const DMarg& mg, double x) {
+  const double u = (x - mg.lo) * mg.inv_span;
+  const double s = u * (double)mg.nint;
+  return min(max((int)s, 0), mg.nint - 1);  // eval_marg's interval, clamped like its extrapolation branch
+}
+
+// basis values of a row in the cell `cell_d` it was sorted into: the straight-line cubic of
+// eval_term inside the edge knots, eval_marg's linear extrapolation outside
+__device__ __forceinline__ void cell_basis(const DMarg& mg, double lo, double inv_span, double nint_d, double cell_d, double x,
+                                           double& b0, double& b1, double& b2, double& b3) {
+  const double u = (x - lo) * inv_span;
+  if (u >= 0.0 && u <= 1.0) {
+    cubic_bspline(u * nint_d - cell_d, b0, b1, b2, b3);
+  } else {
+    double v[PGB_MAXV];
+    eval_marg(mg, x, v);
+    b0 = v[0]; b1 = v[1]; b2 = v[2]; b3 = v[3];
+  }
+}
+
+__global__ void __launch_bounds__(kCellThreads, 1)
+gram_cells_kernel(const double* __restrict__ X, int64_t ld, int64_t n, const double* __restrict__ om,
+                  const double* __restrict__ omz, const DCellRole* __restrict__ roles, int n_roles, int TR,
+                  int band_tiles, int slots_per_cta, double* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ DCellRole R;
+  __shared__ int s_wtot[32];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* xa = reinterpret_cast<double*>(smem_raw);
+  double* xb = xa + TR;
+  double* wv = xb + TR;
+  uint16_t* key = reinterpret_cast<uint16_t*>(wv + TR);
+  uint16_t* perm = key + TR;
+  uint32_t* wh32 = reinterpret_cast<uint32_t*>(perm + TR);  // [warp][cell / 2]
+  uint16_t* wh16 = reinterpret_cast<uint16_t*>(wh32);       // [warp][cell]
+  const uint32_t bar = smem_addr(&s_bar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  const int64_t ntiles = (n + TR - 1) / TR;
+  const int64_t nbands = (ntiles + band_tiles - 1) / band_tiles;
+  const int role_lo = (int)((int64_t)n_roles * blockIdx.x / gridDim.x);  // first role this CTA can ever serve
+  double* my_part = part + (int64_t)blockIdx.x * slots_per_cta * (kCellAcc * kCellThreads);
+  int cur_role = -1;
+  uint32_t phase = 0;
+  double acc[kCellAcc];
+#pragma unroll
+  for (int e = 0; e < kCellAcc; ++e) acc[e] = 0.0;
+  for (int64_t band = 0; band < nbands; ++band) {
+    const int64_t t0 = band * band_tiles;
+    const int64_t nb = min((int64_t)band_tiles, ntiles - t0);
+    const int64_t U = nb * n_roles;
+    const int64_t u_lo = U * blockIdx.x / gridDim.x, u_hi = U * (blockIdx.x + 1) / gridDim.x;
+    // odd bands walk their units backwards: the band starts with the role the previous one ended with
+    for (int64_t uu = 0; uu < u_hi - u_lo; ++uu) {
+      const int64_t u = (band & 1) ? (u_hi - 1 - uu) : (u_lo + uu);
+      const int role = (int)(u / nb);
+      const int64_t tile = t0 + (u - (int64_t)role * nb);
+      if (role != cur_role) {
+        // park the sums of the role we leave in its slot, fetch the sums of the one we enter
+        if (cur_role >= 0) {
+          double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * kCellThreads);
+#pragma unroll
+          for (int e = 0; e < kCellAcc; ++e) dst[e * kCellThreads + tid] = acc[e];
+        }
+        const double* src = my_part + (int64_t)(role - role_lo) * (kCellAcc * kCellThreads);
+#pragma unroll
+        for (int e = 0; e < kCellAcc; ++e) acc[e] = src[e * kCellThreads + tid];
+        __syncthreads();
+        if (tid == 0) R = roles[role];
+        __syncthreads();
+        cur_role = role;
+      }
+      const int NC = R.ncell, diag = R.diag, ncb = R.ncb, key0 = R.key0;
+      const int64_t row0 = tile * TR;
+      const int cnt = (int)min((int64_t)TR, n - row0);
+      const double* ca = X + (int64_t)R.a.feature * ld + row0;
+      const double* cb = diag ? omz + row0 : X + (int64_t)R.b.feature * ld + row0;
+      const double* cw = om + row0;
+      const bool bulk = (cnt == TR) && ((((uintptr_t)ca | (uintptr_t)cb | (uintptr_t)cw) & 15) == 0);
+      if (bulk) {
+        if (tid == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads vs the async writes
+          mbar_expect_tx(bar, 3u * (uint32_t)TR * 8u);
+          bulk_g2s(smem_addr(xa), ca, (uint32_t)TR * 8u, bar);
+          bulk_g2s(smem_addr(xb), cb, (uint32_t)TR * 8u, bar);
+          bulk_g2s(smem_addr(wv), cw, (uint32_t)TR * 8u, bar);
+        }
+      } else {
+        for (int r = tid; r < cnt; r += kCellThreads) {
+          xa[r] = ca[r];
+          xb[r] = cb[r];
+          wv[r] = cw[r];
+        }
+      }
+      for (int i = tid; i < kCellWarps * (kCellThreads / 2); i += kCellThreads) wh32[i] = 0u;
+      __syncthreads();
+      if (bulk) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+      }
+      // ---- counting sort of the tile's rows by cell, stable per warp.  Counters are private to a
+      //      (warp, cell): 16 bits each, two per word, bumped with one shared-memory atomic on the word
+      //      (a warp's conflicting lanes are resolved by the hardware in a fixed order, and no other warp
+      //      touches the word: the sorted order, hence the fp64 sums, are reproducible run to run).
+      //      Rows of other roles of the same pair get key 0xffff.
+      uint32_t* my_wh = wh32 + warp * (kCellThreads / 2);
+      for (int r = tid; r < cnt; r += kCellThreads) {
+        const int ci = cell_of(R.a, xa[r]);
+        const int k = (diag ? ci * ncb + (r % ncb) : ci * ncb + cell_of(R.b, xb[r])) - key0;
+        const bool mine = (unsigned)k < (unsigned)NC;
+        key[r] = mine ? (uint16_t)k : (uint16_t)0xffff;
+        if (mine) atomicAdd(&my_wh[k >> 1], (k & 1) ? 0x10000u : 1u);
+      }
+      __syncthreads();
+      // ---- thread k owns cell k: its rows per warp, exclusive scan over the cells, start offsets back
+      int c = 0;
+#pragma unroll
+      for (int q = 0; q < kCellWarps; ++q) c += wh16[q * kCellThreads + tid];
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) s_wtot[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        const int t = lane < kCellWarps ? s_wtot[lane] : 0;
+        int ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, ti, o);
+          if (lane >= o) ti += v;
+        }
+        s_wtot[lane] = ti - t;
+      }
+      __syncthreads();
+      const int start = incl - c + s_wtot[warp];
+      {
+        int run = start;
+#pragma unroll
+        for (int q = 0; q < kCellWarps; ++q) {
+          const int cq = wh16[q * kCellThreads + tid];
+          wh16[q * kCellThreads + tid] = (uint16_t)run;
+          run += cq;
+        }
+      }
+      __syncthreads();
+      for (int r = tid; r < cnt; r += kCellThreads) {
+        const int k = key[r];
+        if (k != 0xffff) {
+          const uint32_t old = atomicAdd(&my_wh[k >> 1], (k & 1) ? 0x10000u : 1u);
+          perm[(k & 1) ? (old >> 16) : (old & 0xffffu)] = (uint16_t)r;
+        }
+      }
+      __syncthreads();
+      if (!diag) {
+        const int kk = key0 + tid;
+        const double cid = (double)(kk / ncb), cjd = (double)(kk % ncb);
+        const double loa = R.a.lo, isa = R.a.inv_span, na = (double)R.a.nint;
+        const double lob = R.b.lo, isb = R.b.inv_span, nb2 = (double)R.b.nint;
+        for (int s = 0; s < c; ++s) {
+          const int r = perm[start + s];
+          const double ww = wv[r];
+          double a0, a1, a2, a3, b0, b1, b2, b3;
+          cell_basis(R.a, loa, isa, na, cid, xa[r], a0, a1, a2, a3);
+          cell_basis(R.b, lob, isb, nb2, cjd, xb[r], b0, b1, b2, b3);
+          a0 *= ww; a1 *= ww; a2 *= ww; a3 *= ww;
+          acc[0] = fma(a0, b0, acc[0]); acc[1] = fma(a0, b1, acc[1]); acc[2] = fma(a0, b2, acc[2]); acc[3] = fma(a0, b3, acc[3]);
+          acc[4] = fma(a1, b0, acc[4]); acc[5] = fma(a1, b1, acc[5]); acc[6] = fma(a1, b2, acc[6]); acc[7] = fma(a1, b3, acc[7]);
+          acc[8] = fma(a2, b0, acc[8]); acc[9] = fma(a2, b1, acc[9]); acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
+          acc[12] = fma(a3, b0, acc[12]); acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
+        }
+      } else {
+        const double cid = (double)((key0 + tid) / ncb);
+        const double loa = R.a.lo, isa = R.a.inv_span, na = (double)R.a.nint;
+        for (int s = 0; s < c; ++s) {
+          const int r = perm[start + s];
+          const double ww = wv[r], wz = xb[r];
+          double a0, a1, a2, a3;
+          cell_basis(R.a, loa, isa, na, cid, xa[r], a0, a1, a2, a3);
+          const double v0 = a0 * ww, v1 = a1 * ww, v2 = a2 * ww, v3 = a3 * ww;
+          acc[0] = fma(v0, a0, acc[0]); acc[1] = fma(v0, a1, acc[1]); acc[2] = fma(v0, a2, acc[2]); acc[3] = fma(v0, a3, acc[3]);
+          acc[4] = fma(v1, a1, acc[4]); acc[5] = fma(v1, a2, acc[5]); acc[6] = fma(v1, a3, acc[6]);
+          acc[7] = fma(v2, a2, acc[7]); acc[8] = fma(v2, a3, acc[8]); acc[9] = fma(v3, a3, acc[9]);
+          acc[10] += v0; acc[11] += v1; acc[12] += v2; acc[13] += v3;
+          acc[14] = fma(a0, wz, acc[14]); acc[15] = fma(a1, wz, acc[15]); acc[16] = fma(a2, wz, acc[16]); acc[17] = fma(a3, wz, acc[17]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (cur_role >= 0) {
+    double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * kCellThreads);
+#pragma unroll
+    for (int e = 0; e < kCellAcc; ++e) dst[e * kCellThreads + tid] = acc[e];
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// kernel 3: sums[pair][product][cell] = sum over the CTAs that served the cell's role, fixed order
+// ----------------------------------------------------------------------------------------
+__global__ void cells_slot_reduce_kernel(const double* __restrict__ part, const DCellRole* __restrict__ roles,
+                                         const DCellPair* __restrict__ pairs, int n_roles, int grid, int slots_per_cta,
+                                         double* __restrict__ sums) {
+  const int role = blockIdx.x, k = threadIdx.x;
+  const DCellRole R = roles[role];
+  if (k >= R.ncell) return;
+  const DCellPair P = pairs[R.pair];
+  const int64_t nr = n_roles;
+  const int c_lo = R.c_lo, c_hi = R.c_hi;
+  for (int e = 0; e < kCellAcc; ++e) {
+    double v = 0.0;
+    for (int c = c_lo; c <= c_hi; ++c) {
+      const int lo = (int)(nr * c / grid);
+      const int hi = (int)((nr * (c + 1) + grid - 1) / grid) - 1;
+      if (role < lo || role > hi || role - lo >= slots_per_cta) continue;
+      v += part[((int64_t)c * slots_per_cta + (role - lo)) * (kCellAcc * kCellThreads) + e * kCellThreads + k];
+    }
+    sums[P.sum_off + (int64_t)e * P.ncells + R.key0 + k] = v;
+  }
+}
+
+// scalars of the prepass: the public ones into out, sum(omega) and sum(omega z) for the assembly
+__global__ void cells_scalar_reduce_kernel(const double* __restrict__ scal_part, int count, double* __restrict__ out_scal,
+                                           double* __restrict__ extra, int accumulate) {
+  const int s = threadIdx.x;
+  if (s >= PGB_GS_COUNT + 2) return;
+  double v = 0.0;
+  for (int c = 0; c < count; ++c) v += scal_part[(int64_t)c * (PGB_GS_COUNT + 2) + s];
+  if (s < PGB_GS_COUNT) out_scal[s] = accumulate ? out_scal[s] + v : v;
+  else extra[s - PGB_GS_COUNT] = v;
+}
+
+// ----------------------------------------------------------------------------------------
+// kernel 4: [G | r] from the cell sums.  One thread per entry (row <= col) of the upper triangle.
+// ----------------------------------------------------------------------------------------
+__global__ void cells_assemble_kernel(const double* __restrict__ sums, const double* __restrict__ extra,
+                                      const DCellPair* __restrict__ pairs, const int32_t* __restrict__ coef_term,
+                                      const int32_t* __restrict__ pair_of, int n_terms, int m, int icpt,
+                                      double* __restrict__ out, int accumulate) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)m * (m + 1)) return;
+  const int r = (int)(idx / (m + 1)), c = (int)(idx - (int64_t)r * (m + 1));
+  if (c < r) return;
+  double v = 0.0;
+  if (r == icpt && (c == m || c == icpt)) {
+    v = extra[c == m ? 1 : 0];
+  } else if (c == m || c == icpt || r == icpt) {
+    const int cs = (r == icpt) ? c : r;  // the spline coefficient
+    const int ts = coef_term[cs];
+    const DCellPair P = pairs[pair_of[(size_t)ts * n_terms + ts]];
+    const int p = cs - P.off_i;
+    const double* S = sums + P.sum_off + (int64_t)(c == m ? 14 : 10) * P.ncells;
+    for (int a = 0; a < 4; ++a) {
+      const int ci = p - a;
+      if (ci < 0 || ci >= P.nint_i) continue;
+      const double* q = S + (int64_t)a * P.ncells + ci * P.ncb;
+      for (int h = 0; h < P.ncb; ++h) v += q[h];
+    }
+  } else {
+    const int tr = coef_term[r], tc = coef_term[c];
+    if (tr == tc) {
+      const DCellPair P = pairs[pair_of[(size_t)tr * n_terms + tr]];
+      const int p = r - P.off_i, d = c - r;
+      if (d <= 3) {
+        for (int a = 0; a + d < 4; ++a) {
+          const int ci = p - a;
+          if (ci < 0 || ci >= P.nint_i) continue;
+          const int e = a * 4 - a * (a - 1) / 2 + d;
+          const double* q = sums + P.sum_off + (int64_t)e * P.ncells + ci * P.ncb;
+          for (int h = 0; h < P.ncb; ++h) v += q[h];
+        }
+      }
+    } else {
+      const int ta = min(tr, tc), tb = max(tr, tc);
+      const DCellPair P = pairs[pair_of[(size_t)ta * n_terms + tb]];
+      const int p = ((tr == ta) ? r : c) - P.off_i, q = ((tr == ta) ? c : r) - P.off_j;
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+          const int ci = p - a, cj = q - b;
+          if (ci < 0 || ci >= P.nint_i || cj < 0 || cj >= P.ncb) continue;
+          v += sums[P.sum_off + (int64_t)(4 * a + b) * P.ncells + ci * P.ncb + cj];
+        }
+    }
+  }
+  if (c == m) {
+    double* dst = out + (int64_t)m * m + r;
+    *dst = accumulate ? *dst + v : v;
+  } else {
+    double* a = out + (int64_t)r * m + c;
+    const double nv = accumulate ? *a + v : v;
+    *a = nv;
+    out[(int64_t)c * m + r] = nv;
+  }
+}
+
+int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int64_t n, int64_t ld, const double* y,
+                          const float* w, const double* beta, double* out, void* ws, int64_t ws_bytes, int accumulate,
+                          cudaStream_t st) {
+  const pgb_model::Cells& C = M->cells;
+  pgb_model* Mm = const_cast<pgb_model*>(M);
+  const int n_roles = (int)C.roles.size();
+  const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
+  double* part = (double*)ws;
+  double* sums = part + slots * C.slot_doubles;
+  double* scal_part = sums + C.sum_doubles;
+  double* extra = scal_part + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2);
+  double* om = extra + 8;
+  double* omz = om + ((n + 1) & ~(int64_t)1);
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    PGB_CUDA(cudaFuncSetAttribute(gram_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemMax - 1024)));
+    attr_set = true;
+  }
+  pgb_model::Timing& tm = Mm->timing;
+  if (tm.enabled) {
+    while ((int)tm.chunk_ev.size() < 5) {
+      cudaEvent_t e;
+      PGB_CUDA(cudaEventCreate(&e));
+      tm.chunk_ev.push_back(e);
+    }
+    PGB_CUDA(cudaEventRecord(tm.chunk_ev[0], st));
+    PGB_CUDA(cudaEventRecord(tm.chunk_ev[2], st));
+  }
+  const int grid1 = (int)std::min<int64_t>((n + kPreThreads - 1) / kPreThreads, (int64_t)kSMs * 8);
+  const size_t pre_smem = ((size_t)((M->m + 1) & ~1) * 8 + (PGB_GS_COUNT + 2) * 32 * 8 + (size_t)M->n_terms * sizeof(DTerm) + 127) & ~(size_t)127;
+  gram_prepass_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, X, n, ld, y, w, beta, om,
+                                                            omz, scal_part);
+  PGB_CUDA(cudaGetLastError());
+  PGB_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * slots * C.slot_doubles, st));
+  if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[3], st));
+  const int TR = C.tile_rows;
+  const int64_t row_bytes = 8 * (int64_t)M->n_features + 16;
+  int band_tiles = (int)std::max<int64_t>(1, kBandBytes / (row_bytes * TR));
+  if (const char* e = getenv("PGB_CELLS_BAND")) band_tiles = std::max(1, atoi(e));
+  gram_cells_kernel<<<C.grid, kCellThreads, C.smem, st>>>(X, ld, n, om, omz, C.d_roles, n_roles, TR, band_tiles, C.slots_per_cta,
+                                                           part);
+  PGB_CUDA(cudaGetLastError());
+  if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[4], st));
+  cells_slot_reduce_kernel<<<n_roles, kCellThreads, 0, st>>>(part, C.d_roles, C.d_pairs, n_roles, C.grid, C.slots_per_cta, sums);
+  cells_scalar_reduce_kernel<<<1, 32, 0, st>>>(scal_part, grid1, out + (int64_t)M->m * M->m + M->m, extra, accumulate);
+  const int64_t entries = (int64_t)M->m * (M->m + 1);
+  cells_assemble_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, st>>>(sums, extra, C.d_pairs, C.d_coef_term, C.d_pair_of,
+                                                                          M->n_terms, M->m, C.icpt_coef, out, accumulate);
+  PGB_CUDA(cudaGetLastError());
+  pgb_count_launch(5);
+  if (tm.enabled) {
+    PGB_CUDA(cudaEventRecord(tm.chunk_ev[1], st));
+    tm.pending = true;
+    tm.n_chunks = 1;
+  }
+  (void)ws_bytes;
+  return PGB_OK;
+}

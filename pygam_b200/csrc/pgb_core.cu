@@ -55,6 +55,10 @@ int pgb_plan_gram(pgb_model* M);      // pgb_gram.cu
 int pgb_plan_upload(pgb_model* M);    // pgb_gram.cu
 int pgb_plan_coverage_errors(const pgb_model* M);
 void pgb_gram_release(pgb_model* M);  // pgb_gram.cu
+int pgb_plan_cells(pgb_model* M);     // pgb_cells.cu
+int pgb_cells_upload(pgb_model* M);
+int pgb_cells_coverage_errors(const pgb_model* M);
+void pgb_cells_release(pgb_model* M);
 
 static int model_build_host(const pgb_term* terms, int32_t n_terms, int32_t n_features, int32_t dist,
                             int32_t link, double levels, double expectile, int32_t device, pgb_model** out) {
@@ -123,6 +127,7 @@ static int model_build_host(const pgb_term* terms, int32_t n_terms, int32_t n_fe
   M->k = slot;
   if (M->m > 65000) { pgb_set_error("too many coefficients (%d)", M->m); delete M; return PGB_EUNSUPPORTED; }
   int rc = pgb_plan_gram(M);
+  if (rc == PGB_OK) rc = pgb_plan_cells(M);
   if (rc != PGB_OK) { delete M; return rc; }
   *out = M;
   return PGB_OK;
@@ -140,9 +145,11 @@ extern "C" int pgb_model_create(const pgb_term* terms, int32_t n_terms, int32_t 
     e = cudaMemcpy(M->d_terms, M->dterms.data(), sizeof(DTerm) * n_terms, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) rc = pgb_cuda_fail(e, "pgb_model_create");
   if (rc == PGB_OK) rc = pgb_plan_upload(M);
+  if (rc == PGB_OK) rc = pgb_cells_upload(M);
   if (rc != PGB_OK) {
     cudaFree(M->d_terms);
     pgb_gram_release(M);
+    pgb_cells_release(M);
     delete M;
     return rc;
   }
@@ -159,7 +166,7 @@ extern "C" int pgb_model_plan_host(const pgb_term* terms, int32_t n_terms, int32
   int rc = model_build_host(terms, n_terms, n_features, PGB_DIST_NORMAL, PGB_LINK_IDENTITY, 1.0, -1.0, 0, &M);
   if (rc != PGB_OK) return rc;
   if (info) pgb_model_get_info(M, info);
-  if (coverage_errors) *coverage_errors = pgb_plan_coverage_errors(M);
+  if (coverage_errors) *coverage_errors = pgb_plan_coverage_errors(M) + pgb_cells_coverage_errors(M);
   if (getenv("PGB_DEBUG_PLAN")) {
     fprintf(stderr, "plan: m=%d k=%d groups=%zu blocks=%zu steps=%zu roles=%zu tile=%d threads=%d smem=%zu ctas=%d\n",
             M->m, M->k, M->groups.size(), M->blocks.size(), M->steps.size(), M->roles.size(), M->tile_rows,
@@ -175,6 +182,7 @@ extern "C" int pgb_model_plan_host(const pgb_term* terms, int32_t n_terms, int32
 extern "C" void pgb_model_destroy(pgb_model* M) {
   if (!M) return;
   pgb_gram_release(M);
+  pgb_cells_release(M);
   cudaFree(M->d_terms);
   delete M;
 }
@@ -193,6 +201,8 @@ extern "C" int pgb_model_get_info(const pgb_model* M, pgb_model_info* info) {
   info->gram_ctas = M->gram_ctas;
   info->gram_ws_bytes = pgb_gram_ws_bytes(M, 0);
   info->pass_ws_bytes = pgb_stats_ws_bytes(M);
+  info->cell_roles = M->cells.enabled ? (int32_t)M->cells.roles.size() : 0;
+  info->cell_tile_rows = M->cells.enabled ? M->cells.tile_rows : 0;
   return PGB_OK;
 }
 

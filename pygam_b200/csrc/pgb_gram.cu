@@ -537,8 +537,13 @@ static int64_t chunk_rows_for(const pgb_model* M, int64_t n) {
   const int64_t rows = (n + nch - 1) / nch;
   return ((rows + T - 1) / T) * T;
 }
+extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n);  // pgb_cells.cu
+int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int64_t n, int64_t ld, const double* y,
+                          const float* w, const double* beta, double* out, void* ws, int64_t ws_bytes, int accumulate,
+                          cudaStream_t st);
 extern "C" int64_t pgb_gram_ws_bytes(const pgb_model* M, int64_t n) {
   if (!M) return 0;
+  if (M->cells.enabled) return pgb_cells_ws_bytes(M, std::max<int64_t>(n, 1));
   const int64_t tiles = chunk_rows_for(M, std::max<int64_t>(n, 1)) / M->tile_rows;
   return (M->partial_doubles + (int64_t)M->rec_ctas * PGB_GS_COUNT) * 8 + tiles * rec_tile_bytes(M) + 1024;
 }
@@ -970,6 +975,7 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
                   (long long)pgb_gram_ws_bytes(M, n));
     return PGB_EINVAL;
   }
+  if (M->cells.enabled) return pgb_launch_gram_cells(M, mode, X, n, ld, y, w, beta, out, ws, ws_bytes, accumulate, st);
   const int n_roles = (int)M->roles.size();
   const int T = M->tile_rows, TP = tile_pitch(T);
   pgb_model* Mm = const_cast<pgb_model*>(M);

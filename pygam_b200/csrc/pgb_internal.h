@@ -90,7 +90,36 @@ struct DRole {
   int64_t map_off;             // offset of the role's element map
 };
 
+// ---- plan of the cell-owned Gram pass (pgb_cells.cu) -----------------------------------
+// A PAIR is a block G[spline term i, spline term j], i <= j; its CELLS are (interval of x_i, interval
+// of x_j) -- for a diagonal pair (interval of x_i, row index mod ncb).  A ROLE = up to 512 consecutive
+// cells of one pair: what the threads of one CTA own while they serve the role.
+struct DCellRole {
+  DMarg a, b;                       // marginals of the row term and of the column term (b = a on the diagonal)
+  int32_t diag, ncell, ncb, key0;   // cells key0 .. key0 + ncell - 1 of the pair; cell = ci * ncb + cj
+  int32_t pair, c_lo, c_hi, pad;    // CTAs c_lo .. c_hi can serve this role
+};
+struct DCellPair {
+  int32_t ti, tj;                   // terms; tj = -1: diagonal pair of ti
+  int32_t off_i, off_j;             // first coefficients
+  int32_t nint_i, ncb, ncells, pad;
+  int64_t sum_off;                  // sums[sum_off + product * ncells + cell]
+};
+
 struct pgb_model {
+  struct Cells {
+    bool enabled = false;
+    std::vector<DCellRole> roles;
+    std::vector<DCellPair> pairs;
+    std::vector<int32_t> coef_term, pair_of;
+    DCellRole* d_roles = nullptr;
+    DCellPair* d_pairs = nullptr;
+    int32_t* d_coef_term = nullptr;
+    int32_t* d_pair_of = nullptr;
+    int32_t tile_rows = 0, grid = 0, slots_per_cta = 0, icpt_coef = -1;
+    size_t smem = 0;
+    int64_t sum_doubles = 0, slot_doubles = 0;
+  } cells;
   std::vector<pgb_term> terms;
   std::vector<DTerm> dterms;
   std::vector<DGroup> groups;

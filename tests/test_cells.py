@@ -1,0 +1,141 @@
+"""The cell-owned Gram pass (pgb_cells.cu) of all-spline models: its host plan (CPU) and, on the
+GPU, agreement with the general shared-memory path of pgb_gram.cu and with the oracle on the same
+inputs, over the shapes that exercise its scheduling (odd n, several tiles and bands, role
+switches, key ranges, extrapolated rows, weights, no intercept)."""
+import contextlib
+import ctypes as C
+import io
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import helpers
+import pygam_b200 as pg
+from pygam_b200 import _lib
+from test_plan import plan_for
+
+
+def test_cell_plan_of_all_spline_models():
+    rng = np.random.default_rng(0)
+    _, info, errs = plan_for(cases.FIT_CASES["c2_logistic"], rng.random((50, 10)))
+    assert errs == 0
+    assert info.cell_roles == 55 and info.cell_tile_rows >= 1024  # 45 pairs + 10 diagonal blocks
+    # factor and tensor terms keep the general path
+    _, info1, e1 = plan_for(cases.FIT_CASES["c1_wage"], helpers.load("fit_c1_wage")["X"])
+    _, info3, e3 = plan_for(cases.FIT_CASES["c3_poisson"], rng.random((50, 24)))
+    assert (info1.cell_roles, e1, info3.cell_roles, e3) == (0, 0, 0, 0)
+
+
+@pytest.mark.parametrize("n_splines", [4, 5, 20, 60])
+def test_cell_plan_covers_every_entry(n_splines):
+    """key ranges: a pair with more than 512 cells is served by several roles"""
+    case = {"model": "LinearGAM", "terms": [dict(kind="s", feature=0, n_splines=n_splines),
+                                            dict(kind="s", feature=1, n_splines=max(4, n_splines // 2))]}
+    rng = np.random.default_rng(1)
+    _, info, errs = plan_for(case, rng.random((40, 2)))
+    assert errs == 0 and info.cell_roles >= 3
+
+
+# ---------------------------------------------------------------------------------------------
+gpu = pytest.mark.gpu
+
+
+def _engines(gam, n_features, env):
+    """two engines of the same compiled model: cell-owned Gram pass and the general path"""
+    from pygam_b200.engine import Engine
+
+    def make(cells):
+        old = {k: os.environ.get(k) for k in list(env) + ["PGB_GRAM_CELLS"]}
+        os.environ.update(env)
+        os.environ["PGB_GRAM_CELLS"] = "1" if cells else "0"
+        try:
+            return Engine(gam.terms, gam.distribution.name, gam.link.name, gam.distribution.levels, gam._expectile, n_features)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+    a, b = make(True), make(False)
+    assert a.info.cell_roles > 0 and b.info.cell_roles == 0
+    return a, b
+
+
+def _compare(gam, X, y, w=None, env=None, modes=(_lib.MODE_IRLS, _lib.MODE_INIT)):
+    import torch
+    from pygam_b200.engine import DeviceData
+
+    cells, general = _engines(gam, X.shape[1], env or {})
+    data = DeviceData.from_host(X, y, None if w is None else np.asarray(w, dtype=np.float32))
+    m = cells.m
+    rng = np.random.default_rng(3)
+    coef = np.asarray(gam.coef_) * (1 + 0.05 * rng.standard_normal(m))
+    for mode in modes:
+        a = cells.gram_pass(data, coef, mode=mode).cpu().numpy().copy()
+        b = general.gram_pass(data, coef, mode=mode).cpu().numpy().copy()
+        G, Gr = a[:m * m].reshape(m, m), b[:m * m].reshape(m, m)
+        scale = np.abs(Gr).max()
+        assert np.abs(G - Gr).max() <= 2e-13 * scale, (mode, np.abs(G - Gr).max() / scale)
+        np.testing.assert_array_equal(G, G.T)
+        assert np.abs(a[m * m:m * m + m] - b[m * m:m * m + m]).max() <= 2e-13 * max(scale, np.abs(b[m * m:m * m + m]).max())
+        sa, sb = a[m * m + m:], b[m * m + m:]
+        for s in (_lib.GS_NUSED, _lib.GS_NROWS, _lib.GS_NCORRECT):
+            assert sa[s] == sb[s]
+        assert abs(sa[_lib.GS_DEV] - sb[_lib.GS_DEV]) <= 1e-12 * max(1.0, abs(sb[_lib.GS_DEV]))
+        again = cells.gram_pass(data, coef, mode=mode).cpu().numpy()
+        assert np.array_equal(a, again), "the cell-owned pass must be bit-reproducible"
+    del torch
+
+
+def _fit_small(case, X, y, **kw):
+    gam = helpers.build_model(case, max_iter=3, **kw)
+    with contextlib.redirect_stdout(io.StringIO()):
+        gam.fit(X[:4000], y[:4000])
+    return gam
+
+
+@gpu
+@pytest.mark.parametrize("n,env", [(20001, {}), (30000, {"PGB_CELLS_TILE": "1024", "PGB_CELLS_BAND": "2"}),
+                                   (777, {}), (65536, {"PGB_CELLS_TILE": "2048", "PGB_CELLS_BAND": "1"})])
+def test_cells_equal_general_path_config2(n, env):
+    X, y = cases.data_c2(n, seed=11)
+    X[:4000] = np.clip(X[:4000], 0.0, 1.0)
+    X[0, :] = X.min(axis=0)  # the compiled edge knots (from the first 4000 rows) span all rows
+    X[1, :] = X.max(axis=0)
+    gam = _fit_small(cases.FIT_CASES["c2_logistic"], X, y)
+    _compare(gam, X, y, env=env)
+
+
+@gpu
+def test_cells_extrapolated_rows_weights_and_skewed_columns():
+    """rows outside the edge knots take eval_marg's linear extrapolation; normal columns make the
+    cell counts very uneven"""
+    rng = np.random.default_rng(5)
+    n = 25_001
+    X = rng.standard_normal((n, 3))
+    X[4000:] *= 1.7  # later rows reach beyond the knots compiled from the first 4000
+    eta = np.sin(X[:, 0]) + 0.3 * X[:, 1] ** 2 - 0.5 * np.cos(2 * X[:, 2])
+    y = rng.poisson(np.exp(0.3 * eta)).astype(float)
+    w = rng.uniform(0.5, 2.0, n)
+    case = {"model": "PoissonGAM", "terms": [dict(kind="s", feature=0, n_splines=12), dict(kind="s", feature=1),
+                                             dict(kind="s", feature=2, n_splines=31)]}
+    gam = _fit_small(case, X, y)
+    _compare(gam, X, y, w=w, env={"PGB_CELLS_TILE": "4096"})
+
+
+@gpu
+def test_cells_key_ranges_and_no_intercept():
+    rng = np.random.default_rng(6)
+    n = 40_000
+    X = rng.random((n, 2))
+    X[0], X[1] = 0.0, 1.0
+    y = np.sin(6 * X[:, 0]) + X[:, 1] + 0.1 * rng.standard_normal(n)
+    case = {"model": "LinearGAM", "terms": [dict(kind="s", feature=0, n_splines=60), dict(kind="s", feature=1, n_splines=33)]}
+    gam = _fit_small(case, X, y, fit_intercept=False)
+    assert gam.terms.n_coefs == 93
+    _compare(gam, X, y, modes=(_lib.MODE_IRLS,))
+    gam1 = _fit_small({"model": "GammaGAM", "terms": [dict(kind="s", feature=0, n_splines=9)]}, X, np.exp(y))
+    _compare(gam1, X, np.exp(y))

@@ -58,7 +58,9 @@ def main():
         rs.append(r.value)
         ts.append(t.value)
     g, r, t = float(np.median(ms[2:])), float(np.median(rs[2:])), float(np.median(ts[2:]))
-    print(f"{a.case} n={a.rows} m={eng.m} roles={eng.info.n_roles} tile={eng.info.tile_rows} ctas={eng.info.gram_ctas}: "
+    path = (f"cells roles={eng.info.cell_roles} tile={eng.info.cell_tile_rows}" if eng.info.cell_roles else
+            f"roles={eng.info.n_roles} tile={eng.info.tile_rows} ctas={eng.info.gram_ctas}")
+    print(f"{a.case} n={a.rows} m={eng.m} {path}: "
           f"records {r:.3f} ms | accum {g:.3f} ms | pass {t:.3f} ms = {a.rows / t / 1e3:.3e} Mrows/s")
     if a.only_gram:
         return
