@@ -275,20 +275,36 @@ def run_b200(args, rank, world, local_rank):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    gram_ms = gram_pass_ms  # records + accumulation + reductions of all row chunks
+    gram_ms = gram_pass_ms  # every kernel of the Gram pass (prepass/records, accumulation, reductions)
     achieved = n * BYTES_PER_ROW / (gram_ms * 1e-3) / 1e9
     fma_per_clk_sm = n * FMA_PER_ROW / (accum * 1e-3) / (148 * 1.965e9)
-    roofline = {"kernel": "gram_records_kernel + gram_accum_kernel (the Gram pass of one PIRLS iteration)", "bound": "hbm",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+    cells = eng.info.cell_roles > 0
+    traffic = None
+    try:  # dram bytes of the dominant kernel per launch from the committed ncu --set full capture, scaled to n rows
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_gram_cells_traffic.json")))
+        traffic = prof["dram_bytes_per_row"] * n
+    except Exception:
+        pass
+    if cells:
+        kernels = "gram_prepass_kernel + gram_cells_kernel (the Gram pass of one PIRLS iteration)"
+        second = {"name": "fp64_pipe", "algorithmic_fma_per_row": FMA_PER_ROW, "achieved_fma_per_clk_per_sm": fma_per_clk_sm,
+                  "measured_peak_fma_per_clk_per_sm": 62.7, "frac": fma_per_clk_sm / 62.7,
+                  "note": "gram_cells_kernel: a thread owns a knot cell of a term pair and sums the 4 x 4 outer products of "
+                          "the cell's rows in registers (rows counting-sorted by cell in shared memory); the useful work is "
+                          "902 fp64 FMA per row at 88 algorithmic bytes per row = 20 flop/B, so the fp64 pipe (62.7 "
+                          "FMA/clk/SM measured, tools/ubench.cu), not HBM, bounds the pass (DESIGN.md section 4)"}
+    else:
+        kernels = "gram_records_kernel + gram_accum_kernel (the Gram pass of one PIRLS iteration)"
+        second = {"name": "shared_memory_rmw", "algorithmic_fma_per_row": FMA_PER_ROW,
+                  "achieved_fma_per_clk_per_sm": fma_per_clk_sm, "measured_peak_fma_per_clk_per_sm": 7.7,
+                  "frac": fma_per_clk_sm / 7.7,
+                  "note": "general path: products scattered into G held in shared memory, 16 B of read-modify-write per FMA"}
+    roofline = {"kernel": kernels, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
-                "traffic": None, "kernel_ms": gram_ms, "records_kernel_ms": records, "accum_kernel_ms": accum,
+                "traffic": traffic, "kernel_ms": gram_ms, "prepass_kernel_ms": records, "accum_kernel_ms": accum,
                 "kernel_share_of_step": gram_ms / ms_per_step, "algorithmic_bytes_per_row": BYTES_PER_ROW,
-                "shared_memory_rmw": {"algorithmic_fma_per_row": FMA_PER_ROW, "achieved_fma_per_clk_per_sm": fma_per_clk_sm,
-                                      "measured_peak_fma_per_clk_per_sm": 7.7, "frac": fma_per_clk_sm / 7.7,
-                                      "note": "the accumulation kernel scatters 902 fp64 FMA per row into data-dependent "
-                                              "elements of G held in shared memory: 16 B of shared-memory read-modify-write "
-                                              "per FMA at 128 B/clk/SM (tools/ubench.cu measures 7.7 FMA/clk/SM), 8x below "
-                                              "the fp64 pipe and far below HBM (DESIGN.md section 4)"}}
+                "governing": second}
     line = {"metric": "rows/sec per PIRLS iteration", "value": value, "unit": "rows/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(world, n),

@@ -33,14 +33,14 @@
 #include "pgb_internal.h"
 #include "pgb_kernels.cuh"
 
-static const int kCellThreads = 512;      // threads of a cells CTA = cells a role owns
+static const int kCellMaxThreads = 512;   // most threads of a cells CTA = most cells a role owns
 static const int kCellAcc = 18;           // sums per cell (16 for a pair; 10 + 4 + 4 for a diagonal role)
 static const int kPreThreads = 256;
 static const int64_t kBandBytes = 32ll << 20;  // column bytes of a band of rows (stays in the L2)
 
-static const int kCellWarps = kCellThreads / 32;
-// tile: x_i, x_j (or omega z), omega; 16-bit cell key and sorted row index per row; 16-bit counters per (warp, cell)
-static size_t cells_smem(int tile) { return (size_t)tile * (24 + 4) + (size_t)kCellWarps * kCellThreads * 2 + 64; }
+// tile: t_i, t_j (or omega z), omega; sorted row index; the two interval bytes (later the 16-bit cell key) per row;
+// 16-bit counters per (warp, cell)
+static size_t cells_smem(int tile, int threads) { return (size_t)tile * (24 + 2 + 2) + (size_t)(threads / 32) * threads * 2 + 64; }
 
 // ----------------------------------------------------------------------------------------
 // plan
@@ -57,7 +57,7 @@ int pgb_plan_cells(pgb_model* M) {
     if (t.kind == PGB_TERM_INTERCEPT) {
       if (icpt >= 0) return PGB_OK;
       icpt = j;
-    } else if (t.fast && t.marg[0].nint >= 1 && t.marg[0].nint <= 4096) {
+    } else if (t.fast && t.marg[0].nint >= 1 && t.marg[0].nint <= 127  /* the interval is a 7-bit field of the cell record */) {
       ++n_spl;
     } else {
       return PGB_OK;  // some other term: the general path
@@ -65,6 +65,25 @@ int pgb_plan_cells(pgb_model* M) {
   }
   if (n_spl < 1) return PGB_OK;
   C.icpt_coef = icpt >= 0 ? M->dterms[icpt].coef_offset : -1;
+  C.n_spl = n_spl;
+  std::vector<int> spl_of(nt, -1);  // term -> column of the cell records
+  for (int j = 0, q = 0; j < nt; ++j)
+    if (M->dterms[j].fast) spl_of[j] = q++;
+  // CTA shape: one thread per cell of a role.  Pairs of coarse bases (the default n_splines = 20 has 17 x 17
+  // = 289 cells) get narrower CTAs, two per SM, so that no thread idles and one CTA sorts while the other sums
+  int max_cells = 1;
+  for (int i = 0; i < nt; ++i)
+    for (int j = i + 1; j < nt; ++j)
+      if (M->dterms[i].fast && M->dterms[j].fast)
+        max_cells = std::max(max_cells, M->dterms[i].marg[0].nint * M->dterms[j].marg[0].nint);
+  if (n_spl == 1) max_cells = 256;  // diagonal roles only: interval x row split
+  C.threads = max_cells <= 256 ? 256 : max_cells <= 320 ? 320 : max_cells <= 384 ? 384 : 512;
+  C.occ = C.threads <= 320 ? 2 : 1;
+  if (const char* e = getenv("PGB_CELLS_THREADS")) {
+    const int t = atoi(e);
+    if (t == 256 || t == 320 || t == 384 || t == 512) { C.threads = t; C.occ = t <= 320 ? 2 : 1; }
+  }
+  const int TH = C.threads;
   int64_t sum_off = 0;
   int64_t n_sub = 0;
   for (int i = 0; i < nt; ++i) {
@@ -80,21 +99,23 @@ int pgb_plan_cells(pgb_model* M) {
       P.off_j = tj.coef_offset;
       P.nint_i = ti.marg[0].nint;
       // diagonal role: the rows of an interval are spread over `ncb` cells by row index, for balance
-      P.ncb = (j == i) ? std::max(1, std::min(32, kCellThreads / P.nint_i)) : tj.marg[0].nint;
+      P.ncb = (j == i) ? std::max(1, std::min(32, TH / P.nint_i)) : tj.marg[0].nint;
       P.ncells = P.nint_i * P.ncb;
       P.sum_off = sum_off;
       sum_off += (int64_t)kCellAcc * P.ncells;
       const int pair = (int)C.pairs.size();
       C.pairs.push_back(P);
-      for (int k0 = 0; k0 < P.ncells; k0 += kCellThreads) {
+      for (int k0 = 0; k0 < P.ncells; k0 += TH) {
         DCellRole R{};
         R.a = ti.marg[0];
         R.b = tj.marg[0];
         R.diag = (j == i) ? 1 : 0;
         R.ncb = P.ncb;
         R.key0 = k0;
-        R.ncell = std::min(kCellThreads, P.ncells - k0);
+        R.ncell = std::min(TH, P.ncells - k0);
         R.pair = pair;
+        R.sa = spl_of[i];
+        R.sb = spl_of[j];
         C.roles.push_back(R);
         ++n_sub;
       }
@@ -106,13 +127,15 @@ int pgb_plan_cells(pgb_model* M) {
     return PGB_OK;
   }
   C.sum_doubles = sum_off;
-  C.grid = kSMs;
-  C.tile_rows = 7680;
-  if (const char* e = getenv("PGB_CELLS_TILE")) C.tile_rows = std::max(64, atoi(e) & ~1);
-  while (cells_smem(C.tile_rows) + 1024 > kSmemMax) C.tile_rows -= 64;  // 1 KB for the kernel's static shared memory
-  C.smem = cells_smem(C.tile_rows);
+  C.grid = kSMs * C.occ;
+  C.tile_rows = 8192;
+  if (const char* e = getenv("PGB_CELLS_TILE")) C.tile_rows = std::max(64, atoi(e) & ~63);
+  // 1 KB per CTA for the kernel's static shared memory and the driver's reservation
+  while (cells_smem(C.tile_rows, TH) + 1024 > (C.occ == 2 ? kSmemMax / 2 - 1024 : kSmemMax)) C.tile_rows -= 64;
+  for (DCellRole& R : C.roles) R.hmul = ((uint32_t)R.ncb << 16) / (uint32_t)C.tile_rows;
+  C.smem = cells_smem(C.tile_rows, TH);
   C.slots_per_cta = ((int)C.roles.size() + C.grid - 1) / C.grid + 1;
-  C.slot_doubles = (int64_t)kCellAcc * kCellThreads;
+  C.slot_doubles = (int64_t)kCellAcc * TH;
   {
     // CTA c serves roles inside [floor(R c / grid), ceil(R (c + 1) / grid) - 1] in every band
     const int64_t nr = (int64_t)C.roles.size();
@@ -232,20 +255,45 @@ int pgb_cells_coverage_errors(const pgb_model* M) {
   return errors;
 }
 
+// workspace: [CTA partial slots][cell sums][scalar partials][extra][omega][omega z][t of every spline term][cells]
+static int64_t rows_pad(int64_t n) { return (n + 15) & ~(int64_t)15; }
 extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n) {
   const pgb_model::Cells& C = M->cells;
   const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
-  return (slots * C.slot_doubles + C.sum_doubles + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2) + 8 + 2 * (n + 2)) * 8 + 1024;
+  const int64_t np = rows_pad(n);
+  return (slots * C.slot_doubles + C.sum_doubles + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2) + 8 + (2 + C.n_spl) * np) * 8 +
+         (int64_t)C.n_spl * np + 1024;
 }
 
 // ----------------------------------------------------------------------------------------
-// kernel 1: the elementwise IRLS step of every row (or the response of _initial_estimate)
+// kernel 1: one thread per row.  Basis of every spline term -> lp -> the IRLS step (mu, W, mask,
+// working response; pygam.py:764-777) or the response of _initial_estimate; writes per row omega
+// and omega * z, and per (row, spline term) the row's CELL RECORD: the knot interval (1 byte, bit 7:
+// the row lies outside the edge knots) and the local coordinate t in [0, 1] inside it (fp64; for a
+// row outside the knots the normalised coordinate u itself) -- 9 bytes instead of four (value,
+// index) pairs: the cells kernel re-evaluates the four cubic B-spline values from t in registers.
 // ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void extrap_basis(const DMarg& mg, double u, double* v) {
+  // eval_marg's branch outside [0, 1] (utils.py:744-763), from the normalised coordinate
+  const bool below = u < 0.0;
+  const double te = below ? 0.0 : 1.0, dist = below ? u : u - 1.0;
+  double lowv[PGB_MAXV];
+  deboor_uniform<2>(te, lowv);
+  deboor_uniform<3>(te, v);
+#pragma unroll
+  for (int r = 0; r <= 3; ++r) {
+    const double a = (r >= 1) ? lowv[r - 1] : 0.0;
+    const double b = (r <= 2) ? lowv[r] : 0.0;
+    v[r] = ((double)mg.nint * (a - b)) * dist + v[r];
+  }
+}
+
 __global__ void __launch_bounds__(kPreThreads, 4)
 gram_prepass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Family fam, int mode,
                     const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
-                    const float* __restrict__ w, const double* __restrict__ beta, double* __restrict__ om,
-                    double* __restrict__ omz, double* __restrict__ scal_part) {
+                    const float* __restrict__ w, const double* __restrict__ beta, int64_t np, double* __restrict__ om,
+                    double* __restrict__ omz, double* __restrict__ tq, uint8_t* __restrict__ cq,
+                    double* __restrict__ scal_part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   double* s_beta = reinterpret_cast<double*>(smem_raw);
@@ -258,12 +306,41 @@ gram_prepass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Famil
 #pragma unroll
   for (int s = 0; s < PGB_GS_COUNT + 2; ++s) sc[s] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double lp = 0.0;
+    int sp = 0;
+    for (int q = 0; q < n_terms; ++q) {
+      const DTerm& T = s_terms[q];
+      if (T.kind == PGB_TERM_INTERCEPT) {
+        lp += s_beta[T.coef_offset];
+        continue;
+      }
+      const DMarg& mg = T.marg[0];
+      const double u = (__ldg(X + (int64_t)mg.feature * ld + i) - mg.lo) * mg.inv_span;
+      double v[4], t;
+      int cell;
+      if (u >= 0.0 && u <= 1.0) {  // the arithmetic of eval_term's straight-line cubic
+        const double s = u * (double)mg.nint;
+        cell = min((int)s, mg.nint - 1);
+        t = s - (double)cell;
+        cubic_bspline(t, v[0], v[1], v[2], v[3]);
+      } else {
+        extrap_basis(mg, u, v);
+        cell = (u < 0.0 ? 0 : mg.nint - 1) | 0x80;
+        t = u;
+      }
+      const double* bt = s_beta + T.coef_offset + (cell & 0x7f);
+      lp = fma(v[0], bt[0], lp);
+      lp = fma(v[1], bt[1], lp);
+      lp = fma(v[2], bt[2], lp);
+      lp = fma(v[3], bt[3], lp);
+      tq[(int64_t)sp * np + i] = t;
+      cq[(int64_t)sp * np + i] = (uint8_t)cell;
+      ++sp;
+    }
     const double yi = __ldg(y + i);
     double o, oz;
     if (mode == PGB_MODE_IRLS) {
-      EmitLp e{s_beta, 0.0};
-      for (int q = 0; q < n_terms; ++q) eval_term(s_terms[q], X, ld, i, e);
-      const IrlsRow ir = irls_row(fam, e.lp, yi, weight_inv(w, i));
+      const IrlsRow ir = irls_row(fam, lp, yi, weight_inv(w, i));
       o = ir.omega;
       oz = ir.omega * ir.z;
       if (ir.keep) {
@@ -289,49 +366,127 @@ gram_prepass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Famil
 // ----------------------------------------------------------------------------------------
 // kernel 2: cells
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ int cell_of(const DMarg& mg, double x) {
-  const double u = (x - mg.lo) * mg.inv_span;
-  const double s = u * (double)mg.nint;
-  return min(max((int)s, 0), mg.nint - 1);  // eval_marg's interval, clamped like its extrapolation branch
-}
+// the four basis values of a row outside the edge knots (rare: custom edge_knots narrower than the data)
+__device__ __noinline__ void cell_basis_outside(const DMarg* mg, double u, double* v) { extrap_basis(*mg, u, v); }
 
-// basis values of a row in the cell `cell_d` it was sorted into: the straight-line cubic of
-// eval_term inside the edge knots, eval_marg's linear extrapolation outside
-__device__ __forceinline__ void cell_basis(const DMarg& mg, double lo, double inv_span, double nint_d, double cell_d, double x,
-                                           double& b0, double& b1, double& b2, double& b3) {
-  const double u = (x - lo) * inv_span;
-  if (u >= 0.0 && u <= 1.0) {
-    cubic_bspline(u * nint_d - cell_d, b0, b1, b2, b3);
-  } else {
+template <bool CAREFUL>
+__device__ __forceinline__ void cell_basis(const DMarg* mg, double t, double& b0, double& b1, double& b2, double& b3) {
+  if (CAREFUL && (t < 0.0 || t > 1.0)) {
     double v[PGB_MAXV];
-    eval_marg(mg, x, v);
+    cell_basis_outside(mg, t, v);
     b0 = v[0]; b1 = v[1]; b2 = v[2]; b3 = v[3];
+  } else {
+    cubic_bspline(t, b0, b1, b2, b3);
   }
 }
 
-__global__ void __launch_bounds__(kCellThreads, 1)
-gram_cells_kernel(const double* __restrict__ X, int64_t ld, int64_t n, const double* __restrict__ om,
-                  const double* __restrict__ omz, const DCellRole* __restrict__ roles, int n_roles, int TR,
-                  int band_tiles, int slots_per_cta, double* __restrict__ part) {
+// the rows of one cell of a pair (i, j): 16 sums
+template <bool CAREFUL>
+__device__ __forceinline__ void cell_rows_pair(const DCellRole* R, const uint16_t* __restrict__ perm, int c,
+                                               const double* __restrict__ ta, const double* __restrict__ tb,
+                                               const double* __restrict__ wv, double (&acc)[kCellAcc]) {
+#pragma unroll 1
+  for (int s = 0; s < c; ++s) {
+    const int r = perm[s];
+    const double ww = wv[r];
+    double a0, a1, a2, a3, b0, b1, b2, b3;
+    cell_basis<CAREFUL>(&R->a, ta[r], a0, a1, a2, a3);
+    cell_basis<CAREFUL>(&R->b, tb[r], b0, b1, b2, b3);
+    a0 *= ww; a1 *= ww; a2 *= ww; a3 *= ww;
+    acc[0] = fma(a0, b0, acc[0]); acc[1] = fma(a0, b1, acc[1]); acc[2] = fma(a0, b2, acc[2]); acc[3] = fma(a0, b3, acc[3]);
+    acc[4] = fma(a1, b0, acc[4]); acc[5] = fma(a1, b1, acc[5]); acc[6] = fma(a1, b2, acc[6]); acc[7] = fma(a1, b3, acc[7]);
+    acc[8] = fma(a2, b0, acc[8]); acc[9] = fma(a2, b1, acc[9]); acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
+    acc[12] = fma(a3, b0, acc[12]); acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
+  }
+}
+
+// the rows of one cell of a diagonal block: 10 sums of the packed upper triangle, the intercept
+// column (omega b), the right-hand side (omega z b)
+template <bool CAREFUL>
+__device__ __forceinline__ void cell_rows_diag(const DCellRole* R, const uint16_t* __restrict__ perm, int c,
+                                               const double* __restrict__ ta, const double* __restrict__ wz,
+                                               const double* __restrict__ wv, double (&acc)[kCellAcc]) {
+#pragma unroll 1
+  for (int s = 0; s < c; ++s) {
+    const int r = perm[s];
+    const double ww = wv[r], z = wz[r];
+    double a0, a1, a2, a3;
+    cell_basis<CAREFUL>(&R->a, ta[r], a0, a1, a2, a3);
+    const double v0 = a0 * ww, v1 = a1 * ww, v2 = a2 * ww, v3 = a3 * ww;
+    acc[0] = fma(v0, a0, acc[0]); acc[1] = fma(v0, a1, acc[1]); acc[2] = fma(v0, a2, acc[2]); acc[3] = fma(v0, a3, acc[3]);
+    acc[4] = fma(v1, a1, acc[4]); acc[5] = fma(v1, a2, acc[5]); acc[6] = fma(v1, a3, acc[6]);
+    acc[7] = fma(v2, a2, acc[7]); acc[8] = fma(v2, a3, acc[8]); acc[9] = fma(v3, a3, acc[9]);
+    acc[10] += v0; acc[11] += v1; acc[12] += v2; acc[13] += v3;
+    acc[14] = fma(a0, z, acc[14]); acc[15] = fma(a1, z, acc[15]); acc[16] = fma(a2, z, acc[16]); acc[17] = fma(a3, z, acc[17]);
+  }
+}
+
+// the (role, tile) units of one CTA, band by band; odd bands are walked backwards so that a band
+// starts with the role the previous one ended with
+struct UnitIter {
+  int64_t ntiles, nbands, band, uu, u_lo, u_hi, nb, t0;
+  int band_tiles, n_roles;
+  __device__ void set_band() {
+    t0 = band * band_tiles;
+    nb = min((int64_t)band_tiles, ntiles - t0);
+    const int64_t U = nb * n_roles;
+    u_lo = U * blockIdx.x / gridDim.x;
+    u_hi = U * (blockIdx.x + 1) / gridDim.x;
+    uu = 0;
+  }
+  __device__ void skip_empty() {
+    while (band < nbands && uu >= u_hi - u_lo) {
+      ++band;
+      if (band < nbands) set_band();
+    }
+  }
+  __device__ void init(int64_t n, int TR, int bt, int nr) {
+    band_tiles = bt;
+    n_roles = nr;
+    ntiles = (n + TR - 1) / TR;
+    nbands = (ntiles + bt - 1) / bt;
+    band = 0;
+    set_band();
+    skip_empty();
+  }
+  __device__ bool valid() const { return band < nbands; }
+  __device__ int64_t unit() const { return (band & 1) ? (u_hi - 1 - uu) : (u_lo + uu); }
+  __device__ int role() const { return (int)(unit() / nb); }
+  __device__ int64_t tile() const { return t0 + unit() % nb; }
+  __device__ void next() {
+    ++uu;
+    skip_empty();
+  }
+};
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const double* __restrict__ omz,
+                  const double* __restrict__ tq, const uint8_t* __restrict__ cq, const DCellRole* __restrict__ roles,
+                  int n_roles, int TR, int band_tiles, int slots_per_cta, double* __restrict__ part) {
+  constexpr int kCellThreads = THREADS, kCellWarps = THREADS / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ DCellRole R;
   __shared__ int s_wtot[32];
-  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_careful;
+  __shared__ __align__(8) unsigned long long s_bar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* xa = reinterpret_cast<double*>(smem_raw);
-  double* xb = xa + TR;
-  double* wv = xb + TR;
-  uint16_t* key = reinterpret_cast<uint16_t*>(wv + TR);
-  uint16_t* perm = key + TR;
+  double* ta = reinterpret_cast<double*>(smem_raw);   // t of the row term
+  double* tb = ta + TR;                               // t of the column term (diagonal role: omega z)
+  double* wv = tb + TR;                               // omega
+  uint16_t* perm = reinterpret_cast<uint16_t*>(wv + TR);
   uint32_t* wh32 = reinterpret_cast<uint32_t*>(perm + TR);  // [warp][cell / 2]
   uint16_t* wh16 = reinterpret_cast<uint16_t*>(wh32);       // [warp][cell]
-  const uint32_t bar = smem_addr(&s_bar);
+  // interval bytes of the two terms; pass 1 overwrites them with the 16-bit cell keys of the rows (a thread's
+  // four rows: keys 0, 1 in its word of ca, keys 2, 3 in its word of cb)
+  uint8_t* ca = reinterpret_cast<uint8_t*>(wh32 + kCellWarps * (kCellThreads / 2));
+  uint8_t* cb = ca + TR;
+  const uint32_t bar_c = smem_addr(&s_bar[0]), bar_b = smem_addr(&s_bar[1]);
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar_c, 1);
+    mbar_init(bar_b, 1);
     fence_mbar_init();
   }
-  const int64_t ntiles = (n + TR - 1) / TR;
-  const int64_t nbands = (ntiles + band_tiles - 1) / band_tiles;
   const int role_lo = (int)((int64_t)n_roles * blockIdx.x / gridDim.x);  // first role this CTA can ever serve
   double* my_part = part + (int64_t)blockIdx.x * slots_per_cta * (kCellAcc * kCellThreads);
   int cur_role = -1;
@@ -339,150 +494,144 @@ gram_cells_kernel(const double* __restrict__ X, int64_t ld, int64_t n, const dou
   double acc[kCellAcc];
 #pragma unroll
   for (int e = 0; e < kCellAcc; ++e) acc[e] = 0.0;
-  for (int64_t band = 0; band < nbands; ++band) {
-    const int64_t t0 = band * band_tiles;
-    const int64_t nb = min((int64_t)band_tiles, ntiles - t0);
-    const int64_t U = nb * n_roles;
-    const int64_t u_lo = U * blockIdx.x / gridDim.x, u_hi = U * (blockIdx.x + 1) / gridDim.x;
-    // odd bands walk their units backwards: the band starts with the role the previous one ended with
-    for (int64_t uu = 0; uu < u_hi - u_lo; ++uu) {
-      const int64_t u = (band & 1) ? (u_hi - 1 - uu) : (u_lo + uu);
-      const int role = (int)(u / nb);
-      const int64_t tile = t0 + (u - (int64_t)role * nb);
-      if (role != cur_role) {
-        // park the sums of the role we leave in its slot, fetch the sums of the one we enter
-        if (cur_role >= 0) {
-          double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * kCellThreads);
+  UnitIter it;
+  it.init(n, TR, band_tiles, n_roles);
+  // the interval bytes of a unit: a bulk copy of 2 bytes per row, issued one unit ahead
+  auto load_cells = [&](const UnitIter& u) {
+    const int role = u.role();
+    const int64_t row0 = u.tile() * TR;
+    const uint32_t cnt16 = (uint32_t)((min((int64_t)TR, n - row0) + 15) & ~(int64_t)15);
+    const int sa = roles[role].sa, sb = roles[role].sb;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses vs the async writes
+    mbar_expect_tx(bar_c, 2u * cnt16);
+    bulk_g2s(smem_addr(ca), cq + (int64_t)sa * np + row0, cnt16, bar_c);
+    bulk_g2s(smem_addr(cb), cq + (int64_t)sb * np + row0, cnt16, bar_c);
+  };
+  __syncthreads();
+  if (tid == 0 && it.valid()) load_cells(it);
+  for (; it.valid();) {
+    const int role = it.role();
+    const int64_t tile = it.tile();
+    if (role != cur_role) {
+      // park the sums of the role we leave in its slot, fetch the sums of the one we enter
+      if (cur_role >= 0) {
+        double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * kCellThreads);
 #pragma unroll
-          for (int e = 0; e < kCellAcc; ++e) dst[e * kCellThreads + tid] = acc[e];
-        }
-        const double* src = my_part + (int64_t)(role - role_lo) * (kCellAcc * kCellThreads);
+        for (int e = 0; e < kCellAcc; ++e) dst[e * kCellThreads + tid] = acc[e];
+      }
+      const double* src = my_part + (int64_t)(role - role_lo) * (kCellAcc * kCellThreads);
 #pragma unroll
-        for (int e = 0; e < kCellAcc; ++e) acc[e] = src[e * kCellThreads + tid];
-        __syncthreads();
-        if (tid == 0) R = roles[role];
-        __syncthreads();
-        cur_role = role;
-      }
-      const int NC = R.ncell, diag = R.diag, ncb = R.ncb, key0 = R.key0;
-      const int64_t row0 = tile * TR;
-      const int cnt = (int)min((int64_t)TR, n - row0);
-      const double* ca = X + (int64_t)R.a.feature * ld + row0;
-      const double* cb = diag ? omz + row0 : X + (int64_t)R.b.feature * ld + row0;
-      const double* cw = om + row0;
-      const bool bulk = (cnt == TR) && ((((uintptr_t)ca | (uintptr_t)cb | (uintptr_t)cw) & 15) == 0);
-      if (bulk) {
-        if (tid == 0) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads vs the async writes
-          mbar_expect_tx(bar, 3u * (uint32_t)TR * 8u);
-          bulk_g2s(smem_addr(xa), ca, (uint32_t)TR * 8u, bar);
-          bulk_g2s(smem_addr(xb), cb, (uint32_t)TR * 8u, bar);
-          bulk_g2s(smem_addr(wv), cw, (uint32_t)TR * 8u, bar);
-        }
-      } else {
-        for (int r = tid; r < cnt; r += kCellThreads) {
-          xa[r] = ca[r];
-          xb[r] = cb[r];
-          wv[r] = cw[r];
-        }
-      }
-      for (int i = tid; i < kCellWarps * (kCellThreads / 2); i += kCellThreads) wh32[i] = 0u;
-      __syncthreads();
-      if (bulk) {
-        mbar_wait(bar, phase);
-        phase ^= 1;
-      }
-      // ---- counting sort of the tile's rows by cell, stable per warp.  Counters are private to a
-      //      (warp, cell): 16 bits each, two per word, bumped with one shared-memory atomic on the word
-      //      (a warp's conflicting lanes are resolved by the hardware in a fixed order, and no other warp
-      //      touches the word: the sorted order, hence the fp64 sums, are reproducible run to run).
-      //      Rows of other roles of the same pair get key 0xffff.
-      uint32_t* my_wh = wh32 + warp * (kCellThreads / 2);
-      for (int r = tid; r < cnt; r += kCellThreads) {
-        const int ci = cell_of(R.a, xa[r]);
-        const int k = (diag ? ci * ncb + (r % ncb) : ci * ncb + cell_of(R.b, xb[r])) - key0;
-        const bool mine = (unsigned)k < (unsigned)NC;
-        key[r] = mine ? (uint16_t)k : (uint16_t)0xffff;
+      for (int e = 0; e < kCellAcc; ++e) acc[e] = src[e * kCellThreads + tid];
+      if (tid == 0) R = roles[role];
+      cur_role = role;
+    }
+    const int64_t row0 = tile * TR;
+    const int cnt = (int)min((int64_t)TR, n - row0);
+    if (tid == 0) {
+      // t of both terms and omega: in flight while the rows are being sorted.  The workspace columns are
+      // 16-byte aligned and padded to 16 rows: the last tile is rounded up
+      const uint32_t cnt16 = (uint32_t)((cnt + 15) & ~15);
+      const DCellRole* gr = roles + role;
+      const double* ga = tq + (int64_t)gr->sa * np + row0;
+      const double* gb = gr->diag ? omz + row0 : tq + (int64_t)gr->sb * np + row0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar_b, 3u * cnt16 * 8u);
+      bulk_g2s(smem_addr(ta), ga, cnt16 * 8u, bar_b);
+      bulk_g2s(smem_addr(tb), gb, cnt16 * 8u, bar_b);
+      bulk_g2s(smem_addr(wv), om + row0, cnt16 * 8u, bar_b);
+      s_careful = 0;
+    }
+    for (int i = tid; i < kCellWarps * (kCellThreads / 2); i += kCellThreads) wh32[i] = 0u;
+    __syncthreads();
+    const int NC = R.ncell, diag = R.diag, ncb = R.ncb, key0 = R.key0;
+    mbar_wait(bar_c, phase);
+    // ---- counting sort of the tile's rows by cell, stable per warp.  Counters are private to a
+    //      (warp, cell): 16 bits each, two per word, bumped with one shared-memory atomic on the word
+    //      (a warp's conflicting lanes are resolved by the hardware in a fixed order, and no other warp
+    //      touches the word: the sorted order, hence the fp64 sums, are reproducible run to run).
+    //      Rows of other roles of the same pair get key 0xffff.  A thread takes four consecutive rows.
+    uint32_t* my_wh = wh32 + warp * (kCellThreads / 2);
+    const uint32_t hmul = R.hmul;
+    int careful = 0;
+    for (int r4 = 4 * tid; r4 < cnt; r4 += 4 * kCellThreads) {
+      const uint32_t a4 = *reinterpret_cast<const uint32_t*>(ca + r4);
+      const uint32_t b4 = *reinterpret_cast<const uint32_t*>(cb + r4);
+      careful |= (int)((a4 | (diag ? 0u : b4)) & 0x80808080u);
+      uint32_t kk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ci = (a4 >> (8 * q)) & 0x7f;
+        const int cj = diag ? (int)(((uint32_t)(r4 + q) * hmul) >> 16) : (int)((b4 >> (8 * q)) & 0x7f);
+        const int k = ci * ncb + cj - key0;
+        const bool mine = ((unsigned)k < (unsigned)NC) && (r4 + q < cnt);
+        kk[q] = mine ? (uint32_t)k : 0xffffu;
         if (mine) atomicAdd(&my_wh[k >> 1], (k & 1) ? 0x10000u : 1u);
       }
-      __syncthreads();
-      // ---- thread k owns cell k: its rows per warp, exclusive scan over the cells, start offsets back
-      int c = 0;
+      *reinterpret_cast<uint32_t*>(ca + r4) = kk[0] | (kk[1] << 16);
+      *reinterpret_cast<uint32_t*>(cb + r4) = kk[2] | (kk[3] << 16);
+    }
+    if (careful) s_careful = 1;
+    __syncthreads();
+    // ---- thread k owns cell k: its rows per warp, exclusive scan over the cells, start offsets back
+    int c = 0;
 #pragma unroll
-      for (int q = 0; q < kCellWarps; ++q) c += wh16[q * kCellThreads + tid];
-      int incl = c;
+    for (int q = 0; q < kCellWarps; ++q) c += wh16[q * kCellThreads + tid];
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int t = lane < kCellWarps ? s_wtot[lane] : 0;
+      int ti = t;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        const int v = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += v;
       }
-      if (lane == 31) s_wtot[warp] = incl;
-      __syncthreads();
-      if (warp == 0) {
-        const int t = lane < kCellWarps ? s_wtot[lane] : 0;
-        int ti = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, ti, o);
-          if (lane >= o) ti += v;
-        }
-        s_wtot[lane] = ti - t;
-      }
-      __syncthreads();
-      const int start = incl - c + s_wtot[warp];
-      {
-        int run = start;
-#pragma unroll
-        for (int q = 0; q < kCellWarps; ++q) {
-          const int cq = wh16[q * kCellThreads + tid];
-          wh16[q * kCellThreads + tid] = (uint16_t)run;
-          run += cq;
-        }
-      }
-      __syncthreads();
-      for (int r = tid; r < cnt; r += kCellThreads) {
-        const int k = key[r];
-        if (k != 0xffff) {
-          const uint32_t old = atomicAdd(&my_wh[k >> 1], (k & 1) ? 0x10000u : 1u);
-          perm[(k & 1) ? (old >> 16) : (old & 0xffffu)] = (uint16_t)r;
-        }
-      }
-      __syncthreads();
-      if (!diag) {
-        const int kk = key0 + tid;
-        const double cid = (double)(kk / ncb), cjd = (double)(kk % ncb);
-        const double loa = R.a.lo, isa = R.a.inv_span, na = (double)R.a.nint;
-        const double lob = R.b.lo, isb = R.b.inv_span, nb2 = (double)R.b.nint;
-        for (int s = 0; s < c; ++s) {
-          const int r = perm[start + s];
-          const double ww = wv[r];
-          double a0, a1, a2, a3, b0, b1, b2, b3;
-          cell_basis(R.a, loa, isa, na, cid, xa[r], a0, a1, a2, a3);
-          cell_basis(R.b, lob, isb, nb2, cjd, xb[r], b0, b1, b2, b3);
-          a0 *= ww; a1 *= ww; a2 *= ww; a3 *= ww;
-          acc[0] = fma(a0, b0, acc[0]); acc[1] = fma(a0, b1, acc[1]); acc[2] = fma(a0, b2, acc[2]); acc[3] = fma(a0, b3, acc[3]);
-          acc[4] = fma(a1, b0, acc[4]); acc[5] = fma(a1, b1, acc[5]); acc[6] = fma(a1, b2, acc[6]); acc[7] = fma(a1, b3, acc[7]);
-          acc[8] = fma(a2, b0, acc[8]); acc[9] = fma(a2, b1, acc[9]); acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
-          acc[12] = fma(a3, b0, acc[12]); acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
-        }
-      } else {
-        const double cid = (double)((key0 + tid) / ncb);
-        const double loa = R.a.lo, isa = R.a.inv_span, na = (double)R.a.nint;
-        for (int s = 0; s < c; ++s) {
-          const int r = perm[start + s];
-          const double ww = wv[r], wz = xb[r];
-          double a0, a1, a2, a3;
-          cell_basis(R.a, loa, isa, na, cid, xa[r], a0, a1, a2, a3);
-          const double v0 = a0 * ww, v1 = a1 * ww, v2 = a2 * ww, v3 = a3 * ww;
-          acc[0] = fma(v0, a0, acc[0]); acc[1] = fma(v0, a1, acc[1]); acc[2] = fma(v0, a2, acc[2]); acc[3] = fma(v0, a3, acc[3]);
-          acc[4] = fma(v1, a1, acc[4]); acc[5] = fma(v1, a2, acc[5]); acc[6] = fma(v1, a3, acc[6]);
-          acc[7] = fma(v2, a2, acc[7]); acc[8] = fma(v2, a3, acc[8]); acc[9] = fma(v3, a3, acc[9]);
-          acc[10] += v0; acc[11] += v1; acc[12] += v2; acc[13] += v3;
-          acc[14] = fma(a0, wz, acc[14]); acc[15] = fma(a1, wz, acc[15]); acc[16] = fma(a2, wz, acc[16]); acc[17] = fma(a3, wz, acc[17]);
-        }
-      }
-      __syncthreads();
+      s_wtot[lane] = ti - t;
     }
+    __syncthreads();
+    const int start = incl - c + s_wtot[warp];
+    {
+      int run = start;
+#pragma unroll
+      for (int q = 0; q < kCellWarps; ++q) {
+        const int cq2 = wh16[q * kCellThreads + tid];
+        wh16[q * kCellThreads + tid] = (uint16_t)run;
+        run += cq2;
+      }
+    }
+    __syncthreads();
+    for (int r4 = 4 * tid; r4 < cnt; r4 += 4 * kCellThreads) {
+      const uint32_t k01 = *reinterpret_cast<const uint32_t*>(ca + r4), k23 = *reinterpret_cast<const uint32_t*>(cb + r4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t k = (((q & 2) ? k23 : k01) >> (16 * (q & 1))) & 0xffffu;
+        if (k != 0xffffu) {
+          const uint32_t old = atomicAdd(&my_wh[k >> 1], (k & 1) ? 0x10000u : 1u);
+          perm[(k & 1) ? (old >> 16) : (old & 0xffffu)] = (uint16_t)(r4 + q);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- the interval bytes of the next unit go where the keys were, while this unit's rows are summed
+    it.next();
+    if (tid == 0 && it.valid()) load_cells(it);
+    mbar_wait(bar_b, phase);
+    phase ^= 1;
+    // ---- the rows of my cell
+    if (!s_careful) {
+      if (!diag) cell_rows_pair<false>(&R, perm + start, c, ta, tb, wv, acc);
+      else cell_rows_diag<false>(&R, perm + start, c, ta, tb, wv, acc);
+    } else {
+      if (!diag) cell_rows_pair<true>(&R, perm + start, c, ta, tb, wv, acc);
+      else cell_rows_diag<true>(&R, perm + start, c, ta, tb, wv, acc);
+    }
+    __syncthreads();
   }
   if (cur_role >= 0) {
     double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * kCellThreads);
@@ -496,32 +645,35 @@ gram_cells_kernel(const double* __restrict__ X, int64_t ld, int64_t n, const dou
 // ----------------------------------------------------------------------------------------
 __global__ void cells_slot_reduce_kernel(const double* __restrict__ part, const DCellRole* __restrict__ roles,
                                          const DCellPair* __restrict__ pairs, int n_roles, int grid, int slots_per_cta,
-                                         double* __restrict__ sums) {
-  const int role = blockIdx.x, k = threadIdx.x;
+                                         int threads, double* __restrict__ sums) {
+  const int role = blockIdx.x, k = threadIdx.x, e = blockIdx.y;
   const DCellRole R = roles[role];
   if (k >= R.ncell) return;
   const DCellPair P = pairs[R.pair];
   const int64_t nr = n_roles;
   const int c_lo = R.c_lo, c_hi = R.c_hi;
-  for (int e = 0; e < kCellAcc; ++e) {
+  {
     double v = 0.0;
     for (int c = c_lo; c <= c_hi; ++c) {
       const int lo = (int)(nr * c / grid);
       const int hi = (int)((nr * (c + 1) + grid - 1) / grid) - 1;
       if (role < lo || role > hi || role - lo >= slots_per_cta) continue;
-      v += part[((int64_t)c * slots_per_cta + (role - lo)) * (kCellAcc * kCellThreads) + e * kCellThreads + k];
+      v += part[((int64_t)c * slots_per_cta + (role - lo)) * (kCellAcc * threads) + e * threads + k];
     }
     sums[P.sum_off + (int64_t)e * P.ncells + R.key0 + k] = v;
   }
 }
 
-// scalars of the prepass: the public ones into out, sum(omega) and sum(omega z) for the assembly
+// scalars of the prepass: the public ones into out, sum(omega) and sum(omega z) for the assembly.
+// One warp per scalar: lane l sums the partials l, l + 32, ..., then a shuffle tree (fixed order).
 __global__ void cells_scalar_reduce_kernel(const double* __restrict__ scal_part, int count, double* __restrict__ out_scal,
                                            double* __restrict__ extra, int accumulate) {
-  const int s = threadIdx.x;
-  if (s >= PGB_GS_COUNT + 2) return;
+  const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double v = 0.0;
-  for (int c = 0; c < count; ++c) v += scal_part[(int64_t)c * (PGB_GS_COUNT + 2) + s];
+  for (int c = lane; c < count; c += 32) v += scal_part[(int64_t)c * (PGB_GS_COUNT + 2) + s];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane != 0) return;
   if (s < PGB_GS_COUNT) out_scal[s] = accumulate ? out_scal[s] + v : v;
   else extra[s - PGB_GS_COUNT] = v;
 }
@@ -596,16 +748,18 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
   pgb_model* Mm = const_cast<pgb_model*>(M);
   const int n_roles = (int)C.roles.size();
   const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
+  const int64_t np = rows_pad(n);
   double* part = (double*)ws;
   double* sums = part + slots * C.slot_doubles;
   double* scal_part = sums + C.sum_doubles;
   double* extra = scal_part + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2);
-  double* om = extra + 8;
-  double* omz = om + ((n + 1) & ~(int64_t)1);
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    PGB_CUDA(cudaFuncSetAttribute(gram_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemMax - 1024)));
-    attr_set = true;
+  double* om = (double*)(((uintptr_t)(extra + 8) + 127) & ~(uintptr_t)127);
+  double* omz = om + np;
+  double* tq = omz + np;
+  uint8_t* cq = (uint8_t*)(tq + (int64_t)C.n_spl * np);
+  if ((int64_t)((uint8_t*)cq + (int64_t)C.n_spl * np - (uint8_t*)ws) > ws_bytes) {
+    pgb_set_error("pgb_gram_pass: workspace too small");
+    return PGB_EINVAL;
   }
   pgb_model::Timing& tm = Mm->timing;
   if (tm.enabled) {
@@ -619,21 +773,39 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
   }
   const int grid1 = (int)std::min<int64_t>((n + kPreThreads - 1) / kPreThreads, (int64_t)kSMs * 8);
   const size_t pre_smem = ((size_t)((M->m + 1) & ~1) * 8 + (PGB_GS_COUNT + 2) * 32 * 8 + (size_t)M->n_terms * sizeof(DTerm) + 127) & ~(size_t)127;
-  gram_prepass_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, X, n, ld, y, w, beta, om,
-                                                            omz, scal_part);
+  gram_prepass_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, X, n, ld, y, w, beta, np, om,
+                                                            omz, tq, cq, scal_part);
   PGB_CUDA(cudaGetLastError());
   PGB_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * slots * C.slot_doubles, st));
   if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[3], st));
   const int TR = C.tile_rows;
-  const int64_t row_bytes = 8 * (int64_t)M->n_features + 16;
+  const int64_t row_bytes = 9 * (int64_t)C.n_spl + 16;
   int band_tiles = (int)std::max<int64_t>(1, kBandBytes / (row_bytes * TR));
   if (const char* e = getenv("PGB_CELLS_BAND")) band_tiles = std::max(1, atoi(e));
-  gram_cells_kernel<<<C.grid, kCellThreads, C.smem, st>>>(X, ld, n, om, omz, C.d_roles, n_roles, TR, band_tiles, C.slots_per_cta,
-                                                           part);
+#define PGB_CELLS_LAUNCH(TH, OCC)                                                                                        \
+  do {                                                                                                                   \
+    static thread_local bool attr_set = false;                                                                           \
+    if (!attr_set) {                                                                                                     \
+      PGB_CUDA(cudaFuncSetAttribute(gram_cells_kernel<TH, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                    (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024)));                             \
+      attr_set = true;                                                                                                   \
+    }                                                                                                                    \
+    gram_cells_kernel<TH, OCC><<<C.grid, TH, C.smem, st>>>(n, np, om, omz, tq, cq, C.d_roles, n_roles, TR, band_tiles,   \
+                                                           C.slots_per_cta, part);                                       \
+  } while (0)
+  switch (C.threads) {
+    case 256: PGB_CELLS_LAUNCH(256, 2); break;
+    case 320: PGB_CELLS_LAUNCH(320, 2); break;
+    case 384: PGB_CELLS_LAUNCH(384, 1); break;
+    default: PGB_CELLS_LAUNCH(512, 1); break;
+  }
+#undef PGB_CELLS_LAUNCH
   PGB_CUDA(cudaGetLastError());
   if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[4], st));
-  cells_slot_reduce_kernel<<<n_roles, kCellThreads, 0, st>>>(part, C.d_roles, C.d_pairs, n_roles, C.grid, C.slots_per_cta, sums);
-  cells_scalar_reduce_kernel<<<1, 32, 0, st>>>(scal_part, grid1, out + (int64_t)M->m * M->m + M->m, extra, accumulate);
+  cells_slot_reduce_kernel<<<dim3(n_roles, kCellAcc), C.threads, 0, st>>>(part, C.d_roles, C.d_pairs, n_roles, C.grid, C.slots_per_cta,
+                                                                        C.threads, sums);
+  cells_scalar_reduce_kernel<<<1, 32 * (PGB_GS_COUNT + 2), 0, st>>>(scal_part, grid1, out + (int64_t)M->m * M->m + M->m, extra,
+                                                                     accumulate);
   const int64_t entries = (int64_t)M->m * (M->m + 1);
   cells_assemble_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, st>>>(sums, extra, C.d_pairs, C.d_coef_term, C.d_pair_of,
                                                                           M->n_terms, M->m, C.icpt_coef, out, accumulate);
@@ -644,6 +816,5 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
     tm.pending = true;
     tm.n_chunks = 1;
   }
-  (void)ws_bytes;
   return PGB_OK;
 }

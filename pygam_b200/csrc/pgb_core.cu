@@ -531,7 +531,7 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
   PGB_LAUNCHED(1);
   PGB_CUDA(cudaGetLastError());
   if (scalars) {
-    scalar_reduce_kernel<<<1, 32, 0, st>>>((const double*)ws, grid, PGB_SS_COUNT, scalars, 0);
+    scalar_reduce_kernel<<<1, 32 * PGB_SS_COUNT, 0, st>>>((const double*)ws, grid, PGB_SS_COUNT, scalars, 0);
     PGB_LAUNCHED(1);
     PGB_CUDA(cudaGetLastError());
   }

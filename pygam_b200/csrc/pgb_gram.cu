@@ -1022,7 +1022,7 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
                                                                               c > 0 ? 1 : 0, partials);
     PGB_CUDA(cudaGetLastError());
     if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[4 + 3 * c], st));
-    scalar_reduce_kernel<<<1, 32, 0, st>>>(scal_part, grid1, PGB_GS_COUNT, out + (int64_t)M->m * M->m + M->m,
+    scalar_reduce_kernel<<<1, 32 * PGB_GS_COUNT, 0, st>>>(scal_part, grid1, PGB_GS_COUNT, out + (int64_t)M->m * M->m + M->m,
                                            (accumulate || c > 0) ? 1 : 0);
     pgb_count_launch(3);
   }

@@ -97,7 +97,9 @@ struct DRole {
 struct DCellRole {
   DMarg a, b;                       // marginals of the row term and of the column term (b = a on the diagonal)
   int32_t diag, ncell, ncb, key0;   // cells key0 .. key0 + ncell - 1 of the pair; cell = ci * ncb + cj
-  int32_t pair, c_lo, c_hi, pad;    // CTAs c_lo .. c_hi can serve this role
+  int32_t pair, c_lo, c_hi;         // CTAs c_lo .. c_hi can serve this role
+  uint32_t hmul;                    // diagonal role: row r of a tile goes to split (r * hmul) >> 16
+  int32_t sa, sb, pad[2];           // spline index (column of the cell records) of the two terms
 };
 struct DCellPair {
   int32_t ti, tj;                   // terms; tj = -1: diagonal pair of ti
@@ -116,7 +118,7 @@ struct pgb_model {
     DCellPair* d_pairs = nullptr;
     int32_t* d_coef_term = nullptr;
     int32_t* d_pair_of = nullptr;
-    int32_t tile_rows = 0, grid = 0, slots_per_cta = 0, icpt_coef = -1;
+    int32_t tile_rows = 0, grid = 0, slots_per_cta = 0, icpt_coef = -1, n_spl = 0, occ = 1, threads = 512;
     size_t smem = 0;
     int64_t sum_doubles = 0, slot_doubles = 0;
   } cells;

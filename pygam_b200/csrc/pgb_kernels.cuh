@@ -26,14 +26,17 @@ __device__ __forceinline__ void block_reduce_store(double (&acc)[S], double* red
   }
 }
 
-// sum `count` partial vectors of length S in a fixed order: out[s] (+)= sum_c part[c*S+s]
+// sum `count` partial vectors of length S in a fixed order: out[s] (+)= sum_c part[c*S+s].  One warp per
+// scalar (launch with 32 * S threads): lane l sums the partials l, l + 32, ..., then a shuffle tree.
 static __global__ void scalar_reduce_kernel(const double* __restrict__ part, int count, int S,
                                             double* __restrict__ out, int accumulate) {
-  const int s = threadIdx.x;
+  const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (s >= S) return;
-  double v = accumulate ? out[s] : 0.0;
-  for (int c = 0; c < count; ++c) v += part[(int64_t)c * S + s];
-  out[s] = v;
+  double v = 0.0;
+  for (int c = lane; c < count; c += 32) v += part[(int64_t)c * S + s];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) out[s] = accumulate ? out[s] + v : v;
 }
 
 struct EmitLp {
