@@ -323,10 +323,11 @@ gram_prepass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Famil
         cell = min((int)s, mg.nint - 1);
         t = s - (double)cell;
         cubic_bspline(t, v[0], v[1], v[2], v[3]);
+        t -= 0.5;  // the record holds the centred coordinate, in [-0.5, 0.5]
       } else {
         extrap_basis(mg, u, v);
         cell = (u < 0.0 ? 0 : mg.nint - 1) | 0x80;
-        t = u;
+        t = (u < 0.0) ? u - 1.0 : u + 1.0;  // outside the knots: the normalised coordinate, moved out of [-0.5, 0.5]
       }
       const double* bt = s_beta + T.coef_offset + (cell & 0x7f);
       lp = fma(v[0], bt[0], lp);
@@ -366,21 +367,42 @@ gram_prepass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Famil
 // ----------------------------------------------------------------------------------------
 // kernel 2: cells
 // ----------------------------------------------------------------------------------------
-// the four basis values of a row outside the edge knots (rare: custom edge_knots narrower than the data)
-__device__ __noinline__ void cell_basis_outside(const DMarg* mg, double u, double* v) { extrap_basis(*mg, u, v); }
+// The four cubic B-splines of an interval are polynomials of the centred local coordinate s = t - 1/2:
+// b_a(s) = sum_p kM[a][p] s^p.  The cells kernel therefore sums MOMENTS omega s_i^p s_j^q (p, q = 0..3) --
+// 2 + 2 + 3 multiplies and 16 FMAs per (row, pair) instead of two basis evaluations (24) + 4 + 16 -- and
+// cells_transform_kernel maps the 16 moment sums of a cell to the 16 entries of G: B = M S M^T.
+__constant__ double kM[4][4] = {{1.0 / 48.0, -1.0 / 8.0, 1.0 / 4.0, -1.0 / 6.0},
+                                {23.0 / 48.0, -5.0 / 8.0, -1.0 / 4.0, 1.0 / 2.0},
+                                {23.0 / 48.0, 5.0 / 8.0, -1.0 / 4.0, -1.0 / 2.0},
+                                {1.0 / 48.0, 1.0 / 8.0, 1.0 / 4.0, 1.0 / 6.0}};
+
+// A row outside the edge knots (rare: custom edge_knots narrower than the data) has four basis values v
+// that are no cubic of s; its "powers" are mu = M^-1 v, so that M mu = v and the same sums stay valid.
+__device__ __noinline__ void cell_powers_outside(const DMarg* mg, double enc, double* mu) {
+  const double u = enc < 0.0 ? enc + 1.0 : enc - 1.0;
+  double v[PGB_MAXV];
+  extrap_basis(*mg, u, v);
+  mu[0] = v[0] + v[1] + v[2] + v[3];
+  mu[1] = 1.5 * (v[3] - v[0]) + 0.5 * (v[2] - v[1]);
+  mu[2] = (23.0 / 12.0) * (v[0] + v[3]) - (1.0 / 12.0) * (v[1] + v[2]);
+  mu[3] = 1.875 * (v[3] - v[0]) + 0.375 * (v[1] - v[2]);
+}
 
 template <bool CAREFUL>
-__device__ __forceinline__ void cell_basis(const DMarg* mg, double t, double& b0, double& b1, double& b2, double& b3) {
-  if (CAREFUL && (t < 0.0 || t > 1.0)) {
-    double v[PGB_MAXV];
-    cell_basis_outside(mg, t, v);
-    b0 = v[0]; b1 = v[1]; b2 = v[2]; b3 = v[3];
+__device__ __forceinline__ void cell_powers(const DMarg* mg, double s, double& p0, double& p1, double& p2, double& p3) {
+  if (CAREFUL && fabs(s) > 0.75) {
+    double mu[4];
+    cell_powers_outside(mg, s, mu);
+    p0 = mu[0]; p1 = mu[1]; p2 = mu[2]; p3 = mu[3];
   } else {
-    cubic_bspline(t, b0, b1, b2, b3);
+    p0 = 1.0;
+    p1 = s;
+    p2 = s * s;
+    p3 = p2 * s;
   }
 }
 
-// the rows of one cell of a pair (i, j): 16 sums
+// the rows of one cell of a pair (i, j): 16 moment sums, acc[4 p + q] += omega s_i^p s_j^q
 template <bool CAREFUL>
 __device__ __forceinline__ void cell_rows_pair(const DCellRole* R, const uint16_t* __restrict__ perm, int c,
                                                const double* __restrict__ ta, const double* __restrict__ tb,
@@ -390,18 +412,25 @@ __device__ __forceinline__ void cell_rows_pair(const DCellRole* R, const uint16_
     const int r = perm[s];
     const double ww = wv[r];
     double a0, a1, a2, a3, b0, b1, b2, b3;
-    cell_basis<CAREFUL>(&R->a, ta[r], a0, a1, a2, a3);
-    cell_basis<CAREFUL>(&R->b, tb[r], b0, b1, b2, b3);
-    a0 *= ww; a1 *= ww; a2 *= ww; a3 *= ww;
-    acc[0] = fma(a0, b0, acc[0]); acc[1] = fma(a0, b1, acc[1]); acc[2] = fma(a0, b2, acc[2]); acc[3] = fma(a0, b3, acc[3]);
-    acc[4] = fma(a1, b0, acc[4]); acc[5] = fma(a1, b1, acc[5]); acc[6] = fma(a1, b2, acc[6]); acc[7] = fma(a1, b3, acc[7]);
-    acc[8] = fma(a2, b0, acc[8]); acc[9] = fma(a2, b1, acc[9]); acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
-    acc[12] = fma(a3, b0, acc[12]); acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
+    cell_powers<CAREFUL>(&R->a, ta[r], a0, a1, a2, a3);
+    cell_powers<CAREFUL>(&R->b, tb[r], b0, b1, b2, b3);
+    a1 *= ww; a2 *= ww; a3 *= ww;
+    if (CAREFUL) {
+      a0 *= ww;
+      acc[0] = fma(a0, b0, acc[0]); acc[4] = fma(a1, b0, acc[4]); acc[8] = fma(a2, b0, acc[8]); acc[12] = fma(a3, b0, acc[12]);
+    } else {  // s^0 = 1
+      a0 = ww;
+      acc[0] += a0; acc[4] += a1; acc[8] += a2; acc[12] += a3;
+    }
+    acc[1] = fma(a0, b1, acc[1]); acc[2] = fma(a0, b2, acc[2]); acc[3] = fma(a0, b3, acc[3]);
+    acc[5] = fma(a1, b1, acc[5]); acc[6] = fma(a1, b2, acc[6]); acc[7] = fma(a1, b3, acc[7]);
+    acc[9] = fma(a2, b1, acc[9]); acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
+    acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
   }
 }
 
-// the rows of one cell of a diagonal block: 10 sums of the packed upper triangle, the intercept
-// column (omega b), the right-hand side (omega z b)
+// the rows of one cell of a diagonal block: the 10 moment sums of the packed upper triangle (p <= q), the
+// intercept column (omega s^p), the right-hand side (omega z s^p)
 template <bool CAREFUL>
 __device__ __forceinline__ void cell_rows_diag(const DCellRole* R, const uint16_t* __restrict__ perm, int c,
                                                const double* __restrict__ ta, const double* __restrict__ wz,
@@ -411,7 +440,7 @@ __device__ __forceinline__ void cell_rows_diag(const DCellRole* R, const uint16_
     const int r = perm[s];
     const double ww = wv[r], z = wz[r];
     double a0, a1, a2, a3;
-    cell_basis<CAREFUL>(&R->a, ta[r], a0, a1, a2, a3);
+    cell_powers<CAREFUL>(&R->a, ta[r], a0, a1, a2, a3);
     const double v0 = a0 * ww, v1 = a1 * ww, v2 = a2 * ww, v3 = a3 * ww;
     acc[0] = fma(v0, a0, acc[0]); acc[1] = fma(v0, a1, acc[1]); acc[2] = fma(v0, a2, acc[2]); acc[3] = fma(v0, a3, acc[3]);
     acc[4] = fma(v1, a1, acc[4]); acc[5] = fma(v1, a2, acc[5]); acc[6] = fma(v1, a3, acc[6]);
@@ -664,6 +693,57 @@ __global__ void cells_slot_reduce_kernel(const double* __restrict__ part, const 
   }
 }
 
+// moment sums of a cell -> the entries of G the cell touches, in place: B = M S M^T (pair), the packed
+// upper triangle of M S M^T with S symmetric (diagonal block), M x for the intercept column and the rhs
+__global__ void cells_transform_kernel(const DCellPair* __restrict__ pairs, int n_pairs, double* __restrict__ sums) {
+  const DCellPair P = pairs[blockIdx.y];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.ncells) return;
+  double* S = sums + P.sum_off + k;
+  const int64_t st = P.ncells;
+  double x[4][4], y[4][4];
+  if (P.tj >= 0) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[p][q] = S[(4 * p + q) * st];
+  } else {
+    int e = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = p; q < 4; ++q) { x[p][q] = S[e * st]; x[q][p] = x[p][q]; ++e; }
+  }
+  // y = M x
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) y[a][q] = kM[a][0] * x[0][q] + kM[a][1] * x[1][q] + kM[a][2] * x[2][q] + kM[a][3] * x[3][q];
+  // x = y M^T
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) x[a][b] = y[a][0] * kM[b][0] + y[a][1] * kM[b][1] + y[a][2] * kM[b][2] + y[a][3] * kM[b][3];
+  if (P.tj >= 0) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) S[(4 * a + b) * st] = x[a][b];
+  } else {
+    int e = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = a; b < 4; ++b) S[(e++) * st] = x[a][b];
+#pragma unroll
+    for (int g = 10; g <= 14; g += 4) {
+      const double v0 = S[g * st], v1 = S[(g + 1) * st], v2 = S[(g + 2) * st], v3 = S[(g + 3) * st];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) S[(g + a) * st] = kM[a][0] * v0 + kM[a][1] * v1 + kM[a][2] * v2 + kM[a][3] * v3;
+    }
+  }
+}
+
 // scalars of the prepass: the public ones into out, sum(omega) and sum(omega z) for the assembly.
 // One warp per scalar: lane l sums the partials l, l + 32, ..., then a shuffle tree (fixed order).
 __global__ void cells_scalar_reduce_kernel(const double* __restrict__ scal_part, int count, double* __restrict__ out_scal,
@@ -804,13 +884,18 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
   if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[4], st));
   cells_slot_reduce_kernel<<<dim3(n_roles, kCellAcc), C.threads, 0, st>>>(part, C.d_roles, C.d_pairs, n_roles, C.grid, C.slots_per_cta,
                                                                         C.threads, sums);
+  {
+    int max_cells = 1;
+    for (const DCellPair& P : C.pairs) max_cells = std::max(max_cells, P.ncells);
+    cells_transform_kernel<<<dim3((max_cells + 127) / 128, (unsigned)C.pairs.size()), 128, 0, st>>>(C.d_pairs, (int)C.pairs.size(), sums);
+  }
   cells_scalar_reduce_kernel<<<1, 32 * (PGB_GS_COUNT + 2), 0, st>>>(scal_part, grid1, out + (int64_t)M->m * M->m + M->m, extra,
                                                                      accumulate);
   const int64_t entries = (int64_t)M->m * (M->m + 1);
   cells_assemble_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, st>>>(sums, extra, C.d_pairs, C.d_coef_term, C.d_pair_of,
                                                                           M->n_terms, M->m, C.icpt_coef, out, accumulate);
   PGB_CUDA(cudaGetLastError());
-  pgb_count_launch(5);
+  pgb_count_launch(6);
   if (tm.enabled) {
     PGB_CUDA(cudaEventRecord(tm.chunk_ev[1], st));
     tm.pending = true;
