@@ -33,14 +33,15 @@
 #include "pgb_internal.h"
 #include "pgb_kernels.cuh"
 
-static const int kCellMaxThreads = 512;   // most threads of a cells CTA = most cells a role owns
 static const int kCellAcc = 18;           // sums per cell (16 for a pair; 10 + 4 + 4 for a diagonal role)
 static const int kPreThreads = 256;
 static const int64_t kBandBytes = 32ll << 20;  // column bytes of a band of rows (stays in the L2)
 
 // tile: t_i, t_j (or omega z), omega; sorted row index; the two interval bytes (later the 16-bit cell key) per row;
 // 16-bit counters per (warp, cell)
-static size_t cells_smem(int tile, int threads) { return (size_t)tile * (24 + 2 + 2) + (size_t)(threads / 32) * threads * 2 + 64; }
+// counters: per cell one record of W words = 2 W 16-bit counters, one per warp (W = 4 up to 8 warps, else 8)
+static int cells_counter_words(int threads) { return threads / 32 <= 8 ? 4 : 8; }
+static size_t cells_smem(int tile, int threads) { return (size_t)tile * (24 + 2 + 2) + (size_t)threads * cells_counter_words(threads) * 4 + 64; }
 
 // ----------------------------------------------------------------------------------------
 // plan
@@ -494,6 +495,8 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
                   const double* __restrict__ tq, const uint8_t* __restrict__ cq, const DCellRole* __restrict__ roles,
                   int n_roles, int TR, int band_tiles, int slots_per_cta, double* __restrict__ part) {
   constexpr int kCellThreads = THREADS, kCellWarps = THREADS / 32;
+  constexpr int W = (kCellWarps <= 8) ? 4 : 8;  // counter words per cell
+  constexpr int SH = (W == 8) ? 2 : 3;          // a cell's record starts in bank group (cell & (32 / W - 1))
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ DCellRole R;
   __shared__ int s_wtot[32];
@@ -504,11 +507,12 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
   double* tb = ta + TR;                               // t of the column term (diagonal role: omega z)
   double* wv = tb + TR;                               // omega
   uint16_t* perm = reinterpret_cast<uint16_t*>(wv + TR);
-  uint32_t* wh32 = reinterpret_cast<uint32_t*>(perm + TR);  // [warp][cell / 2]
-  uint16_t* wh16 = reinterpret_cast<uint16_t*>(wh32);       // [warp][cell]
+  // 16-bit row counters, one per (cell, warp): cell k's record is W words; warp q's counter is half (q & 1)
+  // of word ((q >> 1) + (k >> SH)) & (W - 1) -- the rotation spreads a warp's atomics over all 32 banks
+  uint32_t* wh32 = reinterpret_cast<uint32_t*>(perm + TR);
   // interval bytes of the two terms; pass 1 overwrites them with the 16-bit cell keys of the rows (a thread's
   // four rows: keys 0, 1 in its word of ca, keys 2, 3 in its word of cb)
-  uint8_t* ca = reinterpret_cast<uint8_t*>(wh32 + kCellWarps * (kCellThreads / 2));
+  uint8_t* ca = reinterpret_cast<uint8_t*>(wh32 + kCellThreads * W);
   uint8_t* cb = ca + TR;
   const uint32_t bar_c = smem_addr(&s_bar[0]), bar_b = smem_addr(&s_bar[1]);
   if (tid == 0) {
@@ -570,7 +574,11 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
       bulk_g2s(smem_addr(wv), om + row0, cnt16 * 8u, bar_b);
       s_careful = 0;
     }
-    for (int i = tid; i < kCellWarps * (kCellThreads / 2); i += kCellThreads) wh32[i] = 0u;
+    {
+      uint4* rec = reinterpret_cast<uint4*>(wh32 + tid * W);
+      rec[0] = make_uint4(0u, 0u, 0u, 0u);
+      if (W == 8) rec[1] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
     const int NC = R.ncell, diag = R.diag, ncb = R.ncb, key0 = R.key0;
     mbar_wait(bar_c, phase);
@@ -579,7 +587,7 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
     //      (a warp's conflicting lanes are resolved by the hardware in a fixed order, and no other warp
     //      touches the word: the sorted order, hence the fp64 sums, are reproducible run to run).
     //      Rows of other roles of the same pair get key 0xffff.  A thread takes four consecutive rows.
-    uint32_t* my_wh = wh32 + warp * (kCellThreads / 2);
+    const uint32_t wq = (uint32_t)warp >> 1, winc = (warp & 1) ? 0x10000u : 1u;
     const uint32_t hmul = R.hmul;
     int careful = 0;
     for (int r4 = 4 * tid; r4 < cnt; r4 += 4 * kCellThreads) {
@@ -594,7 +602,7 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
         const int k = ci * ncb + cj - key0;
         const bool mine = ((unsigned)k < (unsigned)NC) && (r4 + q < cnt);
         kk[q] = mine ? (uint32_t)k : 0xffffu;
-        if (mine) atomicAdd(&my_wh[k >> 1], (k & 1) ? 0x10000u : 1u);
+        if (mine) atomicAdd(&wh32[k * W + ((wq + ((uint32_t)k >> SH)) & (W - 1))], winc);
       }
       *reinterpret_cast<uint32_t*>(ca + r4) = kk[0] | (kk[1] << 16);
       *reinterpret_cast<uint32_t*>(cb + r4) = kk[2] | (kk[3] << 16);
@@ -602,9 +610,19 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
     if (careful) s_careful = 1;
     __syncthreads();
     // ---- thread k owns cell k: its rows per warp, exclusive scan over the cells, start offsets back
+    uint32_t cw[W];
+    {
+      const uint4* rec = reinterpret_cast<const uint4*>(wh32 + tid * W);
+      const uint4 r0 = rec[0];
+      cw[0] = r0.x; cw[1] = r0.y; cw[2] = r0.z; cw[3] = r0.w;
+      if (W == 8) {
+        const uint4 r1 = rec[1];
+        cw[4 % W] = r1.x; cw[5 % W] = r1.y; cw[6 % W] = r1.z; cw[7 % W] = r1.w;
+      }
+    }
     int c = 0;
 #pragma unroll
-    for (int q = 0; q < kCellWarps; ++q) c += wh16[q * kCellThreads + tid];
+    for (int q = 0; q < W; ++q) c += (int)((cw[q] & 0xffffu) + (cw[q] >> 16));
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -626,13 +644,17 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
     __syncthreads();
     const int start = incl - c + s_wtot[warp];
     {
-      int run = start;
+      // the counters become the start offsets of every (cell, warp) run, in storage order
+      uint32_t run = (uint32_t)start;
 #pragma unroll
-      for (int q = 0; q < kCellWarps; ++q) {
-        const int cq2 = wh16[q * kCellThreads + tid];
-        wh16[q * kCellThreads + tid] = (uint16_t)run;
-        run += cq2;
+      for (int q = 0; q < W; ++q) {
+        const uint32_t lo = cw[q] & 0xffffu, hi = cw[q] >> 16;
+        cw[q] = run | ((run + lo) << 16);
+        run += lo + hi;
       }
+      uint4* rec = reinterpret_cast<uint4*>(wh32 + tid * W);
+      rec[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+      if (W == 8) rec[1] = make_uint4(cw[4 % W], cw[5 % W], cw[6 % W], cw[7 % W]);
     }
     __syncthreads();
     for (int r4 = 4 * tid; r4 < cnt; r4 += 4 * kCellThreads) {
@@ -641,8 +663,8 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
       for (int q = 0; q < 4; ++q) {
         const uint32_t k = (((q & 2) ? k23 : k01) >> (16 * (q & 1))) & 0xffffu;
         if (k != 0xffffu) {
-          const uint32_t old = atomicAdd(&my_wh[k >> 1], (k & 1) ? 0x10000u : 1u);
-          perm[(k & 1) ? (old >> 16) : (old & 0xffffu)] = (uint16_t)(r4 + q);
+          const uint32_t old = atomicAdd(&wh32[k * W + ((wq + (k >> SH)) & (W - 1))], winc);
+          perm[(warp & 1) ? (old >> 16) : (old & 0xffffu)] = (uint16_t)(r4 + q);
         }
       }
     }

@@ -269,6 +269,7 @@ __device__ void transpose_inplace(double* B, int m) {
 
 #define PGB_SOLVE_WANT_EDOF PGB_SOLVE_EDOF
 #define PGB_SOLVE_WANT_COV PGB_SOLVE_COV
+#define PGB_SOLVE_FACTORED 0x10000  // internal: the multi-CTA front (below) left L in A, [Q^T G Q]_0 in B, its status after B
 
 __global__ void __launch_bounds__(kSolveThreads)
 solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__ r_all, int share_gram,
@@ -298,14 +299,15 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   double* Y = P + (size_t)m * kLD;            // solved block of the column solves, kNB x wc
   double* A = use_smem ? (Y + (size_t)kNB * wc) : (ws_all + (size_t)sys * 2 * mm);
   double* B = A + mm;
-  if (threadIdx.x == 0) *flag = 0;
+  const bool factored = (flags & PGB_SOLVE_FACTORED) != 0;
+  if (threadIdx.x == 0) *flag = factored ? reinterpret_cast<const int*>(B + mm)[0] : 0;
   __syncthreads();
 
   // ---- A = Q^T E_rest Q + [Q^T E_null Q]_0 + [Q^T G Q]_0, where [.]_0 zeroes the first p rows and
   //      columns: both E_null and G annihilate the null vectors in exact arithmetic.  B ends up
   //      holding [Q^T G Q]_0 for the edof / cov step. ----
   int bad = 0;
-  for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) {
+  for (int e = threadIdx.x; e < (factored ? 0 : (int)mm); e += blockDim.x) {
     const double pe = EtE[e];
     if (!isfinite(pe)) bad = 1;
     A[e] = pe;
@@ -323,7 +325,7 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
     if (!prepared) sym_reflect(A, m, v, tau[q], w, red);
     vec_reflect(x, m, v, tau[q], red);
   }
-  for (int pass = ((Enull && !prepared) ? 0 : 1); pass < 2; ++pass) {
+  for (int pass = factored ? 2 : ((Enull && !prepared) ? 0 : 1); pass < 2; ++pass) {
     const double* src = (pass == 0) ? Enull : G;
     bad = 0;
     for (int e = threadIdx.x; e < (int)mm; e += blockDim.x) {
@@ -350,7 +352,7 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   if (*flag == 0) {
     for (int i = threadIdx.x; i < p; i += blockDim.x) x[i] = 0.0;
     __syncthreads();
-    cholesky_lower(A, m, D, P, flag);
+    if (!factored) cholesky_lower(A, m, D, P, flag);
   }
   __syncthreads();
   const int info = *flag;
@@ -416,6 +418,190 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   }
 }
 
+// ----------------------------------------------------------------------------------------
+// Multi-CTA front of a single large system (the PIRLS iteration of config 2 / 3: m = 251 / 601, two
+// m x m matrices do not fit one SM's shared memory).  The single-CTA kernel above then works out of the
+// L2 at one SM's latency; here every O(m^2 p) and O(m^3) sweep is a grid-wide kernel on the same stream:
+//   B = G, A = A0                                   (front_init_kernel)
+//   B <- H_q B H_q, q = 0 .. p-1                    (front_matvec_kernel + front_rank2_kernel per reflector)
+//   A += [B]_0                                      (front_add_kernel)
+//   A = L L^T, 32-wide block columns                (front_chol_panel_kernel + front_chol_trail_kernel per block)
+// and the single-CTA kernel finishes (right-hand side, triangular solves, diff; edof / cov when asked).
+// ----------------------------------------------------------------------------------------
+static const int kFrontThreads = 256;
+
+__global__ void front_init_kernel(int m, const double* __restrict__ G, const double* __restrict__ A0, double* __restrict__ A,
+                                  double* __restrict__ B, int* __restrict__ status) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m * m) return;
+  const double g = G[e], a = A0[e];
+  if (!isfinite(g) || !isfinite(a)) *status = 2;
+  B[e] = g;
+  A[e] = a;
+}
+
+// w = B v, one warp per row
+__global__ void front_matvec_kernel(int m, const double* __restrict__ B, const double* __restrict__ v, double* __restrict__ w) {
+  const int lane = threadIdx.x & 31, i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= m) return;
+  const double* row = B + (size_t)i * m;
+  double s = 0.0;
+  for (int j = lane; j < m; j += 32) s = fma(row[j], v[j], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) w[i] = s;
+}
+
+// B <- B - v w'^T - w' v^T with w' = tau w - (tau^2 (v^T w) / 2) v  (the update of sym_reflect)
+__global__ void front_rank2_kernel(int m, double* __restrict__ B, const double* __restrict__ v, const double* __restrict__ w,
+                                   const double* __restrict__ tau_q) {
+  __shared__ double red[32];
+  double part = 0.0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) part = fma(v[i], w[i], part);
+  const double alpha = block_sum(part, red);
+  const double tau = *tau_q;
+  const double c = 0.5 * tau * tau * alpha;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m * m; e += gridDim.x * blockDim.x) {
+    const int i = e / m, j = e - i * m;
+    const double vi = v[i], vj = v[j];
+    const double wi = tau * w[i] - c * vi, wj = tau * w[j] - c * vj;
+    B[e] -= vi * wj + wi * vj;
+  }
+}
+
+// A += [B]_0: the first p rows and columns of B (the null directions) are exact zeros
+__global__ void front_add_kernel(int m, int p, double* __restrict__ A, double* __restrict__ B) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m * m) return;
+  const int i = e / m, j = e - i * m;
+  double g = B[e];
+  if (i < p || j < p) { g = 0.0; B[e] = 0.0; }
+  A[e] += g;
+}
+
+// block column k0: every CTA factors the diagonal block (redundantly, one warp) and solves its slice of
+// panel rows, L21 = A21 L11^-T; CTA 0 writes the diagonal block back
+__global__ void __launch_bounds__(kFrontThreads)
+front_chol_panel_kernel(int m, int k0, double* __restrict__ A, int* __restrict__ status) {
+  __shared__ double D[kNB * kLD];
+  __shared__ int bad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (*status != 0) return;
+  const int kb = min(kNB, m - k0);
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < kb * kb; e += blockDim.x) {
+    const int i = e / kb, j = e - i * kb;
+    D[i * kLD + j] = A[(size_t)(k0 + i) * m + k0 + j];
+  }
+  __syncthreads();
+  if (warp == 0) {  // the unblocked factorisation of cholesky_lower: lane = row
+    for (int k = 0; k < kb; ++k) {
+      const double akk = D[k * kLD + k];
+      if (!(akk > 0.0) || !isfinite(akk)) {
+        if (lane == 0) bad = 1;
+        break;
+      }
+      const double d = sqrt(akk), inv = 1.0 / d;
+      __syncwarp();
+      if (lane >= k && lane < kb) D[lane * kLD + k] = (lane == k) ? d : D[lane * kLD + k] * inv;
+      __syncwarp();
+      if (lane > k && lane < kb) {
+        const double lik = D[lane * kLD + k];
+        for (int j = k + 1; j <= lane; ++j) D[lane * kLD + j] = fma(-lik, D[j * kLD + k], D[lane * kLD + j]);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (bad) {
+    if (blockIdx.x == 0 && tid == 0) *status = 1;
+    return;
+  }
+  if (blockIdx.x == 0)
+    for (int e = tid; e < kb * kb; e += blockDim.x) {
+      const int i = e / kb, j = e - i * kb;
+      if (j <= i) A[(size_t)(k0 + i) * m + k0 + j] = D[i * kLD + j];
+    }
+  const int rows = m - k0 - kb;
+  const int ii = blockIdx.x * blockDim.x + tid;
+  if (ii < rows) {
+    double* arow = A + (size_t)(k0 + kb + ii) * m + k0;
+    double pr[kNB];
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) pr[c] = (c < kb) ? arow[c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) {
+      if (c < kb) {
+        double sacc = pr[c];
+#pragma unroll
+        for (int d = 0; d < c; ++d) sacc = fma(-pr[d], D[c * kLD + d], sacc);
+        sacc /= D[c * kLD + c];
+        pr[c] = sacc;
+        arow[c] = sacc;
+      }
+    }
+  }
+}
+
+// trailing update of the lower triangle, A22 -= L21 L21^T, one 32 x 32 tile per CTA
+__global__ void __launch_bounds__(kFrontThreads)
+front_chol_trail_kernel(int m, int k0, double* __restrict__ A, const int* __restrict__ status) {
+  __shared__ double Pi[kNB * kLD], Pj[kNB * kLD];
+  if (*status != 0) return;
+  const int kb = min(kNB, m - k0), base = k0 + kb, rows = m - base;
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (tj > ti) return;
+  const int i0 = ti * kNB, j0 = tj * kNB;
+  for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
+    const int r = e / kNB, c = e - r * kNB;
+    Pi[r * kLD + c] = (i0 + r < rows && c < kb) ? A[(size_t)(base + i0 + r) * m + k0 + c] : 0.0;
+    Pj[r * kLD + c] = (j0 + r < rows && c < kb) ? A[(size_t)(base + j0 + r) * m + k0 + c] : 0.0;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
+    const int r = e / kNB, c = e - r * kNB;
+    const int gi = i0 + r, gj = j0 + c;
+    if (gi < rows && gj <= gi) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int k = 0; k < kNB; ++k) sacc = fma(Pi[r * kLD + k], Pj[c * kLD + k], sacc);
+      A[(size_t)(base + gi) * m + base + gj] -= sacc;
+    }
+  }
+}
+
+static int solve_front(int m, const double* G, const double* A0, const double* hv, const double* tau, int p, double* ws,
+                       cudaStream_t st) {
+  const size_t mm = (size_t)m * m;
+  double* A = ws;
+  double* B = A + mm;
+  int* status = reinterpret_cast<int*>(B + mm);
+  double* w = B + mm + 2;
+  PGB_CUDA(cudaMemsetAsync(status, 0, 8, st));
+  const int eg = (int)((mm + kFrontThreads - 1) / kFrontThreads);
+  front_init_kernel<<<eg, kFrontThreads, 0, st>>>(m, G, A0, A, B, status);
+  const int wpb = kFrontThreads / 32;
+  for (int q = 0; q < p; ++q) {
+    front_matvec_kernel<<<(m + wpb - 1) / wpb, kFrontThreads, 0, st>>>(m, B, hv + (size_t)q * m, w);
+    front_rank2_kernel<<<std::min(eg, 296), kFrontThreads, 0, st>>>(m, B, hv + (size_t)q * m, w, tau + q);
+  }
+  front_add_kernel<<<eg, kFrontThreads, 0, st>>>(m, p, A, B);
+  int launches = 2 + 2 * p + 1;
+  for (int k0 = 0; k0 < m; k0 += kNB) {
+    const int kb = std::min(kNB, m - k0), rows = m - k0 - kb;
+    front_chol_panel_kernel<<<std::max(1, (rows + kFrontThreads - 1) / kFrontThreads), kFrontThreads, 0, st>>>(m, k0, A, status);
+    ++launches;
+    if (rows > 0) {
+      const int nt = (rows + kNB - 1) / kNB;
+      front_chol_trail_kernel<<<dim3(nt, nt), kFrontThreads, 0, st>>>(m, k0, A, status);
+      ++launches;
+    }
+  }
+  pgb_count_launch(launches);
+  PGB_CUDA(cudaGetLastError());
+  return PGB_OK;
+}
+
 // A0 = Q^T E_rest Q + [Q^T E_null Q]_0: the penalty side of the system in the null-space basis.
 // It does not change during a PIRLS loop, so it is computed once per penalty (pgb_solve_prepare)
 // and handed to pgb_solve with PGB_SOLVE_PREPARED.
@@ -475,7 +661,7 @@ static bool solve_fits_smem(int m) { return solve_col_chunk(m, true) >= std::min
 
 extern "C" int64_t pgb_solve_ws_bytes(int32_t m, int32_t nb) {
   if (solve_fits_smem(m)) return 256;
-  return (int64_t)nb * 2 * m * m * 8 + 256;
+  return (int64_t)nb * 2 * m * m * 8 + (int64_t)(m + 4) * 8 + 256;  // A, B; status and one vector of the multi-CTA front
 }
 
 extern "C" int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r, int32_t share_gram,
@@ -498,6 +684,11 @@ extern "C" int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r
   if (!attr_set) {
     PGB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax));
     attr_set = true;
+  }
+  if (!in_smem && nb == 1 && (flags & PGB_SOLVE_PREPARED) && !getenv("PGB_SOLVE_SINGLE_CTA")) {
+    const int rc = solve_front(m, G, EtE, hv, tau, p, (double*)ws, (cudaStream_t)stream);
+    if (rc != PGB_OK) return rc;
+    flags |= PGB_SOLVE_FACTORED;
   }
   solve_kernel<<<nb, kSolveThreads, smem, (cudaStream_t)stream>>>(m, G, r, share_gram, EtE, EtE_null, hv, tau, p, beta_prev,
                                                                   share_prev, out, cov_out, (double*)ws, flags,
