@@ -479,6 +479,26 @@ __global__ void front_add_kernel(int m, int p, double* __restrict__ A, double* _
   A[e] += g;
 }
 
+// Cholesky of one 32 x 32 block by one warp, in registers: lane i holds row i; column k of L is sent
+// around with shuffles.  Returns false when a pivot is not positive (or not finite).
+__device__ __forceinline__ bool chol32_warp(double (&row)[kNB], int lane) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < kNB; ++k) {
+    const double akk = __shfl_sync(0xffffffffu, row[k], k);
+    if (!(akk > 0.0) || !isfinite(akk)) ok = false;
+    const double d = sqrt(akk), inv = 1.0 / d;
+    if (lane == k) row[k] = d;
+    else if (lane > k) row[k] *= inv;
+#pragma unroll
+    for (int j = k + 1; j < kNB; ++j) {
+      const double ljk = __shfl_sync(0xffffffffu, row[k], j);
+      if (lane >= j) row[j] = fma(-row[k], ljk, row[j]);
+    }
+  }
+  return ok;
+}
+
 // block column k0: every CTA factors the diagonal block (redundantly, one warp) and solves its slice of
 // panel rows, L21 = A21 L11^-T; CTA 0 writes the diagonal block back
 __global__ void __launch_bounds__(kFrontThreads)
@@ -488,29 +508,16 @@ front_chol_panel_kernel(int m, int k0, double* __restrict__ A, int* __restrict__
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (*status != 0) return;
   const int kb = min(kNB, m - k0);
-  if (tid == 0) bad = 0;
-  for (int e = tid; e < kb * kb; e += blockDim.x) {
-    const int i = e / kb, j = e - i * kb;
-    D[i * kLD + j] = A[(size_t)(k0 + i) * m + k0 + j];
-  }
-  __syncthreads();
-  if (warp == 0) {  // the unblocked factorisation of cholesky_lower: lane = row
-    for (int k = 0; k < kb; ++k) {
-      const double akk = D[k * kLD + k];
-      if (!(akk > 0.0) || !isfinite(akk)) {
-        if (lane == 0) bad = 1;
-        break;
-      }
-      const double d = sqrt(akk), inv = 1.0 / d;
-      __syncwarp();
-      if (lane >= k && lane < kb) D[lane * kLD + k] = (lane == k) ? d : D[lane * kLD + k] * inv;
-      __syncwarp();
-      if (lane > k && lane < kb) {
-        const double lik = D[lane * kLD + k];
-        for (int j = k + 1; j <= lane; ++j) D[lane * kLD + j] = fma(-lik, D[j * kLD + k], D[lane * kLD + j]);
-      }
-      __syncwarp();
-    }
+  if (warp == 0) {
+    // a short last block is padded with the identity
+    double row[kNB];
+#pragma unroll
+    for (int j = 0; j < kNB; ++j)
+      row[j] = (lane < kb && j < kb) ? ((j <= lane) ? A[(size_t)(k0 + lane) * m + k0 + j] : 0.0) : ((j == lane) ? 1.0 : 0.0);
+    const bool ok = chol32_warp(row, lane);
+    if (lane == 0) bad = ok ? 0 : 1;
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) D[lane * kLD + j] = row[j];
   }
   __syncthreads();
   if (bad) {
@@ -525,21 +532,20 @@ front_chol_panel_kernel(int m, int k0, double* __restrict__ A, int* __restrict__
   const int rows = m - k0 - kb;
   const int ii = blockIdx.x * blockDim.x + tid;
   if (ii < rows) {
+    // row of L21: forward substitution, right-looking (the updates of one step are independent)
     double* arow = A + (size_t)(k0 + kb + ii) * m + k0;
     double pr[kNB];
 #pragma unroll
     for (int c = 0; c < kNB; ++c) pr[c] = (c < kb) ? arow[c] : 0.0;
 #pragma unroll
-    for (int c = 0; c < kNB; ++c) {
-      if (c < kb) {
-        double sacc = pr[c];
+    for (int d = 0; d < kNB; ++d) {
+      pr[d] /= D[d * kLD + d];
 #pragma unroll
-        for (int d = 0; d < c; ++d) sacc = fma(-pr[d], D[c * kLD + d], sacc);
-        sacc /= D[c * kLD + c];
-        pr[c] = sacc;
-        arow[c] = sacc;
-      }
+      for (int c = d + 1; c < kNB; ++c) pr[c] = fma(-pr[d], D[c * kLD + d], pr[c]);
     }
+#pragma unroll
+    for (int c = 0; c < kNB; ++c)
+      if (c < kb) arow[c] = pr[c];
   }
 }
 
