@@ -289,7 +289,12 @@ __device__ __forceinline__ void extrap_basis(const DMarg& mg, double u, double* 
   }
 }
 
-__global__ void __launch_bounds__(kPreThreads, 4)
+struct PreSpl {  // what the prepass needs of one spline term
+  double lo, inv_span, nint_d;
+  int32_t feature, nint, coef_offset, term;
+};
+
+__global__ void __launch_bounds__(kPreThreads, 3)
 gram_prepass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Family fam, int mode,
                     const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
                     const float* __restrict__ w, const double* __restrict__ beta, int64_t np, double* __restrict__ om,
@@ -300,49 +305,68 @@ gram_prepass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Famil
   double* s_beta = reinterpret_cast<double*>(smem_raw);
   double* s_red = s_beta + ((m + 1) & ~1);
   DTerm* s_terms = reinterpret_cast<DTerm*>(s_red + (PGB_GS_COUNT + 2) * 32);
+  PreSpl* s_spl = reinterpret_cast<PreSpl*>(s_terms + n_terms);
+  __shared__ int s_nspl, s_icpt;
   for (int i = tid; i < m; i += blockDim.x) s_beta[i] = (mode == PGB_MODE_IRLS) ? beta[i] : 0.0;
   load_terms_smem(s_terms, g_terms, n_terms);
   __syncthreads();
+  if (tid == 0) {
+    int ns = 0, ic = -1;
+    for (int q = 0; q < n_terms; ++q) {
+      const DTerm& T = s_terms[q];
+      if (T.kind == PGB_TERM_INTERCEPT) { ic = T.coef_offset; continue; }
+      const DMarg& mg = T.marg[0];
+      s_spl[ns++] = PreSpl{mg.lo, mg.inv_span, (double)mg.nint, mg.feature, mg.nint, T.coef_offset, q};
+    }
+    s_nspl = ns;
+    s_icpt = ic;
+  }
+  __syncthreads();
+  const int n_spl = s_nspl;
+  const double icpt_beta = s_icpt >= 0 ? s_beta[s_icpt] : 0.0;
   double sc[PGB_GS_COUNT + 2];
 #pragma unroll
   for (int s = 0; s < PGB_GS_COUNT + 2; ++s) sc[s] = 0.0;
+  constexpr int NX = 8;  // feature columns of a row fetched together: 8 loads in flight per thread
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double lp = 0.0;
-    int sp = 0;
-    for (int q = 0; q < n_terms; ++q) {
-      const DTerm& T = s_terms[q];
-      if (T.kind == PGB_TERM_INTERCEPT) {
-        lp += s_beta[T.coef_offset];
-        continue;
-      }
-      const DMarg& mg = T.marg[0];
-      const double u = (__ldg(X + (int64_t)mg.feature * ld + i) - mg.lo) * mg.inv_span;
-      double v[4], t;
-      int cell;
-      if (u >= 0.0 && u <= 1.0) {  // the arithmetic of eval_term's straight-line cubic
-        const double s = u * (double)mg.nint;
-        cell = min((int)s, mg.nint - 1);
-        t = s - (double)cell;
-        cubic_bspline(t, v[0], v[1], v[2], v[3]);
-        t -= 0.5;  // the record holds the centred coordinate, in [-0.5, 0.5]
-      } else {
-        extrap_basis(mg, u, v);
-        cell = (u < 0.0 ? 0 : mg.nint - 1) | 0x80;
-        t = (u < 0.0) ? u - 1.0 : u + 1.0;  // outside the knots: the normalised coordinate, moved out of [-0.5, 0.5]
-      }
-      const double* bt = s_beta + T.coef_offset + (cell & 0x7f);
-      lp = fma(v[0], bt[0], lp);
-      lp = fma(v[1], bt[1], lp);
-      lp = fma(v[2], bt[2], lp);
-      lp = fma(v[3], bt[3], lp);
-      tq[(int64_t)sp * np + i] = t;
-      cq[(int64_t)sp * np + i] = (uint8_t)cell;
-      ++sp;
-    }
     const double yi = __ldg(y + i);
+    const double winv = weight_inv(w, i);
+    double lp = icpt_beta;
+    for (int base = 0; base < n_spl; base += NX) {
+      double xv[NX];
+#pragma unroll
+      for (int q = 0; q < NX; ++q)
+        if (base + q < n_spl) xv[q] = __ldg(X + (int64_t)s_spl[base + q].feature * ld + i);
+#pragma unroll
+      for (int q = 0; q < NX; ++q) {
+        if (base + q >= n_spl) break;
+        const PreSpl& S = s_spl[base + q];
+        const double u = (xv[q] - S.lo) * S.inv_span;
+        double v[4], t;
+        int cell;
+        if (u >= 0.0 && u <= 1.0) {  // the arithmetic of eval_term's straight-line cubic
+          const double s = u * S.nint_d;
+          cell = min((int)s, S.nint - 1);
+          t = s - (double)cell;
+          cubic_bspline(t, v[0], v[1], v[2], v[3]);
+          t -= 0.5;  // the record holds the centred coordinate, in [-0.5, 0.5]
+        } else {
+          extrap_basis(s_terms[S.term].marg[0], u, v);
+          cell = (u < 0.0 ? 0 : S.nint - 1) | 0x80;
+          t = (u < 0.0) ? u - 1.0 : u + 1.0;  // outside the knots: the normalised coordinate, moved out of [-0.5, 0.5]
+        }
+        const double* bt = s_beta + S.coef_offset + (cell & 0x7f);
+        lp = fma(v[0], bt[0], lp);
+        lp = fma(v[1], bt[1], lp);
+        lp = fma(v[2], bt[2], lp);
+        lp = fma(v[3], bt[3], lp);
+        tq[(int64_t)(base + q) * np + i] = t;
+        cq[(int64_t)(base + q) * np + i] = (uint8_t)cell;
+      }
+    }
     double o, oz;
     if (mode == PGB_MODE_IRLS) {
-      const IrlsRow ir = irls_row(fam, lp, yi, weight_inv(w, i));
+      const IrlsRow ir = irls_row(fam, lp, yi, winv);
       o = ir.omega;
       oz = ir.omega * ir.z;
       if (ir.keep) {
@@ -874,7 +898,7 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
     PGB_CUDA(cudaEventRecord(tm.chunk_ev[2], st));
   }
   const int grid1 = (int)std::min<int64_t>((n + kPreThreads - 1) / kPreThreads, (int64_t)kSMs * 8);
-  const size_t pre_smem = ((size_t)((M->m + 1) & ~1) * 8 + (PGB_GS_COUNT + 2) * 32 * 8 + (size_t)M->n_terms * sizeof(DTerm) + 127) & ~(size_t)127;
+  const size_t pre_smem = ((size_t)((M->m + 1) & ~1) * 8 + (PGB_GS_COUNT + 2) * 32 * 8 + (size_t)M->n_terms * (sizeof(DTerm) + sizeof(PreSpl)) + 127) & ~(size_t)127;
   gram_prepass_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, X, n, ld, y, w, beta, np, om,
                                                             omz, tq, cq, scal_part);
   PGB_CUDA(cudaGetLastError());
