@@ -128,8 +128,9 @@ enum { PGB_GS_NUSED = 0,     /* rows kept by GAM._mask (pygam.py:638-663)       
        PGB_GS_COUNT = 8 };
 
 enum { PGB_MODE_IRLS = 0,    /* weights and working response at beta (pygam.py:764-777)     */
-       PGB_MODE_INIT = 1 };  /* unweighted Gram and X^T link(y') of _initial_estimate
+       PGB_MODE_INIT = 1,    /* unweighted Gram and X^T link(y') of _initial_estimate
                                 (pygam.py:696-710)                                          */
+       PGB_MODE_PLANNED = 0x100 }; /* or-ed into mode: ws holds what pgb_gram_prepare left for this X */
 
 /* The fused pass: evaluates the B-spline / tensor basis row in registers, the link and
  * distribution step, and accumulates G = X^T W^2 X, r = X^T W^2 z.  Replaces
@@ -140,6 +141,13 @@ int64_t pgb_gram_ws_bytes(const pgb_model* model, int64_t n);
 int pgb_gram_pass(const pgb_model* model, int32_t mode, const double* X, int64_t n, int64_t ld,
                   const double* y, const float* w, const double* beta, double* out, void* ws,
                   int64_t ws_bytes, void* stream);
+/* What does not change between the PIRLS iterations of one fit (pygam.py:741 builds the model matrix once,
+ * before the loop): for an all-spline model the knot interval and local coordinate of every (row, term)
+ * and, per term pair and row tile, the order of the rows by knot cell.  Writes them into `ws` (same
+ * workspace and size as pgb_gram_pass); later calls of pgb_gram_pass for the same X, n and ws pass
+ * mode | PGB_MODE_PLANNED and skip the basis search and the in-kernel sort.  No-op for other models. */
+int pgb_gram_prepare(const pgb_model* model, const double* X, int64_t n, int64_t ld, void* ws,
+                     int64_t ws_bytes, void* stream);
 
 /* Time the Gram pass with CUDA events: enable, run pgb_gram_pass, then read the device time (ms) of
  * the records kernel (basis + IRLS step -> row records) and of the accumulation kernel (records ->

@@ -23,6 +23,7 @@ GS_NUSED, GS_DEV, GS_NCORRECT, GS_ZWZ, GS_NROWS, GS_NONFINITE, GS_COUNT = 0, 1, 
  SS_NULL_LOGLIK, SS_NONFINITE) = range(11)
 SS_COUNT = 16
 MODE_IRLS, MODE_INIT = 0, 1
+MODE_PLANNED = 0x100  # or-ed into mode: the workspace holds what pgb_gram_prepare left for this X
 SOLVE_OUT_EXTRA = 8
 SOLVE_EDOF, SOLVE_COV, SOLVE_PREPARED = 1, 2, 4
 
@@ -79,6 +80,7 @@ SYMBOLS = {
     "pgb_model_matrix": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P]),
     "pgb_gram_ws_bytes": (C.c_int64, [_P, C.c_int64]),
     "pgb_gram_pass": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_int64, _P]),
+    "pgb_gram_prepare": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
     "pgb_stats_ws_bytes": (C.c_int64, [_P]),
     "pgb_stats_pass": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_double, C.c_double,
                                  C.c_int32, _P, _P, _P, _P, C.c_int64, _P]),

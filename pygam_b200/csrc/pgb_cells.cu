@@ -262,8 +262,10 @@ extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n) {
   const pgb_model::Cells& C = M->cells;
   const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
   const int64_t np = rows_pad(n);
+  const int64_t ntl = (n + C.tile_rows - 1) / C.tile_rows;
+  const int64_t order = (int64_t)C.roles.size() * ntl * (C.tile_rows + C.threads + 8) * 2;  // sorted rows + cell starts (pgb_gram_prepare)
   return (slots * C.slot_doubles + C.sum_doubles + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2) + 8 + (2 + C.n_spl) * np) * 8 +
-         (int64_t)C.n_spl * np + 1024;
+         (int64_t)C.n_spl * np + order + 2048;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -513,11 +515,16 @@ struct UnitIter {
   }
 };
 
-template <int THREADS, int MINB>
+// EMIT = false: sort the rows of every tile and sum them right away (rows streamed through once: the
+// host-buffer path).  EMIT = true: sort only and write the order -- per (role, tile) the sorted row indices and
+// the start offset of every cell -- for gram_cells_sorted_kernel: the cells of a row do not depend on beta,
+// so a fit sorts its rows once (pgb_gram_prepare) and every PIRLS iteration reuses the order.
+template <int THREADS, int MINB, bool EMIT>
 __global__ void __launch_bounds__(THREADS, MINB)
 gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const double* __restrict__ omz,
                   const double* __restrict__ tq, const uint8_t* __restrict__ cq, const DCellRole* __restrict__ roles,
-                  int n_roles, int TR, int band_tiles, int slots_per_cta, double* __restrict__ part) {
+                  int n_roles, int TR, int band_tiles, int slots_per_cta, double* __restrict__ part,
+                  uint16_t* __restrict__ perm_g, uint16_t* __restrict__ starts_g) {
   constexpr int kCellThreads = THREADS, kCellWarps = THREADS / 32;
   constexpr int W = (kCellWarps <= 8) ? 4 : 8;  // counter words per cell
   constexpr int SH = (W == 8) ? 2 : 3;          // a cell's record starts in bank group (cell & (32 / W - 1))
@@ -571,20 +578,24 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
     const int64_t tile = it.tile();
     if (role != cur_role) {
       // park the sums of the role we leave in its slot, fetch the sums of the one we enter
-      if (cur_role >= 0) {
-        double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * kCellThreads);
+      if (!EMIT) {
+        if (cur_role >= 0) {
+          double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * kCellThreads);
 #pragma unroll
-        for (int e = 0; e < kCellAcc; ++e) dst[e * kCellThreads + tid] = acc[e];
+          for (int e = 0; e < kCellAcc; ++e) dst[e * kCellThreads + tid] = acc[e];
+        }
+        const double* src = my_part + (int64_t)(role - role_lo) * (kCellAcc * kCellThreads);
+#pragma unroll
+        for (int e = 0; e < kCellAcc; ++e) acc[e] = src[e * kCellThreads + tid];
       }
-      const double* src = my_part + (int64_t)(role - role_lo) * (kCellAcc * kCellThreads);
-#pragma unroll
-      for (int e = 0; e < kCellAcc; ++e) acc[e] = src[e * kCellThreads + tid];
       if (tid == 0) R = roles[role];
       cur_role = role;
     }
     const int64_t row0 = tile * TR;
     const int cnt = (int)min((int64_t)TR, n - row0);
-    if (tid == 0) {
+    if (EMIT) {
+      if (tid == 0) s_careful = 0;
+    } else if (tid == 0) {
       // t of both terms and omega: in flight while the rows are being sorted.  The workspace columns are
       // 16-byte aligned and padded to 16 rows: the last tile is rounded up
       const uint32_t cnt16 = (uint32_t)((cnt + 15) & ~15);
@@ -696,10 +707,112 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
     // ---- the interval bytes of the next unit go where the keys were, while this unit's rows are summed
     it.next();
     if (tid == 0 && it.valid()) load_cells(it);
+    if (EMIT) {
+      // the order of this (role, tile): sorted row indices, start of every cell, total, "careful" flag
+      const int64_t ntl = (n + TR - 1) / TR;
+      uint32_t* pg = reinterpret_cast<uint32_t*>(perm_g + ((int64_t)role * ntl + tile) * TR);
+      const uint32_t* ps = reinterpret_cast<const uint32_t*>(perm);
+      for (int i = tid; i < (cnt + 1) / 2; i += kCellThreads) pg[i] = ps[i];
+      uint16_t* sg = starts_g + ((int64_t)role * ntl + tile) * (kCellThreads + 8);
+      sg[tid] = (uint16_t)start;
+      if (tid == kCellThreads - 1) {
+        sg[kCellThreads] = (uint16_t)(start + c);
+        sg[kCellThreads + 1] = (uint16_t)(s_careful ? 1 : 0);
+      }
+      phase ^= 1;
+      __syncthreads();
+      continue;
+    }
     mbar_wait(bar_b, phase);
     phase ^= 1;
     // ---- the rows of my cell
     if (!s_careful) {
+      if (!diag) cell_rows_pair<false>(&R, perm + start, c, ta, tb, wv, acc);
+      else cell_rows_diag<false>(&R, perm + start, c, ta, tb, wv, acc);
+    } else {
+      if (!diag) cell_rows_pair<true>(&R, perm + start, c, ta, tb, wv, acc);
+      else cell_rows_diag<true>(&R, perm + start, c, ta, tb, wv, acc);
+    }
+    __syncthreads();
+  }
+  if (!EMIT && cur_role >= 0) {
+    double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * kCellThreads);
+#pragma unroll
+    for (int e = 0; e < kCellAcc; ++e) dst[e * kCellThreads + tid] = acc[e];
+  }
+}
+
+// The cells kernel of a prepared shard (pgb_gram_prepare): the rows of every (role, tile) are already in cell
+// order, so a tile is one set of bulk copies (t_i, t_j, omega, the sorted row indices, the cell starts) and the
+// sums.  Same scheduling, partial slots and reproducible order as gram_cells_kernel.
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+gram_cells_sorted_kernel(int64_t n, int64_t np, const double* __restrict__ om, const double* __restrict__ omz,
+                         const double* __restrict__ tq, const DCellRole* __restrict__ roles, int n_roles, int TR,
+                         int band_tiles, int slots_per_cta, double* __restrict__ part,
+                         const uint16_t* __restrict__ perm_g, const uint16_t* __restrict__ starts_g) {
+  constexpr int kCellThreads = THREADS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ DCellRole R;
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int tid = threadIdx.x;
+  double* ta = reinterpret_cast<double*>(smem_raw);
+  double* tb = ta + TR;
+  double* wv = tb + TR;
+  uint16_t* perm = reinterpret_cast<uint16_t*>(wv + TR);
+  uint16_t* starts = perm + TR;  // [THREADS + 8]
+  const uint32_t bar = smem_addr(&s_bar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  const int64_t ntl = (n + TR - 1) / TR;
+  const int role_lo = (int)((int64_t)n_roles * blockIdx.x / gridDim.x);
+  double* my_part = part + (int64_t)blockIdx.x * slots_per_cta * (kCellAcc * kCellThreads);
+  int cur_role = -1;
+  uint32_t phase = 0;
+  double acc[kCellAcc];
+#pragma unroll
+  for (int e = 0; e < kCellAcc; ++e) acc[e] = 0.0;
+  UnitIter it;
+  it.init(n, TR, band_tiles, n_roles);
+  __syncthreads();
+  for (; it.valid(); it.next()) {
+    const int role = it.role();
+    const int64_t tile = it.tile();
+    const int64_t row0 = tile * TR;
+    const int cnt = (int)min((int64_t)TR, n - row0);
+    if (tid == 0) {
+      const uint32_t cnt16 = (uint32_t)((cnt + 15) & ~15);
+      const DCellRole* gr = roles + role;
+      const double* ga = tq + (int64_t)gr->sa * np + row0;
+      const double* gb = gr->diag ? omz + row0 : tq + (int64_t)gr->sb * np + row0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the previous tile's generic reads vs the async writes
+      mbar_expect_tx(bar, 3u * cnt16 * 8u + cnt16 * 2u + (uint32_t)(kCellThreads + 8) * 2u);
+      bulk_g2s(smem_addr(ta), ga, cnt16 * 8u, bar);
+      bulk_g2s(smem_addr(tb), gb, cnt16 * 8u, bar);
+      bulk_g2s(smem_addr(wv), om + row0, cnt16 * 8u, bar);
+      bulk_g2s(smem_addr(perm), perm_g + ((int64_t)role * ntl + tile) * TR, cnt16 * 2u, bar);
+      bulk_g2s(smem_addr(starts), starts_g + ((int64_t)role * ntl + tile) * (kCellThreads + 8), (uint32_t)(kCellThreads + 8) * 2u, bar);
+    }
+    if (role != cur_role) {
+      if (cur_role >= 0) {
+        double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * kCellThreads);
+#pragma unroll
+        for (int e = 0; e < kCellAcc; ++e) dst[e * kCellThreads + tid] = acc[e];
+      }
+      const double* src = my_part + (int64_t)(role - role_lo) * (kCellAcc * kCellThreads);
+#pragma unroll
+      for (int e = 0; e < kCellAcc; ++e) acc[e] = src[e * kCellThreads + tid];
+      if (tid == 0) R = roles[role];
+      cur_role = role;
+      __syncthreads();
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    const int start = starts[tid], c = (int)starts[tid + 1] - start;
+    const int diag = R.diag;
+    if (!starts[kCellThreads + 1]) {
       if (!diag) cell_rows_pair<false>(&R, perm + start, c, ta, tb, wv, acc);
       else cell_rows_diag<false>(&R, perm + start, c, ta, tb, wv, acc);
     } else {
@@ -713,6 +826,97 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
 #pragma unroll
     for (int e = 0; e < kCellAcc; ++e) dst[e * kCellThreads + tid] = acc[e];
   }
+}
+
+// the prepass of a prepared shard: lp from the stored cell records (no basis interval search, no record
+// writes), then the IRLS step; writes omega and omega z and the iteration scalars
+__global__ void __launch_bounds__(kPreThreads, 3)
+gram_prepass_planned_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Family fam, int mode, int64_t n,
+                            const double* __restrict__ y, const float* __restrict__ w, const double* __restrict__ beta,
+                            int64_t np, const double* __restrict__ tq, const uint8_t* __restrict__ cq,
+                            double* __restrict__ om, double* __restrict__ omz, double* __restrict__ scal_part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  double* s_beta = reinterpret_cast<double*>(smem_raw);
+  double* s_red = s_beta + ((m + 1) & ~1);
+  DTerm* s_terms = reinterpret_cast<DTerm*>(s_red + (PGB_GS_COUNT + 2) * 32);
+  PreSpl* s_spl = reinterpret_cast<PreSpl*>(s_terms + n_terms);
+  __shared__ int s_nspl, s_icpt;
+  for (int i = tid; i < m; i += blockDim.x) s_beta[i] = (mode == PGB_MODE_IRLS) ? beta[i] : 0.0;
+  load_terms_smem(s_terms, g_terms, n_terms);
+  __syncthreads();
+  if (tid == 0) {
+    int ns = 0, ic = -1;
+    for (int q = 0; q < n_terms; ++q) {
+      const DTerm& T = s_terms[q];
+      if (T.kind == PGB_TERM_INTERCEPT) { ic = T.coef_offset; continue; }
+      const DMarg& mg = T.marg[0];
+      s_spl[ns++] = PreSpl{mg.lo, mg.inv_span, (double)mg.nint, mg.feature, mg.nint, T.coef_offset, q};
+    }
+    s_nspl = ns;
+    s_icpt = ic;
+  }
+  __syncthreads();
+  const int n_spl = s_nspl;
+  const double icpt_beta = s_icpt >= 0 ? s_beta[s_icpt] : 0.0;
+  double sc[PGB_GS_COUNT + 2];
+#pragma unroll
+  for (int s = 0; s < PGB_GS_COUNT + 2; ++s) sc[s] = 0.0;
+  constexpr int NX = 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double yi = __ldg(y + i);
+    double o, oz;
+    if (mode == PGB_MODE_IRLS) {
+      const double winv = weight_inv(w, i);
+      double lp = icpt_beta;
+      for (int base = 0; base < n_spl; base += NX) {
+        double tv[NX];
+        int cv[NX];
+#pragma unroll
+        for (int q = 0; q < NX; ++q)
+          if (base + q < n_spl) {
+            tv[q] = __ldg(tq + (int64_t)(base + q) * np + i);
+            cv[q] = __ldg(cq + (int64_t)(base + q) * np + i);
+          }
+#pragma unroll
+        for (int q = 0; q < NX; ++q) {
+          if (base + q >= n_spl) break;
+          const PreSpl& S = s_spl[base + q];
+          double v[4];
+          if (!(cv[q] & 0x80)) {
+            cubic_bspline(tv[q] + 0.5, v[0], v[1], v[2], v[3]);
+          } else {
+            const double u = tv[q] < 0.0 ? tv[q] + 1.0 : tv[q] - 1.0;
+            extrap_basis(s_terms[S.term].marg[0], u, v);
+          }
+          const double* bt = s_beta + S.coef_offset + (cv[q] & 0x7f);
+          lp = fma(v[0], bt[0], lp);
+          lp = fma(v[1], bt[1], lp);
+          lp = fma(v[2], bt[2], lp);
+          lp = fma(v[3], bt[3], lp);
+        }
+      }
+      const IrlsRow ir = irls_row(fam, lp, yi, winv);
+      o = ir.omega;
+      oz = ir.omega * ir.z;
+      if (ir.keep) {
+        sc[PGB_GS_NUSED] += 1.0;
+        sc[PGB_GS_DEV] += dist_dev(fam, yi, ir.mu);
+        sc[PGB_GS_NCORRECT] += (yi == ((ir.mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
+      }
+    } else {
+      o = 1.0;
+      oz = init_response(fam, yi);
+      sc[PGB_GS_NUSED] += 1.0;
+      if (!isfinite(oz)) sc[PGB_GS_NONFINITE] += 1.0;
+    }
+    sc[PGB_GS_NROWS] += 1.0;
+    sc[PGB_GS_COUNT] += o;
+    sc[PGB_GS_COUNT + 1] += oz;
+    om[i] = o;
+    omz[i] = oz;
+  }
+  block_reduce_store<PGB_GS_COUNT + 2>(sc, s_red, scal_part + (int64_t)blockIdx.x * (PGB_GS_COUNT + 2));
 }
 
 // ----------------------------------------------------------------------------------------
@@ -867,26 +1071,99 @@ __global__ void cells_assemble_kernel(const double* __restrict__ sums, const dou
   }
 }
 
+struct CellWs {
+  double *part, *sums, *scal_part, *extra, *om, *omz, *tq;
+  uint8_t* cq;
+  uint16_t *perm, *starts;
+  int64_t np, ntl;
+};
+static bool cells_ws_layout(const pgb_model* M, int64_t n, void* ws, int64_t ws_bytes, CellWs& L) {
+  const pgb_model::Cells& C = M->cells;
+  const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
+  L.np = rows_pad(n);
+  L.ntl = (n + C.tile_rows - 1) / C.tile_rows;
+  L.part = (double*)ws;
+  L.sums = L.part + slots * C.slot_doubles;
+  L.scal_part = L.sums + C.sum_doubles;
+  L.extra = L.scal_part + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2);
+  L.om = (double*)(((uintptr_t)(L.extra + 8) + 127) & ~(uintptr_t)127);
+  L.omz = L.om + L.np;
+  L.tq = L.omz + L.np;
+  L.cq = (uint8_t*)(L.tq + (int64_t)C.n_spl * L.np);
+  L.perm = (uint16_t*)(((uintptr_t)(L.cq + (int64_t)C.n_spl * L.np) + 127) & ~(uintptr_t)127);
+  L.starts = L.perm + (int64_t)C.roles.size() * L.ntl * C.tile_rows;
+  const uint8_t* end = (const uint8_t*)(L.starts + (int64_t)C.roles.size() * L.ntl * (C.threads + 8));
+  return (int64_t)(end - (const uint8_t*)ws) <= ws_bytes;
+}
+
+static size_t cells_pre_smem(const pgb_model* M) {
+  return ((size_t)((M->m + 1) & ~1) * 8 + (PGB_GS_COUNT + 2) * 32 * 8 + (size_t)M->n_terms * (sizeof(DTerm) + sizeof(PreSpl)) + 127) &
+         ~(size_t)127;
+}
+static int cells_band_tiles(const pgb_model* M) {
+  const pgb_model::Cells& C = M->cells;
+  const int64_t row_bytes = 9 * (int64_t)C.n_spl + 16;
+  int band_tiles = (int)std::max<int64_t>(1, kBandBytes / (row_bytes * C.tile_rows));
+  if (const char* e = getenv("PGB_CELLS_BAND")) band_tiles = std::max(1, atoi(e));
+  return band_tiles;
+}
+
+#define PGB_CELLS_DISPATCH(KERNEL_CALL)                 \
+  switch (C.threads) {                                  \
+    case 256: KERNEL_CALL(256, 2); break;               \
+    case 320: KERNEL_CALL(320, 2); break;               \
+    case 384: KERNEL_CALL(384, 1); break;               \
+    default: KERNEL_CALL(512, 1); break;                \
+  }
+
+// pgb_gram_prepare for an all-spline model: cell records of every row and the cell order of every (role, tile)
+int pgb_cells_prepare(const pgb_model* M, const double* X, int64_t n, int64_t ld, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const pgb_model::Cells& C = M->cells;
+  CellWs L;
+  if (!cells_ws_layout(M, n, ws, ws_bytes, L)) {
+    pgb_set_error("pgb_gram_prepare: workspace too small");
+    return PGB_EINVAL;
+  }
+  const int n_roles = (int)C.roles.size();
+  const int grid1 = (int)std::min<int64_t>((n + kPreThreads - 1) / kPreThreads, (int64_t)kSMs * 8);
+  // records only: the response of this launch is column 0 of X (any n finite doubles will do), its omega is discarded
+  gram_prepass_kernel<<<grid1, kPreThreads, cells_pre_smem(M), st>>>(M->d_terms, M->n_terms, M->m, M->fam, PGB_MODE_INIT, X, n, ld, X,
+                                                                    nullptr, nullptr, L.np, L.om, L.omz, L.tq, L.cq, L.scal_part);
+  PGB_CUDA(cudaGetLastError());
+  const int TR = C.tile_rows, band_tiles = cells_band_tiles(M);
+#define PGB_CELLS_EMIT(TH, OCC)                                                                                          \
+  do {                                                                                                                   \
+    static thread_local bool attr_set = false;                                                                           \
+    if (!attr_set) {                                                                                                     \
+      PGB_CUDA(cudaFuncSetAttribute(gram_cells_kernel<TH, OCC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                    (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024)));                             \
+      attr_set = true;                                                                                                   \
+    }                                                                                                                    \
+    gram_cells_kernel<TH, OCC, true><<<C.grid, TH, C.smem, st>>>(n, L.np, L.om, L.omz, L.tq, L.cq, C.d_roles, n_roles, TR, \
+                                                                 band_tiles, C.slots_per_cta, L.part, L.perm, L.starts); \
+  } while (0)
+  PGB_CELLS_DISPATCH(PGB_CELLS_EMIT)
+#undef PGB_CELLS_EMIT
+  PGB_CUDA(cudaGetLastError());
+  pgb_count_launch(2);
+  return PGB_OK;
+}
+
 int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int64_t n, int64_t ld, const double* y,
                           const float* w, const double* beta, double* out, void* ws, int64_t ws_bytes, int accumulate,
-                          cudaStream_t st) {
+                          int planned, cudaStream_t st) {
   const pgb_model::Cells& C = M->cells;
   pgb_model* Mm = const_cast<pgb_model*>(M);
   const int n_roles = (int)C.roles.size();
   const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
-  const int64_t np = rows_pad(n);
-  double* part = (double*)ws;
-  double* sums = part + slots * C.slot_doubles;
-  double* scal_part = sums + C.sum_doubles;
-  double* extra = scal_part + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2);
-  double* om = (double*)(((uintptr_t)(extra + 8) + 127) & ~(uintptr_t)127);
-  double* omz = om + np;
-  double* tq = omz + np;
-  uint8_t* cq = (uint8_t*)(tq + (int64_t)C.n_spl * np);
-  if ((int64_t)((uint8_t*)cq + (int64_t)C.n_spl * np - (uint8_t*)ws) > ws_bytes) {
+  CellWs L;
+  if (!cells_ws_layout(M, n, ws, ws_bytes, L)) {
     pgb_set_error("pgb_gram_pass: workspace too small");
     return PGB_EINVAL;
   }
+  double *part = L.part, *sums = L.sums, *scal_part = L.scal_part, *extra = L.extra, *om = L.om, *omz = L.omz, *tq = L.tq;
+  uint8_t* cq = L.cq;
+  const int64_t np = L.np;
   pgb_model::Timing& tm = Mm->timing;
   if (tm.enabled) {
     while ((int)tm.chunk_ev.size() < 5) {
@@ -898,33 +1175,35 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
     PGB_CUDA(cudaEventRecord(tm.chunk_ev[2], st));
   }
   const int grid1 = (int)std::min<int64_t>((n + kPreThreads - 1) / kPreThreads, (int64_t)kSMs * 8);
-  const size_t pre_smem = ((size_t)((M->m + 1) & ~1) * 8 + (PGB_GS_COUNT + 2) * 32 * 8 + (size_t)M->n_terms * (sizeof(DTerm) + sizeof(PreSpl)) + 127) & ~(size_t)127;
-  gram_prepass_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, X, n, ld, y, w, beta, np, om,
-                                                            omz, tq, cq, scal_part);
+  const size_t pre_smem = cells_pre_smem(M);
+  if (planned)
+    gram_prepass_planned_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, n, y, w, beta, np, tq,
+                                                                      cq, om, omz, scal_part);
+  else
+    gram_prepass_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, X, n, ld, y, w, beta, np, om,
+                                                              omz, tq, cq, scal_part);
   PGB_CUDA(cudaGetLastError());
   PGB_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * slots * C.slot_doubles, st));
   if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[3], st));
-  const int TR = C.tile_rows;
-  const int64_t row_bytes = 9 * (int64_t)C.n_spl + 16;
-  int band_tiles = (int)std::max<int64_t>(1, kBandBytes / (row_bytes * TR));
-  if (const char* e = getenv("PGB_CELLS_BAND")) band_tiles = std::max(1, atoi(e));
+  const int TR = C.tile_rows, band_tiles = cells_band_tiles(M);
 #define PGB_CELLS_LAUNCH(TH, OCC)                                                                                        \
   do {                                                                                                                   \
     static thread_local bool attr_set = false;                                                                           \
     if (!attr_set) {                                                                                                     \
-      PGB_CUDA(cudaFuncSetAttribute(gram_cells_kernel<TH, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+      PGB_CUDA(cudaFuncSetAttribute(gram_cells_kernel<TH, OCC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                    (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024)));                             \
+      PGB_CUDA(cudaFuncSetAttribute(gram_cells_sorted_kernel<TH, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                     (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024)));                             \
       attr_set = true;                                                                                                   \
     }                                                                                                                    \
-    gram_cells_kernel<TH, OCC><<<C.grid, TH, C.smem, st>>>(n, np, om, omz, tq, cq, C.d_roles, n_roles, TR, band_tiles,   \
-                                                           C.slots_per_cta, part);                                       \
+    if (planned)                                                                                                         \
+      gram_cells_sorted_kernel<TH, OCC><<<C.grid, TH, (size_t)TR * 26 + (TH + 8) * 2 + 64, st>>>(                        \
+          n, np, om, omz, tq, C.d_roles, n_roles, TR, band_tiles, C.slots_per_cta, part, L.perm, L.starts);              \
+    else                                                                                                                 \
+      gram_cells_kernel<TH, OCC, false><<<C.grid, TH, C.smem, st>>>(n, np, om, omz, tq, cq, C.d_roles, n_roles, TR,      \
+                                                                    band_tiles, C.slots_per_cta, part, nullptr, nullptr); \
   } while (0)
-  switch (C.threads) {
-    case 256: PGB_CELLS_LAUNCH(256, 2); break;
-    case 320: PGB_CELLS_LAUNCH(320, 2); break;
-    case 384: PGB_CELLS_LAUNCH(384, 1); break;
-    default: PGB_CELLS_LAUNCH(512, 1); break;
-  }
+  PGB_CELLS_DISPATCH(PGB_CELLS_LAUNCH)
 #undef PGB_CELLS_LAUNCH
   PGB_CUDA(cudaGetLastError());
   if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[4], st));

@@ -540,7 +540,8 @@ static int64_t chunk_rows_for(const pgb_model* M, int64_t n) {
 extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n);  // pgb_cells.cu
 int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int64_t n, int64_t ld, const double* y,
                           const float* w, const double* beta, double* out, void* ws, int64_t ws_bytes, int accumulate,
-                          cudaStream_t st);
+                          int planned, cudaStream_t st);
+int pgb_cells_prepare(const pgb_model* M, const double* X, int64_t n, int64_t ld, void* ws, int64_t ws_bytes, cudaStream_t st);
 extern "C" int64_t pgb_gram_ws_bytes(const pgb_model* M, int64_t n) {
   if (!M) return 0;
   if (M->cells.enabled) return pgb_cells_ws_bytes(M, std::max<int64_t>(n, 1));
@@ -965,6 +966,8 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partials, const DR
 static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_t n, int64_t ld,
                        const double* y, const float* w, const double* beta, double* out, void* ws,
                        int64_t ws_bytes, int accumulate, cudaStream_t st) {
+  const int planned = (mode & PGB_MODE_PLANNED) ? 1 : 0;
+  mode &= ~PGB_MODE_PLANNED;
   if (!M || !X || !y || !out || !ws || n < 1 || ld < n || (mode == PGB_MODE_IRLS && !beta) ||
       (mode != PGB_MODE_IRLS && mode != PGB_MODE_INIT)) {
     pgb_set_error("pgb_gram_pass: bad arguments");
@@ -975,7 +978,7 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
                   (long long)pgb_gram_ws_bytes(M, n));
     return PGB_EINVAL;
   }
-  if (M->cells.enabled) return pgb_launch_gram_cells(M, mode, X, n, ld, y, w, beta, out, ws, ws_bytes, accumulate, st);
+  if (M->cells.enabled) return pgb_launch_gram_cells(M, mode, X, n, ld, y, w, beta, out, ws, ws_bytes, accumulate, planned, st);
   const int n_roles = (int)M->roles.size();
   const int T = M->tile_rows, TP = tile_pitch(T);
   pgb_model* Mm = const_cast<pgb_model*>(M);
@@ -1062,6 +1065,15 @@ extern "C" int pgb_gram_last_ms(pgb_model* M, float* records_ms, float* accum_ms
     *accum_ms += b;
   }
   return PGB_OK;
+}
+
+// The knot cells of a row, and therefore the cell order of the rows, do not depend on beta: a fit prepares
+// its resident shard once and passes PGB_MODE_PLANNED afterwards.  No-op for models on the general path.
+extern "C" int pgb_gram_prepare(const pgb_model* M, const double* X, int64_t n, int64_t ld, void* ws, int64_t ws_bytes,
+                                void* stream) {
+  if (!M || !X || !ws || n < 1 || ld < n) { pgb_set_error("pgb_gram_prepare: bad arguments"); return PGB_EINVAL; }
+  if (!M->cells.enabled) return PGB_OK;
+  return pgb_cells_prepare(M, X, n, ld, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int pgb_gram_pass(const pgb_model* M, int32_t mode, const double* X, int64_t n, int64_t ld,

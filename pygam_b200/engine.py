@@ -8,6 +8,7 @@ packed ``[G | r | scalars]`` buffer is all-reduced once per PIRLS iteration (SUR
 """
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -209,6 +210,8 @@ class Engine:
         self.cov = None
         self.stat_scalars = torch.zeros(_lib.SS_COUNT, **f64)
         self._gram_ws = None
+        self._plan_key = None
+        self._plan_data = None
         self._stats_ws = torch.empty(int(self.lib.pgb_stats_ws_bytes(self.handle)) // 8 + 1, **f64)
         self._solve_ws = torch.empty(int(self.lib.pgb_solve_ws_bytes(m, 1)) // 8 + 1, **f64)
         self._chol_ws = None
@@ -260,7 +263,22 @@ class Engine:
         need = int(self.lib.pgb_gram_ws_bytes(self.handle, n)) // 8 + 1
         if self._gram_ws is None or self._gram_ws.numel() < need:
             self._gram_ws = torch.empty(need, dtype=torch.float64, device=self.device)
+            self._plan_key = None
         return self._gram_ws
+
+    def _planned(self, data, ws):
+        """What does not depend on the coefficients (knot cells of the rows and their order, all-spline models)
+        is prepared once per resident shard: the reference builds its model matrix once per fit, too
+        (pygam.py:741).  Returns the mode flag for pgb_gram_pass."""
+        if self.info.cell_roles == 0 or os.environ.get("PGB_GRAM_PLAN", "1") == "0":
+            return 0
+        key = (data.Xt.data_ptr(), data.n, ws.data_ptr(), data.Xt._version)
+        if self._plan_key != key:
+            _lib.check(self.lib.pgb_gram_prepare(self.handle, _ptr(data.Xt), data.n, data.n, _ptr(ws), ws.numel() * 8,
+                                                 _stream()), "pgb_gram_prepare")
+            self._plan_key = key
+            self._plan_data = data.Xt  # keeps the tensor (and its address) alive as long as the plan
+        return _lib.MODE_PLANNED
 
     def gram_pass(self, data, coef=None, mode=_lib.MODE_IRLS, reduce=True):
         """G = X^T W^2 X, r = X^T W^2 z and the iteration scalars at `coef` (device tensors).
@@ -268,6 +286,7 @@ class Engine:
         ws = self._ensure_gram_ws(data.n)
         if coef is not None:
             self.beta.copy_(torch.as_tensor(coef, dtype=torch.float64))
+        mode = mode | self._planned(data, ws)
         _lib.check(self.lib.pgb_gram_pass(self.handle, mode, _ptr(data.Xt), data.n, data.n, _ptr(data.y),
                                           _ptr(data.w), _ptr(self.beta), _ptr(self.out), _ptr(ws),
                                           ws.numel() * 8, _stream()), "pgb_gram_pass")

@@ -87,6 +87,18 @@ def _compare(gam, X, y, w=None, env=None, modes=(_lib.MODE_IRLS, _lib.MODE_INIT)
         assert abs(sa[_lib.GS_DEV] - sb[_lib.GS_DEV]) <= 1e-12 * max(1.0, abs(sb[_lib.GS_DEV]))
         again = cells.gram_pass(data, coef, mode=mode).cpu().numpy()
         assert np.array_equal(a, again), "the cell-owned pass must be bit-reproducible"
+        # the prepared order (pgb_gram_prepare, the default for resident data) and the in-kernel sort of the
+        # streaming path visit the rows of a cell in the same order; the prepared prepass rebuilds t from the
+        # stored centred coordinate (one rounding in lp), so IRLS weights agree to rounding, INIT bit for bit
+        os.environ["PGB_GRAM_PLAN"] = "0"
+        try:
+            unplanned = cells.gram_pass(data, coef, mode=mode).cpu().numpy()
+        finally:
+            os.environ.pop("PGB_GRAM_PLAN", None)
+        if mode == _lib.MODE_INIT:
+            assert np.array_equal(a, unplanned)
+        else:
+            assert np.abs(a - unplanned).max() <= 1e-13 * scale
     del torch
 
 
