@@ -138,6 +138,8 @@ enum { PGB_MODE_IRLS = 0,    /* weights and working response at beta (pygam.py:7
  * out: m*m + m + PGB_GS_COUNT doubles = [G (row-major, symmetric) | r | scalars], so that one
  * all-reduce of `out` combines row shards. */
 int64_t pgb_gram_ws_bytes(const pgb_model* model, int64_t n);
+/* smaller workspace for callers that never call pgb_gram_prepare (no PGB_MODE_PLANNED passes) */
+int64_t pgb_gram_ws_bytes_streaming(const pgb_model* model, int64_t n);
 int pgb_gram_pass(const pgb_model* model, int32_t mode, const double* X, int64_t n, int64_t ld,
                   const double* y, const float* w, const double* beta, double* out, void* ws,
                   int64_t ws_bytes, void* stream);

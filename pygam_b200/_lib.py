@@ -79,6 +79,7 @@ SYMBOLS = {
     "pgb_col_levels": (C.c_int, [_P, C.c_int64, C.c_double, C.c_int32, _P, _P]),
     "pgb_model_matrix": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P]),
     "pgb_gram_ws_bytes": (C.c_int64, [_P, C.c_int64]),
+    "pgb_gram_ws_bytes_streaming": (C.c_int64, [_P, C.c_int64]),
     "pgb_gram_pass": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "pgb_gram_prepare": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
     "pgb_stats_ws_bytes": (C.c_int64, [_P]),

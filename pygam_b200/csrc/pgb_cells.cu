@@ -84,6 +84,9 @@ int pgb_plan_cells(pgb_model* M) {
     const int t = atoi(e);
     if (t == 256 || t == 320 || t == 384 || t == 512) { C.threads = t; C.occ = t <= 320 ? 2 : 1; }
   }
+  // occ 3: wide CTAs run alone while they sort (registers), but the kernel of a prepared shard only sums: two of
+  // them per SM with half the tile each, so that one waits for its tile while the other computes (measured: -10 %)
+  if (C.occ == 1 && !(getenv("PGB_CELLS_OCC2") && atoi(getenv("PGB_CELLS_OCC2")) == 0)) C.occ = 3;
   const int TH = C.threads;
   int64_t sum_off = 0;
   int64_t n_sub = 0;
@@ -128,11 +131,12 @@ int pgb_plan_cells(pgb_model* M) {
     return PGB_OK;
   }
   C.sum_doubles = sum_off;
-  C.grid = kSMs * C.occ;
-  C.tile_rows = 8192;
+  C.grid = kSMs * (C.occ == 3 ? 2 : C.occ);
+  C.tile_rows = (C.occ == 3) ? 4096 : 8192;
   if (const char* e = getenv("PGB_CELLS_TILE")) C.tile_rows = std::max(64, atoi(e) & ~63);
   // 1 KB per CTA for the kernel's static shared memory and the driver's reservation
   while (cells_smem(C.tile_rows, TH) + 1024 > (C.occ == 2 ? kSmemMax / 2 - 1024 : kSmemMax)) C.tile_rows -= 64;
+  if (C.occ == 3) while ((size_t)C.tile_rows * 26 + (TH + 8) * 2 + 1024 > kSmemMax / 2 - 1024) C.tile_rows -= 64;
   for (DCellRole& R : C.roles) R.hmul = ((uint32_t)R.ncb << 16) / (uint32_t)C.tile_rows;
   C.smem = cells_smem(C.tile_rows, TH);
   C.slots_per_cta = ((int)C.roles.size() + C.grid - 1) / C.grid + 1;
@@ -258,12 +262,13 @@ int pgb_cells_coverage_errors(const pgb_model* M) {
 
 // workspace: [CTA partial slots][cell sums][scalar partials][extra][omega][omega z][t of every spline term][cells]
 static int64_t rows_pad(int64_t n) { return (n + 15) & ~(int64_t)15; }
-extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n) {
+extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n, int with_order) {
   const pgb_model::Cells& C = M->cells;
   const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
   const int64_t np = rows_pad(n);
   const int64_t ntl = (n + C.tile_rows - 1) / C.tile_rows;
-  const int64_t order = (int64_t)C.roles.size() * ntl * (C.tile_rows + C.threads + 8) * 2;  // sorted rows + cell starts (pgb_gram_prepare)
+  // sorted rows + cell starts (pgb_gram_prepare); not needed by passes that sort inside the kernel
+  const int64_t order = with_order ? (int64_t)C.roles.size() * ntl * (C.tile_rows + C.threads + 8) * 2 : 0;
   return (slots * C.slot_doubles + C.sum_doubles + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2) + 8 + (2 + C.n_spl) * np) * 8 +
          (int64_t)C.n_spl * np + order + 2048;
 }
@@ -1077,7 +1082,7 @@ struct CellWs {
   uint16_t *perm, *starts;
   int64_t np, ntl;
 };
-static bool cells_ws_layout(const pgb_model* M, int64_t n, void* ws, int64_t ws_bytes, CellWs& L) {
+static bool cells_ws_layout(const pgb_model* M, int64_t n, void* ws, int64_t ws_bytes, bool with_order, CellWs& L) {
   const pgb_model::Cells& C = M->cells;
   const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
   L.np = rows_pad(n);
@@ -1092,7 +1097,7 @@ static bool cells_ws_layout(const pgb_model* M, int64_t n, void* ws, int64_t ws_
   L.cq = (uint8_t*)(L.tq + (int64_t)C.n_spl * L.np);
   L.perm = (uint16_t*)(((uintptr_t)(L.cq + (int64_t)C.n_spl * L.np) + 127) & ~(uintptr_t)127);
   L.starts = L.perm + (int64_t)C.roles.size() * L.ntl * C.tile_rows;
-  const uint8_t* end = (const uint8_t*)(L.starts + (int64_t)C.roles.size() * L.ntl * (C.threads + 8));
+  const uint8_t* end = with_order ? (const uint8_t*)(L.starts + (int64_t)C.roles.size() * L.ntl * (C.threads + 8)) : (const uint8_t*)L.perm;
   return (int64_t)(end - (const uint8_t*)ws) <= ws_bytes;
 }
 
@@ -1115,12 +1120,13 @@ static int cells_band_tiles(const pgb_model* M) {
     case 384: KERNEL_CALL(384, 1); break;               \
     default: KERNEL_CALL(512, 1); break;                \
   }
+template <int THREADS, int MINB> struct SortedOcc { static const int value = MINB; };
 
 // pgb_gram_prepare for an all-spline model: cell records of every row and the cell order of every (role, tile)
 int pgb_cells_prepare(const pgb_model* M, const double* X, int64_t n, int64_t ld, void* ws, int64_t ws_bytes, cudaStream_t st) {
   const pgb_model::Cells& C = M->cells;
   CellWs L;
-  if (!cells_ws_layout(M, n, ws, ws_bytes, L)) {
+  if (!cells_ws_layout(M, n, ws, ws_bytes, true, L)) {
     pgb_set_error("pgb_gram_prepare: workspace too small");
     return PGB_EINVAL;
   }
@@ -1157,7 +1163,7 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
   const int n_roles = (int)C.roles.size();
   const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
   CellWs L;
-  if (!cells_ws_layout(M, n, ws, ws_bytes, L)) {
+  if (!cells_ws_layout(M, n, ws, ws_bytes, planned != 0, L)) {
     pgb_set_error("pgb_gram_pass: workspace too small");
     return PGB_EINVAL;
   }
@@ -1196,7 +1202,16 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
                                     (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024)));                             \
       attr_set = true;                                                                                                   \
     }                                                                                                                    \
-    if (planned)                                                                                                         \
+    if (planned && C.occ == 3) {                                                                                         \
+      static thread_local bool attr2 = false;                                                                            \
+      if (!attr2) {                                                                                                      \
+        PGB_CUDA(cudaFuncSetAttribute(gram_cells_sorted_kernel<TH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                      (int)(kSmemMax / 2 - 2048)));                                                       \
+        attr2 = true;                                                                                                    \
+      }                                                                                                                  \
+      gram_cells_sorted_kernel<TH, 2><<<C.grid, TH, (size_t)TR * 26 + (TH + 8) * 2 + 64, st>>>(                          \
+          n, np, om, omz, tq, C.d_roles, n_roles, TR, band_tiles, C.slots_per_cta, part, L.perm, L.starts);              \
+    } else if (planned)                                                                                                  \
       gram_cells_sorted_kernel<TH, OCC><<<C.grid, TH, (size_t)TR * 26 + (TH + 8) * 2 + 64, st>>>(                        \
           n, np, om, omz, tq, C.d_roles, n_roles, TR, band_tiles, C.slots_per_cta, part, L.perm, L.starts);              \
     else                                                                                                                 \

@@ -537,14 +537,15 @@ static int64_t chunk_rows_for(const pgb_model* M, int64_t n) {
   const int64_t rows = (n + nch - 1) / nch;
   return ((rows + T - 1) / T) * T;
 }
-extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n);  // pgb_cells.cu
+extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n, int with_order);  // pgb_cells.cu
 int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int64_t n, int64_t ld, const double* y,
                           const float* w, const double* beta, double* out, void* ws, int64_t ws_bytes, int accumulate,
                           int planned, cudaStream_t st);
 int pgb_cells_prepare(const pgb_model* M, const double* X, int64_t n, int64_t ld, void* ws, int64_t ws_bytes, cudaStream_t st);
+extern "C" int64_t pgb_gram_ws_bytes_streaming(const pgb_model* M, int64_t n);
 extern "C" int64_t pgb_gram_ws_bytes(const pgb_model* M, int64_t n) {
   if (!M) return 0;
-  if (M->cells.enabled) return pgb_cells_ws_bytes(M, std::max<int64_t>(n, 1));
+  if (M->cells.enabled) return pgb_cells_ws_bytes(M, std::max<int64_t>(n, 1), 1);
   const int64_t tiles = chunk_rows_for(M, std::max<int64_t>(n, 1)) / M->tile_rows;
   return (M->partial_doubles + (int64_t)M->rec_ctas * PGB_GS_COUNT) * 8 + tiles * rec_tile_bytes(M) + 1024;
 }
@@ -973,9 +974,9 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
     pgb_set_error("pgb_gram_pass: bad arguments");
     return PGB_EINVAL;
   }
-  if (ws_bytes < pgb_gram_ws_bytes(M, n)) {
-    pgb_set_error("pgb_gram_pass: workspace too small (%lld < %lld)", (long long)ws_bytes,
-                  (long long)pgb_gram_ws_bytes(M, n));
+  const int64_t ws_need = planned ? pgb_gram_ws_bytes(M, n) : pgb_gram_ws_bytes_streaming(M, n);
+  if (ws_bytes < ws_need) {
+    pgb_set_error("pgb_gram_pass: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)ws_need);
     return PGB_EINVAL;
   }
   if (M->cells.enabled) return pgb_launch_gram_cells(M, mode, X, n, ld, y, w, beta, out, ws, ws_bytes, accumulate, planned, st);
@@ -1067,6 +1068,14 @@ extern "C" int pgb_gram_last_ms(pgb_model* M, float* records_ms, float* accum_ms
   return PGB_OK;
 }
 
+// workspace of passes that never use pgb_gram_prepare (rows streamed through once, or not enough memory for
+// the stored order: 2 bytes per row and term pair)
+extern "C" int64_t pgb_gram_ws_bytes_streaming(const pgb_model* M, int64_t n) {
+  if (!M) return 0;
+  if (M->cells.enabled) return pgb_cells_ws_bytes(M, std::max<int64_t>(n, 1), 0);
+  return pgb_gram_ws_bytes(M, n);
+}
+
 // The knot cells of a row, and therefore the cell order of the rows, do not depend on beta: a fit prepares
 // its resident shard once and passes PGB_MODE_PLANNED afterwards.  No-op for models on the general path.
 extern "C" int pgb_gram_prepare(const pgb_model* M, const double* X, int64_t n, int64_t ld, void* ws, int64_t ws_bytes,
@@ -1106,7 +1115,7 @@ static int stage_ensure(pgb_model* M, int64_t chunk_rows, bool need_w) {
   const int F = M->n_features, m = M->m;
   cudaError_t e = cudaSuccess;
   auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-  S.ws_bytes = pgb_gram_ws_bytes(M, chunk_rows);
+  S.ws_bytes = pgb_gram_ws_bytes_streaming(M, chunk_rows);
   for (int b = 0; b < 2; ++b) {
     ck(cudaStreamCreateWithFlags(&S.st[b], cudaStreamNonBlocking));
     ck(cudaEventCreateWithFlags(&S.done[b], cudaEventDisableTiming));

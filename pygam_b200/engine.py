@@ -212,6 +212,7 @@ class Engine:
         self._gram_ws = None
         self._plan_key = None
         self._plan_data = None
+        self._ws_has_order = True
         self._stats_ws = torch.empty(int(self.lib.pgb_stats_ws_bytes(self.handle)) // 8 + 1, **f64)
         self._solve_ws = torch.empty(int(self.lib.pgb_solve_ws_bytes(m, 1)) // 8 + 1, **f64)
         self._chol_ws = None
@@ -262,15 +263,23 @@ class Engine:
     def _ensure_gram_ws(self, n):
         need = int(self.lib.pgb_gram_ws_bytes(self.handle, n)) // 8 + 1
         if self._gram_ws is None or self._gram_ws.numel() < need:
-            self._gram_ws = torch.empty(need, dtype=torch.float64, device=self.device)
             self._plan_key = None
+            self._gram_ws = None
+            try:
+                self._gram_ws = torch.empty(need, dtype=torch.float64, device=self.device)
+                self._ws_has_order = True
+            except torch.cuda.OutOfMemoryError:
+                # no room for the stored row order (2 bytes per row and term pair): sort inside the kernel
+                small = int(self.lib.pgb_gram_ws_bytes_streaming(self.handle, n)) // 8 + 1
+                self._gram_ws = torch.empty(small, dtype=torch.float64, device=self.device)
+                self._ws_has_order = False
         return self._gram_ws
 
     def _planned(self, data, ws):
         """What does not depend on the coefficients (knot cells of the rows and their order, all-spline models)
         is prepared once per resident shard: the reference builds its model matrix once per fit, too
         (pygam.py:741).  Returns the mode flag for pgb_gram_pass."""
-        if self.info.cell_roles == 0 or os.environ.get("PGB_GRAM_PLAN", "1") == "0":
+        if self.info.cell_roles == 0 or not self._ws_has_order or os.environ.get("PGB_GRAM_PLAN", "1") == "0":
             return 0
         key = (data.Xt.data_ptr(), data.n, ws.data_ptr(), data.Xt._version)
         if self._plan_key != key:
