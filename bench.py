@@ -251,6 +251,35 @@ def run_b200(args, rank, world, local_rank):
     accum, records, gram_pass_ms = float(acc[0].item()), float(acc[1].item()), float(acc[2].item())
     value = n * world / (ms_per_step * 1e-3)
 
+    # ---- the O(k)-per-row passes (statistics sums, predict_mu): the HBM-bound kernels of the path ----
+    def time_pass(fn, reps=10):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    eng.beta.copy_(torch.as_tensor(coef, dtype=torch.float64))
+    mu_buf = torch.empty(n, dtype=torch.float64, device=dev)
+    st_ws = eng._stats_ws
+    cur = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _stats_call(yy, mu_out):
+        _lib.check(lib.pgb_stats_pass(eng.handle, C.c_void_p(Xt.data_ptr()), n, n, C.c_void_p(yy.data_ptr() if yy is not None else 0),
+                                      C.c_void_p(0), C.c_void_p(eng.beta.data_ptr()), -1.0, 0.0, 0,
+                                      C.c_void_p(eng.stat_scalars.data_ptr()), C.c_void_p(0),
+                                      C.c_void_p(mu_out.data_ptr() if mu_out is not None else 0), C.c_void_p(st_ws.data_ptr()),
+                                      st_ws.numel() * 8, cur), "pgb_stats_pass")
+
+    stats_ms = time_pass(lambda: _stats_call(y, None))
+    predict_ms = time_pass(lambda: _stats_call(None, mu_buf))
+    del mu_buf
+
     # ---- end to end: host buffers in, coefficients out, every step ----
     e2e = None
     if not args.no_e2e:
@@ -329,7 +358,16 @@ def run_b200(args, rank, world, local_rank):
                 "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
                 "traffic": traffic, "kernel_ms": gram_ms, "prepass_kernel_ms": records, "accum_kernel_ms": accum,
                 "kernel_share_of_step": gram_ms / ms_per_step, "algorithmic_bytes_per_row": BYTES_PER_ROW,
-                "governing": second}
+                "governing": second,
+                "ok_passes": {"note": "the O(k)-per-row passes of the path, same shard and coefficients, CUDA events over 10 "
+                                      "launches each: statistics sums (stats_pass_kernel, reads 8F+8 B per row) and predict_mu "
+                                      "(reads 8F, writes 8 B per row)",
+                              "statistics_pass_ms": stats_ms,
+                              "statistics_pass_gbs": n * BYTES_PER_ROW / (stats_ms * 1e-3) / 1e9,
+                              "statistics_pass_frac": n * BYTES_PER_ROW / (stats_ms * 1e-3) / 1e9 / hbm_peak,
+                              "predict_mu_ms": predict_ms,
+                              "predict_mu_gbs": n * BYTES_PER_ROW / (predict_ms * 1e-3) / 1e9,
+                              "predict_mu_frac": n * BYTES_PER_ROW / (predict_ms * 1e-3) / 1e9 / hbm_peak}}
     line = {"metric": "rows/sec per PIRLS iteration", "value": value, "unit": "rows/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(world, n, prepare_ms),

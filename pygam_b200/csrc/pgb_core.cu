@@ -381,114 +381,283 @@ extern "C" int pgb_interval_pass(const pgb_model* M, const double* X, int64_t n,
 
 // ----------------------------------------------------------------------------------------
 // statistics / predict pass: lp, mu and the sums of _estimate_model_statistics on ALL rows
+// (_linear_predictor pygam.py:385-421, predict_mu 423-450, the n-sized sums of 1031-1056)
 // ----------------------------------------------------------------------------------------
-// One CTA walks tiles of R rows (round robin over the grid).  Thread 0 issues one TMA bulk copy
-// per input column of the NEXT tile (feature columns, y, w -> shared memory, completion on an
-// mbarrier) before the CTA evaluates the current one: a two-stage producer/consumer ring.
-// Unaligned inputs and the ragged last tile are staged with plain loads instead.
+// An O(k)-per-row pass: 8 F + 8 bytes per row against ~20 fp64-pipe slots per loaded double
+// (B200: 62.7 fp64 FMA/clk/SM vs 6.5 TB/s), so both the instruction count per row and the bytes in
+// flight matter.
+//  * plain cubic s() terms (the `fast` flag) do not evaluate their four basis functions: every CTA
+//    turns beta into one cubic polynomial per knot interval (s_tab, four coefficients per interval,
+//    coefficient-major so that the four loads of a warp hit distinct banks or broadcast) and a row
+//    costs an interval search and a Horner step -- ten fp64 instructions per term instead of ~26.
+//    floor(s) is taken with a round-down add of 2^52 (no F2I / I2F conversions).  Rows outside the
+//    edge knots and every other kind of term go through eval_term as before.
+//  * one CTA walks tiles of R rows (round robin over a persistent grid).  Thread 0 issues one TMA bulk
+//    copy per input column of the tile NS-1 steps ahead (completion on the stage's `full` mbarrier);
+//    a warp that has read its rows of a stage arrives on the stage's `empty` mbarrier, which is all
+//    thread 0 waits for before it refills the stage: no CTA-wide barrier inside the loop.
+//  * the link / distribution switches are resolved at compile time for the canonical families (FAMK).
+//  * rows after the last full tile, and inputs that are not 16-byte aligned, are read with plain loads.
+#define PGB_PASS_MAX_FAST 48
+struct PassSpl {
+  double lo, inv_span, dn;
+  int32_t feature, nint, coef, tab;  // tab: offset of the term's polynomial table in s_tab (doubles)
+};
+struct PassPlan {
+  int32_t n_fast, n_other, icpt, tab_doubles, fast_limit, pad;
+  int16_t term[PGB_PASS_MAX_FAST];
+  PassSpl spl[PGB_PASS_MAX_FAST];
+};
+
+static void pass_plan_build(const pgb_model* M, PassPlan& P) {
+  P.n_fast = P.n_other = P.tab_doubles = P.pad = 0;
+  P.icpt = -1;
+  P.fast_limit = M->n_terms;
+  for (int q = 0; q < M->n_terms; ++q) {
+    const DTerm& T = M->dterms[q];
+    if (T.kind == PGB_TERM_INTERCEPT && P.icpt < 0) { P.icpt = T.coef_offset; continue; }
+    if (T.fast && P.n_fast < PGB_PASS_MAX_FAST && q < P.fast_limit) {
+      const DMarg& g = T.marg[0];
+      P.term[P.n_fast] = (int16_t)q;
+      P.spl[P.n_fast++] = PassSpl{g.lo, g.inv_span, (double)g.nint, g.feature, g.nint, T.coef_offset, P.tab_doubles};
+      P.tab_doubles += 4 * (g.nint + 2);
+      continue;
+    }
+    if (T.fast && P.fast_limit == M->n_terms) P.fast_limit = q;  // fast terms from here on take the general path
+    ++P.n_other;
+  }
+}
+
+// the terms that are not in the plan (f(), l(), te(), by=, other orders, cyclic bases): the general evaluation
+template <class Load>
+__device__ __forceinline__ double pass_other_terms(const DTerm* s_terms, int n_terms, int icpt, int fast_limit,
+                                                   const double* s_beta, const Load& load) {
+  EmitLp e{s_beta, 0.0};
+  for (int q = 0; q < n_terms; ++q) {
+    const DTerm& T = s_terms[q];
+    if ((T.kind == PGB_TERM_INTERCEPT && T.coef_offset == icpt) || (T.fast && q < fast_limit)) continue;
+    eval_term(T, load, e);
+  }
+  return e.lp;
+}
+
+// lp of NR rows (row k through load[k]) -- the fast terms of all NR rows side by side (independent dependency chains).
+// Table of a term: (nint + 2) entries of four coefficients, coefficient-major; entry i < nint is the cubic of knot
+// interval i in powers of t = s - i; entries nint and nint + 1 are the tangent lines at the two edge knots, which is
+// exactly the reference's linear extrapolation (utils.py:744-763), in powers of s and of s - (nint - 1).
+template <int NR, bool OTHER, class Load>
+__device__ __forceinline__ void pass_lp(const PassPlan& P, const DTerm* s_terms, int n_terms, const double* s_beta,
+                                        const double* s_tab, double icpt, const Load (&load)[NR], double (&lp)[NR]) {
+#pragma unroll
+  for (int k = 0; k < NR; ++k) lp[k] = icpt;
+  for (int q = 0; q < P.n_fast; ++q) {
+    const PassSpl& S = P.spl[q];
+    const double lo = S.lo, inv_span = S.inv_span, dn = S.dn;
+    const int ni = S.nint, f = S.feature, pitch = ni + 2;
+    const double* tab = s_tab + S.tab;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const double x = load[k](f);
+      const double u = (x - lo) * inv_span;
+      const double s = u * dn;
+      const double r = __dadd_rd(s, 4503599627370496.0);  // 2^52 + floor(s) for 0 <= s < 2^31
+      const unsigned iu = (unsigned)__double2loint(r);
+      // 0 <= u <= 1 as one unsigned compare of the bit pattern (negative numbers and NaNs are larger)
+      const bool inside = (unsigned long long)__double_as_longlong(u) <= 0x3FF0000000000000ull;
+      const bool below = __double2hiint(u) < 0;
+      const bool top = iu >= (unsigned)ni;  // u == 1: last interval, t = 1 (eval_term does the same)
+      const unsigned i = inside ? (top ? (unsigned)(ni - 1) : iu) : (below ? (unsigned)ni : (unsigned)(ni + 1));
+      const double fl = inside ? (top ? dn - 1.0 : r - 4503599627370496.0) : (below ? 0.0 : dn - 1.0);
+      const double t = s - fl;
+      const double* tb = tab + i;
+      lp[k] += fma(fma(fma(tb[3 * pitch], t, tb[2 * pitch]), t, tb[pitch]), t, tb[0]);
+    }
+  }
+  if (OTHER) {
+#pragma unroll
+    for (int k = 0; k < NR; ++k) lp[k] += pass_other_terms(s_terms, n_terms, P.icpt, P.fast_limit, s_beta, load[k]);
+  }
+}
+
+// link, deviance and the statistics sums of one row
 template <bool HAS_Y, bool FULL>
-__global__ void __launch_bounds__(kPassThreads, 2)
-stats_pass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, int F, Family fam,
-                  const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
-                  const float* __restrict__ w, const double* __restrict__ beta, double scale,
-                  double ybar, int poisson_round, int R, int bulk_ok, double* __restrict__ part,
+__device__ __forceinline__ void pass_finish(const Family& fam, double lp, int64_t gi, double yi, double wi, double scale,
+                                            double ybar, int poisson_round, double* __restrict__ lp_out,
+                                            double* __restrict__ mu_out, double (&acc)[PGB_SS_COUNT]) {
+  const double mu = link_inv(fam, lp);
+  if (lp_out) lp_out[gi] = lp;
+  if (mu_out) mu_out[gi] = mu;
+  if (!isfinite(lp) || !isfinite(mu)) acc[PGB_SS_NONFINITE] += 1.0;
+  if (HAS_Y) {
+    const double d = dist_dev(fam, yi, mu);
+    const double res = yi - mu;
+    acc[PGB_SS_N] += 1.0;
+    acc[PGB_SS_WDEV] += wi * d;
+    acc[PGB_SS_PEARSON] += wi * (res * res) / dist_var(fam, mu);  // distributions.py:78
+    acc[PGB_SS_DEV] += d;
+    acc[PGB_SS_NCORRECT] += (yi == ((mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
+    acc[PGB_SS_SUMY] += yi;
+    acc[PGB_SS_SUMW] += wi;
+    if (FULL) {
+      const double yl = poisson_round ? rint(yi * wi) : yi;  // pygam.py:2797-2798
+      acc[PGB_SS_LOGLIK] += dist_logpdf(fam, yl, mu, wi, scale);
+      acc[PGB_SS_NULL_WDEV] += wi * dist_dev(fam, yi, ybar);
+      acc[PGB_SS_NULL_LOGLIK] += dist_logpdf(fam, yl, ybar, wi, scale);
+    }
+  }
+}
+
+// kPassThreads consumer threads (RPT rows each per tile) + one producer warp
+template <bool HAS_Y, bool FULL, int FAMK, int RPT, bool OTHER>
+__global__ void __launch_bounds__(kPassThreads + 32, 2)
+stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ g_terms, int n_terms, int m, int F,
+                  Family fam_in, const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
+                  const float* __restrict__ w, const double* __restrict__ beta, double scale, double ybar,
+                  int poisson_round, int NS, int64_t n_bulk_tiles, double* __restrict__ part,
                   double* __restrict__ lp_out, double* __restrict__ mu_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int R = RPT * kPassThreads;
+  Family fam = fam_in;
+  if (FAMK == 1) { fam.dist = PGB_DIST_NORMAL; fam.link = PGB_LINK_IDENTITY; }
+  if (FAMK == 2) { fam.dist = PGB_DIST_BINOMIAL; fam.link = PGB_LINK_LOGIT; }
+  if (FAMK == 3) { fam.dist = PGB_DIST_POISSON; fam.link = PGB_LINK_LOG; }
   const int ncol = F + (HAS_Y ? 1 : 0);
-  double* tiles = reinterpret_cast<double*>(smem_raw);                     // [2][ncol][R]
-  float* wtiles = reinterpret_cast<float*>(tiles + (size_t)2 * ncol * R);  // [2][R]
-  double* s_beta = reinterpret_cast<double*>(wtiles + 2 * R);
-  double* s_red = s_beta + ((m + 1) & ~1);
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(s_red + PGB_SS_COUNT * 32);
-  DTerm* s_terms = reinterpret_cast<DTerm*>(mbar + 2);
+  double* tiles = reinterpret_cast<double*>(smem_raw);                      // [NS][ncol][R]
+  float* wtiles = reinterpret_cast<float*>(tiles + (size_t)NS * ncol * R);  // [NS][R]
+  double* s_beta = reinterpret_cast<double*>(wtiles + (size_t)NS * R);
+  double* s_tab = s_beta + ((m + 1) & ~1);
+  double* s_red = s_tab + P.tab_doubles;
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(s_red + PGB_SS_COUNT * 32);  // full[NS], empty[NS]
+  DTerm* s_terms = reinterpret_cast<DTerm*>(mbar + 2 * NS);
   const int tid = threadIdx.x;
   for (int i = tid; i < m; i += blockDim.x) s_beta[i] = beta[i];
   load_terms_smem(s_terms, g_terms, n_terms);
   if (tid == 0) {
-    mbar_init(smem_addr(&mbar[0]), 1);
-    mbar_init(smem_addr(&mbar[1]), 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(smem_addr(&mbar[s]), 1);
+      mbar_init(smem_addr(&mbar[NS + s]), kPassThreads / 32);
+    }
     fence_mbar_init();
   }
   __syncthreads();
-
-  const int64_t n_tiles = (n + R - 1) / R;
+  // one cubic per (fast term, knot interval): p(t) = sum_a beta[c + a] b_a(t) in powers of t; two tangent lines
+  for (int q = 0; q < P.n_fast; ++q) {
+    const PassSpl& S = P.spl[q];
+    const int pitch = S.nint + 2;
+    for (int c = tid; c < pitch; c += blockDim.x) {
+      const int ci = c < S.nint ? c : (c == S.nint ? 0 : S.nint - 1);
+      const double* b = s_beta + S.coef + ci;
+      double c0 = (b[0] + 4.0 * b[1] + b[2]) * (1.0 / 6.0);
+      double c1 = (b[2] - b[0]) * 0.5;
+      double c2 = (b[0] - 2.0 * b[1] + b[2]) * 0.5;
+      double c3 = ((b[3] - b[0]) + 3.0 * (b[1] - b[2])) * (1.0 / 6.0);
+      if (c == S.nint) { c2 = 0.0; c3 = 0.0; }  // below the first knot: p(0) + p'(0) s
+      if (c == S.nint + 1) {                    // above the last knot: p(1) + p'(1) (t - 1)
+        const double p1 = (b[1] + 4.0 * b[2] + b[3]) * (1.0 / 6.0), d1 = (b[3] - b[1]) * 0.5;
+        c0 = p1 - d1; c1 = d1; c2 = 0.0; c3 = 0.0;
+      }
+      double* tb = s_tab + S.tab + c;
+      tb[0] = c0; tb[pitch] = c1; tb[2 * pitch] = c2; tb[3 * pitch] = c3;
+    }
+  }
+  __syncthreads();
   const bool use_w = HAS_Y && (w != nullptr);
-  auto tile_rows = [&](int64_t t) { return (int)min((int64_t)R, n - t * R); };
-  // stage tile t into buffer b: TMA bulk copies for a full aligned tile, plain loads otherwise
-  auto issue = [&](int64_t t, int b) {
-    const int rows = tile_rows(t);
-    const int64_t row0 = t * R;
-    double* dst = tiles + (size_t)b * ncol * R;
-    if (bulk_ok && rows == R) {
-      if (tid == 0) {
-        const uint32_t bar = smem_addr(&mbar[b]);
+  const size_t stage_doubles = (size_t)ncol * R;
+
+  if (tid >= kPassThreads) {
+    // ---- producer warp: one lane keeps NS tiles in flight ----
+    if (tid == kPassThreads) {
+      int stage = 0;
+      int64_t j = 0;
+      for (int64_t t = blockIdx.x; t < n_bulk_tiles; t += gridDim.x, ++j) {
+        if (j >= NS) mbar_wait(smem_addr(&mbar[NS + stage]), (uint32_t)(((j / NS) - 1) & 1));
+        const int64_t row0 = t * R;
+        double* dst = tiles + (size_t)stage * stage_doubles;
+        const uint32_t bar = smem_addr(&mbar[stage]);
         mbar_expect_tx(bar, (uint32_t)(ncol * R * 8 + (use_w ? R * 4 : 0)));
         for (int f = 0; f < F; ++f) bulk_g2s(smem_addr(dst + (size_t)f * R), X + (int64_t)f * ld + row0, R * 8, bar);
         if (HAS_Y) bulk_g2s(smem_addr(dst + (size_t)F * R), y + row0, R * 8, bar);
-        if (use_w) bulk_g2s(smem_addr(wtiles + (size_t)b * R), w + row0, R * 4, bar);
+        if (use_w) bulk_g2s(smem_addr(wtiles + (size_t)stage * R), w + row0, R * 4, bar);
+        if (++stage == NS) stage = 0;
       }
-    } else {
-      for (int e = tid; e < ncol * rows; e += blockDim.x) {
-        const int f = e / rows, r = e - f * rows;
-        dst[(size_t)f * R + r] = (f < F) ? __ldg(X + (int64_t)f * ld + row0 + r) : __ldg(y + row0 + r);
-      }
-      if (use_w)
-        for (int r = tid; r < rows; r += blockDim.x) wtiles[(size_t)b * R + r] = __ldg(w + row0 + r);
     }
-  };
+    return;
+  }
 
+  // ---- consumers ----
+  const double icpt = P.icpt >= 0 ? s_beta[P.icpt] : 0.0;
   double acc[PGB_SS_COUNT];
 #pragma unroll
   for (int s = 0; s < PGB_SS_COUNT; ++s) acc[s] = 0.0;
-  uint32_t phase0 = 0u, phase1 = 0u;
-  int64_t t = blockIdx.x;
-  if (t < n_tiles) issue(t, 0);
-  int b = 0;
-  for (; t < n_tiles; t += gridDim.x, b ^= 1) {
-    const int64_t tn = t + gridDim.x;
-    if (tn < n_tiles) issue(tn, b ^ 1);  // buffer b^1 was released by the barrier that ended the previous iteration
-    const int rows = tile_rows(t);
-    if (bulk_ok && rows == R) {
-      if (b == 0) { mbar_wait(smem_addr(&mbar[0]), phase0); phase0 ^= 1u; }
-      else { mbar_wait(smem_addr(&mbar[1]), phase1); phase1 ^= 1u; }
-    } else {
-      __syncthreads();
-    }
-    const double* tile = tiles + (size_t)b * ncol * R;
-    const float* wt = wtiles + (size_t)b * R;
-    const int64_t row0 = t * R;
-    for (int r = tid; r < rows; r += blockDim.x) {
-      EmitLp e{s_beta, 0.0};
-      const LoadTile load{tile, R, r};
-      for (int q = 0; q < n_terms; ++q) eval_term(s_terms[q], load, e);
-      const double lp = e.lp;
-      const double mu = link_inv(fam, lp);
-      if (lp_out) lp_out[row0 + r] = lp;
-      if (mu_out) mu_out[row0 + r] = mu;
-      if (!isfinite(lp) || !isfinite(mu)) acc[PGB_SS_NONFINITE] += 1.0;
-      if (HAS_Y) {
-        const double yi = tile[(size_t)F * R + r];
-        const double wi = use_w ? (double)wt[r] : 1.0;
-        const double d = dist_dev(fam, yi, mu);
-        const double res = yi - mu;
-        acc[PGB_SS_N] += 1.0;
-        acc[PGB_SS_WDEV] += wi * d;
-        acc[PGB_SS_PEARSON] += wi * (res * res) / dist_var(fam, mu);  // distributions.py:78
-        acc[PGB_SS_DEV] += d;
-        acc[PGB_SS_NCORRECT] += (yi == ((mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
-        acc[PGB_SS_SUMY] += yi;
-        acc[PGB_SS_SUMW] += wi;
-        if (FULL) {
-          const double yl = poisson_round ? rint(yi * wi) : yi;  // pygam.py:2797-2798
-          acc[PGB_SS_LOGLIK] += dist_logpdf(fam, yl, mu, wi, scale);
-          acc[PGB_SS_NULL_WDEV] += wi * dist_dev(fam, yi, ybar);
-          acc[PGB_SS_NULL_LOGLIK] += dist_logpdf(fam, yl, ybar, wi, scale);
-        }
+  // full tiles from the ring
+  {
+    int stage = 0;
+    uint32_t round = 0;
+    for (int64_t t = blockIdx.x; t < n_bulk_tiles; t += gridDim.x) {
+      mbar_wait(smem_addr(&mbar[stage]), round & 1u);
+      const double* tile = tiles + (size_t)stage * stage_doubles;
+      const float* wt = wtiles + (size_t)stage * R;
+      const int64_t row0 = t * R;
+      LoadTile load[RPT];
+      double lp[RPT], yv[RPT], wv[RPT];
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) load[k] = LoadTile{tile, R, tid + k * kPassThreads};
+      pass_lp<RPT, OTHER>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const int r = tid + k * kPassThreads;
+        yv[k] = HAS_Y ? tile[(size_t)F * R + r] : 0.0;
+        wv[k] = use_w ? (double)wt[r] : 1.0;
       }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(smem_addr(&mbar[NS + stage]));  // the stage can be refilled
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) pass_finish<HAS_Y, FULL>(fam, lp[k], row0 + tid + k * kPassThreads, yv[k], wv[k], scale, ybar, poisson_round, lp_out, mu_out, acc);
+      if (++stage == NS) { stage = 0; ++round; }
     }
-    __syncthreads();  // everyone is done with buffer b before it is refilled two tiles from now
   }
-  block_reduce_store<PGB_SS_COUNT>(acc, s_red, part + (int64_t)blockIdx.x * PGB_SS_COUNT);
+  // the remaining rows (and inputs that are not 16-byte aligned) with plain loads
+  for (int64_t i = n_bulk_tiles * R + (int64_t)blockIdx.x * kPassThreads + tid; i < n; i += (int64_t)gridDim.x * kPassThreads) {
+    const LoadGlobal load[1] = {LoadGlobal{X, ld, i}};
+    double lp[1];
+    pass_lp<1, OTHER>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp);
+    pass_finish<HAS_Y, FULL>(fam, lp[0], i, HAS_Y ? __ldg(y + i) : 0.0, use_w ? (double)__ldg(w + i) : 1.0, scale, ybar, poisson_round,
+                            lp_out, mu_out, acc);
+  }
+  // fixed-order sum of the consumer threads (the producer warp has left: a named barrier of the consumers only)
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int s = 0; s < PGB_SS_COUNT; ++s) {
+      double v = acc[s];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) s_red[s * 32 + warp] = v;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kPassThreads) : "memory");
+    if (tid < PGB_SS_COUNT) {
+      double v = 0.0;
+      for (int wq = 0; wq < kPassThreads / 32; ++wq) v += s_red[tid * 32 + wq];
+      part[(int64_t)blockIdx.x * PGB_SS_COUNT + tid] = v;
+    }
+  }
+}
+
+template <bool HAS_Y, bool FULL, int FAMK, int RPT, bool OTHER>
+static int stats_pass_launch(const PassPlan& P, const pgb_model* M, int grid, size_t smem, cudaStream_t st, const double* X,
+                             int64_t n, int64_t ld, const double* y, const float* w, const double* beta, double scale,
+                             double ybar, int poisson_round, int NS, int64_t n_bulk_tiles, double* part, double* lp_out,
+                             double* mu_out) {
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<HAS_Y, FULL, FAMK, RPT, OTHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kSmemMax));
+    attr_set = true;
+  }
+  stats_pass_kernel<HAS_Y, FULL, FAMK, RPT, OTHER><<<grid, kPassThreads + 32, smem, st>>>(
+      P, M->d_terms, M->n_terms, M->m, M->n_features, M->fam, X, n, ld, y, w, beta, scale, ybar, poisson_round, NS,
+      n_bulk_tiles, part, lp_out, mu_out);
+  return PGB_OK;
 }
 
 extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, int64_t ld,
@@ -498,36 +667,64 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
   if (!M || !X || !beta || n < 1 || ld < n) { pgb_set_error("pgb_stats_pass: bad arguments"); return PGB_EINVAL; }
   if (ws_bytes < pgb_stats_ws_bytes(M) || !ws) { pgb_set_error("pgb_stats_pass: workspace too small"); return PGB_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
+  PassPlan P;
+  pass_plan_build(M, P);
   const int F = M->n_features, ncol = F + (y ? 1 : 0);
-  const size_t fixed = (size_t)((M->m + 1) & ~1) * 8 + PGB_SS_COUNT * 32 * 8 + 16 + (size_t)M->n_terms * sizeof(DTerm);
-  // rows per tile: two stages per CTA, two CTAs per SM
-  int R = 1024;
-  while (R > 256 && fixed + (size_t)2 * R * (ncol * 8 + 4) > kSmemMax / 2 - 2048) R -= 256;
-  const size_t smem = fixed + (size_t)2 * R * (ncol * 8 + 4);
-  if (smem > kSmemMax) {
+  const size_t fixed = (size_t)((M->m + 1) & ~1) * 8 + (size_t)P.tab_doubles * 8 + PGB_SS_COUNT * 32 * 8 + 2 * 8 * 8 +
+                       (size_t)M->n_terms * sizeof(DTerm);
+  const size_t rowbytes = (size_t)ncol * 8 + 4;
+  // stages of R = RPT * 256 rows: two CTAs per SM when at least two stages fit in half of the shared memory; two rows
+  // per thread when that still leaves two stages (three for narrow rows)
+  int occ = 2, NS = 0, RPT = 1;
+  for (; occ >= 1; --occ) {
+    const size_t budget = (occ == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024);
+    if (budget <= fixed) continue;
+    const size_t stages1 = (budget - fixed) / (kPassThreads * rowbytes);
+    if (stages1 >= 2) {
+      if (stages1 >= 4 && !(y && scale > 0.0) && !P.n_other) RPT = 2;
+      NS = (int)std::min<size_t>(4, stages1 / RPT);
+      break;
+    }
+  }
+  if (NS < 2) {
     pgb_set_error("pgb_stats_pass: %d features do not fit the staging tiles", F);
     return PGB_EUNSUPPORTED;
   }
+  const int R = RPT * kPassThreads;
+  const size_t smem = fixed + (size_t)NS * R * rowbytes;
   // TMA bulk copies need 16-byte aligned sources: every column start and every tile start
   const bool bulk_ok = ((uintptr_t)X % 16 == 0) && (ld % 2 == 0) && (!y || (uintptr_t)y % 16 == 0) &&
                        (!w || (uintptr_t)w % 16 == 0);
-  const int64_t n_tiles = (n + R - 1) / R;
-  const int grid = (int)std::min<int64_t>(n_tiles, std::min(M->pass_ctas, kSMs * 2));
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    attr_set = true;
+  const int64_t n_bulk_tiles = bulk_ok ? n / R : 0;
+  const int64_t n_units = std::max<int64_t>(n_bulk_tiles, (n - n_bulk_tiles * R + kPassThreads - 1) / kPassThreads);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, std::min(M->pass_ctas, kSMs * occ)));
+  const Family& fm = M->fam;
+  const int famk = (fm.dist == PGB_DIST_NORMAL && fm.link == PGB_LINK_IDENTITY)   ? 1
+                   : (fm.dist == PGB_DIST_BINOMIAL && fm.link == PGB_LINK_LOGIT) ? 2
+                   : (fm.dist == PGB_DIST_POISSON && fm.link == PGB_LINK_LOG)    ? 3
+                                                                                 : 0;
+  int rc = PGB_OK;
+#define PGB_STATS_ARGS P, M, grid, smem, st, X, n, ld, y, w, beta, scale, ybar, poisson_round, NS, n_bulk_tiles, (double*)ws, lp_out, mu_out
+#define PGB_STATS_FAM(HY, FL, RP, OT)                                             \
+  switch (famk) {                                                                 \
+    case 1: rc = stats_pass_launch<HY, FL, 1, RP, OT>(PGB_STATS_ARGS); break;     \
+    case 2: rc = stats_pass_launch<HY, FL, 2, RP, OT>(PGB_STATS_ARGS); break;     \
+    case 3: rc = stats_pass_launch<HY, FL, 3, RP, OT>(PGB_STATS_ARGS); break;     \
+    default: rc = stats_pass_launch<HY, FL, 0, RP, OT>(PGB_STATS_ARGS); break;    \
   }
-#define PGB_STATS_LAUNCH(HY, FL)                                                                              \
-  stats_pass_kernel<HY, FL><<<grid, kPassThreads, smem, st>>>(M->d_terms, M->n_terms, M->m, F, M->fam, X, n, ld, \
-                                                              y, w, beta, scale, ybar, poisson_round, R,      \
-                                                              bulk_ok ? 1 : 0, (double*)ws, lp_out, mu_out)
-  if (!y) PGB_STATS_LAUNCH(false, false);
-  else if (scale > 0.0) PGB_STATS_LAUNCH(true, true);
-  else PGB_STATS_LAUNCH(true, false);
-#undef PGB_STATS_LAUNCH
+#define PGB_STATS_RPT(HY, FL)                                  \
+  if (P.n_other) { PGB_STATS_FAM(HY, FL, 1, true) }            \
+  else if (RPT == 2) { PGB_STATS_FAM(HY, FL, 2, false) }       \
+  else { PGB_STATS_FAM(HY, FL, 1, false) }
+  if (y && scale > 0.0) {
+    if (P.n_other) { PGB_STATS_FAM(true, true, 1, true) }
+    else { PGB_STATS_FAM(true, true, 1, false) }
+  } else if (!y) { PGB_STATS_RPT(false, false) }
+  else { PGB_STATS_RPT(true, false) }
+#undef PGB_STATS_RPT
+#undef PGB_STATS_FAM
+#undef PGB_STATS_ARGS
+  if (rc != PGB_OK) return rc;
   PGB_LAUNCHED(1);
   PGB_CUDA(cudaGetLastError());
   if (scalars) {
@@ -537,4 +734,3 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
   }
   return PGB_OK;
 }
-

@@ -78,4 +78,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
                  : "memory");
   } while (!done);
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

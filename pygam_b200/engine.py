@@ -33,8 +33,11 @@ class DeviceData:
     def __init__(self, Xt, y=None, w=None):
         if not (isinstance(Xt, torch.Tensor) and Xt.dtype == torch.float64 and Xt.dim() == 2):
             raise ValueError("Xt must be a 2-d float64 tensor of shape (n_features, n_rows)")
-        self.Xt = Xt.contiguous()
+        # rows of Xt (feature columns) must be unit-stride; the leading dimension may be padded (from_host pads it to
+        # a multiple of 16 rows so that every column starts 16-byte aligned: the TMA bulk copies of the O(k) passes)
+        self.Xt = Xt if (Xt.stride(1) == 1 and Xt.stride(0) >= Xt.shape[1]) or Xt.shape[0] <= 1 else Xt.contiguous()
         self.n_features, self.n = self.Xt.shape
+        self.ld = self.Xt.stride(0) if self.n_features > 1 else self.n
         self.y = None if y is None else y.to(device=Xt.device, dtype=torch.float64).contiguous()
         self.w = None if w is None else w.to(device=Xt.device, dtype=torch.float32).contiguous()
         if self.y is not None and self.y.numel() != self.n:
@@ -59,7 +62,11 @@ class DeviceData:
         X = np.asarray(X)
         if X.ndim == 1:
             X = X[:, None]
-        Xt = torch.from_numpy(np.ascontiguousarray(X.T, dtype=np.float64)).to(device)
+        n, F = X.shape
+        ld = (n + 15) // 16 * 16
+        buf = torch.zeros((F, ld), dtype=torch.float64, device=device)
+        Xt = buf[:, :n]
+        Xt.copy_(torch.from_numpy(np.ascontiguousarray(X.T, dtype=np.float64)))
         yt = None if y is None else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64).ravel()).to(device)
         wt = None if w is None else torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32).ravel()).to(device)
         return cls(Xt, yt, wt)
@@ -98,7 +105,7 @@ def _cuda_column_stats(data):
     minmax = torch.empty(2 * F, dtype=torch.float64, device=data.device)
     bad = torch.empty(F, dtype=torch.int64, device=data.device)
     ws = torch.empty(int(lib.pgb_col_stats_ws_bytes(F)) // 8 + 1, dtype=torch.float64, device=data.device)
-    _lib.check(lib.pgb_col_stats(_ptr(data.Xt), data.n, data.n, F, _ptr(minmax), _ptr(bad), _ptr(ws),
+    _lib.check(lib.pgb_col_stats(_ptr(data.Xt), data.n, data.ld, F, _ptr(minmax), _ptr(bad), _ptr(ws),
                                  ws.numel() * 8, _stream()), "pgb_col_stats")
     mm = minmax.view(F, 2)
     lo = all_reduce_(mm[:, 0].contiguous(), "min")
@@ -283,7 +290,7 @@ class Engine:
             return 0
         key = (data.Xt.data_ptr(), data.n, ws.data_ptr(), data.Xt._version)
         if self._plan_key != key:
-            _lib.check(self.lib.pgb_gram_prepare(self.handle, _ptr(data.Xt), data.n, data.n, _ptr(ws), ws.numel() * 8,
+            _lib.check(self.lib.pgb_gram_prepare(self.handle, _ptr(data.Xt), data.n, data.ld, _ptr(ws), ws.numel() * 8,
                                                  _stream()), "pgb_gram_prepare")
             self._plan_key = key
             self._plan_data = data.Xt  # keeps the tensor (and its address) alive as long as the plan
@@ -296,7 +303,7 @@ class Engine:
         if coef is not None:
             self.beta.copy_(torch.as_tensor(coef, dtype=torch.float64))
         mode = mode | self._planned(data, ws)
-        _lib.check(self.lib.pgb_gram_pass(self.handle, mode, _ptr(data.Xt), data.n, data.n, _ptr(data.y),
+        _lib.check(self.lib.pgb_gram_pass(self.handle, mode, _ptr(data.Xt), data.n, data.ld, _ptr(data.y),
                                           _ptr(data.w), _ptr(self.beta), _ptr(self.out), _ptr(ws),
                                           ws.numel() * 8, _stream()), "pgb_gram_pass")
         if reduce:
@@ -362,7 +369,7 @@ class Engine:
         self.beta.copy_(torch.as_tensor(coef, dtype=torch.float64))
         mu = torch.empty(data.n, dtype=torch.float64, device=self.device) if want_mu else None
         lp = torch.empty(data.n, dtype=torch.float64, device=self.device) if want_lp else None
-        _lib.check(self.lib.pgb_stats_pass(self.handle, _ptr(data.Xt), data.n, data.n, _ptr(data.y), _ptr(data.w),
+        _lib.check(self.lib.pgb_stats_pass(self.handle, _ptr(data.Xt), data.n, data.ld, _ptr(data.y), _ptr(data.w),
                                            _ptr(self.beta), float(scale), float(ybar), 1 if poisson_round else 0,
                                            _ptr(self.stat_scalars), _ptr(lp), _ptr(mu), _ptr(self._stats_ws),
                                            self._stats_ws.numel() * 8, _stream()), "pgb_stats_pass")
@@ -379,13 +386,13 @@ class Engine:
         if cov is not None:
             covd = torch.from_numpy(np.ascontiguousarray(cov, dtype=np.float64)).to(self.device)
             var = torch.empty(data.n, dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.pgb_interval_pass(self.handle, _ptr(data.Xt), data.n, data.n, _ptr(self.beta), _ptr(covd),
+        _lib.check(self.lib.pgb_interval_pass(self.handle, _ptr(data.Xt), data.n, data.ld, _ptr(self.beta), _ptr(covd),
                                               int(term), _ptr(lp), _ptr(var), _stream()), "pgb_interval_pass")
         return lp, var
 
     def model_matrix(self, data):
         out = torch.empty(data.n * self.m, dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.pgb_model_matrix(self.handle, _ptr(data.Xt), data.n, data.n, _ptr(out), _stream()),
+        _lib.check(self.lib.pgb_model_matrix(self.handle, _ptr(data.Xt), data.n, data.ld, _ptr(out), _stream()),
                    "pgb_model_matrix")
         return out.view(data.n, self.m)
 

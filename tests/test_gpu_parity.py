@@ -121,6 +121,37 @@ def test_stats_pass_matches_oracle(name):
         assert abs(sc[k] - scr[k]) <= 1e-11 * max(1.0, abs(scr[k])), (k, sc[k], scr[k])
 
 
+@pytest.mark.parametrize("name", ["c2_logistic", "c3_poisson", "c5_expectile"])
+def test_stats_pass_extrapolated_rows_and_unaligned_inputs(name):
+    """rows outside the edge knots (the tangent-line entries of the per-interval polynomial table, utils.py:744-763)
+    and inputs the TMA ring cannot take (odd leading dimension: plain loads) against the oracle"""
+    case = cases.FIT_CASES[name]
+    g = load("fit_" + name)
+    gam, eng, ora = _compiled(case, g)
+    cpu = _cpu_data(g, case)
+    X = cpu.Xt.numpy().T.copy()
+    lo, hi = X.min(axis=0), X.max(axis=0)
+    X = lo + (X - lo) * 1.3 - 0.15 * (hi - lo)  # ~23 % of every feature outside [lo, hi], both sides
+    X[0, :] = lo  # exactly on the edge knots
+    X[1, :] = hi
+    n = X.shape[0] - (1 - X.shape[0] % 2)  # odd number of rows
+    for rows, padded in ((X.shape[0], True), (n, False)):
+        c = DeviceData.from_host(X[:rows], cpu.y.numpy()[:rows], None if cpu.w is None else cpu.w.numpy()[:rows], device="cpu")
+        if padded:
+            gpu = DeviceData.from_host(X[:rows], cpu.y.numpy()[:rows], None if cpu.w is None else cpu.w.numpy()[:rows])
+            assert gpu.ld % 2 == 0
+        else:
+            gpu = DeviceData(torch.from_numpy(np.ascontiguousarray(X[:rows].T)).cuda(), c.y.cuda(), None if c.w is None else c.w.cuda())
+            assert gpu.ld % 2 == 1
+        sc, lp, mu = eng.stats_pass(gpu, g["coef"], want_mu=True, want_lp=True)
+        scr, lpr, mur = ora.stats_pass(c, g["coef"], want_mu=True, want_lp=True)
+        assert helpers.rel(lp.cpu().numpy(), lpr.numpy()) < 1e-12
+        fin = np.isfinite(mur.numpy())
+        assert helpers.rel(mu.cpu().numpy()[fin], mur.numpy()[fin]) < 1e-11
+        for k in (_lib.SS_N, _lib.SS_SUMY):
+            assert abs(sc[k] - scr[k]) <= 1e-11 * max(1.0, abs(scr[k])), (k, sc[k], scr[k])
+
+
 @pytest.mark.parametrize("name", ["c1_wage", "c2_logistic", "c3_poisson", "mixed_terms", "no_intercept",
                                   "c5_expectile"])
 def test_solve_matches_numpy_mirror(name):

@@ -35,7 +35,7 @@ if h:
     col = lambda name: next((i for i, c in enumerate(H) if c.startswith(name)), None)
     ist, iex = col("Warp Stall Sampling (All"), col("Instructions Executed")
     iwf = H.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in H else None
-    body = [r for r in rows[h[0] + 1:] if len(r) == len(H)]
+    body = [r for r in rows[h[0] + 1:] if len(r) == len(H) and r[isrc] != "Source"]
     tot = sum(float(r[ist] or 0) for r in body) or 1.0
     # position of every instruction in program order, and a coarse histogram over the kernel
     nb = 12

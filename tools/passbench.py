@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--case", default="c4_linear")
     ap.add_argument("--rows", type=int, default=32_000_000)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around one call of each pass "
+                    "(ncu --profile-from-start off)")
     a = ap.parse_args()
     gen, F = GEN[a.case]
     Xs, ys = gen(20000)
@@ -59,6 +61,12 @@ def main():
                                           P(eng.stat_scalars), C.c_void_p(0), P(mu_out), P(ws), ws.numel() * 8, st), name)
         for _ in range(3):
             call()
+        if a.profile:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            call()
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
