@@ -400,17 +400,17 @@ extern "C" int pgb_interval_pass(const pgb_model* M, const double* X, int64_t n,
 //  * rows after the last full tile, and inputs that are not 16-byte aligned, are read with plain loads.
 #define PGB_PASS_MAX_FAST 48
 struct PassSpl {
-  double lo, inv_span, dn;
-  int32_t feature, nint, coef, tab;  // tab: offset of the term's polynomial table in s_tab (doubles)
+  double lo, scale, dn;  // s = (x - lo) * scale is the position in knot intervals, scale = nint / span
+  int32_t feature, nint, coef, pad;
 };
 struct PassPlan {
-  int32_t n_fast, n_other, icpt, tab_doubles, fast_limit, pad;
+  int32_t n_fast, n_other, icpt, tab_doubles, fast_limit, pitch;  // pitch: table entries per term (max nint + 2)
   int16_t term[PGB_PASS_MAX_FAST];
   PassSpl spl[PGB_PASS_MAX_FAST];
 };
 
 static void pass_plan_build(const pgb_model* M, PassPlan& P) {
-  P.n_fast = P.n_other = P.tab_doubles = P.pad = 0;
+  P.n_fast = P.n_other = P.tab_doubles = P.pitch = 0;
   P.icpt = -1;
   P.fast_limit = M->n_terms;
   for (int q = 0; q < M->n_terms; ++q) {
@@ -419,13 +419,15 @@ static void pass_plan_build(const pgb_model* M, PassPlan& P) {
     if (T.fast && P.n_fast < PGB_PASS_MAX_FAST && q < P.fast_limit) {
       const DMarg& g = T.marg[0];
       P.term[P.n_fast] = (int16_t)q;
-      P.spl[P.n_fast++] = PassSpl{g.lo, g.inv_span, (double)g.nint, g.feature, g.nint, T.coef_offset, P.tab_doubles};
-      P.tab_doubles += 4 * (g.nint + 2);
+      P.spl[P.n_fast++] = PassSpl{g.lo, g.inv_span * (double)g.nint, (double)g.nint, g.feature, g.nint, T.coef_offset, 0};
+      P.pitch = std::max(P.pitch, g.nint + 2);
       continue;
     }
     if (T.fast && P.fast_limit == M->n_terms) P.fast_limit = q;  // fast terms from here on take the general path
     ++P.n_other;
   }
+  P.pitch |= 1;  // odd pitch: the four coefficient arrays of an entry start in different banks
+  P.tab_doubles = 4 * P.pitch * P.n_fast;
 }
 
 // the terms that are not in the plan (f(), l(), te(), by=, other orders, cyclic bases): the general evaluation
@@ -442,35 +444,54 @@ __device__ __forceinline__ double pass_other_terms(const DTerm* s_terms, int n_t
 }
 
 // lp of NR rows (row k through load[k]) -- the fast terms of all NR rows side by side (independent dependency chains).
-// Table of a term: (nint + 2) entries of four coefficients, coefficient-major; entry i < nint is the cubic of knot
-// interval i in powers of t = s - i; entries nint and nint + 1 are the tangent lines at the two edge knots, which is
-// exactly the reference's linear extrapolation (utils.py:744-763), in powers of s and of s - (nint - 1).
+// Table of term q: s_tab[(4 q + p) * pitch + e], p = power, e = 1 + floor(s) clamped to 0 .. nint + 1.  Entry e in
+// 1 .. nint is the cubic of knot interval e - 1; entries 0 and nint + 1 are the tangent lines at the two edge knots,
+// which is exactly the reference's linear extrapolation (utils.py:744-763); all in powers of s - (e - 1).
+// The first loop assumes 0 <= s < nint and only notes when that fails (a feature outside the edge knots or on the last
+// one, or a NaN); such a row is evaluated again by the second loop, which clamps the entry (a NaN stays a NaN: fmax
+// drops it from the entry choice, the power keeps it).
 template <int NR, bool OTHER, class Load>
 __device__ __forceinline__ void pass_lp(const PassPlan& P, const DTerm* s_terms, int n_terms, const double* s_beta,
                                         const double* s_tab, double icpt, const Load (&load)[NR], double (&lp)[NR]) {
+  const double kC = 4503599627370497.0;  // 2^52 + 1: RD(s + kC) = kC + floor(s), exact for -1 <= s < 2^32
+  unsigned bad[NR];
 #pragma unroll
-  for (int k = 0; k < NR; ++k) lp[k] = icpt;
-  for (int q = 0; q < P.n_fast; ++q) {
-    const PassSpl& S = P.spl[q];
-    const double lo = S.lo, inv_span = S.inv_span, dn = S.dn;
-    const int ni = S.nint, f = S.feature, pitch = ni + 2;
-    const double* tab = s_tab + S.tab;
+  for (int k = 0; k < NR; ++k) { lp[k] = icpt; bad[k] = 0u; }
+  const int pitch = P.pitch;
+  {
+    const double* tab = s_tab;
+    for (int q = 0; q < P.n_fast; ++q, tab += 4 * pitch) {
+      const PassSpl& S = P.spl[q];
+      const double lo = S.lo, scale = S.scale;
+      const int f = S.feature;
+      const unsigned ni = (unsigned)S.nint;
 #pragma unroll
-    for (int k = 0; k < NR; ++k) {
-      const double x = load[k](f);
-      const double u = (x - lo) * inv_span;
-      const double s = u * dn;
-      const double r = __dadd_rd(s, 4503599627370496.0);  // 2^52 + floor(s) for 0 <= s < 2^31
-      const unsigned iu = (unsigned)__double2loint(r);
-      // 0 <= u <= 1 as one unsigned compare of the bit pattern (negative numbers and NaNs are larger)
-      const bool inside = (unsigned long long)__double_as_longlong(u) <= 0x3FF0000000000000ull;
-      const bool below = __double2hiint(u) < 0;
-      const bool top = iu >= (unsigned)ni;  // u == 1: last interval, t = 1 (eval_term does the same)
-      const unsigned i = inside ? (top ? (unsigned)(ni - 1) : iu) : (below ? (unsigned)ni : (unsigned)(ni + 1));
-      const double fl = inside ? (top ? dn - 1.0 : r - 4503599627370496.0) : (below ? 0.0 : dn - 1.0);
-      const double t = s - fl;
-      const double* tb = tab + i;
-      lp[k] += fma(fma(fma(tb[3 * pitch], t, tb[2 * pitch]), t, tb[pitch]), t, tb[0]);
+      for (int k = 0; k < NR; ++k) {
+        const double s = (load[k](f) - lo) * scale;
+        const double r = __dadd_rd(s, kC);
+        const unsigned e = (unsigned)__double2loint(r);
+        bad[k] |= (unsigned)(__double2hiint(r) ^ 0x43300000) | (unsigned)(e - 1u >= ni);
+        const double* tb = tab + min(e, ni + 1u);  // in bounds whatever s was
+        const double t = s - (r - kC);
+        lp[k] += fma(fma(fma(tb[3 * pitch], t, tb[2 * pitch]), t, tb[pitch]), t, tb[0]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    if (bad[k]) {
+      double v = icpt;
+      const double* tab = s_tab;
+#pragma unroll 1
+      for (int q = 0; q < P.n_fast; ++q, tab += 4 * pitch) {
+        const PassSpl& S = P.spl[q];
+        const double s = (load[k](S.feature) - S.lo) * S.scale;
+        const double r = __dadd_rd(fmin(fmax(s, -1.0), S.dn), kC);
+        const double* tb = tab + __double2loint(r);
+        const double t = s - (r - kC);
+        v += fma(fma(fma(tb[3 * pitch], t, tb[2 * pitch]), t, tb[pitch]), t, tb[0]);
+      }
+      lp[k] = v;
     }
   }
   if (OTHER) {
@@ -543,20 +564,21 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
   // one cubic per (fast term, knot interval): p(t) = sum_a beta[c + a] b_a(t) in powers of t; two tangent lines
   for (int q = 0; q < P.n_fast; ++q) {
     const PassSpl& S = P.spl[q];
-    const int pitch = S.nint + 2;
-    for (int c = tid; c < pitch; c += blockDim.x) {
-      const int ci = c < S.nint ? c : (c == S.nint ? 0 : S.nint - 1);
+    const int pitch = P.pitch;
+    for (int e = tid; e < S.nint + 2; e += blockDim.x) {
+      const int ci = e == 0 ? 0 : (e > S.nint ? S.nint - 1 : e - 1);
       const double* b = s_beta + S.coef + ci;
       double c0 = (b[0] + 4.0 * b[1] + b[2]) * (1.0 / 6.0);
       double c1 = (b[2] - b[0]) * 0.5;
       double c2 = (b[0] - 2.0 * b[1] + b[2]) * 0.5;
       double c3 = ((b[3] - b[0]) + 3.0 * (b[1] - b[2])) * (1.0 / 6.0);
-      if (c == S.nint) { c2 = 0.0; c3 = 0.0; }  // below the first knot: p(0) + p'(0) s
-      if (c == S.nint + 1) {                    // above the last knot: p(1) + p'(1) (t - 1)
-        const double p1 = (b[1] + 4.0 * b[2] + b[3]) * (1.0 / 6.0), d1 = (b[3] - b[1]) * 0.5;
-        c0 = p1 - d1; c1 = d1; c2 = 0.0; c3 = 0.0;
+      if (e == 0) { c0 -= c1; c2 = 0.0; c3 = 0.0; }  // below the first knot: p(0) + p'(0) s, in powers of s + 1
+      if (e > S.nint) {                              // above the last knot: p(1) + p'(1) (s - nint)
+        c0 = (b[1] + 4.0 * b[2] + b[3]) * (1.0 / 6.0);
+        c1 = (b[3] - b[1]) * 0.5;
+        c2 = 0.0; c3 = 0.0;
       }
-      double* tb = s_tab + S.tab + c;
+      double* tb = s_tab + (size_t)4 * q * pitch + e;
       tb[0] = c0; tb[pitch] = c1; tb[2 * pitch] = c2; tb[3 * pitch] = c3;
     }
   }
