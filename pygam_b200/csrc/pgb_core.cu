@@ -438,6 +438,31 @@ __device__ __forceinline__ double pass_other_terms(const DTerm* s_terms, int n_t
   for (int q = 0; q < n_terms; ++q) {
     const DTerm& T = s_terms[q];
     if ((T.kind == PGB_TERM_INTERCEPT && T.coef_offset == icpt) || (T.fast && q < fast_limit)) continue;
+    if (T.kind == PGB_TERM_TENSOR && T.n_marg == 2 && T.by < 0 && T.marg[0].order == 3 && T.marg[1].order == 3 &&
+        !T.marg[0].periodic && !T.marg[1].periodic) {
+      // te() of two cubic marginals inside its edge knots, straight line: two interval searches, two closed-form
+      // cubic bases, 4 x 4 coefficients (utils.py:943-946: first marginal slowest)
+      const DMarg& g0 = T.marg[0];
+      const DMarg& g1 = T.marg[1];
+      const double u0 = (load(g0.feature) - g0.lo) * g0.inv_span, u1 = (load(g1.feature) - g1.lo) * g1.inv_span;
+      if ((unsigned long long)__double_as_longlong(u0) <= 0x3FF0000000000000ull &&
+          (unsigned long long)__double_as_longlong(u1) <= 0x3FF0000000000000ull) {
+        const double s0 = u0 * (double)g0.nint, s1 = u1 * (double)g1.nint;
+        const int i0 = min((int)s0, g0.nint - 1), i1 = min((int)s1, g1.nint - 1);
+        double a[4], b[4];
+        cubic_bspline(s0 - (double)i0, a[0], a[1], a[2], a[3]);
+        cubic_bspline(s1 - (double)i1, b[0], b[1], b[2], b[3]);
+        const double* cb = s_beta + T.coef_offset + i0 * g1.nspl + i1;
+        double v = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double* c = cb + r * g1.nspl;
+          v = fma(a[r], fma(b[3], c[3], fma(b[2], c[2], fma(b[1], c[1], b[0] * c[0]))), v);
+        }
+        e.lp += v;
+        continue;
+      }
+    }
     eval_term(T, load, e);
   }
   return e.lp;

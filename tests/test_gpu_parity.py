@@ -277,6 +277,39 @@ def _device_c2(n, seed):
     return DeviceData(Xt, y)
 
 
+def test_stats_pass_sums_match_written_mu_and_add_over_row_shards():
+    """4e6 rows of config 2: the sums of the statistics pass equal the same sums taken (torch, fp64) from the mu the
+    predict pass writes; shards with a ragged tail and an odd leading dimension (plain loads) add up to the whole"""
+    n = 4_000_000
+    data = _device_c2(n, 91)
+    gam = helpers.build_model(cases.FIT_CASES["c2_logistic"], max_iter=2)
+    gam.fit(data)
+    eng = gam._engine
+    coef = gam.coef_
+    sc, _, _ = eng.stats_pass(data, coef, reduce=False)
+    _, lp, mu = eng.stats_pass(DeviceData(data.Xt), coef, want_mu=True, want_lp=True, reduce=False)
+    y = data.y
+    assert sc[_lib.SS_N] == n and sc[_lib.SS_NONFINITE] == 0
+    assert abs(sc[_lib.SS_SUMY] - float(y.sum())) <= 1e-12 * n
+    assert float((mu - torch.sigmoid(lp)).abs().max()) < 1e-15 * 8
+    dev = float((-2.0 * torch.log(torch.where(y == 1.0, mu, 1.0 - mu))).sum())
+    pearson = float(((y - mu) ** 2 / (mu * (1.0 - mu))).sum())
+    assert abs(sc[_lib.SS_DEV] - dev) <= 1e-12 * dev
+    assert abs(sc[_lib.SS_WDEV] - dev) <= 1e-12 * dev
+    assert abs(sc[_lib.SS_PEARSON] - pearson) <= 1e-12 * pearson
+    assert sc[_lib.SS_NCORRECT] == float((y == (mu > 0.5).double()).sum())
+    h = 1_234_567  # odd: the second shard starts 8-byte aligned only
+    a, _, _ = eng.stats_pass(DeviceData(data.Xt[:, :h].contiguous(), y[:h].contiguous()), coef, reduce=False)
+    b, _, _ = eng.stats_pass(DeviceData(data.Xt[:, h:].contiguous(), y[h:].contiguous()), coef, reduce=False)
+    for k in (_lib.SS_N, _lib.SS_NCORRECT, _lib.SS_SUMY):
+        assert a[k] + b[k] == sc[k]
+    for k in (_lib.SS_DEV, _lib.SS_PEARSON):
+        assert abs(a[k] + b[k] - sc[k]) <= 1e-12 * abs(sc[k])
+    # bit-reproducible run to run
+    sc2, _, _ = eng.stats_pass(data, coef, reduce=False)
+    assert np.array_equal(sc, sc2)
+
+
 def test_gram_is_additive_over_row_shards_and_oracle_checked_on_a_prefix():
     """G, r and the scalars of 2e6 rows equal the sum over two row shards (what the all-reduce
     relies on), and the Gram of a 20k-row prefix equals the oracle's"""

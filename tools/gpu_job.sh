@@ -1,8 +1,7 @@
 set -x
 mkdir -p gpurun_out
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1_final_n1.json 2> gpurun_out/bench_r1_final_n1.err; echo "bench exit $?"
-cat gpurun_out/bench_r1_final_n1.json
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1_final_ref.json 2> gpurun_out/bench_r1_final_ref.err; echo "ref exit $?"
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu28.log 2>&1
-tail -n 3 gpurun_out/ncu28.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest46.log 2>&1; echo "pytest exit $?"
+tail -n 8 gpurun_out/pytest46.log
+timeout 300 python tools/passbench.py --case c3_poisson --rows 4000000 > gpurun_out/pb6.log 2>&1
+timeout 300 python tools/passbench.py --case c2_logistic --rows 16000000 >> gpurun_out/pb6.log 2>&1
+cat gpurun_out/pb6.log
