@@ -403,14 +403,26 @@ struct PassSpl {
   double lo, scale, dn;  // s = (x - lo) * scale is the position in knot intervals, scale = nint / span
   int32_t feature, nint, coef, pad;
 };
+#define PGB_PASS_MAX_TE 8
+struct PassTe {  // te() of two cubic marginals: s_q = (x_q - lo_q) * scale_q, nint_q intervals, k1 = n_splines of marginal 1
+  double lo0, scale0, lo1, scale1;
+  int32_t f0, f1, n0, n1, k1, coef;
+};
+__host__ __device__ inline bool pass_te_eligible(const DTerm& T) {
+  return T.kind == PGB_TERM_TENSOR && T.n_marg == 2 && T.by < 0 && T.marg[0].order == 3 && T.marg[1].order == 3 &&
+         !T.marg[0].periodic && !T.marg[1].periodic;
+}
 struct PassPlan {
   int32_t n_fast, n_other, icpt, tab_doubles, fast_limit, pitch;  // pitch: table entries per term (max nint + 2)
+  int32_t n_te, te_limit;
+  PassTe te[PGB_PASS_MAX_TE];
   int16_t term[PGB_PASS_MAX_FAST];
   PassSpl spl[PGB_PASS_MAX_FAST];
 };
 
 static void pass_plan_build(const pgb_model* M, PassPlan& P) {
-  P.n_fast = P.n_other = P.tab_doubles = P.pitch = 0;
+  P.n_fast = P.n_other = P.tab_doubles = P.pitch = P.n_te = 0;
+  P.te_limit = M->n_terms;
   P.icpt = -1;
   P.fast_limit = M->n_terms;
   for (int q = 0; q < M->n_terms; ++q) {
@@ -423,6 +435,16 @@ static void pass_plan_build(const pgb_model* M, PassPlan& P) {
       P.pitch = std::max(P.pitch, g.nint + 2);
       continue;
     }
+    if (pass_te_eligible(T) && q < P.te_limit) {
+      if (P.n_te < PGB_PASS_MAX_TE) {
+        const DMarg& a = T.marg[0];
+        const DMarg& b = T.marg[1];
+        P.te[P.n_te++] = PassTe{a.lo, a.inv_span * (double)a.nint, b.lo, b.inv_span * (double)b.nint,
+                                a.feature, b.feature, a.nint, b.nint, b.nspl, T.coef_offset};
+        continue;
+      }
+      P.te_limit = q;  // tensor terms from here on take the general path
+    }
     if (T.fast && P.fast_limit == M->n_terms) P.fast_limit = q;  // fast terms from here on take the general path
     ++P.n_other;
   }
@@ -432,40 +454,64 @@ static void pass_plan_build(const pgb_model* M, PassPlan& P) {
 
 // the terms that are not in the plan (f(), l(), te(), by=, other orders, cyclic bases): the general evaluation
 template <class Load>
-__device__ __forceinline__ double pass_other_terms(const DTerm* s_terms, int n_terms, int icpt, int fast_limit,
+__device__ __forceinline__ double pass_other_terms(const DTerm* s_terms, int n_terms, int icpt, int fast_limit, int te_limit,
                                                    const double* s_beta, const Load& load) {
   EmitLp e{s_beta, 0.0};
   for (int q = 0; q < n_terms; ++q) {
     const DTerm& T = s_terms[q];
     if ((T.kind == PGB_TERM_INTERCEPT && T.coef_offset == icpt) || (T.fast && q < fast_limit)) continue;
-    if (T.kind == PGB_TERM_TENSOR && T.n_marg == 2 && T.by < 0 && T.marg[0].order == 3 && T.marg[1].order == 3 &&
-        !T.marg[0].periodic && !T.marg[1].periodic) {
-      // te() of two cubic marginals inside its edge knots, straight line: two interval searches, two closed-form
-      // cubic bases, 4 x 4 coefficients (utils.py:943-946: first marginal slowest)
-      const DMarg& g0 = T.marg[0];
-      const DMarg& g1 = T.marg[1];
-      const double u0 = (load(g0.feature) - g0.lo) * g0.inv_span, u1 = (load(g1.feature) - g1.lo) * g1.inv_span;
-      if ((unsigned long long)__double_as_longlong(u0) <= 0x3FF0000000000000ull &&
-          (unsigned long long)__double_as_longlong(u1) <= 0x3FF0000000000000ull) {
-        const double s0 = u0 * (double)g0.nint, s1 = u1 * (double)g1.nint;
-        const int i0 = min((int)s0, g0.nint - 1), i1 = min((int)s1, g1.nint - 1);
-        double a[4], b[4];
-        cubic_bspline(s0 - (double)i0, a[0], a[1], a[2], a[3]);
-        cubic_bspline(s1 - (double)i1, b[0], b[1], b[2], b[3]);
-        const double* cb = s_beta + T.coef_offset + i0 * g1.nspl + i1;
-        double v = 0.0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const double* c = cb + r * g1.nspl;
-          v = fma(a[r], fma(b[3], c[3], fma(b[2], c[2], fma(b[1], c[1], b[0] * c[0]))), v);
-        }
-        e.lp += v;
-        continue;
-      }
-    }
+    if (q < te_limit && pass_te_eligible(T)) continue;
     eval_term(T, load, e);
   }
   return e.lp;
+}
+
+// One cubic marginal of a planned te() term at s = position in knot intervals.  EXT = false assumes 0 <= s < nint and
+// returns a non-zero flag when that fails (the interval index is clamped for memory safety only); EXT = true is the
+// redo of a flagged row: the tangent of the basis at the edge knots outside them (utils.py:744-763), NaN for a NaN.
+template <bool EXT>
+__device__ __forceinline__ unsigned pass_te_marg(double s, int ni, int& i, double (&v)[4]) {
+  if (EXT) {
+    if (s < 0.0 || s > (double)ni) {
+      const bool below = s < 0.0;
+      const double h = 0.5 * (below ? s : s - (double)ni);
+      i = below ? 0 : ni - 1;
+      v[0] = below ? 1.0 / 6.0 - h : 0.0;
+      v[1] = below ? 2.0 / 3.0 : 1.0 / 6.0 - h;
+      v[2] = below ? 1.0 / 6.0 + h : 2.0 / 3.0;
+      v[3] = below ? 0.0 : 1.0 / 6.0 + h;
+      return 0u;
+    }
+    if (!(s >= 0.0)) {  // NaN
+      i = 0;
+      v[0] = v[1] = v[2] = v[3] = s;
+      return 0u;
+    }
+    i = min((int)s, ni - 1);
+    cubic_bspline(s - (double)i, v[0], v[1], v[2], v[3]);
+    return 0u;
+  }
+  const double r = __dadd_rd(s, 4503599627370496.0);  // 2^52 + floor(s), exact for 0 <= s < 2^32
+  const unsigned iu = (unsigned)__double2loint(r);
+  i = (int)min(iu, (unsigned)(ni - 1));
+  cubic_bspline(s - (r - 4503599627370496.0), v[0], v[1], v[2], v[3]);
+  return (unsigned)(__double2hiint(r) ^ 0x43300000) | (unsigned)(iu >= (unsigned)ni);
+}
+
+template <bool EXT, class Load>
+__device__ __forceinline__ double pass_te_term(const PassTe& T, const double* s_beta, const Load& load, unsigned& bad) {
+  int i0, i1;
+  double a[4], b[4];
+  bad |= pass_te_marg<EXT>((load(T.f0) - T.lo0) * T.scale0, T.n0, i0, a);
+  bad |= pass_te_marg<EXT>((load(T.f1) - T.lo1) * T.scale1, T.n1, i1, b);
+  const double* cb = s_beta + T.coef + i0 * T.k1 + i1;  // first marginal slowest (utils.py:943-946)
+  double v = 0.0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const double* c = cb + r * T.k1;
+    v = fma(a[r], fma(b[3], c[3], fma(b[2], c[2], fma(b[1], c[1], b[0] * c[0]))), v);
+  }
+  return v;
 }
 
 // lp of NR rows (row k through load[k]) -- the fast terms of all NR rows side by side (independent dependency chains).
@@ -502,6 +548,10 @@ __device__ __forceinline__ void pass_lp(const PassPlan& P, const DTerm* s_terms,
       }
     }
   }
+  for (int q = 0; q < P.n_te; ++q) {
+#pragma unroll
+    for (int k = 0; k < NR; ++k) lp[k] += pass_te_term<false>(P.te[q], s_beta, load[k], bad[k]);
+  }
 #pragma unroll
   for (int k = 0; k < NR; ++k) {
     if (bad[k]) {
@@ -516,12 +566,14 @@ __device__ __forceinline__ void pass_lp(const PassPlan& P, const DTerm* s_terms,
         const double t = s - (r - kC);
         v += fma(fma(fma(tb[3 * pitch], t, tb[2 * pitch]), t, tb[pitch]), t, tb[0]);
       }
+#pragma unroll 1
+      for (int q = 0; q < P.n_te; ++q) v += pass_te_term<true>(P.te[q], s_beta, load[k], bad[k]);
       lp[k] = v;
     }
   }
   if (OTHER) {
 #pragma unroll
-    for (int k = 0; k < NR; ++k) lp[k] += pass_other_terms(s_terms, n_terms, P.icpt, P.fast_limit, s_beta, load[k]);
+    for (int k = 0; k < NR; ++k) lp[k] += pass_other_terms(s_terms, n_terms, P.icpt, P.fast_limit, P.te_limit, s_beta, load[k]);
   }
 }
 
