@@ -785,16 +785,22 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
       break;
     }
   }
-  if (NS < 2) {
-    pgb_set_error("pgb_stats_pass: %d features do not fit the staging tiles", F);
-    return PGB_EUNSUPPORTED;
+  if (NS < 2) {  // rows too wide for two stages (F > ~110): no staging, every row through the plain-load path
+    NS = 0;
+    RPT = 1;
+    occ = 2;
+    if (fixed > kSmemMax / 2 - 2048) occ = 1;
+    if (fixed > kSmemMax - 1024) {
+      pgb_set_error("pgb_stats_pass: the model (%d coefficients) does not fit shared memory", M->m);
+      return PGB_EUNSUPPORTED;
+    }
   }
   const int R = RPT * kPassThreads;
   const size_t smem = fixed + (size_t)NS * R * rowbytes;
   // TMA bulk copies need 16-byte aligned sources: every column start and every tile start
   const bool bulk_ok = ((uintptr_t)X % 16 == 0) && (ld % 2 == 0) && (!y || (uintptr_t)y % 16 == 0) &&
                        (!w || (uintptr_t)w % 16 == 0);
-  const int64_t n_bulk_tiles = bulk_ok ? n / R : 0;
+  const int64_t n_bulk_tiles = (bulk_ok && NS >= 2) ? n / R : 0;
   const int64_t n_units = std::max<int64_t>(n_bulk_tiles, (n - n_bulk_tiles * R + kPassThreads - 1) / kPassThreads);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, std::min(M->pass_ctas, kSMs * occ)));
   const Family& fm = M->fam;

@@ -152,6 +152,40 @@ def test_stats_pass_extrapolated_rows_and_unaligned_inputs(name):
             assert abs(sc[k] - scr[k]) <= 1e-11 * max(1.0, abs(scr[k])), (k, sc[k], scr[k])
 
 
+def test_stats_pass_more_terms_than_the_plan_holds():
+    """52 s() terms (the plan of the statistics pass holds 48; the rest take the general evaluation after the table
+    loop), 10 te() terms (the plan holds 8), a factor and a linear term; rows outside the edge knots; vs the oracle"""
+    rng = np.random.default_rng(5)
+    n, F = 3000, 74
+    X = rng.uniform(0.0, 1.0, size=(n, F))
+    X[:, 72] = rng.integers(0, 4, size=n)
+    y = np.sin(3 * X[:, 0]) + X[:, 1] ** 2 + 0.1 * rng.standard_normal(n)
+    terms = pg.s(0, n_splines=8)
+    for j in range(1, 52):
+        terms = terms + pg.s(j, n_splines=6 + j % 5)
+    for j in range(10):
+        terms = terms + pg.te(52 + 2 * j, 53 + 2 * j, n_splines=5)
+    terms = terms + pg.f(72) + pg.l(73)
+    gam = pg.LinearGAM(terms, max_iter=1)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        gam.fit(X, y)
+    eng = gam._engine
+    ora = OracleEngine(gam.terms, gam.distribution.name, gam.link.name, gam.distribution.levels, gam._expectile, F, "cpu")
+    coef = rng.standard_normal(eng.m)
+    Xn = X.copy()
+    Xn[:, :72] = Xn[:, :72] * 1.2 - 0.1  # ~17 % of every continuous feature outside the edge knots
+    c = DeviceData.from_host(Xn, y, device="cpu")
+    g = DeviceData.from_host(Xn, y)
+    sc, lp, mu = eng.stats_pass(g, coef, want_mu=True, want_lp=True)
+    scr, lpr, mur = ora.stats_pass(c, coef, want_mu=True, want_lp=True)
+    assert helpers.rel(lp.cpu().numpy(), lpr.numpy()) < 1e-12
+    assert helpers.rel(mu.cpu().numpy(), mur.numpy()) < 1e-12
+    for k in (_lib.SS_N, _lib.SS_DEV, _lib.SS_PEARSON, _lib.SS_SUMY):
+        assert abs(sc[k] - scr[k]) <= 1e-11 * max(1.0, abs(scr[k])), (k, sc[k], scr[k])
+
+
 @pytest.mark.parametrize("name", ["c1_wage", "c2_logistic", "c3_poisson", "mixed_terms", "no_intercept",
                                   "c5_expectile"])
 def test_solve_matches_numpy_mirror(name):
