@@ -1,7 +1,5 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 300 -k "more_terms" > gpurun_out/pytest53.log 2>&1; rc=$?; echo "pytest exit $rc"
-tail -n 25 gpurun_out/pytest53.log
-if [ $rc -ne 0 ]; then exit 1; fi
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 > gpurun_out/pytest54.log 2>&1; echo "full pytest exit $?"
-tail -n 6 gpurun_out/pytest54.log
+N=${PGB_N:-8}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_r1_final_n$N.json 2> gpurun_out/bench_r1_final_n$N.err; echo "bench exit $?"
+python tools/show_bench.py gpurun_out/bench_r1_final_n$N.json
