@@ -1,5 +1,5 @@
 set -x
 mkdir -p gpurun_out
-N=${PGB_N:-8}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_r1_final_n$N.json 2> gpurun_out/bench_r1_final_n$N.err; echo "bench exit $?"
-python tools/show_bench.py gpurun_out/bench_r1_final_n$N.json
+timeout 300 python tools/passbench.py --case c2_logistic --rows 16000001 > gpurun_out/pb8.log 2>&1
+timeout 300 python tools/passbench.py --case c4_linear --rows 32000001 >> gpurun_out/pb8.log 2>&1
+cat gpurun_out/pb8.log
