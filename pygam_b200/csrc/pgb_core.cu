@@ -716,7 +716,22 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
     }
   }
   // the remaining rows (and inputs that are not 16-byte aligned) with plain loads
-  for (int64_t i = n_bulk_tiles * R + (int64_t)blockIdx.x * kPassThreads + tid; i < n; i += (int64_t)gridDim.x * kPassThreads) {
+  const int64_t step = (int64_t)gridDim.x * kPassThreads;
+  int64_t i = n_bulk_tiles * R + (int64_t)blockIdx.x * kPassThreads + tid;
+  if (RPT == 2) {  // two rows per thread here as well: twice the loads in flight when nothing is staged
+    for (; i + step < n; i += 2 * step) {
+      const LoadGlobal load[2] = {LoadGlobal{X, ld, i}, LoadGlobal{X, ld, i + step}};
+      double lp[2];
+      pass_lp<2, OTHER>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int64_t ik = i + k * step;
+        pass_finish<HAS_Y, FULL>(fam, lp[k], ik, HAS_Y ? __ldg(y + ik) : 0.0, use_w ? (double)__ldg(w + ik) : 1.0, scale, ybar,
+                                 poisson_round, lp_out, mu_out, acc);
+      }
+    }
+  }
+  for (; i < n; i += step) {
     const LoadGlobal load[1] = {LoadGlobal{X, ld, i}};
     double lp[1];
     pass_lp<1, OTHER>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp);
