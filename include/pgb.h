@@ -94,6 +94,19 @@ int pgb_model_create(const pgb_term* terms, int32_t n_terms, int32_t n_features,
                      int32_t link, double levels, double expectile, int32_t device,
                      pgb_model** out);
 void pgb_model_destroy(pgb_model* model);
+/* TEST-ONLY entry point (tests/test_cells.py): the same model with the plan of its Gram pass constrained, so
+ * that the parity tests can compare the two decompositions of the same sums (cell-owned register accumulation
+ * vs the general shared-memory path) and exercise tile and band boundaries at small n.  The product never
+ * calls it; all fields zero = pgb_model_create. */
+typedef struct pgb_debug_opts {
+  int32_t force_general_path; /* skip the cell-owned pass even where the model qualifies            */
+  int32_t cells_tile_rows;    /* rows per shared-memory tile of the cell-owned pass (0: planned)    */
+  int32_t cells_band_tiles;   /* tiles per L2 band (0: planned)                                     */
+  int32_t cells_threads;      /* CTA width of the cell kernels: 256, 320, 384 or 512 (0: planned)   */
+} pgb_debug_opts;
+int pgb_debug_model_create(const pgb_term* terms, int32_t n_terms, int32_t n_features, int32_t dist,
+                           int32_t link, double levels, double expectile, int32_t device,
+                           const pgb_debug_opts* opts, pgb_model** out);
 /* Host-only planning of the Gram pass (no CUDA call): fills info; *coverage_errors = entries of
  * the upper triangle of [G | r] not produced by exactly one accumulator element (0 = valid). */
 int pgb_model_plan_host(const pgb_term* terms, int32_t n_terms, int32_t n_features,

@@ -45,6 +45,12 @@ class PgbTerm(C.Structure):
     ]
 
 
+class PgbDebugOpts(C.Structure):
+    """test-only plan constraints of pgb_debug_model_create (include/pgb.h)"""
+    _fields_ = [("force_general_path", C.c_int32), ("cells_tile_rows", C.c_int32), ("cells_band_tiles", C.c_int32),
+                ("cells_threads", C.c_int32)]
+
+
 class PgbModelInfo(C.Structure):
     _fields_ = [
         ("m", C.c_int32),
@@ -70,6 +76,8 @@ SYMBOLS = {
     "pgb_gram_last_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pgb_model_create": (C.c_int, [C.POINTER(PgbTerm), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_double, C.c_double, C.c_int32, C.POINTER(_P)]),
+    "pgb_debug_model_create": (C.c_int, [C.POINTER(PgbTerm), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_double, C.c_double, C.c_int32, C.POINTER(PgbDebugOpts), C.POINTER(_P)]),
     "pgb_model_destroy": (None, [_P]),
     "pgb_model_plan_host": (C.c_int, [C.POINTER(PgbTerm), C.c_int32, C.c_int32, C.POINTER(PgbModelInfo),
                                       C.POINTER(C.c_int32)]),

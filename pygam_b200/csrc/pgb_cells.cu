@@ -32,6 +32,7 @@
 
 #include "pgb_internal.h"
 #include "pgb_kernels.cuh"
+#include "pgb_cells_shared.cuh"
 
 static const int kCellAcc = 18;           // sums per cell (16 for a pair; 10 + 4 + 4 for a diagonal role)
 static const int kPreThreads = 256;
@@ -46,56 +47,90 @@ static size_t cells_smem(int tile, int threads) { return (size_t)tile * (24 + 2 
 // ----------------------------------------------------------------------------------------
 // plan
 // ----------------------------------------------------------------------------------------
+// CTAs [c_lo, c_hi] that can serve role r when nr roles are dealt to `grid` CTAs (UnitIter)
+static void role_cta_range(int64_t nr, int grid, int r, int& lo, int& hi) {
+  lo = grid;
+  hi = -1;
+  for (int c = 0; c < grid; ++c) {
+    const int64_t a = nr * c / grid, b = (nr * (c + 1) + grid - 1) / grid - 1;
+    if (r >= a && r <= b) { lo = std::min(lo, c); hi = std::max(hi, c); }
+  }
+}
+
+// class of a term for the cell-owned pass: 0 intercept, 1 plain cubic s(), 2 generic (te() of two plain cubic
+// marginals, f(), l()), -1: not representable (the model takes the general path of pgb_gram.cu)
+static int cells_term_class(const DTerm& t) {
+  if (t.kind == PGB_TERM_INTERCEPT) return 0;
+  if (t.by >= 0) return -1;
+  auto cubic_ok = [](const DMarg& g) { return g.order == 3 && !g.periodic && g.nint >= 1 && g.nint <= 127; };
+  if (t.kind == PGB_TERM_SPLINE) return (t.fast && cubic_ok(t.marg[0])) ? 1 : -1;
+  if (t.kind == PGB_TERM_TENSOR) return (t.n_marg == 2 && cubic_ok(t.marg[0]) && cubic_ok(t.marg[1])) ? 2 : -1;
+  if (t.kind == PGB_TERM_FACTOR) return (t.marg[0].order == 0 && !t.marg[0].periodic && t.n_coefs >= 1 && t.n_coefs <= 200) ? 2 : -1;
+  if (t.kind == PGB_TERM_LINEAR) return 2;
+  return -1;
+}
+
+struct HostFactor { int kind, col, n, nspl, stride; };
+static void term_factors(const DTerm& t, int cls, std::vector<HostFactor>& out) {
+  out.clear();
+  if (cls == 1) out.push_back({PGB_FK_CUBIC, t.fc0, t.marg[0].nint, t.marg[0].nspl, 1});
+  else if (cls == 2 && t.kind == PGB_TERM_TENSOR) {
+    out.push_back({PGB_FK_CUBIC, t.fc0, t.marg[0].nint, t.marg[0].nspl, t.marg[1].nspl});
+    out.push_back({PGB_FK_CUBIC, t.fc0 + 1, t.marg[1].nint, t.marg[1].nspl, 1});
+  } else if (cls == 2 && t.kind == PGB_TERM_FACTOR) out.push_back({PGB_FK_LEVEL, t.fc0, t.n_coefs, t.n_coefs, 1});
+  else if (cls == 2 && t.kind == PGB_TERM_LINEAR) out.push_back({PGB_FK_VALUE, t.fc0, 1, 1, 1});
+}
+
 int pgb_plan_cells(pgb_model* M) {
   pgb_model::Cells& C = M->cells;
   C = pgb_model::Cells();
-  if (const char* e = getenv("PGB_GRAM_CELLS"))
-    if (atoi(e) == 0) return PGB_OK;
+  if (M->dbg.force_general) return PGB_OK;  // test-only entry point pgb_debug_model_create
   const int nt = M->n_terms;
-  int n_spl = 0, icpt = -1;
+  int n_spl = 0, n_gen = 0, icpt = -1, ncol = 0;
+  std::vector<int> cls(nt, -1);
   for (int j = 0; j < nt; ++j) {
-    const DTerm& t = M->dterms[j];
-    if (t.kind == PGB_TERM_INTERCEPT) {
+    DTerm& t = M->dterms[j];
+    t.fc0 = -1;
+    cls[j] = cells_term_class(t);
+    if (cls[j] < 0) return PGB_OK;  // some other term: the general path
+    if (cls[j] == 0) {
       if (icpt >= 0) return PGB_OK;
       icpt = j;
-    } else if (t.fast && t.marg[0].nint >= 1 && t.marg[0].nint <= 127  /* the interval is a 7-bit field of the cell record */) {
-      ++n_spl;
-    } else {
-      return PGB_OK;  // some other term: the general path
+      continue;
     }
+    t.fc0 = ncol;
+    ncol += (t.kind == PGB_TERM_TENSOR) ? 2 : 1;
+    if (cls[j] == 1) ++n_spl; else ++n_gen;
   }
-  if (n_spl < 1) return PGB_OK;
+  if (n_spl + n_gen < 1) return PGB_OK;
   C.icpt_coef = icpt >= 0 ? M->dterms[icpt].coef_offset : -1;
   C.n_spl = n_spl;
-  std::vector<int> spl_of(nt, -1);  // term -> column of the cell records
-  for (int j = 0, q = 0; j < nt; ++j)
-    if (M->dterms[j].fast) spl_of[j] = q++;
+  C.ncol = ncol;
+  C.mixed = n_gen > 0;
   // CTA shape: one thread per cell of a role.  Pairs of coarse bases (the default n_splines = 20 has 17 x 17
   // = 289 cells) get narrower CTAs, two per SM, so that no thread idles and one CTA sorts while the other sums
   int max_cells = 1;
   for (int i = 0; i < nt; ++i)
     for (int j = i + 1; j < nt; ++j)
-      if (M->dterms[i].fast && M->dterms[j].fast)
+      if (cls[i] == 1 && cls[j] == 1)
         max_cells = std::max(max_cells, M->dterms[i].marg[0].nint * M->dterms[j].marg[0].nint);
-  if (n_spl == 1) max_cells = 256;  // diagonal roles only: interval x row split
+  if (n_spl <= 1) max_cells = 256;  // diagonal and generic roles only
   C.threads = max_cells <= 256 ? 256 : max_cells <= 320 ? 320 : max_cells <= 384 ? 384 : 512;
   C.occ = C.threads <= 320 ? 2 : 1;
-  if (const char* e = getenv("PGB_CELLS_THREADS")) {
-    const int t = atoi(e);
+  if (const int t = M->dbg.cells_threads)
     if (t == 256 || t == 320 || t == 384 || t == 512) { C.threads = t; C.occ = t <= 320 ? 2 : 1; }
-  }
   // occ 3: wide CTAs run alone while they sort (registers), but the kernel of a prepared shard only sums: two of
   // them per SM with half the tile each, so that one waits for its tile while the other computes (measured: -10 %)
-  if (C.occ == 1 && !(getenv("PGB_CELLS_OCC2") && atoi(getenv("PGB_CELLS_OCC2")) == 0)) C.occ = 3;
+  if (C.occ == 1) C.occ = 3;
   const int TH = C.threads;
   int64_t sum_off = 0;
   int64_t n_sub = 0;
   for (int i = 0; i < nt; ++i) {
     const DTerm& ti = M->dterms[i];
-    if (!ti.fast) continue;
+    if (cls[i] != 1) continue;
     for (int j = i; j < nt; ++j) {
       const DTerm& tj = M->dterms[j];
-      if (!tj.fast) continue;
+      if (cls[j] != 1) continue;
       DCellPair P{};
       P.ti = i;
       P.tj = (j == i) ? -1 : j;
@@ -118,42 +153,116 @@ int pgb_plan_cells(pgb_model* M) {
         R.key0 = k0;
         R.ncell = std::min(TH, P.ncells - k0);
         R.pair = pair;
-        R.sa = spl_of[i];
-        R.sb = spl_of[j];
+        R.sa = ti.fc0;
+        R.sb = tj.fc0;
         C.roles.push_back(R);
         ++n_sub;
       }
     }
   }
   // a pair split over many roles re-reads its rows once per role: leave very fine bases to the general path
-  if (n_sub > 4 * (int64_t)C.pairs.size() || C.roles.size() > 4096) {
+  if ((n_sub > 4 * (int64_t)C.pairs.size() && !C.pairs.empty()) || C.roles.size() > 4096) {
     C = pgb_model::Cells();
     return PGB_OK;
   }
   C.sum_doubles = sum_off;
+  // ---- generic pairs: every block with a te() / f() / l() term on one side (incl. its intercept and rhs columns)
+  C.term_class.assign(nt, 0);
+  for (int j = 0; j < nt; ++j) C.term_class[j] = cls[j];
+  C.gpair_of.assign((size_t)(nt + 1) * (nt + 1), -1);
+  if (C.mixed) {
+    std::vector<HostFactor> fa, fb;
+    int64_t gsum_off = 0, starts_off = 0;
+    for (int i = 0; i < nt; ++i) {
+      for (int j = i; j <= nt; ++j) {
+        const int ci = cls[i], cj = (j < nt) ? cls[j] : 0;
+        if (ci != 2 && cj != 2) continue;
+        term_factors(M->dterms[i], ci, fa);
+        if (j < nt) term_factors(M->dterms[j], cj, fb); else fb.clear();
+        if (fa.size() + fb.size() > 4) { C = pgb_model::Cells(); return PGB_OK; }
+        DGenPair P{};
+        P.ta = i;
+        P.tb = j;
+        P.off_a = M->dterms[i].coef_offset;
+        P.off_b = (j < nt) ? M->dterms[j].coef_offset : 0;
+        P.wz = (j == nt) ? 1 : 0;
+        P.in_a = P.in_b = P.out0 = P.out1 = -1;
+        std::vector<int> cubics;
+        DGenOrder O{};
+        for (int side = 0; side < 2; ++side)
+          for (const HostFactor& f : (side ? fb : fa)) {
+            const int q = P.nf++;
+            P.f_kind[q] = f.kind; P.f_side[q] = side; P.f_col[q] = f.col; P.f_n[q] = f.n;
+            P.f_nspl[q] = f.nspl; P.f_stride[q] = f.stride; P.f_key[q] = -1; P.f_ax[q] = -1;
+            if (f.kind == PGB_FK_VALUE) { P.val_col[P.nval++] = f.col; continue; }
+            if (f.kind == PGB_FK_CUBIC) cubics.push_back(q);
+            int kd = -1;
+            for (int d = 0; d < O.nkey; ++d) if (O.key_col[d] == f.col) kd = d;
+            if (kd < 0) { kd = O.nkey++; O.key_col[kd] = f.col; O.key_n[kd] = f.n; O.key_kind[kd] = f.kind; }
+            P.f_key[q] = kd;
+          }
+        const int nc = (int)cubics.size();
+        if (nc >= 1) { P.in_b = cubics[nc - 1]; P.f_ax[P.in_b] = 0; }
+        if (nc >= 2) { P.in_a = cubics[nc - 2]; P.f_ax[P.in_a] = 1; }
+        if (nc >= 3) { P.out0 = cubics[nc - 3]; P.f_ax[P.out0] = 2; }
+        if (nc >= 4) { P.out1 = cubics[nc - 4]; P.f_ax[P.out1] = 3; }
+        P.n_ax = nc;
+        P.n_acc = nc >= 2 ? 16 : nc == 1 ? 4 : 1;
+        P.nsl = nc >= 4 ? 16 : nc == 3 ? 4 : 1;
+        P.nprod = P.n_acc * P.nsl;
+        int64_t kc = 1;
+        for (int d = O.nkey - 1; d >= 0; --d) { O.key_mul[d] = (int32_t)kc; kc *= O.key_n[d]; }
+        O.nh = (int)std::max<int64_t>(1, std::min<int64_t>(32, 256 / kc));
+        if (kc * O.nh > 65000) { C = pgb_model::Cells(); return PGB_OK; }
+        O.ncells = (int32_t)(kc * O.nh);
+        O.spitch = (O.ncells + 2 + 7) & ~7;
+        int oi = -1;
+        for (size_t q = 0; q < C.gorders.size() && oi < 0; ++q) {
+          const DGenOrder& Q = C.gorders[q];
+          bool same = Q.nkey == O.nkey && Q.nh == O.nh;
+          for (int d = 0; d < O.nkey && same; ++d) same = Q.key_col[d] == O.key_col[d] && Q.key_n[d] == O.key_n[d];
+          if (same) oi = (int)q;
+        }
+        if (oi < 0) {
+          O.starts_off = starts_off;
+          starts_off += O.spitch;
+          oi = (int)C.gorders.size();
+          C.gorders.push_back(O);
+        }
+        const DGenOrder& Q = C.gorders[oi];
+        P.order = oi; P.nh = Q.nh; P.ncells = Q.ncells; P.spitch = Q.spitch; P.starts_off = Q.starts_off;
+        for (int d = 0; d < 4; ++d) P.key_mul[d] = Q.key_mul[d];
+        P.sum_off = C.sum_doubles + gsum_off;
+        gsum_off += (int64_t)P.nprod * P.ncells;
+        const int pi = (int)C.gpairs.size();
+        C.gpair_of[(size_t)i * (nt + 1) + j] = pi;
+        C.gpairs.push_back(P);
+        const int ncl = std::max(1, TH / P.nsl);
+        for (int k0 = 0; k0 < P.ncells; k0 += ncl) {
+          DGenRole R{};
+          R.pair = pi; R.key0 = k0; R.ncl = std::min(ncl, P.ncells - k0);
+          C.groles.push_back(R);
+        }
+      }
+    }
+    C.gsum_doubles = gsum_off;
+    C.gstarts_u16 = starts_off;
+    if (C.groles.size() > 16384 || C.gorders.size() > 4096) { C = pgb_model::Cells(); return PGB_OK; }
+  }
   C.grid = kSMs * (C.occ == 3 ? 2 : C.occ);
   C.tile_rows = (C.occ == 3) ? 4096 : 8192;
-  if (const char* e = getenv("PGB_CELLS_TILE")) C.tile_rows = std::max(64, atoi(e) & ~63);
+  if (M->dbg.cells_tile_rows > 0) C.tile_rows = std::max(64, M->dbg.cells_tile_rows & ~63);
   // 1 KB per CTA for the kernel's static shared memory and the driver's reservation
   while (cells_smem(C.tile_rows, TH) + 1024 > (C.occ == 2 ? kSmemMax / 2 - 1024 : kSmemMax)) C.tile_rows -= 64;
   if (C.occ == 3) while ((size_t)C.tile_rows * 26 + (TH + 8) * 2 + 1024 > kSmemMax / 2 - 1024) C.tile_rows -= 64;
   for (DCellRole& R : C.roles) R.hmul = ((uint32_t)R.ncb << 16) / (uint32_t)C.tile_rows;
+  for (DGenOrder& O : C.gorders) O.hmul = ((uint32_t)O.nh << 16) / (uint32_t)C.tile_rows;
   C.smem = cells_smem(C.tile_rows, TH);
   C.slots_per_cta = ((int)C.roles.size() + C.grid - 1) / C.grid + 1;
+  C.gslots_per_cta = C.groles.empty() ? 0 : ((int)C.groles.size() + C.grid - 1) / C.grid + 1;
   C.slot_doubles = (int64_t)kCellAcc * TH;
-  {
-    // CTA c serves roles inside [floor(R c / grid), ceil(R (c + 1) / grid) - 1] in every band
-    const int64_t nr = (int64_t)C.roles.size();
-    for (int r = 0; r < (int)nr; ++r) {
-      int lo = C.grid, hi = -1;
-      for (int c = 0; c < C.grid; ++c) {
-        const int64_t a = nr * c / C.grid, b = (nr * (c + 1) + C.grid - 1) / C.grid - 1;
-        if (r >= a && r <= b) { lo = std::min(lo, c); hi = std::max(hi, c); }
-      }
-      C.roles[r].c_lo = lo;
-      C.roles[r].c_hi = hi;
-    }
-  }
+  for (int r = 0; r < (int)C.roles.size(); ++r) role_cta_range((int64_t)C.roles.size(), C.grid, r, C.roles[r].c_lo, C.roles[r].c_hi);
+  for (int r = 0; r < (int)C.groles.size(); ++r) role_cta_range((int64_t)C.groles.size(), C.grid, r, C.groles[r].c_lo, C.groles[r].c_hi);
   // coefficient -> (term, local index) for the assembly
   C.coef_term.assign(M->m, -1);
   for (int j = 0; j < nt; ++j)
@@ -181,6 +290,11 @@ int pgb_cells_upload(pgb_model* M) {
   up((void**)&C.d_pairs, C.pairs.data(), C.pairs.size() * sizeof(DCellPair));
   up((void**)&C.d_coef_term, C.coef_term.data(), C.coef_term.size() * sizeof(int32_t));
   up((void**)&C.d_pair_of, C.pair_of.data(), C.pair_of.size() * sizeof(int32_t));
+  up((void**)&C.d_gorders, C.gorders.data(), C.gorders.size() * sizeof(DGenOrder));
+  up((void**)&C.d_gpairs, C.gpairs.data(), C.gpairs.size() * sizeof(DGenPair));
+  up((void**)&C.d_groles, C.groles.data(), C.groles.size() * sizeof(DGenRole));
+  up((void**)&C.d_term_class, C.term_class.data(), C.term_class.size() * sizeof(int32_t));
+  up((void**)&C.d_gpair_of, C.gpair_of.data(), C.gpair_of.size() * sizeof(int32_t));
   if (e != cudaSuccess) return pgb_cuda_fail(e, "pgb_cells_upload");
   return PGB_OK;
 }
@@ -191,55 +305,53 @@ void pgb_cells_release(pgb_model* M) {
   cudaFree(C.d_pairs);
   cudaFree(C.d_coef_term);
   cudaFree(C.d_pair_of);
+  cudaFree(C.d_gorders);
+  cudaFree(C.d_gpairs);
+  cudaFree(C.d_groles);
+  cudaFree(C.d_term_class);
+  cudaFree(C.d_gpair_of);
   C.d_roles = nullptr; C.d_pairs = nullptr; C.d_coef_term = nullptr; C.d_pair_of = nullptr;
+  C.d_gorders = nullptr; C.d_gpairs = nullptr; C.d_groles = nullptr; C.d_term_class = nullptr; C.d_gpair_of = nullptr;
 }
 
-// host-only self check: every entry of the upper triangle of [G | r] must be assembled from at
-// least one (pair, product, cell) combination, and every combination of every pair must be used by
-// exactly one entry; returns the number of violations
+CellsView pgb_cells_view_host(const pgb_model* M) {
+  const pgb_model::Cells& C = M->cells;
+  return CellsView{C.coef_term.data(), C.pair_of.data(), C.term_class.data(), C.gpair_of.data(), C.pairs.data(),
+                   C.gpairs.data(), M->n_terms, M->m, C.icpt_coef};
+}
+
+// host-only self check: every structurally non-zero entry of the upper triangle of [G | r] must be assembled
+// from at least one (pair, product, cell) combination, and every combination of every pair must be used
+// (exactly once for the spline pairs; a symmetric generic block holds both triangles, of which the assembly
+// reads one); returns the number of violations
 int pgb_cells_coverage_errors(const pgb_model* M) {
   const pgb_model::Cells& C = M->cells;
   if (!C.enabled) return 0;
   const int m = M->m, nt = M->n_terms;
   int errors = 0;
-  std::vector<int> used((size_t)C.sum_doubles, 0);
+  std::vector<int> used((size_t)(C.sum_doubles + C.gsum_doubles), 0);
+  const CellsView V = pgb_cells_view_host(M);
   for (int r = 0; r < m; ++r)
     for (int c = r; c <= m; ++c) {
-      const int tr = C.coef_term[r], tc = (c < m) ? C.coef_term[c] : -2;
       int hits = 0;
-      if (r == C.icpt_coef && (c == m || c == C.icpt_coef)) { ++hits; }  // from the prepass sums
-      else if (c == m || c == C.icpt_coef || r == C.icpt_coef) {
-        const int ts = (r == C.icpt_coef) ? tc : tr;
-        const int p = ((r == C.icpt_coef) ? c : r) - M->dterms[ts].coef_offset;
-        const DCellPair& P = C.pairs[C.pair_of[(size_t)ts * nt + ts]];
-        for (int a = 0; a < 4; ++a) {
-          const int ci = p - a;
-          if (ci < 0 || ci >= P.nint_i) continue;
-          for (int h = 0; h < P.ncb; ++h) { ++used[P.sum_off + (int64_t)((c == m ? 14 : 10) + a) * P.ncells + ci * P.ncb + h]; ++hits; }
+      cells_entry_visit(V, r, c, [&](int64_t off, int cnt) {
+        ++hits;
+        for (int h = 0; h < cnt; ++h) ++used[off + h];
+      });
+      const int tr = C.coef_term[r], tc = (c < m) ? C.coef_term[c] : nt;
+      bool structural_zero = false;  // same term, coefficients further apart than the support of a cubic / another level
+      if (tr == tc) {
+        const DTerm& T = M->dterms[tr];
+        const int la = r - T.coef_offset, lb = c - T.coef_offset;
+        if (T.kind == PGB_TERM_SPLINE) structural_zero = lb - la > 3;
+        else if (T.kind == PGB_TERM_FACTOR) structural_zero = la != lb;
+        else if (T.kind == PGB_TERM_TENSOR) {
+          const int K1 = T.marg[1].nspl;
+          structural_zero = std::abs(la / K1 - lb / K1) > 3 || std::abs(la % K1 - lb % K1) > 3;
         }
-      } else if (tr == tc) {
-        const DCellPair& P = C.pairs[C.pair_of[(size_t)tr * nt + tr]];
-        const int p = r - P.off_i, d = c - r;
-        if (d > 3) { continue; }
-        for (int a = 0; a + d < 4; ++a) {
-          const int ci = p - a;
-          if (ci < 0 || ci >= P.nint_i) continue;
-          const int e = a * 4 - a * (a - 1) / 2 + d;  // (a, a + d) of the packed upper triangle
-          for (int h = 0; h < P.ncb; ++h) { ++used[P.sum_off + (int64_t)e * P.ncells + ci * P.ncb + h]; ++hits; }
-        }
-      } else {
-        const int ta = std::min(tr, tc), tb = std::max(tr, tc);
-        const DCellPair& P = C.pairs[C.pair_of[(size_t)ta * nt + tb]];
-        const int p = ((tr == ta) ? r : c) - P.off_i, q = ((tr == ta) ? c : r) - P.off_j;
-        for (int a = 0; a < 4; ++a)
-          for (int b = 0; b < 4; ++b) {
-            const int ci = p - a, cj = q - b;
-            if (ci < 0 || ci >= P.nint_i || cj < 0 || cj >= P.ncb) continue;
-            ++used[P.sum_off + (int64_t)(4 * a + b) * P.ncells + ci * P.ncb + cj];
-            ++hits;
-          }
       }
-      if (hits < 1) ++errors;
+      if (hits < 1 && !structural_zero) ++errors;
+      if (hits >= 1 && structural_zero) ++errors;
     }
   for (const DCellPair& P : C.pairs) {
     const int n_acc = (P.tj < 0) ? 18 : 16;
@@ -250,6 +362,14 @@ int pgb_cells_coverage_errors(const pgb_model* M) {
         if (used[P.sum_off + (int64_t)e * P.ncells + k] != want) ++errors;
       }
   }
+  for (const DGenPair& P : C.gpairs) {
+    // the moments of cells next to the edge of a marginal are used by fewer entries, but every (product, cell)
+    // of an off-diagonal pair feeds exactly one entry; a diagonal pair (ta == tb) holds both triangles
+    for (int64_t q = 0; q < (int64_t)P.nprod * P.ncells; ++q) {
+      const int u = used[P.sum_off + q];
+      if (P.ta != P.tb ? u != 1 : u > 1) ++errors;
+    }
+  }
   // every cell of every pair belongs to exactly one role
   for (size_t p = 0; p < C.pairs.size(); ++p) {
     int covered = 0;
@@ -257,20 +377,31 @@ int pgb_cells_coverage_errors(const pgb_model* M) {
       if (R.pair == (int)p) covered += R.ncell;
     if (covered != C.pairs[p].ncells) ++errors;
   }
+  for (size_t p = 0; p < C.gpairs.size(); ++p) {
+    int covered = 0;
+    for (const DGenRole& R : C.groles)
+      if (R.pair == (int)p) covered += R.ncl;
+    if (covered != C.gpairs[p].ncells) ++errors;
+  }
   return errors;
 }
 
-// workspace: [CTA partial slots][cell sums][scalar partials][extra][omega][omega z][t of every spline term][cells]
+// workspace: [CTA partial slots: spline roles | generic roles][cell sums: spline pairs | generic pairs][scalar partials]
+// [extra][omega][omega z][record coordinate of every factor column][cell bytes][stored order: spline roles | generic orders]
 static int64_t rows_pad(int64_t n) { return (n + 15) & ~(int64_t)15; }
 extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n, int with_order) {
   const pgb_model::Cells& C = M->cells;
-  const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
+  const int64_t slots = (int64_t)C.grid * (C.slots_per_cta + C.gslots_per_cta);
   const int64_t np = rows_pad(n);
   const int64_t ntl = (n + C.tile_rows - 1) / C.tile_rows;
-  // sorted rows + cell starts (pgb_gram_prepare); not needed by passes that sort inside the kernel
-  const int64_t order = with_order ? (int64_t)C.roles.size() * ntl * (C.tile_rows + C.threads + 8) * 2 : 0;
-  return (slots * C.slot_doubles + C.sum_doubles + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2) + 8 + (2 + C.n_spl) * np) * 8 +
-         (int64_t)C.n_spl * np + order + 2048;
+  // sorted rows + cell starts (pgb_gram_prepare); not needed by passes that sort inside the kernel.  A model with
+  // generic pairs always sorts into the workspace (its streaming pass runs the sort kernels first)
+  int64_t order = 0;
+  if (with_order || C.mixed)
+    order = ((int64_t)C.roles.size() * ntl * (C.tile_rows + C.threads + 8) + (int64_t)C.gorders.size() * ntl * C.tile_rows +
+             C.gstarts_u16 * ntl) * 2 + 512;
+  return (slots * C.slot_doubles + C.sum_doubles + C.gsum_doubles + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2) + 8 + (2 + C.ncol) * np) * 8 +
+         (int64_t)C.ncol * np + order + 2048;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -281,20 +412,7 @@ extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n, int with_or
 // row outside the knots the normalised coordinate u itself) -- 9 bytes instead of four (value,
 // index) pairs: the cells kernel re-evaluates the four cubic B-spline values from t in registers.
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void extrap_basis(const DMarg& mg, double u, double* v) {
-  // eval_marg's branch outside [0, 1] (utils.py:744-763), from the normalised coordinate
-  const bool below = u < 0.0;
-  const double te = below ? 0.0 : 1.0, dist = below ? u : u - 1.0;
-  double lowv[PGB_MAXV];
-  deboor_uniform<2>(te, lowv);
-  deboor_uniform<3>(te, v);
-#pragma unroll
-  for (int r = 0; r <= 3; ++r) {
-    const double a = (r >= 1) ? lowv[r - 1] : 0.0;
-    const double b = (r <= 2) ? lowv[r] : 0.0;
-    v[r] = ((double)mg.nint * (a - b)) * dist + v[r];
-  }
-}
+__device__ __forceinline__ void extrap_basis(const DMarg& mg, double u, double* v) { extrap_basis_n(mg.nint, u, v); }
 
 struct PreSpl {  // what the prepass needs of one spline term
   double lo, inv_span, nint_d;
@@ -403,10 +521,6 @@ gram_prepass_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Famil
 // b_a(s) = sum_p kM[a][p] s^p.  The cells kernel therefore sums MOMENTS omega s_i^p s_j^q (p, q = 0..3) --
 // 2 + 2 + 3 multiplies and 16 FMAs per (row, pair) instead of two basis evaluations (24) + 4 + 16 -- and
 // cells_transform_kernel maps the 16 moment sums of a cell to the 16 entries of G: B = M S M^T.
-__constant__ double kM[4][4] = {{1.0 / 48.0, -1.0 / 8.0, 1.0 / 4.0, -1.0 / 6.0},
-                                {23.0 / 48.0, -5.0 / 8.0, -1.0 / 4.0, 1.0 / 2.0},
-                                {23.0 / 48.0, 5.0 / 8.0, -1.0 / 4.0, -1.0 / 2.0},
-                                {1.0 / 48.0, 1.0 / 8.0, 1.0 / 4.0, 1.0 / 6.0}};
 
 // A row outside the edge knots (rare: custom edge_knots narrower than the data) has four basis values v
 // that are no cubic of s; its "powers" are mu = M^-1 v, so that M mu = v and the same sums stay valid.
@@ -925,6 +1039,248 @@ gram_prepass_planned_kernel(const DTerm* __restrict__ g_terms, int n_terms, int 
 }
 
 // ----------------------------------------------------------------------------------------
+// models with te() / f() / l() terms: the prepass of every term kind, the sort of the generic orders and the
+// generic sum kernel
+// ----------------------------------------------------------------------------------------
+// One thread per row: lp over all terms, the IRLS step, and the cell record of every factor column: cubic
+// marginals (s(), both marginals of te()) as in gram_prepass_kernel, f(): the coefficient index of the row's
+// level (0xff: none), l(): the feature value.  te() rows follow TensorTerm.build_columns (terms.py:1454-1477,
+// utils.py:899-948: index a * K_2 + b), f() rows FactorTerm.build_columns (terms.py:1077-1096), l() rows
+// LinearTerm.build_columns (terms.py:693-708).
+__global__ void __launch_bounds__(kPreThreads, 3)
+gram_prepass_mixed_kernel(const DTerm* __restrict__ g_terms, int n_terms, int m, Family fam, int mode,
+                          const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
+                          const float* __restrict__ w, const double* __restrict__ beta, int64_t np, double* __restrict__ om,
+                          double* __restrict__ omz, double* __restrict__ tq, uint8_t* __restrict__ cq,
+                          double* __restrict__ scal_part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  double* s_beta = reinterpret_cast<double*>(smem_raw);
+  double* s_red = s_beta + ((m + 1) & ~1);
+  DTerm* s_terms = reinterpret_cast<DTerm*>(s_red + (PGB_GS_COUNT + 2) * 32);
+  for (int i = tid; i < m; i += blockDim.x) s_beta[i] = (mode == PGB_MODE_IRLS) ? beta[i] : 0.0;
+  load_terms_smem(s_terms, g_terms, n_terms);
+  __syncthreads();
+  double sc[PGB_GS_COUNT + 2];
+#pragma unroll
+  for (int s = 0; s < PGB_GS_COUNT + 2; ++s) sc[s] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double yi = __ldg(y + i);
+    const double winv = weight_inv(w, i);
+    const double lp = prepass_row_lp(
+        s_terms, n_terms, s_beta, [&](int f) { return __ldg(X + (int64_t)f * ld + i); },
+        [&](int c, double t) { tq[(int64_t)c * np + i] = t; }, [&](int c, int b) { cq[(int64_t)c * np + i] = (uint8_t)b; });
+    double o, oz;
+    if (mode == PGB_MODE_IRLS) {
+      const IrlsRow ir = irls_row(fam, lp, yi, winv);
+      o = ir.omega;
+      oz = ir.omega * ir.z;
+      if (ir.keep) {
+        sc[PGB_GS_NUSED] += 1.0;
+        sc[PGB_GS_DEV] += dist_dev(fam, yi, ir.mu);
+        sc[PGB_GS_NCORRECT] += (yi == ((ir.mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
+      }
+    } else {
+      o = 1.0;
+      oz = init_response(fam, yi);
+      sc[PGB_GS_NUSED] += 1.0;
+      if (!isfinite(oz)) sc[PGB_GS_NONFINITE] += 1.0;
+    }
+    sc[PGB_GS_NROWS] += 1.0;
+    sc[PGB_GS_COUNT] += o;       // G[intercept, intercept]
+    sc[PGB_GS_COUNT + 1] += oz;  // r[intercept]
+    om[i] = o;
+    omz[i] = oz;
+  }
+  block_reduce_store<PGB_GS_COUNT + 2>(sc, s_red, scal_part + (int64_t)blockIdx.x * (PGB_GS_COUNT + 2));
+}
+
+// The order of a generic key: per (order, tile) the tile's rows sorted by cell (ties by row index, so the order and
+// with it every fp64 sum is reproducible) and the start of every cell.  Counting sort in shared memory, kGenChunk
+// cells at a time; rows without an entry (level byte 0xff) are left out.
+static const int kGenThreads = 256;
+static const int kGenChunk = 2048;
+__global__ void __launch_bounds__(kGenThreads)
+gram_cells_order_kernel(int64_t n, int64_t np, const uint8_t* __restrict__ cq, const DGenOrder* __restrict__ orders,
+                        int n_orders, int TR, int64_t ntl, uint16_t* __restrict__ perm_g, uint16_t* __restrict__ starts_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t* keys = reinterpret_cast<uint16_t*>(smem_raw);
+  uint16_t* perm = keys + TR;
+  int* cnt = reinterpret_cast<int*>(perm + TR);
+  int* cur = cnt + kGenChunk;
+  __shared__ DGenOrder O;
+  __shared__ int s_wtot[kGenThreads / 32], s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int PER = kGenChunk / kGenThreads;
+  for (int64_t u = blockIdx.x; u < ntl * n_orders; u += gridDim.x) {
+    const int64_t tile = u / n_orders;
+    const int o = (int)(u - tile * n_orders);
+    __syncthreads();
+    if (tid == 0) { O = orders[o]; s_base = 0; }
+    __syncthreads();
+    const int64_t row0 = tile * TR;
+    const int cnt_rows = (int)min((int64_t)TR, n - row0);
+    for (int r = tid; r < cnt_rows; r += kGenThreads)
+      keys[r] = (uint16_t)gen_key(O, r, [&](int c) { return (uint32_t)__ldg(cq + (int64_t)c * np + row0 + r); });
+    uint16_t* sg = starts_g + O.starts_off * ntl + tile * O.spitch;
+    for (int k0 = 0; k0 < O.ncells; k0 += kGenChunk) {
+      for (int j = tid; j < kGenChunk; j += kGenThreads) cnt[j] = 0;
+      __syncthreads();
+      for (int r = tid; r < cnt_rows; r += kGenThreads) {
+        const unsigned k = (unsigned)keys[r] - (unsigned)k0;
+        if (keys[r] != 0xffffu && k < (unsigned)kGenChunk) atomicAdd(&cnt[k], 1);
+      }
+      __syncthreads();
+      // exclusive scan of the chunk's counters: thread t owns counters PER t .. PER t + PER - 1
+      int loc[PER], tot = 0;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) { loc[j] = tot; tot += cnt[tid * PER + j]; }
+      int incl = tot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (lane == 31) s_wtot[warp] = incl;
+      __syncthreads();
+      int wbase = 0;
+      for (int q = 0; q < warp; ++q) wbase += s_wtot[q];
+      const int base = s_base + wbase + incl - tot;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int k = k0 + tid * PER + j;
+        cur[tid * PER + j] = base + loc[j];
+        cnt[tid * PER + j] = base + loc[j];
+        if (k < O.ncells) sg[k] = (uint16_t)(base + loc[j]);
+      }
+      __syncthreads();
+      if (tid == kGenThreads - 1) s_base = base + tot;
+      for (int r = tid; r < cnt_rows; r += kGenThreads) {
+        const unsigned k = (unsigned)keys[r] - (unsigned)k0;
+        if (keys[r] != 0xffffu && k < (unsigned)kGenChunk) perm[atomicAdd(&cur[k], 1)] = (uint16_t)r;
+      }
+      __syncthreads();
+      // rows of a cell in ascending order (the atomics above place them in an arbitrary one)
+      for (int j = tid; j < kGenChunk && k0 + j < O.ncells; j += kGenThreads) {
+        const int a = cnt[j], b = cur[j];
+        for (int i = a + 1; i < b; ++i) {
+          const uint16_t v = perm[i];
+          int q = i - 1;
+          while (q >= a && perm[q] > v) { perm[q + 1] = perm[q]; --q; }
+          perm[q + 1] = v;
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) sg[O.ncells] = (uint16_t)s_base;
+    const int placed = s_base;
+    uint16_t* pg = perm_g + ((int64_t)o * ntl + tile) * TR;
+    for (int i = tid; i < placed; i += kGenThreads) pg[i] = perm[i];
+  }
+}
+
+// The generic sum kernel: thread (cell, slice) of a role walks the rows of its cell in the stored order and reads
+// their record coordinates straight from the (L2-resident) band -- a role touches only the few rows of its own
+// cells, so nothing is staged in shared memory; the lanes of a cell's slices read the same addresses.  Same
+// units, partial slots and reproducible order as the spline kernels.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 320 ? 2 : 1))
+gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, const double* __restrict__ omz,
+                          const double* __restrict__ tq, const DGenRole* __restrict__ roles,
+                          const DGenPair* __restrict__ pairs, int n_roles, int TR, int band_tiles, int slots_per_cta,
+                          double* __restrict__ part, const uint16_t* __restrict__ perm_g,
+                          const uint16_t* __restrict__ starts_g, int64_t ntl) {
+  __shared__ DGenPair P;
+  __shared__ DGenRole R;
+  const int tid = threadIdx.x;
+  const int role_lo = (int)((int64_t)n_roles * blockIdx.x / gridDim.x);
+  double* my_part = part + (int64_t)blockIdx.x * slots_per_cta * (kCellAcc * THREADS);
+  int cur_role = -1;
+  double acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  UnitIter it;
+  it.init(n, TR, band_tiles, n_roles);
+  for (; it.valid(); it.next()) {
+    const int role = it.role();
+    const int64_t tile = it.tile();
+    if (role != cur_role) {
+      if (cur_role >= 0) {
+        double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * THREADS);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dst[e * THREADS + tid] = acc[e];
+      }
+      const double* src = my_part + (int64_t)(role - role_lo) * (kCellAcc * THREADS);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = src[e * THREADS + tid];
+      __syncthreads();
+      if (tid == 0) {
+        R = roles[role];
+        P = pairs[R.pair];
+      }
+      __syncthreads();
+      cur_role = role;
+    }
+    const int nsl = P.nsl;
+    const int k = tid / nsl, sg = tid - k * nsl;
+    if (k >= R.ncl) continue;
+    const uint16_t* st = starts_g + P.starts_off * ntl + tile * P.spitch + R.key0 + k;
+    const int s0 = st[0], s1 = st[1];
+    if (s0 >= s1) continue;
+    const int64_t row0 = tile * TR;
+    const uint16_t* pg = perm_g + ((int64_t)P.order * ntl + tile) * TR;
+    const double* wcol = (P.wz ? omz : om) + row0;
+    const double* tcol = tq + row0;
+    int rn = pg[s0];
+    for (int s = s0; s < s1; ++s) {
+      const int r = rn;
+      if (s + 1 < s1) rn = pg[s + 1];
+      gen_row_acc(P, sg, __ldg(wcol + r), [&](int c) { return __ldg(tcol + (int64_t)c * np + r); }, acc);
+    }
+  }
+  if (cur_role >= 0) {
+    double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * THREADS);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) dst[e * THREADS + tid] = acc[e];
+  }
+}
+
+// generic sums[pair][product][cell] = sum over the CTAs that served the cell's role, fixed order; product =
+// sum index of the thread + n_acc * slice
+__global__ void cells_generic_reduce_kernel(const double* __restrict__ part, const DGenRole* __restrict__ roles,
+                                            const DGenPair* __restrict__ pairs, int n_roles, int grid, int slots_per_cta,
+                                            int threads, double* __restrict__ sums) {
+  const int role = blockIdx.x, tid = threadIdx.x, e = blockIdx.y;
+  const DGenRole R = roles[role];
+  const DGenPair& P = pairs[R.pair];
+  const int nsl = P.nsl, n_acc = P.n_acc;
+  const int k = tid / nsl, sg = tid - k * nsl;
+  if (k >= R.ncl || e >= n_acc) return;
+  const int64_t nr = n_roles;
+  double v = 0.0;
+  for (int c = R.c_lo; c <= R.c_hi; ++c) {
+    const int lo = (int)(nr * c / grid);
+    const int hi = (int)((nr * (c + 1) + grid - 1) / grid) - 1;
+    if (role < lo || role > hi || role - lo >= slots_per_cta) continue;
+    v += part[((int64_t)c * slots_per_cta + (role - lo)) * (kCellAcc * threads) + e * threads + tid];
+  }
+  sums[P.sum_off + (int64_t)(e + n_acc * sg) * P.ncells + R.key0 + k] = v;
+}
+
+// change of basis of the generic sums along moment axis `axis`: one thread per line of four sums
+__global__ void cells_generic_transform_kernel(const DGenPair* __restrict__ pairs, int axis, double* __restrict__ sums) {
+  const DGenPair& P = pairs[blockIdx.y];
+  if (axis >= P.n_ax) return;
+  const int64_t lines = (int64_t)P.ncells * (P.nprod / 4);
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= lines) return;
+  const int64_t cell = idx % P.ncells, l = idx / P.ncells;
+  const int64_t sh = (int64_t)1 << (2 * axis);
+  const int64_t e0 = (l / sh) * (4 * sh) + (l % sh);
+  moment_line(sums + P.sum_off + e0 * P.ncells + cell, sh * P.ncells);
+}
+
+// ----------------------------------------------------------------------------------------
 // kernel 3: sums[pair][product][cell] = sum over the CTAs that served the cell's role, fixed order
 // ----------------------------------------------------------------------------------------
 __global__ void cells_slot_reduce_kernel(const double* __restrict__ part, const DCellRole* __restrict__ roles,
@@ -954,49 +1310,7 @@ __global__ void cells_transform_kernel(const DCellPair* __restrict__ pairs, int 
   const DCellPair P = pairs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= P.ncells) return;
-  double* S = sums + P.sum_off + k;
-  const int64_t st = P.ncells;
-  double x[4][4], y[4][4];
-  if (P.tj >= 0) {
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) x[p][q] = S[(4 * p + q) * st];
-  } else {
-    int e = 0;
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-      for (int q = p; q < 4; ++q) { x[p][q] = S[e * st]; x[q][p] = x[p][q]; ++e; }
-  }
-  // y = M x
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) y[a][q] = kM[a][0] * x[0][q] + kM[a][1] * x[1][q] + kM[a][2] * x[2][q] + kM[a][3] * x[3][q];
-  // x = y M^T
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) x[a][b] = y[a][0] * kM[b][0] + y[a][1] * kM[b][1] + y[a][2] * kM[b][2] + y[a][3] * kM[b][3];
-  if (P.tj >= 0) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) S[(4 * a + b) * st] = x[a][b];
-  } else {
-    int e = 0;
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = a; b < 4; ++b) S[(e++) * st] = x[a][b];
-#pragma unroll
-    for (int g = 10; g <= 14; g += 4) {
-      const double v0 = S[g * st], v1 = S[(g + 1) * st], v2 = S[(g + 2) * st], v3 = S[(g + 3) * st];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) S[(g + a) * st] = kM[a][0] * v0 + kM[a][1] * v1 + kM[a][2] * v2 + kM[a][3] * v3;
-    }
-  }
+  spline_transform_cell(P.tj < 0, sums + P.sum_off + k, P.ncells);
 }
 
 // scalars of the prepass: the public ones into out, sum(omega) and sum(omega z) for the assembly.
@@ -1016,55 +1330,22 @@ __global__ void cells_scalar_reduce_kernel(const double* __restrict__ scal_part,
 // ----------------------------------------------------------------------------------------
 // kernel 4: [G | r] from the cell sums.  One thread per entry (row <= col) of the upper triangle.
 // ----------------------------------------------------------------------------------------
-__global__ void cells_assemble_kernel(const double* __restrict__ sums, const double* __restrict__ extra,
-                                      const DCellPair* __restrict__ pairs, const int32_t* __restrict__ coef_term,
-                                      const int32_t* __restrict__ pair_of, int n_terms, int m, int icpt,
+__global__ void cells_assemble_kernel(const double* __restrict__ sums, const double* __restrict__ extra, CellsView V,
                                       double* __restrict__ out, int accumulate) {
+  const int m = V.m;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)m * (m + 1)) return;
   const int r = (int)(idx / (m + 1)), c = (int)(idx - (int64_t)r * (m + 1));
   if (c < r) return;
   double v = 0.0;
-  if (r == icpt && (c == m || c == icpt)) {
-    v = extra[c == m ? 1 : 0];
-  } else if (c == m || c == icpt || r == icpt) {
-    const int cs = (r == icpt) ? c : r;  // the spline coefficient
-    const int ts = coef_term[cs];
-    const DCellPair P = pairs[pair_of[(size_t)ts * n_terms + ts]];
-    const int p = cs - P.off_i;
-    const double* S = sums + P.sum_off + (int64_t)(c == m ? 14 : 10) * P.ncells;
-    for (int a = 0; a < 4; ++a) {
-      const int ci = p - a;
-      if (ci < 0 || ci >= P.nint_i) continue;
-      const double* q = S + (int64_t)a * P.ncells + ci * P.ncb;
-      for (int h = 0; h < P.ncb; ++h) v += q[h];
-    }
-  } else {
-    const int tr = coef_term[r], tc = coef_term[c];
-    if (tr == tc) {
-      const DCellPair P = pairs[pair_of[(size_t)tr * n_terms + tr]];
-      const int p = r - P.off_i, d = c - r;
-      if (d <= 3) {
-        for (int a = 0; a + d < 4; ++a) {
-          const int ci = p - a;
-          if (ci < 0 || ci >= P.nint_i) continue;
-          const int e = a * 4 - a * (a - 1) / 2 + d;
-          const double* q = sums + P.sum_off + (int64_t)e * P.ncells + ci * P.ncb;
-          for (int h = 0; h < P.ncb; ++h) v += q[h];
-        }
-      }
+  cells_entry_visit(V, r, c, [&](int64_t off, int cnt) {
+    if (off < 0) {
+      v += extra[off == -1 ? 0 : 1];
     } else {
-      const int ta = min(tr, tc), tb = max(tr, tc);
-      const DCellPair P = pairs[pair_of[(size_t)ta * n_terms + tb]];
-      const int p = ((tr == ta) ? r : c) - P.off_i, q = ((tr == ta) ? c : r) - P.off_j;
-      for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) {
-          const int ci = p - a, cj = q - b;
-          if (ci < 0 || ci >= P.nint_i || cj < 0 || cj >= P.ncb) continue;
-          v += sums[P.sum_off + (int64_t)(4 * a + b) * P.ncells + ci * P.ncb + cj];
-        }
+      const double* q = sums + off;
+      for (int h = 0; h < cnt; ++h) v += q[h];
     }
-  }
+  });
   if (c == m) {
     double* dst = out + (int64_t)m * m + r;
     *dst = accumulate ? *dst + v : v;
@@ -1077,27 +1358,29 @@ __global__ void cells_assemble_kernel(const double* __restrict__ sums, const dou
 }
 
 struct CellWs {
-  double *part, *sums, *scal_part, *extra, *om, *omz, *tq;
+  double *part, *gpart, *sums, *scal_part, *extra, *om, *omz, *tq;
   uint8_t* cq;
-  uint16_t *perm, *starts;
+  uint16_t *perm, *starts, *gperm, *gstarts;
   int64_t np, ntl;
 };
 static bool cells_ws_layout(const pgb_model* M, int64_t n, void* ws, int64_t ws_bytes, bool with_order, CellWs& L) {
   const pgb_model::Cells& C = M->cells;
-  const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
   L.np = rows_pad(n);
   L.ntl = (n + C.tile_rows - 1) / C.tile_rows;
   L.part = (double*)ws;
-  L.sums = L.part + slots * C.slot_doubles;
-  L.scal_part = L.sums + C.sum_doubles;
+  L.gpart = L.part + (int64_t)C.grid * C.slots_per_cta * C.slot_doubles;
+  L.sums = L.gpart + (int64_t)C.grid * C.gslots_per_cta * C.slot_doubles;
+  L.scal_part = L.sums + C.sum_doubles + C.gsum_doubles;
   L.extra = L.scal_part + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2);
   L.om = (double*)(((uintptr_t)(L.extra + 8) + 127) & ~(uintptr_t)127);
   L.omz = L.om + L.np;
   L.tq = L.omz + L.np;
-  L.cq = (uint8_t*)(L.tq + (int64_t)C.n_spl * L.np);
-  L.perm = (uint16_t*)(((uintptr_t)(L.cq + (int64_t)C.n_spl * L.np) + 127) & ~(uintptr_t)127);
+  L.cq = (uint8_t*)(L.tq + (int64_t)C.ncol * L.np);
+  L.perm = (uint16_t*)(((uintptr_t)(L.cq + (int64_t)C.ncol * L.np) + 127) & ~(uintptr_t)127);
   L.starts = L.perm + (int64_t)C.roles.size() * L.ntl * C.tile_rows;
-  const uint8_t* end = with_order ? (const uint8_t*)(L.starts + (int64_t)C.roles.size() * L.ntl * (C.threads + 8)) : (const uint8_t*)L.perm;
+  L.gperm = (uint16_t*)(((uintptr_t)(L.starts + (int64_t)C.roles.size() * L.ntl * (C.threads + 8)) + 127) & ~(uintptr_t)127);
+  L.gstarts = L.gperm + (int64_t)C.gorders.size() * L.ntl * C.tile_rows;
+  const uint8_t* end = (with_order || C.mixed) ? (const uint8_t*)(L.gstarts + C.gstarts_u16 * L.ntl) : (const uint8_t*)L.perm;
   return (int64_t)(end - (const uint8_t*)ws) <= ws_bytes;
 }
 
@@ -1107,9 +1390,9 @@ static size_t cells_pre_smem(const pgb_model* M) {
 }
 static int cells_band_tiles(const pgb_model* M) {
   const pgb_model::Cells& C = M->cells;
-  const int64_t row_bytes = 9 * (int64_t)C.n_spl + 16;
+  const int64_t row_bytes = 9 * (int64_t)C.ncol + 16;
   int band_tiles = (int)std::max<int64_t>(1, kBandBytes / (row_bytes * C.tile_rows));
-  if (const char* e = getenv("PGB_CELLS_BAND")) band_tiles = std::max(1, atoi(e));
+  if (M->dbg.cells_band_tiles > 0) band_tiles = M->dbg.cells_band_tiles;
   return band_tiles;
 }
 
@@ -1122,37 +1405,76 @@ static int cells_band_tiles(const pgb_model* M) {
   }
 template <int THREADS, int MINB> struct SortedOcc { static const int value = MINB; };
 
-// pgb_gram_prepare for an all-spline model: cell records of every row and the cell order of every (role, tile)
-int pgb_cells_prepare(const pgb_model* M, const double* X, int64_t n, int64_t ld, void* ws, int64_t ws_bytes, cudaStream_t st) {
+static int cells_set_smem_attr(const void* fn, int bytes) {
+  // per device (a process may drive several GPUs): the attribute is cheap to set, so no caching
+  PGB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return PGB_OK;
+}
+
+// the sort kernels: cell order of every (spline role, tile) and of every (generic order, tile), from the cell records
+static int cells_emit_order(const pgb_model* M, int64_t n, const CellWs& L, cudaStream_t st) {
   const pgb_model::Cells& C = M->cells;
+  const int n_roles = (int)C.roles.size();
+  const int TR = C.tile_rows, band_tiles = cells_band_tiles(M);
+  if (n_roles > 0) {
+#define PGB_CELLS_EMIT(TH, OCC)                                                                                          \
+  do {                                                                                                                   \
+    int rc_ = cells_set_smem_attr((const void*)gram_cells_kernel<TH, OCC, true>,                                         \
+                                  (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024));                               \
+    if (rc_ != PGB_OK) return rc_;                                                                                       \
+    gram_cells_kernel<TH, OCC, true><<<C.grid, TH, C.smem, st>>>(n, L.np, L.om, L.omz, L.tq, L.cq, C.d_roles, n_roles, TR, \
+                                                                 band_tiles, C.slots_per_cta, L.part, L.perm, L.starts); \
+  } while (0)
+    PGB_CELLS_DISPATCH(PGB_CELLS_EMIT)
+#undef PGB_CELLS_EMIT
+    PGB_CUDA(cudaGetLastError());
+    pgb_count_launch(1);
+  }
+  if (!C.gorders.empty()) {
+    const int smem = 4 * TR + 8 * kGenChunk;
+    int rc = cells_set_smem_attr((const void*)gram_cells_order_kernel, smem);
+    if (rc != PGB_OK) return rc;
+    const int64_t units = L.ntl * (int64_t)C.gorders.size();
+    gram_cells_order_kernel<<<(unsigned)std::min<int64_t>(units, (int64_t)kSMs * 4), kGenThreads, smem, st>>>(
+        n, L.np, L.cq, C.d_gorders, (int)C.gorders.size(), TR, L.ntl, L.gperm, L.gstarts);
+    PGB_CUDA(cudaGetLastError());
+    pgb_count_launch(1);
+  }
+  return PGB_OK;
+}
+
+static int cells_launch_prepass(const pgb_model* M, int32_t mode, bool planned, const double* X, int64_t n, int64_t ld,
+                                const double* y, const float* w, const double* beta, const CellWs& L, int& grid1,
+                                cudaStream_t st) {
+  const pgb_model::Cells& C = M->cells;
+  grid1 = (int)std::min<int64_t>((n + kPreThreads - 1) / kPreThreads, (int64_t)kSMs * 8);
+  const size_t pre_smem = cells_pre_smem(M);
+  if (C.mixed)
+    gram_prepass_mixed_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, X, n, ld, y, w, beta,
+                                                                    L.np, L.om, L.omz, L.tq, L.cq, L.scal_part);
+  else if (planned)
+    gram_prepass_planned_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, n, y, w, beta, L.np,
+                                                                      L.tq, L.cq, L.om, L.omz, L.scal_part);
+  else
+    gram_prepass_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, X, n, ld, y, w, beta, L.np,
+                                                              L.om, L.omz, L.tq, L.cq, L.scal_part);
+  PGB_CUDA(cudaGetLastError());
+  pgb_count_launch(1);
+  return PGB_OK;
+}
+
+// pgb_gram_prepare: cell records of every row and the cell order of every (role, tile)
+int pgb_cells_prepare(const pgb_model* M, const double* X, int64_t n, int64_t ld, void* ws, int64_t ws_bytes, cudaStream_t st) {
   CellWs L;
   if (!cells_ws_layout(M, n, ws, ws_bytes, true, L)) {
     pgb_set_error("pgb_gram_prepare: workspace too small");
     return PGB_EINVAL;
   }
-  const int n_roles = (int)C.roles.size();
-  const int grid1 = (int)std::min<int64_t>((n + kPreThreads - 1) / kPreThreads, (int64_t)kSMs * 8);
   // records only: the response of this launch is column 0 of X (any n finite doubles will do), its omega is discarded
-  gram_prepass_kernel<<<grid1, kPreThreads, cells_pre_smem(M), st>>>(M->d_terms, M->n_terms, M->m, M->fam, PGB_MODE_INIT, X, n, ld, X,
-                                                                    nullptr, nullptr, L.np, L.om, L.omz, L.tq, L.cq, L.scal_part);
-  PGB_CUDA(cudaGetLastError());
-  const int TR = C.tile_rows, band_tiles = cells_band_tiles(M);
-#define PGB_CELLS_EMIT(TH, OCC)                                                                                          \
-  do {                                                                                                                   \
-    static thread_local bool attr_set = false;                                                                           \
-    if (!attr_set) {                                                                                                     \
-      PGB_CUDA(cudaFuncSetAttribute(gram_cells_kernel<TH, OCC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                    (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024)));                             \
-      attr_set = true;                                                                                                   \
-    }                                                                                                                    \
-    gram_cells_kernel<TH, OCC, true><<<C.grid, TH, C.smem, st>>>(n, L.np, L.om, L.omz, L.tq, L.cq, C.d_roles, n_roles, TR, \
-                                                                 band_tiles, C.slots_per_cta, L.part, L.perm, L.starts); \
-  } while (0)
-  PGB_CELLS_DISPATCH(PGB_CELLS_EMIT)
-#undef PGB_CELLS_EMIT
-  PGB_CUDA(cudaGetLastError());
-  pgb_count_launch(2);
-  return PGB_OK;
+  int grid1 = 0;
+  int rc = cells_launch_prepass(M, PGB_MODE_INIT, false, X, n, ld, X, nullptr, nullptr, L, grid1, st);
+  if (rc != PGB_OK) return rc;
+  return cells_emit_order(M, n, L, st);
 }
 
 int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int64_t n, int64_t ld, const double* y,
@@ -1160,8 +1482,7 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
                           int planned, cudaStream_t st) {
   const pgb_model::Cells& C = M->cells;
   pgb_model* Mm = const_cast<pgb_model*>(M);
-  const int n_roles = (int)C.roles.size();
-  const int64_t slots = (int64_t)C.grid * C.slots_per_cta;
+  const int n_roles = (int)C.roles.size(), n_groles = (int)C.groles.size();
   CellWs L;
   if (!cells_ws_layout(M, n, ws, ws_bytes, planned != 0, L)) {
     pgb_set_error("pgb_gram_pass: workspace too small");
@@ -1180,62 +1501,76 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
     PGB_CUDA(cudaEventRecord(tm.chunk_ev[0], st));
     PGB_CUDA(cudaEventRecord(tm.chunk_ev[2], st));
   }
-  const int grid1 = (int)std::min<int64_t>((n + kPreThreads - 1) / kPreThreads, (int64_t)kSMs * 8);
-  const size_t pre_smem = cells_pre_smem(M);
-  if (planned)
-    gram_prepass_planned_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, n, y, w, beta, np, tq,
-                                                                      cq, om, omz, scal_part);
-  else
-    gram_prepass_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, X, n, ld, y, w, beta, np, om,
-                                                              omz, tq, cq, scal_part);
-  PGB_CUDA(cudaGetLastError());
-  PGB_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * slots * C.slot_doubles, st));
+  int grid1 = 0;
+  int rc = cells_launch_prepass(M, mode, planned != 0, X, n, ld, y, w, beta, L, grid1, st);
+  if (rc != PGB_OK) return rc;
+  // a model with generic pairs that was not prepared sorts its rows now (rows streamed through once)
+  if (C.mixed && !planned) {
+    rc = cells_emit_order(M, n, L, st);
+    if (rc != PGB_OK) return rc;
+  }
+  PGB_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * (int64_t)C.grid * (C.slots_per_cta + C.gslots_per_cta) * C.slot_doubles, st));
   if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[3], st));
   const int TR = C.tile_rows, band_tiles = cells_band_tiles(M);
+  const bool sorted = planned || C.mixed;
 #define PGB_CELLS_LAUNCH(TH, OCC)                                                                                        \
   do {                                                                                                                   \
-    static thread_local bool attr_set = false;                                                                           \
-    if (!attr_set) {                                                                                                     \
-      PGB_CUDA(cudaFuncSetAttribute(gram_cells_kernel<TH, OCC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                    (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024)));                             \
-      PGB_CUDA(cudaFuncSetAttribute(gram_cells_sorted_kernel<TH, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                    (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024)));                             \
-      attr_set = true;                                                                                                   \
-    }                                                                                                                    \
-    if (planned && C.occ == 3) {                                                                                         \
-      static thread_local bool attr2 = false;                                                                            \
-      if (!attr2) {                                                                                                      \
-        PGB_CUDA(cudaFuncSetAttribute(gram_cells_sorted_kernel<TH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                      (int)(kSmemMax / 2 - 2048)));                                                       \
-        attr2 = true;                                                                                                    \
-      }                                                                                                                  \
+    if (n_roles > 0 && sorted && C.occ == 3) {                                                                           \
+      rc = cells_set_smem_attr((const void*)gram_cells_sorted_kernel<TH, 2>, (int)(kSmemMax / 2 - 2048));                \
+      if (rc != PGB_OK) return rc;                                                                                       \
       gram_cells_sorted_kernel<TH, 2><<<C.grid, TH, (size_t)TR * 26 + (TH + 8) * 2 + 64, st>>>(                          \
           n, np, om, omz, tq, C.d_roles, n_roles, TR, band_tiles, C.slots_per_cta, part, L.perm, L.starts);              \
-    } else if (planned)                                                                                                  \
+    } else if (n_roles > 0 && sorted) {                                                                                  \
+      rc = cells_set_smem_attr((const void*)gram_cells_sorted_kernel<TH, OCC>,                                           \
+                               (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024));                                  \
+      if (rc != PGB_OK) return rc;                                                                                       \
       gram_cells_sorted_kernel<TH, OCC><<<C.grid, TH, (size_t)TR * 26 + (TH + 8) * 2 + 64, st>>>(                        \
           n, np, om, omz, tq, C.d_roles, n_roles, TR, band_tiles, C.slots_per_cta, part, L.perm, L.starts);              \
-    else                                                                                                                 \
+    } else if (n_roles > 0) {                                                                                            \
+      rc = cells_set_smem_attr((const void*)gram_cells_kernel<TH, OCC, false>,                                           \
+                               (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024));                                  \
+      if (rc != PGB_OK) return rc;                                                                                       \
       gram_cells_kernel<TH, OCC, false><<<C.grid, TH, C.smem, st>>>(n, np, om, omz, tq, cq, C.d_roles, n_roles, TR,      \
                                                                     band_tiles, C.slots_per_cta, part, nullptr, nullptr); \
+    }                                                                                                                    \
+    if (n_groles > 0)                                                                                                    \
+      gram_cells_generic_kernel<TH><<<C.grid, TH, 0, st>>>(n, np, om, omz, tq, C.d_groles, C.d_gpairs, n_groles, TR,     \
+                                                           band_tiles, C.gslots_per_cta, L.gpart, L.gperm, L.gstarts,    \
+                                                           L.ntl);                                                       \
   } while (0)
   PGB_CELLS_DISPATCH(PGB_CELLS_LAUNCH)
 #undef PGB_CELLS_LAUNCH
   PGB_CUDA(cudaGetLastError());
   if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[4], st));
-  cells_slot_reduce_kernel<<<dim3(n_roles, kCellAcc), C.threads, 0, st>>>(part, C.d_roles, C.d_pairs, n_roles, C.grid, C.slots_per_cta,
-                                                                        C.threads, sums);
-  {
+  int launches = 3;
+  if (n_roles > 0) {
+    cells_slot_reduce_kernel<<<dim3(n_roles, kCellAcc), C.threads, 0, st>>>(part, C.d_roles, C.d_pairs, n_roles, C.grid,
+                                                                          C.slots_per_cta, C.threads, sums);
     int max_cells = 1;
     for (const DCellPair& P : C.pairs) max_cells = std::max(max_cells, P.ncells);
     cells_transform_kernel<<<dim3((max_cells + 127) / 128, (unsigned)C.pairs.size()), 128, 0, st>>>(C.d_pairs, (int)C.pairs.size(), sums);
+    launches += 3;
+  }
+  if (n_groles > 0) {
+    cells_generic_reduce_kernel<<<dim3(n_groles, 16), C.threads, 0, st>>>(L.gpart, C.d_groles, C.d_gpairs, n_groles, C.grid,
+                                                                        C.gslots_per_cta, C.threads, sums);
+    int64_t max_lines = 1;
+    int max_ax = 0;
+    for (const DGenPair& P : C.gpairs) {
+      max_lines = std::max(max_lines, (int64_t)P.ncells * (P.nprod / 4));
+      max_ax = std::max(max_ax, P.n_ax);
+    }
+    for (int ax = 0; ax < max_ax; ++ax)
+      cells_generic_transform_kernel<<<dim3((unsigned)((max_lines + 127) / 128), (unsigned)C.gpairs.size()), 128, 0, st>>>(C.d_gpairs, ax, sums);
+    launches += 2 + max_ax;
   }
   cells_scalar_reduce_kernel<<<1, 32 * (PGB_GS_COUNT + 2), 0, st>>>(scal_part, grid1, out + (int64_t)M->m * M->m + M->m, extra,
                                                                      accumulate);
   const int64_t entries = (int64_t)M->m * (M->m + 1);
-  cells_assemble_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, st>>>(sums, extra, C.d_pairs, C.d_coef_term, C.d_pair_of,
-                                                                          M->n_terms, M->m, C.icpt_coef, out, accumulate);
+  const CellsView V{C.d_coef_term, C.d_pair_of, C.d_term_class, C.d_gpair_of, C.d_pairs, C.d_gpairs, M->n_terms, M->m, C.icpt_coef};
+  cells_assemble_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, st>>>(sums, extra, V, out, accumulate);
   PGB_CUDA(cudaGetLastError());
-  pgb_count_launch(6);
+  pgb_count_launch(launches);
   if (tm.enabled) {
     PGB_CUDA(cudaEventRecord(tm.chunk_ev[1], st));
     tm.pending = true;

@@ -60,14 +60,21 @@ int pgb_cells_upload(pgb_model* M);
 int pgb_cells_coverage_errors(const pgb_model* M);
 void pgb_cells_release(pgb_model* M);
 
-static int model_build_host(const pgb_term* terms, int32_t n_terms, int32_t n_features, int32_t dist,
-                            int32_t link, double levels, double expectile, int32_t device, pgb_model** out) {
+int pgb_model_build_host(const pgb_term* terms, int32_t n_terms, int32_t n_features, int32_t dist,
+                            int32_t link, double levels, double expectile, int32_t device, const pgb_debug_opts* dbg,
+                            pgb_model** out) {
   if (!terms || n_terms < 1 || !out) { pgb_set_error("pgb_model_create: bad arguments"); return PGB_EINVAL; }
   if (dist < 0 || dist > PGB_DIST_INVGAUSS || link < 0 || link > PGB_LINK_INVSQUARED) {
     pgb_set_error("unknown distribution %d or link %d", dist, link);
     return PGB_EINVAL;
   }
   pgb_model* M = new pgb_model();
+  if (dbg) {
+    M->dbg.force_general = dbg->force_general_path;
+    M->dbg.cells_tile_rows = dbg->cells_tile_rows;
+    M->dbg.cells_band_tiles = dbg->cells_band_tiles;
+    M->dbg.cells_threads = dbg->cells_threads;
+  }
   M->device = device;
   M->n_terms = n_terms;
   M->n_features = n_features;
@@ -117,6 +124,7 @@ static int model_build_host(const pgb_term* terms, int32_t n_terms, int32_t n_fe
     }
     d.nnz = term_nnz(t);
     d.fast = (t.kind == PGB_TERM_SPLINE && t.order[0] == 3 && !t.periodic[0] && t.by < 0) ? 1 : 0;
+    d.fc0 = -1;
     d.slot0 = slot;
     slot += d.nnz;
     coef += t.n_coefs;
@@ -133,11 +141,10 @@ static int model_build_host(const pgb_term* terms, int32_t n_terms, int32_t n_fe
   return PGB_OK;
 }
 
-extern "C" int pgb_model_create(const pgb_term* terms, int32_t n_terms, int32_t n_features,
-                                int32_t dist, int32_t link, double levels, double expectile,
-                                int32_t device, pgb_model** out) {
+static int model_create(const pgb_term* terms, int32_t n_terms, int32_t n_features, int32_t dist, int32_t link,
+                        double levels, double expectile, int32_t device, const pgb_debug_opts* dbg, pgb_model** out) {
   pgb_model* M = nullptr;
-  int rc = model_build_host(terms, n_terms, n_features, dist, link, levels, expectile, device, &M);
+  int rc = pgb_model_build_host(terms, n_terms, n_features, dist, link, levels, expectile, device, dbg, &M);
   if (rc != PGB_OK) return rc;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaMalloc(&M->d_terms, sizeof(DTerm) * n_terms);
@@ -157,24 +164,29 @@ extern "C" int pgb_model_create(const pgb_term* terms, int32_t n_terms, int32_t 
   return PGB_OK;
 }
 
+extern "C" int pgb_model_create(const pgb_term* terms, int32_t n_terms, int32_t n_features,
+                                int32_t dist, int32_t link, double levels, double expectile,
+                                int32_t device, pgb_model** out) {
+  return model_create(terms, n_terms, n_features, dist, link, levels, expectile, device, nullptr, out);
+}
+
+// test-only entry point: the same model with the plan of its Gram pass constrained (see pgb_debug_opts)
+extern "C" int pgb_debug_model_create(const pgb_term* terms, int32_t n_terms, int32_t n_features, int32_t dist,
+                                      int32_t link, double levels, double expectile, int32_t device,
+                                      const pgb_debug_opts* opts, pgb_model** out) {
+  return model_create(terms, n_terms, n_features, dist, link, levels, expectile, device, opts, out);
+}
+
 // Host-only planning of the Gram pass for a model descriptor (no CUDA call): fills `info` and
 // returns in *coverage_errors how many entries of the upper triangle of [G | r] are not produced
 // by exactly one accumulator element (0 for a valid plan).  Used by the CPU test-suite.
 extern "C" int pgb_model_plan_host(const pgb_term* terms, int32_t n_terms, int32_t n_features,
                                    pgb_model_info* info, int32_t* coverage_errors) {
   pgb_model* M = nullptr;
-  int rc = model_build_host(terms, n_terms, n_features, PGB_DIST_NORMAL, PGB_LINK_IDENTITY, 1.0, -1.0, 0, &M);
+  int rc = pgb_model_build_host(terms, n_terms, n_features, PGB_DIST_NORMAL, PGB_LINK_IDENTITY, 1.0, -1.0, 0, nullptr, &M);
   if (rc != PGB_OK) return rc;
   if (info) pgb_model_get_info(M, info);
   if (coverage_errors) *coverage_errors = pgb_plan_coverage_errors(M) + pgb_cells_coverage_errors(M);
-  if (getenv("PGB_DEBUG_PLAN")) {
-    fprintf(stderr, "plan: m=%d k=%d groups=%zu blocks=%zu steps=%zu roles=%zu tile=%d threads=%d smem=%zu ctas=%d\n",
-            M->m, M->k, M->groups.size(), M->blocks.size(), M->steps.size(), M->roles.size(), M->tile_rows,
-            M->gram_threads, M->gram_smem, M->gram_ctas);
-    for (const DRole& r : M->roles)
-      fprintf(stderr, "  role warps=%d max_steps=%d slots=%d acc=%lld ctas=%d all_terms=%d\n", r.n_warps, r.max_steps,
-              r.n_slots, (long long)r.acc_size, r.n_ctas, r.needs_all_terms);
-  }
   delete M;
   return PGB_OK;
 }
@@ -201,7 +213,7 @@ extern "C" int pgb_model_get_info(const pgb_model* M, pgb_model_info* info) {
   info->gram_ctas = M->gram_ctas;
   info->gram_ws_bytes = pgb_gram_ws_bytes(M, 0);
   info->pass_ws_bytes = pgb_stats_ws_bytes(M);
-  info->cell_roles = M->cells.enabled ? (int32_t)M->cells.roles.size() : 0;
+  info->cell_roles = M->cells.enabled ? (int32_t)(M->cells.roles.size() + M->cells.groles.size()) : 0;
   info->cell_tile_rows = M->cells.enabled ? M->cells.tile_rows : 0;
   return PGB_OK;
 }
@@ -762,12 +774,8 @@ static int stats_pass_launch(const PassPlan& P, const pgb_model* M, int grid, si
                              int64_t n, int64_t ld, const double* y, const float* w, const double* beta, double scale,
                              double ybar, int poisson_round, int NS, int64_t n_bulk_tiles, double* part, double* lp_out,
                              double* mu_out) {
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<HAS_Y, FULL, FAMK, RPT, OTHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kSmemMax));
-    attr_set = true;
-  }
+  PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<HAS_Y, FULL, FAMK, RPT, OTHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)kSmemMax));
   stats_pass_kernel<HAS_Y, FULL, FAMK, RPT, OTHER><<<grid, kPassThreads + 32, smem, st>>>(
       P, M->d_terms, M->n_terms, M->m, M->n_features, M->fam, X, n, ld, y, w, beta, scale, ybar, poisson_round, NS,
       n_bulk_tiles, part, lp_out, mu_out);

@@ -15,6 +15,8 @@
 
 #define PGB_SQRT_EPS 1.4901161193847656e-08 /* sqrt(np.finfo(float).eps), pygam.py:657, 749 */
 #define PGB_MAXV (PGB_MAX_ORDER + 1)
+// host + device: the row-level arithmetic is shared with the host-side self check of the cell plan (tests only)
+#define PGB_HD __host__ __device__ __forceinline__
 
 struct DMarg {
   int32_t feature, nspl, order, periodic;
@@ -30,6 +32,8 @@ struct DTerm {
   // term's first coefficient inside the group, first global record slot (4 per quad)
   int32_t group, idx_base, gslot0;
   int32_t fast;  // plain cubic spline term (order 3, basis "ps", no by): straight-line evaluation
+  int32_t fc0;   // first column of the term's factors in the cell records (pgb_cells.cu), -1: none
+  int32_t pad0;
   DMarg marg[PGB_MAX_MARG];
 };
 
@@ -44,7 +48,7 @@ struct Family {
 // the value of basis function (interval + r) at local coordinate t in [0, 1].
 // ----------------------------------------------------------------------------------------
 template <int D>
-__device__ __forceinline__ void deboor_uniform(double t, double* v) {
+PGB_HD void deboor_uniform(double t, double* v) {
   v[0] = 1.0;
 #pragma unroll
   for (int j = 1; j <= D; ++j) {
@@ -64,7 +68,7 @@ __device__ __forceinline__ void deboor_uniform(double t, double* v) {
 // the four non-zero cubic B-splines of a uniform knot vector at local coordinate t, closed form:
 // [(1-t)^3, 3t^3 - 6t^2 + 4, -3t^3 + 3t^2 + 3t + 1, t^3] / 6; agrees with
 // the recursion above to rounding and is what the straight-line cubic path uses everywhere
-__device__ __forceinline__ void cubic_bspline(double t, double& b0, double& b1, double& b2, double& b3) {
+PGB_HD void cubic_bspline(double t, double& b0, double& b1, double& b2, double& b3) {
   const double omt = 1.0 - t, t2 = t * t, t3 = t2 * t;
   b0 = (omt * omt) * (omt * (1.0 / 6.0));
   b3 = t3 * (1.0 / 6.0);
@@ -72,7 +76,7 @@ __device__ __forceinline__ void cubic_bspline(double t, double& b0, double& b1, 
   b2 = fma(t3, -0.5, fma(t2, 0.5, fma(t, 0.5, 1.0 / 6.0)));
 }
 
-__device__ __forceinline__ void deboor_dispatch(int d, double t, double* v) {
+PGB_HD void deboor_dispatch(int d, double t, double* v) {
   switch (d) {
     case 0: v[0] = 1.0; break;
     case 1: deboor_uniform<1>(t, v); break;
@@ -88,7 +92,7 @@ __device__ __forceinline__ void deboor_dispatch(int d, double t, double* v) {
 // One marginal basis row.  Returns the index of the first non-zero basis function; v[0..order]
 // are the values (always order+1 entries, zeros included, so that every row of a term has the
 // same number of slots).  Column indices of a periodic basis wrap modulo nspl in the caller.
-__device__ __forceinline__ int eval_marg(const DMarg& mg, double x, double* v) {
+PGB_HD int eval_marg(const DMarg& mg, double x, double* v) {
   const int d = mg.order;
   if (d == 0) {
     // order-0 (factor / Haar) basis is discontinuous: pick the cell with the reference's own
@@ -250,7 +254,7 @@ __device__ __forceinline__ void eval_term(const DTerm& T, const double* __restri
 // ----------------------------------------------------------------------------------------
 // links (links.py:21-314)
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ double link_inv(const Family& f, double lp) {
+PGB_HD double link_inv(const Family& f, double lp) {
   switch (f.link) {
     case PGB_LINK_IDENTITY: return lp;
     case PGB_LINK_LOGIT: { const double e = exp(lp); return f.levels * e / (e + 1.0); }  // links.py:121-122
@@ -259,7 +263,7 @@ __device__ __forceinline__ double link_inv(const Family& f, double lp) {
     default: return 1.0 / sqrt(lp);
   }
 }
-__device__ __forceinline__ double link_fwd(const Family& f, double mu) {
+PGB_HD double link_fwd(const Family& f, double mu) {
   switch (f.link) {
     case PGB_LINK_IDENTITY: return mu;
     case PGB_LINK_LOGIT: return log(mu) - log(f.levels - mu);  // links.py:105
@@ -268,7 +272,7 @@ __device__ __forceinline__ double link_fwd(const Family& f, double mu) {
     default: return 1.0 / (mu * mu);
   }
 }
-__device__ __forceinline__ double link_grad(const Family& f, double mu) {
+PGB_HD double link_grad(const Family& f, double mu) {
   switch (f.link) {
     case PGB_LINK_IDENTITY: return 1.0;
     case PGB_LINK_LOGIT: return f.levels / (mu * (f.levels - mu));  // links.py:137
@@ -281,7 +285,7 @@ __device__ __forceinline__ double link_grad(const Family& f, double mu) {
 // ----------------------------------------------------------------------------------------
 // distributions (distributions.py:97-612)
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ double dist_var(const Family& f, double mu) {
+PGB_HD double dist_var(const Family& f, double mu) {
   switch (f.dist) {
     case PGB_DIST_NORMAL: return 1.0;
     case PGB_DIST_BINOMIAL: return mu * (1.0 - mu / f.levels);
@@ -290,11 +294,11 @@ __device__ __forceinline__ double dist_var(const Family& f, double mu) {
     default: return mu * mu * mu;
   }
 }
-__device__ __forceinline__ double ylogydu(double y, double u) {  // utils.py:773-789
+PGB_HD double ylogydu(double y, double u) {  // utils.py:773-789
   return (y != 0.0) ? y * log(y / u) : 0.0;
 }
 // unscaled, unweighted deviance of one row
-__device__ __forceinline__ double dist_dev(const Family& f, double y, double mu) {
+PGB_HD double dist_dev(const Family& f, double y, double mu) {
   switch (f.dist) {
     case PGB_DIST_NORMAL: { const double r = y - mu; return r * r; }
     case PGB_DIST_BINOMIAL:
@@ -359,7 +363,7 @@ struct IrlsRow {
 
 // winv is 1 / w as the reference computes it: user weights are float32 (pygam.py:889), so
 // `weights ** -1` (pygam.py:633) is a float32 reciprocal; 1.0 when no weights were given
-__device__ __forceinline__ IrlsRow irls_row(const Family& f, double lp, double y, double winv) {
+PGB_HD IrlsRow irls_row(const Family& f, double lp, double y, double winv) {
   IrlsRow r;
   const double mu = link_inv(f, lp);
   const double g = link_grad(f, mu);
@@ -377,12 +381,16 @@ __device__ __forceinline__ IrlsRow irls_row(const Family& f, double lp, double y
   return r;
 }
 
-__device__ __forceinline__ double weight_inv(const float* __restrict__ w, int64_t i) {
+PGB_HD double weight_inv(const float* __restrict__ w, int64_t i) {
+#ifdef __CUDA_ARCH__
   return w ? (double)__fdiv_rn(1.0f, __ldg(w + i)) : 1.0;
+#else
+  return w ? (double)(1.0f / w[i]) : 1.0;
+#endif
 }
 
 // response of _initial_estimate (pygam.py:696-704)
-__device__ __forceinline__ double init_response(const Family& f, double y) {
+PGB_HD double init_response(const Family& f, double y) {
   if (y == 0.0) y += 0.01;
   if (y == 1.0) y -= 0.01;
   return link_fwd(f, y);

@@ -281,7 +281,6 @@ int pgb_plan_gram(pgb_model* M) {
     for (const DBlock& b : M->blocks)
       if (b.role == r && b.n_items == 1) ++n_single;
     int K = n_single > 40 ? 4 : n_single > 24 ? 3 : n_single > 12 ? 2 : 1;
-    if (const char* ek = getenv("PGB_GRAM_K")) K = std::max(1, std::min(PGB_MAX_K, atoi(ek)));
     std::vector<std::vector<DHalf>> chains;
     {
       std::vector<std::vector<Item>> by_cq(quads);
@@ -361,7 +360,6 @@ int pgb_plan_gram(pgb_model* M) {
     return smem;
   };
   tile = 128;
-  if (const char* et = getenv("PGB_GRAM_TILE")) tile = std::max(kMinTile, atoi(et) & ~7);
   while (tile > kMinTile && smem_for(tile) > kSmemMax) tile -= 8;
   for (int t2 = tile; t2 >= 64; t2 -= 8) {
     if (smem_for(t2) + 1024 <= kSmemMax / 2) { tile = t2; break; }
@@ -992,14 +990,10 @@ static int launch_gram(const pgb_model* M, int32_t mode, const double* X, int64_
   rp = (rp + 255) & ~(uintptr_t)255;
   double* rec_val = (double*)rp;
   uint16_t* rec_idx = (uint16_t*)(rec_val + chunk_tiles * M->n_slots_all * TP);
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    PGB_CUDA(cudaFuncSetAttribute(gram_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    PGB_CUDA(cudaFuncSetAttribute(gram_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    attr_set = true;
-  }
-  const char* edbg = getenv("PGB_GRAM_DEBUG");  // timing experiments only
-  const int dbg = edbg ? atoi(edbg) : 0;
+  // the attribute is per device and cheap to set: no caching (a thread may drive engines on several GPUs)
+  PGB_CUDA(cudaFuncSetAttribute(gram_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  PGB_CUDA(cudaFuncSetAttribute(gram_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  const int dbg = 0;
   pgb_model::Timing& tm = Mm->timing;
   const int n_chunks = (int)((n + chunk_rows - 1) / chunk_rows);
   if (tm.enabled) {

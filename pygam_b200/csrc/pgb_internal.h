@@ -108,19 +108,70 @@ struct DCellPair {
   int64_t sum_off;                  // sums[sum_off + product * ncells + cell]
 };
 
+// ---- generic cell pairs (pgb_cells.cu): every block of [G | r] with a te(), f() or l() term on one side ----
+// A term is a product of FACTORS, each with one column of the cell records: a cubic marginal (s(), a marginal
+// of te(): knot interval byte + centred local coordinate), a level (f(): coefficient index byte, 0xff = the row
+// has no entry in this term) or a value (l(): the feature itself).  The block of two terms is a sum over the
+// rows of omega * prod(factor power vectors), so inside one CELL (fixed interval / level of every factor) it
+// is a set of MOMENT sums: digit d of the product index = exponent of the d-th cubic factor ("axis").  A
+// thread owns (cell, slice): the slice fixes the exponents of the OUTER cubic factors, the two INNER ones span
+// the thread's 4 x 4 register sums.  Rows of a tile are ordered by cell once per (key signature, tile) --
+// the ORDER -- and shared by every pair with the same key (te diagonal block, te x intercept, te x rhs).
+enum { PGB_FK_CUBIC = 0, PGB_FK_LEVEL = 1, PGB_FK_VALUE = 2 };
+struct DGenOrder {
+  int32_t nkey, nh, ncells, spitch;   // key dimensions, hash split of the rows, cells = prod(key_n) * nh
+  uint32_t hmul;
+  int32_t key_col[4], key_n[4], key_mul[4], key_kind[4];
+  int32_t pad;
+  int64_t starts_off;                 // starts of tile t at starts_g[starts_off * n_tiles + t * spitch]
+};
+struct DGenPair {
+  int32_t ta, tb;                     // terms, ta <= tb; tb == n_terms: the right-hand side column
+  int32_t off_a, off_b;               // first coefficients
+  int32_t nf;                         // factor occurrences: those of ta, then those of tb
+  int32_t f_kind[4], f_side[4], f_col[4];
+  int32_t f_n[4];                     // cubic: knot intervals; level: coefficients
+  int32_t f_nspl[4], f_stride[4];     // coefficient index of the factor = (local index / stride) % nspl
+  int32_t f_key[4], f_ax[4];          // key dimension / moment axis of the factor (-1: none)
+  int32_t n_ax, n_acc, nsl, nprod;    // axes; sums per thread (1, 4, 16); slices (1, 4, 16); nprod = n_acc * nsl
+  int32_t in_a, in_b, out0, out1;     // factor occurrences of the inner / outer cubic factors (-1: none)
+  int32_t nval, val_col[2];           // value factors multiplied into the weight
+  int32_t wz;                         // weight column: omega z (rhs) instead of omega
+  int32_t order, nh, ncells, spitch;  // copy of the order's geometry
+  int32_t key_mul[4];
+  int64_t sum_off, starts_off;
+};
+struct DGenRole {
+  int32_t pair, key0, ncl;            // cells key0 .. key0 + ncl - 1 of the pair; thread = (cell - key0) * nsl + slice
+  int32_t c_lo, c_hi, pad;
+};
+
 struct pgb_model {
   struct Cells {
     bool enabled = false;
+    bool mixed = false;                // the model has te() / f() / l() terms: generic pairs next to the spline pairs
     std::vector<DCellRole> roles;
     std::vector<DCellPair> pairs;
     std::vector<int32_t> coef_term, pair_of;
+    std::vector<DGenOrder> gorders;
+    std::vector<DGenPair> gpairs;
+    std::vector<DGenRole> groles;
+    std::vector<int32_t> term_class, gpair_of;  // 0 intercept, 1 plain cubic s(), 2 generic; (ta, tb) -> generic pair
     DCellRole* d_roles = nullptr;
     DCellPair* d_pairs = nullptr;
     int32_t* d_coef_term = nullptr;
     int32_t* d_pair_of = nullptr;
+    DGenOrder* d_gorders = nullptr;
+    DGenPair* d_gpairs = nullptr;
+    DGenRole* d_groles = nullptr;
+    int32_t* d_term_class = nullptr;
+    int32_t* d_gpair_of = nullptr;
     int32_t tile_rows = 0, grid = 0, slots_per_cta = 0, icpt_coef = -1, n_spl = 0, occ = 1, threads = 512;
+    int32_t ncol = 0;                  // record columns (one per factor)
+    int32_t gslots_per_cta = 0;
     size_t smem = 0;
     int64_t sum_doubles = 0, slot_doubles = 0;
+    int64_t gsum_doubles = 0, gstarts_u16 = 0;  // generic sums; starts of all orders per tile
   } cells;
   std::vector<pgb_term> terms;
   std::vector<DTerm> dterms;
@@ -149,6 +200,11 @@ struct pgb_model {
   int64_t partial_doubles = 0;  // doubles of all partials of all roles
   int64_t map_size = 0;
   int32_t pass_ctas = 0;        // CTAs of the O(k) passes
+  // set only through the test-only entry point pgb_debug_model_create (tests compare the two Gram paths and
+  // exercise tile / band boundaries at small n); zero in every model the product creates
+  struct Debug {
+    int32_t force_general = 0, cells_tile_rows = 0, cells_band_tiles = 0, cells_threads = 0;
+  } dbg;
   // staging of the host-buffer entry point (allocated on first use, reused afterwards)
   struct HostStage {
     int64_t cap_rows = 0, ws_bytes = 0;

@@ -686,12 +686,8 @@ extern "C" int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r
   const int wc = solve_col_chunk(m, in_smem);
   if (wc < 1) { pgb_set_error("pgb_solve: m=%d too large", m); return PGB_EUNSUPPORTED; }
   const size_t smem = solve_vec_smem(m) + (size_t)kNB * wc * 8 + (in_smem ? (size_t)2 * m * m * 8 : 0);
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    PGB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax));
-    attr_set = true;
-  }
-  if (!in_smem && nb == 1 && (flags & PGB_SOLVE_PREPARED) && !getenv("PGB_SOLVE_SINGLE_CTA")) {
+  PGB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax));
+  if (!in_smem && nb == 1 && (flags & PGB_SOLVE_PREPARED)) {
     const int rc = solve_front(m, G, EtE, hv, tau, p, (double*)ws, (cudaStream_t)stream);
     if (rc != PGB_OK) return rc;
     flags |= PGB_SOLVE_FACTORED;
@@ -732,11 +728,7 @@ extern "C" int pgb_chol_check(int32_t m, const double* A, int32_t* info_out, voi
     pgb_set_error("pgb_chol_check: workspace too small");
     return PGB_EINVAL;
   }
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    PGB_CUDA(cudaFuncSetAttribute(chol_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax));
-    attr_set = true;
-  }
+  PGB_CUDA(cudaFuncSetAttribute(chol_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax));
   chol_check_kernel<<<1, kSolveThreads, vec + (in_smem ? (size_t)m * m * 8 : 0), (cudaStream_t)stream>>>(
       m, A, info_out, (double*)ws, in_smem ? 1 : 0);
   pgb_count_launch(1);

@@ -8,7 +8,6 @@ packed ``[G | r | scalars]`` buffer is all-reduced once per PIRLS iteration (SUR
 """
 
 import ctypes as C
-import os
 
 import numpy as np
 import torch
@@ -184,7 +183,8 @@ def _fill_marginal(d, q, t):
 class Engine:
     """compiled model + workspaces on one device"""
 
-    def __init__(self, terms, dist_name, link_name, levels=1.0, expectile=None, n_features=None, device=None):
+    def __init__(self, terms, dist_name, link_name, levels=1.0, expectile=None, n_features=None, device=None,
+                 debug_opts=None):
         if not torch.cuda.is_available():
             raise RuntimeError("pygam_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -195,10 +195,14 @@ class Engine:
         self.n_features = int(n_features)
         desc = build_descriptor(terms, self.n_features)
         handle = C.c_void_p()
-        _lib.check(self.lib.pgb_model_create(desc, len(terms), self.n_features, _lib.DISTS[dist_name],
-                                             _lib.LINKS[link_name], float(levels),
-                                             float(expectile) if expectile is not None else -1.0,
-                                             self.device.index or 0, C.byref(handle)), "pgb_model_create")
+        args = (desc, len(terms), self.n_features, _lib.DISTS[dist_name], _lib.LINKS[link_name], float(levels),
+                float(expectile) if expectile is not None else -1.0, self.device.index or 0)
+        if debug_opts is None:
+            _lib.check(self.lib.pgb_model_create(*args, C.byref(handle)), "pgb_model_create")
+        else:  # tests only: the same model with the plan of its Gram pass constrained
+            _lib.check(self.lib.pgb_debug_model_create(*args, C.byref(debug_opts), C.byref(handle)),
+                       "pgb_debug_model_create")
+        self.use_plan = True  # tests switch the stored row order off to exercise the in-kernel sort
         self.handle = handle
         info = _lib.PgbModelInfo()
         _lib.check(self.lib.pgb_model_get_info(self.handle, C.byref(info)), "pgb_model_get_info")
@@ -286,7 +290,7 @@ class Engine:
         """What does not depend on the coefficients (knot cells of the rows and their order, all-spline models)
         is prepared once per resident shard: the reference builds its model matrix once per fit, too
         (pygam.py:741).  Returns the mode flag for pgb_gram_pass."""
-        if self.info.cell_roles == 0 or not self._ws_has_order or os.environ.get("PGB_GRAM_PLAN", "1") == "0":
+        if self.info.cell_roles == 0 or not self._ws_has_order or not self.use_plan:
             return 0
         key = (data.Xt.data_ptr(), data.n, ws.data_ptr(), data.Xt._version)
         if self._plan_key != key:

@@ -3,9 +3,7 @@ GPU, agreement with the general shared-memory path of pgb_gram.cu and with the o
 inputs, over the shapes that exercise its scheduling (odd n, several tiles and bands, role
 switches, key ranges, extrapolated rows, weights, no intercept)."""
 import contextlib
-import ctypes as C
 import io
-import os
 
 import numpy as np
 import pytest
@@ -22,10 +20,13 @@ def test_cell_plan_of_all_spline_models():
     _, info, errs = plan_for(cases.FIT_CASES["c2_logistic"], rng.random((50, 10)))
     assert errs == 0
     assert info.cell_roles == 55 and info.cell_tile_rows >= 1024  # 45 pairs + 10 diagonal blocks
-    # factor and tensor terms keep the general path
+    # f(), l() and te() of two cubic marginals are generic pairs of the same pass (configs 1 and 3) ...
     _, info1, e1 = plan_for(cases.FIT_CASES["c1_wage"], helpers.load("fit_c1_wage")["X"])
     _, info3, e3 = plan_for(cases.FIT_CASES["c3_poisson"], rng.random((50, 24)))
-    assert (info1.cell_roles, e1, info3.cell_roles, e3) == (0, 0, 0, 0)
+    assert info1.cell_roles > 3 and info3.cell_roles > 210 + 40 and (e1, e3) == (0, 0)
+    # ... other spline orders, cyclic bases and by= keep the general path
+    _, infom, em = plan_for(cases.FIT_CASES["mixed_terms"], helpers.load("fit_mixed_terms")["X"])
+    assert (infom.cell_roles, em) == (0, 0)
 
 
 @pytest.mark.parametrize("n_splines", [4, 5, 20, 60])
@@ -43,21 +44,14 @@ gpu = pytest.mark.gpu
 
 
 def _engines(gam, n_features, env):
-    """two engines of the same compiled model: cell-owned Gram pass and the general path"""
+    """two engines of the same compiled model: cell-owned Gram pass and the general path (the test-only entry
+    point pgb_debug_model_create constrains the plan)"""
     from pygam_b200.engine import Engine
 
     def make(cells):
-        old = {k: os.environ.get(k) for k in list(env) + ["PGB_GRAM_CELLS"]}
-        os.environ.update(env)
-        os.environ["PGB_GRAM_CELLS"] = "1" if cells else "0"
-        try:
-            return Engine(gam.terms, gam.distribution.name, gam.link.name, gam.distribution.levels, gam._expectile, n_features)
-        finally:
-            for k, v in old.items():
-                if v is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = v
+        opts = _lib.PgbDebugOpts(0 if cells else 1, int(env.get("tile", 0)), int(env.get("band", 0)), int(env.get("threads", 0)))
+        return Engine(gam.terms, gam.distribution.name, gam.link.name, gam.distribution.levels, gam._expectile, n_features,
+                      debug_opts=opts)
 
     a, b = make(True), make(False)
     assert a.info.cell_roles > 0 and b.info.cell_roles == 0
@@ -69,6 +63,8 @@ def _compare(gam, X, y, w=None, env=None, modes=(_lib.MODE_IRLS, _lib.MODE_INIT)
     from pygam_b200.engine import DeviceData
 
     cells, general = _engines(gam, X.shape[1], env or {})
+    # a model with generic pairs runs the same prepass with and without the stored order: bit-equal results
+    mixed = any(type(t).__name__ in ("TensorTerm", "FactorTerm", "LinearTerm") for t in gam.terms)
     data = DeviceData.from_host(X, y, None if w is None else np.asarray(w, dtype=np.float32))
     m = cells.m
     rng = np.random.default_rng(3)
@@ -90,12 +86,12 @@ def _compare(gam, X, y, w=None, env=None, modes=(_lib.MODE_IRLS, _lib.MODE_INIT)
         # the prepared order (pgb_gram_prepare, the default for resident data) and the in-kernel sort of the
         # streaming path visit the rows of a cell in the same order; the prepared prepass rebuilds t from the
         # stored centred coordinate (one rounding in lp), so IRLS weights agree to rounding, INIT bit for bit
-        os.environ["PGB_GRAM_PLAN"] = "0"
+        cells.use_plan = False
         try:
             unplanned = cells.gram_pass(data, coef, mode=mode).cpu().numpy()
         finally:
-            os.environ.pop("PGB_GRAM_PLAN", None)
-        if mode == _lib.MODE_INIT:
+            cells.use_plan = True
+        if mode == _lib.MODE_INIT or mixed:
             assert np.array_equal(a, unplanned)
         else:
             assert np.abs(a - unplanned).max() <= 1e-13 * scale
@@ -110,8 +106,8 @@ def _fit_small(case, X, y, **kw):
 
 
 @gpu
-@pytest.mark.parametrize("n,env", [(20001, {}), (30000, {"PGB_CELLS_TILE": "1024", "PGB_CELLS_BAND": "2"}),
-                                   (777, {}), (65536, {"PGB_CELLS_TILE": "2048", "PGB_CELLS_BAND": "1"})])
+@pytest.mark.parametrize("n,env", [(20001, {}), (30000, {"tile": 1024, "band": 2}),
+                                   (777, {}), (65536, {"tile": 2048, "band": 1})])
 def test_cells_equal_general_path_config2(n, env):
     X, y = cases.data_c2(n, seed=11)
     X[:4000] = np.clip(X[:4000], 0.0, 1.0)
@@ -135,7 +131,7 @@ def test_cells_extrapolated_rows_weights_and_skewed_columns():
     case = {"model": "PoissonGAM", "terms": [dict(kind="s", feature=0, n_splines=12), dict(kind="s", feature=1),
                                              dict(kind="s", feature=2, n_splines=31)]}
     gam = _fit_small(case, X, y)
-    _compare(gam, X, y, w=w, env={"PGB_CELLS_TILE": "4096"})
+    _compare(gam, X, y, w=w, env={"tile": 4096})
 
 
 @gpu
@@ -151,3 +147,37 @@ def test_cells_key_ranges_and_no_intercept():
     _compare(gam, X, y, modes=(_lib.MODE_IRLS,))
     gam1 = _fit_small({"model": "GammaGAM", "terms": [dict(kind="s", feature=0, n_splines=9)]}, X, np.exp(y))
     _compare(gam1, X, np.exp(y))
+
+
+@gpu
+@pytest.mark.parametrize("name,env", [("c1_wage", {}), ("c1_wage", {"tile": 512, "band": 2}), ("c3_poisson", {}),
+                                      ("c3_poisson", {"tile": 1024, "band": 1, "threads": 256}), ("dummy_coding", {}),
+                                      ("multi_penalty", {"tile": 256})])
+def test_cells_equal_general_path_mixed_terms(name, env):
+    """te() / f() / l() blocks as generic cell pairs (BASELINE configs 1 and 3) vs the general path"""
+    case = cases.FIT_CASES[name]
+    g = helpers.load("fit_" + name)
+    gam = helpers.build_model(case, max_iter=3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if case["model"] == "PoissonGAM":
+            gam.fit(g["X"], g["y"], exposure=g.get("exposure"), weights=g.get("weights"))
+        else:
+            gam.fit(g["X"], g["y"], weights=g.get("weights"))
+    _compare(gam, g["X"], g["y"], w=g.get("weights"), env=env)
+
+
+@gpu
+def test_cells_te_f_l_rows_outside_knots_large():
+    """te() twice (4-d cells), f(), l(), custom edge knots narrower than the data, several tiles and bands"""
+    rng = np.random.default_rng(7)
+    n = 50_003
+    X = np.column_stack([rng.random(n), rng.random(n), rng.integers(0, 4, n).astype(float), rng.standard_normal(n),
+                         rng.random(n), rng.random(n)])
+    eta = np.sin(4 * X[:, 0]) * X[:, 1] + 0.3 * X[:, 2] + 0.2 * X[:, 3] + X[:, 4] * X[:, 5]
+    y = rng.poisson(np.exp(0.4 * eta)).astype(float)
+    s, te, f, l = cases.s, cases.te, cases.f, cases.l
+    case = dict(model="PoissonGAM",
+                terms=[te(s(0, n_splines=6), s(1, n_splines=5)), f(2), l(3), s(4, n_splines=7, edge_knots=[0.1, 0.8]),
+                       te(s(5, n_splines=5, edge_knots=[0.2, 0.9]), s(0, n_splines=4))])
+    gam = _fit_small(case, X, y)
+    _compare(gam, X, y, env={"tile": 2048, "band": 3})

@@ -28,7 +28,6 @@ def main():
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--only-gram", action="store_true")
-    ap.add_argument("--dbg", type=int, default=0, help="PGB_GRAM_DEBUG bits applied to the timed passes only")
     a = ap.parse_args()
     gen, F = GEN[a.case]
     Xs, ys = gen(20000)
@@ -46,9 +45,6 @@ def main():
     lib = _lib.load()
     coef = gam.coef_
     _lib.check(lib.pgb_gram_timing(eng.handle, 1), "timing")
-    if a.dbg:
-        os.environ["PGB_GRAM_DEBUG"] = str(a.dbg)
-        C.CDLL(None).setenv(b"PGB_GRAM_DEBUG", str(a.dbg).encode(), 1)
     ms, rs, ts = [], [], []
     for _ in range(a.reps + 2):
         eng.gram_pass(data, coef)
