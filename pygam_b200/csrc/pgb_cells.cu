@@ -259,10 +259,34 @@ int pgb_plan_cells(pgb_model* M) {
   for (DGenOrder& O : C.gorders) O.hmul = ((uint32_t)O.nh << 16) / (uint32_t)C.tile_rows;
   C.smem = cells_smem(C.tile_rows, TH);
   C.slots_per_cta = ((int)C.roles.size() + C.grid - 1) / C.grid + 1;
-  C.gslots_per_cta = C.groles.empty() ? 0 : ((int)C.groles.size() + C.grid - 1) / C.grid + 1;
+  C.gslots_per_cta = 0;
+  if (!C.groles.empty()) {
+    // weight of a role's tile: the dependent gathers of its fullest threads, about rows per cell + a constant
+    const int nr = (int)C.groles.size();
+    C.grole_prefix.assign(nr + 1, 0);
+    for (int r = 0; r < nr; ++r) {
+      const DGenPair& P = C.gpairs[C.groles[r].pair];
+      const int w = 3 + (int)std::min<int64_t>(60, ((int64_t)C.tile_rows + P.ncells - 1) / P.ncells);
+      C.grole_prefix[r + 1] = C.grole_prefix[r] + w;
+    }
+    const int64_t W = C.grole_prefix[nr];
+    C.gcta_role_lo.assign(C.grid, 0);
+    for (int r = 0; r < nr; ++r) { C.groles[r].c_lo = C.grid; C.groles[r].c_hi = -1; }
+    for (int c = 0, r0 = 0; c < C.grid; ++c) {
+      // CTA c covers [W c / grid, W (c + 1) / grid) of the weight axis; role r covers [prefix[r], prefix[r + 1])
+      while (r0 < nr - 1 && (int64_t)C.grole_prefix[r0 + 1] * C.grid <= W * c) ++r0;
+      C.gcta_role_lo[c] = r0;
+      int cnt = 0;
+      for (int r = r0; r < nr && (int64_t)C.grole_prefix[r] * C.grid < W * (c + 1); ++r) {
+        C.groles[r].c_lo = std::min(C.groles[r].c_lo, c);
+        C.groles[r].c_hi = std::max(C.groles[r].c_hi, c);
+        ++cnt;
+      }
+      C.gslots_per_cta = std::max(C.gslots_per_cta, cnt + 1);
+    }
+  }
   C.slot_doubles = (int64_t)kCellAcc * TH;
   for (int r = 0; r < (int)C.roles.size(); ++r) role_cta_range((int64_t)C.roles.size(), C.grid, r, C.roles[r].c_lo, C.roles[r].c_hi);
-  for (int r = 0; r < (int)C.groles.size(); ++r) role_cta_range((int64_t)C.groles.size(), C.grid, r, C.groles[r].c_lo, C.groles[r].c_hi);
   // coefficient -> (term, local index) for the assembly
   C.coef_term.assign(M->m, -1);
   for (int j = 0; j < nt; ++j)
@@ -295,6 +319,8 @@ int pgb_cells_upload(pgb_model* M) {
   up((void**)&C.d_groles, C.groles.data(), C.groles.size() * sizeof(DGenRole));
   up((void**)&C.d_term_class, C.term_class.data(), C.term_class.size() * sizeof(int32_t));
   up((void**)&C.d_gpair_of, C.gpair_of.data(), C.gpair_of.size() * sizeof(int32_t));
+  up((void**)&C.d_grole_prefix, C.grole_prefix.data(), C.grole_prefix.size() * sizeof(int32_t));
+  up((void**)&C.d_gcta_role_lo, C.gcta_role_lo.data(), C.gcta_role_lo.size() * sizeof(int32_t));
   if (e != cudaSuccess) return pgb_cuda_fail(e, "pgb_cells_upload");
   return PGB_OK;
 }
@@ -310,6 +336,9 @@ void pgb_cells_release(pgb_model* M) {
   cudaFree(C.d_groles);
   cudaFree(C.d_term_class);
   cudaFree(C.d_gpair_of);
+  cudaFree(C.d_grole_prefix);
+  cudaFree(C.d_gcta_role_lo);
+  C.d_grole_prefix = nullptr; C.d_gcta_role_lo = nullptr;
   C.d_roles = nullptr; C.d_pairs = nullptr; C.d_coef_term = nullptr; C.d_pair_of = nullptr;
   C.d_gorders = nullptr; C.d_gpairs = nullptr; C.d_groles = nullptr; C.d_term_class = nullptr; C.d_gpair_of = nullptr;
 }
@@ -1109,19 +1138,27 @@ gram_cells_order_kernel(int64_t n, int64_t np, const uint8_t* __restrict__ cq, c
   int* cnt = reinterpret_cast<int*>(perm + TR);
   int* cur = cnt + kGenChunk;
   __shared__ DGenOrder O;
-  __shared__ int s_wtot[kGenThreads / 32], s_base;
+  __shared__ int s_wtot[kGenThreads / 32], s_base, s_careful;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int PER = kGenChunk / kGenThreads;
   for (int64_t u = blockIdx.x; u < ntl * n_orders; u += gridDim.x) {
     const int64_t tile = u / n_orders;
     const int o = (int)(u - tile * n_orders);
     __syncthreads();
-    if (tid == 0) { O = orders[o]; s_base = 0; }
+    if (tid == 0) { O = orders[o]; s_base = 0; s_careful = 0; }
     __syncthreads();
     const int64_t row0 = tile * TR;
     const int cnt_rows = (int)min((int64_t)TR, n - row0);
+    uint32_t outside = 0;  // a row outside the edge knots of a cubic key column: the sum kernel takes its careful variant
     for (int r = tid; r < cnt_rows; r += kGenThreads)
-      keys[r] = (uint16_t)gen_key(O, r, [&](int c) { return (uint32_t)__ldg(cq + (int64_t)c * np + row0 + r); });
+      keys[r] = (uint16_t)gen_key(O, r, [&](int c) {
+        const uint32_t b = __ldg(cq + (int64_t)c * np + row0 + r);
+        outside |= b;
+        return b;
+      });
+    bool any_out = false;
+    for (int d = 0; d < O.nkey; ++d) any_out |= O.key_kind[d] == PGB_FK_CUBIC;
+    if (any_out && (outside & 0x80u)) s_careful = 1;
     uint16_t* sg = starts_g + O.starts_off * ntl + tile * O.spitch;
     for (int k0 = 0; k0 < O.ncells; k0 += kGenChunk) {
       for (int j = tid; j < kGenChunk; j += kGenThreads) cnt[j] = 0;
@@ -1172,35 +1209,198 @@ gram_cells_order_kernel(int64_t n, int64_t np, const uint8_t* __restrict__ cq, c
       }
       __syncthreads();
     }
-    if (tid == 0) sg[O.ncells] = (uint16_t)s_base;
+    if (tid == 0) {
+      sg[O.ncells] = (uint16_t)s_base;
+      sg[O.ncells + 1] = (uint16_t)s_careful;
+    }
     const int placed = s_base;
     uint16_t* pg = perm_g + ((int64_t)o * ntl + tile) * TR;
     for (int i = tid; i < placed; i += kGenThreads) pg[i] = perm[i];
   }
 }
 
+// ---- weighted units of the generic kernel.  A role's tile costs about (rows per cell + a constant) dependent
+// gathers, which differs by an order of magnitude between a 4-d te() x te() pair and the intercept column of a te():
+// role r counts w_r virtual units per tile, the virtual axis of a band (nb tiles x sum of the weights) is cut into
+// equal shares, and a (role, tile) belongs to the CTA whose share holds its first virtual unit.
+struct WUnitIter {
+  const int32_t* pre;  // prefix sums of the role weights (n_roles + 1 entries, shared memory)
+  int64_t ntiles, nbands, band, nb, t0, v_lo, v_hi;
+  int64_t t;
+  int band_tiles, n_roles, W, r;
+  bool ok;
+  __device__ int find_role(int64_t x) const {  // largest r with pre[r] * nb <= x
+    int lo = 0, hi = n_roles - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((int64_t)pre[mid] * nb <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+  }
+  __device__ int64_t vstart() const { return (int64_t)pre[r] * nb + t * (pre[r + 1] - pre[r]); }
+  __device__ void set_band() {
+    t0 = band * band_tiles;
+    nb = min((int64_t)band_tiles, ntiles - t0);
+    const int64_t V = nb * W;
+    v_lo = V * blockIdx.x / gridDim.x;
+    v_hi = V * (blockIdx.x + 1) / gridDim.x;
+    ok = false;
+    if (v_hi <= v_lo) return;
+    if (!(band & 1)) {  // forwards: first unit that starts at or after v_lo
+      r = find_role(v_lo);
+      const int w = pre[r + 1] - pre[r];
+      t = (v_lo - (int64_t)pre[r] * nb + w - 1) / w;
+      if (t >= nb) { ++r; t = 0; }
+      ok = r < n_roles && vstart() < v_hi;
+    } else {  // backwards: last unit that starts before v_hi
+      r = find_role(v_hi - 1);
+      const int w = pre[r + 1] - pre[r];
+      t = min(nb - 1, (v_hi - 1 - (int64_t)pre[r] * nb) / w);
+      ok = vstart() >= v_lo;
+    }
+  }
+  __device__ void skip_empty() {
+    while (band < nbands && !ok) {
+      ++band;
+      if (band < nbands) set_band();
+    }
+  }
+  __device__ void init(int64_t n, int TR, int bt, int nr, const int32_t* prefix) {
+    pre = prefix;
+    band_tiles = bt;
+    n_roles = nr;
+    W = prefix[nr];
+    ntiles = (n + TR - 1) / TR;
+    nbands = (ntiles + bt - 1) / bt;
+    band = 0;
+    set_band();
+    skip_empty();
+  }
+  __device__ bool valid() const { return band < nbands; }
+  __device__ int role() const { return r; }
+  __device__ int64_t tile() const { return t0 + t; }
+  __device__ void next() {
+    if (!(band & 1)) {
+      if (++t >= nb) { ++r; t = 0; }
+      ok = r < n_roles && vstart() < v_hi;
+    } else {
+      if (--t < 0) { --r; t = nb - 1; }
+      ok = r >= 0 && vstart() >= v_lo;
+    }
+    skip_empty();
+  }
+};
+
+template <bool CAREFUL>
+__device__ __forceinline__ void gen_pw(int nint, double s, double (&p)[4]) {
+  if (CAREFUL) {
+    record_powers(nint, s, p);
+  } else {
+    p[0] = 1.0;
+    p[1] = s;
+    p[2] = s * s;
+    p[3] = p[2] * s;
+  }
+}
+// s^e for a thread-constant exponent e
+template <bool CAREFUL>
+__device__ __forceinline__ double gen_pow(int nint, double s, int e) {
+  if (CAREFUL) {
+    double p[4];
+    record_powers(nint, s, p);
+    return sel4(p, e);
+  }
+  const double x = (e & 1) ? s : 1.0, y = (e & 2) ? s * s : 1.0;
+  return x * y;
+}
+
+// One row of a generic pair: NOUT outer cubic factors (exponents e0, e1 of this thread's slice), NIN inner ones
+// (2: acc[4 p + q], 1: acc[q], 0: acc[0]), NVAL value factors.  v[] = the row's record coordinates in the order
+// (values, outer 0, outer 1, inner a, inner b).
+template <int NOUT, int NIN, int NVAL, bool CAREFUL>
+__device__ __forceinline__ void gen_row(double mult, const double* v, const int* nint, int e0, int e1, double (&acc)[16]) {
+#pragma unroll
+  for (int q = 0; q < NVAL; ++q) mult *= v[q];
+  if (NOUT >= 1) mult *= gen_pow<CAREFUL>(nint[0], v[NVAL], e0);
+  if (NOUT >= 2) mult *= gen_pow<CAREFUL>(nint[1], v[NVAL + 1], e1);
+  if (NIN == 0) {
+    acc[0] += mult;
+  } else if (NIN == 1) {
+    double b[4];
+    gen_pw<CAREFUL>(nint[3], v[NVAL + NOUT], b);
+    if (CAREFUL) acc[0] = fma(mult, b[0], acc[0]); else acc[0] += mult;
+    acc[1] = fma(mult, b[1], acc[1]); acc[2] = fma(mult, b[2], acc[2]); acc[3] = fma(mult, b[3], acc[3]);
+  } else {
+    double a[4], b[4];
+    gen_pw<CAREFUL>(nint[2], v[NVAL + NOUT], a);
+    gen_pw<CAREFUL>(nint[3], v[NVAL + NOUT + 1], b);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const double u = (p == 0 && !CAREFUL) ? mult : mult * a[p];
+      if (CAREFUL) acc[4 * p] = fma(u, b[0], acc[4 * p]); else acc[4 * p] += u;
+      acc[4 * p + 1] = fma(u, b[1], acc[4 * p + 1]);
+      acc[4 * p + 2] = fma(u, b[2], acc[4 * p + 2]);
+      acc[4 * p + 3] = fma(u, b[3], acc[4 * p + 3]);
+    }
+  }
+}
+
+// the rows s0 .. s1 - 1 of a cell in the stored order, two rows in flight: the gathers of a pair of rows are issued
+// together, the row indices of the next pair are fetched one step ahead
+template <int NOUT, int NIN, int NVAL, bool CAREFUL>
+__device__ __forceinline__ void gen_rows(const uint16_t* __restrict__ pg, int s0, int s1, const double* __restrict__ wcol,
+                                         const double* const* cols, const int* nint, int e0, int e1, double (&acc)[16]) {
+  constexpr int NC = NVAL + NOUT + NIN;
+  int r0 = pg[s0], r1 = (s0 + 1 < s1) ? pg[s0 + 1] : 0;
+  for (int s = s0; s < s1; s += 2) {
+    const bool two = s + 1 < s1;
+    const int ra = r0, rb = r1;
+    if (s + 2 < s1) r0 = pg[s + 2];
+    if (s + 3 < s1) r1 = pg[s + 3];
+    double va[NC > 0 ? NC : 1], vb[NC > 0 ? NC : 1];
+    const double wa = __ldg(wcol + ra);
+    const double wb = two ? __ldg(wcol + rb) : 0.0;
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+      va[q] = __ldg(cols[q] + ra);
+      vb[q] = two ? __ldg(cols[q] + rb) : 0.0;
+    }
+    gen_row<NOUT, NIN, NVAL, CAREFUL>(wa, va, nint, e0, e1, acc);
+    if (two) gen_row<NOUT, NIN, NVAL, CAREFUL>(wb, vb, nint, e0, e1, acc);
+  }
+}
+
 // The generic sum kernel: thread (cell, slice) of a role walks the rows of its cell in the stored order and reads
 // their record coordinates straight from the (L2-resident) band -- a role touches only the few rows of its own
 // cells, so nothing is staged in shared memory; the lanes of a cell's slices read the same addresses.  Same
-// units, partial slots and reproducible order as the spline kernels.
+// partial slots and reproducible order as the spline kernels.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 320 ? 2 : 1))
 gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, const double* __restrict__ omz,
                           const double* __restrict__ tq, const DGenRole* __restrict__ roles,
-                          const DGenPair* __restrict__ pairs, int n_roles, int TR, int band_tiles, int slots_per_cta,
+                          const DGenPair* __restrict__ pairs, int n_roles, const int32_t* __restrict__ role_prefix,
+                          const int32_t* __restrict__ cta_role_lo, int TR, int band_tiles, int slots_per_cta,
                           double* __restrict__ part, const uint16_t* __restrict__ perm_g,
                           const uint16_t* __restrict__ starts_g, int64_t ntl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* s_pre = reinterpret_cast<int32_t*>(smem_raw);
   __shared__ DGenPair P;
   __shared__ DGenRole R;
   const int tid = threadIdx.x;
-  const int role_lo = (int)((int64_t)n_roles * blockIdx.x / gridDim.x);
+  for (int i = tid; i <= n_roles; i += THREADS) s_pre[i] = role_prefix[i];
+  __syncthreads();
+  const int role_lo = cta_role_lo[blockIdx.x];
   double* my_part = part + (int64_t)blockIdx.x * slots_per_cta * (kCellAcc * THREADS);
   int cur_role = -1;
   double acc[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) acc[e] = 0.0;
-  UnitIter it;
-  it.init(n, TR, band_tiles, n_roles);
+  // per role: this thread's cell and slice, the columns it gathers
+  int k = 0, e0 = 0, e1 = 0, shape = 0;
+  int nint[4] = {1, 1, 1, 1};
+  const double* cbase[6] = {tq, tq, tq, tq, tq, tq};
+  WUnitIter it;
+  it.init(n, TR, band_tiles, n_roles, s_pre);
   for (; it.valid(); it.next()) {
     const int role = it.role();
     const int64_t tile = it.tile();
@@ -1220,23 +1420,50 @@ gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, 
       }
       __syncthreads();
       cur_role = role;
+      const int nsl = P.nsl;
+      k = tid / nsl;
+      const int sg = tid - k * nsl;
+      e0 = sg & 3;
+      e1 = (sg >> 2) & 3;
+      const int nout = (P.out0 >= 0) + (P.out1 >= 0), nin = (P.in_b >= 0) + (P.in_a >= 0);
+      shape = nout * 9 + nin * 3 + P.nval;
+      int q = 0;
+      for (int j = 0; j < P.nval; ++j) cbase[q++] = tq + (int64_t)P.val_col[j] * np;
+      if (P.out0 >= 0) { nint[0] = P.f_n[P.out0]; cbase[q++] = tq + (int64_t)P.f_col[P.out0] * np; }
+      if (P.out1 >= 0) { nint[1] = P.f_n[P.out1]; cbase[q++] = tq + (int64_t)P.f_col[P.out1] * np; }
+      if (P.in_a >= 0) { nint[2] = P.f_n[P.in_a]; cbase[q++] = tq + (int64_t)P.f_col[P.in_a] * np; }
+      if (P.in_b >= 0) { nint[3] = P.f_n[P.in_b]; cbase[q++] = tq + (int64_t)P.f_col[P.in_b] * np; }
+      if (k >= R.ncl) k = -1;
     }
-    const int nsl = P.nsl;
-    const int k = tid / nsl, sg = tid - k * nsl;
-    if (k >= R.ncl) continue;
-    const uint16_t* st = starts_g + P.starts_off * ntl + tile * P.spitch + R.key0 + k;
-    const int s0 = st[0], s1 = st[1];
+    if (k < 0) continue;
+    const uint16_t* sgt = starts_g + P.starts_off * ntl + tile * P.spitch;
+    const int s0 = sgt[R.key0 + k], s1 = sgt[R.key0 + k + 1];
     if (s0 >= s1) continue;
+    const bool careful = sgt[P.ncells + 1] != 0;
     const int64_t row0 = tile * TR;
     const uint16_t* pg = perm_g + ((int64_t)P.order * ntl + tile) * TR;
     const double* wcol = (P.wz ? omz : om) + row0;
-    const double* tcol = tq + row0;
-    int rn = pg[s0];
-    for (int s = s0; s < s1; ++s) {
-      const int r = rn;
-      if (s + 1 < s1) rn = pg[s + 1];
-      gen_row_acc(P, sg, __ldg(wcol + r), [&](int c) { return __ldg(tcol + (int64_t)c * np + r); }, acc);
+    const double* cols[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) cols[q] = cbase[q] + row0;
+#define PGB_GEN_CASE(NOUT, NIN, NVAL)                                                                             \
+  case (NOUT) * 9 + (NIN) * 3 + (NVAL):                                                                           \
+    if (!careful) gen_rows<NOUT, NIN, NVAL, false>(pg, s0, s1, wcol, cols, nint, e0, e1, acc);                    \
+    else gen_rows<NOUT, NIN, NVAL, true>(pg, s0, s1, wcol, cols, nint, e0, e1, acc);                              \
+    break;
+    switch (shape) {
+      PGB_GEN_CASE(1, 2, 0)  // s() x te()
+      PGB_GEN_CASE(2, 2, 0)  // te() x te(), the diagonal block of a te()
+      PGB_GEN_CASE(0, 2, 0)  // te() x intercept / rhs / f()
+      PGB_GEN_CASE(0, 2, 1)  // te() x l()
+      PGB_GEN_CASE(0, 1, 0)  // s() x f()
+      PGB_GEN_CASE(0, 1, 1)  // s() x l()
+      PGB_GEN_CASE(0, 0, 0)  // f() x f() / intercept / rhs
+      PGB_GEN_CASE(0, 0, 1)  // l() x f() / intercept / rhs
+      PGB_GEN_CASE(0, 0, 2)  // l() x l()
+      default: break;        // no other shape is planned (pgb_plan_cells)
     }
+#undef PGB_GEN_CASE
   }
   if (cur_role >= 0) {
     double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * THREADS);
@@ -1248,21 +1475,19 @@ gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, 
 // generic sums[pair][product][cell] = sum over the CTAs that served the cell's role, fixed order; product =
 // sum index of the thread + n_acc * slice
 __global__ void cells_generic_reduce_kernel(const double* __restrict__ part, const DGenRole* __restrict__ roles,
-                                            const DGenPair* __restrict__ pairs, int n_roles, int grid, int slots_per_cta,
-                                            int threads, double* __restrict__ sums) {
+                                            const DGenPair* __restrict__ pairs, const int32_t* __restrict__ cta_role_lo,
+                                            int slots_per_cta, int threads, double* __restrict__ sums) {
   const int role = blockIdx.x, tid = threadIdx.x, e = blockIdx.y;
   const DGenRole R = roles[role];
   const DGenPair& P = pairs[R.pair];
   const int nsl = P.nsl, n_acc = P.n_acc;
   const int k = tid / nsl, sg = tid - k * nsl;
   if (k >= R.ncl || e >= n_acc) return;
-  const int64_t nr = n_roles;
   double v = 0.0;
   for (int c = R.c_lo; c <= R.c_hi; ++c) {
-    const int lo = (int)(nr * c / grid);
-    const int hi = (int)((nr * (c + 1) + grid - 1) / grid) - 1;
-    if (role < lo || role > hi || role - lo >= slots_per_cta) continue;
-    v += part[((int64_t)c * slots_per_cta + (role - lo)) * (kCellAcc * threads) + e * threads + tid];
+    const int slot = role - cta_role_lo[c];
+    if (slot < 0 || slot >= slots_per_cta) continue;
+    v += part[((int64_t)c * slots_per_cta + slot) * (kCellAcc * threads) + e * threads + tid];
   }
   sums[P.sum_off + (int64_t)(e + n_acc * sg) * P.ncells + R.key0 + k] = v;
 }
@@ -1534,9 +1759,9 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
                                                                     band_tiles, C.slots_per_cta, part, nullptr, nullptr); \
     }                                                                                                                    \
     if (n_groles > 0)                                                                                                    \
-      gram_cells_generic_kernel<TH><<<C.grid, TH, 0, st>>>(n, np, om, omz, tq, C.d_groles, C.d_gpairs, n_groles, TR,     \
-                                                           band_tiles, C.gslots_per_cta, L.gpart, L.gperm, L.gstarts,    \
-                                                           L.ntl);                                                       \
+      gram_cells_generic_kernel<TH><<<C.grid, TH, (size_t)(n_groles + 1) * 4, st>>>(                                   \
+          n, np, om, omz, tq, C.d_groles, C.d_gpairs, n_groles, C.d_grole_prefix, C.d_gcta_role_lo, TR, band_tiles,    \
+          C.gslots_per_cta, L.gpart, L.gperm, L.gstarts, L.ntl);                                                       \
   } while (0)
   PGB_CELLS_DISPATCH(PGB_CELLS_LAUNCH)
 #undef PGB_CELLS_LAUNCH
@@ -1552,7 +1777,7 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
     launches += 3;
   }
   if (n_groles > 0) {
-    cells_generic_reduce_kernel<<<dim3(n_groles, 16), C.threads, 0, st>>>(L.gpart, C.d_groles, C.d_gpairs, n_groles, C.grid,
+    cells_generic_reduce_kernel<<<dim3(n_groles, 16), C.threads, 0, st>>>(L.gpart, C.d_groles, C.d_gpairs, C.d_gcta_role_lo,
                                                                         C.gslots_per_cta, C.threads, sums);
     int64_t max_lines = 1;
     int max_ax = 0;

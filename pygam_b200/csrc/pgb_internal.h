@@ -157,6 +157,7 @@ struct pgb_model {
     std::vector<DGenPair> gpairs;
     std::vector<DGenRole> groles;
     std::vector<int32_t> term_class, gpair_of;  // 0 intercept, 1 plain cubic s(), 2 generic; (ta, tb) -> generic pair
+    std::vector<int32_t> grole_prefix, gcta_role_lo;  // weighted units of the generic kernel (WUnitIter)
     DCellRole* d_roles = nullptr;
     DCellPair* d_pairs = nullptr;
     int32_t* d_coef_term = nullptr;
@@ -166,6 +167,8 @@ struct pgb_model {
     DGenRole* d_groles = nullptr;
     int32_t* d_term_class = nullptr;
     int32_t* d_gpair_of = nullptr;
+    int32_t* d_grole_prefix = nullptr;
+    int32_t* d_gcta_role_lo = nullptr;
     int32_t tile_rows = 0, grid = 0, slots_per_cta = 0, icpt_coef = -1, n_spl = 0, occ = 1, threads = 512;
     int32_t ncol = 0;                  // record columns (one per factor)
     int32_t gslots_per_cta = 0;
