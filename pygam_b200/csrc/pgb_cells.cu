@@ -36,6 +36,9 @@
 
 static const int kCellAcc = 18;           // sums per cell (16 for a pair; 10 + 4 + 4 for a diagonal role)
 static const int kPreThreads = 256;
+static const int kGenAcc = 64;            // sums per thread of the generic kernel (4 x 4 inner x 4 exponents of the first outer factor)
+static const int kGenSumThreads = 256;    // CTA of the generic kernel
+static const int kGenOcc = 1;             // its CTAs per SM (64 sums per thread: about 200 registers)
 static const int64_t kBandBytes = 32ll << 20;  // column bytes of a band of rows (stays in the L2)
 
 // tile: t_i, t_j (or omega z), omega; sorted row index; the two interval bytes (later the 16-bit cell key) per row;
@@ -210,9 +213,12 @@ int pgb_plan_cells(pgb_model* M) {
         P.n_acc = nc >= 2 ? 16 : nc == 1 ? 4 : 1;
         P.nsl = nc >= 4 ? 16 : nc == 3 ? 4 : 1;
         P.nprod = P.n_acc * P.nsl;
+        P.ne = nc >= 3 ? 4 : 1;
+        P.nslt = P.nsl / P.ne;
         int64_t kc = 1;
         for (int d = O.nkey - 1; d >= 0; --d) { O.key_mul[d] = (int32_t)kc; kc *= O.key_n[d]; }
-        O.nh = (int)std::max<int64_t>(1, std::min<int64_t>(32, 256 / kc));
+        // hash split of the rows of a cell: runs of about 32 rows per (cell, split) and generic tile
+        O.nh = (int)std::max<int64_t>(1, std::min<int64_t>(256, 1024 / kc));
         if (kc * O.nh > 65000) { C = pgb_model::Cells(); return PGB_OK; }
         O.ncells = (int32_t)(kc * O.nh);
         O.spitch = (O.ncells + 2 + 7) & ~7;
@@ -237,7 +243,7 @@ int pgb_plan_cells(pgb_model* M) {
         const int pi = (int)C.gpairs.size();
         C.gpair_of[(size_t)i * (nt + 1) + j] = pi;
         C.gpairs.push_back(P);
-        const int ncl = std::max(1, TH / P.nsl);
+        const int ncl = std::max(1, kGenSumThreads / P.nslt);
         for (int k0 = 0; k0 < P.ncells; k0 += ncl) {
           DGenRole R{};
           R.pair = pi; R.key0 = k0; R.ncl = std::min(ncl, P.ncells - k0);
@@ -250,13 +256,18 @@ int pgb_plan_cells(pgb_model* M) {
     if (C.groles.size() > 16384 || C.gorders.size() > 4096) { C = pgb_model::Cells(); return PGB_OK; }
   }
   C.grid = kSMs * (C.occ == 3 ? 2 : C.occ);
+  C.ggrid = kSMs * kGenOcc;
   C.tile_rows = (C.occ == 3) ? 4096 : 8192;
   if (M->dbg.cells_tile_rows > 0) C.tile_rows = std::max(64, M->dbg.cells_tile_rows & ~63);
   // 1 KB per CTA for the kernel's static shared memory and the driver's reservation
   while (cells_smem(C.tile_rows, TH) + 1024 > (C.occ == 2 ? kSmemMax / 2 - 1024 : kSmemMax)) C.tile_rows -= 64;
   if (C.occ == 3) while ((size_t)C.tile_rows * 26 + (TH + 8) * 2 + 1024 > kSmemMax / 2 - 1024) C.tile_rows -= 64;
   for (DCellRole& R : C.roles) R.hmul = ((uint32_t)R.ncb << 16) / (uint32_t)C.tile_rows;
-  for (DGenOrder& O : C.gorders) O.hmul = ((uint32_t)O.nh << 16) / (uint32_t)C.tile_rows;
+  // The generic orders sort much longer tiles than the spline roles: a thread's run of rows must be long enough
+  // to amortise its start (three dependent gathers) and to even out the lanes of a warp; nothing of a generic
+  // tile is staged in shared memory, so only the 16-bit row index bounds it
+  C.gtile_rows = M->dbg.cells_tile_rows > 0 ? 8 * C.tile_rows : 32768;
+  for (DGenOrder& O : C.gorders) O.hmul = ((uint32_t)O.nh << 16) / (uint32_t)C.gtile_rows;
   C.smem = cells_smem(C.tile_rows, TH);
   C.slots_per_cta = ((int)C.roles.size() + C.grid - 1) / C.grid + 1;
   C.gslots_per_cta = 0;
@@ -266,18 +277,18 @@ int pgb_plan_cells(pgb_model* M) {
     C.grole_prefix.assign(nr + 1, 0);
     for (int r = 0; r < nr; ++r) {
       const DGenPair& P = C.gpairs[C.groles[r].pair];
-      const int w = 3 + (int)std::min<int64_t>(60, ((int64_t)C.tile_rows + P.ncells - 1) / P.ncells);
+      const int w = 3 + (int)std::min<int64_t>(250, ((int64_t)C.gtile_rows + P.ncells - 1) / P.ncells);
       C.grole_prefix[r + 1] = C.grole_prefix[r] + w;
     }
     const int64_t W = C.grole_prefix[nr];
-    C.gcta_role_lo.assign(C.grid, 0);
-    for (int r = 0; r < nr; ++r) { C.groles[r].c_lo = C.grid; C.groles[r].c_hi = -1; }
-    for (int c = 0, r0 = 0; c < C.grid; ++c) {
+    C.gcta_role_lo.assign(C.ggrid, 0);
+    for (int r = 0; r < nr; ++r) { C.groles[r].c_lo = C.ggrid; C.groles[r].c_hi = -1; }
+    for (int c = 0, r0 = 0; c < C.ggrid; ++c) {
       // CTA c covers [W c / grid, W (c + 1) / grid) of the weight axis; role r covers [prefix[r], prefix[r + 1])
-      while (r0 < nr - 1 && (int64_t)C.grole_prefix[r0 + 1] * C.grid <= W * c) ++r0;
+      while (r0 < nr - 1 && (int64_t)C.grole_prefix[r0 + 1] * C.ggrid <= W * c) ++r0;
       C.gcta_role_lo[c] = r0;
       int cnt = 0;
-      for (int r = r0; r < nr && (int64_t)C.grole_prefix[r] * C.grid < W * (c + 1); ++r) {
+      for (int r = r0; r < nr && (int64_t)C.grole_prefix[r] * C.ggrid < W * (c + 1); ++r) {
         C.groles[r].c_lo = std::min(C.groles[r].c_lo, c);
         C.groles[r].c_hi = std::max(C.groles[r].c_hi, c);
         ++cnt;
@@ -286,6 +297,7 @@ int pgb_plan_cells(pgb_model* M) {
     }
   }
   C.slot_doubles = (int64_t)kCellAcc * TH;
+  C.gslot_doubles = (int64_t)kGenAcc * kGenSumThreads;
   for (int r = 0; r < (int)C.roles.size(); ++r) role_cta_range((int64_t)C.roles.size(), C.grid, r, C.roles[r].c_lo, C.roles[r].c_hi);
   // coefficient -> (term, local index) for the assembly
   C.coef_term.assign(M->m, -1);
@@ -420,16 +432,17 @@ int pgb_cells_coverage_errors(const pgb_model* M) {
 static int64_t rows_pad(int64_t n) { return (n + 15) & ~(int64_t)15; }
 extern "C" int64_t pgb_cells_ws_bytes(const pgb_model* M, int64_t n, int with_order) {
   const pgb_model::Cells& C = M->cells;
-  const int64_t slots = (int64_t)C.grid * (C.slots_per_cta + C.gslots_per_cta);
+  const int64_t slot_all = ((int64_t)C.grid * C.slots_per_cta * C.slot_doubles + (int64_t)C.ggrid * C.gslots_per_cta * C.gslot_doubles);
   const int64_t np = rows_pad(n);
   const int64_t ntl = (n + C.tile_rows - 1) / C.tile_rows;
+  const int64_t gntl = C.mixed ? (n + C.gtile_rows - 1) / C.gtile_rows : 0;
   // sorted rows + cell starts (pgb_gram_prepare); not needed by passes that sort inside the kernel.  A model with
   // generic pairs always sorts into the workspace (its streaming pass runs the sort kernels first)
   int64_t order = 0;
   if (with_order || C.mixed)
-    order = ((int64_t)C.roles.size() * ntl * (C.tile_rows + C.threads + 8) + (int64_t)C.gorders.size() * ntl * C.tile_rows +
-             C.gstarts_u16 * ntl) * 2 + 512;
-  return (slots * C.slot_doubles + C.sum_doubles + C.gsum_doubles + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2) + 8 + (2 + C.ncol) * np) * 8 +
+    order = ((int64_t)C.roles.size() * ntl * (C.tile_rows + C.threads + 8) + (int64_t)C.gorders.size() * gntl * C.gtile_rows +
+             C.gstarts_u16 * gntl) * 2 + 512;
+  return (slot_all + C.sum_doubles + C.gsum_doubles + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2) + 8 + (2 + C.ncol) * np) * 8 +
          (int64_t)C.ncol * np + order + 2048;
 }
 
@@ -1314,26 +1327,15 @@ __device__ __forceinline__ double gen_pow(int nint, double s, int e) {
   return x * y;
 }
 
-// One row of a generic pair: NOUT outer cubic factors (exponents e0, e1 of this thread's slice), NIN inner ones
-// (2: acc[4 p + q], 1: acc[q], 0: acc[0]), NVAL value factors.  v[] = the row's record coordinates in the order
-// (values, outer 0, outer 1, inner a, inner b).
-template <int NOUT, int NIN, int NVAL, bool CAREFUL>
-__device__ __forceinline__ void gen_row(double mult, const double* v, const int* nint, int e0, int e1, double (&acc)[16]) {
-#pragma unroll
-  for (int q = 0; q < NVAL; ++q) mult *= v[q];
-  if (NOUT >= 1) mult *= gen_pow<CAREFUL>(nint[0], v[NVAL], e0);
-  if (NOUT >= 2) mult *= gen_pow<CAREFUL>(nint[1], v[NVAL + 1], e1);
+// inner block of a row: acc[4 p + q] += (mult a_p) b_q (NIN = 2), acc[q] += mult b_q (NIN = 1), acc[0] += mult
+template <int NIN, bool CAREFUL>
+__device__ __forceinline__ void gen_inner(double mult, const double (&a)[4], const double (&b)[4], double* acc) {
   if (NIN == 0) {
     acc[0] += mult;
   } else if (NIN == 1) {
-    double b[4];
-    gen_pw<CAREFUL>(nint[3], v[NVAL + NOUT], b);
     if (CAREFUL) acc[0] = fma(mult, b[0], acc[0]); else acc[0] += mult;
     acc[1] = fma(mult, b[1], acc[1]); acc[2] = fma(mult, b[2], acc[2]); acc[3] = fma(mult, b[3], acc[3]);
   } else {
-    double a[4], b[4];
-    gen_pw<CAREFUL>(nint[2], v[NVAL + NOUT], a);
-    gen_pw<CAREFUL>(nint[3], v[NVAL + NOUT + 1], b);
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const double u = (p == 0 && !CAREFUL) ? mult : mult * a[p];
@@ -1345,11 +1347,32 @@ __device__ __forceinline__ void gen_row(double mult, const double* v, const int*
   }
 }
 
+// One row of a generic pair: NOUT outer cubic factors, NIN inner ones, NVAL value factors.  With outer factors the
+// thread covers all four exponents of the first one (sums acc[16 j + ..] for exponent j) and the exponent e1 of its
+// slice of the second.  v[] = the row's record coordinates in the order (values, outer 0, outer 1, inner a, inner b).
+template <int NOUT, int NIN, int NVAL, bool CAREFUL>
+__device__ __forceinline__ void gen_row(double mult, const double* v, const int* nint, int e1, double (&acc)[kGenAcc]) {
+#pragma unroll
+  for (int q = 0; q < NVAL; ++q) mult *= v[q];
+  if (NOUT >= 2) mult *= gen_pow<CAREFUL>(nint[1], v[NVAL + 1], e1);
+  double a[4] = {1.0, 0.0, 0.0, 0.0}, b[4] = {1.0, 0.0, 0.0, 0.0};
+  if (NIN == 2) gen_pw<CAREFUL>(nint[2], v[NVAL + NOUT], a);
+  if (NIN >= 1) gen_pw<CAREFUL>(nint[3], v[NVAL + NOUT + NIN - 1], b);
+  if (NOUT == 0) {
+    gen_inner<NIN, CAREFUL>(mult, a, b, acc);
+  } else {
+    double o[4];
+    gen_pw<CAREFUL>(nint[0], v[NVAL], o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gen_inner<NIN, CAREFUL>((j == 0 && !CAREFUL) ? mult : mult * o[j], a, b, acc + 16 * j);
+  }
+}
+
 // the rows s0 .. s1 - 1 of a cell in the stored order, two rows in flight: the gathers of a pair of rows are issued
 // together, the row indices of the next pair are fetched one step ahead
 template <int NOUT, int NIN, int NVAL, bool CAREFUL>
 __device__ __forceinline__ void gen_rows(const uint16_t* __restrict__ pg, int s0, int s1, const double* __restrict__ wcol,
-                                         const double* const* cols, const int* nint, int e0, int e1, double (&acc)[16]) {
+                                         const double* const* cols, const int* nint, int e1, double (&acc)[kGenAcc]) {
   constexpr int NC = NVAL + NOUT + NIN;
   int r0 = pg[s0], r1 = (s0 + 1 < s1) ? pg[s0 + 1] : 0;
   for (int s = s0; s < s1; s += 2) {
@@ -1365,8 +1388,8 @@ __device__ __forceinline__ void gen_rows(const uint16_t* __restrict__ pg, int s0
       va[q] = __ldg(cols[q] + ra);
       vb[q] = two ? __ldg(cols[q] + rb) : 0.0;
     }
-    gen_row<NOUT, NIN, NVAL, CAREFUL>(wa, va, nint, e0, e1, acc);
-    if (two) gen_row<NOUT, NIN, NVAL, CAREFUL>(wb, vb, nint, e0, e1, acc);
+    gen_row<NOUT, NIN, NVAL, CAREFUL>(wa, va, nint, e1, acc);
+    if (two) gen_row<NOUT, NIN, NVAL, CAREFUL>(wb, vb, nint, e1, acc);
   }
 }
 
@@ -1374,14 +1397,14 @@ __device__ __forceinline__ void gen_rows(const uint16_t* __restrict__ pg, int s0
 // their record coordinates straight from the (L2-resident) band -- a role touches only the few rows of its own
 // cells, so nothing is staged in shared memory; the lanes of a cell's slices read the same addresses.  Same
 // partial slots and reproducible order as the spline kernels.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 320 ? 2 : 1))
+__global__ void __launch_bounds__(kGenSumThreads, kGenOcc)
 gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, const double* __restrict__ omz,
                           const double* __restrict__ tq, const DGenRole* __restrict__ roles,
                           const DGenPair* __restrict__ pairs, int n_roles, const int32_t* __restrict__ role_prefix,
                           const int32_t* __restrict__ cta_role_lo, int TR, int band_tiles, int slots_per_cta,
                           double* __restrict__ part, const uint16_t* __restrict__ perm_g,
                           const uint16_t* __restrict__ starts_g, int64_t ntl) {
+  constexpr int THREADS = kGenSumThreads;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* s_pre = reinterpret_cast<int32_t*>(smem_raw);
   __shared__ DGenPair P;
@@ -1390,13 +1413,13 @@ gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, 
   for (int i = tid; i <= n_roles; i += THREADS) s_pre[i] = role_prefix[i];
   __syncthreads();
   const int role_lo = cta_role_lo[blockIdx.x];
-  double* my_part = part + (int64_t)blockIdx.x * slots_per_cta * (kCellAcc * THREADS);
+  double* my_part = part + (int64_t)blockIdx.x * slots_per_cta * (kGenAcc * THREADS);
   int cur_role = -1;
-  double acc[16];
+  double acc[kGenAcc];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  for (int e = 0; e < kGenAcc; ++e) acc[e] = 0.0;
   // per role: this thread's cell and slice, the columns it gathers
-  int k = 0, e0 = 0, e1 = 0, shape = 0;
+  int k = 0, e1 = 0, shape = 0;
   int nint[4] = {1, 1, 1, 1};
   const double* cbase[6] = {tq, tq, tq, tq, tq, tq};
   WUnitIter it;
@@ -1406,13 +1429,13 @@ gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, 
     const int64_t tile = it.tile();
     if (role != cur_role) {
       if (cur_role >= 0) {
-        double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * THREADS);
+        double* dst = my_part + (int64_t)(cur_role - role_lo) * (kGenAcc * THREADS);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) dst[e * THREADS + tid] = acc[e];
+        for (int e = 0; e < kGenAcc; ++e) dst[e * THREADS + tid] = acc[e];
       }
-      const double* src = my_part + (int64_t)(role - role_lo) * (kCellAcc * THREADS);
+      const double* src = my_part + (int64_t)(role - role_lo) * (kGenAcc * THREADS);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) acc[e] = src[e * THREADS + tid];
+      for (int e = 0; e < kGenAcc; ++e) acc[e] = src[e * THREADS + tid];
       __syncthreads();
       if (tid == 0) {
         R = roles[role];
@@ -1420,11 +1443,9 @@ gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, 
       }
       __syncthreads();
       cur_role = role;
-      const int nsl = P.nsl;
-      k = tid / nsl;
-      const int sg = tid - k * nsl;
-      e0 = sg & 3;
-      e1 = (sg >> 2) & 3;
+      const int nslt = P.nslt;
+      k = tid / nslt;
+      e1 = tid - k * nslt;
       const int nout = (P.out0 >= 0) + (P.out1 >= 0), nin = (P.in_b >= 0) + (P.in_a >= 0);
       shape = nout * 9 + nin * 3 + P.nval;
       int q = 0;
@@ -1448,8 +1469,8 @@ gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, 
     for (int q = 0; q < 6; ++q) cols[q] = cbase[q] + row0;
 #define PGB_GEN_CASE(NOUT, NIN, NVAL)                                                                             \
   case (NOUT) * 9 + (NIN) * 3 + (NVAL):                                                                           \
-    if (!careful) gen_rows<NOUT, NIN, NVAL, false>(pg, s0, s1, wcol, cols, nint, e0, e1, acc);                    \
-    else gen_rows<NOUT, NIN, NVAL, true>(pg, s0, s1, wcol, cols, nint, e0, e1, acc);                              \
+    if (!careful) gen_rows<NOUT, NIN, NVAL, false>(pg, s0, s1, wcol, cols, nint, e1, acc);                        \
+    else gen_rows<NOUT, NIN, NVAL, true>(pg, s0, s1, wcol, cols, nint, e1, acc);                                  \
     break;
     switch (shape) {
       PGB_GEN_CASE(1, 2, 0)  // s() x te()
@@ -1466,9 +1487,9 @@ gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, 
 #undef PGB_GEN_CASE
   }
   if (cur_role >= 0) {
-    double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * THREADS);
+    double* dst = my_part + (int64_t)(cur_role - role_lo) * (kGenAcc * THREADS);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) dst[e * THREADS + tid] = acc[e];
+    for (int e = 0; e < kGenAcc; ++e) dst[e * THREADS + tid] = acc[e];
   }
 }
 
@@ -1476,20 +1497,21 @@ gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, 
 // sum index of the thread + n_acc * slice
 __global__ void cells_generic_reduce_kernel(const double* __restrict__ part, const DGenRole* __restrict__ roles,
                                             const DGenPair* __restrict__ pairs, const int32_t* __restrict__ cta_role_lo,
-                                            int slots_per_cta, int threads, double* __restrict__ sums) {
+                                            int slots_per_cta, double* __restrict__ sums) {
   const int role = blockIdx.x, tid = threadIdx.x, e = blockIdx.y;
   const DGenRole R = roles[role];
   const DGenPair& P = pairs[R.pair];
-  const int nsl = P.nsl, n_acc = P.n_acc;
-  const int k = tid / nsl, sg = tid - k * nsl;
-  if (k >= R.ncl || e >= n_acc) return;
+  const int nslt = P.nslt, nthr = P.n_acc * P.ne;  // sums per thread
+  const int k = tid / nslt, sg = tid - k * nslt;
+  if (k >= R.ncl || e >= nthr) return;
+  // thread sum e = inner index + 16 j (j: exponent of the first outer factor; 16 = n_acc whenever ne == 4)
   double v = 0.0;
   for (int c = R.c_lo; c <= R.c_hi; ++c) {
     const int slot = role - cta_role_lo[c];
     if (slot < 0 || slot >= slots_per_cta) continue;
-    v += part[((int64_t)c * slots_per_cta + slot) * (kCellAcc * threads) + e * threads + tid];
+    v += part[((int64_t)c * slots_per_cta + slot) * (kGenAcc * kGenSumThreads) + e * kGenSumThreads + tid];
   }
-  sums[P.sum_off + (int64_t)(e + n_acc * sg) * P.ncells + R.key0 + k] = v;
+  sums[P.sum_off + (int64_t)(e + nthr * sg) * P.ncells + R.key0 + k] = v;
 }
 
 // change of basis of the generic sums along moment axis `axis`: one thread per line of four sums
@@ -1586,15 +1608,16 @@ struct CellWs {
   double *part, *gpart, *sums, *scal_part, *extra, *om, *omz, *tq;
   uint8_t* cq;
   uint16_t *perm, *starts, *gperm, *gstarts;
-  int64_t np, ntl;
+  int64_t np, ntl, gntl;
 };
 static bool cells_ws_layout(const pgb_model* M, int64_t n, void* ws, int64_t ws_bytes, bool with_order, CellWs& L) {
   const pgb_model::Cells& C = M->cells;
   L.np = rows_pad(n);
   L.ntl = (n + C.tile_rows - 1) / C.tile_rows;
+  L.gntl = C.mixed ? (n + C.gtile_rows - 1) / C.gtile_rows : 0;
   L.part = (double*)ws;
   L.gpart = L.part + (int64_t)C.grid * C.slots_per_cta * C.slot_doubles;
-  L.sums = L.gpart + (int64_t)C.grid * C.gslots_per_cta * C.slot_doubles;
+  L.sums = L.gpart + (int64_t)C.ggrid * C.gslots_per_cta * C.gslot_doubles;
   L.scal_part = L.sums + C.sum_doubles + C.gsum_doubles;
   L.extra = L.scal_part + (int64_t)kSMs * 8 * (PGB_GS_COUNT + 2);
   L.om = (double*)(((uintptr_t)(L.extra + 8) + 127) & ~(uintptr_t)127);
@@ -1604,8 +1627,8 @@ static bool cells_ws_layout(const pgb_model* M, int64_t n, void* ws, int64_t ws_
   L.perm = (uint16_t*)(((uintptr_t)(L.cq + (int64_t)C.ncol * L.np) + 127) & ~(uintptr_t)127);
   L.starts = L.perm + (int64_t)C.roles.size() * L.ntl * C.tile_rows;
   L.gperm = (uint16_t*)(((uintptr_t)(L.starts + (int64_t)C.roles.size() * L.ntl * (C.threads + 8)) + 127) & ~(uintptr_t)127);
-  L.gstarts = L.gperm + (int64_t)C.gorders.size() * L.ntl * C.tile_rows;
-  const uint8_t* end = (with_order || C.mixed) ? (const uint8_t*)(L.gstarts + C.gstarts_u16 * L.ntl) : (const uint8_t*)L.perm;
+  L.gstarts = L.gperm + (int64_t)C.gorders.size() * L.gntl * C.gtile_rows;
+  const uint8_t* end = (with_order || C.mixed) ? (const uint8_t*)(L.gstarts + C.gstarts_u16 * L.gntl) : (const uint8_t*)L.perm;
   return (int64_t)(end - (const uint8_t*)ws) <= ws_bytes;
 }
 
@@ -1656,12 +1679,12 @@ static int cells_emit_order(const pgb_model* M, int64_t n, const CellWs& L, cuda
     pgb_count_launch(1);
   }
   if (!C.gorders.empty()) {
-    const int smem = 4 * TR + 8 * kGenChunk;
+    const int smem = 4 * C.gtile_rows + 8 * kGenChunk;
     int rc = cells_set_smem_attr((const void*)gram_cells_order_kernel, smem);
     if (rc != PGB_OK) return rc;
-    const int64_t units = L.ntl * (int64_t)C.gorders.size();
+    const int64_t units = L.gntl * (int64_t)C.gorders.size();
     gram_cells_order_kernel<<<(unsigned)std::min<int64_t>(units, (int64_t)kSMs * 4), kGenThreads, smem, st>>>(
-        n, L.np, L.cq, C.d_gorders, (int)C.gorders.size(), TR, L.ntl, L.gperm, L.gstarts);
+        n, L.np, L.cq, C.d_gorders, (int)C.gorders.size(), C.gtile_rows, L.gntl, L.gperm, L.gstarts);
     PGB_CUDA(cudaGetLastError());
     pgb_count_launch(1);
   }
@@ -1734,7 +1757,7 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
     rc = cells_emit_order(M, n, L, st);
     if (rc != PGB_OK) return rc;
   }
-  PGB_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * (int64_t)C.grid * (C.slots_per_cta + C.gslots_per_cta) * C.slot_doubles, st));
+  PGB_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * ((int64_t)C.grid * C.slots_per_cta * C.slot_doubles + (int64_t)C.ggrid * C.gslots_per_cta * C.gslot_doubles), st));
   if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[3], st));
   const int TR = C.tile_rows, band_tiles = cells_band_tiles(M);
   const bool sorted = planned || C.mixed;
@@ -1758,13 +1781,13 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
       gram_cells_kernel<TH, OCC, false><<<C.grid, TH, C.smem, st>>>(n, np, om, omz, tq, cq, C.d_roles, n_roles, TR,      \
                                                                     band_tiles, C.slots_per_cta, part, nullptr, nullptr); \
     }                                                                                                                    \
-    if (n_groles > 0)                                                                                                    \
-      gram_cells_generic_kernel<TH><<<C.grid, TH, (size_t)(n_groles + 1) * 4, st>>>(                                   \
-          n, np, om, omz, tq, C.d_groles, C.d_gpairs, n_groles, C.d_grole_prefix, C.d_gcta_role_lo, TR, band_tiles,    \
-          C.gslots_per_cta, L.gpart, L.gperm, L.gstarts, L.ntl);                                                       \
   } while (0)
   PGB_CELLS_DISPATCH(PGB_CELLS_LAUNCH)
 #undef PGB_CELLS_LAUNCH
+  if (n_groles > 0)
+    gram_cells_generic_kernel<<<C.ggrid, kGenSumThreads, (size_t)(n_groles + 1) * 4, st>>>(
+        n, np, om, omz, tq, C.d_groles, C.d_gpairs, n_groles, C.d_grole_prefix, C.d_gcta_role_lo, C.gtile_rows,
+        std::max(1, (int)((int64_t)band_tiles * TR / C.gtile_rows)), C.gslots_per_cta, L.gpart, L.gperm, L.gstarts, L.gntl);
   PGB_CUDA(cudaGetLastError());
   if (tm.enabled) PGB_CUDA(cudaEventRecord(tm.chunk_ev[4], st));
   int launches = 3;
@@ -1777,8 +1800,8 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
     launches += 3;
   }
   if (n_groles > 0) {
-    cells_generic_reduce_kernel<<<dim3(n_groles, 16), C.threads, 0, st>>>(L.gpart, C.d_groles, C.d_gpairs, C.d_gcta_role_lo,
-                                                                        C.gslots_per_cta, C.threads, sums);
+    cells_generic_reduce_kernel<<<dim3(n_groles, kGenAcc), kGenSumThreads, 0, st>>>(L.gpart, C.d_groles, C.d_gpairs, C.d_gcta_role_lo,
+                                                                                   C.gslots_per_cta, sums);
     int64_t max_lines = 1;
     int max_ax = 0;
     for (const DGenPair& P : C.gpairs) {

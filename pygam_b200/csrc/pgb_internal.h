@@ -133,7 +133,8 @@ struct DGenPair {
   int32_t f_n[4];                     // cubic: knot intervals; level: coefficients
   int32_t f_nspl[4], f_stride[4];     // coefficient index of the factor = (local index / stride) % nspl
   int32_t f_key[4], f_ax[4];          // key dimension / moment axis of the factor (-1: none)
-  int32_t n_ax, n_acc, nsl, nprod;    // axes; sums per thread (1, 4, 16); slices (1, 4, 16); nprod = n_acc * nsl
+  int32_t n_ax, n_acc, nsl, nprod;    // axes; sums of the inner factors (1, 4, 16); outer exponent combinations (1, 4, 16); nprod = n_acc * nsl
+  int32_t ne, nslt;                   // exponents of the first outer factor a thread covers (1 or 4: n_acc * ne sums per thread); thread slices = nsl / ne
   int32_t in_a, in_b, out0, out1;     // factor occurrences of the inner / outer cubic factors (-1: none)
   int32_t nval, val_col[2];           // value factors multiplied into the weight
   int32_t wz;                         // weight column: omega z (rhs) instead of omega
@@ -142,7 +143,7 @@ struct DGenPair {
   int64_t sum_off, starts_off;
 };
 struct DGenRole {
-  int32_t pair, key0, ncl;            // cells key0 .. key0 + ncl - 1 of the pair; thread = (cell - key0) * nsl + slice
+  int32_t pair, key0, ncl;            // cells key0 .. key0 + ncl - 1 of the pair; thread = (cell - key0) * nslt + slice
   int32_t c_lo, c_hi, pad;
 };
 
@@ -171,10 +172,12 @@ struct pgb_model {
     int32_t* d_gcta_role_lo = nullptr;
     int32_t tile_rows = 0, grid = 0, slots_per_cta = 0, icpt_coef = -1, n_spl = 0, occ = 1, threads = 512;
     int32_t ncol = 0;                  // record columns (one per factor)
-    int32_t gslots_per_cta = 0;
+    int32_t gslots_per_cta = 0, ggrid = 0;  // partial slots per CTA and grid of the generic kernel
+    int32_t gtile_rows = 0;                 // rows per tile of the generic orders (16-bit row indices: < 65536)
     size_t smem = 0;
     int64_t sum_doubles = 0, slot_doubles = 0;
     int64_t gsum_doubles = 0, gstarts_u16 = 0;  // generic sums; starts of all orders per tile
+    int64_t gslot_doubles = 0;                   // partial slot of a generic role: kGenAcc sums x kGenSumThreads threads
   } cells;
   std::vector<pgb_term> terms;
   std::vector<DTerm> dterms;

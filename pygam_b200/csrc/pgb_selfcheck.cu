@@ -74,7 +74,7 @@ extern "C" int pgb_selfcheck_cells_gram(const pgb_term* terms, int32_t n_terms, 
   for (const DGenPair& P : C.gpairs) {
     const DGenOrder& O = C.gorders[P.order];
     for (int64_t i = 0; i < n; ++i) {
-      const uint32_t key = gen_key(O, (int)(i % TR), [&](int c) { return (uint32_t)cq[(size_t)c * n + i]; });
+      const uint32_t key = gen_key(O, (int)(i % C.gtile_rows), [&](int c) { return (uint32_t)cq[(size_t)c * n + i]; });
       if ((key & 0xffffu) == 0xffffu) continue;
       if ((int)key >= P.ncells) { delete M; return PGB_EINVAL; }
       for (int sg = 0; sg < P.nsl; ++sg) {
