@@ -231,6 +231,17 @@ int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r, int32_t s
               const double* beta_prev, int32_t share_prev, int32_t flags, double* out,
               double* cov_out, void* ws, int64_t ws_bytes, void* stream);
 
+/* Rank-limited solve for fewer kept rows than coefficients: the reference crops its SVD of [R; E] to the leading
+ * rank = min(m, n, rows kept by GAM._mask) singular triplets (pygam.py:789-799; pygam/tests/test_GAM_methods.py:93-107).
+ * With A = G + EtE + EtE_null = V D^2 V^T (symmetric Jacobi eigen-decomposition on the device) this is
+ * beta = V_k D_k^-2 V_k^T r over the k = rank largest eigenvalues, edof = tr(D_k^-1 V_k^T G V_k D_k^-1) and
+ * cov = V_k D_k^-2 (V_k^T G V_k) D_k^-2 V_k^T.  EtE, EtE_null: the penalty in the ORIGINAL basis (EtE_null may be
+ * NULL).  out, cov_out, flags (PGB_SOLVE_COV) as pgb_solve; ws: pgb_solve_truncated_ws_bytes(m). */
+int64_t pgb_solve_truncated_ws_bytes(int32_t m);
+int pgb_solve_truncated(int32_t m, int32_t rank, const double* G, const double* r, const double* EtE,
+                        const double* EtE_null, const double* beta_prev, int32_t flags, double* out,
+                        double* cov_out, void* ws, int64_t ws_bytes, void* stream);
+
 /* Cholesky test of S + P (+ C) alone: GAM._cholesky (pygam.py:499-537, utils.py:30-91).
  * info_out (device int32): 0 = positive definite. */
 int64_t pgb_chol_ws_bytes(int32_t m);

@@ -717,6 +717,207 @@ chol_check_kernel(int m, const double* __restrict__ Ain, int* __restrict__ info,
   if (threadIdx.x == 0) *info = *flag;
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Rank-limited solve: fewer kept rows than coefficients.
+// The reference crops its SVD of [R; E] to the leading min(m, n, rows kept by the mask) singular triplets
+// (pygam.py:789-799, exercised by pygam/tests/test_GAM_methods.py:93-107): with A = G + E^T E = V D^2 V^T that is
+//   beta = V_k D_k^-2 V_k^T r,   edof = tr(D_k^-1 V_k^T G V_k D_k^-1),   cov = V_k D_k^-2 (V_k^T G V_k) D_k^-2 V_k^T
+// over the k largest eigenvalues.  One CTA: two-sided cyclic Jacobi on A in global memory (round-robin pairs: the
+// m / 2 rotations of a step touch disjoint rows and columns and are applied together), then the three formulas.
+// m is small whenever this is needed (there are fewer rows than coefficients).
+// ----------------------------------------------------------------------------------------
+static const int kEigThreads = 512;
+__global__ void __launch_bounds__(kEigThreads)
+solve_truncated_kernel(int m, int rank, const double* __restrict__ G, const double* __restrict__ r,
+                       const double* __restrict__ EtE, const double* __restrict__ EtE2, const double* __restrict__ beta_prev,
+                       double* __restrict__ out, double* __restrict__ cov_out, double* __restrict__ ws, int want_cov) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int me = (m + 1) & ~1;        // players of the round-robin (one dummy when m is odd)
+  const int np2 = me / 2;
+  double* cs = sm;                    // [np2][2] rotation of every pair of the step
+  int* pq = reinterpret_cast<int*>(cs + 2 * np2);   // [np2][2]
+  double* lam = reinterpret_cast<double*>(pq + 2 * np2 + (2 * np2 & 1 ? 1 : 0));  // [m]
+  double* vr = lam + m;               // [m] V^T r / lambda
+  int* rk = reinterpret_cast<int*>(vr + m);  // [m] rank of eigenvalue i in descending order
+  double* red = reinterpret_cast<double*>(rk + m + (m & 1));  // [64]
+  double* A = ws;                     // m x m
+  double* V = A + (size_t)m * m;      // m x m, columns = eigenvectors
+  double* M = V + (size_t)m * m;      // m x m scratch
+  __shared__ int s_flag;
+  int bad = 0;
+  for (int e = tid; e < m * m; e += T) {
+    const int i = e / m, j = e - i * m;
+    const double a = G[e] + EtE[e] + (EtE2 ? EtE2[e] : 0.0);
+    if (!isfinite(a)) bad = 1;
+    A[e] = a;
+    V[e] = (i == j) ? 1.0 : 0.0;
+  }
+  if (tid == 0) s_flag = 0;
+  __syncthreads();
+  if (bad) s_flag = 2;
+  __syncthreads();
+  // symmetrise (G is symmetric by construction; the penalty is assembled on the host)
+  for (int e = tid; e < m * m; e += T) {
+    const int i = e / m, j = e - i * m;
+    if (i < j) { const double a = 0.5 * (A[e] + A[j * m + i]); A[e] = a; A[j * m + i] = a; }
+  }
+  __syncthreads();
+  for (int sweep = 0; sweep < 40 && s_flag == 0; ++sweep) {
+    // convergence: off-diagonal mass against the diagonal
+    double off = 0.0, dg = 0.0;
+    for (int e = tid; e < m * m; e += T) {
+      const int i = e / m, j = e - i * m;
+      const double a = A[e];
+      if (i == j) dg += a * a; else off += a * a;
+    }
+    for (int o = 16; o > 0; o >>= 1) { off += __shfl_down_sync(0xffffffffu, off, o); dg += __shfl_down_sync(0xffffffffu, dg, o); }
+    if ((tid & 31) == 0) { red[tid >> 5] = off; red[32 + (tid >> 5)] = dg; }
+    __syncthreads();
+    if (tid == 0) {
+      double so = 0.0, sd = 0.0;
+      for (int w = 0; w < T / 32; ++w) { so += red[w]; sd += red[32 + w]; }
+      if (so <= 1e-30 * sd) s_flag = -1;  // converged
+    }
+    __syncthreads();
+    if (s_flag != 0) break;
+    for (int step = 0; step < me - 1; ++step) {
+      // pairs of this step: player me - 1 stays, the others rotate
+      for (int k = tid; k < np2; k += T) {
+        int p = (k == 0) ? me - 1 : (step + k) % (me - 1);
+        int q = (k == 0) ? step : (step - k + (me - 1)) % (me - 1);
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, sn = 0.0;
+        if (q < m) {
+          const double apq = A[p * m + q];
+          if (apq != 0.0) {
+            const double tau = (A[q * m + q] - A[p * m + p]) / (2.0 * apq);
+            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t * t);
+            sn = t * c;
+          }
+        } else {
+          p = -1;
+        }
+        cs[2 * k] = c; cs[2 * k + 1] = sn;
+        pq[2 * k] = p; pq[2 * k + 1] = q;
+      }
+      __syncthreads();
+      // columns: A <- A J, V <- V J
+      for (int e = tid; e < np2 * m; e += T) {
+        const int k = e / m, i = e - k * m;
+        const int p = pq[2 * k], q = pq[2 * k + 1];
+        if (p < 0) continue;
+        const double c = cs[2 * k], sn = cs[2 * k + 1];
+        const double aip = A[i * m + p], aiq = A[i * m + q];
+        A[i * m + p] = c * aip - sn * aiq;
+        A[i * m + q] = sn * aip + c * aiq;
+        const double vip = V[i * m + p], viq = V[i * m + q];
+        V[i * m + p] = c * vip - sn * viq;
+        V[i * m + q] = sn * vip + c * viq;
+      }
+      __syncthreads();
+      // rows: A <- J^T A
+      for (int e = tid; e < np2 * m; e += T) {
+        const int k = e / m, j = e - k * m;
+        const int p = pq[2 * k], q = pq[2 * k + 1];
+        if (p < 0) continue;
+        const double c = cs[2 * k], sn = cs[2 * k + 1];
+        const double apj = A[p * m + j], aqj = A[q * m + j];
+        A[p * m + j] = c * apj - sn * aqj;
+        A[q * m + j] = sn * apj + c * aqj;
+      }
+      __syncthreads();
+    }
+  }
+  const int info = (s_flag == 2) ? 2 : 0;
+  // eigenvalues, their order, V^T r / lambda
+  for (int i = tid; i < m; i += T) lam[i] = A[i * m + i];
+  __syncthreads();
+  for (int i = tid; i < m; i += T) {
+    int rnk = 0;
+    for (int j = 0; j < m; ++j) rnk += (lam[j] > lam[i]) || (lam[j] == lam[i] && j < i);
+    rk[i] = rnk;
+    double d = 0.0;
+    for (int j = 0; j < m; ++j) d += V[j * m + i] * r[j];
+    vr[i] = (rnk < rank && lam[i] > 0.0) ? d / lam[i] : 0.0;
+  }
+  __syncthreads();
+  // beta = V_k (V_k^T r / lambda_k)
+  for (int i = tid; i < m; i += T) {
+    double b = 0.0;
+    for (int j = 0; j < m; ++j) b += V[i * m + j] * vr[j];
+    out[i] = b;
+  }
+  // M = G V (columns of kept eigenvectors only), then W = V^T M scaled by 1 / (lambda_i lambda_j) into A
+  for (int e = tid; e < m * m; e += T) {
+    const int i = e / m, j = e - i * m;
+    double a = 0.0;
+    if (rk[j] < rank)
+      for (int l = 0; l < m; ++l) a += G[i * m + l] * V[l * m + j];
+    M[e] = a;
+  }
+  __syncthreads();
+  for (int e = tid; e < m * m; e += T) {
+    const int i = e / m, j = e - i * m;
+    double a = 0.0;
+    if (rk[i] < rank && rk[j] < rank && lam[i] > 0.0 && lam[j] > 0.0) {
+      for (int l = 0; l < m; ++l) a += V[l * m + i] * M[l * m + j];
+      a /= lam[i] * lam[j];
+    }
+    A[e] = a;  // Lambda^-1 V^T G V Lambda^-1 on the kept block
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double edof = 0.0, nb2 = 0.0, nd2 = 0.0;
+    for (int i = 0; i < m; ++i) {
+      if (rk[i] < rank) edof += A[i * m + i] * lam[i];  // v^T G v / lambda
+      nb2 += out[i] * out[i];
+      if (beta_prev) { const double d = beta_prev[i] - out[i]; nd2 += d * d; }
+    }
+    out[m] = edof;
+    out[m + 1] = beta_prev ? sqrt(nd2) / sqrt(nb2) : 0.0;
+    out[m + 2] = (double)info;
+    out[m + 3] = 0.0;
+    out[m + 4] = sqrt(nb2);
+  }
+  if (want_cov) {
+    // cov = V (Lambda^-1 V^T G V Lambda^-1) V^T: M = V A, cov = M V^T
+    for (int e = tid; e < m * m; e += T) {
+      const int i = e / m, j = e - i * m;
+      double a = 0.0;
+      for (int l = 0; l < m; ++l) a += V[i * m + l] * A[l * m + j];
+      M[e] = a;
+    }
+    __syncthreads();
+    for (int e = tid; e < m * m; e += T) {
+      const int i = e / m, j = e - i * m;
+      double a = 0.0;
+      for (int l = 0; l < m; ++l) a += M[i * m + l] * V[j * m + l];
+      cov_out[e] = a;
+    }
+  }
+}
+
+extern "C" int64_t pgb_solve_truncated_ws_bytes(int32_t m) { return (int64_t)3 * m * m * 8 + 256; }
+
+extern "C" int pgb_solve_truncated(int32_t m, int32_t rank, const double* G, const double* r, const double* EtE,
+                                   const double* EtE_null, const double* beta_prev, int32_t flags, double* out,
+                                   double* cov_out, void* ws, int64_t ws_bytes, void* stream) {
+  if (m < 1 || rank < 1 || rank > m || !G || !r || !EtE || !out || !ws || ws_bytes < pgb_solve_truncated_ws_bytes(m) ||
+      ((flags & PGB_SOLVE_COV) && !cov_out)) {
+    pgb_set_error("pgb_solve_truncated: bad arguments");
+    return PGB_EINVAL;
+  }
+  const size_t smem = ((size_t)(m + 2) * 2 + 2 * m + 64 + 8) * 8 + (size_t)(3 * m + 8) * 4;
+  solve_truncated_kernel<<<1, kEigThreads, smem, (cudaStream_t)stream>>>(m, rank, G, r, EtE, EtE_null, beta_prev, out, cov_out,
+                                                                        (double*)ws, (flags & PGB_SOLVE_COV) ? 1 : 0);
+  pgb_count_launch(1);
+  PGB_CUDA(cudaGetLastError());
+  return PGB_OK;
+}
+
 extern "C" int64_t pgb_chol_ws_bytes(int32_t m) { return (int64_t)m * m * 8 + 256; }
 
 extern "C" int pgb_chol_check(int32_t m, const double* A, int32_t* info_out, void* ws, int64_t ws_bytes,

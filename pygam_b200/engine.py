@@ -34,7 +34,8 @@ class DeviceData:
             raise ValueError("Xt must be a 2-d float64 tensor of shape (n_features, n_rows)")
         # rows of Xt (feature columns) must be unit-stride; the leading dimension may be padded (from_host pads it to
         # a multiple of 16 rows so that every column starts 16-byte aligned: the TMA bulk copies of the O(k) passes)
-        self.Xt = Xt if (Xt.stride(1) == 1 and Xt.stride(0) >= Xt.shape[1]) or Xt.shape[0] <= 1 else Xt.contiguous()
+        ok = Xt.shape[1] <= 1 or (Xt.stride(1) == 1 and (Xt.shape[0] <= 1 or Xt.stride(0) >= Xt.shape[1]))
+        self.Xt = Xt if ok else Xt.contiguous()
         self.n_features, self.n = self.Xt.shape
         self.ld = self.Xt.stride(0) if self.n_features > 1 else self.n
         self.y = None if y is None else y.to(device=Xt.device, dtype=torch.float64).contiguous()
@@ -81,6 +82,26 @@ def all_reduce_(t, op="sum"):
     return t
 
 
+def world():
+    """(rank, world size) of the default process group; (0, 1) without one"""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def all_gather_rows(local, total_rows, lo, device):
+    """rows [lo, lo + len(local)) of a (total_rows, width) host array live on this rank: returns the full array on
+    every rank (grid-search candidates solved rank by rank).  One all-reduce(sum) of the zero-padded
+    array: the message is small and every rank needs all of it."""
+    full = torch.zeros((total_rows, local.shape[1]), dtype=torch.float64, device=device)
+    if len(local):
+        full[lo:lo + len(local)] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(device)
+    all_reduce_(full, "sum")
+    return full.cpu().numpy()
+
+
 def column_stats(data):
     """per-feature (min, max) and non-finite count of the (global) data: gen_edge_knots
     (utils.py:592-621) and the finite check of check_X (utils.py:180-182), on the device"""
@@ -125,7 +146,11 @@ def _cuda_count_levels(data, feature, lo, hi):
     present = all_reduce_(present, "max")
     p = present.cpu().numpy()
     if p[rng] != 0:
-        # non-integer levels: exact distinct count (single process only)
+        # non-integer levels: exact distinct count of the local shard; the ranks of a sharded fit would have to
+        # exchange their level sets first
+        if world()[1] > 1:
+            raise NotImplementedError(f"categorical feature {feature} has non-integer levels: not supported with "
+                                      "row shards on several ranks (code the levels as integers)")
         vals = torch.unique(data.Xt[feature])
         return int(vals.numel())
     return int(p[:rng].sum())
@@ -367,6 +392,79 @@ class Engine:
             res["cov"] = self.cov.view(m, m).cpu().numpy().copy()
         return res
 
+    def solve_truncated(self, rank, coef_prev=None, want_cov=False):
+        """fewer kept rows than coefficients: the reference's SVD cropped to `rank` singular triplets
+        (pygam.py:789-799) = the `rank` largest eigenpairs of G + EtE, with the Gram data in self.out and the
+        penalty of the last set_penalty; same result dict as solve()"""
+        m = self.m
+        if want_cov and self.cov is None:
+            self.cov = torch.empty(m * m, dtype=torch.float64, device=self.device)
+        prev = None
+        if coef_prev is not None:
+            self.beta_prev.copy_(torch.as_tensor(coef_prev, dtype=torch.float64))
+            prev = self.beta_prev
+        need = int(self.lib.pgb_solve_truncated_ws_bytes(m)) // 8 + 1
+        if getattr(self, "_trunc_ws", None) is None:
+            self._trunc_ws = torch.empty(need, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.pgb_solve_truncated(m, int(rank), _ptr(self.out), _ptr(self.out[m * m:]), _ptr(self.EtE),
+                                                _ptr(self.EtE_null) if self._has_null_part else C.c_void_p(0), _ptr(prev),
+                                                _lib.SOLVE_COV if want_cov else 0, _ptr(self.sol),
+                                                _ptr(self.cov) if want_cov else C.c_void_p(0), _ptr(self._trunc_ws),
+                                                self._trunc_ws.numel() * 8, _stream()), "pgb_solve_truncated")
+        s = self.sol.cpu().numpy()
+        res = dict(coef=s[:m].copy(), edof=float(s[m]), diff=float(s[m + 1]),
+                   info=int(s[m + 2]) if np.isfinite(s[m + 2]) else 2, logdet=0.0)
+        if not np.isfinite(res["coef"]).all():
+            res["info"] = 2
+        if want_cov:
+            res["cov"] = self.cov.view(m, m).cpu().numpy().copy()
+        return res
+
+    def solve_batch(self, EtE, EtE_null=None, want_cov=False, max_bytes=1 << 28):
+        """K penalised systems that share the Gram data currently in self.out (grid-search candidates of a model
+        whose weights do not depend on the coefficients): one CTA per system, pgb_solve(nb = K).
+        EtE, EtE_null: (K, m, m) host arrays.  Returns coef (K, m), edof (K,), info (K,) [, cov (K, m, m)]."""
+        m = self.m
+        EtE = np.ascontiguousarray(EtE, dtype=np.float64).reshape(-1, m, m)
+        K = EtE.shape[0]
+        if EtE_null is not None:
+            EtE_null = np.ascontiguousarray(EtE_null, dtype=np.float64).reshape(K, m, m)
+        per = m * m * 8 * (4 + (1 if want_cov else 0))
+        chunk = max(1, min(K, int(max_bytes // per)))
+        f64 = dict(dtype=torch.float64, device=self.device)
+        coef = np.empty((K, m))
+        edof = np.empty(K)
+        info = np.empty(K, dtype=np.int64)
+        cov = np.empty((K, m, m)) if want_cov else None
+        flags = _lib.SOLVE_EDOF | _lib.SOLVE_PREPARED | (_lib.SOLVE_COV if want_cov else 0)
+        ws = torch.empty(int(self.lib.pgb_solve_ws_bytes(m, chunk)) // 8 + 1, **f64)
+        prep_ws = torch.empty(chunk * m * m, **f64)
+        A0 = torch.empty(chunk * m * m, **f64)
+        out = torch.empty(chunk * (m + _lib.SOLVE_OUT_EXTRA), **f64)
+        covd = torch.empty(chunk * m * m, **f64) if want_cov else None
+        G = self.out
+        r = self.out[m * m:]
+        for k0 in range(0, K, chunk):
+            nb = min(chunk, K - k0)
+            E = torch.from_numpy(EtE[k0:k0 + nb].reshape(-1)).to(self.device)
+            En = None if EtE_null is None else torch.from_numpy(EtE_null[k0:k0 + nb].reshape(-1)).to(self.device)
+            _lib.check(self.lib.pgb_solve_prepare(m, nb, _ptr(E), _ptr(En), _ptr(self.hv), _ptr(self.tau), self.p, _ptr(A0),
+                                                  _ptr(prep_ws), prep_ws.numel() * 8, _stream()), "pgb_solve_prepare")
+            _lib.check(self.lib.pgb_solve(m, nb, _ptr(G), _ptr(r), 1, _ptr(A0), C.c_void_p(0), _ptr(self.hv),
+                                          _ptr(self.tau), self.p, C.c_void_p(0), 1, flags, _ptr(out), _ptr(covd),
+                                          _ptr(ws), ws.numel() * 8, _stream()), "pgb_solve")
+            o = out[:nb * (m + _lib.SOLVE_OUT_EXTRA)].view(nb, m + _lib.SOLVE_OUT_EXTRA).cpu().numpy()
+            coef[k0:k0 + nb] = o[:, :m]
+            edof[k0:k0 + nb] = o[:, m]
+            inf = o[:, m + 2]
+            info[k0:k0 + nb] = np.where(np.isfinite(inf), inf, 2).astype(np.int64)
+            if want_cov:
+                cov[k0:k0 + nb] = covd[:nb * m * m].view(nb, m, m).cpu().numpy()
+        res = dict(coef=coef, edof=edof, info=info)
+        if want_cov:
+            res["cov"] = cov
+        return res
+
     def stats_pass(self, data, coef, scale=-1.0, ybar=0.0, poisson_round=False, want_mu=False, want_lp=False,
                    reduce=True):
         """lp / mu and the statistics sums on ALL rows (pygam.py:1031-1056, 423-450)"""
@@ -429,9 +527,10 @@ def get_backend():
     return _BACKEND
 
 
-def set_backend(backend):
-    """test hook: the CPU test-suite swaps in an oracle-backed engine to exercise the host logic
-    (PIRLS driver, grid search, sharding) without a GPU; the product never calls this"""
+def swap_backend_for_tests(backend):
+    """TEST HOOK, never called by the product: the CPU test-suite swaps in an oracle-backed engine
+    (tests/oracle_backend.py) to exercise the host logic -- PIRLS driver, grid search, sharding -- without a GPU.
+    The product has exactly one backend, the CUDA engine above."""
     global _BACKEND
     old = _BACKEND
     _BACKEND = backend

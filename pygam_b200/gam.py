@@ -19,7 +19,8 @@ import scipy.stats
 import torch
 
 from . import _lib
-from .engine import DeviceData, all_reduce_, column_stats, count_levels, descriptor_key, get_backend
+from .engine import (DeviceData, all_gather_rows, all_reduce_, column_stats, count_levels, descriptor_key,
+                     get_backend, world)
 from .terms import FactorTerm, Intercept, SplineTerm, Term, TermList
 
 EPS = np.finfo(np.float64).eps  # pygam/utils.py:16
@@ -278,8 +279,11 @@ class GAM:
 
     # ---- engine ----
     def _get_engine(self, data):
+        # the analytic null vectors are part of the engine: they can change between fits of the same descriptor
+        # (an order-0 basis whose kept edge knots no longer span the data, terms.null_vectors)
         desc_key = (descriptor_key(self.terms, data.n_features), self.distribution.name, self.link.name,
-                    float(self.distribution.levels), self._expectile, data.n_features, str(data.device))
+                    float(self.distribution.levels), self._expectile, data.n_features, str(data.device),
+                    self.terms.null_vectors().tobytes())
         if self._engine is None or self._engine_key != desc_key:
             self._engine = get_backend().make_engine(self.terms, self.distribution.name, self.link.name,
                                                      self.distribution.levels, self._expectile,
@@ -391,7 +395,13 @@ class GAM:
                     self._gram_cache = cache
             self._log_start(dev, ncorrect, nused)
 
-            sol = eng.solve(coef_prev=self.coef_)
+            # fewer kept rows than coefficients: the reference's SVD is cropped to that many singular triplets
+            # (pygam.py:789-799); the statistics below use the rank of the last iteration like the reference's U1
+            self._solve_rank = int(min(m, n, nused))
+            if self._solve_rank < m:
+                sol = eng.solve_truncated(self._solve_rank, coef_prev=self.coef_)
+            else:
+                sol = eng.solve(coef_prev=self.coef_)
             if sol["info"] == 2:
                 raise ValueError("QR decomposition produced NaN or Inf. Check X data.")
             if sol["info"] != 0:
@@ -438,7 +448,10 @@ class GAM:
         st = self.statistics_
         # edof and cov from the LAST iteration's Gram matrix (weights at the previous
         # coefficients), as the reference's B and U1 are (pygam.py:815-817)
-        sol = eng.solve(coef_prev=None, want_edof=True, want_cov=True)
+        if getattr(self, "_solve_rank", self.terms.n_coefs) < self.terms.n_coefs:
+            sol = eng.solve_truncated(self._solve_rank, want_cov=True)
+        else:
+            sol = eng.solve(coef_prev=None, want_edof=True, want_cov=True)
         st["edof_per_coef"] = None
         st["edof"] = sol["edof"]
         sc, _, _ = eng.stats_pass(data, self.coef_)
@@ -519,7 +532,10 @@ class GAM:
         self.statistics_ = {}
         self.statistics_["n_samples"] = self._n_global
         self.statistics_["m_features"] = data.n_features
-        self.logs_ = {c: [] for c in self.callbacks}
+        if not hasattr(self, "logs_"):  # pygam.py:901-902: created once, so the logs of a refit are appended
+            self.logs_ = {c: [] for c in self.callbacks}
+        for c in self.callbacks:
+            self.logs_.setdefault(c, [])
         self._pirls(data)
         return self
 
@@ -783,6 +799,14 @@ class GAM:
             models.append(self)
             scores.append(self.statistics_[objective])
             best_model, best_score = models[-1], scores[-1]
+        if self._batched_gridsearch_ok(data, params):
+            # LinearGAM over a lam grid: one Gram pass, all candidates solved as one batch (split over the ranks)
+            done = self._gridsearch_linear_batched(data, param_grid_list, objective, models, scores)
+            if done:
+                param_grid_list = []
+                for gam, score in zip(models, scores):
+                    if score < best_score:
+                        best_model, best_score = gam, score
         for param_grid in param_grid_list:
             try:
                 gam = copy.deepcopy(self)
@@ -813,6 +837,136 @@ class GAM:
         if return_scores:
             return OrderedDict(zip(models, scores))
         return self
+
+
+    # ---- grid search of a model whose weights do not depend on the coefficients ----
+    def _batched_gridsearch_ok(self, data, params):
+        return (self._coef_independent_gram() and list(params) == ["lam"] and data.w is None
+                and not self.terms.hasconstraint and set(self.callbacks) <= {"deviance", "diffs", "coef"})
+
+    def _gridsearch_linear_batched(self, data, param_grid_list, objective, models, scores):
+        """pygam.py:2042-2070 for Normal / identity without weights or constraints.  G = X^T X and r = X^T y do not
+        depend on lam or on the coefficients, so the whole grid costs ONE Gram pass, one O(k) pass for the moments
+        of y, and K independent m x m solves (a batch, split over the ranks).  Every quantity the reference
+        recomputes from the data per candidate is a quadratic form here: the deviance at beta is
+        y^T y - 2 beta^T r + beta^T G beta.  The warm-start chain (pygam.py:2051-2053) only decides how many
+        iterations a candidate logs: the first solve from the previous candidate's coefficients already lands on
+        the solution, and a second iteration runs iff its relative change was >= tol.
+        Returns False (nothing appended) when the quadratic forms would cancel too many digits."""
+        eng = self._get_engine(data)
+        m = self.terms.n_coefs
+        nt = torch.tensor([float(data.n)], dtype=torch.float64, device=data.device)
+        n = int(all_reduce_(nt, "sum").item())
+        cache = self._gram_cache if (self._gram_cache is not None and self._gram_cache.get("data") is data) else None
+        if cache is None:
+            eng.gram_pass(data, np.zeros(m))
+            if eng.gram_scalars()[_lib.GS_NUSED] != n:
+                return False
+            cache = dict(data=data, out=eng.out.clone())
+            self._gram_cache = cache
+        else:
+            eng.out.copy_(cache["out"])
+        host = eng.out.cpu().numpy()
+        G, r = host[:m * m].reshape(m, m).copy(), host[m * m:m * m + m].copy()
+        sc0, _, _ = eng.stats_pass(data, np.zeros(m))
+        yy, sy = float(sc0[_lib.SS_DEV]), float(sc0[_lib.SS_SUMY])
+
+        def dev_at(beta):
+            return yy - 2.0 * float(beta @ r) + float(beta @ (G @ beta))
+
+        # candidates in grid order: penalties and the reference's Cholesky test of S + P (a failing one is skipped)
+        S = np.eye(m) * np.sqrt(EPS)
+        cands = []
+        for param_grid in param_grid_list:
+            try:
+                gam = copy.deepcopy(self)
+                gam.set_params(**param_grid)
+                gam._validate_params()
+                Pn, Pr = gam.terms.build_penalties(split=True)
+                EtE = gam._cholesky_check(eng, S + (Pn + Pr))
+                cands.append((gam, EtE - Pn, Pn, param_grid))
+            except ValueError as error:
+                if self.verbose:
+                    warnings.warn(str(error) + "\non model with params:\n" + str(param_grid) + "\nskipping...\n")
+        K = len(cands)
+        if K == 0:
+            return True
+        rank, nranks = world()
+        lo, hi = K * rank // nranks, K * (rank + 1) // nranks
+        loc = eng.solve_batch(np.stack([c[1] for c in cands[lo:hi]]) if hi > lo else np.zeros((0, m, m)),
+                              np.stack([c[2] for c in cands[lo:hi]]) if hi > lo else np.zeros((0, m, m)),
+                              want_cov=True) if hi > lo else dict(coef=np.zeros((0, m)), edof=np.zeros(0),
+                                                                  info=np.zeros(0), cov=np.zeros((0, m, m)))
+        packed = np.concatenate([loc["coef"], loc["edof"][:, None], np.asarray(loc["info"], dtype=np.float64)[:, None],
+                                 loc["cov"].reshape(hi - lo, m * m)], axis=1)
+        packed = np.where(np.isfinite(packed), packed, 0.0) if nranks > 1 else packed
+        full = all_gather_rows(packed, K, lo, data.device) if nranks > 1 else packed
+        prev = np.asarray(models[-1].coef_, dtype=np.float64) if models else np.ones(m) * np.sqrt(EPS)
+        new_models, new_scores = [], []
+        for k, (gam, _, _, param_grid) in enumerate(cands):
+            beta, edof, info = full[k, :m], float(full[k, m]), int(full[k, m + 1])
+            if info != 0 or not np.isfinite(beta).all():
+                if self.verbose:
+                    warnings.warn("penalised normal equations are not positive definite\non model with params:\n"
+                                  + str(param_grid) + "\nskipping...\n")
+                continue
+            dev = dev_at(beta)
+            if not (dev > 1e-7 * yy):
+                return False  # cancellation: take the data passes instead
+            gam._n_global = n
+            gam.statistics_ = {"n_samples": n, "m_features": data.n_features}
+            if not hasattr(gam, "logs_"):
+                gam.logs_ = {}
+            for c in gam.callbacks:
+                gam.logs_.setdefault(c, [])
+            diff = float(np.linalg.norm(prev - beta) / np.linalg.norm(beta))
+            gam.coef_ = prev
+            gam._log_start(dev_at(prev), 0.0, n)
+            gam._log_end(diff)
+            gam.coef_ = beta.copy()
+            if diff >= gam.tol and gam.max_iter >= 2:
+                gam._log_start(dev, 0.0, n)
+                diff = 0.0  # the second solve of the same system returns the same coefficients
+                gam._log_end(diff)
+            gam._linear_statistics_from_moments(n, edof, dev, yy, sy, full[k, m + 2:].reshape(m, m))
+            if diff >= gam.tol:
+                print("did not converge")
+            new_models.append(gam)
+            new_scores.append(gam.statistics_[objective])
+            prev = gam.coef_
+        models.extend(new_models)
+        scores.extend(new_scores)
+        for k in _DEVICE_KEYS:
+            for gam in new_models:
+                gam.__dict__[k] = self.__dict__.get(k)
+        return True
+
+    def _linear_statistics_from_moments(self, n, edof, dev, yy, sy, cov_unscaled):
+        """_estimate_model_statistics (pygam.py:993-1057) of a Normal / identity model without weights from the
+        residual sum of squares `dev` and the moments of y: the log-likelihood of Normal(mu, scale) rows
+        (distributions.py:110-131) is -dev / (2 scale^2) - n (log(2 pi) / 2 + log(scale)), the null model's mean
+        is sum(y) / n (pygam.py:1141-1147)."""
+        dist, st = self.distribution, self.statistics_
+        st["edof_per_coef"] = None
+        st["edof"] = edof
+        if not dist._known_scale:
+            dist.scale = float(np.sqrt(dev / (n - edof)))
+        st["scale"] = dist.scale
+        st["cov"] = cov_unscaled * dist.scale ** 2
+        st["se"] = np.maximum(st["cov"].diagonal(), 0.0) ** 0.5
+        s2 = dist.scale ** 2
+        const = n * (0.5 * np.log(2.0 * np.pi) + np.log(dist.scale))
+        ll = -0.5 * dev / s2 - const
+        null_dev = yy - sy * sy / n
+        null_ll = -0.5 * null_dev / s2 - const
+        st["AIC"] = -2 * ll + 2 * edof + 2 * (not dist._known_scale)
+        st["AICc"] = st["AIC"] + 2 * (edof + 1) * (edof + 2) / (n - edof - 2)
+        st["pseudo_r2"] = OrderedDict([("explained_deviance", 1.0 - dev / null_dev), ("McFadden", ll / null_ll),
+                                       ("McFadden_adj", 1.0 - (ll - edof) / null_ll)])
+        st["GCV"], st["UBRE"] = self._estimate_GCV_UBRE(dev, n, edof)
+        st["loglikelihood"] = ll
+        st["deviance"] = dev / s2
+        st["p_values"] = self._estimate_p_values()
 
 
 class _ShapeOnly:

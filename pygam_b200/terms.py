@@ -265,6 +265,18 @@ class SplineTerm(Term):
             self.edge_knots_ = np.asarray(self.edge_knots, dtype=np.float64)
         if getattr(self, "edge_knots_", None) is None:
             self.edge_knots_ = _edge_knots(X, self.feature, self.dtype, col_minmax)
+        # do the edge knots span the data of THIS fit?  edge_knots_ survives refits (terms.py:920) and can be set by
+        # the user; an order-0 basis has an all-zero row outside them, so the block is a partition of unity -- and
+        # (1 on the block, -1 on the intercept) a null vector of the design -- only if they do (null_vectors below)
+        self._covers_data_ = None
+        if col_minmax is not None or hasattr(X, "__getitem__"):
+            if col_minmax is not None:
+                lo, hi = col_minmax[self.feature]
+            else:
+                col = np.asarray(X[:, self.feature])
+                lo, hi = col.min(), col.max()
+            ek = np.sort(np.asarray(self.edge_knots_, dtype=np.float64))
+            self._covers_data_ = bool(ek[0] <= lo and hi <= ek[-1])
         return self
 
 
@@ -635,10 +647,8 @@ class TermList:
                 icpt = start
             elif t.by is None and (
                 (isinstance(t, FactorTerm) and t.coding == "one-hot")
-                or (isinstance(t, SplineTerm) and not isinstance(t, FactorTerm)
-                    and not (t.spline_order == 0 and t.edge_knots is not None))
-                or (t.istensor and not any(q.spline_order == 0 and q.edge_knots is not None
-                                           for q in t._terms))
+                or (isinstance(t, SplineTerm) and not isinstance(t, FactorTerm) and _rows_sum_to_one(t))
+                or (t.istensor and all(_rows_sum_to_one(q) for q in t._terms))
             ):
                 blocks.append((start, n))
             start += n
@@ -659,6 +669,17 @@ class TermList:
         if not vecs:
             return np.zeros((m, 0))
         return np.stack(vecs, axis=1)
+
+
+def _rows_sum_to_one(t):
+    """does every model-matrix row of the spline (marginal) sum to one on the data it was compiled for?  Orders
+    >= 1 extrapolate linearly outside the edge knots (utils.py:744-763; the slopes of a partition of unity sum to
+    zero), an order-0 basis is zero there: it qualifies only when the knots span the data (not known: only when
+    the knots came from the data, i.e. the user gave none)."""
+    if t.spline_order > 0:
+        return True
+    covers = getattr(t, "_covers_data_", None)
+    return t.edge_knots is None if covers is None else covers
 
 
 def _flatten(v):

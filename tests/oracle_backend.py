@@ -183,6 +183,46 @@ class OracleEngine:
             res["diff"] = np.linalg.norm(np.asarray(coef_prev) - res["coef"]) / np.linalg.norm(res["coef"])
         return res
 
+    def solve_truncated(self, rank, coef_prev=None, want_cov=False):
+        """numpy mirror of pgb_solve_truncated: the `rank` largest eigenpairs of G + EtE"""
+        m = self.m
+        o = self.out.numpy()
+        G = o[: m * m].reshape(m, m)
+        r = o[m * m: m * m + m]
+        A = G + self.EtE + (0.0 if self.EtE_null is None else self.EtE_null)
+        lam, V = np.linalg.eigh(0.5 * (A + A.T))
+        keep = np.argsort(-lam, kind="stable")[:rank]
+        Vk, lk = V[:, keep], lam[keep]
+        coef = Vk @ ((Vk.T @ r) / lk)
+        W = (Vk.T @ G @ Vk) / np.outer(lk, lk)
+        res = dict(info=0, coef=coef, edof=float(np.sum(np.diag(W) * lk)), diff=np.nan)
+        if coef_prev is not None:
+            res["diff"] = np.linalg.norm(np.asarray(coef_prev) - coef) / np.linalg.norm(coef)
+        if want_cov:
+            res["cov"] = Vk @ W @ Vk.T
+        return res
+
+    def solve_batch(self, EtE, EtE_null=None, want_cov=False, max_bytes=None):
+        m = self.m
+        o = self.out.numpy()
+        G = o[: m * m].reshape(m, m)
+        r = o[m * m: m * m + m]
+        K = len(EtE)
+        coef, edof, info = np.full((K, m), np.nan), np.full(K, np.nan), np.zeros(K, dtype=np.int64)
+        cov = np.full((K, m, m), np.nan) if want_cov else None
+        for k in range(K):
+            res = solve_mirror(G, r, EtE[k], self.V, self.tau, want_cov=want_cov,
+                               EtE_null=None if EtE_null is None else EtE_null[k])
+            info[k] = res["info"]
+            if res["info"] == 0:
+                coef[k], edof[k] = res["coef"], res["edof"]
+                if want_cov:
+                    cov[k] = res["cov"]
+        out = dict(coef=coef, edof=edof, info=info)
+        if want_cov:
+            out["cov"] = cov
+        return out
+
     def stats_pass(self, data, coef, scale=-1.0, ybar=0.0, poisson_round=False, want_mu=False, want_lp=False,
                    reduce=True):
         B = self._modelmat(data)

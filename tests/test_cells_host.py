@@ -31,11 +31,11 @@ def _selfcheck_lib():
 
 
 def _fit_on_cpu(case, g):
-    old = pg_engine.set_backend(OracleBackend())
+    old = pg_engine.swap_backend_for_tests(OracleBackend())
     try:
         gam = helpers.fit_case(case, g, max_iter=2)
     finally:
-        pg_engine.set_backend(old)
+        pg_engine.swap_backend_for_tests(old)
     return gam
 
 

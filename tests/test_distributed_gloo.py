@@ -36,7 +36,7 @@ def _worker(rank, world, port, name, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    pg_engine.set_backend(OracleBackend())
+    pg_engine.swap_backend_for_tests(OracleBackend())
     case = cases.FIT_CASES[name]
     g = helpers.load("fit_" + name)
     n = len(g["y"])
@@ -59,12 +59,12 @@ def test_two_rank_row_sharding_matches_single_process(name, tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), name, str(tmp_path)), nprocs=2, join=True)
     r0 = dict(np.load(tmp_path / "rank0.npz"))
     r1 = dict(np.load(tmp_path / "rank1.npz"))
-    old = pg_engine.set_backend(OracleBackend())
+    old = pg_engine.swap_backend_for_tests(OracleBackend())
     try:
         g = helpers.load("fit_" + name)
         single = helpers.fit_case(cases.FIT_CASES[name], g)
     finally:
-        pg_engine.set_backend(old)
+        pg_engine.swap_backend_for_tests(old)
     # both ranks hold the same model (the solve is replicated and deterministic)
     np.testing.assert_array_equal(r0["coef"], r1["coef"])
     assert int(r0["n"]) == len(g["y"]) == int(r1["n"])

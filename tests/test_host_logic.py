@@ -17,9 +17,9 @@ import pygam_b200 as pg
 
 @pytest.fixture(autouse=True)
 def oracle_backend():
-    old = pg_engine.set_backend(OracleBackend())
+    old = pg_engine.swap_backend_for_tests(OracleBackend())
     yield
-    pg_engine.set_backend(old)
+    pg_engine.swap_backend_for_tests(old)
 
 
 def test_penalties_known_answers():

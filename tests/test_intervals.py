@@ -70,11 +70,11 @@ def _check(name):
 
 @pytest.mark.parametrize("name", CASES)
 def test_intervals_host_logic(name):
-    old = pg_engine.set_backend(OracleBackend())
+    old = pg_engine.swap_backend_for_tests(OracleBackend())
     try:
         _check(name)
     finally:
-        pg_engine.set_backend(old)
+        pg_engine.swap_backend_for_tests(old)
 
 
 @pytest.mark.gpu

@@ -1,0 +1,283 @@
+"""Parity cases round 1 left open (VERDICT r1 "What's weak" 1-3): masked rows (GAM._mask, pygam.py:638-663 -- logit
+overflow to NaN, weights below sqrt(EPS)), the all-masked OptimizationError, a non-positive-definite penalty skipped
+inside gridsearch (pygam/tests/test_utils.py:176-183), the inv_squared link, p-values / standard errors / AICc,
+ExpectileGAM.fit_quantile, pickle / deepcopy of a fitted model, rows < coefficients, the 11^3 lam grid of config 4 and
+configs 2 / 3 at 1e5 / 5e4 rows.  Fixtures: tests/golden/r2_*.npz, outputs of the unmodified reference
+(tests/golden/make_golden_r2.py).  Every product test runs twice: on the CPU with the oracle-backed test engine (host
+logic) and, marked gpu, on the CUDA engine through the C ABI."""
+import contextlib
+import copy
+import hashlib
+import io
+import os
+import pickle
+import warnings
+
+import numpy as np
+import pytest
+
+import cases
+import helpers
+from helpers import rel
+from oracle import gam_oracle as orc
+from oracle_backend import OracleBackend
+import pygam_b200 as pg
+from pygam_b200 import engine as pg_engine
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+BACKENDS = [pytest.param("oracle", id="host-logic"), pytest.param("cuda", marks=pytest.mark.gpu, id="cuda")]
+
+
+def r2(name):
+    return dict(np.load(os.path.join(GOLD, f"r2_{name}.npz")))
+
+
+@contextlib.contextmanager
+def backend(kind):
+    if kind == "oracle":
+        old = pg_engine.swap_backend_for_tests(OracleBackend())
+        try:
+            yield
+        finally:
+            pg_engine.swap_backend_for_tests(old)
+    else:
+        yield
+
+
+def quiet_fit(gam, *a, **kw):
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return gam.fit(*a, **kw)
+
+
+def check_fit(gam, g, X, coef_tol=1e-8, stat_tol=1e-10, log_tol=1e-8):
+    assert len(gam.logs_["diffs"]) == int(g["n_iter"])
+    assert (gam.logs_["diffs"][-1] < gam.tol) == bool(g["log_diffs"][-1] < g["tol"])
+    np.testing.assert_allclose(gam.logs_["deviance"], g["log_deviance"], rtol=log_tol)
+    Pz = helpers.identifiable_projector(gam)
+    err = np.linalg.norm(Pz @ (gam.coef_ - g["coef"])) / np.linalg.norm(g["coef"])
+    assert err < coef_tol, err
+    st = gam.statistics_
+    for key in ("edof", "deviance", "scale", "loglikelihood", "AIC", "AICc"):
+        refv = float(g["stat_" + key])
+        assert abs(st[key] - refv) <= max(stat_tol, 1e-9 if key in ("edof", "loglikelihood", "AIC", "AICc") else 0) * max(1.0, abs(refv)), (key, st[key], refv)
+    for key in ("GCV", "UBRE"):
+        refv = float(g["stat_" + key])
+        if not np.isnan(refv):
+            assert abs(st[key] - refv) <= stat_tol * abs(refv), (key, st[key], refv)
+    assert rel(gam._linear_predictor(X[:64]), g["lp_head"]) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
+# the oracle itself against the new fixtures
+# ---------------------------------------------------------------------------------------------
+MASK_LOGIT = dict(model="LogisticGAM", terms=[cases.s(0), cases.s(1), cases.s(2)])
+INV_SQ = dict(model="GAM", terms=[cases.s(0), cases.s(1), cases.s(2)], model_kwargs=dict(distribution="gamma", link="inv_squared"))
+
+
+def _oracle_check(res, g, tol=1e-9):
+    # the reference creates logs_ once (pygam.py:901-902): a refitted object carries the logs of its earlier fits in
+    # front of the last fit's
+    k = len(res["logs"]["diffs"])
+    assert k <= int(g["n_iter"])
+    np.testing.assert_allclose(res["logs"]["deviance"], g["log_deviance"][-k:], rtol=1e-9)
+    for key in ("edof", "deviance", "AIC", "AICc", "loglikelihood"):
+        assert abs(res["statistics"][key] - float(g["stat_" + key])) <= tol * max(1.0, abs(float(g["stat_" + key]))), key
+
+
+def test_oracle_masked_rows_logit_overflow():
+    g = r2("mask_logit")
+    with np.errstate(all="ignore"):
+        res = orc.fit(MASK_LOGIT, g["X"], g["y"], coef=g["coef0"])
+    _oracle_check(res, g)
+    # half of the rows overflow in the first iteration: exp(lp) = inf, mu = NaN (links.py:121-122)
+    lp0 = orc.model_matrix(orc.compile_terms(orc.normalize_terms(MASK_LOGIT["terms"]), g["X"]), g["X"]).dot(g["coef0"])
+    assert (lp0 > 709.8).sum() > 1000
+
+
+def test_oracle_masked_rows_tiny_weights_and_inv_squared_and_truncated_svd():
+    g = r2("mask_weights")
+    _oracle_check(orc.fit(cases.FIT_CASES["c4_linear"], g["X"], g["y"], weights=g["weights"]), g)
+    g = r2("inv_squared")
+    with np.errstate(all="ignore"):
+        _oracle_check(orc.fit(INV_SQ, g["X"], g["y"]), g, tol=1e-7)
+    g = r2("rows_lt_coefs")  # n = 15 < m = 41: the truncated SVD of pygam.py:789-799 is part of the restatement
+    res = orc.fit(dict(model="LinearGAM", terms=[cases.s(0), cases.s(1)]), g["X"], g["y"])
+    assert len(res["logs"]["diffs"]) == int(g["n_iter"])
+    assert abs(res["statistics"]["edof"] - float(g["stat_edof"])) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# the product
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_masked_rows_logit_overflow(kind):
+    """lp > 709 on half of the rows of the first iteration: mu = NaN, the rows are masked out of G, r, the
+    logged deviance and the accuracy; the fit then recovers like the reference's (12 iterations)"""
+    g = r2("mask_logit")
+    with backend(kind):
+        gam = helpers.build_model(MASK_LOGIT)
+        quiet_fit(gam, g["X"], g["y"])
+        gam.coef_ = g["coef0"].copy()
+        quiet_fit(gam, g["X"], g["y"])
+        # iterations 6-9 solve a rank-57 system of 57 kept rows whose cropped spectrum reaches down to the
+        # sqrt(EPS)-sized eigenvalues: their logged deviances agree to 1e-7 only, in the reference's own arithmetic
+        # too; the converged fit is held to the usual tolerances
+        check_fit(gam, g, g["X"], log_tol=1e-6)
+        np.testing.assert_allclose(gam.logs_["accuracy"], g["log_accuracy"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_masked_rows_tiny_weights_and_all_masked(kind):
+    g = r2("mask_weights")
+    with backend(kind):
+        gam = helpers.build_model(cases.FIT_CASES["c4_linear"])
+        quiet_fit(gam, g["X"], g["y"], weights=g["weights"])
+        check_fit(gam, g, g["X"])
+        # every row below the mask threshold: OptimizationError (pygam.py:658-662)
+        with pytest.raises(pg.OptimizationError):
+            quiet_fit(helpers.build_model(cases.FIT_CASES["c4_linear"]), g["X"], g["y"], weights=np.full(len(g["y"]), 1e-20))
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_inv_squared_link(kind):
+    g = r2("inv_squared")
+    with backend(kind):
+        gam = pg.GAM(pg.s(0) + pg.s(1) + pg.s(2), distribution="gamma", link="inv_squared")
+        quiet_fit(gam, g["X"], g["y"])
+        check_fit(gam, g, g["X"], coef_tol=1e-7, stat_tol=1e-8)
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_gridsearch_skips_a_penalty_that_is_not_positive_definite(kind):
+    """pygam/tests/test_utils.py:176-183: lam = 1e10 .. 1e12 must not crash the grid search; a candidate whose
+    S + P has no Cholesky factor is skipped (pygam.py:2055-2066)"""
+    X, y = cases.data_c2(1500)
+    with backend(kind), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gam = pg.LogisticGAM(pg.s(0) + pg.s(1))
+        with contextlib.redirect_stdout(io.StringIO()):
+            scores = gam.gridsearch(X[:, :2], y, lam=np.logspace(10, 12, 3), return_scores=True)
+        assert len(scores) <= 3 and gam._is_fitted
+        lin = pg.LinearGAM(pg.s(0) + pg.s(1))
+        with contextlib.redirect_stdout(io.StringIO()):
+            s2 = lin.gridsearch(X[:, :2], X[:, 0] + y, lam=np.logspace(10, 16, 4), return_scores=True)
+        assert 1 <= len(s2) <= 4 and lin._is_fitted
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+@pytest.mark.parametrize("name", ["c1_wage", "c2_logistic", "gamma", "linear_weights", "poisson_exposure", "tensor_by"])
+def test_p_values_standard_errors_aicc(kind, name):
+    """statistics_ entries stored in the round-1 fixtures that no test compared"""
+    case = cases.FIT_CASES[name]
+    g = helpers.load("fit_" + name)
+    with backend(kind):
+        gam = helpers.fit_case(case, g)
+    st = gam.statistics_
+    assert abs(st["AICc"] - float(g["stat_AICc"])) <= 1e-9 * abs(float(g["stat_AICc"]))
+    Pz = helpers.identifiable_projector(gam)
+    if "stat_cov" in g:  # standard errors on the identifiable part (the raw diagonal carries the null-space noise)
+        se = np.sqrt(np.maximum(np.diag(Pz @ st["cov"] @ Pz), 0))
+        se_ref = np.sqrt(np.maximum(np.diag(Pz @ g["stat_cov"] @ Pz), 0))
+        assert rel(se, se_ref) < 1e-6
+    # p-values: Wald statistics of the centred spline coefficients; the intercept's cov entry sits on the null space
+    pv, pv_ref = np.asarray(st["p_values"], float), g["stat_p_values"]
+    assert len(pv) == len(pv_ref) and np.all((pv >= 0) & (pv <= 1))
+    # _compute_p_value takes pinv(cov block) with scipy's rank cut-off (pygam.py:1283).  Where the reference's block
+    # has singular values near that cut-off (fewer distinct x than splines: wage's 7 years on 20 splines; te() x by)
+    # its rank -- hence the p-value -- is decided by the rounding noise of ITS cov: only unambiguous blocks compare
+    for i, t in enumerate(gam.terms):
+        if t.isintercept or "stat_cov" not in g:
+            continue
+        idx = gam.terms.get_coef_indices(i)
+        sv = np.linalg.svd(g["stat_cov"][idx][:, idx], compute_uv=False)
+        cut = sv.max() * len(idx) * np.finfo(float).eps
+        if np.any((sv > cut * 1e-4) & (sv < cut * 1e6)):
+            continue
+        np.testing.assert_allclose(pv[i], pv_ref[i], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_fit_quantile(kind):
+    g = r2("fit_quantile")
+    with backend(kind):
+        gam = pg.ExpectileGAM(pg.s(0) + pg.s(1), expectile=0.5)
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gam.fit_quantile(g["X"], g["y"], quantile=0.8)
+        assert gam.expectile == float(g["expectile"])  # same bisection path
+        assert abs(gam._get_quantile_ratio(g["X"], g["y"]) - float(g["ratio"])) < 1e-12
+        assert abs(gam.statistics_["GCV"] - float(g["stat_GCV"])) <= 1e-8 * float(g["stat_GCV"])
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_pickle_and_deepcopy_of_a_fitted_model(kind):
+    g = helpers.load("fit_gamma")
+    with backend(kind):
+        gam = helpers.fit_case(cases.FIT_CASES["gamma"], g)
+        mu = gam.predict_mu(g["X_new"])
+        for clone in (pickle.loads(pickle.dumps(gam)), copy.deepcopy(gam)):
+            np.testing.assert_array_equal(clone.coef_, gam.coef_)
+            assert clone.statistics_["edof"] == gam.statistics_["edof"]
+            np.testing.assert_array_equal(clone.predict_mu(g["X_new"]), mu)  # the clone rebuilds its engine
+        assert abs(gam.loglikelihood(g["X"], g["y"]) - float(g["stat_loglikelihood"])) <= 1e-9 * abs(float(g["stat_loglikelihood"]))
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_fewer_rows_than_coefficients(kind):
+    """n = 15 rows, m = 41 coefficients: the reference crops its SVD to rank n (pygam.py:789-799,
+    pygam/tests/test_GAM_methods.py:93-107); pgb_solve_truncated takes the n largest eigenpairs of G + E^T E"""
+    g = r2("rows_lt_coefs")
+    with backend(kind):
+        gam = pg.LinearGAM(pg.s(0) + pg.s(1))
+        quiet_fit(gam, g["X"], g["y"])
+        assert len(gam.logs_["diffs"]) == int(g["n_iter"])
+        st = gam.statistics_
+        assert abs(st["edof"] - float(g["stat_edof"])) < 1e-7
+        assert abs(st["GCV"] - float(g["stat_GCV"])) < 1e-7 * float(g["stat_GCV"])
+        assert rel(gam._linear_predictor(g["X"]), g["lp_head"]) < 1e-6
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_config4_grid_11_cubed(kind):
+    """BASELINE config 4 at n = 3000: 1331 candidates, one Gram pass, batched solves; scores, iteration counts
+    (363 x 1, 968 x 2 on the wage data of the survey; here whatever the reference logged), edof and AIC"""
+    g = r2("grid_c4_grid11")
+    X, y = cases.data_c4(3000)
+    with backend(kind):
+        gam = helpers.build_model(cases.FIT_CASES["c4_linear"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            scores = gam.gridsearch(X, y, return_scores=True, lam=[np.logspace(-3, 3, 11)] * 3)
+    models = list(scores)
+    assert len(models) == 1331 == len(g["scores"])
+    np.testing.assert_allclose(list(scores.values()), g["scores"], rtol=1e-10)
+    np.testing.assert_array_equal([len(mm.logs_["diffs"]) for mm in models], g["n_iters"])
+    np.testing.assert_allclose([mm.statistics_["edof"] for mm in models], g["edofs"], rtol=1e-9)
+    np.testing.assert_allclose([mm.statistics_["AIC"] for mm in models], g["aics"], rtol=1e-9)
+    np.testing.assert_allclose([mm.logs_["deviance"][0] for mm in models[1:]], g["first_dev"][1:], rtol=1e-9)
+    assert abs(gam.statistics_["GCV"] - float(g["best_score"])) <= 1e-10 * float(g["best_score"])
+    np.testing.assert_allclose(np.ravel(gam.lam), g["best_lam"])
+
+
+def _big(name, gen, n):
+    g = r2(name)
+    X, y = gen(n)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+    assert sha(X) == str(g["sha_X"]) and sha(y) == str(g["sha_y"]), "the seeded generator drifted from the fixture"
+    return g, X, y
+
+
+@pytest.mark.gpu
+def test_config2_at_100k_rows_matches_reference():
+    g, X, y = _big("big_c2", cases.data_c2, 100_000)
+    gam = helpers.build_model(cases.FIT_CASES["c2_logistic"])
+    quiet_fit(gam, X, y)
+    check_fit(gam, g, X)
+
+
+@pytest.mark.gpu
+def test_config3_at_50k_rows_matches_reference():
+    g, X, y = _big("big_c3", cases.data_c3, 50_000)
+    gam = helpers.build_model(cases.FIT_CASES["c3_poisson"])
+    quiet_fit(gam, X, y)
+    check_fit(gam, g, X)

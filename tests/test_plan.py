@@ -14,14 +14,14 @@ from pygam_b200 import engine as pg_engine
 
 
 def plan_for(case, X):
-    old = pg_engine.set_backend(OracleBackend())
+    old = pg_engine.swap_backend_for_tests(OracleBackend())
     try:
         gam = helpers.build_model(case)
         data = gam._prepare_data(X, None, None, fitting=False)
         mm, _ = pg_engine.column_stats(data)
         gam._validate_data_dep_params(data, mm)
     finally:
-        pg_engine.set_backend(old)
+        pg_engine.swap_backend_for_tests(old)
     desc = pg_engine.build_descriptor(gam.terms, X.shape[1])
     info = _lib.PgbModelInfo()
     errs = C.c_int32(-1)
