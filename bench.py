@@ -6,23 +6,36 @@ A step is ONE PIRLS iteration of BASELINE config 2 (LogisticGAM, 10 s() terms, n
 X^T W X, X^T W z), all-reduce of the packed [G | r | scalars] buffer over the row shards, and
 the m x m penalised solve.  Inputs are resident in HBM for `value`; `e2e` times the same
 iteration through the host-buffer C-ABI entry point (pinned host X/y -> device inside the timed
-region, coefficients read back).  `--impl reference` times the CPU port of the reference
-algorithm (oracle/gam_oracle.py: sparse model matrix, dense QR, SVD) on a bounded row sample.
+region, coefficients read back); `e2e.fit` is a whole LogisticGAM.fit(numpy X, numpy y) from host
+arrays to coef_ and statistics_.  `configs` carries the other BASELINE configurations (config 3 at
+1.25e8 rows per GPU, the north star's 20 s() shape, config 4's 11^3 grid search at 5e7 rows,
+config 5 at 1e8 rows, config 1 on the wage data), each with a parity check of a row prefix
+against the CPU oracle.  `--impl reference` times the UNMODIFIED reference (pyGAM installed into
+baseline/_ref) per PIRLS iteration on a bounded row sample, with all host cores.
 
     python bench.py --gpus 1 --steps 10 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
         --master-port 29500 bench.py --gpus 8 --steps 10 --warmup 3
 """
-import argparse
-import ctypes as C
-import json
 import os
-import subprocess
-import sys
-import threading
-import time
 
-import numpy as np
+# The CPU arm must use every host core: torchrun exports OMP_NUM_THREADS=1 to its ranks, which made the N > 1
+# reference runs of round 1 2.2x slower than the N = 1 run.  Set before numpy / BLAS load.
+_CORES = os.cpu_count() or 1
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = str(_CORES)
+
+import argparse  # noqa: E402
+import contextlib  # noqa: E402
+import ctypes as C  # noqa: E402
+import io  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import sys  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -34,6 +47,9 @@ N_SPLINES = 25
 BYTES_PER_ROW = 8 * N_FEATURES + 8  # every feature column and y read once, fp64
 K_NNZ = 4 * N_FEATURES + 1
 FMA_PER_ROW = K_NNZ * (K_NNZ + 1) // 2 + K_NNZ  # upper triangle of the rank-1 update + rhs
+FP64_FMA_PER_CLK_SM = 62.7  # measured (tools/ubench.cu, profiles/r1_ubench_fp64_dmma_smem_rmw.log)
+SM_CLOCK_HZ = 1.965e9
+N_SMS = 148
 
 
 def parse():
@@ -46,6 +62,10 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=100_000, help="rows of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--configs", default="auto",
+                    help="other BASELINE configurations measured into the `configs` block: comma list of "
+                         "c1,c3,s20,c4,c5,c2strong, 'none', or 'auto' (all at N=1; c3,c4,c2strong at N>1)")
+    ap.add_argument("--config-scale", type=float, default=1.0, help="scale the rows of the `configs` block (tests)")
     return ap.parse_args()
 
 
@@ -69,23 +89,75 @@ def _config(world, rows):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm, timed per PIRLS iteration
+# CPU arm: the unmodified reference (pyGAM from baseline/_ref), timed per PIRLS iteration with a CallBack
+# (pygam.py:838-840); the oracle port only if the reference cannot be imported
 # ---------------------------------------------------------------------------------------------
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return {f"{p.get('internal_api')}": p.get("num_threads") for p in threadpool_info()}
+    except Exception:
+        return {}
+
+
+def import_reference():
+    """pyGAM as installed by `pip install --no-index --no-deps --target baseline/_ref /root/reference`,
+    else the read-only checkout (authoring container only); None when neither is there"""
+    for path in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(path, "pygam")):
+            for p in (os.path.join(ROOT, "baseline", "stub"), path):
+                if p not in sys.path:
+                    sys.path.insert(0, p)
+            try:
+                import pygam  # noqa: F401
+
+                return pygam, path
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write(f"reference at {path} not importable: {e}\n")
+    return None, None
+
+
 def cpu_iterations(n_rows, steps, warmup):
     import cases
-    from oracle import gam_oracle as orc
 
     X, y = cases.data_c2(n_rows, seed=1234)
-    case = dict(cases.FIT_CASES["c2_logistic"])
-    # tol = 0 never stops early: exactly warmup + steps + 1 iterations, stamped at loop start
-    case["model_kwargs"] = dict(max_iter=warmup + steps + 1, tol=0.0)
-    t0 = time.perf_counter()
-    res = orc.fit(case, X, y, timer=time.perf_counter)
-    stamps = np.asarray(res["logs"]["time"])
+    pygam, where = import_reference()
+    if pygam is not None:
+        from pygam.callbacks import CallBack
+
+        class Stamp(CallBack):
+            def __init__(self):
+                super().__init__(name="stamp")
+
+            def on_loop_start(self, gam):
+                return time.perf_counter()
+
+        terms = pygam.s(0, n_splines=N_SPLINES)
+        for j in range(1, N_FEATURES):
+            terms = terms + pygam.s(j, n_splines=N_SPLINES)
+        # tol = 0 never stops early: exactly warmup + steps + 1 iterations, stamped at loop start
+        gam = pygam.LogisticGAM(terms, max_iter=warmup + steps + 1, tol=0.0, callbacks=["deviance", "diffs", Stamp()])
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            gam.fit(X, y)
+        stamps = np.asarray(gam.logs_["stamp"])
+        kind = "reference"
+        what = f"unmodified pyGAM {getattr(pygam, '__version__', '')} ({os.path.relpath(where, ROOT) if where.startswith(ROOT) else where})"
+    else:
+        from oracle import gam_oracle as orc
+
+        case = dict(cases.FIT_CASES["c2_logistic"])
+        case["model_kwargs"] = dict(max_iter=warmup + steps + 1, tol=0.0)
+        t0 = time.perf_counter()
+        res = orc.fit(case, X, y, timer=time.perf_counter)
+        stamps = np.asarray(res["logs"]["time"])
+        kind = "port"
+        what = "oracle port of the reference PIRLS (the reference could not be imported)"
     setup = stamps[0] - t0
     per_iter = np.diff(stamps)[warmup:warmup + steps]
     return dict(ms_per_step=float(np.mean(per_iter) * 1e3), rows_per_s=float(n_rows / np.mean(per_iter)),
-                setup_s=float(setup), iters=len(per_iter))
+                setup_s=float(setup), iters=len(per_iter), kind=kind, what=what, blas=blas_threads())
 
 
 def run_reference(args, rank, world):
@@ -93,15 +165,21 @@ def run_reference(args, rank, world):
         return
     steps, warmup = args.steps, args.warmup
     r = cpu_iterations(args.cpu_rows, steps, warmup)
-    cores = os.cpu_count()
-    sample = (f"{args.cpu_rows} of the workload's rows (seeded like the GPU arm), {steps} timed PIRLS iterations "
-              f"after {warmup} warm-up; model-matrix setup {r['setup_s']:.1f}s excluded")
+    sample = (f"{r['what']}: {args.cpu_rows} rows of the workload (seeded like the GPU arm), {steps} timed PIRLS iterations "
+              f"after {warmup} warm-up, stamped by a CallBack at on_loop_start; model-matrix setup {r['setup_s']:.1f}s "
+              f"excluded; BLAS threads {r['blas']}, os.cpu_count() {_CORES}")
+    cfg = _config(1, args.cpu_rows)
+    cfg["workload"] = ("BASELINE configs[1] shape: LogisticGAM, 10 s() terms, n_splines=25 (m=251, k=41), "
+                       f"{args.cpu_rows} synthetic rows on the host (the reference needs 15 KB of RAM per row: the GPU arm's "
+                       f"{args.rows} rows per GPU do not fit any host), one PIRLS iteration per step")
+    cfg["parallelism"] = f"single process, {_CORES} BLAS threads"
+    cfg["gpu_arm_rows_per_gpu"] = args.rows
     line = {"metric": "rows/sec per PIRLS iteration", "value": r["rows_per_s"], "unit": "rows/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config(args.gpus, args.rows),
-            "cpu_baseline": {"value": r["rows_per_s"], "unit": "rows/s", "cores": cores, "kind": "port",
-                             "sample": sample},
+            "config": cfg,
+            "cpu_baseline": {"value": r["rows_per_s"], "unit": "rows/s", "cores": _CORES, "kind": r["kind"],
+                             "blas_threads": r["blas"], "sample": sample},
             "e2e": {"value": r["rows_per_s"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line)
@@ -150,6 +228,241 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def hbm_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s"
+
+
+# ---- the other BASELINE configurations -----------------------------------------------------------------------------
+def _terms(pg, n_s, te_pairs=(), n_splines=None):
+    terms = None
+    for j in range(n_s):
+        t = pg.s(j) if n_splines is None else pg.s(j, n_splines=n_splines)
+        terms = t if terms is None else terms + t
+    for a, b in te_pairs:
+        terms = terms + pg.te(a, b)
+    return terms
+
+
+def synth(torch, dev, name, n, seed):
+    """SURVEY.md 8d generators, on the device (feature-major)"""
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    two_pi = 2 * np.pi
+    if name in ("c3", "s20"):
+        F = 24 if name == "c3" else 20
+        Xt = torch.rand((F, n), dtype=torch.float64, device=dev, generator=gen)
+        eta = torch.full((n,), 0.5, dtype=torch.float64, device=dev)
+        for j in range(20):
+            eta += 0.075 * torch.sin(two_pi * Xt[j])
+        if name == "c3":
+            eta += 0.5 * Xt[20] * Xt[21] - 0.5 * Xt[22] * Xt[23]
+        y = torch.poisson(torch.exp(eta), generator=gen)
+    elif name in ("c4",):
+        Xt = torch.rand((3, n), dtype=torch.float64, device=dev, generator=gen)
+        y = torch.sin(two_pi * Xt[0]) + Xt[1] ** 2 + 0.5 * torch.cos(2 * two_pi * Xt[2])
+        y += 0.3 * torch.randn(n, dtype=torch.float64, device=dev, generator=gen)
+    elif name == "c5":
+        Xt = torch.rand((4, n), dtype=torch.float64, device=dev, generator=gen)
+        y = torch.sqrt(Xt[0]) + torch.sin(3 * Xt[1]) + Xt[2] ** 2 + 0.2 * torch.cos(6 * Xt[3])
+        y += 0.3 * torch.randn(n, dtype=torch.float64, device=dev, generator=gen)
+    else:  # c2
+        Xt = torch.rand((N_FEATURES, n), dtype=torch.float64, device=dev, generator=gen)
+        eta = torch.zeros(n, dtype=torch.float64, device=dev)
+        for j in range(N_FEATURES):
+            eta += 0.5 * torch.sin(two_pi * (j + 1) * Xt[j] / 3.0)
+        y = (torch.rand(n, dtype=torch.float64, device=dev, generator=gen) < torch.sigmoid(eta)).double()
+    return Xt, y
+
+
+def make_model(pg, name):
+    if name == "c3":
+        return pg.PoissonGAM(_terms(pg, 20, [(20, 21), (22, 23)])), dict(model="PoissonGAM", terms="c3")
+    if name == "s20":
+        return pg.PoissonGAM(_terms(pg, 20)), dict(model="PoissonGAM", terms="s20")
+    if name == "c4":
+        return pg.LinearGAM(_terms(pg, 3)), dict(model="LinearGAM", terms="c4")
+    if name == "c5":
+        t = (pg.s(0, constraints="monotonic_inc") + pg.s(1) + pg.s(2, constraints="monotonic_inc")
+             + pg.s(3, constraints="convex"))
+        return pg.ExpectileGAM(t, expectile=0.9), dict(model="ExpectileGAM", terms="c5")
+    if name == "c1":
+        return pg.LinearGAM(pg.s(0) + pg.s(1) + pg.f(2)), dict(model="LinearGAM", terms="c1")
+    return pg.LogisticGAM(_terms(pg, N_FEATURES, n_splines=N_SPLINES)), dict(model="LogisticGAM", terms="c2")
+
+
+def oracle_case(name):
+    import cases
+
+    s, te = cases.s, cases.te
+    if name == "c3":
+        return cases.FIT_CASES["c3_poisson"]
+    if name == "s20":
+        return dict(model="PoissonGAM", terms=[s(j) for j in range(20)])
+    if name == "c4":
+        return cases.FIT_CASES["c4_linear"]
+    if name == "c5":
+        return cases.FIT_CASES["c5_expectile"]
+    if name == "c1":
+        return cases.FIT_CASES["c1_wage"]
+    del te
+    return cases.FIT_CASES["c2_logistic"]
+
+
+WORK = {  # name: (rows per GPU, features, non-zeros per model-matrix row, parity prefix, description)
+    "c3": (125_000_000, 24, 113, 10_000, "BASELINE configs[2]: PoissonGAM, 20 s() + 2 te() (m=601, k=113)"),
+    "s20": (125_000_000, 20, 81, 10_000, "north star shape: PoissonGAM, 20 s() terms (m=401, k=81)"),
+    "c4": (50_000_000, 3, 13, 100_000, "BASELINE configs[3]: LinearGAM gridsearch over an 11^3 lam grid on 3 s() terms (m=61)"),
+    "c5": (100_000_000, 4, 17, 20_000, "BASELINE configs[4]: ExpectileGAM(0.9), monotonic / convex constrained s() terms (m=81)"),
+    "c1": (3000, 3, 10, 3000, "BASELINE configs[0]: LinearGAM(s(0)+s(1)+f(2)) on the wage data (m=46)"),
+}
+
+
+def parity_prefix(pg, name, Xh, yh, quiet):
+    """the engine and the CPU oracle on the same row prefix -- identical iteration count, GCV / UBRE
+    to 1e-10 (constrained: 1e-7), edof"""
+    from oracle import gam_oracle as orc
+
+    gam, _ = make_model(pg, name)
+    t0 = time.perf_counter()
+    with quiet():
+        gam.fit(Xh, yh)
+    t_gpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with quiet(), np.errstate(all="ignore"):
+        ref = orc.fit(oracle_case(name), Xh, yh)
+    t_cpu = time.perf_counter() - t0
+    st, rst = gam.statistics_, ref["statistics"]
+    obj = "UBRE" if gam.distribution._known_scale else "GCV"
+    rel = abs(st[obj] - rst[obj]) / abs(rst[obj])
+    tol = 1e-7 if name == "c5" else 1e-10
+    ok = (len(gam.logs_["diffs"]) == len(ref["logs"]["diffs"])) and rel <= tol and abs(st["edof"] - rst["edof"]) <= 1e-6 * rst["edof"]
+    return {"rows": int(len(yh)), "ok": bool(ok), "iterations": [len(gam.logs_["diffs"]), len(ref["logs"]["diffs"])],
+            obj + "_rel_diff": float(rel), "edof": [float(st["edof"]), float(rst["edof"])],
+            "oracle_fit_s": t_cpu, "engine_fit_s_incl_upload": t_gpu}
+
+
+def run_config(name, args, torch, dist, pg, dev, rank, world, hbm_peak):
+    """one entry of the `configs` block: full fit (or grid search) on device-resident rows, the steady-state
+    iteration against both roofs, a parity prefix"""
+    from pygam_b200 import _lib
+    from pygam_b200.engine import DeviceData
+
+    rows, F, k, n_ref, desc = WORK[name]
+    n = rows if name == "c1" else max(20_000, int(rows * args.config_scale))
+
+    def quiet():
+        return contextlib.redirect_stdout(io.StringIO())
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {"workload": desc, "rows_per_gpu": n, "global_rows": n * world}
+    if name == "c1":
+        w = np.load(os.path.join(ROOT, "tests", "golden", "wage_xy.npz"))
+        Xh, yh = w["X"], w["y"]
+        data = DeviceData.from_host(Xh, yh)
+        if world > 1:
+            return None
+    else:
+        free, _ = torch.cuda.mem_get_info()
+        need = n * (8 * F + 8) * 1.3 + n * (9 * F + 16 + 2.2 * (F * (F + 1) // 2 if name != "c3" else 260))
+        if need > 0.92 * free:
+            n = int(n * 0.92 * free / need) // 1_000_000 * 1_000_000
+            out["rows_per_gpu"], out["global_rows"] = n, n * world
+            out["note"] = "rows reduced to fit the free HBM"
+        Xt, y = synth(torch, dev, name, n, 4321 + 17 * rank)
+        data = DeviceData(Xt, y)
+        Xh = Xt[:, :n_ref].T.contiguous().cpu().numpy()
+        yh = y[:n_ref].cpu().numpy()
+    bytes_row = 8 * F + 8
+    fma_row = k * (k + 1) // 2 + k
+    gam, _ = make_model(pg, name)
+    sync()
+    t0 = time.perf_counter()
+    if name == "c4":
+        with quiet():
+            gam.gridsearch(data, lam=[np.logspace(-3, 3, 11)] * 3)
+        sync()
+        out["gridsearch_wall_s"] = time.perf_counter() - t0
+        out["candidates"] = 1331
+        out["how"] = ("one Gram pass over the rows, one O(k) pass for the moments of y, 1331 m x m solves as one batch "
+                      f"split over {world} rank(s), scores from quadratic forms (GAM._gridsearch_linear_batched)")
+        out["best_lam"] = [float(v) for v in np.ravel(gam.lam)]
+        out["best_GCV"] = float(gam.statistics_["GCV"])
+    else:
+        with quiet():
+            gam.fit(data)
+        sync()
+        out["fit_wall_s"] = time.perf_counter() - t0
+        out["iterations"] = len(gam.logs_["diffs"])
+        out["converged"] = bool(gam.logs_["diffs"][-1] < gam.tol)
+        obj = "UBRE" if gam.distribution._known_scale else "GCV"
+        out[obj] = float(gam.statistics_[obj])
+        out["edof"] = float(gam.statistics_["edof"])
+    # steady-state iteration: Gram pass (+ all-reduce) + solve at the fitted coefficients, CUDA events
+    eng = gam._engine
+    coef = np.array(gam.coef_)
+    reps = 3
+    for _ in range(2):
+        eng.gram_pass(data, coef)
+        eng.solve(coef_prev=coef)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(reps):
+        eng.gram_pass(data, coef)
+        eng.solve(coef_prev=coef)
+    e1.record()
+    sync()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_iter = float(ms.item())
+    _lib.check(eng.lib.pgb_gram_timing(eng.handle, 1), "timing")
+    eng.gram_pass(data, coef)
+    f, r, t = C.c_float(), C.c_float(), C.c_float()
+    _lib.check(eng.lib.pgb_gram_last_ms(eng.handle, C.byref(r), C.byref(f), C.byref(t)), "ms")
+    _lib.check(eng.lib.pgb_gram_timing(eng.handle, 0), "timing")
+    gram_ms = t.value
+    out.update({
+        "ms_per_iteration": ms_iter, "rows_per_s": n * world / (ms_iter * 1e-3), "gram_pass_ms": gram_ms,
+        "algorithmic_bytes_per_row": bytes_row, "algorithmic_fma_per_row": fma_row,
+        "hbm_frac": n * bytes_row / (gram_ms * 1e-3) / 1e9 / hbm_peak,
+        "fp64_fma_per_clk_per_sm": n * fma_row / (gram_ms * 1e-3) / (N_SMS * SM_CLOCK_HZ),
+        "fp64_frac": n * fma_row / (gram_ms * 1e-3) / (N_SMS * SM_CLOCK_HZ) / FP64_FMA_PER_CLK_SM,
+        "gram_path": "cell-owned" if eng.info.cell_roles > 0 else "general (shared-memory accumulation)"})
+    # the O(k) passes of this shape against the HBM roof
+    if name != "c1":
+        for _ in range(2):
+            eng.stats_pass(data, coef)
+        sync()
+        e0.record()
+        for _ in range(5):
+            eng.stats_pass(data, coef, reduce=False)
+        e1.record()
+        sync()
+        st_ms = e0.elapsed_time(e1) / 5
+        out["statistics_pass_ms"] = st_ms
+        out["statistics_pass_hbm_frac"] = n * bytes_row / (st_ms * 1e-3) / 1e9 / hbm_peak
+    del data
+    if name != "c1":
+        del Xt, y
+    gam._engine = None
+    eng = None
+    torch.cuda.empty_cache()
+    if rank == 0:
+        try:
+            out["parity_prefix"] = parity_prefix(pg, name, Xh, yh, quiet)
+        except Exception as e:  # noqa: BLE001
+            out["parity_prefix"] = {"ok": False, "error": repr(e)[:200]}
+    sync()
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -164,27 +477,15 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     n = args.rows
     lib = _lib.load()
+    hbm_peak, peak_source = hbm_peak_gbs()
 
     # synthetic shard, generated on the device
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    Xt = torch.rand((N_FEATURES, n), dtype=torch.float64, device=dev, generator=gen)
-    eta = torch.zeros(n, dtype=torch.float64, device=dev)
-    for j in range(N_FEATURES):
-        eta += 0.5 * torch.sin(2 * np.pi * (j + 1) * Xt[j] / 3.0)
-    y = (torch.rand(n, dtype=torch.float64, device=dev, generator=gen) < torch.sigmoid(eta)).double()
-    del eta
+    Xt, y = synth(torch, dev, "c2", n, 1234 + rank)
     data = DeviceData(Xt, y)
-
-    terms = None
-    for j in range(N_FEATURES):
-        t = pg.s(j, n_splines=N_SPLINES)
-        terms = t if terms is None else terms + t
-    gam = pg.LogisticGAM(terms, max_iter=1)
+    gam, _ = make_model(pg, "c2")
+    gam.max_iter = 1
     # compile the model (edge knots from the global column extrema) and get the initial estimate
     # through the public API: one PIRLS iteration
-    import contextlib
-    import io
-
     with contextlib.redirect_stdout(io.StringIO()):
         gam.fit(data)
     eng = gam._engine
@@ -212,7 +513,7 @@ def run_b200(args, rank, world, local_rank):
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         p0.record()
-        _lib.check(lib.pgb_gram_prepare(eng.handle, C.c_void_p(Xt.data_ptr()), n, n, C.c_void_p(ws.data_ptr()),
+        _lib.check(lib.pgb_gram_prepare(eng.handle, C.c_void_p(Xt.data_ptr()), n, data.ld, C.c_void_p(ws.data_ptr()),
                                         ws.numel() * 8, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pgb_gram_prepare")
         p1.record()
         torch.cuda.synchronize()
@@ -270,7 +571,7 @@ def run_b200(args, rank, world, local_rank):
     cur = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def _stats_call(yy, mu_out):
-        _lib.check(lib.pgb_stats_pass(eng.handle, C.c_void_p(Xt.data_ptr()), n, n, C.c_void_p(yy.data_ptr() if yy is not None else 0),
+        _lib.check(lib.pgb_stats_pass(eng.handle, C.c_void_p(Xt.data_ptr()), n, data.ld, C.c_void_p(yy.data_ptr() if yy is not None else 0),
                                       C.c_void_p(0), C.c_void_p(eng.beta.data_ptr()), -1.0, 0.0, 0,
                                       C.c_void_p(eng.stat_scalars.data_ptr()), C.c_void_p(0),
                                       C.c_void_p(mu_out.data_ptr() if mu_out is not None else 0), C.c_void_p(st_ws.data_ptr()),
@@ -316,49 +617,83 @@ def run_b200(args, rank, world, local_rank):
         e2e = {"value": n * world / (e2e_ms * 1e-3), "unit": "rows/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
                "h2d_bytes_per_step": int(n * BYTES_PER_ROW + m * 8), "d2h_bytes_per_step": int(out_h.numel() * 8 + (m + 8) * 8),
                "api": "pgb_gram_pass_host (pinned host X, y -> chunked H2D on 2 streams overlapped with the Gram "
-                      "kernels) + all-reduce + pgb_solve, coefficients read back"}
-        del Xh, yh
+                      "kernels) + all-reduce + pgb_solve, coefficients read back; every step re-uploads the rows, which "
+                      "no fit does: e2e.fit below is the call a user makes",
+               "note_scaling": "N ranks stream N x 880 MB per step through one host: the host memory / PCIe root bandwidth "
+                               "(not NCCL, not the kernels) bounds this leg at N >= 4 (DESIGN.md 7)"}
+        # the call a user makes: numpy arrays in, fitted model out (upload once, prepare, k iterations, statistics)
+        if world == 1:
+            Xn = np.ascontiguousarray(Xh.numpy().T)  # (n, F) row-major, like any user's array
+            yn = yh.numpy().copy()
+            del Xh
+            fit_gam, _ = make_model(pg, "c2")
+            with contextlib.redirect_stdout(io.StringIO()):
+                make_model(pg, "c2")[0].fit(Xn[:200_000], yn[:200_000])  # warm-up of allocator / code paths
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fit_gam.fit(Xn, yn)
+                torch.cuda.synchronize()
+                fit_s = time.perf_counter() - t0
+            iters = len(fit_gam.logs_["diffs"])
+            e2e["fit"] = {"api": "LogisticGAM(10 x s(n_splines=25)).fit(X_numpy, y_numpy): host arrays -> coef_, statistics_",
+                          "rows": n, "wall_s": fit_s, "iterations": iters, "rows_per_s_per_iteration": n * iters / fit_s,
+                          "h2d_bytes": int(n * BYTES_PER_ROW), "UBRE": float(fit_gam.statistics_["UBRE"]),
+                          "edof": float(fit_gam.statistics_["edof"])}
+            del Xn, yn, fit_gam
+        else:
+            del Xh
+        del yh
+
+    del data, Xt, y
+    gam._engine = None
+    eng = None
+    torch.cuda.empty_cache()
+    # ---- the other BASELINE configurations ----
+    which = args.configs
+    if which == "auto":
+        which = "c1,c3,s20,c4,c5" if world == 1 else "c3,c4,c2strong"
+    configs = {}
+    for name in [w for w in which.split(",") if w and w != "none"]:
+        try:
+            if name == "c2strong":
+                configs[name] = strong_point(args, torch, dist, pg, dev, rank, world)
+            else:
+                res = run_config(name, args, torch, dist, pg, dev, rank, world, hbm_peak)
+                if res is not None:
+                    configs[name] = res
+        except Exception as e:  # noqa: BLE001
+            configs[name] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    gram_ms = gram_pass_ms  # every kernel of the Gram pass (prepass/records, accumulation, reductions)
+    gram_ms = gram_pass_ms  # every kernel of the Gram pass (prepass, cell sums, reductions)
     achieved = n * BYTES_PER_ROW / (gram_ms * 1e-3) / 1e9
-    fma_per_clk_sm = n * FMA_PER_ROW / (accum * 1e-3) / (148 * 1.965e9)
-    cells = eng.info.cell_roles > 0
+    fma_per_clk_sm = n * FMA_PER_ROW / (accum * 1e-3) / (N_SMS * SM_CLOCK_HZ)
     traffic = None
-    try:  # dram bytes of the dominant kernel per launch from the committed ncu --set full capture, scaled to n rows
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_gram_cells_traffic.json")))
-        traffic = prof["dram_bytes_per_row"] * n
-    except Exception:
-        pass
-    if cells:
-        kernels = "gram_prepass_kernel + gram_cells_kernel (the Gram pass of one PIRLS iteration)"
-        second = {"name": "fp64_pipe", "algorithmic_fma_per_row": FMA_PER_ROW, "achieved_fma_per_clk_per_sm": fma_per_clk_sm,
-                  "measured_peak_fma_per_clk_per_sm": 62.7, "frac": fma_per_clk_sm / 62.7,
-                  "note": "gram_cells_kernel: a thread owns a knot cell of a term pair and sums the 4 x 4 outer products of "
-                          "the cell's rows in registers (row order by cell prepared once per fit; the streaming path counting-sorts in shared memory); the useful work is "
-                          "902 fp64 FMA per row at 88 algorithmic bytes per row = 20 flop/B, so the fp64 pipe (62.7 "
-                          "FMA/clk/SM measured, tools/ubench.cu), not HBM, bounds the pass (DESIGN.md section 4)"}
-    else:
-        kernels = "gram_records_kernel + gram_accum_kernel (the Gram pass of one PIRLS iteration)"
-        second = {"name": "shared_memory_rmw", "algorithmic_fma_per_row": FMA_PER_ROW,
-                  "achieved_fma_per_clk_per_sm": fma_per_clk_sm, "measured_peak_fma_per_clk_per_sm": 7.7,
-                  "frac": fma_per_clk_sm / 7.7,
-                  "note": "general path: products scattered into G held in shared memory, 16 B of read-modify-write per FMA"}
+    traffic_src = None
+    for fn in ("r2_ncu_gram_cells_traffic.json", "r1_ncu_gram_cells_traffic.json"):
+        try:  # dram bytes of the two kernels per launch from the committed ncu --set full capture, scaled to n rows
+            prof = json.load(open(os.path.join(ROOT, "profiles", fn)))
+            traffic, traffic_src = prof["dram_bytes_per_row"] * n, "profiles/" + fn
+            break
+        except Exception:
+            pass
+    kernels = ("gram_prepass_planned_kernel + gram_cells_sorted_kernel<512, 2> (the Gram pass of one PIRLS iteration of a "
+               "prepared shard)")
+    second = {"name": "fp64_pipe", "algorithmic_fma_per_row": FMA_PER_ROW, "achieved_fma_per_clk_per_sm": fma_per_clk_sm,
+              "measured_peak_fma_per_clk_per_sm": FP64_FMA_PER_CLK_SM, "frac": fma_per_clk_sm / FP64_FMA_PER_CLK_SM,
+              "note": "gram_cells_sorted_kernel: a thread owns a knot cell of a term pair and sums the moments of the "
+                      "cell's rows in registers (row order by cell prepared once per fit); the useful work is 902 fp64 FMA "
+                      "per row at 88 algorithmic bytes per row = 20 flop/B, so the fp64 pipe (62.7 FMA/clk/SM measured, "
+                      "tools/ubench.cu), not HBM, bounds the pass (DESIGN.md section 4)"}
     roofline = {"kernel": kernels, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
-                "traffic": traffic, "kernel_ms": gram_ms, "prepass_kernel_ms": records, "accum_kernel_ms": accum,
-                "kernel_share_of_step": gram_ms / ms_per_step, "algorithmic_bytes_per_row": BYTES_PER_ROW,
-                "governing": second,
+                "frac": achieved / hbm_peak, "peak_source": peak_source,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": gram_ms, "prepass_kernel_ms": records,
+                "accum_kernel_ms": accum, "kernel_share_of_step": gram_ms / ms_per_step,
+                "algorithmic_bytes_per_row": BYTES_PER_ROW, "governing": second,
                 "ok_passes": {"note": "the O(k)-per-row passes of the path, same shard and coefficients, CUDA events over 10 "
                                       "launches each: statistics sums (stats_pass_kernel, reads 8F+8 B per row) and predict_mu "
                                       "(reads 8F, writes 8 B per row)",
@@ -374,15 +709,55 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
     if e2e is not None:
         line["e2e"] = e2e
+    if configs:
+        line["configs"] = configs
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_iterations(args.cpu_rows, 3, 1)
-        line["cpu_baseline"] = {"value": r["rows_per_s"], "unit": "rows/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"oracle port of the reference PIRLS (sparse model matrix + dense QR + SVD) "
-                                          f"on {args.cpu_rows} rows of the same synthetic workload, 3 timed iterations "
-                                          f"after 1 warm-up, {r['ms_per_step']:.0f} ms per iteration"}
+        line["cpu_baseline"] = {"value": r["rows_per_s"], "unit": "rows/s", "cores": _CORES, "kind": r["kind"],
+                                "blas_threads": r["blas"],
+                                "sample": f"{r['what']} on {args.cpu_rows} rows of the same synthetic workload, 3 timed "
+                                          f"iterations after 1 warm-up (CallBack stamps), {r['ms_per_step']:.0f} ms per "
+                                          f"iteration, setup {r['setup_s']:.1f}s excluded"}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_point(args, torch, dist, pg, dev, rank, world):
+    """config 2 with a FIXED total of 1e7 rows over the ranks: what the fixed cost per iteration (solve front, all-reduce,
+    host synchronisation) does to a strong-scaled run"""
+    from pygam_b200.engine import DeviceData
+
+    total = int(10_000_000 * args.config_scale)
+    n = total // world
+    Xt, y = synth(torch, dev, "c2", n, 999 + rank)
+    data = DeviceData(Xt, y)
+    gam, _ = make_model(pg, "c2")
+    gam.max_iter = 2
+    with contextlib.redirect_stdout(io.StringIO()):
+        gam.fit(data)
+    eng, coef = gam._engine, np.array(gam.coef_)
+    for _ in range(3):
+        eng.gram_pass(data, coef)
+        eng.solve(coef_prev=coef)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        eng.gram_pass(data, coef)
+        eng.solve(coef_prev=coef)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    del data, Xt, y
+    gam._engine = None
+    torch.cuda.empty_cache()
+    return {"workload": "config 2, strong scaling: 1e7 rows in total", "global_rows": n * world, "rows_per_gpu": n,
+            "ms_per_iteration": float(ms.item()), "rows_per_s": n * world / (float(ms.item()) * 1e-3)}
 
 
 def _emit(line):

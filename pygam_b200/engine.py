@@ -66,7 +66,9 @@ class DeviceData:
         ld = (n + 15) // 16 * 16
         buf = torch.zeros((F, ld), dtype=torch.float64, device=device)
         Xt = buf[:, :n]
-        Xt.copy_(torch.from_numpy(np.ascontiguousarray(X.T, dtype=np.float64)))
+        # the rows go up as they are (row-major) and are transposed on the device: a host-side transpose of a
+        # 1e7 x 10 array costs more than the whole fit
+        Xt.copy_(torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(device).T)
         yt = None if y is None else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64).ravel()).to(device)
         wt = None if w is None else torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32).ravel()).to(device)
         return cls(Xt, yt, wt)
