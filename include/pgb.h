@@ -247,6 +247,10 @@ int pgb_solve_truncated(int32_t m, int32_t rank, const double* G, const double* 
 int64_t pgb_chol_ws_bytes(int32_t m);
 int pgb_chol_check(int32_t m, const double* A, int32_t* info_out, void* ws, int64_t ws_bytes,
                    void* stream);
+/* the same test for nb matrices at once (the candidates of a grid search, pygam.py:2042-2070): A = nb x m x m,
+ * info_out = nb int32, ws >= nb * m * m doubles (only used when a matrix does not fit shared memory) */
+int pgb_chol_check_batch(int32_t m, int32_t nb, const double* A, int32_t* info_out, void* ws, int64_t ws_bytes,
+                         void* stream);
 
 /* ---- host-buffer entry points (end-to-end path) -----------------------------------------
  * Same as pgb_gram_pass but X, y, w live in (pinned) HOST memory, row-shard by row-shard:

@@ -102,6 +102,7 @@ SYMBOLS = {
     "pgb_solve_truncated": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P]),
     "pgb_chol_ws_bytes": (C.c_int64, [C.c_int32]),
     "pgb_chol_check": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, _P]),
+    "pgb_chol_check_batch": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P]),
     "pgb_gram_pass_host": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, C.c_int64]),
 }
 

@@ -708,13 +708,15 @@ chol_check_kernel(int m, const double* __restrict__ Ain, int* __restrict__ info,
   double* D = sm;
   double* P = D + kNB * kLD;
   int* flag = reinterpret_cast<int*>(P + (size_t)m * kLD);
-  double* A = use_smem ? (P + (size_t)m * kLD + 2) : ws;
+  const size_t sys = blockIdx.x;  // one CTA per matrix of a batch
+  double* A = use_smem ? (P + (size_t)m * kLD + 2) : ws + sys * (size_t)m * m;
+  Ain += sys * (size_t)m * m;
   if (threadIdx.x == 0) *flag = 0;
   for (int e = threadIdx.x; e < m * m; e += blockDim.x) A[e] = Ain[e];
   __syncthreads();
   cholesky_lower(A, m, D, P, flag);
   __syncthreads();
-  if (threadIdx.x == 0) *info = *flag;
+  if (threadIdx.x == 0) info[sys] = *flag;
 }
 
 
@@ -919,6 +921,23 @@ extern "C" int pgb_solve_truncated(int32_t m, int32_t rank, const double* G, con
 }
 
 extern "C" int64_t pgb_chol_ws_bytes(int32_t m) { return (int64_t)m * m * 8 + 256; }
+
+extern "C" int pgb_chol_check_batch(int32_t m, int32_t nb, const double* A, int32_t* info_out, void* ws, int64_t ws_bytes,
+                                    void* stream) {
+  if (m < 1 || nb < 1 || !A || !info_out) { pgb_set_error("pgb_chol_check: bad arguments"); return PGB_EINVAL; }
+  const size_t vec = ((size_t)kNB * kLD + (size_t)m * kLD + 2) * 8;
+  const bool in_smem = vec + (size_t)m * m * 8 <= kSolveSmemMax;
+  if (!in_smem && (!ws || ws_bytes < (int64_t)nb * m * m * 8)) {
+    pgb_set_error("pgb_chol_check: workspace too small");
+    return PGB_EINVAL;
+  }
+  PGB_CUDA(cudaFuncSetAttribute(chol_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax));
+  chol_check_kernel<<<nb, kSolveThreads, vec + (in_smem ? (size_t)m * m * 8 : 0), (cudaStream_t)stream>>>(
+      m, A, info_out, (double*)ws, in_smem ? 1 : 0);
+  pgb_count_launch(1);
+  PGB_CUDA(cudaGetLastError());
+  return PGB_OK;
+}
 
 extern "C" int pgb_chol_check(int32_t m, const double* A, int32_t* info_out, void* ws, int64_t ws_bytes,
                               void* stream) {

@@ -370,6 +370,23 @@ class Engine:
                                            _stream()), "pgb_chol_check")
         return int(self._chol_info.item()) == 0
 
+    def chol_ok_batch(self, A):
+        """utils.cholesky's test (utils.py:77-91) for K matrices at once: (K, m, m) host array -> bool (K,)"""
+        m = self.m
+        A = np.ascontiguousarray(A, dtype=np.float64).reshape(-1, m, m)
+        K = A.shape[0]
+        ok = np.zeros(K, dtype=bool)
+        chunk = max(1, min(K, (1 << 28) // (m * m * 8)))
+        for k0 in range(0, K, chunk):
+            nb = min(chunk, K - k0)
+            Ad = torch.from_numpy(A[k0:k0 + nb].reshape(-1)).to(self.device)
+            info = torch.zeros(nb, dtype=torch.int32, device=self.device)
+            ws = torch.empty(nb * m * m, dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.pgb_chol_check_batch(m, nb, _ptr(Ad), _ptr(info), _ptr(ws), ws.numel() * 8, _stream()),
+                       "pgb_chol_check_batch")
+            ok[k0:k0 + nb] = info.cpu().numpy() == 0
+        return ok
+
     def solve(self, coef_prev=None, want_edof=False, want_cov=False, out=None):
         """beta = (G + EtE)^-1 r with the Gram data currently in self.out; returns host dict"""
         m = self.m

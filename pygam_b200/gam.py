@@ -63,6 +63,25 @@ PLURAL = ["feature", "dtype", "lam", "n_splines", "spline_order", "constraints",
           "edge_knots_"]
 
 
+class _LazyStats(dict):
+    """statistics_ of a grid-search candidate.  'p_values' costs a pseudo-inverse per term (pygam.py:1241-1295) and
+    is read for the best model and by summary(): it is computed on first access instead of 1331 times."""
+
+    def __init__(self, owner, *a, **kw):
+        super().__init__(*a, **kw)
+        self._owner = owner
+
+    def __missing__(self, key):
+        if key == "p_values":
+            self[key] = self._owner._estimate_p_values()
+            return self[key]
+        raise KeyError(key)
+
+    def __reduce__(self):  # pickles / deep-copies as a plain dict with everything computed
+        self["p_values"]
+        return (dict, (dict(self),))
+
+
 def _flatten(v):
     out = []
     for x in v:
@@ -301,6 +320,21 @@ class GAM:
                 new.__dict__[k] = v  # device state is shared, never copied
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def _clone_for_candidate(self):
+        """what gridsearch's deepcopy(self) (pygam.py:2045) amounts to for a candidate that only changes lam:
+        terms, distribution and logs are copied, the device state is shared, fitted statistics are not carried"""
+        new = self.__class__.__new__(self.__class__)
+        for k, v in self.__dict__.items():
+            if k in _DEVICE_KEYS or k == "link":
+                new.__dict__[k] = v
+            elif k == "statistics_":
+                continue
+            elif k in ("terms", "distribution", "callbacks", "_pending_plural", "logs_", "coef_"):
+                new.__dict__[k] = copy.deepcopy(v)
+            else:
+                new.__dict__[k] = v
         return new
 
     def __getstate__(self):
@@ -833,7 +867,7 @@ class GAM:
         if keep_best:
             for k, v in best_model.__dict__.items():
                 if k not in _DEVICE_KEYS:
-                    self.__dict__[k] = copy.deepcopy(v)
+                    self.__dict__[k] = copy.deepcopy(v)  # a candidate's lazy statistics_ copies as a plain, complete dict
         if return_scores:
             return OrderedDict(zip(models, scores))
         return self
@@ -874,20 +908,46 @@ class GAM:
         def dev_at(beta):
             return yy - 2.0 * float(beta @ r) + float(beta @ (G @ beta))
 
-        # candidates in grid order: penalties and the reference's Cholesky test of S + P (a failing one is skipped)
+        # candidates in grid order.  The penalty is linear in lam (terms.py:307-349: sum_k lam_k P_k, block by block), so
+        # the K penalties are one tensor contraction of the lam grid with the unit components; the reference's
+        # Cholesky test of S + P (pygam.py:499-537) runs as one batch, its retry loop only for the failures
         S = np.eye(m) * np.sqrt(EPS)
-        cands = []
+        gams, lams, grids = [], [], []
         for param_grid in param_grid_list:
             try:
-                gam = copy.deepcopy(self)
+                gam = self._clone_for_candidate()
                 gam.set_params(**param_grid)
                 gam._validate_params()
-                Pn, Pr = gam.terms.build_penalties(split=True)
-                EtE = gam._cholesky_check(eng, S + (Pn + Pr))
-                cands.append((gam, EtE - Pn, Pn, param_grid))
+                gams.append(gam)
+                lams.append(np.asarray(_flatten(gam.terms.lam), dtype=np.float64))
+                grids.append(param_grid)
             except ValueError as error:
                 if self.verbose:
                     warnings.warn(str(error) + "\non model with params:\n" + str(param_grid) + "\nskipping...\n")
+        if not gams:
+            return True
+        L = np.stack(lams)
+        scratch = copy.deepcopy(self.terms)
+        unit_n, unit_r = [], []
+        for c in range(L.shape[1]):
+            e = np.zeros(L.shape[1])
+            e[c] = 1.0
+            scratch.lam = list(e)
+            pn, pr = scratch.build_penalties(split=True)
+            unit_n.append(pn)
+            unit_r.append(pr)
+        Pn_all = (L @ np.stack(unit_n).reshape(L.shape[1], m * m)).reshape(-1, m, m)
+        Pr_all = (L @ np.stack(unit_r).reshape(L.shape[1], m * m)).reshape(-1, m, m)
+        A_all = S[None] + (Pn_all + Pr_all)
+        ok = eng.chol_ok_batch(A_all)
+        cands = []
+        for k, gam in enumerate(gams):
+            try:
+                EtE = A_all[k] if ok[k] else gam._cholesky_check(eng, A_all[k])
+                cands.append((gam, EtE - Pn_all[k], Pn_all[k], grids[k]))
+            except ValueError as error:
+                if self.verbose:
+                    warnings.warn(str(error) + "\non model with params:\n" + str(grids[k]) + "\nskipping...\n")
         K = len(cands)
         if K == 0:
             return True
@@ -914,7 +974,7 @@ class GAM:
             if not (dev > 1e-7 * yy):
                 return False  # cancellation: take the data passes instead
             gam._n_global = n
-            gam.statistics_ = {"n_samples": n, "m_features": data.n_features}
+            gam.statistics_ = _LazyStats(gam, {"n_samples": n, "m_features": data.n_features})
             if not hasattr(gam, "logs_"):
                 gam.logs_ = {}
             for c in gam.callbacks:
@@ -966,7 +1026,8 @@ class GAM:
         st["GCV"], st["UBRE"] = self._estimate_GCV_UBRE(dev, n, edof)
         st["loglikelihood"] = ll
         st["deviance"] = dev / s2
-        st["p_values"] = self._estimate_p_values()
+        if not isinstance(st, _LazyStats):
+            st["p_values"] = self._estimate_p_values()
 
 
 class _ShapeOnly:

@@ -47,6 +47,16 @@ class Term:
         self.edge_knots_ = None
         self._validate()
 
+    def __deepcopy__(self, memo):
+        """terms hold scalars, strings, callables and (nested) lists of them, numpy arrays and -- te() -- marginal
+        terms: copy exactly that, without the generic deep-copy machinery (grid search copies the term list once
+        per candidate, pygam.py:2045)"""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = _copy_value(v, memo)
+        return new
+
     # -- argument normalisation (terms.py:148-210) --
     def _validate(self):
         if self.feature is not None:
@@ -163,6 +173,18 @@ class Term:
             total = total + constraint_l2 * np.eye(n)
             parts.append(constraint_l2 * np.eye(n))
         return split_by_constant(parts, n) if split else total
+
+
+def _copy_value(v, memo):
+    if isinstance(v, (list, tuple)):
+        return type(v)(_copy_value(x, memo) for x in v)
+    if isinstance(v, np.ndarray):
+        return v.copy()
+    if isinstance(v, Term):
+        return copy.deepcopy(v, memo)
+    if isinstance(v, dict):
+        return {k: _copy_value(x, memo) for k, x in v.items()}
+    return v  # int, float, str, bool, None, callables (penalty / constraint functions)
 
 
 def split_by_constant(parts, n):
@@ -356,6 +378,13 @@ class TensorTerm(Term):
         self.dtype = "numerical"
         if by is not None and not (isinstance(by, (int, np.integer)) and by >= 0):
             raise ValueError(f"by must be an integer >= 0, but found {by}")
+
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__dict__.update({k: v for k, v in self.__dict__.items() if k != "_terms"})
+        new._terms = [copy.deepcopy(t, memo) for t in self._terms]
+        return new
 
     def __len__(self):
         return len(self._terms)

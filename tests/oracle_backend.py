@@ -170,6 +170,9 @@ class OracleEngine:
         except scipy.linalg.LinAlgError:
             return False
 
+    def chol_ok_batch(self, A):
+        return np.array([self.chol_ok(a) for a in A], dtype=bool)
+
     def solve(self, coef_prev=None, want_edof=False, want_cov=False):
         m = self.m
         o = self.out.numpy()
