@@ -358,6 +358,13 @@ class Engine:
                                               _ptr(self.hv), _ptr(self.tau), self.p, _ptr(self.A0), _ptr(self._prep_ws),
                                               self._prep_ws.numel() * 8, _stream()), "pgb_solve_prepare")
 
+    def penalty_host(self):
+        """the penalty of the last set_penalty, E^T E = S + P (+ C), as an (m, m) host array"""
+        E = self.EtE.view(self.m, self.m).cpu().numpy().copy()
+        if self._has_null_part:
+            E += self.EtE_null.view(self.m, self.m).cpu().numpy()
+        return E
+
     def chol_ok(self, A):
         """True when A (host, m x m) has a Cholesky factor: utils.cholesky (utils.py:77-91)"""
         m = self.m

@@ -64,22 +64,48 @@ PLURAL = ["feature", "dtype", "lam", "n_splines", "spline_order", "constraints",
 
 
 class _LazyStats(dict):
-    """statistics_ of a grid-search candidate.  'p_values' costs a pseudo-inverse per term (pygam.py:1241-1295) and
-    is read for the best model and by summary(): it is computed on first access instead of 1331 times."""
+    """statistics_ with entries that are computed on first access: 'edof_per_coef' (an m x m factorisation on the
+    host, only summary() reads it) and, for grid-search candidates, 'p_values' (a pseudo-inverse per term,
+    pygam.py:1241-1295, read for the best model and by summary())."""
 
-    def __init__(self, owner, *a, **kw):
+    def __init__(self, owner, *a, lazy=("edof_per_coef",), **kw):
         super().__init__(*a, **kw)
         self._owner = owner
+        self._lazy = set(lazy)
+        self._ctx = None  # (G, E^T E) on the host, for edof_per_coef
 
     def __missing__(self, key):
-        if key == "p_values":
-            self[key] = self._owner._estimate_p_values()
+        if key in self._lazy:
+            if key == "p_values":
+                self[key] = self._owner._estimate_p_values()
+            else:
+                self[key] = self._owner._estimate_edof_per_coef(self._ctx)
+                self._ctx = None
             return self[key]
         raise KeyError(key)
 
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def materialise(self):
+        for key in list(self._lazy):
+            self[key]
+        return dict(self)
+
     def __reduce__(self):  # pickles / deep-copies as a plain dict with everything computed
-        self["p_values"]
-        return (dict, (dict(self),))
+        return (dict, (self.materialise(),))
+
+
+def _sig_code(p_value):
+    """utils.sig_code (utils.py:569-590)"""
+    assert 0 <= p_value <= 1, "p_value must be on [0, 1]"
+    for cut, code in ((0.001, "***"), (0.01, "**"), (0.05, "*"), (0.1, ".")):
+        if p_value < cut:
+            return code
+    return " "
 
 
 def _flatten(v):
@@ -486,7 +512,9 @@ class GAM:
             sol = eng.solve_truncated(self._solve_rank, want_cov=True)
         else:
             sol = eng.solve(coef_prev=None, want_edof=True, want_cov=True)
-        st["edof_per_coef"] = None
+        if isinstance(st, _LazyStats):  # edof_per_coef on first access, from the last iteration's G and penalty
+            mm = self.terms.n_coefs
+            st._ctx = (eng.out[:mm * mm].view(mm, mm).cpu().numpy().copy(), eng.penalty_host())
         st["edof"] = sol["edof"]
         sc, _, _ = eng.stats_pass(data, self.coef_)
         self._dev_memo = (data, np.asarray(self.coef_, dtype=np.float64).tobytes(), sc[_lib.SS_DEV],
@@ -545,6 +573,217 @@ class GAM:
         score = score / rank
         return 1 - scipy.stats.f.cdf(score, rank, self.statistics_["n_samples"] - self.statistics_["edof"])
 
+    def _estimate_edof_per_coef(self, ctx):
+        """diag(U1 U1^T) of the reference (pygam.py:1033) = diag(R (G + E^T E)^-1 R^T) with R^T R = G, R upper
+        triangular (the R of its QR of W.B).  G is singular along the analytic null space of the design and wherever
+        a block has fewer distinct x than splines; there the reference's R rows are rounding noise and its split of
+        edof over the coefficients is not reproducible (its SUM is).  Here R is the Cholesky factor in the limit of
+        exact arithmetic: a dependent column gets a zero row.  Agrees with the reference to 1e-12 on designs without
+        null directions, to its own noise (~1e-2 per coefficient) otherwise."""
+        if ctx is None:
+            return None
+        G, EtE = ctx
+        m = len(G)
+        if getattr(self, "_solve_rank", m) < m:
+            return None  # rows < coefficients: the reference's U1 is cropped and summary() prints no per-term edof
+        R = np.zeros((m, m))
+        d = np.diag(G)
+        for j in range(m):
+            piv = G[j, j] - R[:j, j] @ R[:j, j]
+            if not piv > 1e-12 * d[j]:
+                continue
+            R[j, j:] = (G[j, j:] - R[:j, j] @ R[:j, j:]) / np.sqrt(piv)
+        Z = np.linalg.solve(G + EtE, R.T)
+        return np.einsum("ij,ji->i", R, Z)
+
+    # ---- reporting (pygam.py:917-991, 1645-1806, 2087-2368): small-n host code over coef_, cov and the O(k) passes ----
+    def summary(self):
+        """pygam.py:1645-1806: the same table"""
+        if not self._is_fitted:
+            raise AttributeError("GAM has not been fitted. Call fit first.")
+        st = self.statistics_
+        wd, wr = 47, 58
+
+        def space_row(left, right, total):
+            left, right = str(left), str(right)
+            return left + " " * (total - len(left) - len(right)) + right
+
+        objective = "UBRE" if self.distribution._known_scale else "GCV"
+        dist_name = {"normal": "NormalDist", "binomial": "BinomialDist", "poisson": "PoissonDist", "gamma": "GammaDist",
+                     "inv_gauss": "InvGaussDist"}[self.distribution.name]
+        link_name = {"identity": "IdentityLink", "logit": "LogitLink", "log": "LogLink", "inverse": "InverseLink",
+                     "inv_squared": "InvSquaredLink"}[self.link.name]
+        rows = [(space_row("Distribution:", dist_name, wd), space_row("Effective DoF:", np.round(st["edof"], 4), wr)),
+                (space_row("Link Function:", link_name, wd), space_row("Log Likelihood:", np.round(st["loglikelihood"], 4), wr)),
+                (space_row("Number of Samples:", st["n_samples"], wd), space_row("AIC: ", np.round(st["AIC"], 4), wr)),
+                ("", space_row("AICc: ", np.round(st["AICc"], 4), wr)),
+                ("", space_row(objective + ":", np.round(st[objective], 4), wr)),
+                ("", space_row("Scale:", np.round(st["scale"], 4), wr)),
+                ("", space_row("Pseudo R-Squared:", np.round(st["pseudo_r2"]["explained_deviance"], 4), wr))]
+        out = ["{:47} {:58}".format(self.__class__.__name__, ""), "{:47} {:58}".format("=" * wd, "=" * wr)]
+        out += ["{:47} {:58}".format(a[:wd], b[:wr]) for a, b in rows]
+        out.append("=" * 106)
+        fmt = [("Feature Function", 33), ("Lambda", 20), ("Rank", 12), ("EDoF", 12), ("P > x", 12), ("Sig. Code", 12)]
+        line = " ".join("{:%d}" % w for _, w in fmt)
+        out.append(line.format(*[h for h, _ in fmt]))
+        out.append(line.format(*["=" * w for _, w in fmt]))
+        epc = st["edof_per_coef"]
+        for i, term in enumerate(self.terms):
+            if epc is not None and len(epc) == len(self.coef_):
+                edof = np.round(epc[self.terms.get_coef_indices(i)].sum(), 1)
+            else:
+                edof = ""
+            pv = st["p_values"][i]
+            cells = [repr(term), "" if term.isintercept else np.round(_flatten(term.lam), 4), f"{term.n_coefs}", f"{edof}",
+                     "%.2e" % pv, _sig_code(pv)]
+            out.append(line.format(*[str(c)[:w] for c, (_, w) in zip(cells, fmt)]))
+        out.append("=" * 106)
+        out.append("Significance codes:  0 '***' 0.001 '**' 0.01 '*' 0.05 '.' 0.1 ' ' 1")
+        out.append("")
+        out.append("WARNING: Fitting splines and a linear function to a feature introduces a model identifiability problem\n"
+                   "         which can cause p-values to appear significant when they are not.")
+        out.append("")
+        out.append("WARNING: p-values calculated in this manner behave correctly for un-penalized models or models with\n"
+                   "         known smoothing parameters, but when smoothing parameters have been estimated, the p-values\n"
+                   "         are typically lower than they should be, meaning that the tests reject the null too readily.")
+        print("\n".join(out))
+        warnings.warn("KNOWN BUG: p-values computed in this summary are likely much smaller than they should be. \n \n"
+                      "Please do not make inferences based on these values! \n\n"
+                      "Collaborate on a solution, and stay up to date at: \ngithub.com/dswah/pyGAM/issues/163 \n",
+                      stacklevel=2)
+
+    def _deviance_rows(self, y, mu, weights=None, scaled=True):
+        """Distribution.deviance (distributions.py:162-185, 267-291, 372-397, 469-494, 572-597 and the decorators
+        13-30) on host arrays"""
+        name, lv = self.distribution.name, float(self.distribution.levels)
+        y, mu = np.asarray(y, dtype=np.float64), np.asarray(mu, dtype=np.float64)
+
+        def ylogydu(a, u):
+            with np.errstate(all="ignore"):
+                return np.where(a != 0, a * np.log(np.where(a != 0, a, 1.0) / u), 0.0)
+
+        with np.errstate(all="ignore"):
+            if name == "normal":
+                dev = (y - mu) ** 2
+            elif name == "binomial":
+                dev = 2 * (ylogydu(y, mu) + ylogydu(lv - y, lv - mu))
+            elif name == "poisson":
+                dev = 2 * (ylogydu(y, mu) - (y - mu))
+            elif name == "gamma":
+                dev = 2 * ((y - mu) / mu - np.log(y / mu))
+            else:
+                dev = ((y - mu) ** 2) / (mu ** 2 * y)
+        if scaled and self.distribution.scale:
+            dev = dev / (self.distribution.scale ** 2 if name == "normal" else self.distribution.scale)
+        if weights is not None:
+            dev = dev * np.asarray(weights)
+        return dev
+
+    def deviance_residuals(self, X, y, weights=None, scaled=False):
+        """pygam.py:940-991: sign(y - mu) sqrt(deviance row); mu on the device, the n-sized result on the host"""
+        if not self._is_fitted:
+            raise AttributeError("GAM has not been fitted. Call fit first.")
+        data = self._prepare_data(X, y, weights, fitting=True)
+        yh = data.y.cpu().numpy()
+        wh = np.ones_like(yh) if data.w is None else data.w.cpu().numpy().astype(np.float64)
+        mu = self.predict_mu(X)
+        return np.sign(yh - mu) * self._deviance_rows(yh, mu, weights=wh, scaled=scaled) ** 0.5
+
+    def _estimate_r2(self, X, y, weights=None):
+        """pygam.py:1114-1154 through the O(k) statistics pass"""
+        data = self._prepare_data(X, y, weights, fitting=True)
+        eng = self._get_engine(data)
+        sc, _, _ = eng.stats_pass(data, self.coef_)
+        n = sc[_lib.SS_N]
+        sc2, _, _ = eng.stats_pass(data, self.coef_, scale=self.distribution.scale, ybar=sc[_lib.SS_SUMY] / n,
+                                   poisson_round=isinstance(self, PoissonGAM))
+        ll, null_ll = sc2[_lib.SS_LOGLIK], sc2[_lib.SS_NULL_LOGLIK]
+        return OrderedDict([("explained_deviance", 1.0 - sc[_lib.SS_WDEV] / sc2[_lib.SS_NULL_WDEV]),
+                            ("McFadden", ll / null_ll), ("McFadden_adj", 1.0 - (ll - self.statistics_["edof"]) / null_ll)])
+
+    def score(self, X, y, weights=None):
+        """explained deviance on (X, y) (pygam.py:917-938)"""
+        if not self._is_fitted:
+            raise AttributeError("GAM has not been fitted. Call fit first.")
+        return self._estimate_r2(X, y, weights=weights)["explained_deviance"]
+
+    def _dist_sample(self, mu):
+        """Distribution.sample (distributions.py:187-205, 293-308, 399-412, 496-515, 599-612): host RNG"""
+        name, scale = self.distribution.name, self.distribution.scale
+        if name == "normal":
+            return np.random.normal(loc=mu, scale=scale if scale else 1.0, size=None)
+        if name == "binomial":
+            lv = self.distribution.levels
+            return np.random.binomial(n=lv, p=mu / lv, size=None)
+        if name == "poisson":
+            return np.random.poisson(lam=mu, size=None)
+        if name == "gamma":
+            shape = 1.0 / scale
+            return np.random.gamma(shape=shape, scale=mu / shape, size=None)
+        return np.random.wald(mean=mu, scale=scale, size=None)
+
+    def sample(self, X, y, quantity="y", sample_at_X=None, weights=None, n_draws=100, n_bootstraps=5, objective="auto"):
+        """Simulate from the posterior of the coefficients and smoothing parameters (pygam.py:2087-2210): bootstrap
+        refits (each a grid search + a fit on the device), draws from N(coef_b, cov_b) on the host"""
+        if quantity not in {"mu", "coef", "y"}:
+            raise ValueError(f"`quantity` must be one of 'mu', 'coef', 'y'; got {quantity}")
+        coef_draws = self._sample_coef(X, y, weights=weights, n_draws=n_draws, n_bootstraps=n_bootstraps,
+                                       objective=objective)
+        if quantity == "coef":
+            return coef_draws
+        if sample_at_X is None:
+            sample_at_X = X
+        lp = self._modelmat(sample_at_X).dot(coef_draws.T)
+        mu = self._link_mu(lp).T
+        if quantity == "mu":
+            return mu
+        return self._dist_sample(mu)
+
+    def _sample_coef(self, X, y, weights=None, n_draws=100, n_bootstraps=1, objective="auto"):
+        """pygam.py:2212-2268"""
+        if not self._is_fitted:
+            raise AttributeError("GAM has not been fitted. Call fit first.")
+        if n_bootstraps < 1:
+            raise ValueError(f"n_bootstraps must be >= 1; got {n_bootstraps}")
+        if n_draws < 1:
+            raise ValueError(f"n_draws must be >= 1; got {n_draws}")
+        coefs, covs = self._bootstrap_samples_of_smoothing(X, y, weights=weights, n_bootstraps=n_bootstraps,
+                                                           objective=objective)
+        return self._simulate_coef_from_bootstraps(n_draws, coefs, covs)
+
+    def _bootstrap_samples_of_smoothing(self, X, y, weights=None, n_bootstraps=1, objective="auto"):
+        """pygam.py:2270-2337 (Wood 2006, p. 198): y* ~ distribution(mu), lam* by grid search on y*, refit on y"""
+        def load_diagonal(cov, load=None):  # utils.py:838-866
+            n = cov.shape[0]
+            return cov + np.eye(n) * (np.sqrt(EPS) if load is None else load)
+
+        mu = self.predict_mu(X)
+        coef_bootstraps = [self.coef_]
+        cov_bootstraps = [load_diagonal(self.statistics_["cov"])]
+        for _ in range(n_bootstraps - 1):
+            y_bootstrap = self._dist_sample(mu)
+            gam = copy.deepcopy(self)
+            lam_grid = np.exp(np.random.randn(11, len(_flatten(self.lam))) * 6 - 3)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                gam.gridsearch(X, y_bootstrap, weights=weights, lam=lam_grid, objective=objective)
+            lam = gam.lam
+            gam = copy.deepcopy(self)
+            gam.lam = lam
+            gam.fit(X, y, weights=weights)
+            coef_bootstraps.append(gam.coef_)
+            cov_bootstraps.append(load_diagonal(gam.statistics_["cov"]))
+        return coef_bootstraps, cov_bootstraps
+
+    def _simulate_coef_from_bootstraps(self, n_draws, coef_bootstraps, cov_bootstraps):
+        """pygam.py:2339-2368"""
+        idx = np.random.choice(np.arange(len(coef_bootstraps)), size=n_draws, replace=True)
+        coef_draws = np.empty((n_draws, len(self.coef_)))
+        for b in np.unique(idx):
+            draws = np.flatnonzero(idx == b)
+            coef_draws[draws] = np.random.multivariate_normal(coef_bootstraps[b], cov_bootstraps[b], size=len(draws))
+        return coef_draws
+
     # ---- public API ----
     def fit(self, X, y=None, weights=None):
         """Fit the model (pygam.py:860-915).  X: (n, F) array-like on the host, or a
@@ -563,7 +802,7 @@ class GAM:
         nt = torch.tensor([float(data.n)], dtype=torch.float64, device=data.device)
         self._n_global = int(all_reduce_(nt, "sum").item())
         self._validate_data_dep_params(data, col_minmax)
-        self.statistics_ = {}
+        self.statistics_ = _LazyStats(self)
         self.statistics_["n_samples"] = self._n_global
         self.statistics_["m_features"] = data.n_features
         if not hasattr(self, "logs_"):  # pygam.py:901-902: created once, so the logs of a refit are appended
@@ -759,9 +998,6 @@ class GAM:
 
     def _C(self):
         return self.terms.build_constraints(self.coef_, self._constraint_lam, self._constraint_l2)
-
-    def deviance_residuals(self, X, y, weights=None, scaled=False):
-        raise NotImplementedError("n-sized residual vectors are out of scope of the hot path (DESIGN.md)")
 
     def loglikelihood(self, X, y, weights=None):
         data = self._prepare_data(X, y, weights, fitting=True)
@@ -974,7 +1210,9 @@ class GAM:
             if not (dev > 1e-7 * yy):
                 return False  # cancellation: take the data passes instead
             gam._n_global = n
-            gam.statistics_ = _LazyStats(gam, {"n_samples": n, "m_features": data.n_features})
+            gam.statistics_ = _LazyStats(gam, {"n_samples": n, "m_features": data.n_features},
+                                         lazy=("edof_per_coef", "p_values"))
+            gam.statistics_._ctx = (G, cands[k][1] + cands[k][2])
             if not hasattr(gam, "logs_"):
                 gam.logs_ = {}
             for c in gam.callbacks:
@@ -1007,7 +1245,6 @@ class GAM:
         (distributions.py:110-131) is -dev / (2 scale^2) - n (log(2 pi) / 2 + log(scale)), the null model's mean
         is sum(y) / n (pygam.py:1141-1147)."""
         dist, st = self.distribution, self.statistics_
-        st["edof_per_coef"] = None
         st["edof"] = edof
         if not dist._known_scale:
             dist.scale = float(np.sqrt(dev / (n - edof)))
@@ -1026,8 +1263,6 @@ class GAM:
         st["GCV"], st["UBRE"] = self._estimate_GCV_UBRE(dev, n, edof)
         st["loglikelihood"] = ll
         st["deviance"] = dev / s2
-        if not isinstance(st, _LazyStats):
-            st["p_values"] = self._estimate_p_values()
 
 
 class _ShapeOnly:

@@ -163,6 +163,9 @@ class OracleEngine:
         self.EtE = np.array(EtE, dtype=np.float64)
         self.EtE_null = None if EtE_null is None else np.array(EtE_null, dtype=np.float64)
 
+    def penalty_host(self):
+        return self.EtE + (0.0 if self.EtE_null is None else self.EtE_null)
+
     def chol_ok(self, A):
         try:
             scipy.linalg.cholesky(A, lower=False)
