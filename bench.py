@@ -324,9 +324,11 @@ def parity_prefix(pg, name, Xh, yh, quiet):
     to 1e-10 (constrained: 1e-7), edof"""
     from oracle import gam_oracle as orc
 
+    from pygam_b200.engine import single_rank
+
     gam, _ = make_model(pg, name)
     t0 = time.perf_counter()
-    with quiet():
+    with quiet(), single_rank():  # rank 0 alone fits the prefix: no collective inside
         gam.fit(Xh, yh)
     t_gpu = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -474,7 +476,10 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a rank that fails must not leave the others waiting for ten minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     n = args.rows
     lib = _lib.load()
     hbm_peak, peak_source = hbm_peak_gbs()

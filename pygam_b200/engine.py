@@ -74,11 +74,29 @@ class DeviceData:
         return cls(Xt, yt, wt)
 
 
+_LOCAL_ONLY = 0
+
+
+class single_rank:
+    """``with single_rank(): gam.fit(...)`` -- fit (or predict) on this rank's rows only although a process group is
+    initialised: no collective is issued inside the block (a side model fitted by one rank of a sharded job)"""
+
+    def __enter__(self):
+        global _LOCAL_ONLY
+        _LOCAL_ONLY += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _LOCAL_ONLY
+        _LOCAL_ONLY -= 1
+        return False
+
+
 def all_reduce_(t, op="sum"):
     """in-place all-reduce over the default process group when one is initialised"""
     import torch.distributed as dist
 
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if _LOCAL_ONLY == 0 and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         ops = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}
         dist.all_reduce(t, op=ops[op])
     return t
@@ -88,7 +106,7 @@ def world():
     """(rank, world size) of the default process group; (0, 1) without one"""
     import torch.distributed as dist
 
-    if dist.is_available() and dist.is_initialized():
+    if _LOCAL_ONLY == 0 and dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
 

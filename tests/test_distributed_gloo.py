@@ -77,3 +77,49 @@ def test_two_rank_row_sharding_matches_single_process(name, tmp_path):
     # and the sharded fit still matches the unmodified reference
     helpers_tol = 1e-8
     assert np.linalg.norm(Pz @ (r0["coef"] - g["coef"])) <= helpers_tol * np.linalg.norm(g["coef"])
+
+
+def _grid_worker(rank, world, port, out_dir):
+    for p in (os.path.dirname(HERE), HERE, os.path.join(HERE, "golden")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import contextlib
+    import io
+
+    import cases
+    import helpers
+    from oracle_backend import OracleBackend
+    from pygam_b200 import engine as pg_engine
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pg_engine.swap_backend_for_tests(OracleBackend())
+    X, y = cases.data_c4(3000)
+    lo, hi = len(y) * rank // world, len(y) * (rank + 1) // world
+    gam = helpers.build_model(cases.FIT_CASES["c4_linear"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        scores = gam.gridsearch(X[lo:hi], y[lo:hi], return_scores=True, lam=[np.logspace(-3, 3, 5)] * 3)
+    # a side model fitted by this rank alone, while the group is up: no collective inside single_rank()
+    with pg_engine.single_rank(), contextlib.redirect_stdout(io.StringIO()):
+        side = helpers.build_model(cases.FIT_CASES["c4_linear"]).fit(X[:500 + 100 * rank], y[:500 + 100 * rank])
+    np.savez(os.path.join(out_dir, f"grid{rank}.npz"), scores=np.array(list(scores.values())),
+             n_iters=np.array([len(m.logs_["diffs"]) for m in scores]), best=gam.statistics_["GCV"], coef=gam.coef_,
+             side_n=side.statistics_["n_samples"])
+    dist.destroy_process_group()
+
+
+def test_two_rank_gridsearch_splits_the_candidates(tmp_path):
+    """LinearGAM grid search on row shards: the Gram matrix is all-reduced once, each rank solves half of the 125
+    candidates, the results are exchanged, and both ranks end with the reference's scores"""
+    import helpers
+
+    mp.spawn(_grid_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = dict(np.load(tmp_path / "grid0.npz")), dict(np.load(tmp_path / "grid1.npz"))
+    g = helpers.load("grid_c4_grid5")
+    np.testing.assert_array_equal(r0["scores"], r1["scores"])
+    np.testing.assert_array_equal(r0["coef"], r1["coef"])
+    np.testing.assert_allclose(r0["scores"], g["scores"], rtol=1e-9)
+    np.testing.assert_array_equal(r0["n_iters"], g["n_iters"])
+    assert abs(float(r0["best"]) - float(g["best_score"])) <= 1e-10 * float(g["best_score"])
+    assert (int(r0["side_n"]), int(r1["side_n"])) == (500, 600)
