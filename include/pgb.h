@@ -103,6 +103,7 @@ typedef struct pgb_debug_opts {
   int32_t cells_tile_rows;    /* rows per shared-memory tile of the cell-owned pass (0: planned)    */
   int32_t cells_band_tiles;   /* tiles per L2 band (0: planned)                                     */
   int32_t cells_threads;      /* CTA width of the cell kernels: 256, 320, 384 or 512 (0: planned)   */
+  int32_t cells_kernel;       /* sum kernel of a prepared shard: 1 barrier version, 2 ring (0: planned) */
 } pgb_debug_opts;
 int pgb_debug_model_create(const pgb_term* terms, int32_t n_terms, int32_t n_features, int32_t dist,
                            int32_t link, double levels, double expectile, int32_t device,

@@ -48,7 +48,7 @@ class PgbTerm(C.Structure):
 class PgbDebugOpts(C.Structure):
     """test-only plan constraints of pgb_debug_model_create (include/pgb.h)"""
     _fields_ = [("force_general_path", C.c_int32), ("cells_tile_rows", C.c_int32), ("cells_band_tiles", C.c_int32),
-                ("cells_threads", C.c_int32)]
+                ("cells_threads", C.c_int32), ("cells_kernel", C.c_int32)]
 
 
 class PgbModelInfo(C.Structure):

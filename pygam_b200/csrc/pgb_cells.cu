@@ -38,6 +38,8 @@ static const int kCellAcc = 18;           // sums per cell (16 for a pair; 10 + 
 static const int kPreThreads = 256;
 static const int kGenAcc = 64;            // sums per thread of the generic kernel (4 x 4 inner x 4 exponents of the first outer factor)
 static const int kGenSumThreads = 256;    // CTA of the generic kernel
+static const int kRingStages = 2;         // tile buffers per group of the ring kernel
+static size_t ring_stage_bytes(int TR, int threads) { return (((size_t)TR * 26 + (size_t)(threads + 8) * 2) + 15) & ~(size_t)15; }
 static const int kGenOcc = 1;             // its CTAs per SM (64 sums per thread: about 200 registers)
 static const int64_t kBandBytes = 32ll << 20;  // column bytes of a band of rows (stays in the L2)
 
@@ -119,12 +121,15 @@ int pgb_plan_cells(pgb_model* M) {
         max_cells = std::max(max_cells, M->dterms[i].marg[0].nint * M->dterms[j].marg[0].nint);
   if (n_spl <= 1) max_cells = 256;  // diagonal and generic roles only
   C.threads = max_cells <= 256 ? 256 : max_cells <= 320 ? 320 : max_cells <= 384 ? 384 : 512;
-  C.occ = C.threads <= 320 ? 2 : 1;
+  C.occ = C.threads <= 320 ? 2 : 1;  // CTAs per SM of the sort kernels (gram_cells_kernel)
   if (const int t = M->dbg.cells_threads)
     if (t == 256 || t == 320 || t == 384 || t == 512) { C.threads = t; C.occ = t <= 320 ? 2 : 1; }
-  // occ 3: wide CTAs run alone while they sort (registers), but the kernel of a prepared shard only sums: two of
-  // them per SM with half the tile each, so that one waits for its tile while the other computes (measured: -10 %)
-  if (C.occ == 1) C.occ = 3;
+  // the ring kernel of a prepared shard runs G independent groups of `threads` consumers per CTA, one CTA per SM
+  // (0: the barrier version gram_cells_sorted_kernel, two CTAs per SM -- measured faster for the narrow CTAs of coarse
+  // bases, whose ring tiles would be half as long)
+  C.ring_groups = C.threads <= 384 ? 0 : 1;
+  if (M->dbg.cells_kernel == 1) C.ring_groups = 0;
+  if (M->dbg.cells_kernel == 2) C.ring_groups = C.threads <= 384 ? 2 : 1;
   const int TH = C.threads;
   int64_t sum_off = 0;
   int64_t n_sub = 0;
@@ -255,13 +260,17 @@ int pgb_plan_cells(pgb_model* M) {
     C.gstarts_u16 = starts_off;
     if (C.groles.size() > 16384 || C.gorders.size() > 4096) { C = pgb_model::Cells(); return PGB_OK; }
   }
-  C.grid = kSMs * (C.occ == 3 ? 2 : C.occ);
+  // units are dealt to kSMs x G "virtual CTAs": the groups of the ring kernel, the CTAs of the sort kernels
+  C.grid = kSMs * (C.ring_groups > 0 ? C.ring_groups : 2);
   C.ggrid = kSMs * kGenOcc;
-  C.tile_rows = (C.occ == 3) ? 4096 : 8192;
+  C.tile_rows = 8192;
   if (M->dbg.cells_tile_rows > 0) C.tile_rows = std::max(64, M->dbg.cells_tile_rows & ~63);
-  // 1 KB per CTA for the kernel's static shared memory and the driver's reservation
+  // 1 KB per CTA for the kernels' static shared memory and the driver's reservation
   while (cells_smem(C.tile_rows, TH) + 1024 > (C.occ == 2 ? kSmemMax / 2 - 1024 : kSmemMax)) C.tile_rows -= 64;
-  if (C.occ == 3) while ((size_t)C.tile_rows * 26 + (TH + 8) * 2 + 1024 > kSmemMax / 2 - 1024) C.tile_rows -= 64;
+  if (C.ring_groups > 0)
+    while ((size_t)C.ring_groups * kRingStages * ring_stage_bytes(C.tile_rows, TH) + 1024 > kSmemMax) C.tile_rows -= 64;
+  else
+    while ((size_t)C.tile_rows * 26 + (TH + 8) * 2 + 1024 > kSmemMax / 2 - 1024) C.tile_rows -= 64;
   for (DCellRole& R : C.roles) R.hmul = ((uint32_t)R.ncb << 16) / (uint32_t)C.tile_rows;
   // The generic orders sort much longer tiles than the spline roles: a thread's run of rows must be long enough
   // to amortise its start (three dependent gathers) and to even out the lanes of a warp; nothing of a generic
@@ -590,51 +599,79 @@ __device__ __forceinline__ void cell_powers(const DMarg* mg, double s, double& p
   }
 }
 
-// the rows of one cell of a pair (i, j): 16 moment sums, acc[4 p + q] += omega s_i^p s_j^q
+// one row of a pair cell: acc[4 p + q] += omega s_i^p s_j^q.  Inside the knots the powers are chained through
+// omega (u_p = u_{p-1} s_i): 3 + 2 multiplies, 4 adds and 12 FMAs = 21 fp64 instructions for 16 sums.
+template <bool CAREFUL>
+__device__ __forceinline__ void pair_row(const DCellRole* R, double sa, double sb, double ww, double (&acc)[kCellAcc]) {
+  if (CAREFUL) {
+    double a0, a1, a2, a3, b0, b1, b2, b3;
+    cell_powers<true>(&R->a, sa, a0, a1, a2, a3);
+    cell_powers<true>(&R->b, sb, b0, b1, b2, b3);
+    a0 *= ww; a1 *= ww; a2 *= ww; a3 *= ww;
+    acc[0] = fma(a0, b0, acc[0]); acc[1] = fma(a0, b1, acc[1]); acc[2] = fma(a0, b2, acc[2]); acc[3] = fma(a0, b3, acc[3]);
+    acc[4] = fma(a1, b0, acc[4]); acc[5] = fma(a1, b1, acc[5]); acc[6] = fma(a1, b2, acc[6]); acc[7] = fma(a1, b3, acc[7]);
+    acc[8] = fma(a2, b0, acc[8]); acc[9] = fma(a2, b1, acc[9]); acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
+    acc[12] = fma(a3, b0, acc[12]); acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
+  } else {
+    const double u1 = ww * sa, u2 = u1 * sa, u3 = u2 * sa;
+    const double b2 = sb * sb, b3 = b2 * sb;
+    acc[0] += ww; acc[1] = fma(ww, sb, acc[1]); acc[2] = fma(ww, b2, acc[2]); acc[3] = fma(ww, b3, acc[3]);
+    acc[4] += u1; acc[5] = fma(u1, sb, acc[5]); acc[6] = fma(u1, b2, acc[6]); acc[7] = fma(u1, b3, acc[7]);
+    acc[8] += u2; acc[9] = fma(u2, sb, acc[9]); acc[10] = fma(u2, b2, acc[10]); acc[11] = fma(u2, b3, acc[11]);
+    acc[12] += u3; acc[13] = fma(u3, sb, acc[13]); acc[14] = fma(u3, b2, acc[14]); acc[15] = fma(u3, b3, acc[15]);
+  }
+}
+
+// one row of a diagonal cell: the 10 moment sums of the packed upper triangle (p <= q), the intercept column
+// (omega s^p), the right-hand side (omega z s^p)
+template <bool CAREFUL>
+__device__ __forceinline__ void diag_row(const DCellRole* R, double sa, double z, double ww, double (&acc)[kCellAcc]) {
+  double a0, a1, a2, a3;
+  cell_powers<CAREFUL>(&R->a, sa, a0, a1, a2, a3);
+  const double v0 = a0 * ww, v1 = a1 * ww, v2 = a2 * ww, v3 = a3 * ww;
+  acc[0] = fma(v0, a0, acc[0]); acc[1] = fma(v0, a1, acc[1]); acc[2] = fma(v0, a2, acc[2]); acc[3] = fma(v0, a3, acc[3]);
+  acc[4] = fma(v1, a1, acc[4]); acc[5] = fma(v1, a2, acc[5]); acc[6] = fma(v1, a3, acc[6]);
+  acc[7] = fma(v2, a2, acc[7]); acc[8] = fma(v2, a3, acc[8]); acc[9] = fma(v3, a3, acc[9]);
+  acc[10] += v0; acc[11] += v1; acc[12] += v2; acc[13] += v3;
+  acc[14] = fma(a0, z, acc[14]); acc[15] = fma(a1, z, acc[15]); acc[16] = fma(a2, z, acc[16]); acc[17] = fma(a3, z, acc[17]);
+}
+
+// the rows of one cell, in the stored order, two rows in flight (their gathers are issued together)
 template <bool CAREFUL>
 __device__ __forceinline__ void cell_rows_pair(const DCellRole* R, const uint16_t* __restrict__ perm, int c,
                                                const double* __restrict__ ta, const double* __restrict__ tb,
                                                const double* __restrict__ wv, double (&acc)[kCellAcc]) {
+  int s = 0;
 #pragma unroll 1
-  for (int s = 0; s < c; ++s) {
-    const int r = perm[s];
-    const double ww = wv[r];
-    double a0, a1, a2, a3, b0, b1, b2, b3;
-    cell_powers<CAREFUL>(&R->a, ta[r], a0, a1, a2, a3);
-    cell_powers<CAREFUL>(&R->b, tb[r], b0, b1, b2, b3);
-    a1 *= ww; a2 *= ww; a3 *= ww;
-    if (CAREFUL) {
-      a0 *= ww;
-      acc[0] = fma(a0, b0, acc[0]); acc[4] = fma(a1, b0, acc[4]); acc[8] = fma(a2, b0, acc[8]); acc[12] = fma(a3, b0, acc[12]);
-    } else {  // s^0 = 1
-      a0 = ww;
-      acc[0] += a0; acc[4] += a1; acc[8] += a2; acc[12] += a3;
-    }
-    acc[1] = fma(a0, b1, acc[1]); acc[2] = fma(a0, b2, acc[2]); acc[3] = fma(a0, b3, acc[3]);
-    acc[5] = fma(a1, b1, acc[5]); acc[6] = fma(a1, b2, acc[6]); acc[7] = fma(a1, b3, acc[7]);
-    acc[9] = fma(a2, b1, acc[9]); acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
-    acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
+  for (; s + 1 < c; s += 2) {
+    const int r0 = perm[s], r1 = perm[s + 1];
+    const double w0 = wv[r0], x0 = ta[r0], y0 = tb[r0];
+    const double w1 = wv[r1], x1 = ta[r1], y1 = tb[r1];
+    pair_row<CAREFUL>(R, x0, y0, w0, acc);
+    pair_row<CAREFUL>(R, x1, y1, w1, acc);
+  }
+  if (s < c) {
+    const int r0 = perm[s];
+    pair_row<CAREFUL>(R, ta[r0], tb[r0], wv[r0], acc);
   }
 }
 
-// the rows of one cell of a diagonal block: the 10 moment sums of the packed upper triangle (p <= q), the
-// intercept column (omega s^p), the right-hand side (omega z s^p)
 template <bool CAREFUL>
 __device__ __forceinline__ void cell_rows_diag(const DCellRole* R, const uint16_t* __restrict__ perm, int c,
                                                const double* __restrict__ ta, const double* __restrict__ wz,
                                                const double* __restrict__ wv, double (&acc)[kCellAcc]) {
+  int s = 0;
 #pragma unroll 1
-  for (int s = 0; s < c; ++s) {
-    const int r = perm[s];
-    const double ww = wv[r], z = wz[r];
-    double a0, a1, a2, a3;
-    cell_powers<CAREFUL>(&R->a, ta[r], a0, a1, a2, a3);
-    const double v0 = a0 * ww, v1 = a1 * ww, v2 = a2 * ww, v3 = a3 * ww;
-    acc[0] = fma(v0, a0, acc[0]); acc[1] = fma(v0, a1, acc[1]); acc[2] = fma(v0, a2, acc[2]); acc[3] = fma(v0, a3, acc[3]);
-    acc[4] = fma(v1, a1, acc[4]); acc[5] = fma(v1, a2, acc[5]); acc[6] = fma(v1, a3, acc[6]);
-    acc[7] = fma(v2, a2, acc[7]); acc[8] = fma(v2, a3, acc[8]); acc[9] = fma(v3, a3, acc[9]);
-    acc[10] += v0; acc[11] += v1; acc[12] += v2; acc[13] += v3;
-    acc[14] = fma(a0, z, acc[14]); acc[15] = fma(a1, z, acc[15]); acc[16] = fma(a2, z, acc[16]); acc[17] = fma(a3, z, acc[17]);
+  for (; s + 1 < c; s += 2) {
+    const int r0 = perm[s], r1 = perm[s + 1];
+    const double w0 = wv[r0], x0 = ta[r0], z0 = wz[r0];
+    const double w1 = wv[r1], x1 = ta[r1], z1 = wz[r1];
+    diag_row<CAREFUL>(R, x0, z0, w0, acc);
+    diag_row<CAREFUL>(R, x1, z1, w1, acc);
+  }
+  if (s < c) {
+    const int r0 = perm[s];
+    diag_row<CAREFUL>(R, ta[r0], wz[r0], wv[r0], acc);
   }
 }
 
@@ -642,13 +679,13 @@ __device__ __forceinline__ void cell_rows_diag(const DCellRole* R, const uint16_
 // starts with the role the previous one ended with
 struct UnitIter {
   int64_t ntiles, nbands, band, uu, u_lo, u_hi, nb, t0;
-  int band_tiles, n_roles;
+  int band_tiles, n_roles, cta, ncta;
   __device__ void set_band() {
     t0 = band * band_tiles;
     nb = min((int64_t)band_tiles, ntiles - t0);
     const int64_t U = nb * n_roles;
-    u_lo = U * blockIdx.x / gridDim.x;
-    u_hi = U * (blockIdx.x + 1) / gridDim.x;
+    u_lo = U * cta / ncta;
+    u_hi = U * (cta + 1) / ncta;
     uu = 0;
   }
   __device__ void skip_empty() {
@@ -657,7 +694,11 @@ struct UnitIter {
       if (band < nbands) set_band();
     }
   }
-  __device__ void init(int64_t n, int TR, int bt, int nr) {
+  __device__ void init(int64_t n, int TR, int bt, int nr) { init(n, TR, bt, nr, (int)blockIdx.x, (int)gridDim.x); }
+  // (c, nc): the units of virtual CTA c of nc (a CTA of the ring kernel runs several independent groups)
+  __device__ void init(int64_t n, int TR, int bt, int nr, int c, int nc) {
+    cta = c;
+    ncta = nc;
     band_tiles = bt;
     n_roles = nr;
     ntiles = (n + TR - 1) / TR;
@@ -869,6 +910,42 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
     it.next();
     if (tid == 0 && it.valid()) load_cells(it);
     if (EMIT) {
+      // Bank-aware order inside every cell.  The sum kernels gather t_i, t_j and omega of row perm[start + s] for the
+      // 32 cells of a warp at once: a 64-bit shared-memory load of 32 unrelated rows costs about 4.2 wavefronts where
+      // 2 is the minimum (both half-warps on 16 distinct bank pairs, bank pair = row & 15) -- the shared-memory pipe,
+      // not the fp64 pipe, bounded the kernel.  The order of the rows of a cell is free, so step by step every lane
+      // picks, among the rows its cell has left, one whose bank pair no other lane of its half-warp has taken
+      // (four rounds of match / re-pick; a lane that runs out of candidates keeps a conflicting row).
+      {
+        int maxc = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
+        uint16_t* run = perm + start;
+        const unsigned half = (unsigned)lane & 16u;
+        for (int s = 0; s < maxc; ++s) {
+          const bool act = s < c;
+          int cand = s;
+          bool settled = false;
+#pragma unroll 1
+          for (int round = 0; round < 4; ++round) {
+            const unsigned key = act ? (((unsigned)run[cand] & 15u) | half) : (32u + (unsigned)lane);
+            const unsigned same = __match_any_sync(0xffffffffu, key);
+            const unsigned done = __ballot_sync(0xffffffffu, settled) & same;
+            const int winner = done ? (__ffs(done) - 1) : (__ffs(same) - 1);
+            if (act && !settled) {
+              if (lane == winner) settled = true;
+              else if (cand + 1 < c) ++cand;
+            }
+          }
+          if (act && cand != s) {
+            const uint16_t tmp = run[s];
+            run[s] = run[cand];
+            run[cand] = tmp;
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
       // the order of this (role, tile): sorted row indices, start of every cell, total, "careful" flag
       const int64_t ntl = (n + TR - 1) / TR;
       uint32_t* pg = reinterpret_cast<uint32_t*>(perm_g + ((int64_t)role * ntl + tile) * TR);
@@ -986,6 +1063,120 @@ gram_cells_sorted_kernel(int64_t n, int64_t np, const double* __restrict__ om, c
     double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * kCellThreads);
 #pragma unroll
     for (int e = 0; e < kCellAcc; ++e) dst[e * kCellThreads + tid] = acc[e];
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// The sum kernel of a prepared shard as a RING: one CTA per SM runs G independent groups; a group = NW warps
+// (thread = cell, as above) and a ring of kRingStages tile buffers with a full / empty
+// mbarrier pair each.  Lane 0 of the group's first warp issues the five bulk copies of the NEXT unit (t_i, t_j, omega, the
+// sorted row indices, the cell starts) as soon as every consumer warp has released the stage; a consumer warp waits
+// for `full`, sums the rows of its 32 cells and arrives on `empty` -- no CTA-wide barrier anywhere in the loop.
+// Why (ncu source page of the barrier version, profiles/r2_ncu_c3_sorted_320x2_source.txt): 25 % of its stall samples
+// sat in the wait for a tile's copies (issued and awaited by the same CTA, hidden only by the second CTA of the SM)
+// and 9 % behind the barrier that ends a tile, where every warp waits for the fullest of the CTA's 512 cells; here a
+// warp waits for the fullest of its own 32 cells only and the copies of the next unit are in flight while this one
+// is summed.
+// ----------------------------------------------------------------------------------------
+
+template <int THREADS, int G>
+__global__ void __launch_bounds__(G * THREADS, 1)
+gram_cells_ring_kernel(int64_t n, int64_t np, const double* __restrict__ om, const double* __restrict__ omz,
+                       const double* __restrict__ tq, const DCellRole* __restrict__ roles, int n_roles, int TR,
+                       int band_tiles, int slots_per_cta, double* __restrict__ part,
+                       const uint16_t* __restrict__ perm_g, const uint16_t* __restrict__ starts_g) {
+  constexpr int NW = THREADS / 32, S = kRingStages;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long s_bar[G][2 * S];
+  const int g = threadIdx.x / THREADS, t = threadIdx.x - g * THREADS, lane = t & 31;
+  const size_t stage_bytes = (((size_t)TR * 26 + (size_t)(THREADS + 8) * 2) + 15) & ~(size_t)15;
+  unsigned char* gbase = smem_raw + (size_t)g * S * stage_bytes;
+  if (t == 0) {
+    for (int q = 0; q < S; ++q) {
+      mbar_init(smem_addr(&s_bar[g][q]), 1);           // full: the issuing lane's arrive + the bytes of the copies
+      mbar_init(smem_addr(&s_bar[g][S + q]), NW);      // empty: one arrive per warp
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int64_t ntl = (n + TR - 1) / TR;
+  const int vcta = (int)blockIdx.x * G + g, nvcta = (int)gridDim.x * G;
+  UnitIter it;
+  it.init(n, TR, band_tiles, n_roles, vcta, nvcta);
+  // the copies of unit j are issued by lane 0 of warp 0 when it STARTS unit j - 1 (unit 0: before the loop), as soon
+  // as every warp has released the stage of unit j - 2: they have a whole unit of summing to arrive
+  const bool issuer = (t == 0);
+  UnitIter ahead = it;
+  auto issue = [&](const UnitIter& u, int j) {
+    const int q = j % S;
+    if (j >= S) mbar_wait(smem_addr(&s_bar[g][S + q]), (uint32_t)((j / S) - 1) & 1u);
+    const int role = u.role();
+    const int64_t tile = u.tile(), row0 = tile * TR;
+    const uint32_t cnt16 = (uint32_t)((min((int64_t)TR, n - row0) + 15) & ~(int64_t)15);
+    const DCellRole* gr = roles + role;
+    double* ta = reinterpret_cast<double*>(gbase + (size_t)q * stage_bytes);
+    const double* ga = tq + (int64_t)gr->sa * np + row0;
+    const double* gb = gr->diag ? omz + row0 : tq + (int64_t)gr->sb * np + row0;
+    const uint32_t bar = smem_addr(&s_bar[g][q]);
+    mbar_expect_tx(bar, 3u * cnt16 * 8u + cnt16 * 2u + (uint32_t)(THREADS + 8) * 2u);
+    bulk_g2s(smem_addr(ta), ga, cnt16 * 8u, bar);
+    bulk_g2s(smem_addr(ta + TR), gb, cnt16 * 8u, bar);
+    bulk_g2s(smem_addr(ta + 2 * TR), om + row0, cnt16 * 8u, bar);
+    bulk_g2s(smem_addr(ta + 3 * TR), perm_g + ((int64_t)role * ntl + tile) * TR, cnt16 * 2u, bar);
+    bulk_g2s(smem_addr(reinterpret_cast<uint16_t*>(ta + 3 * TR) + TR), starts_g + ((int64_t)role * ntl + tile) * (THREADS + 8),
+             (uint32_t)(THREADS + 8) * 2u, bar);
+  };
+  if (issuer && ahead.valid()) issue(ahead, 0);
+  if (ahead.valid()) ahead.next();
+  // thread t owns cell key0 + t of the role it serves
+  const int role_lo = (int)((int64_t)n_roles * vcta / nvcta);
+  double* my_part = part + (int64_t)vcta * slots_per_cta * (kCellAcc * THREADS);
+  int cur_role = -1, diag = 0;
+  const DCellRole* Rg = roles;
+  double acc[kCellAcc];
+#pragma unroll
+  for (int e = 0; e < kCellAcc; ++e) acc[e] = 0.0;
+  for (int i = 0; it.valid(); it.next(), ++i) {
+    if (ahead.valid()) {
+      if (issuer) issue(ahead, i + 1);
+      ahead.next();
+    }
+    const int q = i % S, role = it.role();
+    if (role != cur_role) {
+      if (cur_role >= 0) {
+        double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * THREADS);
+#pragma unroll
+        for (int e = 0; e < kCellAcc; ++e) dst[e * THREADS + t] = acc[e];
+      }
+      const double* src = my_part + (int64_t)(role - role_lo) * (kCellAcc * THREADS);
+#pragma unroll
+      for (int e = 0; e < kCellAcc; ++e) acc[e] = src[e * THREADS + t];
+      Rg = roles + role;
+      diag = Rg->diag;
+      cur_role = role;
+    }
+    mbar_wait(smem_addr(&s_bar[g][q]), (uint32_t)(i / S) & 1u);
+    const unsigned char* sb = gbase + (size_t)q * stage_bytes;
+    const double* ta = reinterpret_cast<const double*>(sb);
+    const double* tb = ta + TR;
+    const double* wv = tb + TR;
+    const uint16_t* perm = reinterpret_cast<const uint16_t*>(wv + TR);
+    const uint16_t* starts = perm + TR;
+    const int start = starts[t], c = (int)starts[t + 1] - start;
+    if (!starts[THREADS + 1]) {
+      if (!diag) cell_rows_pair<false>(Rg, perm + start, c, ta, tb, wv, acc);
+      else cell_rows_diag<false>(Rg, perm + start, c, ta, tb, wv, acc);
+    } else {
+      if (!diag) cell_rows_pair<true>(Rg, perm + start, c, ta, tb, wv, acc);
+      else cell_rows_diag<true>(Rg, perm + start, c, ta, tb, wv, acc);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_addr(&s_bar[g][S + q]));
+  }
+  if (cur_role >= 0) {
+    double* dst = my_part + (int64_t)(cur_role - role_lo) * (kCellAcc * THREADS);
+#pragma unroll
+    for (int e = 0; e < kCellAcc; ++e) dst[e * THREADS + t] = acc[e];
   }
 }
 
@@ -1651,7 +1842,6 @@ static int cells_band_tiles(const pgb_model* M) {
     case 384: KERNEL_CALL(384, 1); break;               \
     default: KERNEL_CALL(512, 1); break;                \
   }
-template <int THREADS, int MINB> struct SortedOcc { static const int value = MINB; };
 
 static int cells_set_smem_attr(const void* fn, int bytes) {
   // per device (a process may drive several GPUs): the attribute is cheap to set, so no caching
@@ -1763,16 +1953,17 @@ int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int
   const bool sorted = planned || C.mixed;
 #define PGB_CELLS_LAUNCH(TH, OCC)                                                                                        \
   do {                                                                                                                   \
-    if (n_roles > 0 && sorted && C.occ == 3) {                                                                           \
+    if (n_roles > 0 && sorted && C.ring_groups > 0) {                                                                    \
+      constexpr int G_ = (TH <= 384) ? 2 : 1;                                                                            \
+      const size_t smem_ = (size_t)G_ * kRingStages * ring_stage_bytes(TR, TH);                                          \
+      rc = cells_set_smem_attr((const void*)gram_cells_ring_kernel<TH, G_>, (int)(kSmemMax - 1024));                     \
+      if (rc != PGB_OK) return rc;                                                                                       \
+      gram_cells_ring_kernel<TH, G_><<<kSMs, G_ * TH, smem_, st>>>(n, np, om, omz, tq, C.d_roles, n_roles, TR,           \
+                                                                   band_tiles, C.slots_per_cta, part, L.perm, L.starts); \
+    } else if (n_roles > 0 && sorted) {                                                                                  \
       rc = cells_set_smem_attr((const void*)gram_cells_sorted_kernel<TH, 2>, (int)(kSmemMax / 2 - 2048));                \
       if (rc != PGB_OK) return rc;                                                                                       \
       gram_cells_sorted_kernel<TH, 2><<<C.grid, TH, (size_t)TR * 26 + (TH + 8) * 2 + 64, st>>>(                          \
-          n, np, om, omz, tq, C.d_roles, n_roles, TR, band_tiles, C.slots_per_cta, part, L.perm, L.starts);              \
-    } else if (n_roles > 0 && sorted) {                                                                                  \
-      rc = cells_set_smem_attr((const void*)gram_cells_sorted_kernel<TH, OCC>,                                           \
-                               (int)(OCC == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024));                                  \
-      if (rc != PGB_OK) return rc;                                                                                       \
-      gram_cells_sorted_kernel<TH, OCC><<<C.grid, TH, (size_t)TR * 26 + (TH + 8) * 2 + 64, st>>>(                        \
           n, np, om, omz, tq, C.d_roles, n_roles, TR, band_tiles, C.slots_per_cta, part, L.perm, L.starts);              \
     } else if (n_roles > 0) {                                                                                            \
       rc = cells_set_smem_attr((const void*)gram_cells_kernel<TH, OCC, false>,                                           \

@@ -74,6 +74,7 @@ int pgb_model_build_host(const pgb_term* terms, int32_t n_terms, int32_t n_featu
     M->dbg.cells_tile_rows = dbg->cells_tile_rows;
     M->dbg.cells_band_tiles = dbg->cells_band_tiles;
     M->dbg.cells_threads = dbg->cells_threads;
+    M->dbg.cells_kernel = dbg->cells_kernel;
   }
   M->device = device;
   M->n_terms = n_terms;

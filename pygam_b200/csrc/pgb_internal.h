@@ -171,6 +171,7 @@ struct pgb_model {
     int32_t* d_grole_prefix = nullptr;
     int32_t* d_gcta_role_lo = nullptr;
     int32_t tile_rows = 0, grid = 0, slots_per_cta = 0, icpt_coef = -1, n_spl = 0, occ = 1, threads = 512;
+    int32_t ring_groups = 1;               // independent consumer groups per CTA of the ring kernel
     int32_t ncol = 0;                  // record columns (one per factor)
     int32_t gslots_per_cta = 0, ggrid = 0;  // partial slots per CTA and grid of the generic kernel
     int32_t gtile_rows = 0;                 // rows per tile of the generic orders (16-bit row indices: < 65536)
@@ -209,7 +210,7 @@ struct pgb_model {
   // set only through the test-only entry point pgb_debug_model_create (tests compare the two Gram paths and
   // exercise tile / band boundaries at small n); zero in every model the product creates
   struct Debug {
-    int32_t force_general = 0, cells_tile_rows = 0, cells_band_tiles = 0, cells_threads = 0;
+    int32_t force_general = 0, cells_tile_rows = 0, cells_band_tiles = 0, cells_threads = 0, cells_kernel = 0;
   } dbg;
   // staging of the host-buffer entry point (allocated on first use, reused afterwards)
   struct HostStage {

@@ -49,7 +49,7 @@ def _engines(gam, n_features, env):
     from pygam_b200.engine import Engine
 
     def make(cells):
-        opts = _lib.PgbDebugOpts(0 if cells else 1, int(env.get("tile", 0)), int(env.get("band", 0)), int(env.get("threads", 0)))
+        opts = _lib.PgbDebugOpts(0 if cells else 1, int(env.get("tile", 0)), int(env.get("band", 0)), int(env.get("threads", 0)), int(env.get("kernel", 0)))
         return Engine(gam.terms, gam.distribution.name, gam.link.name, gam.distribution.levels, gam._expectile, n_features,
                       debug_opts=opts)
 
@@ -91,10 +91,8 @@ def _compare(gam, X, y, w=None, env=None, modes=(_lib.MODE_IRLS, _lib.MODE_INIT)
             unplanned = cells.gram_pass(data, coef, mode=mode).cpu().numpy()
         finally:
             cells.use_plan = True
-        if mode == _lib.MODE_INIT or mixed:
-            assert np.array_equal(a, unplanned)
-        else:
-            assert np.abs(a - unplanned).max() <= 1e-13 * scale
+        # same sums, other order of the rows inside a cell (the prepared order is bank-aware): agreement to rounding
+        assert np.abs(a - unplanned).max() <= 1e-13 * scale
     del torch
 
 
@@ -106,7 +104,8 @@ def _fit_small(case, X, y, **kw):
 
 
 @gpu
-@pytest.mark.parametrize("n,env", [(20001, {}), (30000, {"tile": 1024, "band": 2}),
+@pytest.mark.parametrize("n,env", [(20001, {}), (30000, {"tile": 1024, "band": 2}), (30000, {"tile": 1024, "band": 2, "kernel": 1}),
+                                   (50001, {"tile": 512, "band": 3, "kernel": 2, "threads": 320}),
                                    (777, {}), (65536, {"tile": 2048, "band": 1})])
 def test_cells_equal_general_path_config2(n, env):
     X, y = cases.data_c2(n, seed=11)
