@@ -14,6 +14,10 @@
 // out of shared memory -- this is the grid-search path, one candidate per CTA; larger ones
 // work in the caller's workspace (L2-resident).
 #include <cuda_runtime.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
 #include <math.h>
 
 #include <algorithm>
@@ -656,6 +660,24 @@ extern "C" int pgb_solve_prepare(int32_t m, int32_t nb, const double* EtE, const
   return PGB_OK;
 }
 
+// cached CUDA graphs of the multi-CTA front + finishing kernel, one per distinct argument set
+struct SolveGraphKey {
+  int32_t m, p, flags;
+  const void *G, *r, *A0, *hv, *tau, *beta_prev, *out, *cov, *ws;
+  bool operator==(const SolveGraphKey& o) const {
+    return m == o.m && p == o.p && flags == o.flags && G == o.G && r == o.r && A0 == o.A0 && hv == o.hv && tau == o.tau &&
+           beta_prev == o.beta_prev && out == o.out && cov == o.cov && ws == o.ws;
+  }
+};
+struct SolveGraph {
+  SolveGraphKey key;
+  int dev, launches;
+  cudaGraphExec_t exec;
+};
+static std::mutex g_graph_mu;
+static std::vector<SolveGraph> g_graphs;
+long long pgb_launch_count(void);
+
 static size_t solve_vec_smem(int m) { return ((size_t)4 * m + 34 + kNB * kLD + (size_t)m * kLD) * 8; }
 // columns of B solved at a time: as many as fit next to the vectors and the panel (at least 32)
 static int solve_col_chunk(int m, bool with_matrices) {
@@ -688,6 +710,47 @@ extern "C" int pgb_solve(int32_t m, int32_t nb, const double* G, const double* r
   const size_t smem = solve_vec_smem(m) + (size_t)kNB * wc * 8 + (in_smem ? (size_t)2 * m * m * 8 : 0);
   PGB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemMax));
   if (!in_smem && nb == 1 && (flags & PGB_SOLVE_PREPARED)) {
+    // One large system: the front is ~40 short dependent kernels.  A PIRLS loop calls this with the same buffers
+    // every iteration, so the whole sequence is captured once into a CUDA graph and replayed (the launch and
+    // inter-kernel gaps were 15 % of a config-2 iteration, more in a strong-scaled run).
+    const SolveGraphKey key{m, p, flags, G, r, EtE, hv, tau, beta_prev, out, cov_out, ws};
+    int dev = 0;
+    PGB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    for (SolveGraph& e : g_graphs)
+      if (e.dev == dev && e.key == key) {
+        PGB_CUDA(cudaGraphLaunch(e.exec, (cudaStream_t)stream));
+        pgb_count_launch(e.launches);
+        return PGB_OK;
+      }
+    cudaStream_t cs = nullptr;  // capture on a private stream: the caller's may be the legacy default stream
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool ok = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int launches = 0;
+    if (ok) {
+      const long long before = pgb_launch_count();
+      int rc = solve_front(m, G, EtE, hv, tau, p, (double*)ws, cs);
+      solve_kernel<<<1, kSolveThreads, smem, cs>>>(m, G, r, share_gram, EtE, EtE_null, hv, tau, p, beta_prev, share_prev, out,
+                                                   cov_out, (double*)ws, flags | PGB_SOLVE_FACTORED, 0, wc);
+      launches = (int)(pgb_launch_count() - before) + 1;
+      ok = cudaStreamEndCapture(cs, &graph) == cudaSuccess && rc == PGB_OK && graph != nullptr &&
+           cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    }
+    if (graph) cudaGraphDestroy(graph);
+    if (cs) cudaStreamDestroy(cs);
+    if (ok) {
+      if (g_graphs.size() >= 16) {  // a handful of engines per process; drop the oldest
+        cudaGraphExecDestroy(g_graphs.front().exec);
+        g_graphs.erase(g_graphs.begin());
+      }
+      g_graphs.push_back(SolveGraph{key, dev, launches, exec});
+      PGB_CUDA(cudaGraphLaunch(exec, (cudaStream_t)stream));
+      pgb_count_launch(1);
+      return PGB_OK;
+    }
+    cudaGetLastError();  // capture not possible here: plain launches
     const int rc = solve_front(m, G, EtE, hv, tau, p, (double*)ws, (cudaStream_t)stream);
     if (rc != PGB_OK) return rc;
     flags |= PGB_SOLVE_FACTORED;
