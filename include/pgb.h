@@ -165,6 +165,13 @@ int pgb_gram_pass(const pgb_model* model, int32_t mode, const double* X, int64_t
 int pgb_gram_prepare(const pgb_model* model, const double* X, int64_t n, int64_t ld, void* ws,
                      int64_t ws_bytes, void* stream);
 
+/* Optional second step of the preparation, for shards that will see many passes (long fits, a grid search over
+ * the same rows): rewrites the stored order of the rows INSIDE every knot cell so that the gathers of the sum
+ * kernels hit fewer shared-memory bank conflicts (cell sums of config 2: -13 % per pass; costs about three passes;
+ * the sums of a cell are taken in another order, so [G | r] changes in the last bits).  ws: the workspace
+ * pgb_gram_prepare filled for the same model and n.  No-op for models on the general path. */
+int pgb_gram_refine(const pgb_model* model, int64_t n, void* ws, int64_t ws_bytes, void* stream);
+
 /* Time the Gram pass with CUDA events: enable, run pgb_gram_pass, then read the device time (ms) of
  * the records kernel (basis + IRLS step -> row records) and of the accumulation kernel (records ->
  * G, r), each summed over the row chunks, and of the whole pass (with the reductions). */

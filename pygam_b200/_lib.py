@@ -90,6 +90,7 @@ SYMBOLS = {
     "pgb_gram_ws_bytes_streaming": (C.c_int64, [_P, C.c_int64]),
     "pgb_gram_pass": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "pgb_gram_prepare": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
+    "pgb_gram_refine": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P]),
     "pgb_stats_ws_bytes": (C.c_int64, [_P]),
     "pgb_stats_pass": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_double, C.c_double,
                                  C.c_int32, _P, _P, _P, _P, C.c_int64, _P]),

@@ -717,6 +717,74 @@ struct UnitIter {
   }
 };
 
+// Bank-aware order inside every cell (pgb_gram_refine).  The sum kernels gather t_i, t_j and omega of row
+// perm[start + s] for the 32 cells of a warp at once: a 64-bit shared-memory load of 32 unrelated rows costs about
+// 4.2 wavefronts where 2 is the minimum (both half-warps on 16 distinct bank pairs, bank pair = row & 15) -- the
+// shared-memory pipe, not the fp64 pipe, bounded the kernel.  The order of the rows of a cell is free, so step by
+// step every lane picks, among the rows its cell has left, one whose bank pair no other lane of its half-warp has
+// taken (up to four rounds of compare / re-pick; a lane that runs out of candidates keeps a conflicting row).
+// Simulated cost per half-warp gather: 2.20 -> 1.70 wavefronts; measured: cells kernel of config 2 -13 %.
+__device__ __forceinline__ void bank_aware_reorder(uint16_t* run, int c, int lane) {
+  int maxc = c;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
+  const unsigned half = (unsigned)lane & 16u;
+  for (int s = 0; s < maxc; ++s) {
+    const bool act = s < c;
+    int cand = s;
+    bool settled = false;
+#pragma unroll 1
+    for (int round = 0; round < 4; ++round) {
+      // lanes of my half-warp whose candidate sits in my bank pair: five ballots over the bits of the key
+      // (the match instruction is an order of magnitude slower)
+      const unsigned key = ((unsigned)run[act ? cand : 0] & 15u) | half;
+      unsigned same = __ballot_sync(0xffffffffu, act);
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (key >> b) & 1u);
+        same &= ((key >> b) & 1u) ? bal : ~bal;
+      }
+      const unsigned done = __ballot_sync(0xffffffffu, settled) & same;
+      const int winner = done ? (__ffs(done) - 1) : (__ffs(same) - 1);
+      if (act && !settled) {
+        if (lane == winner) settled = true;
+        else if (cand + 1 < c) ++cand;
+      }
+      if (__ballot_sync(0xffffffffu, act && !settled) == 0u) break;  // every lane has its bank pair
+    }
+    if (act && cand != s) {
+      const uint16_t tmp = run[s];
+      run[s] = run[cand];
+      run[cand] = tmp;
+    }
+    __syncwarp();
+  }
+}
+
+// pgb_gram_refine: the stored order of every (role, tile) of a prepared shard, cell by cell, in bank-aware order.
+// One CTA per unit: the tile's row indices and cell starts are staged in shared memory, reordered, written back.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+gram_cells_refine_kernel(int64_t n, int TR, int n_roles, uint16_t* __restrict__ perm_g, const uint16_t* __restrict__ starts_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t* perm = reinterpret_cast<uint16_t*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t ntl = (n + TR - 1) / TR;
+  for (int64_t u = blockIdx.x; u < ntl * n_roles; u += gridDim.x) {
+    const int64_t tile = u % ntl;
+    const int cnt = (int)min((int64_t)TR, n - tile * TR);
+    uint32_t* pg = reinterpret_cast<uint32_t*>(perm_g + u * TR);
+    const uint16_t* sg = starts_g + u * (THREADS + 8);
+    __syncthreads();
+    for (int i = tid; i < (cnt + 1) / 2; i += THREADS) reinterpret_cast<uint32_t*>(perm)[i] = pg[i];
+    const int start = sg[tid], c = (int)sg[tid + 1] - start;
+    __syncthreads();
+    bank_aware_reorder(perm + start, c, lane);
+    __syncthreads();
+    for (int i = tid; i < (cnt + 1) / 2; i += THREADS) pg[i] = reinterpret_cast<const uint32_t*>(perm)[i];
+  }
+}
+
 // EMIT = false: sort the rows of every tile and sum them right away (rows streamed through once: the
 // host-buffer path).  EMIT = true: sort only and write the order -- per (role, tile) the sorted row indices and
 // the start offset of every cell -- for gram_cells_sorted_kernel: the cells of a row do not depend on beta,
@@ -910,42 +978,6 @@ gram_cells_kernel(int64_t n, int64_t np, const double* __restrict__ om, const do
     it.next();
     if (tid == 0 && it.valid()) load_cells(it);
     if (EMIT) {
-      // Bank-aware order inside every cell.  The sum kernels gather t_i, t_j and omega of row perm[start + s] for the
-      // 32 cells of a warp at once: a 64-bit shared-memory load of 32 unrelated rows costs about 4.2 wavefronts where
-      // 2 is the minimum (both half-warps on 16 distinct bank pairs, bank pair = row & 15) -- the shared-memory pipe,
-      // not the fp64 pipe, bounded the kernel.  The order of the rows of a cell is free, so step by step every lane
-      // picks, among the rows its cell has left, one whose bank pair no other lane of its half-warp has taken
-      // (four rounds of match / re-pick; a lane that runs out of candidates keeps a conflicting row).
-      {
-        int maxc = c;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
-        uint16_t* run = perm + start;
-        const unsigned half = (unsigned)lane & 16u;
-        for (int s = 0; s < maxc; ++s) {
-          const bool act = s < c;
-          int cand = s;
-          bool settled = false;
-#pragma unroll 1
-          for (int round = 0; round < 4; ++round) {
-            const unsigned key = act ? (((unsigned)run[cand] & 15u) | half) : (32u + (unsigned)lane);
-            const unsigned same = __match_any_sync(0xffffffffu, key);
-            const unsigned done = __ballot_sync(0xffffffffu, settled) & same;
-            const int winner = done ? (__ffs(done) - 1) : (__ffs(same) - 1);
-            if (act && !settled) {
-              if (lane == winner) settled = true;
-              else if (cand + 1 < c) ++cand;
-            }
-          }
-          if (act && cand != s) {
-            const uint16_t tmp = run[s];
-            run[s] = run[cand];
-            run[cand] = tmp;
-          }
-          __syncwarp();
-        }
-      }
-      __syncthreads();
       // the order of this (role, tile): sorted row indices, start of every cell, total, "careful" flag
       const int64_t ntl = (n + TR - 1) / TR;
       uint32_t* pg = reinterpret_cast<uint32_t*>(perm_g + ((int64_t)role * ntl + tile) * TR);
@@ -1913,6 +1945,29 @@ int pgb_cells_prepare(const pgb_model* M, const double* X, int64_t n, int64_t ld
   int rc = cells_launch_prepass(M, PGB_MODE_INIT, false, X, n, ld, X, nullptr, nullptr, L, grid1, st);
   if (rc != PGB_OK) return rc;
   return cells_emit_order(M, n, L, st);
+}
+
+// pgb_gram_refine: see gram_cells_refine_kernel
+int pgb_cells_refine(const pgb_model* M, int64_t n, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const pgb_model::Cells& C = M->cells;
+  CellWs L;
+  if (!cells_ws_layout(M, n, ws, ws_bytes, true, L)) {
+    pgb_set_error("pgb_gram_refine: workspace too small");
+    return PGB_EINVAL;
+  }
+  const int n_roles = (int)C.roles.size();
+  if (n_roles == 0) return PGB_OK;
+  const int TR = C.tile_rows;
+  const unsigned grid = (unsigned)std::min<int64_t>(L.ntl * n_roles, (int64_t)kSMs * 8);
+  switch (C.threads) {
+    case 256: gram_cells_refine_kernel<256><<<grid, 256, (size_t)TR * 2 + 64, st>>>(n, TR, n_roles, L.perm, L.starts); break;
+    case 320: gram_cells_refine_kernel<320><<<grid, 320, (size_t)TR * 2 + 64, st>>>(n, TR, n_roles, L.perm, L.starts); break;
+    case 384: gram_cells_refine_kernel<384><<<grid, 384, (size_t)TR * 2 + 64, st>>>(n, TR, n_roles, L.perm, L.starts); break;
+    default: gram_cells_refine_kernel<512><<<grid, 512, (size_t)TR * 2 + 64, st>>>(n, TR, n_roles, L.perm, L.starts); break;
+  }
+  PGB_CUDA(cudaGetLastError());
+  pgb_count_launch(1);
+  return PGB_OK;
 }
 
 int pgb_launch_gram_cells(const pgb_model* M, int32_t mode, const double* X, int64_t n, int64_t ld, const double* y,

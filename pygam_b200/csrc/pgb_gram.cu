@@ -1079,6 +1079,13 @@ extern "C" int pgb_gram_prepare(const pgb_model* M, const double* X, int64_t n, 
   return pgb_cells_prepare(M, X, n, ld, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+int pgb_cells_refine(const pgb_model* M, int64_t n, void* ws, int64_t ws_bytes, cudaStream_t st);  // pgb_cells.cu
+extern "C" int pgb_gram_refine(const pgb_model* M, int64_t n, void* ws, int64_t ws_bytes, void* stream) {
+  if (!M || !ws || n < 1) { pgb_set_error("pgb_gram_refine: bad arguments"); return PGB_EINVAL; }
+  if (!M->cells.enabled) return PGB_OK;
+  return pgb_cells_refine(M, n, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int pgb_gram_pass(const pgb_model* M, int32_t mode, const double* X, int64_t n, int64_t ld,
                              const double* y, const float* w, const double* beta, double* out, void* ws,
                              int64_t ws_bytes, void* stream) {

@@ -91,8 +91,15 @@ def _compare(gam, X, y, w=None, env=None, modes=(_lib.MODE_IRLS, _lib.MODE_INIT)
             unplanned = cells.gram_pass(data, coef, mode=mode).cpu().numpy()
         finally:
             cells.use_plan = True
-        # same sums, other order of the rows inside a cell (the prepared order is bank-aware): agreement to rounding
+        # same sums, same order of the rows inside a cell; the prepared prepass of an all-spline model rebuilds t from
+        # the stored centred coordinate (one rounding in lp): agreement to rounding
         assert np.abs(a - unplanned).max() <= 1e-13 * scale
+        # the optional second step of the preparation (pgb_gram_refine) reorders the rows inside every cell
+        cells.refine_order(data)
+        refined = cells.gram_pass(data, coef, mode=mode).cpu().numpy().copy()
+        assert np.abs(refined - b).max() <= 2e-13 * max(scale, np.abs(b[m * m:m * m + m]).max())
+        assert np.array_equal(refined, cells.gram_pass(data, coef, mode=mode).cpu().numpy())
+        cells._plan_key = None  # the next mode starts from a fresh preparation
     del torch
 
 
