@@ -400,9 +400,16 @@ extern "C" int pgb_interval_pass(const pgb_model* M, const double* X, int64_t n,
 // (B200: 62.7 fp64 FMA/clk/SM vs 6.5 TB/s), so both the instruction count per row and the bytes in
 // flight matter.
 //  * plain cubic s() terms (the `fast` flag) do not evaluate their four basis functions: every CTA
-//    turns beta into one cubic polynomial per knot interval (s_tab, four coefficients per interval,
-//    coefficient-major so that the four loads of a warp hit distinct banks or broadcast) and a row
-//    costs an interval search and a Horner step -- ten fp64 instructions per term instead of ~26.
+//    turns beta into one cubic polynomial per knot interval (s_tab, four coefficients per interval)
+//    and a row costs an interval search and a Horner step -- ten fp64 instructions per term instead
+//    of ~26.  What bounds the pass is the gather of those 32 bytes per (row, term) from shared
+//    memory: the rows of a warp sit in unrelated intervals, and a plain table costs 17 wavefronts per
+//    warp and term where 8 move the bytes (ncu, round 1).  The table is therefore stored as two
+//    16-byte halves per interval, (c0, c1) and (c2, c3), in `rep` = 8 copies: copy l lives entirely in
+//    the l-th group of four banks and is read by the lanes with (lane & 7) == l, so the eight lanes
+//    that share a wavefront of a 128-bit load never meet in a bank whatever their intervals are: two
+//    conflict-free LDS.128 per (row, term).  6 KB per term; with too many terms for that, rep = 1
+//    (template parameter REP: the second half of an entry sits at a compile-time offset).
 //    floor(s) is taken with a round-down add of 2^52 (no F2I / I2F conversions).  Rows outside the
 //    edge knots and every other kind of term go through eval_term as before.
 //  * one CTA walks tiles of R rows (round robin over a persistent grid).  Thread 0 issues one TMA bulk
@@ -414,7 +421,7 @@ extern "C" int pgb_interval_pass(const pgb_model* M, const double* X, int64_t n,
 #define PGB_PASS_MAX_FAST 48
 struct PassSpl {
   double lo, scale, dn;  // s = (x - lo) * scale is the position in knot intervals, scale = nint / span
-  int32_t feature, nint, coef, pad;
+  int32_t feature, nint, coef, toff;  // toff: byte offset of the feature's column in a staged tile
 };
 #define PGB_PASS_MAX_TE 8
 struct PassTe {  // te() of two cubic marginals: s_q = (x_q - lo_q) * scale_q, nint_q intervals, k1 = n_splines of marginal 1
@@ -427,14 +434,16 @@ __host__ __device__ inline bool pass_te_eligible(const DTerm& T) {
 }
 struct PassPlan {
   int32_t n_fast, n_other, icpt, tab_doubles, fast_limit, pitch;  // pitch: table entries per term (max nint + 2)
-  int32_t n_te, te_limit;
+  int32_t n_te, te_limit, rep_shift, pad;                          // 1 << rep_shift copies of every table
   PassTe te[PGB_PASS_MAX_TE];
   int16_t term[PGB_PASS_MAX_FAST];
   PassSpl spl[PGB_PASS_MAX_FAST];
 };
 
-static void pass_plan_build(const pgb_model* M, PassPlan& P) {
+static void pass_plan_build(const pgb_model* M, PassPlan& P, int rep_shift) {
   P.n_fast = P.n_other = P.tab_doubles = P.pitch = P.n_te = 0;
+  P.rep_shift = rep_shift;
+  P.pad = 0;
   P.te_limit = M->n_terms;
   P.icpt = -1;
   P.fast_limit = M->n_terms;
@@ -461,8 +470,7 @@ static void pass_plan_build(const pgb_model* M, PassPlan& P) {
     if (T.fast && P.fast_limit == M->n_terms) P.fast_limit = q;  // fast terms from here on take the general path
     ++P.n_other;
   }
-  P.pitch |= 1;  // odd pitch: the four coefficient arrays of an entry start in different banks
-  P.tab_doubles = 4 * P.pitch * P.n_fast;
+  P.tab_doubles = (4 * P.pitch * P.n_fast) << rep_shift;
 }
 
 // the terms that are not in the plan (f(), l(), te(), by=, other orders, cyclic bases): the general evaluation
@@ -528,59 +536,75 @@ __device__ __forceinline__ double pass_te_term(const PassTe& T, const double* s_
 }
 
 // lp of NR rows (row k through load[k]) -- the fast terms of all NR rows side by side (independent dependency chains).
-// Table of term q: s_tab[(4 q + p) * pitch + e], p = power, e = 1 + floor(s) clamped to 0 .. nint + 1.  Entry e in
+// Table of term q, as 16-byte pairs (c_2h, c_2h+1), h = 0, 1, of entry e: REP = 8: pair[2 q pitch 8 + (2 e + h) 8 + l],
+// l = copy; REP = 1: pair[(2 q + h) pitch + e].  e = 1 + floor(s) clamped to 0 .. nint + 1.  Entry e in
 // 1 .. nint is the cubic of knot interval e - 1; entries 0 and nint + 1 are the tangent lines at the two edge knots,
 // which is exactly the reference's linear extrapolation (utils.py:744-763); all in powers of s - (e - 1).
 // The first loop assumes 0 <= s < nint and only notes when that fails (a feature outside the edge knots or on the last
 // one, or a NaN); such a row is evaluated again by the second loop, which clamps the entry (a NaN stays a NaN: fmax
 // drops it from the entry choice, the power keeps it).
-template <int NR, bool OTHER, class Load>
+template <int REP>
+__device__ __forceinline__ int pass_tab_index(int e, int h, int l, int pitch) {
+  return REP == 8 ? (2 * e + h) * 8 + l : h * pitch + e;
+}
+
+template <int NR, bool OTHER, int REP, class Load>
 __device__ __forceinline__ void pass_lp(const PassPlan& P, const DTerm* s_terms, int n_terms, const double* s_beta,
                                         const double* s_tab, double icpt, const Load (&load)[NR], double (&lp)[NR]) {
   const double kC = 4503599627370497.0;  // 2^52 + 1: RD(s + kC) = kC + floor(s), exact for -1 <= s < 2^32
-  unsigned bad[NR];
+  bool bad[NR];
 #pragma unroll
-  for (int k = 0; k < NR; ++k) { lp[k] = icpt; bad[k] = 0u; }
+  for (int k = 0; k < NR; ++k) { lp[k] = icpt; bad[k] = false; }
   const int pitch = P.pitch;
+  const int hi_off = REP == 8 ? 8 : pitch;  // pairs between the two halves of an entry
+  const int stride = 2 * pitch * REP;       // pairs per term
+  const double2* tab0 = reinterpret_cast<const double2*>(s_tab) + (REP == 8 ? (threadIdx.x & 7) : 0);
   {
-    const double* tab = s_tab;
-    for (int q = 0; q < P.n_fast; ++q, tab += 4 * pitch) {
+    const double2* tab = tab0;
+    for (int q = 0; q < P.n_fast; ++q, tab += stride) {
       const PassSpl& S = P.spl[q];
       const double lo = S.lo, scale = S.scale;
-      const int f = S.feature;
+      const int f = S.feature, toff = S.toff;
       const unsigned ni = (unsigned)S.nint;
 #pragma unroll
       for (int k = 0; k < NR; ++k) {
-        const double s = (load[k](f) - lo) * scale;
+        const double s = (load[k].at(f, toff) - lo) * scale;
         const double r = __dadd_rd(s, kC);
         const unsigned e = (unsigned)__double2loint(r);
-        bad[k] |= (unsigned)(__double2hiint(r) ^ 0x43300000) | (unsigned)(e - 1u >= ni);
-        const double* tb = tab + min(e, ni + 1u);  // in bounds whatever s was
+        bad[k] = bad[k] || (e - 1u >= ni) || (__double2hiint(r) != 0x43300000);  // ISETP.OR into one predicate
+        const double2* tb = tab + (REP == 8 ? min(e, ni + 1u) << 4 : min(e, ni + 1u));  // in bounds whatever s was
         const double t = s - (r - kC);
-        lp[k] += fma(fma(fma(tb[3 * pitch], t, tb[2 * pitch]), t, tb[pitch]), t, tb[0]);
+        const double2 lo2 = tb[0], hi2 = tb[hi_off];
+        lp[k] += fma(fma(fma(hi2.y, t, hi2.x), t, lo2.y), t, lo2.x);
       }
     }
   }
   for (int q = 0; q < P.n_te; ++q) {
 #pragma unroll
-    for (int k = 0; k < NR; ++k) lp[k] += pass_te_term<false>(P.te[q], s_beta, load[k], bad[k]);
+    for (int k = 0; k < NR; ++k) {
+      unsigned b = 0u;
+      lp[k] += pass_te_term<false>(P.te[q], s_beta, load[k], b);
+      bad[k] = bad[k] || (b != 0u);
+    }
   }
 #pragma unroll
   for (int k = 0; k < NR; ++k) {
     if (bad[k]) {
       double v = icpt;
-      const double* tab = s_tab;
+      const double2* tab = tab0;
 #pragma unroll 1
-      for (int q = 0; q < P.n_fast; ++q, tab += 4 * pitch) {
+      for (int q = 0; q < P.n_fast; ++q, tab += stride) {
         const PassSpl& S = P.spl[q];
         const double s = (load[k](S.feature) - S.lo) * S.scale;
         const double r = __dadd_rd(fmin(fmax(s, -1.0), S.dn), kC);
-        const double* tb = tab + __double2loint(r);
+        const double2* tb = tab + (REP == 8 ? __double2loint(r) << 4 : __double2loint(r));
         const double t = s - (r - kC);
-        v += fma(fma(fma(tb[3 * pitch], t, tb[2 * pitch]), t, tb[pitch]), t, tb[0]);
+        const double2 lo2 = tb[0], hi2 = tb[hi_off];
+        v += fma(fma(fma(hi2.y, t, hi2.x), t, lo2.y), t, lo2.x);
       }
+      unsigned b = 0u;
 #pragma unroll 1
-      for (int q = 0; q < P.n_te; ++q) v += pass_te_term<true>(P.te[q], s_beta, load[k], bad[k]);
+      for (int q = 0; q < P.n_te; ++q) v += pass_te_term<true>(P.te[q], s_beta, load[k], b);
       lp[k] = v;
     }
   }
@@ -619,8 +643,8 @@ __device__ __forceinline__ void pass_finish(const Family& fam, double lp, int64_
 }
 
 // kPassThreads consumer threads (RPT rows each per tile) + one producer warp
-template <bool HAS_Y, bool FULL, int FAMK, int RPT, bool OTHER>
-__global__ void __launch_bounds__(kPassThreads + 32, 2)
+template <bool HAS_Y, bool FULL, int FAMK, int RPT, bool OTHER, int REP>
+__global__ void __launch_bounds__(kPassThreads + 32, 1)
 stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ g_terms, int n_terms, int m, int F,
                   Family fam_in, const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
                   const float* __restrict__ w, const double* __restrict__ beta, double scale, double ybar,
@@ -654,8 +678,8 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
   // one cubic per (fast term, knot interval): p(t) = sum_a beta[c + a] b_a(t) in powers of t; two tangent lines
   for (int q = 0; q < P.n_fast; ++q) {
     const PassSpl& S = P.spl[q];
-    const int pitch = P.pitch;
-    for (int e = tid; e < S.nint + 2; e += blockDim.x) {
+    for (int el = tid; el < (S.nint + 2) * REP; el += blockDim.x) {
+      const int e = el / REP, l = el % REP;
       const int ci = e == 0 ? 0 : (e > S.nint ? S.nint - 1 : e - 1);
       const double* b = s_beta + S.coef + ci;
       double c0 = (b[0] + 4.0 * b[1] + b[2]) * (1.0 / 6.0);
@@ -668,8 +692,9 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
         c1 = (b[3] - b[1]) * 0.5;
         c2 = 0.0; c3 = 0.0;
       }
-      double* tb = s_tab + (size_t)4 * q * pitch + e;
-      tb[0] = c0; tb[pitch] = c1; tb[2 * pitch] = c2; tb[3 * pitch] = c3;
+      double2* tb = reinterpret_cast<double2*>(s_tab) + (size_t)2 * q * P.pitch * REP;
+      tb[pass_tab_index<REP>(e, 0, l, P.pitch)] = make_double2(c0, c1);
+      tb[pass_tab_index<REP>(e, 1, l, P.pitch)] = make_double2(c2, c3);
     }
   }
   __syncthreads();
@@ -701,31 +726,46 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
   double acc[PGB_SS_COUNT];
 #pragma unroll
   for (int s = 0; s < PGB_SS_COUNT; ++s) acc[s] = 0.0;
-  // full tiles from the ring
+  // full tiles from the ring.  The predict instances with one row per thread take two tiles before they finish either:
+  // the inverse link of a row is one dependency chain (exp, a division), and two of them side by side give the warp more
+  // instructions to issue (config 2: 65 -> 68 % of the HBM peak; the statistics instances did not gain, measured).
   {
     int stage = 0;
     uint32_t round = 0;
-    for (int64_t t = blockIdx.x; t < n_bulk_tiles; t += gridDim.x) {
-      mbar_wait(smem_addr(&mbar[stage]), round & 1u);
-      const double* tile = tiles + (size_t)stage * stage_doubles;
-      const float* wt = wtiles + (size_t)stage * R;
-      const int64_t row0 = t * R;
-      LoadTile load[RPT];
-      double lp[RPT], yv[RPT], wv[RPT];
+    constexpr int NT = (RPT == 1 && !HAS_Y) ? 2 : 1;  // tiles per trip
+    for (int64_t t = blockIdx.x; t < n_bulk_tiles; t += (int64_t)NT * gridDim.x) {
+      double lp[NT][RPT], yv[NT][RPT], wv[NT][RPT];
+      const bool two = NT == 2 && t + gridDim.x < n_bulk_tiles;
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) load[k] = LoadTile{tile, R, tid + k * kPassThreads};
-      pass_lp<RPT, OTHER>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp);
+      for (int u = 0; u < NT; ++u) {
+        if (u == 1 && !two) break;
+        mbar_wait(smem_addr(&mbar[stage]), round & 1u);
+        const double* tile = tiles + (size_t)stage * stage_doubles;
+        const float* wt = wtiles + (size_t)stage * R;
+        LoadTile load[RPT];
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) {
-        const int r = tid + k * kPassThreads;
-        yv[k] = HAS_Y ? tile[(size_t)F * R + r] : 0.0;
-        wv[k] = use_w ? (double)wt[r] : 1.0;
+        for (int k = 0; k < RPT; ++k) load[k] = LoadTile{tile, R, tid + k * kPassThreads};
+        pass_lp<RPT, OTHER, REP>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp[u]);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int r = tid + k * kPassThreads;
+          yv[u][k] = HAS_Y ? tile[(size_t)F * R + r] : 0.0;
+          wv[u][k] = use_w ? (double)wt[r] : 1.0;
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(smem_addr(&mbar[NS + stage]));  // the stage can be refilled
+        if (++stage == NS) { stage = 0; ++round; }
       }
-      __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(smem_addr(&mbar[NS + stage]));  // the stage can be refilled
+      const int64_t row0 = t * R + tid;
+      if (two) {
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) pass_finish<HAS_Y, FULL>(fam, lp[k], row0 + tid + k * kPassThreads, yv[k], wv[k], scale, ybar, poisson_round, lp_out, mu_out, acc);
-      if (++stage == NS) { stage = 0; ++round; }
+        for (int u = 0; u < NT; ++u)
+          pass_finish<HAS_Y, FULL>(fam, lp[u][0], row0 + (int64_t)u * gridDim.x * R, yv[u][0], wv[u][0], scale, ybar, poisson_round, lp_out, mu_out, acc);
+      } else {
+#pragma unroll
+        for (int k = 0; k < RPT; ++k)
+          pass_finish<HAS_Y, FULL>(fam, lp[0][k], row0 + k * kPassThreads, yv[0][k], wv[0][k], scale, ybar, poisson_round, lp_out, mu_out, acc);
+      }
     }
   }
   // the remaining rows (and inputs that are not 16-byte aligned) with plain loads
@@ -735,7 +775,7 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
     for (; i + step < n; i += 2 * step) {
       const LoadGlobal load[2] = {LoadGlobal{X, ld, i}, LoadGlobal{X, ld, i + step}};
       double lp[2];
-      pass_lp<2, OTHER>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp);
+      pass_lp<2, OTHER, REP>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp);
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int64_t ik = i + k * step;
@@ -747,7 +787,7 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
   for (; i < n; i += step) {
     const LoadGlobal load[1] = {LoadGlobal{X, ld, i}};
     double lp[1];
-    pass_lp<1, OTHER>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp);
+    pass_lp<1, OTHER, REP>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp);
     pass_finish<HAS_Y, FULL>(fam, lp[0], i, HAS_Y ? __ldg(y + i) : 0.0, use_w ? (double)__ldg(w + i) : 1.0, scale, ybar, poisson_round,
                             lp_out, mu_out, acc);
   }
@@ -770,14 +810,14 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
   }
 }
 
-template <bool HAS_Y, bool FULL, int FAMK, int RPT, bool OTHER>
+template <bool HAS_Y, bool FULL, int FAMK, int RPT, bool OTHER, int REP>
 static int stats_pass_launch(const PassPlan& P, const pgb_model* M, int grid, size_t smem, cudaStream_t st, const double* X,
                              int64_t n, int64_t ld, const double* y, const float* w, const double* beta, double scale,
                              double ybar, int poisson_round, int NS, int64_t n_bulk_tiles, double* part, double* lp_out,
                              double* mu_out) {
-  PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<HAS_Y, FULL, FAMK, RPT, OTHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<HAS_Y, FULL, FAMK, RPT, OTHER, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kSmemMax));
-  stats_pass_kernel<HAS_Y, FULL, FAMK, RPT, OTHER><<<grid, kPassThreads + 32, smem, st>>>(
+  stats_pass_kernel<HAS_Y, FULL, FAMK, RPT, OTHER, REP><<<grid, kPassThreads + 32, smem, st>>>(
       P, M->d_terms, M->n_terms, M->m, M->n_features, M->fam, X, n, ld, y, w, beta, scale, ybar, poisson_round, NS,
       n_bulk_tiles, part, lp_out, mu_out);
   return PGB_OK;
@@ -790,43 +830,44 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
   if (!M || !X || !beta || n < 1 || ld < n) { pgb_set_error("pgb_stats_pass: bad arguments"); return PGB_EINVAL; }
   if (ws_bytes < pgb_stats_ws_bytes(M) || !ws) { pgb_set_error("pgb_stats_pass: workspace too small"); return PGB_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
-  PassPlan P;
-  pass_plan_build(M, P);
   const int F = M->n_features, ncol = F + (y ? 1 : 0);
-  const size_t fixed = (size_t)((M->m + 1) & ~1) * 8 + (size_t)P.tab_doubles * 8 + PGB_SS_COUNT * 32 * 8 + 2 * 8 * 8 +
-                       (size_t)M->n_terms * sizeof(DTerm);
   const size_t rowbytes = (size_t)ncol * 8 + 4;
-  // stages of R = RPT * 256 rows: two CTAs per SM when at least two stages fit in half of the shared memory; two rows
-  // per thread when that still leaves two stages (three for narrow rows)
-  int occ = 2, NS = 0, RPT = 1;
-  for (; occ >= 1; --occ) {
-    const size_t budget = (occ == 2 ? kSmemMax / 2 - 2048 : kSmemMax - 1024);
-    if (budget <= fixed) continue;
-    const size_t stages1 = (budget - fixed) / (kPassThreads * rowbytes);
-    if (stages1 >= 2) {
-      if (stages1 >= 4 && !(y && scale > 0.0) && !P.n_other) RPT = 2;
-      NS = (int)std::min<size_t>(4, stages1 / RPT);
+  const size_t budget = kSmemMax - 1024;
+  // one CTA of kPassThreads consumers per SM; stages of R = RPT * kPassThreads rows.  Eight copies of the interval
+  // tables when that leaves three stages, one copy otherwise; two rows per thread when four stages fit.
+  PassPlan P;
+  size_t fixed = 0;
+  int NS = 0, RPT = 1;
+  for (int rep_shift = 3; rep_shift >= 0; rep_shift -= 3) {
+    pass_plan_build(M, P, rep_shift);
+    fixed = (size_t)((M->m + 1) & ~1) * 8 + (size_t)P.tab_doubles * 8 + PGB_SS_COUNT * 32 * 8 + 2 * 8 * 8 +
+            (size_t)M->n_terms * sizeof(DTerm);
+    const size_t stages1 = budget > fixed ? (budget - fixed) / (kPassThreads * rowbytes) : 0;
+    if (stages1 >= 3 || rep_shift == 0) {
+      if (stages1 >= 2) {
+        if (stages1 >= 4 && !(y && scale > 0.0) && !P.n_other) RPT = 2;
+        NS = (int)std::min<size_t>(4, stages1 / RPT);
+      }
       break;
     }
   }
-  if (NS < 2) {  // rows too wide for two stages (F > ~110): no staging, every row through the plain-load path
+  if (NS < 2) {  // rows too wide for two stages (F > ~50): no staging, every row through the plain-load path
     NS = 0;
     RPT = 1;
-    occ = 2;
-    if (fixed > kSmemMax / 2 - 2048) occ = 1;
-    if (fixed > kSmemMax - 1024) {
+    if (fixed > budget) {
       pgb_set_error("pgb_stats_pass: the model (%d coefficients) does not fit shared memory", M->m);
       return PGB_EUNSUPPORTED;
     }
   }
   const int R = RPT * kPassThreads;
+  for (int q = 0; q < P.n_fast; ++q) P.spl[q].toff = P.spl[q].feature * R * 8;
   const size_t smem = fixed + (size_t)NS * R * rowbytes;
   // TMA bulk copies need 16-byte aligned sources: every column start and every tile start
   const bool bulk_ok = ((uintptr_t)X % 16 == 0) && (ld % 2 == 0) && (!y || (uintptr_t)y % 16 == 0) &&
                        (!w || (uintptr_t)w % 16 == 0);
   const int64_t n_bulk_tiles = (bulk_ok && NS >= 2) ? n / R : 0;
   const int64_t n_units = std::max<int64_t>(n_bulk_tiles, (n - n_bulk_tiles * R + kPassThreads - 1) / kPassThreads);
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, std::min(M->pass_ctas, kSMs * occ)));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, std::min(M->pass_ctas, kSMs)));
   const Family& fm = M->fam;
   const int famk = (fm.dist == PGB_DIST_NORMAL && fm.link == PGB_LINK_IDENTITY)   ? 1
                    : (fm.dist == PGB_DIST_BINOMIAL && fm.link == PGB_LINK_LOGIT) ? 2
@@ -834,12 +875,15 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
                                                                                  : 0;
   int rc = PGB_OK;
 #define PGB_STATS_ARGS P, M, grid, smem, st, X, n, ld, y, w, beta, scale, ybar, poisson_round, NS, n_bulk_tiles, (double*)ws, lp_out, mu_out
-#define PGB_STATS_FAM(HY, FL, RP, OT)                                             \
-  switch (famk) {                                                                 \
-    case 1: rc = stats_pass_launch<HY, FL, 1, RP, OT>(PGB_STATS_ARGS); break;     \
-    case 2: rc = stats_pass_launch<HY, FL, 2, RP, OT>(PGB_STATS_ARGS); break;     \
-    case 3: rc = stats_pass_launch<HY, FL, 3, RP, OT>(PGB_STATS_ARGS); break;     \
-    default: rc = stats_pass_launch<HY, FL, 0, RP, OT>(PGB_STATS_ARGS); break;    \
+#define PGB_STATS_REP(HY, FL, FK, RP, OT)                                        \
+  rc = P.rep_shift ? stats_pass_launch<HY, FL, FK, RP, OT, 8>(PGB_STATS_ARGS)       \
+                   : stats_pass_launch<HY, FL, FK, RP, OT, 1>(PGB_STATS_ARGS);
+#define PGB_STATS_FAM(HY, FL, RP, OT)                        \
+  switch (famk) {                                            \
+    case 1: PGB_STATS_REP(HY, FL, 1, RP, OT) break;          \
+    case 2: PGB_STATS_REP(HY, FL, 2, RP, OT) break;          \
+    case 3: PGB_STATS_REP(HY, FL, 3, RP, OT) break;          \
+    default: PGB_STATS_REP(HY, FL, 0, RP, OT) break;         \
   }
 #define PGB_STATS_RPT(HY, FL)                                  \
   if (P.n_other) { PGB_STATS_FAM(HY, FL, 1, true) }            \
@@ -852,6 +896,7 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
   else { PGB_STATS_RPT(true, false) }
 #undef PGB_STATS_RPT
 #undef PGB_STATS_FAM
+#undef PGB_STATS_REP
 #undef PGB_STATS_ARGS
   if (rc != PGB_OK) return rc;
   PGB_LAUNCHED(1);

@@ -154,11 +154,16 @@ struct LoadGlobal {
   const double* __restrict__ X;
   int64_t ld, row;
   __device__ __forceinline__ double operator()(int f) const { return __ldg(X + (int64_t)f * ld + row); }
+  __device__ __forceinline__ double at(int f, int) const { return __ldg(X + (int64_t)f * ld + row); }
 };
 struct LoadTile {
   const double* tile;  // [n_features][tile_ld], element (f, r) at tile[f * tile_ld + r]
   int tile_ld, r;
   __device__ __forceinline__ double operator()(int f) const { return tile[f * tile_ld + r]; }
+  // the same element through its precomputed byte offset f * tile_ld * 8
+  __device__ __forceinline__ double at(int, int byte_off) const {
+    return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tile + r) + byte_off);
+  }
 };
 
 template <class Emit, class Load>
