@@ -80,6 +80,10 @@ typedef struct pgb_model_info {
   int64_t pass_ws_bytes;/* workspace pgb_stats_pass needs                       */
   int32_t cell_roles;   /* > 0: the Gram pass runs cell-owned (all-spline model), this many roles */
   int32_t cell_tile_rows;/* rows per shared-memory tile of the cell-owned Gram pass */
+  int32_t cell_threads; /* threads per CTA of the spline-pair kernel (256, 320, 384 or 512)   */
+  int32_t cell_ring_groups; /* > 0: gram_cells_ring_kernel (one CTA per SM); 0: gram_cells_sorted_kernel, two CTAs per SM */
+  int32_t cell_generic_roles; /* roles of the te()/f()/l() kernel among cell_roles           */
+  int32_t reserved0;
 } pgb_model_info;
 
 const char* pgb_last_error(void);

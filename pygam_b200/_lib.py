@@ -63,6 +63,10 @@ class PgbModelInfo(C.Structure):
         ("pass_ws_bytes", C.c_int64),
         ("cell_roles", C.c_int32),
         ("cell_tile_rows", C.c_int32),
+        ("cell_threads", C.c_int32),
+        ("cell_ring_groups", C.c_int32),
+        ("cell_generic_roles", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

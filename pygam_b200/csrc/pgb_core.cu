@@ -216,6 +216,10 @@ extern "C" int pgb_model_get_info(const pgb_model* M, pgb_model_info* info) {
   info->pass_ws_bytes = pgb_stats_ws_bytes(M);
   info->cell_roles = M->cells.enabled ? (int32_t)(M->cells.roles.size() + M->cells.groles.size()) : 0;
   info->cell_tile_rows = M->cells.enabled ? M->cells.tile_rows : 0;
+  info->cell_threads = M->cells.enabled ? M->cells.threads : 0;
+  info->cell_ring_groups = M->cells.enabled ? M->cells.ring_groups : 0;
+  info->cell_generic_roles = M->cells.enabled ? (int32_t)M->cells.groles.size() : 0;
+  info->reserved0 = 0;
   return PGB_OK;
 }
 

@@ -352,7 +352,10 @@ class Engine:
             self.refine_order(data)
         return _lib.MODE_PLANNED
 
-    REFINE_AFTER_PASSES = 10
+    # pgb_gram_refine costs 1.5 (config 3) to 3.5 (config 2) Gram passes and saves 1-11 % of every later one
+    # (profiles/r2_kbench.log): it pays after 28-140 passes.  A shard that has been passed over 50 times (a grid
+    # search or bootstrap refits, not a single fit) is expected to be passed over as often again.
+    REFINE_AFTER_PASSES = 50
 
     def refine_order(self, data):
         """pgb_gram_refine on the prepared order of `data` (once per preparation)"""

@@ -2,6 +2,7 @@
 # Round-2 measurement job (one gpurun call on a 1-GPU box):  gpurun --timeout 1500 -- 'bash tools/gpu_job_r2.sh'
 # GPU parity suite, the bench line of both arms, kernel timings, the ncu launch list of the bench command and the
 # ncu --set full captures of the Gram kernels; everything goes to gpurun_out/ (summaries are copied to profiles/).
+# gpurun copies at most 64 MiB back: the capture of the statistics pass is its own job (tools/gpu_job_r2_stats.sh).
 set -x
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest exit $?"
@@ -25,8 +26,4 @@ $K2 > gpurun_out/plain_k2.log 2>&1 && ncu --set full --clock-control none --impo
 K3="python tools/kbench.py --case c3_poisson --rows 2000000 --only-gram --reps 1"
 $K3 > gpurun_out/plain_k3.log 2>&1 && ncu --set full --clock-control none --import-source on \
   -k regex:"gram_cells_sorted|gram_cells_generic|gram_prepass_mixed" -s 12 -c 3 -f -o gpurun_out/r2_ncu_c3_gram $K3 > gpurun_out/ncu_k3.log 2>&1
-# the statistics / predict pass of config 2
-P2="python tools/passbench.py --case c2_logistic --rows 8000000 --profile --reps 2"
-$P2 > gpurun_out/plain_p2.log 2>&1 && ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -k regex:stats_pass -f -o gpurun_out/r2_ncu_stats_c2 $P2 > gpurun_out/ncu_p2.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

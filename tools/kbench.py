@@ -45,19 +45,33 @@ def main():
     lib = _lib.load()
     coef = gam.coef_
     _lib.check(lib.pgb_gram_timing(eng.handle, 1), "timing")
-    ms, rs, ts = [], [], []
-    for _ in range(a.reps + 2):
-        eng.gram_pass(data, coef)
-        f, r, t = C.c_float(), C.c_float(), C.c_float()
-        _lib.check(lib.pgb_gram_last_ms(eng.handle, C.byref(r), C.byref(f), C.byref(t)), "ms")
-        ms.append(f.value)
-        rs.append(r.value)
-        ts.append(t.value)
-    g, r, t = float(np.median(ms[2:])), float(np.median(rs[2:])), float(np.median(ts[2:]))
-    path = (f"cells roles={eng.info.cell_roles} tile={eng.info.cell_tile_rows}" if eng.info.cell_roles else
+    eng.REFINE_AFTER_PASSES = 1 << 40  # the second preparation step is run (and timed) explicitly below
+    path = (f"cells roles={eng.info.cell_roles} tile={eng.info.cell_tile_rows} threads={eng.info.cell_threads} "
+            f"ring_groups={eng.info.cell_ring_groups}" if eng.info.cell_roles else
             f"roles={eng.info.n_roles} tile={eng.info.tile_rows} ctas={eng.info.gram_ctas}")
-    print(f"{a.case} n={a.rows} m={eng.m} {path}: "
-          f"records {r:.3f} ms | accum {g:.3f} ms | pass {t:.3f} ms = {a.rows / t / 1e3:.3e} Mrows/s")
+
+    def measure(tag):
+        ms, rs, ts = [], [], []
+        for _ in range(a.reps + 2):
+            eng.gram_pass(data, coef)
+            f, r, t = C.c_float(), C.c_float(), C.c_float()
+            _lib.check(lib.pgb_gram_last_ms(eng.handle, C.byref(r), C.byref(f), C.byref(t)), "ms")
+            ms.append(f.value)
+            rs.append(r.value)
+            ts.append(t.value)
+        g, r, t = float(np.median(ms[2:])), float(np.median(rs[2:])), float(np.median(ts[2:]))
+        print(f"{a.case} n={a.rows} m={eng.m} {path} [{tag}]: "
+              f"records {r:.3f} ms | accum {g:.3f} ms | pass {t:.3f} ms = {a.rows / t / 1e3:.3e} Mrows/s")
+
+    measure("prepared")
+    if eng.info.cell_roles and not a.only_gram:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.refine_order(data)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"  pgb_gram_refine: {e0.elapsed_time(e1):.3f} ms")
+        measure("prepared + refined")
     if a.only_gram:
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
