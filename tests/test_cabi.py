@@ -41,7 +41,7 @@ def test_struct_layout_matches_header():
 
     # pgb_term: 2 + 4*4 int32, 8 doubles, 4 int32 -> 72 + 64 + 16 = 152 bytes
     assert ctypes.sizeof(_lib.PgbTerm) == 152
-    assert ctypes.sizeof(_lib.PgbModelInfo) == 48
+    assert ctypes.sizeof(_lib.PgbModelInfo) == 64  # 6 int32, 2 int64, 6 int32
 
 
 def test_no_cpu_fallback(monkeypatch):
