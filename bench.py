@@ -349,9 +349,10 @@ def cells_kernel_names(info):
     """the kernels of a prepared cell-owned Gram pass of this model, as the launch list names them"""
     th = info.cell_threads
     pair = f"gram_cells_ring_kernel<{th}, {info.cell_ring_groups}>" if info.cell_ring_groups > 0 else f"gram_cells_sorted_kernel<{th}, 2>"
+    irls = "stats_pass_kernel<1, 2, ...> (the IRLS step: omega, omega z per row)"
     if info.cell_generic_roles > 0:
-        return f"gram_prepass_mixed_kernel + {pair} + gram_cells_generic_kernel"
-    return f"gram_prepass_planned_kernel + {pair}"
+        return f"{irls} + {pair} + gram_cells_generic_kernel"
+    return f"{irls} + {pair}"
 
 
 def run_config(name, args, torch, dist, pg, dev, rank, world, hbm_peak):

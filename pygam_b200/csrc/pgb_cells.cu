@@ -1919,6 +1919,13 @@ static int cells_launch_prepass(const pgb_model* M, int32_t mode, bool planned, 
   const pgb_model::Cells& C = M->cells;
   grid1 = (int)std::min<int64_t>((n + kPreThreads - 1) / kPreThreads, (int64_t)kSMs * 8);
   const size_t pre_smem = cells_pre_smem(M);
+  if (planned && mode == PGB_MODE_IRLS) {
+    // a prepared shard needs only omega and omega z of every row: the O(k) pass of pgb_core.cu (TMA-staged columns, one
+    // cubic per knot interval from a conflict-free table) does that at twice the rate of the record kernels below
+    const int rc = pgb_pass_irls(M, X, n, ld, y, w, beta, L.om, L.omz, L.scal_part, &grid1, st);
+    if (rc != PGB_EUNSUPPORTED) return rc;
+    grid1 = (int)std::min<int64_t>((n + kPreThreads - 1) / kPreThreads, (int64_t)kSMs * 8);
+  }
   if (C.mixed)
     gram_prepass_mixed_kernel<<<grid1, kPreThreads, pre_smem, st>>>(M->d_terms, M->n_terms, M->m, M->fam, mode, X, n, ld, y, w, beta,
                                                                     L.np, L.om, L.omz, L.tq, L.cq, L.scal_part);

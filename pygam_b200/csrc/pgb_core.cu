@@ -618,11 +618,31 @@ __device__ __forceinline__ void pass_lp(const PassPlan& P, const DTerm* s_terms,
   }
 }
 
-// link, deviance and the statistics sums of one row
-template <bool HAS_Y, bool FULL>
+// What a pass does with the linear predictor of a row (template parameter FIN)
+enum { PASS_STATS = 0,   // mu, deviance and the sums of pgb_stats_pass
+       PASS_FULL = 1,    // + log-likelihood and the null model (scale known)
+       PASS_IRLS = 2 };  // the IRLS step of a Gram pass: omega, omega z (written to lp_out, mu_out) and the PGB_GS_* sums
+
+// link, deviance and the statistics sums of one row; wi: the weight, for PASS_IRLS its float32 reciprocal (weight_inv)
+template <bool HAS_Y, int FIN>
 __device__ __forceinline__ void pass_finish(const Family& fam, double lp, int64_t gi, double yi, double wi, double scale,
                                             double ybar, int poisson_round, double* __restrict__ lp_out,
                                             double* __restrict__ mu_out, double (&acc)[PGB_SS_COUNT]) {
+  if (FIN == PASS_IRLS) {  // the same row arithmetic and sums as gram_prepass_kernel (pgb_cells.cu)
+    const IrlsRow ir = irls_row(fam, lp, yi, wi);
+    const double o = ir.omega, oz = ir.omega * ir.z;
+    if (ir.keep) {
+      acc[PGB_GS_NUSED] += 1.0;
+      acc[PGB_GS_DEV] += dist_dev(fam, yi, ir.mu);
+      acc[PGB_GS_NCORRECT] += (yi == ((ir.mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
+    }
+    acc[PGB_GS_NROWS] += 1.0;
+    acc[PGB_GS_COUNT] += o;
+    acc[PGB_GS_COUNT + 1] += oz;
+    lp_out[gi] = o;
+    mu_out[gi] = oz;
+    return;
+  }
   const double mu = link_inv(fam, lp);
   if (lp_out) lp_out[gi] = lp;
   if (mu_out) mu_out[gi] = mu;
@@ -637,7 +657,7 @@ __device__ __forceinline__ void pass_finish(const Family& fam, double lp, int64_
     acc[PGB_SS_NCORRECT] += (yi == ((mu > 0.5) ? 1.0 : 0.0)) ? 1.0 : 0.0;
     acc[PGB_SS_SUMY] += yi;
     acc[PGB_SS_SUMW] += wi;
-    if (FULL) {
+    if (FIN == PASS_FULL) {
       const double yl = poisson_round ? rint(yi * wi) : yi;  // pygam.py:2797-2798
       acc[PGB_SS_LOGLIK] += dist_logpdf(fam, yl, mu, wi, scale);
       acc[PGB_SS_NULL_WDEV] += wi * dist_dev(fam, yi, ybar);
@@ -646,8 +666,14 @@ __device__ __forceinline__ void pass_finish(const Family& fam, double lp, int64_
   }
 }
 
+template <int FIN>
+__device__ __forceinline__ double pass_weight(const float* __restrict__ w, int64_t i) {
+  if (FIN == PASS_IRLS) return weight_inv(w, i);
+  return w ? (double)__ldg(w + i) : 1.0;
+}
+
 // kPassThreads consumer threads (RPT rows each per tile) + one producer warp
-template <bool HAS_Y, bool FULL, int FAMK, int RPT, bool OTHER, int REP>
+template <bool HAS_Y, int FIN, int FAMK, int RPT, bool OTHER, int REP>
 __global__ void __launch_bounds__(kPassThreads + 32, 1)
 stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ g_terms, int n_terms, int m, int F,
                   Family fam_in, const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
@@ -754,7 +780,7 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
         for (int k = 0; k < RPT; ++k) {
           const int r = tid + k * kPassThreads;
           yv[u][k] = HAS_Y ? tile[(size_t)F * R + r] : 0.0;
-          wv[u][k] = use_w ? (double)wt[r] : 1.0;
+          wv[u][k] = !use_w ? 1.0 : FIN == PASS_IRLS ? (double)__fdiv_rn(1.0f, wt[r]) : (double)wt[r];
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(smem_addr(&mbar[NS + stage]));  // the stage can be refilled
@@ -764,11 +790,11 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
       if (two) {
 #pragma unroll
         for (int u = 0; u < NT; ++u)
-          pass_finish<HAS_Y, FULL>(fam, lp[u][0], row0 + (int64_t)u * gridDim.x * R, yv[u][0], wv[u][0], scale, ybar, poisson_round, lp_out, mu_out, acc);
+          pass_finish<HAS_Y, FIN>(fam, lp[u][0], row0 + (int64_t)u * gridDim.x * R, yv[u][0], wv[u][0], scale, ybar, poisson_round, lp_out, mu_out, acc);
       } else {
 #pragma unroll
         for (int k = 0; k < RPT; ++k)
-          pass_finish<HAS_Y, FULL>(fam, lp[0][k], row0 + k * kPassThreads, yv[0][k], wv[0][k], scale, ybar, poisson_round, lp_out, mu_out, acc);
+          pass_finish<HAS_Y, FIN>(fam, lp[0][k], row0 + k * kPassThreads, yv[0][k], wv[0][k], scale, ybar, poisson_round, lp_out, mu_out, acc);
       }
     }
   }
@@ -783,7 +809,7 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int64_t ik = i + k * step;
-        pass_finish<HAS_Y, FULL>(fam, lp[k], ik, HAS_Y ? __ldg(y + ik) : 0.0, use_w ? (double)__ldg(w + ik) : 1.0, scale, ybar,
+        pass_finish<HAS_Y, FIN>(fam, lp[k], ik, HAS_Y ? __ldg(y + ik) : 0.0, pass_weight<FIN>(use_w ? w : nullptr, ik), scale, ybar,
                                  poisson_round, lp_out, mu_out, acc);
       }
     }
@@ -792,7 +818,7 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
     const LoadGlobal load[1] = {LoadGlobal{X, ld, i}};
     double lp[1];
     pass_lp<1, OTHER, REP>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp);
-    pass_finish<HAS_Y, FULL>(fam, lp[0], i, HAS_Y ? __ldg(y + i) : 0.0, use_w ? (double)__ldg(w + i) : 1.0, scale, ybar, poisson_round,
+    pass_finish<HAS_Y, FIN>(fam, lp[0], i, HAS_Y ? __ldg(y + i) : 0.0, pass_weight<FIN>(use_w ? w : nullptr, i), scale, ybar, poisson_round,
                             lp_out, mu_out, acc);
   }
   // fixed-order sum of the consumer threads (the producer warp has left: a named barrier of the consumers only)
@@ -806,34 +832,33 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
       if (lane == 0) s_red[s * 32 + warp] = v;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kPassThreads) : "memory");
-    if (tid < PGB_SS_COUNT) {
+    constexpr int NPART = FIN == PASS_IRLS ? PGB_GS_COUNT + 2 : PGB_SS_COUNT;  // the Gram pass reduces PGB_GS_COUNT + 2 sums per CTA
+    if (tid < NPART) {
       double v = 0.0;
       for (int wq = 0; wq < kPassThreads / 32; ++wq) v += s_red[tid * 32 + wq];
-      part[(int64_t)blockIdx.x * PGB_SS_COUNT + tid] = v;
+      part[(int64_t)blockIdx.x * NPART + tid] = v;
     }
   }
 }
 
-template <bool HAS_Y, bool FULL, int FAMK, int RPT, bool OTHER, int REP>
+template <bool HAS_Y, int FIN, int FAMK, int RPT, bool OTHER, int REP>
 static int stats_pass_launch(const PassPlan& P, const pgb_model* M, int grid, size_t smem, cudaStream_t st, const double* X,
                              int64_t n, int64_t ld, const double* y, const float* w, const double* beta, double scale,
                              double ybar, int poisson_round, int NS, int64_t n_bulk_tiles, double* part, double* lp_out,
                              double* mu_out) {
-  PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<HAS_Y, FULL, FAMK, RPT, OTHER, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<HAS_Y, FIN, FAMK, RPT, OTHER, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kSmemMax));
-  stats_pass_kernel<HAS_Y, FULL, FAMK, RPT, OTHER, REP><<<grid, kPassThreads + 32, smem, st>>>(
+  stats_pass_kernel<HAS_Y, FIN, FAMK, RPT, OTHER, REP><<<grid, kPassThreads + 32, smem, st>>>(
       P, M->d_terms, M->n_terms, M->m, M->n_features, M->fam, X, n, ld, y, w, beta, scale, ybar, poisson_round, NS,
       n_bulk_tiles, part, lp_out, mu_out);
   return PGB_OK;
 }
 
-extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, int64_t ld,
-                              const double* y, const float* w, const double* beta, double scale,
-                              double ybar, int32_t poisson_round, double* scalars, double* lp_out,
-                              double* mu_out, void* ws, int64_t ws_bytes, void* stream) {
-  if (!M || !X || !beta || n < 1 || ld < n) { pgb_set_error("pgb_stats_pass: bad arguments"); return PGB_EINVAL; }
-  if (ws_bytes < pgb_stats_ws_bytes(M) || !ws) { pgb_set_error("pgb_stats_pass: workspace too small"); return PGB_EINVAL; }
-  cudaStream_t st = (cudaStream_t)stream;
+// One O(k)-per-row pass over the rows: plan, shared-memory budget, grid and the template instance.  fin: PASS_STATS /
+// PASS_FULL / PASS_IRLS; part receives the per-CTA sums (*grid_out CTAs).
+static int pass_run(const pgb_model* M, const double* X, int64_t n, int64_t ld, const double* y, const float* w,
+                    const double* beta, double scale, double ybar, int32_t poisson_round, int fin, double* part,
+                    double* lp_out, double* mu_out, int* grid_out, cudaStream_t st) {
   const int F = M->n_features, ncol = F + (y ? 1 : 0);
   const size_t rowbytes = (size_t)ncol * 8 + 4;
   const size_t budget = kSmemMax - 1024;
@@ -849,7 +874,7 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
     const size_t stages1 = budget > fixed ? (budget - fixed) / (kPassThreads * rowbytes) : 0;
     if (stages1 >= 3 || rep_shift == 0) {
       if (stages1 >= 2) {
-        if (stages1 >= 4 && !(y && scale > 0.0) && !P.n_other) RPT = 2;
+        if (stages1 >= 4 && fin != PASS_FULL && !P.n_other) RPT = 2;
         NS = (int)std::min<size_t>(4, stages1 / RPT);
       }
       break;
@@ -878,7 +903,7 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
                    : (fm.dist == PGB_DIST_POISSON && fm.link == PGB_LINK_LOG)    ? 3
                                                                                  : 0;
   int rc = PGB_OK;
-#define PGB_STATS_ARGS P, M, grid, smem, st, X, n, ld, y, w, beta, scale, ybar, poisson_round, NS, n_bulk_tiles, (double*)ws, lp_out, mu_out
+#define PGB_STATS_ARGS P, M, grid, smem, st, X, n, ld, y, w, beta, scale, ybar, poisson_round, NS, n_bulk_tiles, part, lp_out, mu_out
 #define PGB_STATS_REP(HY, FL, FK, RP, OT)                                        \
   rc = P.rep_shift ? stats_pass_launch<HY, FL, FK, RP, OT, 8>(PGB_STATS_ARGS)       \
                    : stats_pass_launch<HY, FL, FK, RP, OT, 1>(PGB_STATS_ARGS);
@@ -893,11 +918,12 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
   if (P.n_other) { PGB_STATS_FAM(HY, FL, 1, true) }            \
   else if (RPT == 2) { PGB_STATS_FAM(HY, FL, 2, false) }       \
   else { PGB_STATS_FAM(HY, FL, 1, false) }
-  if (y && scale > 0.0) {
-    if (P.n_other) { PGB_STATS_FAM(true, true, 1, true) }
-    else { PGB_STATS_FAM(true, true, 1, false) }
-  } else if (!y) { PGB_STATS_RPT(false, false) }
-  else { PGB_STATS_RPT(true, false) }
+  if (fin == PASS_FULL) {
+    if (P.n_other) { PGB_STATS_FAM(true, PASS_FULL, 1, true) }
+    else { PGB_STATS_FAM(true, PASS_FULL, 1, false) }
+  } else if (fin == PASS_IRLS) { PGB_STATS_RPT(true, PASS_IRLS) }
+  else if (!y) { PGB_STATS_RPT(false, PASS_STATS) }
+  else { PGB_STATS_RPT(true, PASS_STATS) }
 #undef PGB_STATS_RPT
 #undef PGB_STATS_FAM
 #undef PGB_STATS_REP
@@ -905,10 +931,33 @@ extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, in
   if (rc != PGB_OK) return rc;
   PGB_LAUNCHED(1);
   PGB_CUDA(cudaGetLastError());
+  *grid_out = grid;
+  return PGB_OK;
+}
+
+extern "C" int pgb_stats_pass(const pgb_model* M, const double* X, int64_t n, int64_t ld,
+                              const double* y, const float* w, const double* beta, double scale,
+                              double ybar, int32_t poisson_round, double* scalars, double* lp_out,
+                              double* mu_out, void* ws, int64_t ws_bytes, void* stream) {
+  if (!M || !X || !beta || n < 1 || ld < n) { pgb_set_error("pgb_stats_pass: bad arguments"); return PGB_EINVAL; }
+  if (ws_bytes < pgb_stats_ws_bytes(M) || !ws) { pgb_set_error("pgb_stats_pass: workspace too small"); return PGB_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = 0;
+  const int rc = pass_run(M, X, n, ld, y, w, beta, scale, ybar, poisson_round, (y && scale > 0.0) ? PASS_FULL : PASS_STATS,
+                          (double*)ws, lp_out, mu_out, &grid, st);
+  if (rc != PGB_OK) return rc;
   if (scalars) {
     scalar_reduce_kernel<<<1, 32 * PGB_SS_COUNT, 0, st>>>((const double*)ws, grid, PGB_SS_COUNT, scalars, 0);
     PGB_LAUNCHED(1);
     PGB_CUDA(cudaGetLastError());
   }
   return PGB_OK;
+}
+
+// The IRLS step of a Gram pass over a prepared shard (pgb_cells.cu): lp from X through the pass above, omega and
+// omega z per row, the PGB_GS_* sums and sum omega, sum omega z per CTA in scal_part (*grid_out parts).  Nothing the
+// prepared shard stores is read or written.
+int pgb_pass_irls(const pgb_model* M, const double* X, int64_t n, int64_t ld, const double* y, const float* w,
+                  const double* beta, double* om, double* omz, double* scal_part, int* grid_out, cudaStream_t st) {
+  return pass_run(M, X, n, ld, y, w, beta, -1.0, 0.0, 0, PASS_IRLS, scal_part, om, omz, grid_out, st);
 }

@@ -232,6 +232,9 @@ struct pgb_model {
   } timing;
 };
 
+// pgb_core.cu: the IRLS step of a Gram pass as an instance of the O(k) pass kernel (stats_pass_kernel)
+int pgb_pass_irls(const pgb_model* M, const double* X, int64_t n, int64_t ld, const double* y, const float* w,
+                  const double* beta, double* om, double* omz, double* scal_part, int* grid_out, cudaStream_t st);
 void pgb_count_launch(int n);
 void pgb_set_error(const char* fmt, ...);
 int pgb_cuda_fail(cudaError_t e, const char* what);

@@ -20,10 +20,10 @@ B="python bench.py --steps 2 --warmup 3 --configs none --no-cpu-baseline --no-e2
 $B > gpurun_out/plain_b.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
   --log-file gpurun_out/r2_launches_bench.csv $B > gpurun_out/ncu_b.log 2>&1
 # the Gram kernels of config 2 (prepass + ring) and of config 3 (sorted + generic), full sets with source
-K2="python tools/kbench.py --case c2_logistic --rows 8000000 --only-gram --reps 1"
-$K2 > gpurun_out/plain_k2.log 2>&1 && ncu --set full --clock-control none --import-source on \
-  -k regex:"gram_cells_ring|gram_prepass_planned" -s 8 -c 2 -f -o gpurun_out/r2_ncu_c2_gram $K2 > gpurun_out/ncu_k2.log 2>&1
-K3="python tools/kbench.py --case c3_poisson --rows 2000000 --only-gram --reps 1"
-$K3 > gpurun_out/plain_k3.log 2>&1 && ncu --set full --clock-control none --import-source on \
-  -k regex:"gram_cells_sorted|gram_cells_generic|gram_prepass_mixed" -s 12 -c 3 -f -o gpurun_out/r2_ncu_c3_gram $K3 > gpurun_out/ncu_k3.log 2>&1
+K2="python tools/kbench.py --case c2_logistic --rows 8000000 --only-gram --reps 1 --profile"
+$K2 > gpurun_out/plain_k2.log 2>&1 && ncu --set full --clock-control none \
+  --profile-from-start off -k regex:"gram_cells_ring|stats_pass_kernel" -f -o gpurun_out/r2_ncu_c2_gram $K2 > gpurun_out/ncu_k2.log 2>&1
+K3="python tools/kbench.py --case c3_poisson --rows 2000000 --only-gram --reps 1 --profile"
+$K3 > gpurun_out/plain_k3.log 2>&1 && ncu --set full --clock-control none \
+  --profile-from-start off -k regex:"gram_cells_sorted|gram_cells_generic|stats_pass_kernel" -f -o gpurun_out/r2_ncu_c3_gram $K3 > gpurun_out/ncu_k3.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

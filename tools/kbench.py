@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--only-gram", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around one Gram pass of the prepared "
+                    "shard (ncu --profile-from-start off)")
     a = ap.parse_args()
     gen, F = GEN[a.case]
     Xs, ys = gen(20000)
@@ -64,6 +66,12 @@ def main():
               f"records {r:.3f} ms | accum {g:.3f} ms | pass {t:.3f} ms = {a.rows / t / 1e3:.3e} Mrows/s")
 
     measure("prepared")
+    if a.profile:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        eng.gram_pass(data, coef)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     if eng.info.cell_roles and not a.only_gram:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
