@@ -20,10 +20,14 @@ def test_cell_plan_of_all_spline_models():
     _, info, errs = plan_for(cases.FIT_CASES["c2_logistic"], rng.random((50, 10)))
     assert errs == 0
     assert info.cell_roles == 55 and info.cell_tile_rows >= 1024  # 45 pairs + 10 diagonal blocks
+    # 22 x 22 knot cells per pair: 512-thread CTAs, the ring kernel, no generic roles
+    assert (info.cell_threads, info.cell_ring_groups, info.cell_generic_roles) == (512, 1, 0)
     # f(), l() and te() of two cubic marginals are generic pairs of the same pass (configs 1 and 3) ...
     _, info1, e1 = plan_for(cases.FIT_CASES["c1_wage"], helpers.load("fit_c1_wage")["X"])
     _, info3, e3 = plan_for(cases.FIT_CASES["c3_poisson"], rng.random((50, 24)))
     assert info1.cell_roles > 3 and info3.cell_roles > 210 + 40 and (e1, e3) == (0, 0)
+    # config 3: 17 x 17 cells per spline pair (320-thread CTAs, two per SM), te() pairs in the generic kernel
+    assert (info3.cell_threads, info3.cell_ring_groups) == (320, 0) and info3.cell_generic_roles > 40
     # ... other spline orders, cyclic bases and by= keep the general path
     _, infom, em = plan_for(cases.FIT_CASES["mixed_terms"], helpers.load("fit_mixed_terms")["X"])
     assert (infom.cell_roles, em) == (0, 0)
