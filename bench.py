@@ -676,6 +676,7 @@ def run_b200(args, rank, world, local_rank):
         del yh
 
     del data, Xt, y
+    pass_kernels = cells_kernel_names(eng.info) if eng.info.cell_roles > 0 else "gram_records_kernel + gram_accum_kernel"
     gam._engine = None
     eng = None
     torch.cuda.empty_cache()
@@ -712,7 +713,7 @@ def run_b200(args, rank, world, local_rank):
             break
         except Exception:
             pass
-    kernels = cells_kernel_names(eng.info) + " (the Gram pass of one PIRLS iteration of a prepared shard)"
+    kernels = pass_kernels + " (the Gram pass of one PIRLS iteration of a prepared shard)"
     second = {"name": "fp64_pipe", "algorithmic_fma_per_row": FMA_PER_ROW, "achieved_fma_per_clk_per_sm": fma_per_clk_sm,
               "measured_peak_fma_per_clk_per_sm": FP64_FMA_PER_CLK_SM, "frac": fma_per_clk_sm / FP64_FMA_PER_CLK_SM,
               "note": "spline-pair kernel: a thread owns a knot cell of a term pair and sums the moments of the "

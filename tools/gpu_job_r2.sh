@@ -26,4 +26,9 @@ $K2 > gpurun_out/plain_k2.log 2>&1 && ncu --set full --clock-control none \
 K3="python tools/kbench.py --case c3_poisson --rows 2000000 --only-gram --reps 1 --profile"
 $K3 > gpurun_out/plain_k3.log 2>&1 && ncu --set full --clock-control none \
   --profile-from-start off -k regex:"gram_cells_sorted|gram_cells_generic|stats_pass_kernel" -f -o gpurun_out/r2_ncu_c3_gram $K3 > gpurun_out/ncu_k3.log 2>&1
+# the reports embed the whole module (tens of MB each) and gpurun copies 64 MiB back: summarise here, keep the text
+python tools/ncu_summary.py gpurun_out/r2_ncu_c2_gram.ncu-rep > gpurun_out/r2_ncu_c2_gram_full.txt 2>&1
+python tools/traffic_json.py gpurun_out/r2_ncu_c2_gram.ncu-rep 8000000 > gpurun_out/r2_ncu_gram_cells_traffic.json
+python tools/ncu_summary.py gpurun_out/r2_ncu_c3_gram.ncu-rep > gpurun_out/r2_ncu_c3_gram_full.txt 2>&1
+rm -f gpurun_out/r2_ncu_c2_gram.ncu-rep gpurun_out/r2_ncu_c3_gram.ncu-rep
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

@@ -3,5 +3,5 @@
 set -x
 mkdir -p gpurun_out
 N=${PGB_N:-2}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_r1_final_n$N.json 2> gpurun_out/bench_r1_final_n$N.err; echo "bench exit $?"
-python tools/show_bench.py gpurun_out/bench_r1_final_n$N.json
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "bench exit $?"
+python tools/show_bench.py gpurun_out/r2_bench_n$N.json
