@@ -19,11 +19,17 @@ baseline/_ref) per PIRLS iteration on a bounded row sample, with all host cores.
 """
 import os
 
+import sys
+
 # The CPU arm must use every host core: torchrun exports OMP_NUM_THREADS=1 to its ranks, which made the N > 1
-# reference runs of round 1 2.2x slower than the N = 1 run.  Set before numpy / BLAS load.
+# reference runs of round 1 2.2x slower than the N = 1 run.  Set before numpy / BLAS load.  The ranks of a multi-GPU
+# run of the B200 arm share the host instead (their numpy work is m x m bookkeeping; 8 ranks x 16 spinning BLAS
+# threads on 16 cores cost the N = 8 fits of round 2 seconds of wall time).
 _CORES = os.cpu_count() or 1
+_REFERENCE_ARM = any(a == "reference" or a == "--impl=reference" for a in sys.argv[1:])
+_THREADS = _CORES if _REFERENCE_ARM else max(1, _CORES // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
 for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-    os.environ[_v] = str(_CORES)
+    os.environ[_v] = str(_THREADS)
 
 import argparse  # noqa: E402
 import contextlib  # noqa: E402
@@ -31,7 +37,6 @@ import ctypes as C  # noqa: E402
 import io  # noqa: E402
 import json  # noqa: E402
 import subprocess  # noqa: E402
-import sys  # noqa: E402
 import threading  # noqa: E402
 import time  # noqa: E402
 
