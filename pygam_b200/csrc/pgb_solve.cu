@@ -82,9 +82,22 @@ __device__ void vec_reflect(double* x, int m, const double* v, double tau, doubl
 static const int kNB = 32;
 static const int kLD = kNB + 1;  // padded leading dimension of D and P: conflict-free column access
 
+// Rows of the panel P that are staged in shared memory.  All of them up to m = 687 (every BASELINE model: m <= 601);
+// a larger system keeps as many as fit next to its vectors and reads the rest of the panel from the (L2-resident)
+// matrix itself: slower per element, same arithmetic in the same order.
+__host__ __device__ inline int solve_panel_rows(int m) {  // solve_kernel: 4 m + 34 doubles of vectors, D, >= 32 columns of Y
+  const long long room = 227ll * 1024 - 1024 - ((long long)4 * m + 34 + kNB * kLD + kNB * 32) * 8;
+  const long long rows = room / (kLD * 8);
+  return rows >= m ? m : (rows > 0 ? (int)rows : 0);
+}
+__host__ __device__ inline int chol_panel_rows(int m) {  // chol_check_kernel: D and the flag
+  const long long rows = (227ll * 1024 - 1024 - ((long long)kNB * kLD + 2) * 8) / (kLD * 8);
+  return rows >= m ? m : (int)rows;
+}
+
 // in-place lower Cholesky A = L L^T (upper part left untouched); sets *flag = 1 when A is not
 // positive definite
-__device__ void cholesky_lower(double* A, int m, double* D, double* P, int* flag) {
+__device__ void cholesky_lower(double* A, int m, double* D, double* P, int PR, int* flag) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   for (int k0 = 0; k0 < m; k0 += kNB) {
     const int kb = min(kNB, m - k0);
@@ -121,7 +134,7 @@ __device__ void cholesky_lower(double* A, int m, double* D, double* P, int* flag
     const int rows = m - k0 - kb;
     for (int ii = tid; ii < rows; ii += nt) {
       double* arow = A + (size_t)(k0 + kb + ii) * m + k0;
-      double* prow = P + (size_t)ii * kLD;
+      double* prow = ii < PR ? P + (size_t)ii * kLD : arow;  // rows beyond the staged panel: in place
       for (int c = 0; c < kb; ++c) {
         double sacc = arow[c];
         for (int d = 0; d < c; ++d) sacc = fma(-prow[d], D[c * kLD + d], sacc);
@@ -135,8 +148,8 @@ __device__ void cholesky_lower(double* A, int m, double* D, double* P, int* flag
     for (int e = tid; e < rows * rows; e += nt) {
       const int ii = e / rows, jj = e - ii * rows;
       if (jj <= ii) {
-        const double* pi = P + (size_t)ii * kLD;
-        const double* pj = P + (size_t)jj * kLD;
+        const double* pi = ii < PR ? P + (size_t)ii * kLD : A + (size_t)(k0 + kb + ii) * m + k0;
+        const double* pj = jj < PR ? P + (size_t)jj * kLD : A + (size_t)(k0 + kb + jj) * m + k0;
         double sacc = 0.0;
         for (int c = 0; c < kb; ++c) sacc = fma(pi[c], pj[c], sacc);
         A[(size_t)(k0 + kb + ii) * m + k0 + kb + jj] -= sacc;
@@ -198,7 +211,8 @@ __device__ void tri_solve_vec(const double* L, int m, double* x, bool transpose,
 // B <- L^-1 B (transpose = false) or L^-T B (true), blocked: per block row the diagonal block D,
 // the solved block Y (kNB x wc columns) and the panel of L that updates the remaining rows are in
 // shared memory; the columns of B are processed in chunks of wc (what fits next to the panel)
-__device__ void tri_solve_cols(const double* L, int m, double* B, bool transpose, double* D, double* P, double* Y, int wc) {
+__device__ void tri_solve_cols(const double* L, int m, double* B, bool transpose, double* D, double* P, int PR, double* Y,
+                               int wc) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int nblk = (m + kNB - 1) / kNB;
   for (int j0 = 0; j0 < m; j0 += wc) {
@@ -212,12 +226,13 @@ __device__ void tri_solve_cols(const double* L, int m, double* B, bool transpose
       }
       // panel: the rows of B still to be updated, as P[row][c]
       const int prow0 = transpose ? 0 : k0 + kb, prows = transpose ? k0 : m - k0 - kb;
-      for (int e = tid; e < prows * kb; e += nt) {
+      const int srows = min(prows, PR);  // staged rows of the panel; the others are read from L
+      for (int e = tid; e < srows * kb; e += nt) {
         if (!transpose) {
           const int ii = e / kb, c = e - ii * kb;
           P[(size_t)ii * kLD + c] = L[(size_t)(prow0 + ii) * m + k0 + c];
         } else {
-          const int c = e / prows, ii = e - c * prows;  // consecutive threads read consecutive columns of L
+          const int c = e / srows, ii = e - c * srows;  // consecutive threads read consecutive columns of L
           P[(size_t)ii * kLD + c] = L[(size_t)(k0 + c) * m + ii];
         }
       }
@@ -248,8 +263,13 @@ __device__ void tri_solve_cols(const double* L, int m, double* B, bool transpose
       for (int e = tid; e < prows * nc; e += nt) {
         const int ii = e / nc, j = e - ii * nc;
         const double* pr = P + (size_t)ii * kLD;
+        size_t ps = 1;
+        if (ii >= srows) {
+          pr = transpose ? L + (size_t)k0 * m + ii : L + (size_t)(prow0 + ii) * m + k0;
+          ps = transpose ? (size_t)m : 1;
+        }
         double sacc = 0.0;
-        for (int c = 0; c < kb; ++c) sacc = fma(pr[c], Y[(size_t)c * wc + j], sacc);
+        for (int c = 0; c < kb; ++c) sacc = fma(pr[c * ps], Y[(size_t)c * wc + j], sacc);
         B[(size_t)(prow0 + ii) * m + j0 + j] -= sacc;
       }
       __syncthreads();
@@ -299,8 +319,9 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   double* red = col + m;   // 32 doubles
   int* flag = reinterpret_cast<int*>(red + 32);
   double* D = red + 34;                       // diagonal block of the blocked algorithms
-  double* P = D + kNB * kLD;                  // panel, m x kLD
-  double* Y = P + (size_t)m * kLD;            // solved block of the column solves, kNB x wc
+  double* P = D + kNB * kLD;                  // panel, PR x kLD
+  const int PR = solve_panel_rows(m);
+  double* Y = P + (size_t)PR * kLD;           // solved block of the column solves, kNB x wc
   double* A = use_smem ? (Y + (size_t)kNB * wc) : (ws_all + (size_t)sys * 2 * mm);
   double* B = A + mm;
   const bool factored = (flags & PGB_SOLVE_FACTORED) != 0;
@@ -356,7 +377,7 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   if (*flag == 0) {
     for (int i = threadIdx.x; i < p; i += blockDim.x) x[i] = 0.0;
     __syncthreads();
-    if (!factored) cholesky_lower(A, m, D, P, flag);
+    if (!factored) cholesky_lower(A, m, D, P, PR, flag);
   }
   __syncthreads();
   const int info = *flag;
@@ -390,17 +411,17 @@ solve_kernel(int m, const double* __restrict__ G_all, const double* __restrict__
   double edof = __longlong_as_double(0x7ff8000000000000LL);
   if (flags & (PGB_SOLVE_WANT_EDOF | PGB_SOLVE_WANT_COV)) {
     // Z = L^-1 Gt L^-T (symmetric); edof = tr(Z)
-    tri_solve_cols(A, m, B, false, D, P, Y, wc);
+    tri_solve_cols(A, m, B, false, D, P, PR, Y, wc);
     transpose_inplace(B, m);
-    tri_solve_cols(A, m, B, false, D, P, Y, wc);
+    tri_solve_cols(A, m, B, false, D, P, PR, Y, wc);
     double tr = 0.0;
     for (int i = threadIdx.x; i < m; i += blockDim.x) tr += B[(size_t)i * m + i];
     edof = block_sum(tr, red);
     if ((flags & PGB_SOLVE_WANT_COV) && cov_all) {
       // cov = Q L^-T Z L^-1 Q^T
-      tri_solve_cols(A, m, B, true, D, P, Y, wc);
+      tri_solve_cols(A, m, B, true, D, P, PR, Y, wc);
       transpose_inplace(B, m);
-      tri_solve_cols(A, m, B, true, D, P, Y, wc);
+      tri_solve_cols(A, m, B, true, D, P, PR, Y, wc);
       for (int q = p - 1; q >= 0; --q) {
         for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = hv[(size_t)q * m + i];
         __syncthreads();
@@ -678,7 +699,7 @@ static std::mutex g_graph_mu;
 static std::vector<SolveGraph> g_graphs;
 long long pgb_launch_count(void);
 
-static size_t solve_vec_smem(int m) { return ((size_t)4 * m + 34 + kNB * kLD + (size_t)m * kLD) * 8; }
+static size_t solve_vec_smem(int m) { return ((size_t)4 * m + 34 + kNB * kLD + (size_t)solve_panel_rows(m) * kLD) * 8; }
 // columns of B solved at a time: as many as fit next to the vectors and the panel (at least 32)
 static int solve_col_chunk(int m, bool with_matrices) {
   const size_t used = solve_vec_smem(m) + (with_matrices ? (size_t)2 * m * m * 8 : 0);
@@ -770,14 +791,15 @@ chol_check_kernel(int m, const double* __restrict__ Ain, int* __restrict__ info,
   extern __shared__ __align__(16) double sm[];
   double* D = sm;
   double* P = D + kNB * kLD;
-  int* flag = reinterpret_cast<int*>(P + (size_t)m * kLD);
+  const int PR = chol_panel_rows(m);
+  int* flag = reinterpret_cast<int*>(P + (size_t)PR * kLD);
   const size_t sys = blockIdx.x;  // one CTA per matrix of a batch
-  double* A = use_smem ? (P + (size_t)m * kLD + 2) : ws + sys * (size_t)m * m;
+  double* A = use_smem ? (P + (size_t)PR * kLD + 2) : ws + sys * (size_t)m * m;
   Ain += sys * (size_t)m * m;
   if (threadIdx.x == 0) *flag = 0;
   for (int e = threadIdx.x; e < m * m; e += blockDim.x) A[e] = Ain[e];
   __syncthreads();
-  cholesky_lower(A, m, D, P, flag);
+  cholesky_lower(A, m, D, P, PR, flag);
   __syncthreads();
   if (threadIdx.x == 0) info[sys] = *flag;
 }
@@ -988,7 +1010,7 @@ extern "C" int64_t pgb_chol_ws_bytes(int32_t m) { return (int64_t)m * m * 8 + 25
 extern "C" int pgb_chol_check_batch(int32_t m, int32_t nb, const double* A, int32_t* info_out, void* ws, int64_t ws_bytes,
                                     void* stream) {
   if (m < 1 || nb < 1 || !A || !info_out) { pgb_set_error("pgb_chol_check: bad arguments"); return PGB_EINVAL; }
-  const size_t vec = ((size_t)kNB * kLD + (size_t)m * kLD + 2) * 8;
+  const size_t vec = ((size_t)kNB * kLD + (size_t)chol_panel_rows(m) * kLD + 2) * 8;
   const bool in_smem = vec + (size_t)m * m * 8 <= kSolveSmemMax;
   if (!in_smem && (!ws || ws_bytes < (int64_t)nb * m * m * 8)) {
     pgb_set_error("pgb_chol_check: workspace too small");
@@ -1005,7 +1027,7 @@ extern "C" int pgb_chol_check_batch(int32_t m, int32_t nb, const double* A, int3
 extern "C" int pgb_chol_check(int32_t m, const double* A, int32_t* info_out, void* ws, int64_t ws_bytes,
                               void* stream) {
   if (m < 1 || !A || !info_out) { pgb_set_error("pgb_chol_check: bad arguments"); return PGB_EINVAL; }
-  const size_t vec = ((size_t)kNB * kLD + (size_t)m * kLD + 2) * 8;
+  const size_t vec = ((size_t)kNB * kLD + (size_t)chol_panel_rows(m) * kLD + 2) * 8;
   const bool in_smem = vec + (size_t)m * m * 8 <= kSolveSmemMax;
   if (!in_smem && (!ws || ws_bytes < pgb_chol_ws_bytes(m))) {
     pgb_set_error("pgb_chol_check: workspace too small");

@@ -186,6 +186,71 @@ def test_stats_pass_more_terms_than_the_plan_holds():
         assert abs(sc[k] - scr[k]) <= 1e-11 * max(1.0, abs(scr[k])), (k, sc[k], scr[k])
 
 
+@pytest.mark.parametrize("n_terms,n_splines", [(3, 150), (7, 150), (12, 40)])
+def test_stats_pass_large_interval_tables_and_many_tiles(n_terms, n_splines):
+    """the interval tables of the pass in eight bank-disjoint copies (3 x 150 splines: 113 KB, 12 x 40: 114 KB) and in one
+    copy when eight do not fit beside the staged tiles (7 x 150 splines); 150 001 rows = several tiles of the TMA ring per
+    CTA, a ragged tail, rows outside the edge knots; statistics and predict instances, with and without weights"""
+    rng = np.random.default_rng(17)
+    n = 150_001
+    X = rng.uniform(0.0, 1.0, size=(n, n_terms))
+    eta = np.sin(5 * X[:, 0]) + np.cos(3 * X[:, 1]) * X[:, 2]
+    y = rng.poisson(np.exp(0.4 * eta)).astype(float)
+    terms = pg.s(0, n_splines=n_splines)
+    for j in range(1, n_terms):
+        terms = terms + pg.s(j, n_splines=n_splines - j)
+    gam = pg.PoissonGAM(terms, max_iter=1)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        gam.fit(X[:4000], y[:4000])
+    eng = gam._engine
+    ora = OracleEngine(gam.terms, gam.distribution.name, gam.link.name, gam.distribution.levels, gam._expectile, n_terms, "cpu")
+    coef = 0.3 * rng.standard_normal(eng.m)
+    Xn = X * 1.1 - 0.05  # ~9 % of every feature outside the edge knots
+    w = rng.uniform(0.5, 2.0, n).astype(np.float32)
+    for weights in (None, w):
+        c = DeviceData.from_host(Xn, y, weights, device="cpu")
+        g = DeviceData.from_host(Xn, y, weights)
+        sc, lp, mu = eng.stats_pass(g, coef, want_mu=True, want_lp=True)
+        scr, lpr, mur = ora.stats_pass(c, coef, want_mu=True, want_lp=True)
+        assert helpers.rel(lp.cpu().numpy(), lpr.numpy()) < 1e-12
+        assert helpers.rel(mu.cpu().numpy(), mur.numpy()) < 1e-12
+        for k in (_lib.SS_N, _lib.SS_DEV, _lib.SS_WDEV, _lib.SS_PEARSON, _lib.SS_SUMY, _lib.SS_SUMW):
+            assert abs(sc[k] - scr[k]) <= 1e-11 * max(1.0, abs(scr[k])), (k, sc[k], scr[k])
+        _, _, mu_only = eng.stats_pass(DeviceData(g.Xt, None, None), coef, want_mu=True)  # the predict instance (no y)
+        assert helpers.rel(mu_only.cpu().numpy(), mur.numpy()) < 1e-12
+        # the IRLS step of a prepared Gram pass runs through the same kernel: against the oracle's Gram matrix
+        first = eng.gram_pass(g, coef).cpu().numpy().copy()
+        planned = eng.gram_pass(g, coef).cpu().numpy().copy()
+        ref = ora.gram_pass(c, coef).numpy()
+        m = eng.m
+        scale = np.abs(ref[:m * m]).max()
+        assert np.abs(first - ref)[:m * m + m].max() <= 1e-12 * scale
+        assert np.abs(planned - ref)[:m * m + m].max() <= 1e-12 * scale
+        for k in (_lib.GS_NUSED, _lib.GS_NROWS):
+            assert planned[m * m + m + k] == ref[m * m + m + k]
+        assert abs(planned[m * m + m + _lib.GS_DEV] - ref[m * m + m + _lib.GS_DEV]) <= 1e-11 * abs(ref[m * m + m + _lib.GS_DEV])
+    # the solve of this system against the numpy mirror: m = 1030 (7 x 150 splines) is past the 687 rows of the panel
+    # that pgb_solve stages in shared memory (the rest is read from the matrix) and past the 860 of pgb_chol_check
+    m = eng.m
+    out = ora.gram_pass(DeviceData.from_host(Xn, y, None, device="cpu"), coef).numpy().copy()
+    Pn, Pr = gam.terms.build_penalties(split=True)
+    EtE = np.eye(m) * np.sqrt(orc.EPS) + Pr
+    eng.out.copy_(torch.from_numpy(out))
+    eng.set_penalty(EtE, Pn)
+    sol = eng.solve(coef_prev=coef, want_edof=True, want_cov=True)
+    V, tau = householder(gam.terms.null_vectors())
+    ref = solve_mirror(out[:m * m].reshape(m, m), out[m * m:m * m + m], EtE, V, tau, want_cov=True, EtE_null=Pn)
+    assert sol["info"] == 0
+    Pz = helpers.identifiable_projector(gam)
+    assert np.linalg.norm(Pz @ (sol["coef"] - ref["coef"])) <= 1e-9 * np.linalg.norm(ref["coef"])
+    assert abs(sol["edof"] - ref["edof"]) <= 1e-9 * abs(ref["edof"])
+    assert helpers.rel(Pz @ sol["cov"] @ Pz, Pz @ ref["cov"] @ Pz) < 1e-7
+    assert eng.chol_ok(EtE + Pn)
+    assert not eng.chol_ok(EtE + Pn - 5.0 * np.eye(m))
+
+
 @pytest.mark.parametrize("name", ["c1_wage", "c2_logistic", "c3_poisson", "mixed_terms", "no_intercept",
                                   "c5_expectile"])
 def test_solve_matches_numpy_mirror(name):
