@@ -135,8 +135,26 @@ int pgb_model_build_host(const pgb_term* terms, int32_t n_terms, int32_t n_featu
   M->m = coef;
   M->k = slot;
   if (M->m > 65000) { pgb_set_error("too many coefficients (%d)", M->m); delete M; return PGB_EUNSUPPORTED; }
+  // The general Gram path keeps a whole term-pair block of G in one SM's shared memory: a 200-spline s() or a 25 x 25
+  // te() does not fit.  Such a model is fine as long as the cell-owned pass takes it (plain cubic s(), te() of two
+  // cubics, f(), l()): the general plan is then simply absent.
   int rc = pgb_plan_gram(M);
+  char general_err[512] = "";
+  if (rc == PGB_EUNSUPPORTED && !M->dbg.force_general) {
+    snprintf(general_err, sizeof(general_err), "%s", pgb_last_error());
+    M->general_ok = false;
+    M->roles.clear();
+    M->elem_map.clear();
+    M->gram_ctas = 0;
+    M->partial_doubles = 0;
+    rc = PGB_OK;
+  }
   if (rc == PGB_OK) rc = pgb_plan_cells(M);
+  if (rc == PGB_OK && !M->general_ok && !M->cells.enabled) {
+    pgb_set_error("%s, and the model has terms the cell-owned Gram pass does not take (by=, cyclic or non-cubic bases, "
+                  "te() of more than two marginals)", general_err);
+    rc = PGB_EUNSUPPORTED;
+  }
   if (rc != PGB_OK) { delete M; return rc; }
   *out = M;
   return PGB_OK;
@@ -187,7 +205,7 @@ extern "C" int pgb_model_plan_host(const pgb_term* terms, int32_t n_terms, int32
   int rc = pgb_model_build_host(terms, n_terms, n_features, PGB_DIST_NORMAL, PGB_LINK_IDENTITY, 1.0, -1.0, 0, nullptr, &M);
   if (rc != PGB_OK) return rc;
   if (info) pgb_model_get_info(M, info);
-  if (coverage_errors) *coverage_errors = pgb_plan_coverage_errors(M) + pgb_cells_coverage_errors(M);
+  if (coverage_errors) *coverage_errors = (M->general_ok ? pgb_plan_coverage_errors(M) : 0) + pgb_cells_coverage_errors(M);
   delete M;
   return PGB_OK;
 }

@@ -58,6 +58,7 @@ static size_t role_fixed_smem(const pgb_model* M) {
 
 int pgb_plan_gram(pgb_model* M) {
   const int m = M->m, nt = M->n_terms;
+  M->pass_ctas = kSMs * 8;  // needed by the O(k) passes whether or not this plan succeeds
   std::vector<DTerm>& T = M->dterms;
   // ---- groups and quads; gcoef[g][idx] = coefficient (m = rhs) behind index idx of group g
   M->groups.clear();

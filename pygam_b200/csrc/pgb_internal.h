@@ -207,6 +207,7 @@ struct pgb_model {
   int64_t partial_doubles = 0;  // doubles of all partials of all roles
   int64_t map_size = 0;
   int32_t pass_ctas = 0;        // CTAs of the O(k) passes
+  bool general_ok = true;       // the general Gram plan exists (it needs every term-pair block of G in one SM's shared memory)
   // set only through the test-only entry point pgb_debug_model_create (tests compare the two Gram paths and
   // exercise tile / band boundaries at small n); zero in every model the product creates
   struct Debug {
