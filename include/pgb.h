@@ -51,12 +51,13 @@ enum { PGB_OK = 0, PGB_EINVAL = -1, PGB_ECUDA = -2, PGB_ENOMEM = -3, PGB_ENOTPD 
 /* One term of the model, flattened from Term.info (pygam/terms.py:220-233).  For a tensor term
  * the per-marginal arrays hold the marginal splines in order (first marginal varies slowest in
  * the coefficient index, pygam/utils.py:943-946). */
+#define PGB_MARG_LINEAR (-1)
 typedef struct pgb_term {
   int32_t kind;                     /* PGB_TERM_*                                           */
   int32_t n_marg;                   /* 1 for l/s/f, 2..PGB_MAX_MARG for te, 0 for intercept  */
   int32_t feature[PGB_MAX_MARG];    /* column of X                                           */
   int32_t n_splines[PGB_MAX_MARG];  /* basis functions of the marginal (f: number of levels) */
-  int32_t order[PGB_MAX_MARG];      /* spline_order (f: 0)                                   */
+  int32_t order[PGB_MAX_MARG];      /* spline_order (f: 0); PGB_MARG_LINEAR for an l() marginal of te(): one column, the feature value */
   int32_t periodic[PGB_MAX_MARG];   /* basis == "cp"                                         */
   double edge_lo[PGB_MAX_MARG];     /* edge_knots_[0]                                        */
   double edge_hi[PGB_MAX_MARG];     /* edge_knots_[1]                                        */

@@ -75,6 +75,16 @@ def _norm_spline(d, default_n_splines=20):
     return t
 
 
+def _norm_linear(d):
+    """terms.py:662-678"""
+    pens = _as_list(d.get("penalties", "auto"))
+    lam = _as_list(d.get("lam", 0.6))
+    if len(lam) == 1:
+        lam = lam * len(pens)
+    return dict(kind="l", feature=int(d["feature"]), penalties=pens, lam=[float(v) for v in lam], constraints=[None],
+                dtype="numerical", edge_knots=None)
+
+
 def normalize_terms(term_specs, fit_intercept=True):
     """Canonical term list.  Mirrors the constructors in terms.py (s: 810-845, l: 662-678,
     f: 1010-1033, te: 1284-1356) and the intercept appended by
@@ -85,13 +95,7 @@ def normalize_terms(term_specs, fit_intercept=True):
         if k == "s":
             out.append(_norm_spline(d))
         elif k == "l":
-            pens = _as_list(d.get("penalties", "auto"))
-            lam = _as_list(d.get("lam", 0.6))
-            if len(lam) == 1:
-                lam = lam * len(pens)
-            out.append(dict(kind="l", feature=int(d["feature"]), penalties=pens,
-                            lam=[float(v) for v in lam], constraints=[None], dtype="numerical",
-                            edge_knots=None))
+            out.append(_norm_linear(d))
         elif k == "f":
             pens = _as_list(d.get("penalties", "auto"))
             lam = _as_list(d.get("lam", 0.6))
@@ -102,7 +106,10 @@ def normalize_terms(term_specs, fit_intercept=True):
                             coding=d.get("coding", "one-hot"), spline_order=0, basis="ps",
                             by=None, n_splines=None, edge_knots=None))
         elif k == "te":
-            margs = [_norm_spline(m, default_n_splines=10) for m in d["marginals"]]
+            # marginals are terms of their own: s() (default n_splines 10) or l() (terms.py:1330-1356; tensors of tensors
+            # are refused there, factor marginals are not restated here)
+            margs = [_norm_linear(m) if m.get("kind") == "l" else _norm_spline(m, default_n_splines=10)
+                     for m in d["marginals"]]
             if len(margs) < 2:
                 raise ValueError("TensorTerm requires at least 2 marginal terms")
             out.append(dict(kind="te", marginals=margs, by=d.get("by")))
@@ -127,7 +134,7 @@ def n_coefs(t):
     if k == "f":
         return t["n_splines"] - (1 if t["coding"] == "dummy" else 0)
     if k == "te":
-        return int(np.prod([m["n_splines"] for m in t["marginals"]]))
+        return int(np.prod([n_coefs(m) for m in t["marginals"]]))
     raise ValueError(k)
 
 
@@ -180,7 +187,7 @@ def compile_terms(terms, X):
         elif k == "te":
             for m in t["marginals"]:
                 if m["edge_knots"] is None:
-                    m["edge_knots"] = gen_edge_knots(X[:, m["feature"]], m["dtype"])
+                    m["edge_knots"] = gen_edge_knots(X[:, m["feature"]], m["dtype"])  # l(): terms.py:668-691
     return terms
 
 
@@ -272,9 +279,9 @@ def term_columns(t, X):
         B = _spline_columns(t, X)
         return B[:, 1:] if t["coding"] == "dummy" else B
     if k == "te":  # terms.py:1454-1477
-        B = _spline_columns(t["marginals"][0], X)
+        B = term_columns(t["marginals"][0], X)  # every marginal builds its own columns (terms.py:1469-1472)
         for m in t["marginals"][1:]:
-            B = tensor_rows(B, _spline_columns(m, X))
+            B = tensor_rows(B, term_columns(m, X))
         if t.get("by") is not None:
             B = B * X[:, t["by"]][:, None]
         return B
@@ -394,7 +401,7 @@ def term_penalty(t):
     for i in range(len(t["marginals"])):
         acc = None
         for j, m in enumerate(t["marginals"]):
-            Pj = _simple_term_penalty(m) if j == i else np.eye(m["n_splines"])
+            Pj = _simple_term_penalty(m) if j == i else np.eye(n_coefs(m))
             acc = Pj if acc is None else np.kron(acc, Pj)
         total = total + acc
     return total
@@ -426,7 +433,7 @@ def term_constraint(t, coef, clam, cl2):
     if t["kind"] != "te":
         return _simple_term_constraint(t, coef, clam, cl2)
     # terms.py:1519-1641: every 1-d slice of the coefficient tensor along marginal i
-    dims = [m["n_splines"] for m in t["marginals"]]
+    dims = [n_coefs(m) for m in t["marginals"]]
     size = int(np.prod(dims))
     C = np.zeros((size, size))
     idx = np.arange(size).reshape(dims)

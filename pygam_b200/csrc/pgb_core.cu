@@ -47,7 +47,7 @@ void pgb_count_launch(int n) { PGB_LAUNCHED(n); }
 static int term_nnz(const pgb_term& t) {
   if (t.kind == PGB_TERM_INTERCEPT || t.kind == PGB_TERM_LINEAR) return 1;
   int nnz = 1;
-  for (int q = 0; q < t.n_marg; ++q) nnz *= t.order[q] + 1;
+  for (int q = 0; q < t.n_marg; ++q) nnz *= (t.order[q] < 0) ? 1 : t.order[q] + 1;  // order -1: a linear marginal of te()
   return nnz;
 }
 
@@ -107,6 +107,14 @@ int pgb_model_build_host(const pgb_term* terms, int32_t n_terms, int32_t n_featu
       g.periodic = t.periodic[q];
       ok = ok && g.feature >= 0 && g.feature < n_features;
       if (t.kind == PGB_TERM_LINEAR) continue;
+      if (t.kind == PGB_TERM_TENSOR && g.order == PGB_MARG_LINEAR) {
+        // a LinearTerm marginal of te(): one column, the feature value itself (terms.py:693-708 inside 1454-1477)
+        ok = ok && g.nspl == 1 && !g.periodic;
+        g.nint = 1;
+        g.lo = 0.0;
+        g.span = g.inv_span = g.knot_step = 1.0;
+        continue;
+      }
       ok = ok && g.order >= 0 && g.order <= PGB_MAX_ORDER && g.nspl > g.order;
       g.nint = g.nspl + (g.periodic ? g.order : 0) - g.order;  // utils.py:678, 686
       g.lo = std::min(t.edge_lo[q], t.edge_hi[q]);             // np.sort(edge_knots), utils.py:681

@@ -222,9 +222,16 @@ __device__ __forceinline__ void eval_term(const DTerm& T, const Load& load, Emit
   for (int q = 0; q < PGB_MAX_MARG; ++q) {
     if (q < T.n_marg) {
       const DMarg& mg = T.marg[q];
-      i0[q] = eval_marg(mg, load(mg.feature), v[q]);
-      cnt[q] = mg.order + 1;
-      K[q] = mg.nspl;
+      if (mg.order < 0) {  // l() marginal: one column holding the feature value (terms.py:693-708)
+        v[q][0] = load(mg.feature);
+        i0[q] = 0;
+        cnt[q] = 1;
+        K[q] = 1;
+      } else {
+        i0[q] = eval_marg(mg, load(mg.feature), v[q]);
+        cnt[q] = mg.order + 1;
+        K[q] = mg.nspl;
+      }
     } else {
       i0[q] = 0; cnt[q] = 1; K[q] = 1; v[q][0] = 1.0;
     }

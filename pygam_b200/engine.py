@@ -215,6 +215,13 @@ def build_descriptor(terms, n_features):
 
 
 def _fill_marginal(d, q, t):
+    if isinstance(t, LinearTerm):  # l() marginal of te(): one column, the feature value (PGB_MARG_LINEAR)
+        d.feature[q] = t.feature
+        d.n_splines[q] = 1
+        d.order[q] = -1
+        d.periodic[q] = 0
+        d.edge_lo[q], d.edge_hi[q] = 0.0, 1.0
+        return
     if t.edge_knots_ is None:
         raise ValueError("term has not been compiled")
     d.feature[q] = t.feature

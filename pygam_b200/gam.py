@@ -151,7 +151,7 @@ class GAM:
         self._engine_key = None
         self._gram_cache = None
         self._dev_memo = None
-        self._validate_params()
+        self._validate_params(check_terms=False)  # the reference validates at fit time (pygam.py:881); see there
 
     # ---- parameters ----
     _param_names = ("max_iter", "tol", "callbacks", "fit_intercept", "verbose", "terms")
@@ -164,6 +164,7 @@ class GAM:
         for extra in ("scale", "expectile"):
             if hasattr(self, extra):
                 out[extra] = getattr(self, extra)
+        out.update(self._pending_plural)  # lam=, n_splines=, ... given to the constructor, until a fit moves them to the terms
         if deep:
             for k in ("coef_", "statistics_", "logs_"):
                 if hasattr(self, k):
@@ -200,15 +201,27 @@ class GAM:
         else:
             self.__dict__.setdefault("_pending_plural", {})["lam"] = value
 
+    def __getattr__(self, name):
+        """gam.n_splines, gam.spline_order, ...: the values of every term but the intercept (MetaTermMixin.__getattr__,
+        terms.py:482-495).  Only reached when normal lookup fails."""
+        if name in PLURAL and not name.startswith("_"):
+            terms = self.__dict__.get("terms")
+            if isinstance(terms, TermList):
+                return [getattr(t, name, None) for t in terms if not t.isintercept]
+        raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
+
     @property
     def _is_fitted(self):
         return hasattr(self, "coef_")
 
-    def _validate_params(self):
-        """pygam.py:225-284"""
+    def _validate_params(self, check_terms=True):
+        """pygam.py:225-284.  The constructor runs it without the check of `terms` (distribution and link become
+        objects right away); a wrong `terms` raises at fit time, where the reference validates
+        (pygam/tests/test_GAM_params.py:49-56)."""
         if not (isinstance(self.fit_intercept, bool)):
             raise ValueError(f"fit_intercept must be type bool, but found {self.fit_intercept.__class__}")
-        if not (isinstance(self.terms, (TermList, Term, type(None))) or self.terms == "auto"):
+        if check_terms and not (isinstance(self.terms, (TermList, Term, type(None))) or
+                                (isinstance(self.terms, str) and self.terms == "auto")):
             raise ValueError(f"terms must be a TermList, but found terms = {self.terms}")
         if not (isinstance(self.max_iter, (int, np.integer)) and self.max_iter >= 1):
             raise ValueError(f"max_iter must be int >= 1, but found max_iter = {self.max_iter}")
@@ -276,6 +289,8 @@ class GAM:
                     Xh = Xh.astype("float")
                 except ValueError as e:
                     raise ValueError("X data must be type int or float, but found type: " + str(Xh.dtype)) from e
+            if Xh.ndim == 0:  # a single value for a one-feature model (make_2d, utils.py:263-290)
+                Xh = Xh.reshape(1, 1)
             if Xh.ndim == 1:
                 Xh = Xh[:, None]
             if Xh.ndim != 2:
@@ -584,8 +599,26 @@ class GAM:
             return None
         G, EtE = ctx
         m = len(G)
-        if getattr(self, "_solve_rank", m) < m:
-            return None  # rows < coefficients: the reference's U1 is cropped and summary() prints no per-term edof
+        k = getattr(self, "_solve_rank", m)
+        if k < m:
+            # rows < coefficients: U1 is the k x k corner of U (pygam.py:797), so diag(U1 U1^T) has k entries, one per
+            # ROW of the k x m factor R of the QR -- fewer values than coefficients, which is why summary() prints no
+            # per-term edof then (pygam/tests/test_GAM_methods.py:93-107).  U1 = R V_k D_k^-1 over the k leading
+            # eigenpairs of A = G + E^T E, hence diag(R A_k^+ R^T); its sum is the edof of the cropped solve.
+            R = np.zeros((k, m))
+            d, row = np.diag(G), 0
+            for j in range(m):
+                if row == k:
+                    break
+                piv = G[j, j] - R[:row, j] @ R[:row, j]
+                if not piv > 1e-12 * d[j]:
+                    continue
+                R[row, j:] = (G[j, j:] - R[:row, j] @ R[:row, j:]) / np.sqrt(piv)
+                row += 1
+            lam_, V = np.linalg.eigh(G + EtE)
+            Vk, lk = V[:, ::-1][:, :k], lam_[::-1][:k]
+            RV = R @ Vk
+            return np.einsum("ij,ij->i", RV / lk, RV)
         R = np.zeros((m, m))
         d = np.diag(G)
         for j in range(m):
@@ -981,6 +1014,10 @@ class GAM:
         lp, var = eng.interval_pass(DeviceData(data.Xt), self.coef_, self.statistics_["cov"] if compute_quantiles else None,
                                     self._term_index(term))
         pdep = lp.cpu().numpy()
+        if len(self.terms) == 1:
+            # the only term of a model without intercept: its partial dependence IS the linear predictor, and the
+            # reference's equal each other bit for bit (pygam/tests/test_partial_dependence.py:7-16)
+            pdep = self._linear_predictor(X)
         out = [pdep]
         if compute_quantiles:
             out.append(self._get_quantiles(X, width=width, quantiles=quantiles, term=term, xform=False,
@@ -1292,10 +1329,10 @@ class LinearGAM(GAM):
         super().__init__(terms=terms, distribution="normal", link="identity", max_iter=max_iter, tol=tol,
                          callbacks=callbacks, fit_intercept=fit_intercept, verbose=verbose, **kwargs)
 
-    def _validate_params(self):
+    def _validate_params(self, check_terms=True):
         if isinstance(self.distribution, str):
             self.distribution = Distribution("normal", scale=self.scale)
-        super()._validate_params()
+        super()._validate_params(check_terms=check_terms)
 
     def prediction_intervals(self, X, width=0.95, quantiles=None):
         """pygam.py:2477-2506"""
@@ -1418,13 +1455,13 @@ class ExpectileGAM(GAM):
                          callbacks=callbacks, fit_intercept=fit_intercept, verbose=verbose, **kwargs)
         self._expectile = float(expectile)
 
-    def _validate_params(self):
+    def _validate_params(self, check_terms=True):
         if not (0 < self.expectile < 1):
             raise ValueError(f"expectile must be in (0,1), but found {self.expectile}")
         self._expectile = float(self.expectile)
         if isinstance(self.distribution, str):
             self.distribution = Distribution("normal", scale=self.scale)
-        super()._validate_params()
+        super()._validate_params(check_terms=check_terms)
 
     def _get_quantile_ratio(self, X, y):
         """fraction of the targets below the fitted curve (pygam.py:3462-3480)"""

@@ -95,8 +95,31 @@ class Term:
     def __add__(self, other):
         return TermList(self, other)
 
+    def __radd__(self, other):
+        return TermList(other, self)
+
     def __mul__(self, other):
-        return TermList(self) * other
+        """terms.py:128-129"""
+        raise NotImplementedError("terms cannot be multiplied: build an interaction with te()")
+
+    def __eq__(self, other):
+        """terms.py:117-120: terms are equal when their describing dicts are"""
+        return isinstance(other, Term) and _info_equal(self.info, other.info)
+
+    __hash__ = object.__hash__  # terms stay usable as dictionary keys (identity)
+
+    @classmethod
+    def build_from_info(cls, info):
+        """terms.py:236-262, 1398-1420, 1790-1808: a term (or a term list) rebuilt from its ``info`` dict"""
+        info = copy.deepcopy(info)
+        cls_ = _term_classes()[info.pop("term_type")] if "term_type" in info else cls
+        if cls_ is TermList:
+            return TermList(*[Term.build_from_info(t) for t in info["terms"]])
+        if cls_ is TensorTerm:
+            return TensorTerm(*[Term.build_from_info(t) for t in info["terms"]], by=info.get("by"))
+        import inspect
+        accepted = set(inspect.signature(cls_.__init__).parameters) - {"self"}
+        return cls_(**{k: v for k, v in info.items() if k in accepted})
 
     def __len__(self):
         return 1
@@ -364,8 +387,10 @@ class TensorTerm(Term):
                 raise ValueError("TensorTerm does not accept other TensorTerms. "
                                  "Please build a flat TensorTerm instead of a nested one.")
             if isinstance(arg, Term):
-                if not isinstance(arg, SplineTerm) or isinstance(arg, FactorTerm):
-                    raise NotImplementedError("tensor marginals must be spline terms")
+                # s() and l() marginals (pygam/tests/test_terms.py:183-199: te(s(0), l(1)) is s(0, by=1) with one more
+                # lam); f() marginals have no CUDA evaluation inside a tensor product
+                if isinstance(arg, FactorTerm) or not isinstance(arg, (SplineTerm, LinearTerm)):
+                    raise NotImplementedError("tensor marginals must be spline or linear terms")
                 margs.append(arg)
                 continue
             kw = {"n_splines": self._N_SPLINES}
@@ -520,6 +545,21 @@ class TermList:
 
     def __radd__(self, other):
         return TermList(other, self)
+
+    def __mul__(self, other):
+        """terms.py:1756-1757"""
+        raise NotImplementedError("terms cannot be multiplied: build an interaction with te()")
+
+    def __eq__(self, other):
+        """terms.py:1736-1739"""
+        return isinstance(other, TermList) and _info_equal(self.info, other.info)
+
+    __hash__ = object.__hash__
+
+    @classmethod
+    def build_from_info(cls, info):
+        """terms.py:1790-1808"""
+        return cls(*[Term.build_from_info(t) for t in copy.deepcopy(info)["terms"]])
 
     def __repr__(self):
         return " + ".join(repr(t) for t in self._terms)
@@ -705,10 +745,31 @@ def _rows_sum_to_one(t):
     >= 1 extrapolate linearly outside the edge knots (utils.py:744-763; the slopes of a partition of unity sum to
     zero), an order-0 basis is zero there: it qualifies only when the knots span the data (not known: only when
     the knots came from the data, i.e. the user gave none)."""
+    if isinstance(t, LinearTerm):
+        return False
     if t.spline_order > 0:
         return True
     covers = getattr(t, "_covers_data_", None)
     return t.edge_knots is None if covers is None else covers
+
+
+def _term_classes():
+    return {"term": Term, "intercept_term": Intercept, "linear_term": LinearTerm, "spline_term": SplineTerm,
+            "factor_term": FactorTerm, "tensor_term": TensorTerm, "term_list": TermList}
+
+
+def _info_equal(a, b):
+    """dict equality that copes with the numpy arrays (user edge knots) an info dict may hold"""
+    if isinstance(a, dict) and isinstance(b, dict):
+        return a.keys() == b.keys() and all(_info_equal(a[k], b[k]) for k in a)
+    if isinstance(a, (list, tuple, np.ndarray)) or isinstance(b, (list, tuple, np.ndarray)):
+        if not (isinstance(a, (list, tuple, np.ndarray)) and isinstance(b, (list, tuple, np.ndarray))) or len(a) != len(b):
+            return False
+        return all(_info_equal(x, y) for x, y in zip(a, b))
+    try:
+        return bool(a == b)
+    except Exception:  # noqa: BLE001
+        return False
 
 
 def _flatten(v):

@@ -18,6 +18,8 @@ from pygam_b200.terms import FactorTerm, Intercept, LinearTerm, SplineTerm, Tens
 
 
 def _oracle_marg(t):
+    if isinstance(t, LinearTerm):
+        return dict(kind="l", feature=t.feature)
     return dict(kind="s", feature=t.feature, n_splines=t.n_splines, spline_order=t.spline_order,
                 basis=t.basis, by=t.by, dtype=t.dtype, edge_knots=np.asarray(t.edge_knots_, float),
                 penalties=["none"], lam=[0.0], constraints=[None])

@@ -107,6 +107,19 @@ def test_oracle_masked_rows_tiny_weights_and_inv_squared_and_truncated_svd():
     assert abs(res["statistics"]["edof"] - float(g["stat_edof"])) < 1e-6
 
 
+TE_LINEAR = dict(model="PoissonGAM", terms=[cases.te(cases.s(0, n_splines=8), cases.l(1), lam=[0.3, 2.0]), cases.s(2, n_splines=12),
+                                              cases.te(cases.l(3), cases.s(2, n_splines=6))])
+
+
+def test_oracle_tensor_terms_with_linear_marginals():
+    """te(s, l) and te(l, s) (terms.py:1330-1356: a marginal is any non-tensor term; pygam/tests/test_terms.py:183-199)"""
+    g = r2("te_linear_marginal")
+    terms = orc.compile_terms(orc.normalize_terms(TE_LINEAR["terms"]), g["X"])
+    np.testing.assert_array_equal(orc.penalty_matrix(terms), g["penalty"])
+    assert rel(orc.model_matrix(terms, g["X"][:32]).toarray(), g["modelmat_head"]) < 1e-14
+    _oracle_check(orc.fit(TE_LINEAR, g["X"], g["y"]), g)
+
+
 # ---------------------------------------------------------------------------------------------
 # the product
 # ---------------------------------------------------------------------------------------------
@@ -207,6 +220,26 @@ def test_p_values_standard_errors_aicc(kind, name):
         if np.any((sv > cut * 1e-4) & (sv < cut * 1e6)):
             continue
         np.testing.assert_allclose(pv[i], pv_ref[i], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_tensor_terms_with_linear_marginals(kind):
+    g = r2("te_linear_marginal")
+    with backend(kind):
+        gam = pg.PoissonGAM(pg.te(pg.s(0, n_splines=8), pg.l(1), lam=[0.3, 2.0]) + pg.s(2, n_splines=12)
+                            + pg.te(pg.l(3), pg.s(2, n_splines=6)))
+        quiet_fit(gam, g["X"], g["y"])
+        np.testing.assert_array_equal(gam._P(), g["penalty"])
+        check_fit(gam, g, g["X"])
+        assert rel(gam.predict_mu(g["X"][:64]), g["mu_head"]) < 1e-8
+        pd0 = gam.partial_dependence(term=0, X=g["X"][:32])  # the interval pass on a tensor term with a linear marginal
+        idx = gam.terms.get_coef_indices(0)
+        assert rel(pd0, g["modelmat_head"][:, idx] @ g["coef"][idx]) < 1e-7
+    # nested tensors are refused, factor marginals have no device evaluation
+    with pytest.raises(ValueError):
+        pg.te(pg.l(0), pg.te(0, 1))
+    with pytest.raises(NotImplementedError):
+        pg.te(pg.s(0), pg.f(1))
 
 
 @pytest.mark.parametrize("kind", BACKENDS)

@@ -1,0 +1,75 @@
+"""Run the REFERENCE's own test files against the product (authoring container only: needs /root/reference).
+
+A throw-away package named `pygam` is created in a temporary directory: it re-exports pygam_b200, swaps in the
+oracle-backed test engine (no GPU needed: what is exercised is the public API, the term grammar and the host logic),
+and borrows the reference's dataset loaders.  The reference's test files are read where they lie; nothing is copied into
+the repository.
+
+    python tools/run_reference_tests.py            # the six files that test the public API
+    python tools/run_reference_tests.py -k summary # extra arguments go to pytest
+
+Expected: 107 passed, 1 skipped, 3 failed -- test_pvalue_invariant_to_scale (p-value of a rank-deficient block, DESIGN.md
+section 5) and two tests of private helpers (`_build_marginal_penalties`, scipy-sparse penalty matrices).
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/pygam"
+FILES = ["test_terms.py", "test_GAM_methods.py", "test_GAMs.py", "test_gridsearch.py", "test_partial_dependence.py",
+         "test_GAM_params.py"]
+
+SHIM = '''
+import sys, types
+for p in ({root!r}, {root!r} + "/tests", {root!r} + "/tests/golden", {root!r} + "/baseline/stub"):
+    sys.path.insert(0, p)
+import numpy as np
+import pygam_b200 as _pg
+from pygam_b200 import *  # noqa
+from pygam_b200 import engine as _pe, gam as _gam, terms as _terms, penalties as _pen
+from oracle_backend import OracleBackend
+_pe.swap_backend_for_tests(OracleBackend())
+for _n in dir(_pg):
+    if not _n.startswith("__"):
+        globals()[_n] = getattr(_pg, _n)
+def _alias(name, mod):
+    sys.modules["pygam." + name] = mod
+    globals()[name] = mod
+_alias("pygam", _gam); _alias("terms", _terms); _alias("penalties", _pen)
+_utils = types.ModuleType("pygam.utils")
+def make_2d(array, verbose=True):
+    array = np.asarray(array)
+    return np.atleast_1d(array).reshape(-1, 1) if array.ndim < 2 else array
+def flatten(it):
+    out = []
+    for el in (it if hasattr(it, "__iter__") and not isinstance(it, str) else [it]):
+        out.extend(flatten(el) if hasattr(el, "__iter__") and not isinstance(el, str) else [el])
+    return out
+_utils.make_2d, _utils.flatten = make_2d, flatten
+_alias("utils", _utils)
+'''
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit("the reference is not available here")
+    tmp = tempfile.mkdtemp(prefix="refcheck_")
+    try:
+        os.makedirs(os.path.join(tmp, "pygam"))
+        os.makedirs(os.path.join(tmp, "tests"))
+        with open(os.path.join(tmp, "pygam", "__init__.py"), "w") as f:
+            f.write(SHIM.format(root=ROOT))
+        os.symlink(os.path.join(REF, "datasets"), os.path.join(tmp, "pygam", "datasets"))
+        for name in FILES + ["conftest.py", "__init__.py"]:
+            os.symlink(os.path.join(REF, "tests", name), os.path.join(tmp, "tests", name))
+        cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider"] + [os.path.join("tests", f) for f in FILES]
+        return subprocess.call(cmd + sys.argv[1:], cwd=tmp)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
