@@ -445,8 +445,9 @@ def test_gram_is_additive_over_row_shards_and_oracle_checked_on_a_prefix():
 
 
 def test_large_fit_matches_oracle_on_subsample_statistics():
-    """1e6-row LogisticGAM fit on the GPU: converges in the same number of iterations as the
-    oracle run on the same rows, identical UBRE / edof / deviance to 1e-10"""
+    """2e5-row LogisticGAM fit on the GPU (what the O(n m^2) oracle finishes in seconds; the reference itself at 1e5 /
+    5e4 rows: tests/test_parity_gaps.py big_c2 / big_c3): the same number of iterations as the oracle on the same rows,
+    UBRE / edof / deviance to 1e-10"""
     n = 200_000
     data = _device_c2(n, 123)
     gam = helpers.build_model(cases.FIT_CASES["c2_logistic"]).fit(data)
