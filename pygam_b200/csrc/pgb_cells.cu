@@ -62,17 +62,36 @@ static void role_cta_range(int64_t nr, int grid, int r, int& lo, int& hi) {
   }
 }
 
-// class of a term for the cell-owned pass: 0 intercept, 1 plain cubic s(), 2 generic (te() of two plain cubic
-// marginals, f(), l()), -1: not representable (the model takes the general path of pgb_gram.cu)
+// class of a term for the cell-owned pass: 0 intercept, 1 plain cubic s(), 2 generic (te() of two marginals, each a
+// plain cubic spline or -- at most one -- an l(); a cubic s() with a by-variable, which is the same design as
+// te(s, l); f(); l()), -1: not representable (the model takes the general path of pgb_gram.cu)
 static int cells_term_class(const DTerm& t) {
   if (t.kind == PGB_TERM_INTERCEPT) return 0;
-  if (t.by >= 0) return -1;
   auto cubic_ok = [](const DMarg& g) { return g.order == 3 && !g.periodic && g.nint >= 1 && g.nint <= 127; };
+  if (t.kind == PGB_TERM_SPLINE && t.by >= 0) return cubic_ok(t.marg[0]) ? 2 : -1;
+  if (t.by >= 0) return -1;
   if (t.kind == PGB_TERM_SPLINE) return (t.fast && cubic_ok(t.marg[0])) ? 1 : -1;
-  if (t.kind == PGB_TERM_TENSOR) return (t.n_marg == 2 && cubic_ok(t.marg[0]) && cubic_ok(t.marg[1])) ? 2 : -1;
+  if (t.kind == PGB_TERM_TENSOR) {
+    if (t.n_marg != 2) return -1;
+    const bool l0 = t.marg[0].order == PGB_MARG_LINEAR, l1 = t.marg[1].order == PGB_MARG_LINEAR;
+    return ((l0 || cubic_ok(t.marg[0])) && (l1 || cubic_ok(t.marg[1])) && !(l0 && l1)) ? 2 : -1;
+  }
   if (t.kind == PGB_TERM_FACTOR) return (t.marg[0].order == 0 && !t.marg[0].periodic && t.n_coefs >= 1 && t.n_coefs <= 200) ? 2 : -1;
   if (t.kind == PGB_TERM_LINEAR) return 2;
   return -1;
+}
+
+// the (outer cubic factors, inner cubic factors, value factors) shapes gram_cells_generic_kernel instantiates
+static bool cells_shape_supported(int n_cubic, int n_val) {
+  const int nout = n_cubic > 2 ? n_cubic - 2 : 0, nin = n_cubic < 2 ? n_cubic : 2;
+  const int shape = nout * 9 + nin * 3 + n_val;
+  switch (shape) {
+    case 1 * 9 + 2 * 3 + 0: case 2 * 9 + 2 * 3 + 0: case 0 * 9 + 2 * 3 + 0: case 0 * 9 + 2 * 3 + 1: case 0 * 9 + 1 * 3 + 0:
+    case 0 * 9 + 1 * 3 + 1: case 0: case 1: case 2: case 0 * 9 + 2 * 3 + 2: case 1 * 9 + 2 * 3 + 1: case 0 * 9 + 1 * 3 + 2:
+      return true;
+    default:
+      return false;
+  }
 }
 
 struct HostFactor { int kind, col, n, nspl, stride; };
@@ -80,8 +99,14 @@ static void term_factors(const DTerm& t, int cls, std::vector<HostFactor>& out) 
   out.clear();
   if (cls == 1) out.push_back({PGB_FK_CUBIC, t.fc0, t.marg[0].nint, t.marg[0].nspl, 1});
   else if (cls == 2 && t.kind == PGB_TERM_TENSOR) {
-    out.push_back({PGB_FK_CUBIC, t.fc0, t.marg[0].nint, t.marg[0].nspl, t.marg[1].nspl});
-    out.push_back({PGB_FK_CUBIC, t.fc0 + 1, t.marg[1].nint, t.marg[1].nspl, 1});
+    for (int q = 0; q < 2; ++q) {  // first marginal slowest in the coefficient index (an l() marginal has one column)
+      const DMarg& g = t.marg[q];
+      if (g.order == PGB_MARG_LINEAR) out.push_back({PGB_FK_VALUE, t.fc0 + q, 1, 1, 1});
+      else out.push_back({PGB_FK_CUBIC, t.fc0 + q, g.nint, g.nspl, q == 0 ? t.marg[1].nspl : 1});
+    }
+  } else if (cls == 2 && t.kind == PGB_TERM_SPLINE) {  // s(j, by=k): the basis row times x_k
+    out.push_back({PGB_FK_CUBIC, t.fc0, t.marg[0].nint, t.marg[0].nspl, 1});
+    out.push_back({PGB_FK_VALUE, t.fc0 + 1, 1, 1, 1});
   } else if (cls == 2 && t.kind == PGB_TERM_FACTOR) out.push_back({PGB_FK_LEVEL, t.fc0, t.n_coefs, t.n_coefs, 1});
   else if (cls == 2 && t.kind == PGB_TERM_LINEAR) out.push_back({PGB_FK_VALUE, t.fc0, 1, 1, 1});
 }
@@ -104,7 +129,7 @@ int pgb_plan_cells(pgb_model* M) {
       continue;
     }
     t.fc0 = ncol;
-    ncol += (t.kind == PGB_TERM_TENSOR) ? 2 : 1;
+    ncol += (t.kind == PGB_TERM_TENSOR || (t.kind == PGB_TERM_SPLINE && t.by >= 0)) ? 2 : 1;
     if (cls[j] == 1) ++n_spl; else ++n_gen;
   }
   if (n_spl + n_gen < 1) return PGB_OK;
@@ -210,6 +235,7 @@ int pgb_plan_cells(pgb_model* M) {
             P.f_key[q] = kd;
           }
         const int nc = (int)cubics.size();
+        if (!cells_shape_supported(nc, P.nval)) { C = pgb_model::Cells(); return PGB_OK; }  // general path
         if (nc >= 1) { P.in_b = cubics[nc - 1]; P.f_ax[P.in_b] = 0; }
         if (nc >= 2) { P.in_a = cubics[nc - 2]; P.f_ax[P.in_a] = 1; }
         if (nc >= 3) { P.out0 = cubics[nc - 3]; P.f_ax[P.out0] = 2; }
@@ -1705,7 +1731,10 @@ gram_cells_generic_kernel(int64_t n, int64_t np, const double* __restrict__ om, 
       PGB_GEN_CASE(0, 0, 0)  // f() x f() / intercept / rhs
       PGB_GEN_CASE(0, 0, 1)  // l() x f() / intercept / rhs
       PGB_GEN_CASE(0, 0, 2)  // l() x l()
-      default: break;        // no other shape is planned (pgb_plan_cells)
+      PGB_GEN_CASE(0, 2, 2)  // s(by=) x s(by=) / te(s, l): a cubic and a value factor on either side
+      PGB_GEN_CASE(1, 2, 1)  // s(by=) / te(s, l) x te(s, s)
+      PGB_GEN_CASE(0, 1, 2)  // s(by=) / te(s, l) x l()
+      default: break;        // no other shape is planned (pgb_plan_cells: cells_shape_supported)
     }
 #undef PGB_GEN_CASE
   }

@@ -76,12 +76,33 @@ PGB_HD double prepass_row_lp(const DTerm* terms, int n_terms, const double* beta
       int cell;
       marg_record(T.marg[0], x(T.marg[0].feature), cell, t, v);
       bt += cell & 0x7f;
-      lp = fma(v[0], bt[0], lp);
-      lp = fma(v[1], bt[1], lp);
-      lp = fma(v[2], bt[2], lp);
-      lp = fma(v[3], bt[3], lp);
+      if (T.by >= 0) {  // s(j, by=k): the basis row times x_k (terms.py:953-954); x_k is the record of a value column
+        const double byv = x(T.by);
+        lp = fma(v[0] * byv, bt[0], lp);
+        lp = fma(v[1] * byv, bt[1], lp);
+        lp = fma(v[2] * byv, bt[2], lp);
+        lp = fma(v[3] * byv, bt[3], lp);
+        store_t(T.fc0 + 1, byv);
+      } else {
+        lp = fma(v[0], bt[0], lp);
+        lp = fma(v[1], bt[1], lp);
+        lp = fma(v[2], bt[2], lp);
+        lp = fma(v[3], bt[3], lp);
+      }
       store_t(T.fc0, t);
       store_c(T.fc0, cell);
+    } else if (T.marg[0].order < 0 || T.marg[1].order < 0) {  // te(s, l) / te(l, s): one cubic and one l() marginal
+      const int qs = T.marg[0].order < 0 ? 1 : 0, ql = 1 - qs;
+      double v[4], t;
+      int cell;
+      marg_record(T.marg[qs], x(T.marg[qs].feature), cell, t, v);
+      const double xl = x(T.marg[ql].feature);
+      bt += cell & 0x7f;  // the l() marginal has a single column: index a * 1 + 0 or 0 * K + a
+#pragma unroll
+      for (int a = 0; a < 4; ++a) lp = fma(v[a] * xl, bt[a], lp);
+      store_t(T.fc0 + qs, t);
+      store_c(T.fc0 + qs, cell);
+      store_t(T.fc0 + ql, xl);
     } else {  // te() of two cubic marginals
       double va[4], vb[4], t0, t1;
       int c0, c1;

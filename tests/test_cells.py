@@ -191,3 +191,25 @@ def test_cells_te_f_l_rows_outside_knots_large():
                        te(s(5, n_splines=5, edge_knots=[0.2, 0.9]), s(0, n_splines=4))])
     gam = _fit_small(case, X, y)
     _compare(gam, X, y, env={"tile": 2048, "band": 3})
+
+
+@gpu
+@pytest.mark.parametrize("env", [{}, {"tile": 1024, "band": 2}])
+def test_cells_by_variables_and_linear_marginals(env):
+    """s(j, by=k), te(s, l) and te(l, s) are generic pairs of the cell-owned pass (a cubic factor times a value factor):
+    equal to the general path, with weights, rows outside the knots, several tiles"""
+    rng = np.random.default_rng(11)
+    n = 40_001
+    # every by-variable / l() column is its own feature: the rows of s(j, by=k) and of te(s, l(k)) sum to x_k, so a column
+    # shared between two such terms (or with an l()) would make the design exactly collinear
+    X = np.column_stack([rng.random(n), 2.0 * rng.random(n) - 0.5, rng.integers(0, 3, n).astype(float), rng.standard_normal(n),
+                         rng.random(n), rng.random(n), rng.standard_normal(n), rng.random(n) + 0.5, rng.standard_normal(n)])
+    eta = np.sin(4 * X[:, 0]) * X[:, 1] + 0.3 * X[:, 2] + 0.2 * X[:, 3] * X[:, 4] + X[:, 5] + 0.1 * X[:, 6] * X[:, 5] + 0.2 * X[:, 8]
+    y = rng.poisson(np.exp(0.3 * eta)).astype(float)
+    w = rng.uniform(0.5, 2.0, n)
+    s, te, f, l = cases.s, cases.te, cases.f, cases.l
+    case = dict(model="PoissonGAM",
+                terms=[s(0, by=1, n_splines=7), te(s(4, n_splines=6), l(3)), te(l(6), s(5, n_splines=5, edge_knots=[0.1, 0.85])),
+                       s(5, n_splines=8), f(2), l(8), te(s(0, n_splines=5), s(4, n_splines=4)), s(4, by=7, n_splines=6)])
+    gam = _fit_small(case, X, y)
+    _compare(gam, X, y, w=w, env=env)

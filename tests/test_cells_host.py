@@ -107,3 +107,22 @@ def test_cell_plan_te_f_l_and_rows_outside_the_knots():
                 terms=[te(s(0, n_splines=6), s(1, n_splines=5)), f(2), l(3), s(4, n_splines=7, edge_knots=[0.1, 0.8]),
                        te(s(5, n_splines=5, edge_knots=[0.2, 0.9]), s(0, n_splines=4))])
     assert _check(case, dict(X=X, y=y), tol=5e-13) >= 15
+
+
+def test_cell_plan_by_variables_and_linear_marginals():
+    """s(j, by=k) and te(s, l) / te(l, s): a cubic factor times a value factor, as generic pairs of the cell-owned pass
+    (against each other, against te(s, s), f(), l() and plain s(); rows outside the knots; weights)"""
+    rng = np.random.default_rng(11)
+    n = 1800
+    # every by-variable / l() column is its own feature: the rows of s(j, by=k) and of te(s, l(k)) sum to x_k, so a column
+    # shared between two such terms (or with an l()) would make the design exactly collinear
+    X = np.column_stack([rng.random(n), 2.0 * rng.random(n) - 0.5, rng.integers(0, 3, n).astype(float), rng.standard_normal(n),
+                         rng.random(n), rng.random(n), rng.standard_normal(n), rng.random(n) + 0.5, rng.standard_normal(n)])
+    eta = np.sin(4 * X[:, 0]) * X[:, 1] + 0.3 * X[:, 2] + 0.2 * X[:, 3] * X[:, 4] + X[:, 5] + 0.1 * X[:, 6] * X[:, 5] + 0.2 * X[:, 8]
+    y = rng.poisson(np.exp(0.3 * eta)).astype(float)
+    w = rng.uniform(0.5, 2.0, n)
+    s, te, f, l = cases.s, cases.te, cases.f, cases.l
+    case = dict(model="PoissonGAM",
+                terms=[s(0, by=1, n_splines=7), te(s(4, n_splines=6), l(3)), te(l(6), s(5, n_splines=5, edge_knots=[0.1, 0.85])),
+                       s(5, n_splines=8), f(2), l(8), te(s(0, n_splines=5), s(4, n_splines=4)), s(4, by=7, n_splines=6)])
+    assert _check(case, dict(X=X, y=y, weights=w), tol=5e-13) >= 30
