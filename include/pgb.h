@@ -274,6 +274,15 @@ int pgb_gram_pass_host(pgb_model* model, int32_t mode, const double* X_host, int
                        int64_t ld, const double* y_host, const float* w_host,
                        const double* beta_host, double* out_host, int64_t chunk_rows);
 
+/* The rows of a fit from the caller's host array to the device shard: replaces the ingestion of GAM.fit / predict
+ * (pygam.py:861-917 -> check_X / check_y, utils.py:96-263, which keep X as an (n, F) row-major host array).
+ * src: (n, F) row-major doubles in pageable or pinned host memory; dst: device memory, column j of X goes to
+ * dst[j * ld .. j * ld + n) (the feature-major layout every pass reads).  n_threads worker threads (0: half the
+ * host cores, at most 8) transpose blocks of rows into pinned staging buffers owned by the library and send each block
+ * with one strided copy on a stream of their own; the call returns when all rows are on the device.  dst must not
+ * have work pending on another stream.  F = 1 uploads a vector (y). */
+int pgb_upload_rows(double* dst, int64_t ld, const double* src, int64_t n, int32_t F, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

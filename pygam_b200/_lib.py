@@ -109,6 +109,7 @@ SYMBOLS = {
     "pgb_chol_check": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, _P]),
     "pgb_chol_check_batch": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P]),
     "pgb_gram_pass_host": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, C.c_int64]),
+    "pgb_upload_rows": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32]),
 }
 
 _lib = None

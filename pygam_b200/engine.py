@@ -64,12 +64,32 @@ class DeviceData:
             X = X[:, None]
         n, F = X.shape
         ld = (n + 15) // 16 * 16
-        buf = torch.zeros((F, ld), dtype=torch.float64, device=device)
+        if device.type != "cuda":  # the CPU test engine (tests/oracle_backend.py)
+            buf = torch.zeros((F, ld), dtype=torch.float64, device=device)
+            Xt = buf[:, :n]
+            Xt.copy_(torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).T)
+            yt = None if y is None else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64).ravel()).to(device)
+            wt = None if w is None else torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32).ravel()).to(device)
+            return cls(Xt, yt, wt)
+        # pgb_upload_rows: worker threads transpose blocks of rows into pinned staging buffers and send each block with
+        # one strided copy -- a pageable cudaMemcpy of the rows plus a device-side transpose cost more than the PIRLS
+        # iterations of a 1e7-row fit
+        lib = _lib.load()
+        Xc = np.ascontiguousarray(X, dtype=np.float64)
+        with torch.cuda.device(device):
+            buf = torch.empty((F, ld), dtype=torch.float64, device=device)
+            if ld > n:
+                buf[:, n:].zero_()
+            yt = None
+            if y is not None:
+                yc = np.ascontiguousarray(y, dtype=np.float64).ravel()
+                yt = torch.empty(len(yc), dtype=torch.float64, device=device)
+            torch.cuda.current_stream().synchronize()  # the workers copy on streams of their own
+            if n:
+                _lib.check(lib.pgb_upload_rows(buf.data_ptr(), ld, Xc.ctypes.data, n, F, 0), "pgb_upload_rows")
+            if yt is not None and len(yc):
+                _lib.check(lib.pgb_upload_rows(yt.data_ptr(), len(yc), yc.ctypes.data, len(yc), 1, 0), "pgb_upload_rows")
         Xt = buf[:, :n]
-        # the rows go up as they are (row-major) and are transposed on the device: a host-side transpose of a
-        # 1e7 x 10 array costs more than the whole fit
-        Xt.copy_(torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(device).T)
-        yt = None if y is None else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64).ravel()).to(device)
         wt = None if w is None else torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32).ravel()).to(device)
         return cls(Xt, yt, wt)
 
@@ -152,6 +172,22 @@ def _cuda_column_stats(data):
     hi = all_reduce_(mm[:, 1].contiguous(), "max")
     bad = all_reduce_(bad, "sum")
     return np.stack([lo.cpu().numpy(), hi.cpu().numpy()], axis=1), bad.cpu().numpy()
+
+
+def vector_range(y):
+    """(min over the finite entries, max, number of non-finite entries) of a device vector in one pgb_col_stats pass
+    (utils.check_y, utils.py:204-248, needs nothing else); local rows only"""
+    if not y.is_cuda:  # the CPU test engine
+        fin = torch.isfinite(y)
+        yf = y[fin]
+        return (float(yf.min()) if yf.numel() else np.inf, float(yf.max()) if yf.numel() else -np.inf, int((~fin).sum()))
+    lib = _lib.load()
+    out = torch.empty(3 + int(lib.pgb_col_stats_ws_bytes(1)) // 8 + 1, dtype=torch.float64, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.check(lib.pgb_col_stats(_ptr(y), y.numel(), y.numel(), 1, _ptr(out), _ptr(out[2:]), _ptr(out[3:]),
+                                     (out.numel() - 3) * 8, _stream()), "pgb_col_stats")
+    h = out[:3].cpu()
+    return float(h[0]), float(h[1]), int(h[2:3].view(torch.int64)[0])
 
 
 def _cuda_count_levels(data, feature, lo, hi):

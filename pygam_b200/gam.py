@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .engine import (DeviceData, all_gather_rows, all_reduce_, column_stats, count_levels, descriptor_key,
-                     get_backend, world)
+                     get_backend, vector_range, world)
 from .terms import FactorTerm, Intercept, SplineTerm, Term, TermList
 
 EPS = np.finfo(np.float64).eps  # pygam/utils.py:16
@@ -300,7 +300,7 @@ class GAM:
                 yh = np.asarray(y)
                 if yh.dtype.kind not in "fiub":
                     raise ValueError("y data must be type int or float, but found type: " + str(yh.dtype))
-                yh = yh.astype(np.float64).ravel()
+                yh = np.asarray(yh, dtype=np.float64).ravel()
                 if len(yh) != Xh.shape[0]:
                     raise ValueError(f"Inconsistent input and output data shapes. found X: {Xh.shape} "
                                      f"and y: {yh.shape}")
@@ -320,18 +320,19 @@ class GAM:
 
     def _check_y(self, y):
         """utils.check_y (utils.py:204-248): finite and inside the link's domain"""
-        if not bool(torch.isfinite(y).all()):
+        lo, hi, nonfinite = vector_range(y)
+        if nonfinite:
             raise ValueError("y data must not contain Inf nor NaN")
         lk, levels = self.link.name, float(self.distribution.levels)
         bad = False
         if lk == "logit":
-            bad = bool(((y < 0) | (y > levels)).any())
+            bad = lo < 0 or hi > levels
         elif lk == "log":
-            bad = bool((y < 0).any())
+            bad = lo < 0
         if bad:
             raise ValueError(f"y data is not in domain of {lk} link function. "
                              f"Expected domain: {self._link_domain()}, but found "
-                             f"{[float(y.min()), float(y.max())]}")
+                             f"{[lo, hi]}")
 
     def _link_domain(self):
         return {"logit": [0.0, float(self.distribution.levels)], "log": [0.0, np.inf]}.get(

@@ -52,3 +52,32 @@ def test_no_cpu_fallback(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libpgb.so")
     with pytest.raises(ImportError):
         _lib.load()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,F,threads", [(1, 1, 0), (7, 3, 1), (100_003, 10, 0), (52_430, 10, 3), (600_001, 1, 0), (2_000, 700, 2),
+                                         (1_300_000, 24, 0)])
+def test_upload_rows_is_a_bit_exact_transpose(n, F, threads):
+    """pgb_upload_rows: (n, F) row-major host rows -> feature-major device columns, bit for bit (blocks that end inside
+    the array, one block, more workers than blocks, a vector); DeviceData.from_host goes through it"""
+    import numpy as np
+    import torch
+
+    from pygam_b200 import _lib, engine
+
+    lib = _lib.load()
+    rng = np.random.default_rng(n + F)
+    X = rng.standard_normal((n, F))
+    X[0, 0] = np.nan  # payload bits travel unchanged
+    ld = n + 5
+    dst = torch.full((F, ld), -1.0, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    _lib.check(lib.pgb_upload_rows(dst.data_ptr(), ld, X.ctypes.data, n, F, threads), "pgb_upload_rows")
+    got = dst.cpu().numpy()
+    assert np.array_equal(got[:, :n].view(np.int64), np.ascontiguousarray(X.T).view(np.int64))
+    assert np.all(got[:, n:] == -1.0)
+    X[0, 0] = 0.5
+    y = rng.standard_normal(n)
+    data = engine.DeviceData.from_host(X, y)
+    assert np.array_equal(data.Xt.cpu().numpy(), X.T) and np.array_equal(data.y.cpu().numpy(), y)
+    assert lib.pgb_upload_rows(dst.data_ptr(), n - 1, X.ctypes.data, n, F, 0) == _lib.EINVAL  # ld < n
