@@ -33,6 +33,22 @@ struct Worker {
 Worker g_workers[kMaxWorkers];
 std::mutex g_upload_mutex;  // one upload at a time per process (the staging buffers are shared)
 
+// the staging buffers of the first kSlabWorkers workers are one pinned allocation made by the first call, whatever
+// its size: a small first fit (few blocks, few workers) must not leave the pinning of the other workers' buffers
+// to the first large one
+const int kSlabWorkers = 8;
+double* g_slab = nullptr;
+
+cudaError_t slab_prepare() {
+  if (g_slab) return cudaSuccess;
+  cudaError_t e = cudaHostAlloc((void**)&g_slab, (size_t)kSlabWorkers * 2 * kStageBytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) return e;
+  for (int k = 0; k < kSlabWorkers; ++k)
+    for (int q = 0; q < 2; ++q)
+      if (!g_workers[k].buf[q]) g_workers[k].buf[q] = g_slab + (size_t)(2 * k + q) * (kStageBytes / sizeof(double));
+  return cudaSuccess;
+}
+
 cudaError_t worker_prepare(Worker& w, int device) {
   if (w.device == device) return cudaSuccess;
   cudaError_t e;
@@ -95,6 +111,15 @@ extern "C" int pgb_upload_rows(double* dst, int64_t ld, const double* src, int64
   int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
   T = (int)std::min<int64_t>(std::min(T, kMaxWorkers), n_blocks);
   std::lock_guard<std::mutex> lock(g_upload_mutex);
+  {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess && n_blocks > 1) e = slab_prepare();  // (a one-block upload pins worker 0's two buffers only)
+    for (int k = 0; k < kSlabWorkers && n_blocks > 1 && e == cudaSuccess; ++k) e = worker_prepare(g_workers[k], device);
+    cudaSetDevice(cur);
+    if (e != cudaSuccess) return pgb_cuda_fail(e, "pgb_upload_rows (staging buffers)");
+  }
   cudaError_t errs[kMaxWorkers];
   auto work = [&](int k) {
     cudaError_t e = cudaSetDevice(device);
