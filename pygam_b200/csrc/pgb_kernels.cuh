@@ -5,6 +5,7 @@
 static const int kSMs = 148;                 // B200
 static const size_t kSmemMax = 227 * 1024;   // opt-in shared memory per CTA on sm_100
 static const int kPassThreads = 480;  // + one producer warp = 16 warps: 128 registers per thread
+static const int kPassThreadsWide = 576;  // + one producer warp = 19 warps: 104 registers per thread (lean instances)
 
 // deterministic block reduction of S per-thread sums -> dst[0..S)
 template <int S>

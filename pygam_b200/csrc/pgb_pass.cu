@@ -54,13 +54,20 @@ static int pass_run(const pgb_model* M, const double* X, int64_t n, int64_t ld, 
   // tables when that leaves three stages, one copy otherwise; two rows per thread when four stages fit.
   PassPlan P;
   size_t fixed = 0;
-  int NS = 0, RPT = 1;
+  int NS = 0, RPT = 1, CT = kPassThreads;
   for (int rep_shift = 3; rep_shift >= 0; rep_shift -= 3) {
     pass_plan_build(M, P, rep_shift);
     fixed = (size_t)((M->m + 1) & ~1) * 8 + (size_t)P.tab_doubles * 8 + PGB_SS_COUNT * 32 * 8 + 2 * 8 * 8 +
             (size_t)M->n_terms * sizeof(DTerm);
-    const size_t stages1 = budget > fixed ? (budget - fixed) / (kPassThreads * rowbytes) : 0;
+    size_t stages1 = budget > fixed ? (budget - fixed) / (kPassThreads * rowbytes) : 0;
     if (stages1 >= 3 || rep_shift == 0) {
+      // 576 consumers instead of 480 where three stages of the longer tiles still fit beside the eight table copies
+      // (configs 2, 4, 5: +2 to +5 points of the HBM peak; config 3's 24 columns keep 480 and two stages)
+      const size_t wide1 = budget > fixed ? (budget - fixed) / (kPassThreadsWide * rowbytes) : 0;
+      if (rep_shift == 3 && !P.n_other && wide1 >= 3) {
+        CT = kPassThreadsWide;
+        stages1 = wide1;
+      }
       if (stages1 >= 2) {
         if (stages1 >= 4 && fin != PASS_FULL && !P.n_other) RPT = 2;
         NS = (int)std::min<size_t>(4, stages1 / RPT);
@@ -76,21 +83,21 @@ static int pass_run(const pgb_model* M, const double* X, int64_t n, int64_t ld, 
       return PGB_EUNSUPPORTED;
     }
   }
-  const int R = RPT * kPassThreads;
+  const int R = RPT * CT;
   for (int q = 0; q < P.n_fast; ++q) P.spl[q].toff = P.spl[q].feature * R * 8;
   const size_t smem = fixed + (size_t)NS * R * rowbytes;
   // TMA bulk copies need 16-byte aligned sources: every column start and every tile start
   const bool bulk_ok = ((uintptr_t)X % 16 == 0) && (ld % 2 == 0) && (!y || (uintptr_t)y % 16 == 0) &&
                        (!w || (uintptr_t)w % 16 == 0);
   const int64_t n_bulk_tiles = (bulk_ok && NS >= 2) ? n / R : 0;
-  const int64_t n_units = std::max<int64_t>(n_bulk_tiles, (n - n_bulk_tiles * R + kPassThreads - 1) / kPassThreads);
+  const int64_t n_units = std::max<int64_t>(n_bulk_tiles, (n - n_bulk_tiles * R + CT - 1) / CT);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, std::min(M->pass_ctas, kSMs)));
   const Family& fm = M->fam;
   const int famk = (fm.dist == PGB_DIST_NORMAL && fm.link == PGB_LINK_IDENTITY)   ? 1
                    : (fm.dist == PGB_DIST_BINOMIAL && fm.link == PGB_LINK_LOGIT) ? 2
                    : (fm.dist == PGB_DIST_POISSON && fm.link == PGB_LINK_LOG)    ? 3
                                                                                  : 0;
-  PassLaunch A{P, M, grid, NS, RPT, famk, smem, st, X, n, ld, n_bulk_tiles, y, w, beta, scale, ybar, poisson_round, part, lp_out, mu_out};
+  PassLaunch A{P, M, grid, NS, RPT, famk, CT, smem, st, X, n, ld, n_bulk_tiles, y, w, beta, scale, ybar, poisson_round, part, lp_out, mu_out};
   const int rc = fin == PASS_FULL   ? pass_dispatch<true, PASS_FULL>(A)
                  : fin == PASS_IRLS ? pass_dispatch<true, PASS_IRLS>(A)
                  : y                ? pass_dispatch<true, PASS_STATS>(A)

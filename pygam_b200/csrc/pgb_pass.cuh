@@ -253,16 +253,18 @@ __device__ __forceinline__ double pass_weight(const float* __restrict__ w, int64
   return w ? (double)__ldg(w + i) : 1.0;
 }
 
-// kPassThreads consumer threads (RPT rows each per tile) + one producer warp
-template <bool HAS_Y, int FIN, int FAMK, int RPT, bool OTHER, int REP>
-__global__ void __launch_bounds__(kPassThreads + 32, 1)
+// CT consumer threads (RPT rows each per tile) + one producer warp.  CT = CT (480: 16 warps, 128 registers per
+// thread) or CTWide (576: 19 warps, 104 registers -- the lean instances need 99) where the model leaves three
+// stages of 576-row tiles: three more warps to hide the latency of the table gathers and of the link arithmetic
+template <bool HAS_Y, int FIN, int FAMK, int RPT, bool OTHER, int REP, int CT>
+__global__ void __launch_bounds__(CT + 32, 1)
 stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ g_terms, int n_terms, int m, int F,
                   Family fam_in, const double* __restrict__ X, int64_t n, int64_t ld, const double* __restrict__ y,
                   const float* __restrict__ w, const double* __restrict__ beta, double scale, double ybar,
                   int poisson_round, int NS, int64_t n_bulk_tiles, double* __restrict__ part,
                   double* __restrict__ lp_out, double* __restrict__ mu_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int R = RPT * kPassThreads;
+  constexpr int R = RPT * CT;
   Family fam = fam_in;
   if (FAMK == 1) { fam.dist = PGB_DIST_NORMAL; fam.link = PGB_LINK_IDENTITY; }
   if (FAMK == 2) { fam.dist = PGB_DIST_BINOMIAL; fam.link = PGB_LINK_LOGIT; }
@@ -281,7 +283,7 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(smem_addr(&mbar[s]), 1);
-      mbar_init(smem_addr(&mbar[NS + s]), kPassThreads / 32);
+      mbar_init(smem_addr(&mbar[NS + s]), CT / 32);
     }
     fence_mbar_init();
   }
@@ -312,9 +314,9 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
   const bool use_w = HAS_Y && (w != nullptr);
   const size_t stage_doubles = (size_t)ncol * R;
 
-  if (tid >= kPassThreads) {
+  if (tid >= CT) {
     // ---- producer warp: one lane keeps NS tiles in flight ----
-    if (tid == kPassThreads) {
+    if (tid == CT) {
       int stage = 0;
       int64_t j = 0;
       for (int64_t t = blockIdx.x; t < n_bulk_tiles; t += gridDim.x, ++j) {
@@ -355,11 +357,11 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
         const float* wt = wtiles + (size_t)stage * R;
         LoadTile load[RPT];
 #pragma unroll
-        for (int k = 0; k < RPT; ++k) load[k] = LoadTile{tile, R, tid + k * kPassThreads};
+        for (int k = 0; k < RPT; ++k) load[k] = LoadTile{tile, R, tid + k * CT};
         pass_lp<RPT, OTHER, REP>(P, s_terms, n_terms, s_beta, s_tab, icpt, load, lp[u]);
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          const int r = tid + k * kPassThreads;
+          const int r = tid + k * CT;
           yv[u][k] = HAS_Y ? tile[(size_t)F * R + r] : 0.0;
           wv[u][k] = !use_w ? 1.0 : FIN == PASS_IRLS ? (double)__fdiv_rn(1.0f, wt[r]) : (double)wt[r];
         }
@@ -375,13 +377,13 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
       } else {
 #pragma unroll
         for (int k = 0; k < RPT; ++k)
-          pass_finish<HAS_Y, FIN>(fam, lp[0][k], row0 + k * kPassThreads, yv[0][k], wv[0][k], scale, ybar, poisson_round, lp_out, mu_out, acc);
+          pass_finish<HAS_Y, FIN>(fam, lp[0][k], row0 + k * CT, yv[0][k], wv[0][k], scale, ybar, poisson_round, lp_out, mu_out, acc);
       }
     }
   }
   // the remaining rows (and inputs that are not 16-byte aligned) with plain loads
-  const int64_t step = (int64_t)gridDim.x * kPassThreads;
-  int64_t i = n_bulk_tiles * R + (int64_t)blockIdx.x * kPassThreads + tid;
+  const int64_t step = (int64_t)gridDim.x * CT;
+  int64_t i = n_bulk_tiles * R + (int64_t)blockIdx.x * CT + tid;
   if (RPT == 2) {  // two rows per thread here as well: twice the loads in flight when nothing is staged
     for (; i + step < n; i += 2 * step) {
       const LoadGlobal load[2] = {LoadGlobal{X, ld, i}, LoadGlobal{X, ld, i + step}};
@@ -412,24 +414,24 @@ stats_pass_kernel(const __grid_constant__ PassPlan P, const DTerm* __restrict__ 
       for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
       if (lane == 0) s_red[s * 32 + warp] = v;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kPassThreads) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
     constexpr int NPART = FIN == PASS_IRLS ? PGB_GS_COUNT + 2 : PGB_SS_COUNT;  // the Gram pass reduces PGB_GS_COUNT + 2 sums per CTA
     if (tid < NPART) {
       double v = 0.0;
-      for (int wq = 0; wq < kPassThreads / 32; ++wq) v += s_red[tid * 32 + wq];
+      for (int wq = 0; wq < CT / 32; ++wq) v += s_red[tid * 32 + wq];
       part[(int64_t)blockIdx.x * NPART + tid] = v;
     }
   }
 }
 
-template <bool HAS_Y, int FIN, int FAMK, int RPT, bool OTHER, int REP>
+template <bool HAS_Y, int FIN, int FAMK, int RPT, bool OTHER, int REP, int CT>
 static int stats_pass_launch(const PassPlan& P, const pgb_model* M, int grid, size_t smem, cudaStream_t st, const double* X,
                              int64_t n, int64_t ld, const double* y, const float* w, const double* beta, double scale,
                              double ybar, int poisson_round, int NS, int64_t n_bulk_tiles, double* part, double* lp_out,
                              double* mu_out) {
-  PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<HAS_Y, FIN, FAMK, RPT, OTHER, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PGB_CUDA(cudaFuncSetAttribute(stats_pass_kernel<HAS_Y, FIN, FAMK, RPT, OTHER, REP, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kSmemMax));
-  stats_pass_kernel<HAS_Y, FIN, FAMK, RPT, OTHER, REP><<<grid, kPassThreads + 32, smem, st>>>(
+  stats_pass_kernel<HAS_Y, FIN, FAMK, RPT, OTHER, REP, CT><<<grid, CT + 32, smem, st>>>(
       P, M->d_terms, M->n_terms, M->m, M->n_features, M->fam, X, n, ld, y, w, beta, scale, ybar, poisson_round, NS,
       n_bulk_tiles, part, lp_out, mu_out);
   return PGB_OK;
@@ -439,7 +441,7 @@ static int stats_pass_launch(const PassPlan& P, const pgb_model* M, int grid, si
 struct PassLaunch {
   PassPlan P;
   const pgb_model* M;
-  int grid, NS, RPT, famk;
+  int grid, NS, RPT, famk, threads;
   size_t smem;
   cudaStream_t st;
   const double* X;
@@ -458,9 +460,15 @@ int pass_dispatch(const PassLaunch& A) {
   const PassPlan& P = A.P;
   int rc = PGB_OK;
 #define PGB_STATS_ARGS P, A.M, A.grid, A.smem, A.st, A.X, A.n, A.ld, A.y, A.w, A.beta, A.scale, A.ybar, A.poisson_round, A.NS, A.n_bulk_tiles, A.part, A.lp_out, A.mu_out
-#define PGB_STATS_REP(FK, RP, OT)                                                    \
-  rc = P.rep_shift ? stats_pass_launch<HAS_Y, FIN, FK, RP, OT, 8>(PGB_STATS_ARGS)    \
-                   : stats_pass_launch<HAS_Y, FIN, FK, RP, OT, 1>(PGB_STATS_ARGS);
+#define PGB_STATS_REP(FK, RP, OT)                                                                                   \
+  if constexpr (!(OT)) {                                                                                            \
+    if (A.threads == kPassThreadsWide) {  /* pass_run: only lean models with eight table copies */                  \
+      rc = stats_pass_launch<HAS_Y, FIN, FK, RP, OT, 8, kPassThreadsWide>(PGB_STATS_ARGS);                          \
+      break;                                                                                                        \
+    }                                                                                                               \
+  }                                                                                                                 \
+  rc = P.rep_shift ? stats_pass_launch<HAS_Y, FIN, FK, RP, OT, 8, kPassThreads>(PGB_STATS_ARGS)                     \
+                   : stats_pass_launch<HAS_Y, FIN, FK, RP, OT, 1, kPassThreads>(PGB_STATS_ARGS);
 #define PGB_STATS_FAM(RP, OT)                        \
   switch (A.famk) {                                  \
     case 1: PGB_STATS_REP(1, RP, OT) break;          \
