@@ -10,6 +10,7 @@
 // second device copy of X.  The staging buffers are pinned once per process and reused.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -41,8 +42,14 @@ double* g_slab = nullptr;
 
 cudaError_t slab_prepare() {
   if (g_slab) return cudaSuccess;
-  cudaError_t e = cudaHostAlloc((void**)&g_slab, (size_t)kSlabWorkers * 2 * kStageBytes, cudaHostAllocPortable);
-  if (e != cudaSuccess) return e;
+  const size_t bytes = (size_t)kSlabWorkers * 2 * kStageBytes;
+  if (cudaHostAlloc((void**)&g_slab, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    // no pinned memory to be had (a locked-memory limit): pageable staging buffers still work -- the copies are then
+    // staged once more inside the driver and complete before cudaMemcpy2DAsync returns -- only slower
+    cudaGetLastError();
+    g_slab = static_cast<double*>(aligned_alloc(4096, bytes));
+    if (!g_slab) return cudaErrorMemoryAllocation;
+  }
   for (int k = 0; k < kSlabWorkers; ++k)
     for (int q = 0; q < 2; ++q)
       if (!g_workers[k].buf[q]) g_workers[k].buf[q] = g_slab + (size_t)(2 * k + q) * (kStageBytes / sizeof(double));
@@ -60,7 +67,11 @@ cudaError_t worker_prepare(Worker& w, int device) {
     if ((e = cudaSetDevice(device)) != cudaSuccess) return e;
   }
   for (int q = 0; q < 2; ++q) {
-    if (!w.buf[q] && (e = cudaHostAlloc((void**)&w.buf[q], kStageBytes, cudaHostAllocPortable)) != cudaSuccess) return e;
+    if (!w.buf[q] && cudaHostAlloc((void**)&w.buf[q], kStageBytes, cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();  // pageable staging, as in slab_prepare
+      w.buf[q] = static_cast<double*>(aligned_alloc(4096, kStageBytes));
+      if (!w.buf[q]) return cudaErrorMemoryAllocation;
+    }
     if ((e = cudaEventCreateWithFlags(&w.done[q], cudaEventDisableTiming)) != cudaSuccess) return e;
   }
   if ((e = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
