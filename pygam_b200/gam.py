@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .engine import (DeviceData, all_gather_rows, all_reduce_, column_stats, count_levels, descriptor_key,
-                     get_backend, vector_range, world)
+                     get_backend, single_rank, vector_range, world)
 from .terms import FactorTerm, Intercept, SplineTerm, Term, TermList
 
 EPS = np.finfo(np.float64).eps  # pygam/utils.py:16
@@ -872,16 +872,18 @@ class GAM:
         F = self.statistics_["m_features"]
         if data.n_features != F:
             raise ValueError(f"X data must have {F} features, but found {data.n_features}")
-        if not bool(torch.isfinite(data.Xt).all()):
+        with single_rank():  # this rank's rows only (not memoised in `data`: a fit needs the statistics of all ranks):
+            col_minmax, bad = get_backend().column_stats(data)  # one pass gives the finite check and the column ranges
+        if bad.sum() > 0:
             raise ValueError("X data must not contain Inf nor NaN")
         for t in self.terms:  # categorical range check, utils.py:308-334
             if isinstance(t, FactorTerm):
-                col = data.Xt[t.feature]
                 lo, hi = float(t.edge_knots_[0]), float(t.edge_knots_[-1])
-                if bool(((col < lo) | (col > hi)).any()):
+                xlo, xhi = float(col_minmax[t.feature, 0]), float(col_minmax[t.feature, 1])
+                if xlo < lo or xhi > hi:
                     raise ValueError(f"X data is out of domain for categorical feature {t.feature}. "
                                      f"Expected data on [{lo}, {hi}], but found data on "
-                                     f"[{float(col.min())}, {float(col.max())}]")
+                                     f"[{xlo}, {xhi}]")
 
     def _modelmat(self, X, term=-1):
         """dense model matrix of a (small) X, for inspection (pygam.py:469-497)"""
