@@ -64,7 +64,9 @@ class DeviceData:
             X = X[:, None]
         n, F = X.shape
         ld = (n + 15) // 16 * 16
-        if device.type != "cuda":  # the CPU test engine (tests/oracle_backend.py)
+        if device.type != "cuda":  # the CPU test engine (tests/oracle_backend.py) only: the product has no CPU path
+            if isinstance(get_backend(), CudaBackend):
+                raise RuntimeError("pygam_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
             buf = torch.zeros((F, ld), dtype=torch.float64, device=device)
             Xt = buf[:, :n]
             Xt.copy_(torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).T)
@@ -177,7 +179,9 @@ def _cuda_column_stats(data):
 def vector_range(y):
     """(min over the finite entries, max, number of non-finite entries) of a device vector in one pgb_col_stats pass
     (utils.check_y, utils.py:204-248, needs nothing else); local rows only"""
-    if not y.is_cuda:  # the CPU test engine
+    if not y.is_cuda:  # the CPU test engine (tests/oracle_backend.py) only: the product has no CPU path
+        if isinstance(get_backend(), CudaBackend):
+            raise RuntimeError("pygam_b200 needs the data on a CUDA device; there is no CPU fallback")
         fin = torch.isfinite(y)
         yf = y[fin]
         return (float(yf.min()) if yf.numel() else np.inf, float(yf.max()) if yf.numel() else -np.inf, int((~fin).sum()))
