@@ -431,7 +431,7 @@ class GAM:
         assert np.isfinite(self.coef_).all(), f"coefficients should be well-behaved, but found: {self.coef_}"
         self.coef_ = np.asarray(self.coef_, dtype=np.float64)
 
-        Pn, Pr = self.terms.build_penalties(split=True)
+        Pn, Pr = self.terms._penalties(split=True)
         S = np.eye(m) * np.sqrt(EPS)
         constrained = self.terms.hasconstraint
         if not constrained:
@@ -445,8 +445,8 @@ class GAM:
         diff = np.inf
         for _ in range(self.max_iter):
             if constrained:
-                Pn, Pr = self.terms.build_penalties(split=True)
-                Cn, Cr = self.terms.build_constraints(self.coef_, self._constraint_lam, self._constraint_l2,
+                Pn, Pr = self.terms._penalties(split=True)
+                Cn, Cr = self.terms._constraints(self.coef_, self._constraint_lam, self._constraint_l2,
                                                       split=True)
                 # the reference factors S + P + C (pygam.py:758-761); any diagonal loading its
                 # retry loop adds lands in the part that is not null-annihilating
@@ -582,7 +582,16 @@ class GAM:
         coef = np.array(self.coef_[idxs])
         if isinstance(self.terms[term_i], SplineTerm):
             coef -= coef.mean()
-        inv_cov, rank = scipy.linalg.pinv(cov, return_rank=True)
+        # pinv and rank of the block as scipy.linalg.pinv computes them (pygam.py:1283), with one difference.  A block
+        # with fewer distinct x than splines (wage: 7 years on 20 splines) has directions of exactly zero variance;
+        # in the reference's cov (a product B B^T from its SVD) they sit at 1e-15 of the largest singular value, below
+        # scipy's cut-off max(M, N) eps, and its rank is 7.  cov here comes through the normal equations and carries
+        # eps * cond(G + P) there (1e-11 .. 1e-10 on wage): above that cut-off, which would make the rank 19 and the
+        # p-value 0.40 instead of 0.006.  The cut-off is therefore sqrt(eps) of the largest singular value: the same
+        # rank as the reference wherever the true singular values of the block stay above 1.5e-8 of the largest.
+        U, sv, Vt = np.linalg.svd(cov)
+        rank = int(np.sum(sv > sv[0] * np.sqrt(EPS))) if sv[0] > 0 else 0
+        inv_cov = (Vt[:rank].T / sv[:rank]).dot(U[:, :rank].T)
         score = coef.T.dot(inv_cov).dot(coef)
         if self.distribution._known_scale:
             return 1 - scipy.stats.chi2.cdf(x=score, df=rank)
@@ -1034,10 +1043,10 @@ class GAM:
         return out[0]
 
     def _P(self):
-        return self.terms.build_penalties()
+        return self.terms._penalties()
 
     def _C(self):
-        return self.terms.build_constraints(self.coef_, self._constraint_lam, self._constraint_l2)
+        return self.terms._constraints(self.coef_, self._constraint_lam, self._constraint_l2)
 
     def loglikelihood(self, X, y, weights=None):
         data = self._prepare_data(X, y, weights, fitting=True)
@@ -1209,7 +1218,7 @@ class GAM:
             e = np.zeros(L.shape[1])
             e[c] = 1.0
             scratch.lam = list(e)
-            pn, pr = scratch.build_penalties(split=True)
+            pn, pr = scratch._penalties(split=True)
             unit_n.append(pn)
             unit_r.append(pr)
         Pn_all = (L @ np.stack(unit_n).reshape(L.shape[1], m * m)).reshape(-1, m, m)

@@ -14,6 +14,7 @@ import warnings
 
 import numpy as np
 import scipy.linalg
+import scipy.sparse
 
 from . import penalties as _pen
 
@@ -151,7 +152,16 @@ class Term:
         return self
 
     # -- m x m pieces --
-    def build_penalties(self, split=False):
+    def build_penalties(self, verbose=False):
+        """the penalty matrix of the term as the reference returns it (terms.py:307-349, 1479-1517): scipy sparse.
+        The engine works on the dense form, ``_penalties``."""
+        return scipy.sparse.csc_matrix(self._penalties())
+
+    def build_constraints(self, coef, constraint_lam, constraint_l2):
+        """the constraint matrix of the term as the reference returns it (terms.py:351-396, 1519-1609): scipy sparse"""
+        return scipy.sparse.csc_matrix(self._constraints(coef, constraint_lam, constraint_l2))
+
+    def _penalties(self, split=False):
         """sum_k lam_k * penalty_k(n_coefs) (terms.py:307-349).  With split=True returns the sum
         as (null_part, rest): null_part collects the components that annihilate the constant
         vector of the block (difference penalties), see ``split_by_constant``."""
@@ -177,7 +187,7 @@ class Term:
             parts.append(comp)
         return split_by_constant(parts, n) if split else total
 
-    def build_constraints(self, coef, constraint_lam, constraint_l2, split=False):
+    def _constraints(self, coef, constraint_lam, constraint_l2, split=False):
         """sum_k constraint_k(n, coef) * constraint_lam, plus constraint_l2 * I on a block
         with violations (terms.py:351-396)"""
         if self.isintercept:
@@ -448,37 +458,62 @@ class TensorTerm(Term):
             raise ValueError(f"by variable requires feature {self.by}, but X has only {X.shape[1]} dimensions")
         return self
 
-    def build_penalties(self, split=False):
-        """sum_i I x ... x P_i x ... x I (terms.py:1479-1517)"""
-        total = 0
-        parts = []
-        for i in range(len(self._terms)):
-            acc = None
-            for j, t in enumerate(self._terms):
-                Pj = t.build_penalties() if j == i else np.eye(t.n_coefs)
-                acc = Pj if acc is None else np.kron(acc, Pj)
-            total = total + acc
-            parts.append(acc)
-        return split_by_constant(parts, self.n_coefs) if split else total
+    def _marginal_penalty(self, i):
+        """I x ... x P_i x ... x I, dense (terms.py:1499-1517)"""
+        acc = None
+        for j, t in enumerate(self._terms):
+            Pj = t._penalties() if j == i else np.eye(t.n_coefs)
+            acc = Pj if acc is None else np.kron(acc, Pj)
+        return acc
 
-    def build_constraints(self, coef, constraint_lam, constraint_l2, split=False):
-        """every 1-d slice of the coefficient tensor along each marginal gets that marginal's
-        constraint matrix (terms.py:1519-1609)"""
+    def _marginal_constraint(self, i, coef, constraint_lam, constraint_l2, split=False):
+        """every 1-d slice of the coefficient tensor along marginal i gets that marginal's constraint matrix, dense
+        (terms.py:1560-1609); split=True: (null part, rest)"""
         dims = [t.n_coefs for t in self._terms]
         size = int(np.prod(dims))
         C = np.zeros((size, size))
         Cn = np.zeros((size, size))
         idx = np.arange(size).reshape(dims)
         coef = np.asarray(coef)
-        for i, t in enumerate(self._terms):
-            slices = np.moveaxis(idx, i, 0).reshape(dims[i], size // dims[i])
-            for sl in slices.T:
-                if split:
-                    a, b = t.build_constraints(coef[sl], constraint_lam, constraint_l2, split=True)
-                    Cn[np.ix_(sl, sl)] += a
-                    C[np.ix_(sl, sl)] += b
-                else:
-                    C[np.ix_(sl, sl)] += t.build_constraints(coef[sl], constraint_lam, constraint_l2)
+        t = self._terms[i]
+        slices = np.moveaxis(idx, i, 0).reshape(dims[i], size // dims[i])
+        for sl in slices.T:
+            if split:
+                a, b = t._constraints(coef[sl], constraint_lam, constraint_l2, split=True)
+                Cn[np.ix_(sl, sl)] += a
+                C[np.ix_(sl, sl)] += b
+            else:
+                C[np.ix_(sl, sl)] += t._constraints(coef[sl], constraint_lam, constraint_l2)
+        return (Cn, C) if split else C
+
+    def _build_marginal_penalties(self, i):
+        """the reference's helper of the same name (terms.py:1499-1517): scipy sparse"""
+        return scipy.sparse.csc_matrix(self._marginal_penalty(i))
+
+    def _build_marginal_constraints(self, i, coef, constraint_lam, constraint_l2):
+        """the reference's helper of the same name (terms.py:1560-1609): scipy sparse"""
+        return scipy.sparse.csc_matrix(self._marginal_constraint(i, coef, constraint_lam, constraint_l2))
+
+    def _penalties(self, split=False):
+        """sum_i I x ... x P_i x ... x I (terms.py:1479-1517)"""
+        parts = [self._marginal_penalty(i) for i in range(len(self._terms))]
+        total = 0
+        for acc in parts:
+            total = total + acc
+        return split_by_constant(parts, self.n_coefs) if split else total
+
+    def _constraints(self, coef, constraint_lam, constraint_l2, split=False):
+        """the sum of the marginal constraint matrices (terms.py:1519-1558)"""
+        size = self.n_coefs
+        C = np.zeros((size, size))
+        Cn = np.zeros((size, size))
+        for i in range(len(self._terms)):
+            if split:
+                a, b = self._marginal_constraint(i, coef, constraint_lam, constraint_l2, split=True)
+                Cn += a
+                C += b
+            else:
+                C += self._marginal_constraint(i, coef, constraint_lam, constraint_l2)
         return (Cn, C) if split else C
 
 
@@ -681,22 +716,30 @@ class TermList:
         return feats
 
     # ---- m x m pieces ----
-    def build_penalties(self, split=False):
+    def build_penalties(self, verbose=False):
+        """block-diagonal penalty matrix as the reference returns it (terms.py:1925-1947): scipy sparse"""
+        return scipy.sparse.csc_matrix(self._penalties())
+
+    def build_constraints(self, coef, constraint_lam, constraint_l2):
+        """block-diagonal constraint matrix as the reference returns it (terms.py:1949-1979): scipy sparse"""
+        return scipy.sparse.csc_matrix(self._constraints(coef, constraint_lam, constraint_l2))
+
+    def _penalties(self, split=False):
         """block-diagonal penalty matrix P (terms.py:1925-1947), dense (m, m); split=True returns
         (P_null, P_rest) with P = P_null + P_rest (see ``split_by_constant``)"""
         if split:
-            parts = [t.build_penalties(split=True) for t in self._terms]
+            parts = [t._penalties(split=True) for t in self._terms]
             return (scipy.linalg.block_diag(*[a for a, _ in parts]),
                     scipy.linalg.block_diag(*[b for _, b in parts]))
-        return scipy.linalg.block_diag(*[t.build_penalties() for t in self._terms])
+        return scipy.linalg.block_diag(*[t._penalties() for t in self._terms])
 
-    def build_constraints(self, coef, constraint_lam, constraint_l2, split=False):
+    def _constraints(self, coef, constraint_lam, constraint_l2, split=False):
         """block-diagonal constraint matrix C (terms.py:1949-1979), dense (m, m)"""
         coef = np.asarray(coef, dtype=np.float64).ravel()
         blocks, start = [], 0
         for t in self._terms:
             n = t.n_coefs
-            blocks.append(t.build_constraints(coef[start:start + n], constraint_lam, constraint_l2, split=split))
+            blocks.append(t._constraints(coef[start:start + n], constraint_lam, constraint_l2, split=split))
             start += n
         if split:
             return (scipy.linalg.block_diag(*[a for a, _ in blocks]),

@@ -235,7 +235,7 @@ def test_stats_pass_large_interval_tables_and_many_tiles(n_terms, n_splines):
     # that pgb_solve stages in shared memory (the rest is read from the matrix) and past the 860 of pgb_chol_check
     m = eng.m
     out = ora.gram_pass(DeviceData.from_host(Xn, y, None, device="cpu"), coef).numpy().copy()
-    Pn, Pr = gam.terms.build_penalties(split=True)
+    Pn, Pr = gam.terms._penalties(split=True)
     EtE = np.eye(m) * np.sqrt(orc.EPS) + Pr
     eng.out.copy_(torch.from_numpy(out))
     eng.set_penalty(EtE, Pn)
@@ -260,10 +260,10 @@ def test_solve_matches_numpy_mirror(name):
     m = eng.m
     cpu = _cpu_data(g, case)
     out = ora.gram_pass(cpu, g["coef"]).numpy().copy()
-    Pn, Pr = gam.terms.build_penalties(split=True)
+    Pn, Pr = gam.terms._penalties(split=True)
     np.testing.assert_array_equal(Pn + Pr, gam._P())
     if gam.terms.hasconstraint:  # 1e9-stiff constraint penalty, all of it null-annihilating
-        Cn, Cr = gam.terms.build_constraints(g["coef"], gam._constraint_lam, gam._constraint_l2, split=True)
+        Cn, Cr = gam.terms._constraints(g["coef"], gam._constraint_lam, gam._constraint_l2, split=True)
         Pn, Pr = Pn + Cn, Pr + Cr
         assert np.abs(Cn).max() >= 1e9
     EtE = np.eye(m) * np.sqrt(orc.EPS) + Pr

@@ -42,7 +42,7 @@ def test_fit_matches_reference(name):
     np.testing.assert_array_equal(gam._P(), g["penalty"])
     check_against_golden(gam, g, constrained=name in helpers.CONSTRAINED)
     if "constraint_final" in g:
-        C = gam.terms.build_constraints(g["coef"], gam._constraint_lam, gam._constraint_l2)
+        C = gam.terms._constraints(g["coef"], gam._constraint_lam, gam._constraint_l2)
         np.testing.assert_allclose(C, g["constraint_final"], rtol=1e-15, atol=0)
 
 

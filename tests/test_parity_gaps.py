@@ -208,18 +208,21 @@ def test_p_values_standard_errors_aicc(kind, name):
     # p-values: Wald statistics of the centred spline coefficients; the intercept's cov entry sits on the null space
     pv, pv_ref = np.asarray(st["p_values"], float), g["stat_p_values"]
     assert len(pv) == len(pv_ref) and np.all((pv >= 0) & (pv <= 1))
-    # _compute_p_value takes pinv(cov block) with scipy's rank cut-off (pygam.py:1283).  Where the reference's block
-    # has singular values near that cut-off (fewer distinct x than splines: wage's 7 years on 20 splines; te() x by)
-    # its rank -- hence the p-value -- is decided by the rounding noise of ITS cov: only unambiguous blocks compare
+    # _compute_p_value takes pinv(cov block) with a rank cut-off (pygam.py:1283): scipy's max(M, N) eps in the reference,
+    # sqrt(eps) here (cov through the normal equations carries more noise along directions of zero variance: wage's 7
+    # years on 20 splines are rank 7 in both).  Blocks where the two cut-offs disagree on the REFERENCE's cov do not compare.
+    compared = 0
     for i, t in enumerate(gam.terms):
         if t.isintercept or "stat_cov" not in g:
             continue
         idx = gam.terms.get_coef_indices(i)
         sv = np.linalg.svd(g["stat_cov"][idx][:, idx], compute_uv=False)
         cut = sv.max() * len(idx) * np.finfo(float).eps
-        if np.any((sv > cut * 1e-4) & (sv < cut * 1e6)):
+        if np.any((sv > cut) & (sv < sv.max() * 1e-7)):
             continue
+        compared += 1
         np.testing.assert_allclose(pv[i], pv_ref[i], rtol=1e-5, atol=1e-9)
+    assert compared >= (2 if name == "c1_wage" else 1) or "stat_cov" not in g
 
 
 @pytest.mark.parametrize("kind", BACKENDS)
@@ -346,7 +349,7 @@ def test_truncated_solve_kernel_matches_numpy(m, rank):
     B = rng.standard_normal((rank + 3, m))
     G = B.T @ B
     r = B.T @ rng.standard_normal(rank + 3)
-    P, _ = terms.build_penalties(split=True)
+    P, _ = terms._penalties(split=True)
     E = np.eye(m) * np.sqrt(np.finfo(float).eps) + 0.6 * P
     for e in (eng, ora):
         e.out[:m * m] = torch.from_numpy(G.ravel()).to(e.out.device)

@@ -8,8 +8,7 @@ the repository.
     python tools/run_reference_tests.py            # the six files that test the public API
     python tools/run_reference_tests.py -k summary # extra arguments go to pytest
 
-Expected: 107 passed, 1 skipped, 3 failed -- test_pvalue_invariant_to_scale (p-value of a rank-deficient block, DESIGN.md
-section 5) and two tests of private helpers (`_build_marginal_penalties`, scipy-sparse penalty matrices).
+Expected: 110 passed, 1 skipped.
 """
 import os
 import shutil
