@@ -152,24 +152,9 @@ class Term:
         return self
 
     # -- m x m pieces --
-    def build_penalties(self, verbose=False):
-        """the penalty matrix of the term as the reference returns it (terms.py:307-349, 1479-1517): scipy sparse.
-        The engine works on the dense form, ``_penalties``."""
-        return scipy.sparse.csc_matrix(self._penalties())
-
-    def build_constraints(self, coef, constraint_lam, constraint_l2):
-        """the constraint matrix of the term as the reference returns it (terms.py:351-396, 1519-1609): scipy sparse"""
-        return scipy.sparse.csc_matrix(self._constraints(coef, constraint_lam, constraint_l2))
-
-    def _penalties(self, split=False):
-        """sum_k lam_k * penalty_k(n_coefs) (terms.py:307-349).  With split=True returns the sum
-        as (null_part, rest): null_part collects the components that annihilate the constant
-        vector of the block (difference penalties), see ``split_by_constant``."""
-        if self.isintercept:
-            return (np.array([[0.0]]), np.array([[0.0]])) if split else np.array([[0.0]])
-        n = self.n_coefs
-        total = np.zeros((n, n))
-        parts = []
+    def _penalty_generators(self):
+        """the (callable, lam) pairs of the term, 'auto' resolved (terms.py:322-340)"""
+        out = []
         for pen, lam in zip(self.penalties, self.lam):
             if pen == "auto":
                 if self.dtype == "numerical":
@@ -181,7 +166,45 @@ class Term:
                     pen = "l2"
             if pen is None:
                 pen = "none"
-            fn = _pen.PENALTIES[pen] if isinstance(pen, str) else pen
+            out.append((_pen.PENALTIES[pen] if isinstance(pen, str) else pen, lam))
+        return out
+
+    def build_penalties(self, verbose=False):
+        """the penalty matrix of the term as the reference returns it (terms.py:307-349): scipy sparse, never densified
+        (the reference's tests build it for a 10^6-coefficient te()).  The engine works on the dense form, ``_penalties``."""
+        if self.isintercept:
+            return scipy.sparse.csc_matrix((1, 1))
+        n = self.n_coefs
+        total = scipy.sparse.csc_matrix((n, n))
+        for fn, lam in self._penalty_generators():
+            total = total + scipy.sparse.csc_matrix(fn(n, None)) * lam
+        return scipy.sparse.csc_matrix(total)
+
+    def build_constraints(self, coef, constraint_lam, constraint_l2):
+        """the constraint matrix of the term as the reference returns it (terms.py:351-396): scipy sparse"""
+        if self.isintercept:
+            return scipy.sparse.csc_matrix((1, 1))
+        n = self.n_coefs
+        total = scipy.sparse.csc_matrix((n, n))
+        for c in self.constraints:
+            if c is None:
+                c = "none"
+            fn = _pen.CONSTRAINTS[c] if isinstance(c, str) else c
+            total = total + scipy.sparse.csc_matrix(fn(n, coef)) * constraint_lam
+        if total.count_nonzero() > 0:
+            total = total + constraint_l2 * scipy.sparse.identity(n, format="csc")
+        return scipy.sparse.csc_matrix(total)
+
+    def _penalties(self, split=False):
+        """sum_k lam_k * penalty_k(n_coefs) (terms.py:307-349).  With split=True returns the sum
+        as (null_part, rest): null_part collects the components that annihilate the constant
+        vector of the block (difference penalties), see ``split_by_constant``."""
+        if self.isintercept:
+            return (np.array([[0.0]]), np.array([[0.0]])) if split else np.array([[0.0]])
+        n = self.n_coefs
+        total = np.zeros((n, n))
+        parts = []
+        for fn, lam in self._penalty_generators():
             comp = np.multiply(np.asarray(_dense(fn(n, None)), dtype=np.float64), lam)
             total = total + comp
             parts.append(comp)
@@ -487,12 +510,42 @@ class TensorTerm(Term):
         return (Cn, C) if split else C
 
     def _build_marginal_penalties(self, i):
-        """the reference's helper of the same name (terms.py:1499-1517): scipy sparse"""
-        return scipy.sparse.csc_matrix(self._marginal_penalty(i))
+        """I x ... x P_i x ... x I as a scipy sparse Kronecker product (terms.py:1499-1517)"""
+        acc = None
+        for j, t in enumerate(self._terms):
+            Pj = t.build_penalties() if j == i else scipy.sparse.identity(t.n_coefs, format="csc")
+            acc = Pj if acc is None else scipy.sparse.kron(acc, Pj, format="csc")
+        return scipy.sparse.csc_matrix(acc)
 
     def _build_marginal_constraints(self, i, coef, constraint_lam, constraint_l2):
-        """the reference's helper of the same name (terms.py:1560-1609): scipy sparse"""
-        return scipy.sparse.csc_matrix(self._marginal_constraint(i, coef, constraint_lam, constraint_l2))
+        """the constraint matrices of the 1-d slices along marginal i, assembled in coordinate form (terms.py:1560-1609)"""
+        dims = [t.n_coefs for t in self._terms]
+        size = int(np.prod(dims))
+        coef = np.asarray(coef)
+        idx = np.arange(size).reshape(dims)
+        slices = np.moveaxis(idx, i, 0).reshape(dims[i], size // dims[i])
+        data, rows, cols = [], [], []
+        for sl in slices.T:
+            Cs = self._terms[i].build_constraints(coef[sl], constraint_lam, constraint_l2).tocoo()
+            data.append(Cs.data)
+            rows.append(sl[Cs.row])
+            cols.append(sl[Cs.col])
+        return scipy.sparse.coo_matrix((np.concatenate(data), (np.concatenate(rows), np.concatenate(cols))),
+                                       shape=(size, size)).tocsc()
+
+    def build_penalties(self, verbose=False):
+        """sum_i I x ... x P_i x ... x I, scipy sparse (terms.py:1479-1497)"""
+        P = scipy.sparse.csc_matrix((self.n_coefs, self.n_coefs))
+        for i in range(len(self._terms)):
+            P = P + self._build_marginal_penalties(i)
+        return scipy.sparse.csc_matrix(P)
+
+    def build_constraints(self, coef, constraint_lam, constraint_l2):
+        """the sum of the marginal constraint matrices, scipy sparse (terms.py:1519-1558)"""
+        C = scipy.sparse.csc_matrix((self.n_coefs, self.n_coefs))
+        for i in range(len(self._terms)):
+            C = C + self._build_marginal_constraints(i, coef, constraint_lam, constraint_l2)
+        return scipy.sparse.csc_matrix(C)
 
     def _penalties(self, split=False):
         """sum_i I x ... x P_i x ... x I (terms.py:1479-1517)"""
@@ -718,11 +771,16 @@ class TermList:
     # ---- m x m pieces ----
     def build_penalties(self, verbose=False):
         """block-diagonal penalty matrix as the reference returns it (terms.py:1925-1947): scipy sparse"""
-        return scipy.sparse.csc_matrix(self._penalties())
+        return scipy.sparse.block_diag([t.build_penalties() for t in self._terms], format="csc")
 
     def build_constraints(self, coef, constraint_lam, constraint_l2):
         """block-diagonal constraint matrix as the reference returns it (terms.py:1949-1979): scipy sparse"""
-        return scipy.sparse.csc_matrix(self._constraints(coef, constraint_lam, constraint_l2))
+        coef = np.asarray(coef, dtype=np.float64).ravel()
+        blocks, start = [], 0
+        for t in self._terms:
+            blocks.append(t.build_constraints(coef[start:start + t.n_coefs], constraint_lam, constraint_l2))
+            start += t.n_coefs
+        return scipy.sparse.block_diag(blocks, format="csc")
 
     def _penalties(self, split=False):
         """block-diagonal penalty matrix P (terms.py:1925-1947), dense (m, m); split=True returns

@@ -26,12 +26,12 @@ def test_penalties_known_answers():
     g = load("penalties")
     for n in (1, 2, 3, 5, 8, 20):
         coef = g[f"coef_{n}"]
-        np.testing.assert_array_equal(pg_pen.derivative(n), g[f"derivative_{n}"])
-        np.testing.assert_array_equal(pg_pen.l2(n), g[f"l2_{n}"])
+        np.testing.assert_array_equal(pg_pen.derivative(n).toarray(), g[f"derivative_{n}"])
+        np.testing.assert_array_equal(pg_pen.l2(n).toarray(), g[f"l2_{n}"])
         if n >= 5:
-            np.testing.assert_array_equal(pg_pen.periodic(n), g[f"periodic_{n}"])
+            np.testing.assert_array_equal(pg_pen.periodic(n).toarray(), g[f"periodic_{n}"])
         for cname in ("monotonic_inc", "monotonic_dec", "convex", "concave"):
-            np.testing.assert_array_equal(pg_pen.CONSTRAINTS[cname](n, coef), g[f"{cname}_{n}"])
+            np.testing.assert_array_equal(pg_pen.CONSTRAINTS[cname](n, coef).toarray(), g[f"{cname}_{n}"])
 
 
 @pytest.mark.parametrize("name", sorted(cases.FIT_CASES))
@@ -125,3 +125,28 @@ def test_input_validation():
         pg.LinearGAM(callbacks=[object()])
     with pytest.raises(AttributeError):
         pg.LinearGAM().predict_mu(X)
+
+
+@pytest.mark.parametrize("name", ["c1_wage", "c3_poisson", "c5_expectile", "concave_dec", "multi_penalty", "tensor_by"])
+def test_public_sparse_penalties_equal_the_dense_ones_of_the_engine(name):
+    """build_penalties / build_constraints (scipy sparse, the reference's return type, terms.py:307-396, 1479-1609,
+    1925-1979) against the dense matrices the engine uses; TensorTerm's marginal helpers sum to the term's matrix"""
+    import scipy.sparse
+
+    g = load("fit_" + name)
+    gam = helpers.build_model(cases.FIT_CASES[name])
+    gam.terms.compile(g["X"])
+    coef = np.sin(np.arange(gam.terms.n_coefs) * 1.7)
+    P = gam.terms.build_penalties()
+    C = gam.terms.build_constraints(coef, 1e9, 1e-3)
+    assert scipy.sparse.issparse(P) and scipy.sparse.issparse(C)
+    np.testing.assert_array_equal(P.toarray(), gam.terms._penalties())
+    np.testing.assert_array_equal(C.toarray(), gam.terms._constraints(coef, 1e9, 1e-3))
+    for i, t in enumerate(gam.terms):
+        sl = gam.terms.get_coef_indices(i)
+        np.testing.assert_array_equal(t.build_penalties().toarray(), t._penalties())
+        if t.kind == "tensor_term":
+            tot = sum(t._build_marginal_penalties(q).toarray() for q in range(len(t._terms)))
+            np.testing.assert_array_equal(tot, t._penalties())
+            totc = sum(t._build_marginal_constraints(q, coef[sl], 1e9, 1e-3).toarray() for q in range(len(t._terms)))
+            np.testing.assert_array_equal(totc, t._constraints(coef[sl], 1e9, 1e-3))

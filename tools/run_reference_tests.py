@@ -18,7 +18,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/pygam"
-FILES = ["test_terms.py", "test_GAM_methods.py", "test_GAMs.py", "test_gridsearch.py", "test_partial_dependence.py",
+FILES = ["test_terms.py", "test_GAM_methods.py", "test_GAMs.py", "test_gridsearch.py", "test_partial_dependence.py", "test_penalties.py",
          "test_GAM_params.py"]
 
 SHIM = '''
