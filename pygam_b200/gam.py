@@ -732,7 +732,7 @@ class GAM:
         mu = self.predict_mu(X)
         return np.sign(yh - mu) * self._deviance_rows(yh, mu, weights=wh, scaled=scaled) ** 0.5
 
-    def _estimate_r2(self, X, y, weights=None):
+    def _estimate_r2(self, X, y=None, weights=None):
         """pygam.py:1114-1154 through the O(k) statistics pass"""
         data = self._prepare_data(X, y, weights, fitting=True)
         eng = self._get_engine(data)
@@ -748,7 +748,9 @@ class GAM:
         """explained deviance on (X, y) (pygam.py:917-938)"""
         if not self._is_fitted:
             raise AttributeError("GAM has not been fitted. Call fit first.")
-        return self._estimate_r2(X, y, weights=weights)["explained_deviance"]
+        data = self._prepare_data(X, y, weights, fitting=True)
+        self._check_predict_X(data)
+        return self._estimate_r2(data)["explained_deviance"]
 
     def _dist_sample(self, mu):
         """Distribution.sample (distributions.py:187-205, 293-308, 399-412, 496-515, 599-612): host RNG"""
@@ -1049,7 +1051,10 @@ class GAM:
         return self.terms._constraints(self.coef_, self._constraint_lam, self._constraint_l2)
 
     def loglikelihood(self, X, y, weights=None):
+        """pygam.py:1059-1112: X goes through the checks of any fitted-model input (check_X: features, finite values,
+        categorical ranges), y and weights through those of a fit"""
         data = self._prepare_data(X, y, weights, fitting=True)
+        self._check_predict_X(data)
         eng = self._get_engine(data)
         sc, _, _ = eng.stats_pass(data, self.coef_)
         ybar = sc[_lib.SS_SUMY] / data.n
@@ -1069,6 +1074,8 @@ class GAM:
         data = self._prepare_data(X, y, weights, fitting=True)
         if data.y is None:
             raise ValueError("y is required")
+        if column_stats(data)[1].sum() > 0:  # check_X before any candidate is fitted (pygam.py:1935-1944); memoised for the fits
+            raise ValueError("X data must not contain Inf nor NaN")
         if objective not in ["auto", "GCV", "UBRE", "AIC", "AICc"]:
             raise ValueError("objective mut be in ['auto', 'GCV', 'UBRE', 'AIC', 'AICc'], "
                              f"but found objective = {objective}")

@@ -363,3 +363,38 @@ def test_truncated_solve_kernel_matches_numpy(m, rank):
     assert abs(a["edof"] - b["edof"]) < 1e-9 * max(1.0, abs(b["edof"]))
     assert abs(a["diff"] - b["diff"]) < 1e-9 * b["diff"]
     assert rel(a["cov"], b["cov"]) < 1e-8
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_non_finite_input_is_refused_by_every_entry_point(kind):
+    """check_X / check_y of the reference run wherever external data enters a model (pygam/tests/test_utils.py:108-173):
+    NaN in X, y or the weights raises ValueError in fit, predict, the intervals, partial dependence, residuals,
+    log-likelihood, score, grid search and sample"""
+    rng = np.random.default_rng(3)
+    n = 400
+    X = rng.uniform(0, 1, (n, 2))
+    y = np.sin(5 * X[:, 0]) + X[:, 1] + 0.1 * rng.standard_normal(n)
+    w = np.ones(n)
+    Xn, yn, wn = X.copy(), y.copy(), w.copy()
+    Xn[0, 1], yn[0], wn[0] = np.nan, np.nan, np.nan
+    with backend(kind), contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gam = pg.LinearGAM(pg.s(0, n_splines=8) + pg.s(1, n_splines=8))
+        for args in ((Xn, y, w), (X, yn, w), (X, y, wn)):
+            with pytest.raises(ValueError):
+                gam.fit(*args)
+        gam.fit(X, y)
+        for call in (gam.predict, gam.predict_mu, gam.confidence_intervals, gam.prediction_intervals):
+            with pytest.raises(ValueError):
+                call(Xn)
+        with pytest.raises(ValueError):
+            gam.partial_dependence(term=0, X=Xn)
+        for call in (gam.deviance_residuals, gam.loglikelihood, gam.score, gam.gridsearch):
+            for args in ((Xn, y, w), (X, yn, w), (X, y, wn)):
+                with pytest.raises(ValueError):
+                    call(*args)
+        with pytest.raises(ValueError):
+            gam.sample(Xn, y)
+        with pytest.raises(ValueError):
+            gam.sample(X, yn, weights=w, n_bootstraps=2)
+        assert np.isfinite(gam.loglikelihood(X, y, w)) and 0.0 < gam.score(X, y, w) <= 1.0

@@ -5,10 +5,11 @@ oracle-backed test engine (no GPU needed: what is exercised is the public API, t
 and borrows the reference's dataset loaders.  The reference's test files are read where they lie; nothing is copied into
 the repository.
 
-    python tools/run_reference_tests.py            # the six files that test the public API
+    python tools/run_reference_tests.py            # the eight files that test the public API, the penalties and the input checks
     python tools/run_reference_tests.py -k summary # extra arguments go to pytest
 
-Expected: 110 passed, 1 skipped.
+Expected: 134 passed, 1 skipped (test_core.py, test_datasets.py and test_gen_imgs.py are not run: repr helpers,
+dataset loaders and documentation images are outside the path).
 """
 import os
 import shutil
@@ -18,7 +19,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/pygam"
-FILES = ["test_terms.py", "test_GAM_methods.py", "test_GAMs.py", "test_gridsearch.py", "test_partial_dependence.py", "test_penalties.py",
+FILES = ["test_terms.py", "test_GAM_methods.py", "test_GAMs.py", "test_gridsearch.py", "test_partial_dependence.py", "test_penalties.py", "test_utils.py",
          "test_GAM_params.py"]
 
 SHIM = '''
@@ -38,16 +39,7 @@ def _alias(name, mod):
     sys.modules["pygam." + name] = mod
     globals()[name] = mod
 _alias("pygam", _gam); _alias("terms", _terms); _alias("penalties", _pen)
-_utils = types.ModuleType("pygam.utils")
-def make_2d(array, verbose=True):
-    array = np.asarray(array)
-    return np.atleast_1d(array).reshape(-1, 1) if array.ndim < 2 else array
-def flatten(it):
-    out = []
-    for el in (it if hasattr(it, "__iter__") and not isinstance(it, str) else [it]):
-        out.extend(flatten(el) if hasattr(el, "__iter__") and not isinstance(el, str) else [el])
-    return out
-_utils.make_2d, _utils.flatten = make_2d, flatten
+from pygam_b200 import utils as _utils
 _alias("utils", _utils)
 '''
 
