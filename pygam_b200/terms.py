@@ -29,6 +29,40 @@ def _aslist(v):
     return [v]
 
 
+def _term_get_params(obj, deep=False):
+    """Core.get_params (core.py:139-167) for a term: the user-facing attributes (no leading or trailing underscore)
+    minus the ones the reference hides per term kind (terms.py:535, 661, 845, 1026, 1304, 1722)"""
+    attrs = dict(obj.__dict__)
+    if deep:
+        return attrs
+    hidden = set(getattr(obj, "_hidden_params", ()))
+    return {k: v for k, v in attrs.items() if k[0] != "_" and k[-1] != "_" and k not in hidden}
+
+
+def _term_set_params(obj, deep=False, force=False, **parameters):
+    """Core.set_params (core.py:169-192)"""
+    names = _term_get_params(obj, deep=deep).keys()
+    for k, v in parameters.items():
+        if k in names or force or (hasattr(obj, k) and k == k.strip("_")):
+            setattr(obj, k, v)
+    return obj
+
+
+def _term_build_columns(obj, X, verbose=False):
+    """Term.build_columns / TermList.build_columns (terms.py:693-708, 910-957, 1077-1096, 1454-1477, 1901-1923): the
+    columns of the model matrix of this (compiled) term for the rows of X, scipy sparse like the reference's.  The
+    rows are evaluated on the device (pgb_model_matrix), the way every pass evaluates them."""
+    from .engine import DeviceData, get_backend
+
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim == 1:
+        X = X[:, None]
+    terms = obj if isinstance(obj, TermList) else TermList(obj)
+    data = DeviceData.from_host(X)
+    eng = get_backend().make_engine(terms, "normal", "identity", 1, None, data.n_features, data.device)
+    return scipy.sparse.csc_matrix(eng.model_matrix(data).cpu().numpy())
+
+
 class Term:
     """Common state of a term: feature, per-penalty ``lam``, ``penalties``, ``constraints``."""
 
@@ -151,6 +185,17 @@ class Term:
     def compile(self, X, verbose=False):
         return self
 
+    _hidden_params = ("dtype", "constraints", "by", "edge_knots")
+
+    def get_params(self, deep=False):
+        return _term_get_params(self, deep=deep)
+
+    def set_params(self, deep=False, force=False, **parameters):
+        return _term_set_params(self, deep=deep, force=force, **parameters)
+
+    def build_columns(self, X, verbose=False):
+        return _term_build_columns(self, X, verbose=verbose)
+
     # -- m x m pieces --
     def _penalty_generators(self):
         """the (callable, lam) pairs of the term, 'auto' resolved (terms.py:322-340)"""
@@ -269,6 +314,7 @@ class Intercept(Term):
     kind = "intercept_term"
     isintercept = True
     minimal_name = "intercept"
+    _hidden_params = ("by", "constraints", "dtype", "feature", "lam", "penalties", "edge_knots")
 
     def __init__(self, verbose=False):
         super().__init__(feature=None, lam=[0.0], penalties=[None], constraints=None, verbose=verbose)
@@ -303,6 +349,7 @@ class SplineTerm(Term):
     kind = "spline_term"
     minimal_name = "s"
     _bases = ["ps", "cp"]
+    _hidden_params = ("edge_knots",)
 
     def __init__(self, feature, n_splines=20, spline_order=3, lam=DEFAULT_LAM, penalties="auto",
                  constraints=None, dtype="numerical", basis="ps", by=None, edge_knots=None,
@@ -362,6 +409,7 @@ class FactorTerm(SplineTerm):
     kind = "factor_term"
     minimal_name = "f"
     _encodings = ["one-hot", "dummy"]
+    _hidden_params = ("basis", "by", "constraints", "dtype", "edge_knots", "n_splines", "spline_order")
 
     def __init__(self, feature, lam=DEFAULT_LAM, penalties="auto", coding="one-hot", verbose=False):
         self.coding = coding
@@ -394,6 +442,7 @@ class TensorTerm(Term):
     kind = "tensor_term"
     minimal_name = "te"
     istensor = True
+    _hidden_params = ("dtype", "feature", "edge_knots", "lam", "penalties", "constraints")
     _N_SPLINES = 10
 
     def __init__(self, *args, **kwargs):
@@ -596,6 +645,20 @@ def _edge_knots(X, feature, dtype, col_minmax=None):
 
 class TermList:
     """Ordered collection of unique terms (terms.py:1644-1979)."""
+
+    _hidden_params = ()
+
+    def get_params(self, deep=False):
+        return _term_get_params(self, deep=deep)
+
+    def set_params(self, deep=False, force=False, **parameters):
+        return _term_set_params(self, deep=deep, force=force, **parameters)
+
+    def build_columns(self, X, term=-1, verbose=False):
+        """terms.py:1901-1923: the model matrix of all terms, or (term >= 0) the columns of one of them"""
+        if term == -1:
+            return _term_build_columns(self, X, verbose=verbose)
+        return self._terms[term].build_columns(X, verbose=verbose)
 
     def __init__(self, *terms, **kwargs):
         self.verbose = kwargs.pop("verbose", False)

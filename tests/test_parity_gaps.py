@@ -398,3 +398,33 @@ def test_non_finite_input_is_refused_by_every_entry_point(kind):
         with pytest.raises(ValueError):
             gam.sample(X, yn, weights=w, n_bootstraps=2)
         assert np.isfinite(gam.loglikelihood(X, y, w)) and 0.0 < gam.score(X, y, w) <= 1.0
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+@pytest.mark.parametrize("name", ["c1_wage", "mixed_terms", "tensor_by"])
+def test_term_build_columns_and_params(kind, name):
+    """Term.build_columns / TermList.build_columns (terms.py:693-708, 910-957, 1077-1096, 1454-1477, 1901-1923) return
+    the scipy-sparse columns of the reference's model matrix (fixture rows); get_params / set_params of a term show
+    the parameters the reference shows (core.py:139-192 with the per-kind exclusions of terms.py)"""
+    import scipy.sparse
+
+    g = helpers.load("fit_" + name)
+    with backend(kind):
+        gam = helpers.fit_case(cases.FIT_CASES[name], g)
+        B = gam.terms.build_columns(g["X_new"])
+        assert scipy.sparse.issparse(B)
+        np.testing.assert_allclose(B.toarray(), g["modelmat_new"], rtol=0, atol=5e-13)
+        for i, t in enumerate(gam.terms):
+            cols = gam.terms.get_coef_indices(i)
+            np.testing.assert_allclose(t.build_columns(g["X_new"]).toarray(), g["modelmat_new"][:, cols], rtol=0, atol=5e-13)
+            np.testing.assert_array_equal(gam.terms.build_columns(g["X_new"], term=i).toarray(), t.build_columns(g["X_new"]).toarray())
+    shown = {"intercept_term": ["verbose"], "linear_term": ["feature", "lam", "penalties", "verbose"],
+             "spline_term": ["basis", "by", "constraints", "dtype", "feature", "lam", "n_splines", "penalties", "spline_order", "verbose"],
+             "factor_term": ["coding", "feature", "lam", "penalties", "verbose"], "tensor_term": ["by", "verbose"]}
+    for t in gam.terms:
+        assert sorted(t.get_params()) == shown[t.kind], t
+        assert "edge_knots_" in t.get_params(deep=True) or t.kind in ("intercept_term", "tensor_term")
+    assert sorted(gam.terms.get_params()) == ["verbose"]
+    t = pg.s(0)
+    assert t.set_params(n_splines=7, nonsense=1).n_splines == 7 and not hasattr(t, "nonsense")
+    assert t.set_params(force=True, nonsense=1).nonsense == 1
