@@ -83,6 +83,56 @@ def concave(n, coef):
     return _violation_penalty(n, coef, 2, False)
 
 
+# ---- the same matrices as dense numpy arrays: what the terms hand to the engine (m x m, m <= a few thousand).  Building
+# ---- them through scipy.sparse costs ~0.3 ms per call, which a small fit or a grid-search candidate would notice.
+def _differences_dense(n, order):
+    D = np.eye(n)
+    for _ in range(order):
+        D = D[:, 1:] - D[:, :-1]
+    return D
+
+
+def _derivative_dense(n, coef=None, derivative=2, periodic=False):
+    if n == 1:
+        return np.zeros((1, 1))
+    if periodic:
+        return globals()["derivative"](n, coef, derivative=derivative, periodic=True).toarray()
+    D = _differences_dense(n, derivative)
+    return D @ D.T
+
+
+def _violation_dense(n, coef, order, negative_is_violation):
+    coef = np.ravel(coef)
+    if len(coef) != n:
+        raise ValueError(f"dimension mismatch: expected n equals len(coef), but found n = {n}, "
+                         f"coef.shape = {coef.shape}.")
+    if n == 1:
+        return np.zeros((1, 1))
+    d = np.diff(coef, n=order)
+    viol = (d < 0) if negative_is_violation else (d > 0)
+    D = _differences_dense(n, order) * viol.astype(np.float64)[None, :]
+    return D @ D.T
+
+
+DENSE = {derivative: _derivative_dense,
+         periodic: lambda n, coef=None: _derivative_dense(n, coef, 2, True),
+         l2: lambda n, coef=None: np.eye(n),
+         none: lambda n, coef=None: np.zeros((n, n)),
+         monotonic_inc: lambda n, coef: _violation_dense(n, coef, 1, True),
+         monotonic_dec: lambda n, coef: _violation_dense(n, coef, 1, False),
+         convex: lambda n, coef: _violation_dense(n, coef, 2, True),
+         concave: lambda n, coef: _violation_dense(n, coef, 2, False)}
+
+
+def dense(fn, n, coef=None):
+    """the (n, n) matrix of a penalty / constraint generator as a dense array: the built-in ones directly, any other
+    callable through its own return value (dense or scipy sparse, terms.py:344-347)"""
+    if fn in DENSE:
+        return DENSE[fn](n, coef)
+    out = fn(n, coef)
+    return np.asarray(out.toarray() if hasattr(out, "toarray") else out, dtype=np.float64)
+
+
 def wrap_penalty(p, fit_linear, linear_penalty=0.0):
     """penalties.py:279-309: a penalty generator whose first coefficient (the linear term of the feature) gets
     ``linear_penalty`` and whose other n - 1 coefficients get ``p``"""

@@ -250,7 +250,7 @@ class Term:
         total = np.zeros((n, n))
         parts = []
         for fn, lam in self._penalty_generators():
-            comp = np.multiply(np.asarray(_dense(fn(n, None)), dtype=np.float64), lam)
+            comp = np.multiply(_pen.dense(fn, n, None), lam)
             total = total + comp
             parts.append(comp)
         return split_by_constant(parts, n) if split else total
@@ -267,7 +267,7 @@ class Term:
             if c is None:
                 c = "none"
             fn = _pen.CONSTRAINTS[c] if isinstance(c, str) else c
-            comp = np.asarray(_dense(fn(n, coef)), dtype=np.float64) * constraint_lam
+            comp = _pen.dense(fn, n, coef) * constraint_lam
             total = total + comp
             parts.append(comp)
         if np.count_nonzero(total) > 0:
