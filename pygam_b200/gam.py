@@ -43,16 +43,16 @@ class Distribution:
         self.scale = 1.0 if name in ("binomial", "poisson") else scale
         self.levels = 1 if levels is None else levels
 
-    def __repr__(self):
-        return f"{self.name}(scale={self.scale})"
+    def __repr__(self):  # as an unfitted reference GAM shows its distribution argument
+        return repr(self.name)
 
 
 class Link:
     def __init__(self, name):
         self.name = name
 
-    def __repr__(self):
-        return self.name
+    def __repr__(self):  # as an unfitted reference GAM shows its link argument
+        return repr(self.name)
 
 
 DISTRIBUTIONS = ("normal", "poisson", "binomial", "gamma", "inv_gauss")
@@ -155,6 +155,12 @@ class GAM:
 
     # ---- parameters ----
     _param_names = ("max_iter", "tol", "callbacks", "fit_intercept", "verbose", "terms")
+
+    def __repr__(self):
+        """Core.__repr__ (core.py:128-138): the class name and the user-facing parameters, wrapped at 70 columns"""
+        from .utils import nice_repr
+
+        return nice_repr(self.__class__.__name__, self.get_params(), line_width=70, line_offset=3, decimals=4)
 
     def get_params(self, deep=False):
         names = list(self._param_names)

@@ -1,7 +1,8 @@
 """Host-side input validation helpers with the names and behaviour of the reference's ``pygam/utils.py``.
 
 ``check_array`` (utils.py:118-201), ``check_y`` (204-248), ``check_X`` (251-336), ``check_X_y`` (339-355),
-``check_iterable_depth`` (866-896), ``make_2d`` (96-115), ``flatten`` (846-863), ``sig_code`` (569-590).  They validate
+``check_iterable_depth`` (866-896), ``make_2d`` (96-115), ``flatten`` (846-863), ``sig_code`` (569-590),
+``round_to_n_decimal_places`` (470-495) and ``nice_repr`` (core.py:7-92).  They validate
 HOST arrays a caller is about to hand to a model (type, shape, sample count, finiteness, link domain, categorical
 range); the models run the same checks on the device once the rows are in HBM (``GAM._prepare_data``, ``_check_y``,
 ``_check_predict_X``).  No n-sized arithmetic of a fit goes through this module.
@@ -109,13 +110,46 @@ def check_iterable_depth(obj, max_depth=100):
 
 
 def flatten(iterable):
-    """utils.py:846-863"""
+    """utils.py:866-896: nested iterables become one flat list; anything else is returned as it is"""
     if not (hasattr(iterable, "__iter__") and not isinstance(iterable, str)):
-        return [iterable]
+        return iterable
     out = []
-    for el in iterable:
-        out.extend(flatten(el))
+    for el in list(iterable):
+        el = flatten(el)
+        out.extend(el if isinstance(el, list) else [el])
     return out
+
+
+def round_to_n_decimal_places(array, n=3):
+    """utils.py:470-495: floats rounded to n decimals for printing; a float whose str() is already of the form 1e-05
+    is left alone"""
+    if isinstance(array, float) and "%.e" % array == str(array):
+        return array
+    shape = np.shape(array)
+    return ((np.atleast_1d(array) * 10 ** n).round().astype("int") / (10.0 ** n)).reshape(shape)
+
+
+def nice_repr(name, param_kvs, line_width=30, line_offset=5, decimals=3, args=None, flatten_attrs=True):
+    """core.py:7-92: ``name(key=value, ...)`` with the keys in alphabetical order, floats rounded, and a new line
+    (indented by line_offset) whenever the next ``key=value,`` would pass line_width"""
+    if not param_kvs and not args:
+        return f"{name}()"
+    items = [(None, a) for a in (args or [])] + sorted(param_kvs.items(), key=lambda kv: kv[0])
+    lines, line = [], name + "("
+    for pos, (k, v) in enumerate(items):
+        if flatten_attrs and k != "terms":
+            v = flatten(v)
+        text = str(round_to_n_decimal_places(v, n=decimals)) if isinstance(v, (float, np.ndarray)) else repr(v)
+        piece = f"{text}," if k is None else f"{k}={text},"
+        if len(line + piece) <= line_width:
+            line += piece
+        else:
+            lines.append(line)
+            line = " " * line_offset + piece
+        if len(line) < line_width and pos + 1 < len(items):
+            line += " "
+    lines.append(line[:-1] + ")")  # without the trailing comma
+    return "\n".join(lines)
 
 
 def sig_code(p_value):

@@ -150,3 +150,20 @@ def test_public_sparse_penalties_equal_the_dense_ones_of_the_engine(name):
             np.testing.assert_array_equal(tot, t._penalties())
             totc = sum(t._build_marginal_constraints(q, coef[sl], 1e9, 1e-3).toarray() for q in range(len(t._terms)))
             np.testing.assert_array_equal(totc, t._constraints(coef[sl], 1e9, 1e-3))
+
+
+def test_model_repr_follows_the_reference_format():
+    """Core.__repr__ / nice_repr (core.py:7-138): class name, the user-facing parameters in alphabetical order, floats
+    rounded to four decimals, wrapped at 70 columns with a three-space indent (strings recorded from pyGAM 0.12.0)"""
+    from pygam_b200.utils import nice_repr
+
+    g = pg.LinearGAM(pg.s(0, n_splines=7) + pg.te(1, 2) + pg.f(3), lam=0.5)
+    assert repr(g) == ("LinearGAM(callbacks=['deviance', 'diffs'], fit_intercept=True, \n"
+                       "   lam=0.5, max_iter=100, scale=None, terms=s(0) + te(1, 2) + f(3), \n"
+                       "   tol=0.0001, verbose=False)")
+    assert repr(pg.LogisticGAM()) == ("LogisticGAM(callbacks=['deviance', 'diffs', 'accuracy'], \n"
+                                      "   fit_intercept=True, max_iter=100, terms='auto', tol=0.0001, \n"
+                                      "   verbose=False)")
+    assert nice_repr("hi", {}, line_width=30, line_offset=5, decimals=3) == "hi()"
+    assert nice_repr("hi", {"color": "blue", "n_ears": 3, "height": 1.3336}, line_width=60, line_offset=5,
+                     decimals=3) == "hi(color='blue', height=1.334, n_ears=3)"

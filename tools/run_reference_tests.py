@@ -5,11 +5,11 @@ oracle-backed test engine (no GPU needed: what is exercised is the public API, t
 and borrows the reference's dataset loaders.  The reference's test files are read where they lie; nothing is copied into
 the repository.
 
-    python tools/run_reference_tests.py            # the eight files that test the public API, the penalties and the input checks
+    python tools/run_reference_tests.py            # the nine files that test the public API, the penalties, the input checks and the repr helpers
     python tools/run_reference_tests.py -k summary # extra arguments go to pytest
 
-Expected: 134 passed, 1 skipped (test_core.py, test_datasets.py and test_gen_imgs.py are not run: repr helpers,
-dataset loaders and documentation images are outside the path).
+Expected: 137 passed, 1 skipped (test_datasets.py and test_gen_imgs.py are not run: dataset loaders and
+documentation images are outside the path).
 """
 import os
 import shutil
@@ -19,7 +19,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/pygam"
-FILES = ["test_terms.py", "test_GAM_methods.py", "test_GAMs.py", "test_gridsearch.py", "test_partial_dependence.py", "test_penalties.py", "test_utils.py",
+FILES = ["test_terms.py", "test_GAM_methods.py", "test_GAMs.py", "test_gridsearch.py", "test_partial_dependence.py", "test_penalties.py", "test_utils.py", "test_core.py",
          "test_GAM_params.py"]
 
 SHIM = '''
@@ -39,8 +39,8 @@ def _alias(name, mod):
     sys.modules["pygam." + name] = mod
     globals()[name] = mod
 _alias("pygam", _gam); _alias("terms", _terms); _alias("penalties", _pen)
-from pygam_b200 import utils as _utils
-_alias("utils", _utils)
+from pygam_b200 import utils as _utils, core as _core
+_alias("utils", _utils); _alias("core", _core)
 '''
 
 
