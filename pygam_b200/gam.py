@@ -34,8 +34,17 @@ class OptimizationError(ValueError):
     """pygam/utils.py:26-27"""
 
 
-# host-side stand-ins for the reference's Distribution / Link objects (only built-ins have
-# CUDA implementations; custom Python objects raise NotImplementedError)
+# Host-side Distribution / Link objects with the reference's methods (distributions.py, links.py) for the small
+# arrays a caller handles himself -- gam.distribution.V(mu), gam.link.mu(lp, dist), sampling; the n-sized link,
+# variance, deviance and log-likelihood work of a fit or a predict runs in the kernels (pgb_device.cuh), selected by
+# `name`.  Only the built-in families have CUDA implementations: custom Python objects raise NotImplementedError.
+# pygam_b200.distributions / pygam_b200.links hold the reference's class names (NormalDist, LogitLink, ...).
+def _ylogydu(a, u):
+    """utils.py:773-789: y log(y / u), 0 where y == 0"""
+    with np.errstate(all="ignore"):
+        return np.where(a != 0, a * np.log(np.where(a != 0, a, 1.0) / u), 0.0)
+
+
 class Distribution:
     def __init__(self, name, scale=None, levels=1):
         self.name = name
@@ -46,6 +55,70 @@ class Distribution:
     def __repr__(self):  # as an unfitted reference GAM shows its distribution argument
         return repr(self.name)
 
+    def V(self, mu, weights=None):
+        """variance function over the weights (distributions.py:134-160, 250-265, 355-370, 452-467, 555-570, 23-30)"""
+        mu = np.asarray(mu, dtype=np.float64)
+        v = {"normal": lambda: np.ones_like(mu), "binomial": lambda: mu * (1 - mu / self.levels), "poisson": lambda: mu,
+             "gamma": lambda: mu ** 2}.get(self.name, lambda: mu ** 3)()
+        return v if weights is None else v / np.asarray(weights)
+
+    def deviance(self, y, mu, scaled=True, weights=None):
+        """deviance of every row (distributions.py:162-185, 267-291, 372-397, 469-494, 572-597, decorator 13-20)"""
+        name, lv = self.name, float(self.levels)
+        y, mu = np.asarray(y, dtype=np.float64), np.asarray(mu, dtype=np.float64)
+        with np.errstate(all="ignore"):
+            if name == "normal":
+                dev = (y - mu) ** 2
+            elif name == "binomial":
+                dev = 2 * (_ylogydu(y, mu) + _ylogydu(lv - y, lv - mu))
+            elif name == "poisson":
+                dev = 2 * (_ylogydu(y, mu) - (y - mu))
+            elif name == "gamma":
+                dev = 2 * ((y - mu) / mu - np.log(y / mu))
+            else:
+                dev = ((y - mu) ** 2) / (mu ** 2 * y)
+        if scaled and self.scale:
+            dev = dev / (self.scale ** 2 if name == "normal" else self.scale)
+        if weights is not None:
+            dev = dev * np.asarray(weights)
+        return dev
+
+    def log_pdf(self, y, mu, weights=None):
+        """log of the pdf / pmf as scipy.stats evaluates it (distributions.py:110-131, 225-247, 323-352, 428-449, 531-552)"""
+        y, mu = np.asarray(y, dtype=np.float64), np.asarray(mu, dtype=np.float64)
+        w = np.ones_like(mu) if weights is None else np.asarray(weights, dtype=np.float64)
+        if self.name == "normal":
+            return scipy.stats.norm.logpdf(y, loc=mu, scale=self.scale / w)
+        if self.name == "binomial":
+            return scipy.stats.binom.logpmf(y, self.levels, mu / self.levels)
+        if self.name == "poisson":
+            return scipy.stats.poisson.logpmf(y, mu=mu * w)
+        if self.name == "gamma":
+            nu = w / self.scale
+            return scipy.stats.gamma.logpdf(x=y, a=nu, scale=mu / nu)
+        return scipy.stats.invgauss.logpdf(y, mu, scale=self.scale / w)
+
+    def phi(self, y, mu, edof, weights):
+        """the scale: known, or the Pearson estimate (distributions.py:53-78)"""
+        if self._known_scale:
+            return self.scale ** 2
+        y, mu = np.asarray(y, dtype=np.float64), np.asarray(mu, dtype=np.float64)
+        return np.sum(np.asarray(weights) * self.V(mu) ** -1 * (y - mu) ** 2) / (len(mu) - edof)
+
+    def sample(self, mu):
+        """random draws with expectation mu (distributions.py:187-205, 293-308, 399-412, 496-515, 599-612): host RNG"""
+        name, scale = self.name, self.scale
+        if name == "normal":
+            return np.random.normal(loc=mu, scale=scale if scale else 1.0, size=None)
+        if name == "binomial":
+            return np.random.binomial(n=self.levels, p=mu / self.levels, size=None)
+        if name == "poisson":
+            return np.random.poisson(lam=mu, size=None)
+        if name == "gamma":
+            shape = 1.0 / scale
+            return np.random.gamma(shape=shape, scale=mu / shape, size=None)
+        return np.random.wald(mean=mu, scale=scale, size=None)
+
 
 class Link:
     def __init__(self, name):
@@ -53,6 +126,35 @@ class Link:
 
     def __repr__(self):  # as an unfitted reference GAM shows its link argument
         return repr(self.name)
+
+    def link(self, mu, dist):
+        """g(mu) (links.py:32-46, 91-105, 151-165, 210-224, 269-283)"""
+        mu = np.asarray(mu, dtype=np.float64)
+        with np.errstate(all="ignore"):
+            return {"identity": lambda: mu, "logit": lambda: np.log(mu) - np.log(dist.levels - mu), "log": lambda: np.log(mu),
+                    "inverse": lambda: mu ** -1.0}.get(self.name, lambda: mu ** -2.0)()
+
+    def mu(self, lp, dist):
+        """g^-1(lp) (links.py:48-62, 107-122, 167-181, 226-240, 285-299)"""
+        lp = np.asarray(lp, dtype=np.float64)
+        with np.errstate(all="ignore"):
+            if self.name == "identity":
+                return lp
+            if self.name == "logit":
+                e = np.exp(lp)
+                return float(dist.levels) * e / (e + 1.0)
+            if self.name == "log":
+                return np.exp(lp)
+            if self.name == "inverse":
+                return lp ** -1.0
+            return lp ** -0.5
+
+    def gradient(self, mu, dist):
+        """g'(mu) (links.py:64-77, 124-137, 183-196, 242-255, 301-314)"""
+        mu = np.asarray(mu, dtype=np.float64)
+        with np.errstate(all="ignore"):
+            return {"identity": lambda: np.ones_like(mu), "logit": lambda: dist.levels / (mu * (dist.levels - mu)),
+                    "log": lambda: 1.0 / mu, "inverse": lambda: -1 * mu ** -2.0}.get(self.name, lambda: -2 * mu ** -3.0)()
 
 
 DISTRIBUTIONS = ("normal", "poisson", "binomial", "gamma", "inv_gauss")
@@ -702,31 +804,8 @@ class GAM:
                       stacklevel=2)
 
     def _deviance_rows(self, y, mu, weights=None, scaled=True):
-        """Distribution.deviance (distributions.py:162-185, 267-291, 372-397, 469-494, 572-597 and the decorators
-        13-30) on host arrays"""
-        name, lv = self.distribution.name, float(self.distribution.levels)
-        y, mu = np.asarray(y, dtype=np.float64), np.asarray(mu, dtype=np.float64)
-
-        def ylogydu(a, u):
-            with np.errstate(all="ignore"):
-                return np.where(a != 0, a * np.log(np.where(a != 0, a, 1.0) / u), 0.0)
-
-        with np.errstate(all="ignore"):
-            if name == "normal":
-                dev = (y - mu) ** 2
-            elif name == "binomial":
-                dev = 2 * (ylogydu(y, mu) + ylogydu(lv - y, lv - mu))
-            elif name == "poisson":
-                dev = 2 * (ylogydu(y, mu) - (y - mu))
-            elif name == "gamma":
-                dev = 2 * ((y - mu) / mu - np.log(y / mu))
-            else:
-                dev = ((y - mu) ** 2) / (mu ** 2 * y)
-        if scaled and self.distribution.scale:
-            dev = dev / (self.distribution.scale ** 2 if name == "normal" else self.distribution.scale)
-        if weights is not None:
-            dev = dev * np.asarray(weights)
-        return dev
+        """Distribution.deviance on host arrays"""
+        return self.distribution.deviance(y, mu, scaled=scaled, weights=weights)
 
     def deviance_residuals(self, X, y, weights=None, scaled=False):
         """pygam.py:940-991: sign(y - mu) sqrt(deviance row); mu on the device, the n-sized result on the host"""
@@ -759,19 +838,7 @@ class GAM:
         return self._estimate_r2(data)["explained_deviance"]
 
     def _dist_sample(self, mu):
-        """Distribution.sample (distributions.py:187-205, 293-308, 399-412, 496-515, 599-612): host RNG"""
-        name, scale = self.distribution.name, self.distribution.scale
-        if name == "normal":
-            return np.random.normal(loc=mu, scale=scale if scale else 1.0, size=None)
-        if name == "binomial":
-            lv = self.distribution.levels
-            return np.random.binomial(n=lv, p=mu / lv, size=None)
-        if name == "poisson":
-            return np.random.poisson(lam=mu, size=None)
-        if name == "gamma":
-            shape = 1.0 / scale
-            return np.random.gamma(shape=shape, scale=mu / shape, size=None)
-        return np.random.wald(mean=mu, scale=scale, size=None)
+        return self.distribution.sample(mu)
 
     def sample(self, X, y, quantity="y", sample_at_X=None, weights=None, n_draws=100, n_bootstraps=5, objective="auto"):
         """Simulate from the posterior of the coefficients and smoothing parameters (pygam.py:2087-2210): bootstrap
@@ -914,18 +981,7 @@ class GAM:
     # ---- intervals and partial dependence ----
     def _link_mu(self, lp):
         """Link.mu on host arrays (links.py:32-314), for the small interval outputs"""
-        name, lv = self.link.name, float(self.distribution.levels)
-        with np.errstate(all="ignore"):
-            if name == "identity":
-                return lp
-            if name == "logit":
-                e = np.exp(lp)
-                return lv * e / (e + 1.0)
-            if name == "log":
-                return np.exp(lp)
-            if name == "inverse":
-                return lp ** -1.0
-            return lp ** -0.5
+        return self.link.mu(lp, self.distribution)
 
     def _term_index(self, term):
         return term if term >= 0 else len(self.terms) + term

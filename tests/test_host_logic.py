@@ -167,3 +167,32 @@ def test_model_repr_follows_the_reference_format():
     assert nice_repr("hi", {}, line_width=30, line_offset=5, decimals=3) == "hi()"
     assert nice_repr("hi", {"color": "blue", "n_ears": 3, "height": 1.3336}, line_width=60, line_offset=5,
                      decimals=3) == "hi(color='blue', height=1.334, n_ears=3)"
+
+
+def test_distribution_and_link_objects_by_the_reference_names():
+    """pygam_b200.distributions / pygam_b200.links (distributions.py:97-621, links.py:21-323): the named classes
+    configure a GAM like the strings do and carry the reference's host-side methods (closed forms checked here; all of
+    them were compared with the reference's classes on random inputs when they were written)"""
+    import scipy.stats
+
+    from pygam_b200.distributions import DISTRIBUTIONS, BinomialDist, GammaDist, NormalDist, PoissonDist
+    from pygam_b200.links import LINKS, LogitLink, LogLink
+
+    assert sorted(DISTRIBUTIONS) == ["binomial", "gamma", "inv_gauss", "normal", "poisson"]
+    assert sorted(LINKS) == ["identity", "inv_squared", "inverse", "log", "logit"]
+    mu, y, w = np.array([0.5, 1.5, 2.0]), np.array([1.0, 1.0, 3.0]), np.array([1.0, 2.0, 0.5])
+    d = BinomialDist(levels=3)
+    np.testing.assert_allclose(d.V(mu), mu * (1 - mu / 3))
+    np.testing.assert_allclose(d.V(mu, weights=w), mu * (1 - mu / 3) / w)
+    np.testing.assert_allclose(d.log_pdf(y, mu), scipy.stats.binom.logpmf(y, 3, mu / 3))
+    np.testing.assert_allclose(LogitLink().mu(LogitLink().link(mu, d), d), mu)
+    np.testing.assert_allclose(LogitLink().gradient(mu, d), 3 / (mu * (3 - mu)))
+    n = NormalDist(scale=2.0)
+    np.testing.assert_allclose(n.deviance(y, mu), (y - mu) ** 2 / 4.0)
+    np.testing.assert_allclose(n.deviance(y, mu, scaled=False, weights=w), (y - mu) ** 2 * w)
+    assert n.phi(y, mu, 1.0, w) == 4.0 and not GammaDist()._known_scale
+    np.testing.assert_allclose(PoissonDist().log_pdf(y, mu, weights=w), scipy.stats.poisson.logpmf(y, mu * w))
+    g1 = pg.GAM(pg.s(0), distribution=GammaDist(), link=LogLink())
+    g2 = pg.GAM(pg.s(0), distribution="gamma", link="log")
+    assert (g1.distribution.name, g1.link.name) == (g2.distribution.name, g2.link.name) == ("gamma", "log")
+    assert pg.LogisticGAM().distribution.V(np.array([0.25]))[0] == 0.1875
