@@ -19,6 +19,7 @@ import scipy.stats
 import torch
 
 from . import _lib
+from .callbacks import builtin_name
 from .engine import (DeviceData, all_gather_rows, all_reduce_, column_stats, count_levels, descriptor_key,
                      get_backend, single_rank, vector_range, world)
 from .terms import FactorTerm, Intercept, SplineTerm, Term, TermList
@@ -348,6 +349,8 @@ class GAM:
             self.link = Link(self.link)
         elif not isinstance(self.link, Link):
             raise NotImplementedError("custom Link objects have no CUDA implementation")
+        # Deviance() / Diffs() / Accuracy() / Coef() objects (pygam_b200.callbacks) are the built-ins by another name
+        self.callbacks = [builtin_name(c) or c for c in self.callbacks]
         for c in self.callbacks:
             if not (isinstance(c, str) and c in CALLBACKS):
                 raise NotImplementedError(

@@ -196,3 +196,21 @@ def test_distribution_and_link_objects_by_the_reference_names():
     g2 = pg.GAM(pg.s(0), distribution="gamma", link="log")
     assert (g1.distribution.name, g1.link.name) == (g2.distribution.name, g2.link.name) == ("gamma", "log")
     assert pg.LogisticGAM().distribution.V(np.array([0.25]))[0] == 0.1875
+
+
+def test_callback_objects_by_the_reference_names():
+    """pygam_b200.callbacks (callbacks.py:98-236): the four built-in classes are accepted like their names; any other
+    CallBack is refused (it would need the n-sized y / mu of every iteration on the host)"""
+    from pygam_b200.callbacks import CALLBACKS, Accuracy, CallBack, Coef, Deviance, Diffs
+
+    assert sorted(CALLBACKS) == ["accuracy", "coef", "deviance", "diffs"] and str(Deviance()) == "deviance"
+    g = pg.LogisticGAM(pg.s(0), callbacks=[Deviance(), Diffs(), Accuracy(), Coef()])
+    g._validate_params()
+    assert g.callbacks == ["deviance", "diffs", "accuracy", "coef"]
+
+    class Mine(CallBack):
+        def on_loop_start(self, y, mu):
+            return 0
+
+    with pytest.raises(NotImplementedError):
+        pg.LinearGAM(pg.s(0), callbacks=[Mine(name="mine")])._validate_params()
