@@ -24,6 +24,7 @@ namespace {
 
 const int kMaxWorkers = 16;
 const size_t kStageBytes = 4u << 20;  // per buffer; two per worker
+const size_t kMaxPitch = 2147483647;   // cudaDeviceProp::memPitch on every current device
 
 struct Worker {
   int device = -1;
@@ -142,8 +143,14 @@ extern "C" int pgb_upload_rows(double* dst, int64_t ld, const double* src, int64
       const int64_t r0 = b * rows, nr = std::min(rows, n - r0);
       if (used[q] && (e = cudaEventSynchronize(w.done[q])) != cudaSuccess) break;
       transpose_block(src + r0 * F, F, nr, w.buf[q]);
-      e = cudaMemcpy2DAsync(dst + r0, (size_t)ld * sizeof(double), w.buf[q], (size_t)nr * sizeof(double),
-                            (size_t)nr * sizeof(double), (size_t)F, cudaMemcpyHostToDevice, w.stream);
+      if ((size_t)ld * sizeof(double) <= kMaxPitch) {
+        e = cudaMemcpy2DAsync(dst + r0, (size_t)ld * sizeof(double), w.buf[q], (size_t)nr * sizeof(double),
+                              (size_t)nr * sizeof(double), (size_t)F, cudaMemcpyHostToDevice, w.stream);
+      } else {  // columns further apart than the largest pitch of a strided copy (> 2.6e8 rows): one copy per column
+        for (int64_t j = 0; j < F && e == cudaSuccess; ++j)
+          e = cudaMemcpyAsync(dst + j * ld + r0, w.buf[q] + j * nr, (size_t)nr * sizeof(double), cudaMemcpyHostToDevice,
+                              w.stream);
+      }
       if (e == cudaSuccess) e = cudaEventRecord(w.done[q], w.stream);
       used[q] = true;
     }
